@@ -1,0 +1,183 @@
+"""Host-side engine: owns one bpc_handle (one per device / stream) and moves torch / numpy buffers across the C ABI.
+
+PyTorch is used for device memory and streams only; every computation happens inside libbpc_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _check(handle, rc, what):
+    if rc != 0:
+        msg = L.lib().bpc_last_error(handle)
+        raise L.BpcError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+class Engine:
+    """One B200, one handle.  `precompute` (device tensors), `precompute_host` (host arrays), `stage_logmel`."""
+
+    def __init__(self, device: int = 0, max_batch: int = 4096, params: L.Params | None = None, debug: bool = False):
+        self._lib = L.lib()
+        self.params = params if params is not None else L.default_params()
+        self._h = C.c_void_p()
+        rc = self._lib.bpc_create(C.byref(self._h), C.byref(self.params), int(device), int(max_batch))
+        if rc != 0:
+            msg = self._lib.bpc_last_error(None)
+            raise L.BpcError(f"bpc_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.device = int(device)
+        self.T = self._lib.bpc_num_frames(C.byref(self.params))
+        self.nscal = self._lib.bpc_num_scalars(C.byref(self.params))
+        self.L = int(self.params.expected_len)
+        if debug:
+            self.set_debug(True)
+
+    # ------------------------------------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.bpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_debug(self, on: bool):
+        _check(self._h, self._lib.bpc_set_debug(self._h, int(bool(on))), "bpc_set_debug")
+
+    # ------------------------------------------------------------------------------------------- device tensors
+    @staticmethod
+    def _wav_dtype(t):
+        import torch
+        if t.dtype == torch.float32:
+            return L.WAV_F32
+        if t.dtype == torch.int16:
+            return L.WAV_PCM16
+        raise TypeError("wav must be float32 or int16")
+
+    def precompute(self, wav, feats=None, scalars=None, status=None, stream=None):
+        """wav: cuda tensor [B, L_in] float32 / int16 -> (feats [B,9,128,T], scalars [B,S], status [B]) on device."""
+        import torch
+        if not wav.is_cuda or wav.dim() != 2:
+            raise ValueError("wav must be a 2-D CUDA tensor; host arrays go through precompute_host")
+        wav = wav.contiguous()
+        B, L_in = wav.shape
+        dev = wav.device
+        if feats is None:
+            feats = torch.empty((B, L.NUM_CHANNELS, L.PLANE_ROWS, self.T), dtype=torch.float32, device=dev)
+        if scalars is None:
+            scalars = torch.empty((B, self.nscal), dtype=torch.float32, device=dev)
+        if status is None:
+            status = torch.empty((B,), dtype=torch.int32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
+        rc = self._lib.bpc_precompute(self._h, wav.data_ptr(), self._wav_dtype(wav), B, L_in, feats.data_ptr(),
+                                      scalars.data_ptr(), status.data_ptr(), C.c_void_p(st))
+        _check(self._h, rc, "bpc_precompute")
+        return feats, scalars, status
+
+    def stage_logmel(self, wav, want_stft=True, stream=None):
+        """BASELINE config 2: (stft_db [B,257,T] or None, mel3 [B,3,128,T])."""
+        import torch
+        wav = wav.contiguous()
+        B, L_in = wav.shape
+        dev = wav.device
+        stft = torch.empty((B, 257, self.T), dtype=torch.float32, device=dev) if want_stft else None
+        mel3 = torch.empty((B, 3, L.PLANE_ROWS, self.T), dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
+        rc = self._lib.bpc_stage_logmel(self._h, wav.data_ptr(), self._wav_dtype(wav), B, L_in,
+                                        stft.data_ptr() if want_stft else None, mel3.data_ptr(), C.c_void_p(st))
+        _check(self._h, rc, "bpc_stage_logmel")
+        return stft, mel3
+
+    # ---------------------------------------------------------------------------------------------- host arrays
+    def precompute_host(self, wav: np.ndarray, feats=None, scalars=None, status=None):
+        """wav: numpy [B, L_in] float32 / int16 (pageable or pinned) -> numpy (feats, scalars, status)."""
+        wav = np.ascontiguousarray(wav)
+        if wav.ndim != 2:
+            raise ValueError("wav must be [B, L_in]")
+        if wav.dtype == np.float32:
+            dt = L.WAV_F32
+        elif wav.dtype == np.int16:
+            dt = L.WAV_PCM16
+        else:
+            raise TypeError("wav must be float32 or int16")
+        B, L_in = wav.shape
+        if feats is None:
+            feats = np.empty((B, L.NUM_CHANNELS, L.PLANE_ROWS, self.T), dtype=np.float32)
+        if scalars is None:
+            scalars = np.empty((B, self.nscal), dtype=np.float32)
+        if status is None:
+            status = np.empty((B,), dtype=np.int32)
+        rc = self._lib.bpc_precompute_host(self._h, wav.ctypes.data, dt, B, L_in, feats.ctypes.data,
+                                           scalars.ctypes.data, status.ctypes.data)
+        _check(self._h, rc, "bpc_precompute_host")
+        return feats, scalars, status
+
+    # ------------------------------------------------------------------------------------------------ statistics
+    def channel_stats(self) -> np.ndarray:
+        out = np.empty((9 + self.nscal, 5), dtype=np.float64)
+        _check(self._h, self._lib.bpc_channel_stats(self._h, out.ctypes.data), "bpc_channel_stats")
+        return out
+
+    def channel_stats_device(self):
+        """torch float64 view [(9+S), 5] of the device accumulator (for an NCCL all-reduce)."""
+        import torch
+        ptr = C.c_void_p()
+        rows = C.c_int64()
+        _check(self._h, self._lib.bpc_channel_stats_device(self._h, C.byref(ptr), C.byref(rows)), "stats_device")
+        n = rows.value * 5
+
+        class _Iface:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr.value, False), "version": 2}
+        return torch.as_tensor(_Iface(), device=f"cuda:{self.device}").view(rows.value, 5)
+
+    def reset_stats(self):
+        _check(self._h, self._lib.bpc_channel_stats_reset(self._h), "bpc_channel_stats_reset")
+
+    def launch_count(self) -> int:
+        return int(self._lib.bpc_launch_count(self._h))
+
+    # ----------------------------------------------------------------------------------------------------- debug
+    _DEBUG_SHAPES = {
+        "mag512": lambda s: ((s.T, 260), np.float32), "mel_db": lambda s: ((128, s.T), np.float32),
+        "mfcc_raw": lambda s: ((120, s.T), np.float32), "gammatone_raw": lambda s: ((64, s.T), np.float32),
+        "mod_spec_raw": lambda s: ((40, s.T), np.float32), "chroma_stft_raw": lambda s: ((12, s.T), np.float32),
+        "chroma_cens_raw": lambda s: ((12, s.T), np.float32),
+        "lpc_raw": lambda s: ((12, (s.L - 400 + 159) // 160), np.float32),
+        "onset_env": lambda s: ((s.T,), np.float32), "tuning": lambda s: ((2,), np.int32),
+        "ints": lambda s: ((2,), np.int32),
+    }
+
+    def debug(self, what: str, n: int) -> np.ndarray:
+        """Raw intermediate `what` of the first n segments of the last chunk (needs set_debug(True) before the call)."""
+        shape, dt = self._DEBUG_SHAPES[what](self)
+        out = np.empty((n,) + shape, dtype=dt)
+        got = C.c_int64()
+        rc = self._lib.bpc_debug_copy(self._h, what.encode(), out.ctypes.data, out.nbytes, C.byref(got))
+        _check(self._h, rc, "bpc_debug_copy")
+        if got.value != out.nbytes:
+            raise L.BpcError(f"debug {what}: wanted {out.nbytes} bytes, got {got.value}")
+        return out
+
+
+def table(name: str, tuning_idx: int = 50, params: L.Params | None = None) -> np.ndarray:
+    """Host-side constant table by name (no GPU needed); see include/bpc.h::bpc_table_copy."""
+    p = params if params is not None else L.default_params()
+    T = p.expected_len // p.hop + 1
+    shapes = {"mel_a": ((128, 257), np.float32), "mel_b": ((128, 257), np.float32), "mel_c": ((64, 257), np.float32),
+              "mel_d": ((128, 1025), np.float32), "dct_mel": ((40, 128), np.float32), "dct_time": ((T, T), np.float32),
+              "hann512": ((512,), np.float64), "hann2048": ((2048,), np.float64), "hann384": ((384,), np.float64),
+              "hamming400": ((400,), np.float64), "chroma": ((12, 257), np.float32),
+              "hist_edges": ((101,), np.float64), "halfband": ((127,), np.float64),
+              "cqt_basis": ((36, 257, 2), np.float32), "cqt_sqrt_len": ((252,), np.float64)}
+    shape, dt = shapes[name]
+    out = np.empty(shape, dtype=dt)
+    n = L.lib().bpc_table_copy(C.byref(p), name.encode(), int(tuning_idx), out.ctypes.data, out.size)
+    if n != out.size:
+        raise L.BpcError(f"bpc_table_copy({name}) returned {n}, expected {out.size}")
+    return out

@@ -1,0 +1,576 @@
+// C ABI of libbpc_b200.so (include/bpc.h): handle, constant tables, workspaces, chunked launch sequence, the
+// host-buffer (pinned-staged, double-buffered) path, dataset statistics and debug accessors.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bpc.h"
+#include "kernels.cuh"
+#include "tables.hpp"
+
+using namespace bpc;
+
+namespace {
+
+thread_local std::string g_create_error;
+const double kPi = 3.141592653589793238462643383279502884;
+
+struct Slot {                      // one in-flight chunk of the host-buffer path
+    void* d_wav = nullptr;         // [chunk, L_in_max] raw input (f32 or pcm16)
+    float* d_feats = nullptr;
+    float* d_scalars = nullptr;
+    int32_t* d_status = nullptr;
+    void* h_wav = nullptr;         // pinned staging
+    float* h_feats = nullptr;
+    float* h_scalars = nullptr;
+    int32_t* h_status = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+};
+
+}  // namespace
+
+struct bpc_handle {
+    bpc_params p{};
+    Geometry g{};
+    int device = 0;
+    int64_t max_batch = 0;
+    int chunk = 0;
+    Tables tb{};
+    Workspace ws{};
+    Workspace ws_dbg{};            // same workspace with the debug pointers populated
+    bool debug = false;
+    double* stats_acc = nullptr;   // [(9 + nscal), 5]
+    std::vector<void*> dev_allocs;
+    std::vector<void*> host_allocs;
+    Slot slot[2];
+    bool slots_ready = false;
+    size_t slot_wav_bytes = 0;
+    int last_n = 0;
+    int64_t launches0 = 0;
+    std::string err;
+};
+
+namespace {
+
+#define BPC_CUDA(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                        \
+            return BPC_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+template <typename T>
+int upload(bpc_handle* h, const std::vector<T>& v, const T** out) {
+    void* d = nullptr;
+    BPC_CUDA(h, cudaMalloc(&d, std::max<size_t>(16, v.size() * sizeof(T))));
+    h->dev_allocs.push_back(d);
+    BPC_CUDA(h, cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const T*>(d);
+    return BPC_OK;
+}
+
+template <typename T>
+int dalloc(bpc_handle* h, size_t count, T** out) {
+    void* d = nullptr;
+    BPC_CUDA(h, cudaMalloc(&d, std::max<size_t>(16, count * sizeof(T))));
+    h->dev_allocs.push_back(d);
+    BPC_CUDA(h, cudaMemset(d, 0, std::max<size_t>(16, count * sizeof(T))));
+    *out = reinterpret_cast<T*>(d);
+    return BPC_OK;
+}
+
+int upload_bank(bpc_handle* h, const SparseBank& b, BankDev* out) {
+    const int* s; const int* c; const float* w;
+    int rc;
+    if ((rc = upload(h, b.start, &s))) return rc;
+    if ((rc = upload(h, b.count, &c))) return rc;
+    if ((rc = upload(h, b.w, &w))) return rc;
+    out->start = s; out->count = c; out->w = w; out->rows = b.rows; out->width = b.width;
+    return BPC_OK;
+}
+
+std::vector<double2> twiddles(int n, int count) {
+    std::vector<double2> t(count);
+    for (int j = 0; j < count; ++j) {
+        const double ang = -2.0 * kPi * double(j) / double(n);
+        t[j] = make_double2(std::cos(ang), std::sin(ang));
+    }
+    return t;
+}
+
+int check_params(const bpc_params* p, std::string* why) {
+    if (!p) { *why = "params is NULL"; return BPC_ERR_ARG; }
+    if (p->sr != 16000 || p->n_fft != 512 || p->hop != 256 || p->n_mels != 128 || p->n_mfcc != 40 ||
+        p->n_gammatone != 64 || p->n_lpc != 12) {
+        *why = "this build implements the reference constants only (sr 16000, n_fft 512, hop 256, n_mels 128, "
+               "n_mfcc 40, n_gammatone 64, n_lpc 12; process.py:12-23)";
+        return BPC_ERR_UNSUPPORTED;
+    }
+    if (!(p->fmax > 0.f && p->fmax <= 8000.f)) { *why = "fmax out of range"; return BPC_ERR_ARG; }
+    if (p->expected_len != 16000) {
+        *why = "this build keeps a whole segment on-chip and supports expected_len == 16000 (DURATION 1.0 s) only";
+        return BPC_ERR_UNSUPPORTED;
+    }
+    if (p->pad_scalars_to != 0 && p->pad_scalars_to < BPC_NUM_SCALARS) { *why = "pad_scalars_to < 36"; return BPC_ERR_ARG; }
+    return BPC_OK;
+}
+
+int build_tables(bpc_handle* h) {
+    const bpc_params& p = h->p;
+    Tables& tb = h->tb;
+    int rc;
+    if ((rc = upload(h, hann_periodic(512), &tb.hann512))) return rc;
+    if ((rc = upload(h, hann_periodic(2048), &tb.hann2048))) return rc;
+    if ((rc = upload(h, hann_periodic(384), &tb.hann384))) return rc;
+    if ((rc = upload(h, hamming_sym(400), &tb.hamming400))) return rc;
+    if ((rc = upload(h, twiddles(256, 256), &tb.tw256))) return rc;
+    if ((rc = upload(h, twiddles(1024, 1024), &tb.tw1024))) return rc;
+    if ((rc = upload(h, twiddles(512, 257), &tb.ptw512))) return rc;
+    if ((rc = upload(h, twiddles(2048, 1025), &tb.ptw2048))) return rc;
+    if ((rc = upload(h, twiddles(8000, 8000), &tb.tw8000))) return rc;
+    if ((rc = upload(h, twiddles(16000, 8001), &tb.ptw16000))) return rc;
+    if ((rc = upload_bank(h, mel_bank(p.sr, 512, 128, 0.0, p.fmax), &tb.mel_a))) return rc;
+    if ((rc = upload_bank(h, mel_bank(p.sr, 512, 128, 0.0, p.sr / 2.0), &tb.mel_b))) return rc;
+    if ((rc = upload_bank(h, mel_bank(p.sr, 512, 64, 0.0, p.sr / 2.0), &tb.mel_c))) return rc;
+    if ((rc = upload_bank(h, mel_bank(p.sr, 2048, 128, 0.0, p.sr / 2.0), &tb.mel_d))) return rc;
+    if ((rc = upload(h, dct2_ortho(40, 128), &tb.dct_mel))) return rc;
+    {
+        const int T = h->g.T;
+        std::vector<float> d = dct2_ortho(T, T), dt(size_t(T) * T);
+        for (int u = 0; u < T; ++u)
+            for (int t = 0; t < T; ++t) dt[size_t(t) * T + u] = d[size_t(u) * T + t];     // device wants [t][u]
+        if ((rc = upload(h, dt, &tb.dct_time))) return rc;
+    }
+    std::vector<double> edges = tuning_edges();
+    if ((rc = upload(h, edges, &tb.hist_edges))) return rc;
+    {
+        std::vector<float> all;
+        all.reserve(size_t(kNumTunings) * 12 * 257);
+        for (int i = 0; i < kNumTunings; ++i) {
+            std::vector<float> c = chroma_bank(p.sr, 512, edges[i]);
+            all.insert(all.end(), c.begin(), c.end());
+        }
+        if ((rc = upload(h, all, &tb.chroma))) return rc;
+    }
+    {
+        std::vector<int16_t> col;
+        std::vector<float> re, im;
+        std::vector<double> sl;
+        for (int i = 0; i < kNumTunings; ++i) {
+            CqtBasisEll e = cqt_basis(p.sr, edges[i]);
+            if (e.col.empty()) { h->err = "CQT basis row wider than the ELL width"; return BPC_ERR_UNSUPPORTED; }
+            for (int16_t c : e.col)
+                if (c >= 0 && (c < 60 || c > 144)) { h->err = "CQT basis support outside the staged bin window"; return BPC_ERR_UNSUPPORTED; }
+            col.insert(col.end(), e.col.begin(), e.col.end());
+            re.insert(re.end(), e.re.begin(), e.re.end());
+            im.insert(im.end(), e.im.begin(), e.im.end());
+            sl.insert(sl.end(), e.sqrt_len.begin(), e.sqrt_len.end());
+        }
+        if ((rc = upload(h, col, &tb.cqt_col))) return rc;
+        if ((rc = upload(h, re, &tb.cqt_re))) return rc;
+        if ((rc = upload(h, im, &tb.cqt_im))) return rc;
+        if ((rc = upload(h, sl, &tb.cqt_sqrt_len))) return rc;
+    }
+    if ((rc = upload(h, halfband_taps(), &tb.halfband))) return rc;
+    return BPC_OK;
+}
+
+int build_workspace(bpc_handle* h) {
+    const Geometry& g = h->g;
+    Workspace& w = h->ws;
+    const size_t C = (size_t)h->chunk, T = (size_t)g.T;
+    int rc;
+    w.cap = h->chunk;
+    if ((rc = dalloc(h, C * g.L, &w.y))) return rc;
+    if ((rc = dalloc(h, C * T * kMagStride, &w.mag512))) return rc;
+    if ((rc = dalloc(h, C * ((T + 1) / 2) * 1028, &w.mag2048_even))) return rc;
+    if ((rc = dalloc(h, C * 2, &w.tuning))) return rc;
+    if ((rc = dalloc(h, C * 2, &w.chroma_min))) return rc;
+    if ((rc = dalloc(h, C * 2, &w.ints))) return rc;
+    if ((rc = dalloc(h, (size_t)(9 + g.nscal) * 5, &h->stats_acc))) return rc;
+    w.dbg_mel_db = w.dbg_mfcc = w.dbg_gam = w.dbg_mod = w.dbg_chroma_stft = w.dbg_chroma_cens = w.dbg_lpc =
+        w.dbg_onset = nullptr;
+    h->ws_dbg = w;
+    return BPC_OK;
+}
+
+int ensure_debug(bpc_handle* h) {
+    Workspace& w = h->ws_dbg;
+    if (w.dbg_mel_db) return BPC_OK;
+    const Geometry& g = h->g;
+    const size_t C = (size_t)h->chunk, T = (size_t)g.T;
+    int rc;
+    if ((rc = dalloc(h, C * 128 * T, &w.dbg_mel_db))) return rc;
+    if ((rc = dalloc(h, C * 120 * T, &w.dbg_mfcc))) return rc;
+    if ((rc = dalloc(h, C * 64 * T, &w.dbg_gam))) return rc;
+    if ((rc = dalloc(h, C * 40 * T, &w.dbg_mod))) return rc;
+    if ((rc = dalloc(h, C * 12 * T, &w.dbg_chroma_stft))) return rc;
+    if ((rc = dalloc(h, C * 12 * T, &w.dbg_chroma_cens))) return rc;
+    if ((rc = dalloc(h, C * 12 * (size_t)g.lpc_frames, &w.dbg_lpc))) return rc;
+    if ((rc = dalloc(h, C * T, &w.dbg_onset))) return rc;
+    return BPC_OK;
+}
+
+int reset_stats(bpc_handle* h, cudaStream_t st) {
+    const int rows = 9 + h->g.nscal;
+    std::vector<double> init((size_t)rows * 5, 0.0);
+    for (int r = 0; r < rows; ++r) { init[r * 5 + 3] = 1e300; init[r * 5 + 4] = -1e300; }
+    BPC_CUDA(h, cudaMemcpyAsync(h->stats_acc, init.data(), init.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    BPC_CUDA(h, cudaStreamSynchronize(st));
+    return BPC_OK;
+}
+
+// The launch sequence for one chunk of n <= chunk segments; inputs / outputs are device pointers for this chunk.
+int run_chunk(bpc_handle* h, const void* wav, int wav_dtype, int64_t L_in, int n, float* feats, float* scalars,
+              int32_t* status, cudaStream_t st) {
+    const Geometry& g = h->g;
+    const Workspace& ws = h->debug ? h->ws_dbg : h->ws;
+    const float* y;
+    if (wav_dtype == BPC_WAV_F32 && L_in == g.L && (reinterpret_cast<uintptr_t>(wav) & 15) == 0) {
+        y = static_cast<const float*>(wav);                   // pad_or_truncate is the identity: no copy
+    } else {
+        launch_ingest(wav, wav_dtype, L_in, ws.y, n, g, st);
+        y = ws.y;
+    }
+    if (status) BPC_CUDA(h, cudaMemsetAsync(status, 0, sizeof(int32_t) * n, st));
+    launch_stft512(y, n, g, h->tb, ws, st);
+    launch_spec512_consumers(n, g, h->tb, ws, feats, scalars, status, true, st);
+    launch_spec2048(y, n, g, h->tb, ws, feats, scalars, st);
+    launch_even2048(n, g, h->tb, ws, scalars, status, st);
+    launch_cens(y, n, g, h->tb, ws, feats, st);
+    launch_time_scalars(y, n, g, h->tb, ws, scalars, status, st);
+    launch_hilbert(y, n, g, h->tb, ws, scalars, st);
+    launch_lpc(y, n, g, h->tb, ws, feats, st);
+    launch_pad_scalars(n, g, scalars, st);
+    launch_stats(n, g, feats, scalars, h->stats_acc, st);
+    h->last_n = n;
+    BPC_CUDA(h, cudaGetLastError());
+    return BPC_OK;
+}
+
+int ensure_slots(bpc_handle* h) {
+    if (h->slots_ready) return BPC_OK;
+    const Geometry& g = h->g;
+    const size_t C = (size_t)h->chunk;
+    h->slot_wav_bytes = C * (size_t)g.L * 4 * 2;                        // room for L_in up to 2 * L of float32
+    const size_t feats_bytes = C * 9 * kPlaneRows * (size_t)g.T * 4, scal_bytes = C * (size_t)g.nscal * 4;
+    for (int i = 0; i < 2; ++i) {
+        Slot& s = h->slot[i];
+        BPC_CUDA(h, cudaMalloc(&s.d_wav, h->slot_wav_bytes));
+        BPC_CUDA(h, cudaMalloc((void**)&s.d_feats, feats_bytes));
+        BPC_CUDA(h, cudaMalloc((void**)&s.d_scalars, scal_bytes));
+        BPC_CUDA(h, cudaMalloc((void**)&s.d_status, C * 4));
+        h->dev_allocs.push_back(s.d_wav); h->dev_allocs.push_back(s.d_feats);
+        h->dev_allocs.push_back(s.d_scalars); h->dev_allocs.push_back(s.d_status);
+        BPC_CUDA(h, cudaMallocHost(&s.h_wav, h->slot_wav_bytes));
+        BPC_CUDA(h, cudaMallocHost((void**)&s.h_feats, feats_bytes));
+        BPC_CUDA(h, cudaMallocHost((void**)&s.h_scalars, scal_bytes));
+        BPC_CUDA(h, cudaMallocHost((void**)&s.h_status, C * 4));
+        h->host_allocs.push_back(s.h_wav); h->host_allocs.push_back(s.h_feats);
+        h->host_allocs.push_back(s.h_scalars); h->host_allocs.push_back(s.h_status);
+        BPC_CUDA(h, cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        BPC_CUDA(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    h->slots_ready = true;
+    return BPC_OK;
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+// ================================================================================================= ABI
+extern "C" {
+
+int bpc_abi_version(void) { return BPC_ABI_VERSION; }
+
+void bpc_default_params(bpc_params* p) {
+    if (!p) return;
+    p->sr = 16000; p->n_fft = 512; p->hop = 256; p->n_mels = 128; p->n_mfcc = 40; p->fmax = 4500.f;
+    p->n_gammatone = 64; p->n_lpc = 12; p->expected_len = 16000; p->pad_scalars_to = 0;
+}
+
+int bpc_num_frames(const bpc_params* p) { return p ? p->expected_len / p->hop + 1 : BPC_ERR_ARG; }
+int bpc_num_scalars(const bpc_params* p) {
+    if (!p) return BPC_ERR_ARG;
+    return p->pad_scalars_to > BPC_NUM_SCALARS ? p->pad_scalars_to : BPC_NUM_SCALARS;
+}
+
+int bpc_create(bpc_handle** out, const bpc_params* p, int device, int64_t max_batch) {
+    if (!out) { g_create_error = "out is NULL"; return BPC_ERR_ARG; }
+    *out = nullptr;
+    std::string why;
+    int rc = check_params(p, &why);
+    if (rc) { g_create_error = why; return rc; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return BPC_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return BPC_ERR_ARG; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return BPC_ERR_CUDA; }
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10) {
+        g_create_error = "libbpc_b200 is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) +
+                         std::to_string(prop.minor);
+        return BPC_ERR_UNSUPPORTED;
+    }
+    bpc_handle* h = new bpc_handle();
+    h->p = *p;
+    h->device = device;
+    h->max_batch = max_batch > 0 ? max_batch : 1;
+    h->g.L = p->expected_len;
+    h->g.hop = p->hop;
+    h->g.T = p->expected_len / p->hop + 1;
+    h->g.nscal = bpc_num_scalars(p);
+    h->g.lpc_frames = (p->expected_len - 400 + 159) / 160;
+    const char* env_chunk = std::getenv("BPC_CHUNK");
+    int chunk = env_chunk ? std::atoi(env_chunk) : 592;               // 4 waves of 148 single-CTA-per-segment kernels
+    if (chunk < 1) chunk = 592;
+    h->chunk = (int)std::min<int64_t>(chunk, h->max_batch);
+    h->launches0 = launches_issued();
+    if ((rc = build_tables(h)) || (rc = build_workspace(h)) || (rc = reset_stats(h, 0))) {
+        g_create_error = h->err;
+        bpc_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return BPC_OK;
+}
+
+void bpc_destroy(bpc_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) {
+        if (h->slot[i].st) cudaStreamDestroy(h->slot[i].st);
+        if (h->slot[i].done) cudaEventDestroy(h->slot[i].done);
+    }
+    for (void* d : h->dev_allocs) cudaFree(d);
+    for (void* d : h->host_allocs) cudaFreeHost(d);
+    delete h;
+}
+
+const char* bpc_last_error(const bpc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int bpc_set_debug(bpc_handle* h, int on) {
+    if (!h) return BPC_ERR_ARG;
+    if (on) {
+        int rc = ensure_debug(h);
+        if (rc) return rc;
+    }
+    h->debug = on != 0;
+    return BPC_OK;
+}
+
+int bpc_precompute(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in, float* feats,
+                   float* scalars, int32_t* status, void* stream) {
+    if (!h) return BPC_ERR_ARG;
+    if (!wav || !feats || !scalars || B < 0 || L_in <= 0 || (wav_dtype != BPC_WAV_F32 && wav_dtype != BPC_WAV_PCM16)) {
+        h->err = "bpc_precompute: bad argument";
+        return BPC_ERR_ARG;
+    }
+    BPC_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Geometry& g = h->g;
+    const size_t esz = wav_dtype == BPC_WAV_F32 ? 4 : 2;
+    for (int64_t off = 0; off < B; off += h->chunk) {
+        const int n = (int)std::min<int64_t>(h->chunk, B - off);
+        int rc = run_chunk(h, static_cast<const char*>(wav) + (size_t)off * L_in * esz, wav_dtype, L_in, n,
+                           feats + (size_t)off * 9 * kPlaneRows * g.T, scalars + (size_t)off * g.nscal,
+                           status ? status + off : nullptr, st);
+        if (rc) return rc;
+    }
+    return BPC_OK;
+}
+
+int bpc_precompute_host(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in, float* feats,
+                        float* scalars, int32_t* status) {
+    if (!h) return BPC_ERR_ARG;
+    if (!wav || !feats || !scalars || B < 0 || L_in <= 0 || (wav_dtype != BPC_WAV_F32 && wav_dtype != BPC_WAV_PCM16)) {
+        h->err = "bpc_precompute_host: bad argument";
+        return BPC_ERR_ARG;
+    }
+    BPC_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_slots(h);
+    if (rc) return rc;
+    const Geometry& g = h->g;
+    const size_t esz = wav_dtype == BPC_WAV_F32 ? 4 : 2;
+    if ((size_t)h->chunk * L_in * esz > h->slot_wav_bytes) { h->err = "L_in too large for the staging buffers"; return BPC_ERR_ARG; }
+    const size_t seg_feats = (size_t)9 * kPlaneRows * g.T;
+    const bool pin_in = is_pinned(wav), pin_f = is_pinned(feats), pin_s = is_pinned(scalars);
+    const int64_t nchunks = (B + h->chunk - 1) / h->chunk;
+    for (int64_t i = 0; i <= nchunks; ++i) {
+        if (i < nchunks) {
+            Slot& s = h->slot[i & 1];
+            const int64_t off = i * h->chunk;
+            const int n = (int)std::min<int64_t>(h->chunk, B - off);
+            const char* src = static_cast<const char*>(wav) + (size_t)off * L_in * esz;
+            const size_t in_bytes = (size_t)n * L_in * esz;
+            if (pin_in) {
+                BPC_CUDA(h, cudaMemcpyAsync(s.d_wav, src, in_bytes, cudaMemcpyHostToDevice, s.st));
+            } else {
+                std::memcpy(s.h_wav, src, in_bytes);
+                BPC_CUDA(h, cudaMemcpyAsync(s.d_wav, s.h_wav, in_bytes, cudaMemcpyHostToDevice, s.st));
+            }
+            rc = run_chunk(h, s.d_wav, wav_dtype, L_in, n, s.d_feats, s.d_scalars, s.d_status, s.st);
+            if (rc) return rc;
+            float* fdst = pin_f ? feats + (size_t)off * seg_feats : s.h_feats;
+            float* sdst = pin_s ? scalars + (size_t)off * g.nscal : s.h_scalars;
+            BPC_CUDA(h, cudaMemcpyAsync(fdst, s.d_feats, (size_t)n * seg_feats * 4, cudaMemcpyDeviceToHost, s.st));
+            BPC_CUDA(h, cudaMemcpyAsync(sdst, s.d_scalars, (size_t)n * g.nscal * 4, cudaMemcpyDeviceToHost, s.st));
+            BPC_CUDA(h, cudaMemcpyAsync(s.h_status, s.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, s.st));
+            BPC_CUDA(h, cudaEventRecord(s.done, s.st));
+        }
+        if (i >= 1) {
+            const int64_t j = i - 1;
+            Slot& s = h->slot[j & 1];
+            const int64_t off = j * h->chunk;
+            const int n = (int)std::min<int64_t>(h->chunk, B - off);
+            BPC_CUDA(h, cudaEventSynchronize(s.done));
+            if (!pin_f) std::memcpy(feats + (size_t)off * seg_feats, s.h_feats, (size_t)n * seg_feats * 4);
+            if (!pin_s) std::memcpy(scalars + (size_t)off * g.nscal, s.h_scalars, (size_t)n * g.nscal * 4);
+            if (status) std::memcpy(status + off, s.h_status, (size_t)n * 4);
+        }
+    }
+    return BPC_OK;
+}
+
+int bpc_stage_logmel(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in, float* stft_db,
+                     float* mel3, void* stream) {
+    if (!h) return BPC_ERR_ARG;
+    if (!wav || !mel3 || B < 0 || L_in <= 0) { h->err = "bpc_stage_logmel: bad argument"; return BPC_ERR_ARG; }
+    BPC_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Geometry& g = h->g;
+    const Workspace& ws = h->debug ? h->ws_dbg : h->ws;
+    const size_t esz = wav_dtype == BPC_WAV_F32 ? 4 : 2;
+    for (int64_t off = 0; off < B; off += h->chunk) {
+        const int n = (int)std::min<int64_t>(h->chunk, B - off);
+        const void* w = static_cast<const char*>(wav) + (size_t)off * L_in * esz;
+        const float* y;
+        if (wav_dtype == BPC_WAV_F32 && L_in == g.L && (reinterpret_cast<uintptr_t>(w) & 15) == 0) y = static_cast<const float*>(w);
+        else { launch_ingest(w, wav_dtype, L_in, ws.y, n, g, st); y = ws.y; }
+        launch_stft512(y, n, g, h->tb, ws, st);
+        if (stft_db) launch_stft_db(n, g, ws, stft_db + (size_t)off * 257 * g.T, st);
+        launch_logmel_only(n, g, h->tb, ws, mel3 + (size_t)off * 3 * kPlaneRows * g.T, st);
+        h->last_n = n;
+    }
+    BPC_CUDA(h, cudaGetLastError());
+    return BPC_OK;
+}
+
+int bpc_channel_stats(bpc_handle* h, double* stats_host) {
+    if (!h || !stats_host) return BPC_ERR_ARG;
+    BPC_CUDA(h, cudaSetDevice(h->device));
+    BPC_CUDA(h, cudaDeviceSynchronize());
+    BPC_CUDA(h, cudaMemcpy(stats_host, h->stats_acc, sizeof(double) * 5 * (9 + h->g.nscal), cudaMemcpyDeviceToHost));
+    return BPC_OK;
+}
+
+int bpc_channel_stats_device(bpc_handle* h, double** stats_dev, int64_t* n_rows) {
+    if (!h || !stats_dev) return BPC_ERR_ARG;
+    *stats_dev = h->stats_acc;
+    if (n_rows) *n_rows = 9 + h->g.nscal;
+    return BPC_OK;
+}
+
+int bpc_channel_stats_reset(bpc_handle* h) {
+    if (!h) return BPC_ERR_ARG;
+    BPC_CUDA(h, cudaSetDevice(h->device));
+    BPC_CUDA(h, cudaDeviceSynchronize());
+    return reset_stats(h, 0);
+}
+
+int bpc_debug_copy(bpc_handle* h, const char* what, void* out, int64_t cap_bytes, int64_t* got) {
+    if (!h || !what || !out || !got) return BPC_ERR_ARG;
+    BPC_CUDA(h, cudaSetDevice(h->device));
+    BPC_CUDA(h, cudaDeviceSynchronize());
+    const Geometry& g = h->g;
+    const Workspace& w = h->ws_dbg;
+    const size_t n = (size_t)h->last_n, T = (size_t)g.T;
+    const void* src = nullptr;
+    size_t bytes = 0;
+    const std::string k(what);
+    if (k == "mag512") { src = w.mag512; bytes = n * T * kMagStride * 4; }
+    else if (k == "mel_db") { src = w.dbg_mel_db; bytes = n * 128 * T * 4; }
+    else if (k == "mfcc_raw") { src = w.dbg_mfcc; bytes = n * 120 * T * 4; }
+    else if (k == "gammatone_raw") { src = w.dbg_gam; bytes = n * 64 * T * 4; }
+    else if (k == "mod_spec_raw") { src = w.dbg_mod; bytes = n * 40 * T * 4; }
+    else if (k == "chroma_stft_raw") { src = w.dbg_chroma_stft; bytes = n * 12 * T * 4; }
+    else if (k == "chroma_cens_raw") { src = w.dbg_chroma_cens; bytes = n * 12 * T * 4; }
+    else if (k == "lpc_raw") { src = w.dbg_lpc; bytes = n * 12 * (size_t)g.lpc_frames * 4; }
+    else if (k == "onset_env") { src = w.dbg_onset; bytes = n * T * 4; }
+    else if (k == "tuning") { src = w.tuning; bytes = n * 2 * 4; }
+    else if (k == "ints") { src = w.ints; bytes = n * 2 * 4; }
+    else { h->err = "bpc_debug_copy: unknown key " + k; return BPC_ERR_ARG; }
+    if (!src) { h->err = "bpc_debug_copy: debug buffers are off (bpc_set_debug)"; return BPC_ERR_ARG; }
+    bytes = std::min<size_t>(bytes, (size_t)cap_bytes);
+    BPC_CUDA(h, cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+    *got = (int64_t)bytes;
+    return BPC_OK;
+}
+
+int64_t bpc_table_copy(const bpc_params* p, const char* name, int tuning_idx, void* out, int64_t cap_elems) {
+    std::string why;
+    if (check_params(p, &why) || !name || !out) return BPC_ERR_ARG;
+    const std::string k(name);
+    auto put_f = [&](const std::vector<float>& v) -> int64_t {
+        if ((int64_t)v.size() > cap_elems) return BPC_ERR_ARG;
+        std::memcpy(out, v.data(), v.size() * sizeof(float));
+        return (int64_t)v.size();
+    };
+    auto put_d = [&](const std::vector<double>& v) -> int64_t {
+        if ((int64_t)v.size() > cap_elems) return BPC_ERR_ARG;
+        std::memcpy(out, v.data(), v.size() * sizeof(double));
+        return (int64_t)v.size();
+    };
+    const int T = p->expected_len / p->hop + 1;
+    std::vector<double> edges = tuning_edges();
+    if (tuning_idx < 0 || tuning_idx >= kNumTunings) tuning_idx = 50;
+    if (k == "mel_a") return put_f(mel_bank(p->sr, 512, 128, 0.0, p->fmax).dense);
+    if (k == "mel_b") return put_f(mel_bank(p->sr, 512, 128, 0.0, p->sr / 2.0).dense);
+    if (k == "mel_c") return put_f(mel_bank(p->sr, 512, 64, 0.0, p->sr / 2.0).dense);
+    if (k == "mel_d") return put_f(mel_bank(p->sr, 2048, 128, 0.0, p->sr / 2.0).dense);
+    if (k == "dct_mel") return put_f(dct2_ortho(40, 128));
+    if (k == "dct_time") return put_f(dct2_ortho(T, T));
+    if (k == "hann512") return put_d(hann_periodic(512));
+    if (k == "hann2048") return put_d(hann_periodic(2048));
+    if (k == "hann384") return put_d(hann_periodic(384));
+    if (k == "hamming400") return put_d(hamming_sym(400));
+    if (k == "chroma") return put_f(chroma_bank(p->sr, 512, edges[tuning_idx]));
+    if (k == "hist_edges") return put_d(edges);
+    if (k == "halfband") return put_d(halfband_taps());
+    if (k == "cqt_basis" || k == "cqt_sqrt_len") {
+        std::vector<std::complex<float>> dense;
+        CqtBasisEll e = cqt_basis(p->sr, edges[tuning_idx], &dense);
+        if (e.col.empty()) return BPC_ERR_UNSUPPORTED;
+        if (k == "cqt_sqrt_len") return put_d(e.sqrt_len);
+        std::vector<float> flat(dense.size() * 2);
+        for (size_t i = 0; i < dense.size(); ++i) { flat[2 * i] = dense[i].real(); flat[2 * i + 1] = dense[i].imag(); }
+        return put_f(flat);
+    }
+    return BPC_ERR_ARG;
+}
+
+int64_t bpc_launch_count(const bpc_handle* h) { return h ? launches_issued() - h->launches0 : 0; }
+
+}  // extern "C"

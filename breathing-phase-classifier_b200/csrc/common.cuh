@@ -1,0 +1,167 @@
+// Shared device helpers: reductions, TMA-bulk staging, z-score finalisation.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cfloat>
+
+namespace bpc {
+
+constexpr int kPlaneRows = 128;
+constexpr int kMagStride = 260;          // |STFT512| workspace row stride (257 valid bins, 16-byte aligned rows)
+constexpr int kMaxFrames = 64;           // on-chip kernels of this build hold T <= 64 frames (1 s @ 16 kHz, hop 256)
+constexpr int kMaxLen = 16384;           // ... and L <= 16384 samples
+
+// ------------------------------------------------------------------------------------------------ reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide reductions over blockDim.x threads (multiple of 32, <= 1024).  `scratch` holds >= 32 elements of T and is
+// reused; every thread gets the result.  Contains __syncthreads(): call from all threads.
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, T ident, Op op, T* scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    T r = (lane < nw) ? scratch[lane] : ident;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = op(r, __shfl_xor_sync(0xffffffffu, r, o));
+    return r;
+}
+struct OpAdd { template <typename T> __device__ T operator()(T a, T b) const { return a + b; } };
+struct OpMaxF { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+struct OpMinF { __device__ float operator()(float a, float b) const { return fminf(a, b); } };
+struct OpMaxD { __device__ double operator()(double a, double b) const { return fmax(a, b); } };
+struct OpMinD { __device__ double operator()(double a, double b) const { return fmin(a, b); } };
+
+__device__ __forceinline__ double block_sum(double v, double* scratch) { return block_reduce(v, 0.0, OpAdd(), scratch); }
+__device__ __forceinline__ float block_max(float v, float* scratch) { return block_reduce(v, -FLT_MAX, OpMaxF(), scratch); }
+__device__ __forceinline__ float block_min(float v, float* scratch) { return block_reduce(v, FLT_MAX, OpMinF(), scratch); }
+
+// ------------------------------------------------------------------------------------ numpy-style z-score terms
+// (x - mean) / (std + 1e-8) with mean / std already rounded to float32 (numpy float32 reductions), float32 ops.
+struct ZTerm {
+    float mean, denom;
+    __device__ __forceinline__ float operator()(float x) const { return __fdiv_rn(__fsub_rn(x, mean), denom); }
+};
+__device__ __forceinline__ ZTerm make_zterm(double sum, double sumsq, double n) {
+    const double mean = sum / n;
+    double var = sumsq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    ZTerm z;
+    z.mean = (float)mean;
+    z.denom = __fadd_rn((float)sqrt(var), 1e-8f);
+    return z;
+}
+
+// ----------------------------------------------------------- 1-D TMA bulk copy global -> shared (SASS: UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+// bytes and both addresses must be multiples of 16
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Stage `n` floats of a segment (global, 16-byte aligned base, n % 4 == 0) into shared memory with one TMA bulk
+// copy per <=32 KiB slice; all threads return after the data is visible.  `bar` is a shared uint64_t.
+__device__ __forceinline__ void stage_segment_tma(float* dst, const float* src, int n, uint64_t* bar) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = (uint32_t)n * 4u;
+        mbar_expect_tx(bar, total);
+        for (uint32_t off = 0; off < total; off += 32768u) {
+            const uint32_t len = (total - off) < 32768u ? (total - off) : 32768u;
+            tma_bulk_g2s((char*)dst + off, (const char*)src + off, len, bar);
+        }
+    }
+    mbar_wait(bar, 0);
+}
+
+// float atomic min/max via ordered-int trick (values must not be NaN)
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f) atomicMax((int*)addr, __float_as_int(v));
+    else atomicMin((unsigned int*)addr, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+    if (v >= 0.f) atomicMin((int*)addr, __float_as_int(v));
+    else atomicMax((unsigned int*)addr, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
+    unsigned long long* a = (unsigned long long*)addr;
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        if (__longlong_as_double((long long)assumed) >= v) break;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    } while (assumed != old);
+}
+__device__ __forceinline__ void atomic_min_double(double* addr, double v) {
+    unsigned long long* a = (unsigned long long*)addr;
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        if (__longlong_as_double((long long)assumed) <= v) break;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    } while (assumed != old);
+}
+
+}  // namespace bpc

@@ -1,0 +1,517 @@
+// STFT-512 group: ingest (pad_or_truncate), batched framing + Hann + FP64 real FFT-512 -> |X| workspace, and the four
+// consumer roles of that spectrogram (one CTA per (segment, role)):
+//   role 0  mel / mel_delta / mel_delta2 / mod_spec   (process.py:32-41, 69-72; methods.py:142-143)
+//   role 1  mfcc (+delta, +delta2, row-wise z)          (process.py:43-49)
+//   role 2  "gammatone" = log1p(mel64 @ |X|)            (process.py:59-62; methods.py:136-140)
+//   role 3  chroma_stft rows + low-frequency ratio      (process.py:51-52; methods.py:84-88)
+#include <atomic>
+#include <cmath>
+#include "kernels.cuh"
+#include "fft.cuh"
+#include "tuning.cuh"
+
+namespace bpc {
+
+static std::atomic<int64_t> g_launches{0};
+int64_t launches_issued() { return g_launches.load(); }
+void note_launch(int n) { g_launches.fetch_add(n); }
+
+// ------------------------------------------------------------------------------------------------- ingest
+// methods.py:24-28 pad_or_truncate (+ soundfile's int16 / 32768 when the caller passes PCM16).
+__global__ void k_ingest(const void* __restrict__ wav, int dtype, long long L_in, float* __restrict__ y, int L,
+                         long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / L;
+        const int n = (int)(i - b * L);
+        float v = 0.f;
+        if (n < L_in) {
+            if (dtype == 1) v = (float)((const short*)wav)[b * L_in + n] * (1.0f / 32768.0f);
+            else v = ((const float*)wav)[b * L_in + n];
+        }
+        y[i] = v;
+    }
+}
+
+void launch_ingest(const void* wav, int wav_dtype, int64_t L_in, float* y, int n, const Geometry& g, cudaStream_t st) {
+    const long long total = (long long)n * g.L;
+    const int blocks = (int)((total + 1023) / 1024 < 148 * 16 ? (total + 1023) / 1024 : 148 * 16);
+    k_ingest<<<blocks, 256, 0, st>>>(wav, wav_dtype, (long long)L_in, y, g.L, total);
+    note_launch();
+}
+
+// ------------------------------------------------------------------------------------------------ STFT-512
+// One CTA per segment, one warp per frame (8 frames in flight).  librosa.stft semantics: zero centre padding,
+// periodic Hann (float64) * float32 samples, float64 FFT, complex64 rounding, |.| as hypotf.
+__global__ void __launch_bounds__(256) k_stft512(const float* __restrict__ y, int L, int T, int hop,
+                                                 const double* __restrict__ win, const double2* __restrict__ tw_g,
+                                                 const double2* __restrict__ ptw, float* __restrict__ mag) {
+    __shared__ double2 s_tw[256];
+    __shared__ double2 s_buf[8][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x;
+    s_tw[tid] = tw_g[tid];
+    double w0[8], w1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = lane + 32 * i;
+        w0[i] = win[2 * m];
+        w1[i] = win[2 * m + 1];
+    }
+    __syncthreads();
+    double2* buf = s_buf[warp];
+    const float* yb = y + (size_t)b * L;
+    for (int t = warp; t < T; t += 8) {
+        const int g0 = t * hop - 256;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = lane + 32 * i;
+            const int g = g0 + 2 * m;
+            const float x0 = (g >= 0 && g < L) ? __ldg(yb + g) : 0.f;
+            const float x1 = (g + 1 >= 0 && g + 1 < L) ? __ldg(yb + g + 1) : 0.f;
+            buf[m] = make_double2((double)x0 * w0[i], (double)x1 * w1[i]);
+        }
+        __syncwarp();
+        fft_r4_dif<4, 32>(buf, s_tw, lane, SyncWarp());
+        float* out = mag + ((size_t)b * T + t) * kMagStride;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int k = lane + 32 * i;
+            if (k <= 256) out[k] = c64_abs(rfft_bin<4>(buf, ptw, k));
+        }
+        __syncwarp();
+    }
+}
+
+void launch_stft512(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, cudaStream_t st) {
+    k_stft512<<<n, 256, 0, st>>>(y, g.L, g.T, g.hop, tb.hann512, tb.tw256, tb.ptw512, ws.mag512);
+    note_launch();
+}
+
+// ------------------------------------------------------------------------------------- shared device pieces
+// librosa.power_to_db(S, ref, amin=1e-10, top_db=80) on a shared-memory array, in place (float32 like numpy).
+__device__ void power_to_db_inplace(float* P, int n, bool ref_is_max, float* fscratch) {
+    float ref_db = 0.f;
+    if (ref_is_max) {
+        float mx = -FLT_MAX;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, P[i]);
+        mx = block_max(mx, fscratch);
+        ref_db = (float)(10.0 * log10((double)fmaxf(1e-10f, mx)));
+    }
+    float vmax = -FLT_MAX;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = __fsub_rn(__fmul_rn(10.0f, log10f(fmaxf(1e-10f, P[i]))), ref_db);
+        P[i] = v;
+        vmax = fmaxf(vmax, v);
+    }
+    vmax = block_max(vmax, fscratch);
+    const float floor_db = __fsub_rn(vmax, 80.0f);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) P[i] = fmaxf(P[i], floor_db);
+    __syncthreads();
+}
+
+// librosa.feature.delta(width=9, order, mode='interp') == scipy savgol_filter(9, polyorder=order, deriv=order):
+// interior correlation; the 4 edge samples on each side take the (constant) order-th derivative of the edge fit,
+// i.e. the interior value at t=4 / t=T-5.  float64 accumulate, float32 store.
+__device__ __forceinline__ float delta_at(const float* row, int t, int T, int order) {
+    const int tc = t < 4 ? 4 : (t > T - 5 ? T - 5 : t);
+    const float* r = row + tc;
+    double acc;
+    if (order == 1) {
+        acc = (4.0 * ((double)r[4] - (double)r[-4]) + 3.0 * ((double)r[3] - (double)r[-3]) +
+               2.0 * ((double)r[2] - (double)r[-2]) + ((double)r[1] - (double)r[-1])) / 60.0;
+    } else {
+        acc = (28.0 * ((double)r[4] + (double)r[-4]) + 7.0 * ((double)r[3] + (double)r[-3]) -
+               8.0 * ((double)r[2] + (double)r[-2]) - 17.0 * ((double)r[1] + (double)r[-1]) - 20.0 * (double)r[0]) /
+              462.0;
+    }
+    return (float)acc;
+}
+
+// Band-form filterbank applied to |X| (power = false) or |X|^2 (power = true): out[m*T + t], float32 accumulate.
+__device__ void apply_bank(const BankDev& bank, const float* __restrict__ mag_b, int T, bool power, float* out) {
+    const int total = bank.rows * T;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int m = idx % bank.rows, t = idx / bank.rows;
+        const int s = bank.start[m], c = bank.count[m];
+        const float* src = mag_b + (size_t)t * kMagStride + s;
+        const float* w = bank.w + (size_t)m * bank.width;
+        float acc = 0.f;
+        for (int j = 0; j < c; ++j) {
+            const float v = __ldg(src + j);
+            acc = fmaf(__ldg(w + j), power ? __fmul_rn(v, v) : v, acc);
+        }
+        out[m * T + t] = acc;
+    }
+    __syncthreads();
+}
+
+// C[k*T + t] = sum_n D[k*128 + n] * P[n*T + t], k < 40 (ortho DCT-II along the mel axis, first 40 rows).
+// 4 rows per work item; 4 float32 partial sums per row combined in float64.
+__device__ void dct_mel40(const float* __restrict__ D, const float* P, int T, float* C) {
+    const int items = 10 * T;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int t = it % T, k0 = (it / T) * 4;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int blk = 0; blk < 4; ++blk) {
+            float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+            for (int n = blk * 32; n < blk * 32 + 32; ++n) {
+                const float p = P[n * T + t];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) part[i] = fmaf(__ldg(D + (k0 + i) * 128 + n), p, part[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] += (double)part[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) C[(k0 + i) * T + t] = (float)acc[i];
+    }
+    __syncthreads();
+}
+
+// whole-array statistics of a shared-memory array
+__device__ ZTerm zterm_of(const float* a, int n, double* dscratch, float* fscratch, float* min_out) {
+    double s = 0.0, q = 0.0;
+    float mn = FLT_MAX;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = (double)a[i];
+        s += v;
+        q += v * v;
+        mn = fminf(mn, a[i]);
+    }
+    s = block_sum(s, dscratch);
+    q = block_sum(q, dscratch);
+    if (min_out) *min_out = block_min(mn, fscratch);
+    return make_zterm(s, q, (double)n);
+}
+
+// ------------------------------------------------------------------------------------------- role 0: mel3+mod
+__device__ void role_mel(int b, const Geometry g, const Tables& tb, const Workspace& ws, float* feats, float* mel3,
+                         float* smem, double* dscratch, float* fscratch) {
+    const int T = g.T, NP = kPlaneRows * T;
+    float* P = smem;                 // [128*T] mel power -> mel_db
+    float* C1 = P + NP;              // [40*T]
+    float* C2 = C1 + 40 * T;         // [40*T]
+    const float* mag_b = ws.mag512 + (size_t)b * T * kMagStride;
+
+    apply_bank(tb.mel_a, mag_b, T, true, P);
+    power_to_db_inplace(P, NP, true, fscratch);                      // process.py:33
+    if (ws.dbg_mel_db) {
+        float* d = ws.dbg_mel_db + (size_t)b * NP;
+        for (int i = threadIdx.x; i < NP; i += blockDim.x) d[i] = P[i];
+    }
+    // statistics of mel_db, delta, delta2 (process.py:34-38)
+    double s0 = 0, q0 = 0, s1 = 0, q1 = 0, s2 = 0, q2 = 0;
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) {
+        const int m = i / T, t = i - m * T;
+        const double v0 = (double)P[i];
+        const double v1 = (double)delta_at(P + m * T, t, T, 1);
+        const double v2 = (double)delta_at(P + m * T, t, T, 2);
+        s0 += v0; q0 += v0 * v0;
+        s1 += v1; q1 += v1 * v1;
+        s2 += v2; q2 += v2 * v2;
+    }
+    s0 = block_sum(s0, dscratch); q0 = block_sum(q0, dscratch);
+    s1 = block_sum(s1, dscratch); q1 = block_sum(q1, dscratch);
+    s2 = block_sum(s2, dscratch); q2 = block_sum(q2, dscratch);
+    const ZTerm z0 = make_zterm(s0, q0, (double)NP), z1 = make_zterm(s1, q1, (double)NP),
+                z2 = make_zterm(s2, q2, (double)NP);
+    float *o0, *o1, *o2;
+    if (mel3) {
+        o0 = mel3 + (size_t)b * 3 * NP; o1 = o0 + NP; o2 = o1 + NP;
+    } else {
+        o0 = plane_ptr(feats, b, BPC_CH_MEL, T);
+        o1 = plane_ptr(feats, b, BPC_CH_MEL_DELTA, T);
+        o2 = plane_ptr(feats, b, BPC_CH_MEL_DELTA2, T);
+    }
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) {
+        const int m = i / T, t = i - m * T;
+        o0[i] = z0(P[i]);
+        o1[i] = z1(delta_at(P + m * T, t, T, 1));
+        o2[i] = z2(delta_at(P + m * T, t, T, 2));
+    }
+    if (mel3) return;
+
+    // mod_spec (methods.py:142-143): DCT-II ortho over mel (keep 40), then over time
+    dct_mel40(tb.dct_mel, P, T, C1);
+    const float* DTt = tb.dct_time;                                   // [t][u] = DT[u][t]
+    for (int idx = threadIdx.x; idx < 40 * T; idx += blockDim.x) {
+        const int u = idx % T, k = idx / T;
+        double acc = 0.0;
+        float part = 0.f;
+        for (int t = 0; t < T; ++t) {
+            part = fmaf(__ldg(DTt + t * T + u), C1[k * T + t], part);
+            if ((t & 15) == 15) { acc += (double)part; part = 0.f; }
+        }
+        acc += (double)part;
+        C2[idx] = (float)acc;
+    }
+    __syncthreads();
+    if (ws.dbg_mod) {
+        float* d = ws.dbg_mod + (size_t)b * 40 * T;
+        for (int i = threadIdx.x; i < 40 * T; i += blockDim.x) d[i] = C2[i];
+    }
+    float mn;
+    const ZTerm zm = zterm_of(C2, 40 * T, dscratch, fscratch, &mn);
+    const float fill = zm(mn);                                         // pad_freq: min of the normalised array
+    float* om = plane_ptr(feats, b, BPC_CH_MOD_SPEC, T);
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) om[i] = (i < 40 * T) ? zm(C2[i]) : fill;
+}
+
+// ----------------------------------------------------------------------------------------------- role 1: mfcc
+__device__ void role_mfcc(int b, const Geometry g, const Tables& tb, const Workspace& ws, float* feats, float* smem,
+                          double* dscratch, float* fscratch) {
+    const int T = g.T, NP = kPlaneRows * T;
+    float* P = smem;                 // [128*T]
+    float* MF = P + NP;              // [40*T]
+    float* OUT = MF + 40 * T;        // [120*T]
+    const float* mag_b = ws.mag512 + (size_t)b * T * kMagStride;
+    apply_bank(tb.mel_b, mag_b, T, true, P);
+    power_to_db_inplace(P, NP, false, fscratch);                      // librosa.feature.mfcc: power_to_db(ref=1.0)
+    dct_mel40(tb.dct_mel, P, T, MF);
+    if (ws.dbg_mfcc) {
+        float* d = ws.dbg_mfcc + (size_t)b * 120 * T;
+        for (int i = threadIdx.x; i < 120 * T; i += blockDim.x) {
+            const int r = i / T, t = i - r * T;
+            d[i] = r < 40 ? MF[i] : (r < 80 ? delta_at(MF + (r - 40) * T, t, T, 1) : delta_at(MF + (r - 80) * T, t, T, 2));
+        }
+    }
+    // row-wise z-score of vstack([mfcc, delta, delta2]) (process.py:46-47): one warp per row
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float mn = FLT_MAX;
+    for (int r = warp; r < 120; r += nw) {
+        const int src = r % 40, ord = r / 40;
+        double s = 0.0, q = 0.0;
+        for (int t = lane; t < T; t += 32) {
+            const float v = ord == 0 ? MF[src * T + t] : delta_at(MF + src * T, t, T, ord);
+            OUT[r * T + t] = v;
+            s += (double)v;
+            q += (double)v * (double)v;
+        }
+        s = warp_sum(s);
+        q = warp_sum(q);
+        const ZTerm z = make_zterm(s, q, (double)T);
+        __syncwarp();
+        for (int t = lane; t < T; t += 32) {
+            const float v = z(OUT[r * T + t]);
+            OUT[r * T + t] = v;
+            mn = fminf(mn, v);
+        }
+    }
+    mn = block_min(mn, fscratch);
+    __syncthreads();
+    float* o = plane_ptr(feats, b, BPC_CH_MFCC, T);
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) o[i] = (i < 120 * T) ? OUT[i] : mn;
+}
+
+// ------------------------------------------------------------------------------------------ role 2: gammatone
+__device__ void role_gammatone(int b, const Geometry g, const Tables& tb, const Workspace& ws, float* feats,
+                               float* smem, double* dscratch, float* fscratch) {
+    const int T = g.T, NP = kPlaneRows * T, NG = tb.mel_c.rows * T;
+    float* G = smem;
+    const float* mag_b = ws.mag512 + (size_t)b * T * kMagStride;
+    apply_bank(tb.mel_c, mag_b, T, false, G);
+    for (int i = threadIdx.x; i < NG; i += blockDim.x) G[i] = log1pf(G[i]);
+    __syncthreads();
+    if (ws.dbg_gam) {
+        float* d = ws.dbg_gam + (size_t)b * NG;
+        for (int i = threadIdx.x; i < NG; i += blockDim.x) d[i] = G[i];
+    }
+    float mn;
+    const ZTerm z = zterm_of(G, NG, dscratch, fscratch, &mn);
+    const float fill = z(mn);
+    float* o = plane_ptr(feats, b, BPC_CH_GAMMATONE, T);
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) o[i] = (i < NG) ? z(G[i]) : fill;
+}
+
+// ------------------------------------------------------------------------------------------ role 3: chroma_stft
+__device__ void role_chroma_stft(int b, const Geometry g, const Tables& tb, const Workspace& ws, float* feats,
+                                 float* scalars, int32_t* status, float* smem, double* dscratch, float* fscratch) {
+    const int T = g.T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    float* cand_mag = smem;                       // [kMaxCand]
+    float* cand_pitch = cand_mag + kMaxCand;      // [kMaxCand]
+    float* sortbuf = cand_pitch + kMaxCand;       // [kMaxCand]
+    float* colmax = sortbuf + kMaxCand;           // [64]
+    float* raw = colmax + 64;                     // [12*T]
+    int* hist = (int*)(raw + 12 * T);             // [100]
+    __shared__ int s_ncand;
+    const float* mag_b = ws.mag512 + (size_t)b * T * kMagStride;
+    if (tid == 0) s_ncand = 0;
+
+    // column maxima + low-frequency energy ratio (methods.py:84-88: sum(|X|^2[:32]) / (sum(|X|^2) + 1e-8))
+    double e_low = 0.0, e_tot = 0.0;
+    for (int t = warp; t < T; t += nw) {
+        float mx = 0.f;
+        for (int k = lane; k < 257; k += 32) {
+            const float v = __ldg(mag_b + (size_t)t * kMagStride + k);
+            mx = fmaxf(mx, v);
+            const double p = (double)__fmul_rn(v, v);
+            e_tot += p;
+            if (k < 32) e_low += p;
+        }
+        mx = warp_max(mx);
+        if (lane == 0) colmax[t] = mx;
+    }
+    e_low = block_sum(e_low, dscratch);
+    e_tot = block_sum(e_tot, dscratch);
+    if (tid == 0) {
+        const float lo = (float)e_low, tot = (float)e_tot;                  // np.sum of float32 arrays
+        scalars[(size_t)b * g.nscal + 25] = __fdiv_rn(lo, __fadd_rn(tot, 1e-8f));
+    }
+    __syncthreads();
+
+    // piptrack over bins 5..127 (150 Hz <= k * 31.25 < 4000 Hz), threshold 0.1 * column max
+    const int nb = 123;
+    for (int idx = tid; idx < nb * T; idx += blockDim.x) {
+        const int t = idx / nb, k = 5 + idx - t * nb;
+        const float* col = mag_b + (size_t)t * kMagStride;
+        float pitch, mv;
+        if (piptrack_candidate(__ldg(col + k - 1), __ldg(col + k), __ldg(col + k + 1), __fmul_rn(0.1f, colmax[t]), k,
+                               31.25, &pitch, &mv)) {
+            const int slot = atomicAdd(&s_ncand, 1);
+            if (slot < kMaxCand) { cand_mag[slot] = mv; cand_pitch[slot] = pitch; }
+        }
+    }
+    __syncthreads();
+    int n = s_ncand;
+    uint32_t flags = 0;
+    if (n > kMaxCand) { n = kMaxCand; flags |= BPC_SEG_CAND_OVERFLOW; }
+    bool empty = false;
+    const int tbin = tuning_from_candidates(cand_mag, cand_pitch, n, sortbuf, hist, tb.hist_edges, 12, &empty);
+    if (empty) flags |= BPC_SEG_TUNING_EMPTY;
+    if (tid == 0) {
+        ws.tuning[b * 2 + 0] = tbin;
+        if (status && flags) atomicOr((unsigned int*)&status[b], flags);
+    }
+
+    // raw chroma = chromafb[tuning] @ |X| (float32), one warp per frame
+    const float* fb = tb.chroma + (size_t)tbin * 12 * 257;
+    for (int t = warp; t < T; t += nw) {
+        float acc[12];
+#pragma unroll
+        for (int c = 0; c < 12; ++c) acc[c] = 0.f;
+        for (int k = lane; k < 257; k += 32) {
+            const float v = __ldg(mag_b + (size_t)t * kMagStride + k);
+#pragma unroll
+            for (int c = 0; c < 12; ++c) acc[c] = fmaf(__ldg(fb + c * 257 + k), v, acc[c]);
+        }
+        float cmax = 0.f;
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {
+            acc[c] = warp_sum(acc[c]);
+            cmax = fmaxf(cmax, fabsf(acc[c]));
+        }
+        // util.normalize(norm=inf): float64 division, float32 store; columns below tiny are left alone
+        const double len = (cmax < 1.17549435e-38f) ? 1.0 : (double)cmax;
+        if (lane < 12) {
+            float v = 0.f;
+#pragma unroll
+            for (int c = 0; c < 12; ++c) if (c == lane) v = acc[c];
+            raw[lane * T + t] = (float)((double)v / len);
+        }
+    }
+    __syncthreads();
+    if (ws.dbg_chroma_stft) {
+        float* d = ws.dbg_chroma_stft + (size_t)b * 12 * T;
+        for (int i = tid; i < 12 * T; i += blockDim.x) d[i] = raw[i];
+    }
+    // row-wise z-score (process.py:55), rows 0..11 of the chroma plane; the pad rows are filled by the CENS kernel
+    float mn = FLT_MAX;
+    float* o = plane_ptr(feats, b, BPC_CH_CHROMA, T);
+    for (int r = warp; r < 12; r += nw) {
+        double s = 0.0, q = 0.0;
+        for (int t = lane; t < T; t += 32) {
+            const double v = (double)raw[r * T + t];
+            s += v;
+            q += v * v;
+        }
+        s = warp_sum(s);
+        q = warp_sum(q);
+        const ZTerm z = make_zterm(s, q, (double)T);
+        for (int t = lane; t < T; t += 32) {
+            const float v = z(raw[r * T + t]);
+            o[r * T + t] = v;
+            mn = fminf(mn, v);
+        }
+    }
+    mn = block_min(mn, fscratch);
+    if (tid == 0) ws.chroma_min[b * 2 + 0] = mn;
+}
+
+// ----------------------------------------------------------------------------------------------- the kernel
+constexpr int kConsumerSmemFloats = kPlaneRows * kMaxFrames + 40 * kMaxFrames + 120 * kMaxFrames + 64;
+
+__global__ void __launch_bounds__(256) k_spec512_consumers(Geometry g, Tables tb, Workspace ws, float* feats,
+                                                           float* scalars, int32_t* status, float* mel3,
+                                                           int role_base) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ double dscratch[32];
+    __shared__ float fscratch[32];
+    const int b = blockIdx.x;
+    const int role = blockIdx.y + role_base;
+    switch (role) {
+        case 0: role_mel(b, g, tb, ws, feats, mel3, smem, dscratch, fscratch); break;
+        case 1: role_mfcc(b, g, tb, ws, feats, smem, dscratch, fscratch); break;
+        case 2: role_gammatone(b, g, tb, ws, feats, smem, dscratch, fscratch); break;
+        default: role_chroma_stft(b, g, tb, ws, feats, scalars, status, smem, dscratch, fscratch); break;
+    }
+}
+
+static void set_consumer_smem() {
+    static bool done = false;
+    if (!done) {
+        cudaFuncSetAttribute(k_spec512_consumers, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kConsumerSmemFloats * (int)sizeof(float));
+        done = true;
+    }
+}
+
+void launch_spec512_consumers(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
+                              float* scalars, int32_t* status, bool with_chroma, cudaStream_t st) {
+    set_consumer_smem();
+    dim3 grid(n, with_chroma ? 4 : 3);
+    k_spec512_consumers<<<grid, 256, kConsumerSmemFloats * sizeof(float), st>>>(g, tb, ws, feats, scalars, status,
+                                                                                 nullptr, 0);
+    note_launch();
+}
+
+void launch_logmel_only(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* mel3, cudaStream_t st) {
+    set_consumer_smem();
+    dim3 grid(n, 1);
+    k_spec512_consumers<<<grid, 256, kConsumerSmemFloats * sizeof(float), st>>>(g, tb, ws, nullptr, nullptr, nullptr,
+                                                                                 mel3, 0);
+    note_launch();
+}
+
+// ------------------------------------------------------- config-2 stage output: power_to_db(|X|^2, ref=max) [257, T]
+__global__ void __launch_bounds__(256) k_stft_db(Geometry g, const float* __restrict__ mag, float* __restrict__ out) {
+    extern __shared__ __align__(16) float sP[];    // [257*T]
+    __shared__ float fscratch[32];
+    const int b = blockIdx.x, T = g.T;
+    const float* mag_b = mag + (size_t)b * T * kMagStride;
+    for (int idx = threadIdx.x; idx < 257 * T; idx += blockDim.x) {
+        const int k = idx % 257, t = idx / 257;
+        const float v = __ldg(mag_b + (size_t)t * kMagStride + k);
+        sP[k * T + t] = __fmul_rn(v, v);
+    }
+    __syncthreads();
+    power_to_db_inplace(sP, 257 * T, true, fscratch);
+    float* o = out + (size_t)b * 257 * T;
+    for (int i = threadIdx.x; i < 257 * T; i += blockDim.x) o[i] = sP[i];
+}
+
+void launch_stft_db(int n, const Geometry& g, const Workspace& ws, float* stft_db, cudaStream_t st) {
+    const int bytes = 257 * g.T * (int)sizeof(float);
+    static bool done = false;
+    if (!done) {
+        cudaFuncSetAttribute(k_stft_db, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * kMaxFrames * 4);
+        done = true;
+    }
+    k_stft_db<<<n, 256, bytes, st>>>(g, ws.mag512, stft_db);
+    note_launch();
+}
+
+}  // namespace bpc

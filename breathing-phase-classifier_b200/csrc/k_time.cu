@@ -1,0 +1,556 @@
+// Time-domain scalar features (methods.py:48-114), one CTA per segment:
+//   k_time_basic  rms / zcr frame statistics (idx 0-7), skew / kurtosis / percentiles of |y| (idx 29-32), status bits
+//   k_autocorr    normalised autocorrelation lags 160 / 320 and first-minimum index over lags < 800 (idx 33-35)
+//   k_hilbert     |hilbert(y)| envelope statistics and scipy.signal.find_peaks count / heights (idx 19-24)
+#include <cmath>
+#include "kernels.cuh"
+#include "fft.cuh"
+
+namespace bpc {
+
+// =============================================================================================== k_time_basic
+struct TimeBasicSmem {
+    float y[kMaxLen];
+    unsigned hist[4][2048];
+    double sq[kMaxFrames + 8];       // per-256-block sum of squares
+    int cz[kMaxFrames + 8];          // per-256-block zero-crossing counts
+    float rms[kMaxFrames];
+    double zcr[kMaxFrames];
+    double dscratch[32];
+    float fscratch[32];
+    unsigned prefix[4];
+    unsigned rank[4];
+    unsigned long long bar;
+};
+
+// numpy.percentile(method='linear') lerp
+__device__ __forceinline__ float lerp_q(float a, float b, double g) {
+    const double da = (double)a, db = (double)b;
+    return (float)(g >= 0.5 ? db - (db - da) * (1.0 - g) : da + (db - da) * g);
+}
+
+__global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y, Geometry g, float* scalars,
+                                                    int32_t* status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TimeBasicSmem& S = *reinterpret_cast<TimeBasicSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x, L = g.L, T = g.T;
+    const float* yb = y + (size_t)b * L;
+    if ((L & 3) == 0 && ((size_t)yb & 15) == 0) {
+        stage_segment_tma(S.y, yb, L, (uint64_t*)&S.bar);
+    } else {
+        for (int i = tid; i < L; i += 256) S.y[i] = yb[i];
+    }
+    __syncthreads();
+
+    // ---- moments (scipy.stats.skew / kurtosis, biased) and input checks
+    double s1 = 0.0;
+    int bad = 0, nonzero = 0;
+    for (int i = tid; i < L; i += 256) {
+        const float v = S.y[i];
+        s1 += (double)v;
+        bad |= !isfinite(v);
+        nonzero |= (v != 0.f);
+    }
+    s1 = block_sum(s1, S.dscratch);
+    bad = __syncthreads_or(bad);
+    nonzero = __syncthreads_or(nonzero);
+    const double mean = s1 / L;
+    double m2 = 0.0, m3 = 0.0, m4 = 0.0;
+    for (int i = tid; i < L; i += 256) {
+        const double d = (double)S.y[i] - mean;
+        const double d2 = d * d;
+        m2 += d2;
+        m3 += d2 * d;
+        m4 += d2 * d2;
+    }
+    m2 = block_sum(m2, S.dscratch) / L;
+    m3 = block_sum(m3, S.dscratch) / L;
+    m4 = block_sum(m4, S.dscratch) / L;
+    float* sc = scalars + (size_t)b * g.nscal;
+    if (tid == 0) {
+        sc[29] = (float)(m3 / (m2 * sqrt(m2)));
+        sc[30] = (float)(m4 / (m2 * m2) - 3.0);
+        if (status) {
+            unsigned f = 0;
+            if (bad) f |= BPC_SEG_NONFINITE;
+            if (!nonzero) f |= BPC_SEG_SILENT;
+            if (f) atomicOr((unsigned int*)&status[b], f);
+        }
+    }
+
+    // ---- per-256-sample block sums: squares (rms) and zero crossings (zcr)
+    const int nblk = (L + 255) / 256;
+    for (int j = warp; j < nblk; j += 8) {
+        double sq = 0.0;
+        int cz = 0;
+        for (int i = 256 * j + lane; i < 256 * j + 256 && i < L; i += 32) {
+            const float v = S.y[i];
+            sq += (double)__fmul_rn(v, v);
+            if (i >= 1) {
+                // librosa.zero_crossings: values within +-1e-10 are clipped to +0, then signbit comparison
+                const float a = fabsf(v) <= 1e-10f ? 0.f : v;
+                const float pv = S.y[i - 1];
+                const float p = fabsf(pv) <= 1e-10f ? 0.f : pv;
+                cz += (signbit(a) != signbit(p)) ? 1 : 0;
+            }
+        }
+        sq = warp_sum(sq);
+        cz = warp_sum(cz);
+        if (lane == 0) { S.sq[j] = sq; S.cz[j] = cz; }
+    }
+    __syncthreads();
+    // frame t covers y[256 (t-4), 256 (t+4)) (frame_length 2048 centred, hop 256)
+    for (int t = tid; t < T; t += 256) {
+        double sq = 0.0;
+        int cz = 0;
+        for (int j = t - 4; j < t + 4; ++j)
+            if (j >= 0 && j < nblk) { sq += S.sq[j]; cz += S.cz[j]; }
+        const int first = 256 * (t - 4);                  // first sample of the frame never counts as a crossing
+        if (first >= 1 && first < L) {
+            const float v = S.y[first], pv = S.y[first - 1];
+            const float a = fabsf(v) <= 1e-10f ? 0.f : v, p = fabsf(pv) <= 1e-10f ? 0.f : pv;
+            cz -= (signbit(a) != signbit(p)) ? 1 : 0;
+        }
+        S.rms[t] = sqrtf((float)(sq / 2048.0));
+        S.zcr[t] = (double)cz / 2048.0;
+    }
+    __syncthreads();
+    if (warp < 2) {
+        double s = 0.0, q = 0.0, mx = -1e300, mn = 1e300;
+        for (int t = lane; t < T; t += 32) {
+            const double v = warp == 0 ? (double)S.rms[t] : S.zcr[t];
+            s += v;
+            q += v * v;
+            mx = fmax(mx, v);
+            mn = fmin(mn, v);
+        }
+        s = warp_sum(s);
+        q = warp_sum(q);
+        mx = warp_max(mx);
+        mn = warp_min(mn);
+        if (lane == 0) {
+            const double mu = s / T;
+            const double sd = sqrt(fmax(0.0, q / T - mu * mu));
+            float* o = sc + (warp == 0 ? 0 : 4);
+            o[0] = (float)mu; o[1] = (float)sd; o[2] = (float)mx; o[3] = (float)mn;
+        }
+    }
+
+    // ---- np.percentile(|y|, 90 / 10): exact order statistics by 3-pass radix select on the float bit patterns
+    const double v90 = 0.9 * (double)(L - 1), v10 = 0.1 * (double)(L - 1);
+    if (tid == 0) {
+        S.rank[0] = (unsigned)floor(v90); S.rank[1] = min((unsigned)floor(v90) + 1u, (unsigned)(L - 1));
+        S.rank[2] = (unsigned)floor(v10); S.rank[3] = min((unsigned)floor(v10) + 1u, (unsigned)(L - 1));
+        S.prefix[0] = S.prefix[1] = S.prefix[2] = S.prefix[3] = 0u;
+    }
+    const int shifts[3] = {21, 10, 0};
+    const unsigned masks[3] = {0x7ffu, 0x7ffu, 0x3ffu};
+    for (int pass = 0; pass < 3; ++pass) {
+        for (int i = tid; i < 4 * 2048; i += 256) (&S.hist[0][0])[i] = 0u;
+        __syncthreads();
+        const unsigned p0 = S.prefix[0], p1 = S.prefix[1], p2 = S.prefix[2], p3 = S.prefix[3];
+        const unsigned hi_mask = pass == 0 ? 0u : (pass == 1 ? 0xffe00000u : 0xfffffc00u);
+        for (int i = tid; i < L; i += 256) {
+            const unsigned key = __float_as_uint(fabsf(S.y[i]));
+            const unsigned hi = key & hi_mask, d = (key >> shifts[pass]) & masks[pass];
+            if (hi == p0) atomicAdd(&S.hist[0][d], 1u);
+            if (hi == p1) atomicAdd(&S.hist[1][d], 1u);
+            if (hi == p2) atomicAdd(&S.hist[2][d], 1u);
+            if (hi == p3) atomicAdd(&S.hist[3][d], 1u);
+        }
+        __syncthreads();
+        if (warp < 4) {
+            // find the digit whose cumulative count first exceeds rank; 64 bins per lane
+            const unsigned* h = S.hist[warp];
+            const int nb = (int)masks[pass] + 1, per = nb / 32;
+            unsigned local = 0;
+            for (int i = 0; i < per; ++i) local += h[lane * per + i];
+            unsigned incl = local;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            const unsigned excl = incl - local;
+            const unsigned r = S.rank[warp];
+            const bool mine = r >= excl && r < incl;
+            if (mine) {
+                unsigned c = excl;
+                for (int i = 0; i < per; ++i) {
+                    const unsigned hv = h[lane * per + i];
+                    if (r < c + hv) {
+                        S.prefix[warp] |= ((unsigned)(lane * per + i)) << shifts[pass];
+                        S.rank[warp] = r - c;
+                        break;
+                    }
+                    c += hv;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const float a90 = __uint_as_float(S.prefix[0]), b90 = __uint_as_float(S.prefix[1]);
+        const float a10 = __uint_as_float(S.prefix[2]), b10 = __uint_as_float(S.prefix[3]);
+        sc[31] = lerp_q(a90, b90, v90 - floor(v90));
+        sc[32] = lerp_q(a10, b10, v10 - floor(v10));
+    }
+}
+
+void launch_time_scalars(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws,
+                         float* scalars, int32_t* status, cudaStream_t st);
+
+// ================================================================================================= k_autocorr
+// r[k] = sum_n y[n] y[n+k], k < 800 (methods.py:105-112; the reference computes all 2L-1 lags with np.correlate).
+// Blocked Wiener-Khinchin in FP64: with A_b = y[1024 b : 1024 b + 1024] zero-padded to 2048 and F_b = rfft(A_b),
+//   R[k] = sum_b conj(F_b[k]) * (F_b[k] + (-1)^k F_{b+1}[k]),   r = irfft(R)[0:1024]  (exact linear correlation).
+struct AutocorrSmem {
+    double2 fbuf[1024];
+    double2 tw[1024];
+    double2 prev[1025];
+    double2 R[1025];
+    double r[1024];
+    double dscratch[32];
+    int iscratch[32];
+};
+
+__global__ void __launch_bounds__(256) k_autocorr(const float* __restrict__ y, Geometry g, Tables tb, Workspace ws,
+                                                  float* scalars) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    AutocorrSmem& S = *reinterpret_cast<AutocorrSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x, L = g.L;
+    const float* yb = y + (size_t)b * L;
+    for (int j = tid; j < 1024; j += 256) S.tw[j] = tb.tw1024[j];
+    for (int k = tid; k < 1025; k += 256) { S.R[k] = make_double2(0.0, 0.0); S.prev[k] = make_double2(0.0, 0.0); }
+    __syncthreads();
+    const int nblk = (L + 1023) / 1024;
+    for (int blk = 0; blk < nblk; ++blk) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = tid + 256 * i;
+            double2 v = make_double2(0.0, 0.0);
+            if (m < 512) {
+                const int gi = blk * 1024 + 2 * m;
+                v.x = gi < L ? (double)__ldg(yb + gi) : 0.0;
+                v.y = gi + 1 < L ? (double)__ldg(yb + gi + 1) : 0.0;
+            }
+            S.fbuf[m] = v;
+        }
+        __syncthreads();
+        fft_r4_dif<5, 256>(S.fbuf, S.tw, tid, SyncBlock());
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int k = tid + 256 * i;
+            if (k <= 1024) {
+                const double2 F = rfft_bin<5>(S.fbuf, tb.ptw2048, k);
+                const double2 P = S.prev[k];
+                const double sgn = (k & 1) ? -1.0 : 1.0;
+                double2 acc = S.R[k];
+                // conj(P) * sgn * F  +  conj(F) * F
+                acc.x += sgn * (P.x * F.x + P.y * F.y) + (F.x * F.x + F.y * F.y);
+                acc.y += sgn * (P.x * F.y - P.y * F.x);
+                S.R[k] = acc;
+                S.prev[k] = F;
+            }
+        }
+        __syncthreads();
+    }
+    // irfft(R, 2048) through one complex FFT-1024: Z[k] = E[k] + i O[k], feed conj(Z) to the forward transform
+    for (int k = tid; k < 1024; k += 256) {
+        const double2 xk = S.R[k], xn = S.R[1024 - k];
+        const double2 e = make_double2(0.5 * (xk.x + xn.x), 0.5 * (xk.y - xn.y));
+        const double2 d = make_double2(0.5 * (xk.x - xn.x), 0.5 * (xk.y + xn.y));
+        const double2 w = tb.ptw2048[k];                       // exp(-i th); need exp(+i th) = conj
+        const double2 o = make_double2(d.x * w.x + d.y * w.y, d.y * w.x - d.x * w.y);
+        const double2 z = make_double2(e.x - o.y, e.y + o.x);  // e + i o
+        S.fbuf[k] = make_double2(z.x, -z.y);
+    }
+    __syncthreads();
+    fft_r4_dif<5, 256>(S.fbuf, S.tw, tid, SyncBlock());
+    for (int m = tid; m < 512; m += 256) {
+        const double2 o = S.fbuf[rev4<5>(m)];
+        S.r[2 * m] = o.x / 1024.0;
+        S.r[2 * m + 1] = -o.y / 1024.0;
+    }
+    __syncthreads();
+    // normalise by r[0]; first index of the minimum over lags < sr // 20 (np.argmin; NaN -> first NaN)
+    const double r0 = S.r[0];
+    const int nl = 800 < L ? 800 : L / 2;
+    double best = 1e300;
+    int bi = 0x7fffffff;
+    for (int k = tid; k < nl; k += 256) {
+        const float v = (float)(S.r[k] / r0);
+        if ((double)v < best) { best = (double)v; bi = k; }
+    }
+    // block argmin (value, then smallest index)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { S.dscratch[warp] = best; S.iscratch[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (S.dscratch[w] < best || (S.dscratch[w] == best && S.iscratch[w] < bi)) { best = S.dscratch[w]; bi = S.iscratch[w]; }
+        if (!(r0 == r0) || r0 == 0.0 || bi == 0x7fffffff) bi = 0;          // all-NaN row: argmin returns 0
+        float* sc = scalars + (size_t)b * g.nscal;
+        sc[33] = (float)(S.r[160] / r0);
+        sc[34] = (float)(S.r[320] / r0);
+        sc[35] = (float)((double)bi / 16000.0);
+        ws.ints[b * 2 + 1] = bi;
+    }
+}
+
+// ================================================================================================== k_hilbert
+// scipy.signal.hilbert(y) for L = 16000 through two complex FFT-8000 (8000 = 4^3 * 5^3) in FP64:
+//   forward: real-FFT split of y;  G[k] = -i Y[k] (0 < k < 8000), G[0] = G[8000] = 0;  h = irfft(G).
+// The forward transform is decimation-in-frequency (natural in, digit-reversed out), the inverse runs the transposed
+// (decimation-in-time) network on the data where it lies, so no reordering pass is needed.
+constexpr int kHN = 8000;
+constexpr int kHilbertThreads = 512;
+
+template <int R>
+__device__ __forceinline__ void dft_small(double2* a) {
+    if (R == 4) {
+        const double2 b0 = cadd(a[0], a[2]), b1 = csub(a[0], a[2]), b2 = cadd(a[1], a[3]);
+        const double2 d = csub(a[1], a[3]);
+        const double2 b3 = make_double2(d.y, -d.x);
+        a[0] = cadd(b0, b2); a[1] = cadd(b1, b3); a[2] = csub(b0, b2); a[3] = csub(b1, b3);
+    } else {
+        const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
+        const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
+        const double2 t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]), t3 = csub(a[1], a[4]), t4 = csub(a[2], a[3]);
+        const double2 m1 = make_double2(a[0].x + c1 * t1.x + c2 * t2.x, a[0].y + c1 * t1.y + c2 * t2.y);
+        const double2 m2 = make_double2(a[0].x + c2 * t1.x + c1 * t2.x, a[0].y + c2 * t1.y + c1 * t2.y);
+        const double2 n1 = make_double2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+        const double2 n2 = make_double2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+        a[0] = make_double2(a[0].x + t1.x + t2.x, a[0].y + t1.y + t2.y);
+        a[1] = make_double2(m1.x + n1.y, m1.y - n1.x);      // m1 - i n1
+        a[4] = make_double2(m1.x - n1.y, m1.y + n1.x);      // m1 + i n1
+        a[2] = make_double2(m2.x + n2.y, m2.y - n2.x);
+        a[3] = make_double2(m2.x - n2.y, m2.y + n2.x);
+    }
+}
+
+// one pass over all N/R butterflies with the given span; DIF: twiddle after the small DFT, DIT: before.
+template <int R, bool kDit>
+__device__ __forceinline__ void mixed_pass(double2* x, int span, const double2* __restrict__ tw, int tid) {
+    const int q = span / R, ts = kHN / span;
+    for (int j = tid; j < kHN / R; j += kHilbertThreads) {
+        const int blk = j / q, pos = j - blk * q;
+        const int base = blk * span + pos;
+        double2 a[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) a[r] = x[base + r * q];
+        if (kDit && pos != 0) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) a[r] = cmul(a[r], tw[r * pos * ts]);
+        }
+        dft_small<R>(a);
+        if (!kDit && pos != 0) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) a[r] = cmul(a[r], tw[r * pos * ts]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[base + r * q] = a[r];
+    }
+    __syncthreads();
+}
+
+// position of output bin k after the DIF passes with radices 5,5,5,4,4,4 (spans 8000,1600,320,64,16,4)
+__device__ __forceinline__ int hilbert_pos(int k) {
+    int p = 0, s = kHN;
+    int d;
+    d = k % 5; k /= 5; s /= 5; p += d * s;
+    d = k % 5; k /= 5; s /= 5; p += d * s;
+    d = k % 5; k /= 5; s /= 5; p += d * s;
+    d = k & 3; k >>= 2; s >>= 2; p += d * s;
+    d = k & 3; k >>= 2; s >>= 2; p += d * s;
+    p += k;
+    return p;
+}
+
+struct HilbertTail {
+    double dscratch[32];
+    float fscratch[32];
+    int iscratch[32];
+    float best_v;
+    int best_i;
+};
+
+__global__ void __launch_bounds__(kHilbertThreads) k_hilbert(const float* __restrict__ y, Geometry g, Tables tb,
+                                                              Workspace ws, float* scalars) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* X = reinterpret_cast<double2*>(smem_raw);                       // [8000]
+    HilbertTail& S = *reinterpret_cast<HilbertTail*>(smem_raw + sizeof(double2) * kHN);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x, L = g.L;                                        // L == 16000 (checked on the host)
+    const float* yb = y + (size_t)b * L;
+    for (int m = tid; m < kHN; m += kHilbertThreads) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(yb) + m);
+        X[m] = make_double2((double)v.x, (double)v.y);
+    }
+    __syncthreads();
+    const double2* tw = tb.tw8000;
+    mixed_pass<5, false>(X, 8000, tw, tid);
+    mixed_pass<5, false>(X, 1600, tw, tid);
+    mixed_pass<5, false>(X, 320, tw, tid);
+    mixed_pass<4, false>(X, 64, tw, tid);
+    mixed_pass<4, false>(X, 16, tw, tid);
+    mixed_pass<4, false>(X, 4, tw, tid);
+    // pairs (k, N-k): real-FFT split -> Y[k], Y[N-k]; G = -i Y; inverse split -> conj(Z), written back in place
+    for (int k = tid; k <= kHN / 2; k += kHilbertThreads) {
+        const int kn = (kHN - k) % kHN;
+        const int pk = hilbert_pos(k), pn = hilbert_pos(kn);
+        const double2 zk = X[pk], zn = X[pn];
+        const double2 w = tb.ptw16000[k];                                      // exp(-2 pi i k / 16000)
+        // Y[k] = E + w O ; Y[N-k] = conj(E) - conj(w) conj(O) = conj(E - w O)
+        const double2 e = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));
+        const double2 o = make_double2(0.5 * (zk.y + zn.y), -0.5 * (zk.x - zn.x));
+        const double2 wo = cmul(w, o);
+        double2 yk = cadd(e, wo);
+        double2 yn = cconj(csub(e, wo));
+        // G = -i Y on 0 < k < N (bins k and N-k of the half spectrum), 0 at k = 0 and k = N (both live in pair k = 0)
+        double2 gk = make_double2(yk.y, -yk.x), gn = make_double2(yn.y, -yn.x);
+        if (k == 0) { gk = make_double2(0.0, 0.0); gn = make_double2(0.0, 0.0); }
+        // for k == 0: X_half[0] = gk, X_half[N] = gn (the "N-k" partner of bin 0 is bin N)
+        // inverse split: E' = (G[k] + conj(G[N-k]))/2, O' = (G[k] - conj(G[N-k]))/2 * conj(w), Z = E' + i O'
+        const double2 e2 = make_double2(0.5 * (gk.x + gn.x), 0.5 * (gk.y - gn.y));
+        const double2 d2 = make_double2(0.5 * (gk.x - gn.x), 0.5 * (gk.y + gn.y));
+        const double2 o2 = cmul(d2, cconj(w));
+        const double2 z = make_double2(e2.x - o2.y, e2.y + o2.x);
+        // partner bin: Z[N-k] = conj(E') + i * conj(O') * (-1) ... derive from the same quantities:
+        // E'[N-k] = conj(E'[k]); O'[N-k] = (G[N-k] - conj(G[k]))/2 * conj(w[N-k]) with w[N-k] = -conj(w[k])
+        const double2 dn = make_double2(0.5 * (gn.x - gk.x), 0.5 * (gn.y + gk.y));
+        const double2 on = cmul(dn, make_double2(-w.x, -w.y));                 // conj(w[N-k]) = -w[k]
+        const double2 zn2 = make_double2(e2.x - on.y, -e2.y + on.x);
+        X[pk] = cconj(z);
+        if (kn != k && k != 0) X[pn] = cconj(zn2);
+    }
+    __syncthreads();
+    mixed_pass<4, true>(X, 4, tw, tid);
+    mixed_pass<4, true>(X, 16, tw, tid);
+    mixed_pass<4, true>(X, 64, tw, tid);
+    mixed_pass<5, true>(X, 320, tw, tid);
+    mixed_pass<5, true>(X, 1600, tw, tid);
+    mixed_pass<5, true>(X, 8000, tw, tid);
+    // h[2m] = Re(conj(out[m])) / N, h[2m+1] = Im(conj(out[m])) / N; envelope = |y + i h| (float32 like complex64 abs)
+    float* env = reinterpret_cast<float*>(smem_raw);                           // [16000], first half of X's storage
+    unsigned char* cand = smem_raw + sizeof(float) * 16000;                    // [16000] flags, second half
+    {
+        float e0[16], e1[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int m = tid + kHilbertThreads * i;
+            if (m < kHN) {
+                const double2 o = X[m];
+                const float2 v = __ldg(reinterpret_cast<const float2*>(yb) + m);
+                const double h0 = o.x / (double)kHN, h1 = -o.y / (double)kHN;
+                e0[i] = (float)sqrt((double)v.x * (double)v.x + h0 * h0);
+                e1[i] = (float)sqrt((double)v.y * (double)v.y + h1 * h1);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int m = tid + kHilbertThreads * i;
+            if (m < kHN) { env[2 * m] = e0[i]; env[2 * m + 1] = e1[i]; }
+        }
+    }
+    __syncthreads();
+    double s = 0.0, q = 0.0;
+    for (int i = tid; i < L; i += kHilbertThreads) { const double v = (double)env[i]; s += v; q += v * v; }
+    s = block_sum(s, S.dscratch);
+    q = block_sum(q, S.dscratch);
+    const float emean = (float)(s / L);
+    const float estd = (float)sqrt(fmax(0.0, q / L - (s / L) * (s / L)));
+    // scipy.signal.find_peaks(env, height=emean, distance=1600): local maxima (plateau mid-points), height filter
+    for (int i = tid; i < L; i += kHilbertThreads) cand[i] = 0;
+    __syncthreads();
+    for (int i = tid + 1; i < L - 1; i += kHilbertThreads) {
+        if (env[i - 1] < env[i]) {
+            int ahead = i + 1;
+            while (ahead < L - 1 && env[ahead] == env[i]) ++ahead;
+            if (env[ahead] < env[i]) {
+                const int mid = (i + ahead - 1) / 2;
+                if (env[mid] >= emean) cand[mid] = 1;
+            }
+        }
+    }
+    __syncthreads();
+    int n_peaks = 0;
+    double hs = 0.0, hq = 0.0;
+    for (int iter = 0; iter < 64; ++iter) {
+        // highest-priority remaining candidate (ties: later position first, as a stable ascending argsort would)
+        float bv = -1.f;
+        int bi = -1;
+        for (int i = tid; i < L; i += kHilbertThreads)
+            if (cand[i] && (env[i] > bv || (env[i] == bv && i > bi))) { bv = env[i]; bi = i; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > bv || (ob == bv && oi > bi)) { bv = ob; bi = oi; }
+        }
+        if (lane == 0) { S.fscratch[warp] = bv; S.iscratch[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < kHilbertThreads / 32; ++w)
+                if (S.fscratch[w] > bv || (S.fscratch[w] == bv && S.iscratch[w] > bi)) { bv = S.fscratch[w]; bi = S.iscratch[w]; }
+            S.best_v = bv;
+            S.best_i = bi;
+        }
+        __syncthreads();
+        const int pi = S.best_i;
+        if (pi < 0) break;
+        const float pv = S.best_v;
+        ++n_peaks;
+        hs += (double)pv;
+        hq += (double)pv * (double)pv;
+        for (int i = max(0, pi - 1599) + tid; i <= min(L - 1, pi + 1599); i += kHilbertThreads) cand[i] = 0;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        float* sc = scalars + (size_t)b * g.nscal;
+        sc[19] = emean;
+        sc[20] = estd;
+        sc[21] = __fdiv_rn(emean, __fadd_rn(estd, 1e-8f));
+        sc[22] = (float)n_peaks;
+        const double hm = n_peaks > 0 ? hs / n_peaks : 0.0;
+        sc[23] = (float)hm;
+        sc[24] = n_peaks > 1 ? (float)sqrt(fmax(0.0, hq / n_peaks - hm * hm)) : 0.f;
+        ws.ints[b * 2 + 0] = n_peaks;
+    }
+}
+
+// ==================================================================================================== launchers
+void launch_time_scalars(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws,
+                         float* scalars, int32_t* status, cudaStream_t st) {
+    static bool done = false;
+    if (!done) {
+        cudaFuncSetAttribute(k_time_basic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TimeBasicSmem));
+        cudaFuncSetAttribute(k_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AutocorrSmem));
+        done = true;
+    }
+    k_time_basic<<<n, 256, sizeof(TimeBasicSmem), st>>>(y, g, scalars, status);
+    k_autocorr<<<n, 256, sizeof(AutocorrSmem), st>>>(y, g, tb, ws, scalars);
+    note_launch(2);
+}
+
+void launch_hilbert(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* scalars,
+                    cudaStream_t st) {
+    const int bytes = (int)(sizeof(double2) * kHN + sizeof(HilbertTail));
+    static bool done = false;
+    if (!done) {
+        cudaFuncSetAttribute(k_hilbert, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        done = true;
+    }
+    k_hilbert<<<n, kHilbertThreads, bytes, st>>>(y, g, tb, ws, scalars);
+    note_launch();
+}
+
+}  // namespace bpc

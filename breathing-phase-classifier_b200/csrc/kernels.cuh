@@ -1,0 +1,103 @@
+// Device-side table / workspace descriptors and kernel launchers shared between api.cu and the k_*.cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "common.cuh"
+#include "../../include/bpc.h"
+
+namespace bpc {
+
+struct BankDev {            // band-form triangular filterbank (see tables.hpp::SparseBank)
+    const int* start;       // [rows]
+    const int* count;       // [rows]
+    const float* w;         // [rows, width]
+    int rows, width;
+};
+
+struct Tables {
+    // FFT
+    const double* hann512;        // [512]
+    const double* hann2048;       // [2048]
+    const double2* tw256;         // exp(-2 pi i j / 256), j < 256
+    const double2* tw1024;        // exp(-2 pi i j / 1024), j < 1024
+    const double2* ptw512;        // exp(-2 pi i k / 512),  k <= 256
+    const double2* ptw2048;       // exp(-2 pi i k / 2048), k <= 1024
+    // filterbanks
+    BankDev mel_a, mel_b, mel_c, mel_d;
+    const float* dct_mel;         // [40, 128]
+    const float* dct_time;        // [T, T]
+    const float* chroma;          // [100, 12, 257]
+    const double* hist_edges;     // [101]
+    // CQT
+    const int16_t* cqt_col;       // [100, 36, W]
+    const float* cqt_re;          // [100, 36, W]
+    const float* cqt_im;          // [100, 36, W]
+    const double* cqt_sqrt_len;   // [100, 252]
+    const double* halfband;       // [127]
+    // LPC
+    const double* hamming400;     // [400]
+    // Hilbert (FFT-8000 = 4^3 * 5^3)
+    const double2* tw8000;        // exp(-2 pi i j / 8000), j < 8000
+    const double2* ptw16000;      // exp(-2 pi i k / 16000), k <= 8000
+    // tempogram
+    const double* hann384;        // [384]
+};
+
+struct Workspace {            // per chunk of `cap` segments
+    int cap;
+    float* y;                 // [cap, L]   float32 waveform after pad_or_truncate (only when ingest is needed)
+    float* mag512;            // [cap, T, kMagStride]
+    float* mag2048_even;      // [cap, 1025, 32]  |STFT2048| of the hop-512 frames (rolloff + tuning-36)
+    int* tuning;              // [cap, 2]   tuning bin for 12 / 36 bins per octave
+    float* chroma_min;        // [cap, 2]   min of the normalised chroma_stft / chroma_cens rows
+    int* ints;                // [cap, 2]   n_peaks, first-min index
+    // debug (raw, un-normalised stages of the last chunk)
+    float* dbg_mel_db;        // [cap, 128, T]
+    float* dbg_mfcc;          // [cap, 120, T]
+    float* dbg_gam;           // [cap, 64, T]
+    float* dbg_mod;           // [cap, 40, T]
+    float* dbg_chroma_stft;   // [cap, 12, T]
+    float* dbg_chroma_cens;   // [cap, 12, T]
+    float* dbg_lpc;           // [cap, 12, F]
+    float* dbg_onset;         // [cap, T]
+};
+
+struct Geometry {
+    int L;                    // expected_len
+    int T;                    // frames = L / hop + 1
+    int hop;                  // 256
+    int nscal;                // scalars per segment in the output (36 or padded)
+    int lpc_frames;           // len(range(0, L - 400, 160))
+};
+
+// feats layout: [B, 9, 128, T]; plane pointer of channel c of segment b
+__device__ __forceinline__ float* plane_ptr(float* feats, int b, int c, int T) {
+    return feats + ((size_t)b * 9 + c) * (size_t)kPlaneRows * T;
+}
+
+// ---- launchers (all enqueue on `st`, no sync).  n = segments in this chunk.
+void launch_ingest(const void* wav, int wav_dtype, int64_t L_in, float* y, int n, const Geometry& g, cudaStream_t st);
+void launch_stft512(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, cudaStream_t st);
+void launch_spec512_consumers(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
+                              float* scalars, int32_t* status, bool with_chroma, cudaStream_t st);
+void launch_stft_db(int n, const Geometry& g, const Workspace& ws, float* stft_db, cudaStream_t st);
+void launch_logmel_only(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* mel3, cudaStream_t st);
+void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
+                     float* scalars, cudaStream_t st);
+void launch_even2048(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* scalars,
+                     int32_t* status, cudaStream_t st);
+void launch_time_scalars(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws,
+                         float* scalars, int32_t* status, cudaStream_t st);
+void launch_hilbert(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* scalars,
+                    cudaStream_t st);
+void launch_lpc(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
+                cudaStream_t st);
+void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
+                 cudaStream_t st);
+void launch_stats(int n, const Geometry& g, const float* feats, const float* scalars, double* acc, cudaStream_t st);
+void launch_pad_scalars(int n, const Geometry& g, float* scalars, cudaStream_t st);
+
+int64_t launches_issued();   // process-wide counter bumped by every launcher
+void note_launch(int n = 1);
+
+}  // namespace bpc

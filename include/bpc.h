@@ -1,0 +1,139 @@
+/*
+ * bpc.h -- C ABI of libbpc_b200.so: the B200-native `--precompute` feature-extraction path of
+ * dohyeoplim/breathing-phase-classifier (reference paths below are relative to /root/reference/).
+ *
+ * The reference has no FFI: the path sits behind three Python functions and an on-disk format.  This ABI is what a
+ * ctypes binding of those functions needs:
+ *
+ *   src/precompute/process.py:25-108   process_and_save_npz((file_id, wav_path, target_dir))   -> bpc_precompute*
+ *   src/precompute/core.py:19-45       process_dataset_threaded(df, audio_dir, target_dir, ..) -> bpc_precompute* (batched)
+ *   src/precompute/methods.py:24-28    pad_or_truncate                                          -> done on device (L_in vs expected_len)
+ *   src/precompute/methods.py:48-114   extract_enhanced_scalar_features(y, sr) -> f32[36]       -> `scalars` output
+ *   src/precompute/methods.py:116-143  extract_lpc / gammatone / spectral_modulation features   -> bpc_debug_copy (raw stages)
+ *   src/precompute/process.py:12-23    module constants                                         -> bpc_params
+ *   src/dataset.py:8,25-26,48          consumer contract: sorted-key stacking                    -> feats layout [B,9,128,T]
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no exceptions cross the ABI.  Every function returns 0 on success or a negative
+ *     bpc_status code; bpc_last_error() gives the message.
+ *   - per-segment problems never fail the call (reference: process.py:107-108 returns (id, False, err)); they are
+ *     reported as bit flags in `status[B]` (0 = ok).
+ *   - a handle owns all constant tables and workspaces (allocated once in bpc_create).  Calls on one handle must be
+ *     serialised by the caller; different handles are independent.  Device entry points enqueue on the given
+ *     cudaStream_t and do not synchronise.
+ *   - there is NO CPU fallback: without a CUDA device bpc_create fails with BPC_ERR_CUDA.
+ */
+#ifndef BPC_B200_H
+#define BPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPC_ABI_VERSION 1
+
+/* feats channel order = sorted .npz keys (dataset.py:26) */
+enum bpc_channel {
+    BPC_CH_CHROMA = 0, BPC_CH_GAMMATONE = 1, BPC_CH_LPC = 2, BPC_CH_MEL = 3, BPC_CH_MEL_DELTA = 4,
+    BPC_CH_MEL_DELTA2 = 5, BPC_CH_MFCC = 6, BPC_CH_MOD_SPEC = 7, BPC_CH_TEMPOGRAM = 8, BPC_NUM_CHANNELS = 9
+};
+#define BPC_NUM_SCALARS 36   /* methods.py:54-112 appends 8+11+6+4+4+3 values */
+#define BPC_PLANE_ROWS 128   /* N_MELS, process.py:15 */
+
+enum bpc_wav_dtype { BPC_WAV_F32 = 0, BPC_WAV_PCM16 = 1 };
+
+enum bpc_status {
+    BPC_OK = 0,
+    BPC_ERR_ARG = -1,          /* bad argument / unsupported parameter combination */
+    BPC_ERR_CUDA = -2,         /* CUDA runtime error (message has the cudaError string) */
+    BPC_ERR_ALLOC = -3,
+    BPC_ERR_UNSUPPORTED = -4,  /* e.g. expected_len beyond what this build's kernels hold on-chip */
+    BPC_ERR_NCCL = -5
+};
+
+/* per-segment status bits */
+#define BPC_SEG_NONFINITE      1u   /* input had NaN/Inf */
+#define BPC_SEG_TUNING_EMPTY   2u   /* pitch_tuning saw an empty frequency set -> tuning 0.0 (librosa warns) */
+#define BPC_SEG_CAND_OVERFLOW  4u   /* more piptrack candidates than the on-chip list holds (results for chroma invalid) */
+#define BPC_SEG_SILENT         8u   /* all-zero segment */
+
+/* process.py:12-23 / methods.py:10-22 module constants */
+typedef struct bpc_params {
+    int32_t sr;            /* 16000 */
+    int32_t n_fft;         /* 512   */
+    int32_t hop;           /* 256   */
+    int32_t n_mels;        /* 128   */
+    int32_t n_mfcc;        /* 40    */
+    float   fmax;          /* 4500  */
+    int32_t n_gammatone;   /* 64    */
+    int32_t n_lpc;         /* 12    */
+    int32_t expected_len;  /* int(SR * DURATION) = 16000 */
+    int32_t pad_scalars_to;/* 0 = emit the reference's 36 scalars; 39 = append zeros (README's "39") */
+} bpc_params;
+
+typedef struct bpc_handle bpc_handle;
+
+int  bpc_abi_version(void);
+void bpc_default_params(bpc_params* p);
+/* frames per segment: expected_len / hop + 1 (process.py:30) */
+int  bpc_num_frames(const bpc_params* p);
+/* number of scalars written per segment (36 or pad_scalars_to) */
+int  bpc_num_scalars(const bpc_params* p);
+
+/* max_batch: largest B a single call may pass; workspaces are sized for an internal chunk, not for max_batch. */
+int  bpc_create(bpc_handle** out, const bpc_params* p, int device, int64_t max_batch);
+void bpc_destroy(bpc_handle* h);
+const char* bpc_last_error(const bpc_handle* h);   /* h may be NULL: last error of a failed bpc_create */
+
+/* Full path, device buffers.  wav: [B, L_in] (float32 or int16), feats: [B, 9, 128, T] float32,
+ * scalars: [B, bpc_num_scalars] float32, status: [B] int32 (may be NULL).  L_in != expected_len is truncated / zero
+ * padded on device (methods.py:24-28). */
+int  bpc_precompute(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in,
+                    float* feats, float* scalars, int32_t* status, void* stream);
+
+/* Same, HOST buffers (pageable or pinned): chunks are staged through pinned memory, H2D / compute / D2H overlapped on
+ * internal streams; returns after the results are in the host buffers.  This is the call the Python mirror of
+ * process_dataset_threaded makes (core.py:19-45). */
+int  bpc_precompute_host(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in,
+                         float* feats, float* scalars, int32_t* status);
+
+/* BASELINE config 2 stage: log-power STFT (power_to_db(|X|^2, ref=max), [B, 1+n_fft/2, T], may be NULL) and the
+ * normalised mel / mel_delta / mel_delta2 planes ([B, 3, 128, T]).  Device buffers. */
+int  bpc_stage_logmel(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in,
+                      float* stft_db, float* mel3, void* stream);
+
+/* Dataset-level statistics accumulated over every bpc_precompute* call since the last reset:
+ * stats[(9 + nscal)][5] doubles = {count, sum, sum of squares, min, max}, first the 9 channels (sorted order, over all
+ * 128*T values of each plane), then each scalar.  Host output.  bpc_channel_stats_device returns the device pointer
+ * of the same accumulator so a caller can all-reduce it (NCCL sum over cols 0-2, min col 3, max col 4). */
+int  bpc_channel_stats(bpc_handle* h, double* stats_host);
+int  bpc_channel_stats_device(bpc_handle* h, double** stats_dev, int64_t* n_rows);
+int  bpc_channel_stats_reset(bpc_handle* h);
+
+/* Raw (un-normalised) intermediates of the LAST chunk processed, for parity tests.  `what`:
+ *   "mag512" [n,T,260] |STFT512| (k fastest, 257 valid)      "mel_db" [n,128,T]         "mfcc_raw" [n,120,T]
+ *   "gammatone_raw" [n,64,T]   "mod_spec_raw" [n,40,T]        "chroma_stft_raw" [n,12,T] "chroma_cens_raw" [n,12,T]
+ *   "lpc_raw" [n,12,F]         "onset_env" [n,T]              "tuning" [n,2] int32 (bin index 0..99 for 12 / 36 bpo)
+ *   "ints" [n,2] int32 (n_peaks, autocorr first-min index)
+ * Copies min(cap_bytes, available) bytes to the HOST buffer `out` and stores the byte count in *got. */
+int  bpc_debug_copy(bpc_handle* h, const char* what, void* out, int64_t cap_bytes, int64_t* got);
+
+/* Debug stage buffers cost ~100 KB of extra writes per segment, so they are off by default. */
+int  bpc_set_debug(bpc_handle* h, int on);
+
+/* Host-only access to the constant tables (no GPU needed; used by the CPU test-suite to pin them against the oracle):
+ *   "mel_a" [128,257] "mel_b" [128,257] "mel_c" [64,257] "mel_d" [128,1025] "dct_mel" [40,128] "dct_time" [T,T]
+ *   "hann512" [512] f64 "hann2048" [2048] f64 "chroma" [12,257] (tuning_idx) "cqt_basis" [36,257,2] (tuning_idx)
+ *   "cqt_sqrt_len" [252] f64 (tuning_idx) "halfband" [ntaps] f64 "hist_edges" [101] f64
+ * Writes float32 unless noted; returns the element count or a negative status. */
+int64_t bpc_table_copy(const bpc_params* p, const char* name, int tuning_idx, void* out, int64_t cap_elems);
+
+/* Kernel launches issued by this handle since creation (bench.py's `gpu_launches`). */
+int64_t bpc_launch_count(const bpc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPC_B200_H */
