@@ -43,13 +43,18 @@ _SIGS = {
                                       C.c_void_p]),
     "bpc_stage_logmel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
+    "bpc_modspec": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "bpc_channel_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bpc_channel_stats_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "bpc_channel_stats_reset": (C.c_int, [C.c_void_p]),
     "bpc_debug_copy": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "bpc_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "bpc_table_copy": (C.c_int64, [C.POINTER(Params), C.c_char_p, C.c_int, C.c_void_p, C.c_int64]),
+    "bpc_chunk_size": (C.c_int, [C.c_void_p]),
     "bpc_launch_count": (C.c_int64, [C.c_void_p]),
+    "bpc_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "bpc_kernel_times": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "bpc_kernel_name": (C.c_char_p, [C.c_int]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -32,6 +32,7 @@ class Engine:
         self.T = self._lib.bpc_num_frames(C.byref(self.params))
         self.nscal = self._lib.bpc_num_scalars(C.byref(self.params))
         self.L = int(self.params.expected_len)
+        self.chunk = int(self._lib.bpc_chunk_size(self._h))
         if debug:
             self.set_debug(True)
 
@@ -94,6 +95,19 @@ class Engine:
         _check(self._h, rc, "bpc_stage_logmel")
         return stft, mel3
 
+    def modspec(self, mel_db):
+        """methods.py:142-143 on [n, 128, T] mel_db (numpy or cuda tensor) -> same kind, [n, 40, T]."""
+        import torch
+        is_np = isinstance(mel_db, np.ndarray)
+        x = torch.from_numpy(np.ascontiguousarray(mel_db, dtype=np.float32)).cuda(self.device) if is_np else mel_db.contiguous()
+        if x.dim() != 3 or x.shape[1] != L.PLANE_ROWS or x.shape[2] != self.T:
+            raise ValueError(f"mel_db must be [n, 128, {self.T}]")
+        out = torch.empty((x.shape[0], 40, self.T), dtype=torch.float32, device=x.device)
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        _check(self._h, self._lib.bpc_modspec(self._h, x.data_ptr(), x.shape[0], out.data_ptr(), C.c_void_p(st)),
+               "bpc_modspec")
+        return out.cpu().numpy() if is_np else out
+
     # ---------------------------------------------------------------------------------------------- host arrays
     def precompute_host(self, wav: np.ndarray, feats=None, scalars=None, status=None):
         """wav: numpy [B, L_in] float32 / int16 (pageable or pinned) -> numpy (feats, scalars, status)."""
@@ -138,6 +152,16 @@ class Engine:
 
     def reset_stats(self):
         _check(self._h, self._lib.bpc_channel_stats_reset(self._h), "bpc_channel_stats_reset")
+
+    def set_kernel_timing(self, on: bool):
+        _check(self._h, self._lib.bpc_set_kernel_timing(self._h, int(bool(on))), "bpc_set_kernel_timing")
+
+    def kernel_times(self):
+        """{kernel name: (total ms, launches)} since the last call (synchronises the device)."""
+        ms = np.zeros(10, dtype=np.float64)
+        cnt = np.zeros(10, dtype=np.int64)
+        _check(self._h, self._lib.bpc_kernel_times(self._h, ms.ctypes.data, cnt.ctypes.data, 10), "bpc_kernel_times")
+        return {self._lib.bpc_kernel_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(10) if cnt[i]}
 
     def launch_count(self) -> int:
         return int(self._lib.bpc_launch_count(self._h))

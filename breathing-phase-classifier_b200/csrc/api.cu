@@ -33,6 +33,7 @@ struct Slot {                      // one in-flight chunk of the host-buffer pat
     int32_t* h_status = nullptr;
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t computed = nullptr;   // kernels of this chunk finished (the two slots share one workspace)
 };
 
 }  // namespace
@@ -55,6 +56,9 @@ struct bpc_handle {
     size_t slot_wav_bytes = 0;
     int last_n = 0;
     int64_t launches0 = 0;
+    bool timing = false;           // per-kernel CUDA-event timing (bench.py roofline leg)
+    struct Ev { int id; cudaEvent_t a, b; };
+    std::vector<Ev> evs;
     std::string err;
 };
 
@@ -243,16 +247,26 @@ int run_chunk(bpc_handle* h, const void* wav, int wav_dtype, int64_t L_in, int n
         y = ws.y;
     }
     if (status) BPC_CUDA(h, cudaMemsetAsync(status, 0, sizeof(int32_t) * n, st));
-    launch_stft512(y, n, g, h->tb, ws, st);
-    launch_spec512_consumers(n, g, h->tb, ws, feats, scalars, status, true, st);
-    launch_spec2048(y, n, g, h->tb, ws, feats, scalars, st);
-    launch_even2048(n, g, h->tb, ws, scalars, status, st);
-    launch_cens(y, n, g, h->tb, ws, feats, st);
-    launch_time_scalars(y, n, g, h->tb, ws, scalars, status, st);
-    launch_hilbert(y, n, g, h->tb, ws, scalars, st);
-    launch_lpc(y, n, g, h->tb, ws, feats, st);
+    auto timed = [&](int id, auto&& fn) {
+        if (!h->timing) { fn(); return; }
+        bpc_handle::Ev e{id, nullptr, nullptr};
+        cudaEventCreate(&e.a);
+        cudaEventCreate(&e.b);
+        cudaEventRecord(e.a, st);
+        fn();
+        cudaEventRecord(e.b, st);
+        h->evs.push_back(e);
+    };
+    timed(1, [&] { launch_stft512(y, n, g, h->tb, ws, st); });
+    timed(2, [&] { launch_spec512_consumers(n, g, h->tb, ws, feats, scalars, status, true, st); });
+    timed(3, [&] { launch_spec2048(y, n, g, h->tb, ws, feats, scalars, st); });
+    timed(4, [&] { launch_even2048(n, g, h->tb, ws, scalars, status, st); });
+    timed(5, [&] { launch_cens(y, n, g, h->tb, ws, feats, st); });
+    timed(6, [&] { launch_time_scalars(y, n, g, h->tb, ws, scalars, status, st); });
+    timed(7, [&] { launch_hilbert(y, n, g, h->tb, ws, scalars, st); });
+    timed(8, [&] { launch_lpc(y, n, g, h->tb, ws, feats, st); });
     launch_pad_scalars(n, g, scalars, st);
-    launch_stats(n, g, feats, scalars, h->stats_acc, st);
+    timed(9, [&] { launch_stats(n, g, feats, scalars, h->stats_acc, st); });
     h->last_n = n;
     BPC_CUDA(h, cudaGetLastError());
     return BPC_OK;
@@ -280,6 +294,7 @@ int ensure_slots(bpc_handle* h) {
         h->host_allocs.push_back(s.h_scalars); h->host_allocs.push_back(s.h_status);
         BPC_CUDA(h, cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
         BPC_CUDA(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        BPC_CUDA(h, cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
     }
     h->slots_ready = true;
     return BPC_OK;
@@ -363,6 +378,7 @@ void bpc_destroy(bpc_handle* h) {
     for (int i = 0; i < 2; ++i) {
         if (h->slot[i].st) cudaStreamDestroy(h->slot[i].st);
         if (h->slot[i].done) cudaEventDestroy(h->slot[i].done);
+        if (h->slot[i].computed) cudaEventDestroy(h->slot[i].computed);
     }
     for (void* d : h->dev_allocs) cudaFree(d);
     for (void* d : h->host_allocs) cudaFreeHost(d);
@@ -431,8 +447,12 @@ int bpc_precompute_host(bpc_handle* h, const void* wav, int wav_dtype, int64_t B
                 std::memcpy(s.h_wav, src, in_bytes);
                 BPC_CUDA(h, cudaMemcpyAsync(s.d_wav, s.h_wav, in_bytes, cudaMemcpyHostToDevice, s.st));
             }
+            // H2D of this chunk overlaps the previous chunk's kernels; the kernels themselves are serialised because
+            // both slots use the handle's single workspace.
+            if (i >= 1) BPC_CUDA(h, cudaStreamWaitEvent(s.st, h->slot[(i - 1) & 1].computed, 0));
             rc = run_chunk(h, s.d_wav, wav_dtype, L_in, n, s.d_feats, s.d_scalars, s.d_status, s.st);
             if (rc) return rc;
+            BPC_CUDA(h, cudaEventRecord(s.computed, s.st));
             float* fdst = pin_f ? feats + (size_t)off * seg_feats : s.h_feats;
             float* sdst = pin_s ? scalars + (size_t)off * g.nscal : s.h_scalars;
             BPC_CUDA(h, cudaMemcpyAsync(fdst, s.d_feats, (size_t)n * seg_feats * 4, cudaMemcpyDeviceToHost, s.st));
@@ -474,6 +494,15 @@ int bpc_stage_logmel(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, i
         launch_logmel_only(n, g, h->tb, ws, mel3 + (size_t)off * 3 * kPlaneRows * g.T, st);
         h->last_n = n;
     }
+    BPC_CUDA(h, cudaGetLastError());
+    return BPC_OK;
+}
+
+int bpc_modspec(bpc_handle* h, const float* mel_db, int64_t n, float* out, void* stream) {
+    if (!h) return BPC_ERR_ARG;
+    if (!mel_db || !out || n < 0) { h->err = "bpc_modspec: bad argument"; return BPC_ERR_ARG; }
+    BPC_CUDA(h, cudaSetDevice(h->device));
+    if (n > 0) launch_modspec((int)n, h->g, h->tb, mel_db, out, static_cast<cudaStream_t>(stream));
     BPC_CUDA(h, cudaGetLastError());
     return BPC_OK;
 }
@@ -572,5 +601,36 @@ int64_t bpc_table_copy(const bpc_params* p, const char* name, int tuning_idx, vo
 }
 
 int64_t bpc_launch_count(const bpc_handle* h) { return h ? launches_issued() - h->launches0 : 0; }
+
+int bpc_chunk_size(const bpc_handle* h) { return h ? h->chunk : BPC_ERR_ARG; }
+
+int bpc_set_kernel_timing(bpc_handle* h, int on) {
+    if (!h) return BPC_ERR_ARG;
+    h->timing = on != 0;
+    return BPC_OK;
+}
+
+int bpc_kernel_times(bpc_handle* h, double* ms_out, int64_t* launches_out, int n_ids) {
+    if (!h || !ms_out || !launches_out || n_ids < BPC_NUM_KERNEL_IDS) return BPC_ERR_ARG;
+    BPC_CUDA(h, cudaSetDevice(h->device));
+    BPC_CUDA(h, cudaDeviceSynchronize());
+    for (int i = 0; i < n_ids; ++i) { ms_out[i] = 0.0; launches_out[i] = 0; }
+    for (auto& e : h->evs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e.a, e.b);
+        if (e.id >= 0 && e.id < n_ids) { ms_out[e.id] += (double)ms; launches_out[e.id] += 1; }
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    h->evs.clear();
+    return BPC_OK;
+}
+
+const char* bpc_kernel_name(int id) {
+    static const char* names[BPC_NUM_KERNEL_IDS] = {"k_ingest", "k_stft512", "k_spec512_consumers", "k_spec2048",
+                                                    "k_even2048", "k_cens", "k_time_basic+k_autocorr", "k_hilbert",
+                                                    "k_lpc", "k_stats"};
+    return (id >= 0 && id < BPC_NUM_KERNEL_IDS) ? names[id] : "";
+}
 
 }  // extern "C"

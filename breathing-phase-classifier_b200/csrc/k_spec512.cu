@@ -171,6 +171,22 @@ __device__ void dct_mel40(const float* __restrict__ D, const float* P, int T, fl
     __syncthreads();
 }
 
+// C2[k*T + u] = sum_t DT[u][t] * C1[k*T + t] (ortho DCT-II along time); DTt is stored transposed, [t][u].
+__device__ void dct_time40(const float* __restrict__ DTt, const float* C1, int T, float* C2) {
+    for (int idx = threadIdx.x; idx < 40 * T; idx += blockDim.x) {
+        const int u = idx % T, k = idx / T;
+        double acc = 0.0;
+        float part = 0.f;
+        for (int t = 0; t < T; ++t) {
+            part = fmaf(__ldg(DTt + t * T + u), C1[k * T + t], part);
+            if ((t & 15) == 15) { acc += (double)part; part = 0.f; }
+        }
+        acc += (double)part;
+        C2[idx] = (float)acc;
+    }
+    __syncthreads();
+}
+
 // whole-array statistics of a shared-memory array
 __device__ ZTerm zterm_of(const float* a, int n, double* dscratch, float* fscratch, float* min_out) {
     double s = 0.0, q = 0.0;
@@ -236,19 +252,7 @@ __device__ void role_mel(int b, const Geometry g, const Tables& tb, const Worksp
 
     // mod_spec (methods.py:142-143): DCT-II ortho over mel (keep 40), then over time
     dct_mel40(tb.dct_mel, P, T, C1);
-    const float* DTt = tb.dct_time;                                   // [t][u] = DT[u][t]
-    for (int idx = threadIdx.x; idx < 40 * T; idx += blockDim.x) {
-        const int u = idx % T, k = idx / T;
-        double acc = 0.0;
-        float part = 0.f;
-        for (int t = 0; t < T; ++t) {
-            part = fmaf(__ldg(DTt + t * T + u), C1[k * T + t], part);
-            if ((t & 15) == 15) { acc += (double)part; part = 0.f; }
-        }
-        acc += (double)part;
-        C2[idx] = (float)acc;
-    }
-    __syncthreads();
+    dct_time40(tb.dct_time, C1, T, C2);
     if (ws.dbg_mod) {
         float* d = ws.dbg_mod + (size_t)b * 40 * T;
         for (int i = threadIdx.x; i < 40 * T; i += blockDim.x) d[i] = C2[i];
@@ -511,6 +515,33 @@ void launch_stft_db(int n, const Geometry& g, const Workspace& ws, float* stft_d
         done = true;
     }
     k_stft_db<<<n, 256, bytes, st>>>(g, ws.mag512, stft_db);
+    note_launch();
+}
+
+// ------------------------------------------- methods.py:142-143 on caller-provided mel_db ([n, 128, T] -> [n, 40, T])
+__global__ void __launch_bounds__(256) k_modspec(Geometry g, Tables tb, const float* __restrict__ mel_db,
+                                                 float* __restrict__ out) {
+    extern __shared__ __align__(16) float smem[];
+    const int T = g.T, NP = kPlaneRows * T, b = blockIdx.x;
+    float* P = smem;
+    float* C1 = P + NP;
+    float* C2 = C1 + 40 * T;
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) P[i] = mel_db[(size_t)b * NP + i];
+    __syncthreads();
+    dct_mel40(tb.dct_mel, P, T, C1);
+    dct_time40(tb.dct_time, C1, T, C2);
+    for (int i = threadIdx.x; i < 40 * T; i += blockDim.x) out[(size_t)b * 40 * T + i] = C2[i];
+}
+
+void launch_modspec(int n, const Geometry& g, const Tables& tb, const float* mel_db, float* out, cudaStream_t st) {
+    set_consumer_smem();
+    static bool done = false;
+    if (!done) {
+        cudaFuncSetAttribute(k_modspec, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kConsumerSmemFloats * (int)sizeof(float));
+        done = true;
+    }
+    k_modspec<<<n, 256, kConsumerSmemFloats * sizeof(float), st>>>(g, tb, mel_db, out);
     note_launch();
 }
 

@@ -104,6 +104,10 @@ int  bpc_precompute_host(bpc_handle* h, const void* wav, int wav_dtype, int64_t 
 int  bpc_stage_logmel(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in,
                       float* stft_db, float* mel3, void* stream);
 
+/* methods.py:142-143 extract_spectral_modulation_features on caller-provided mel_db: [n, 128, T] -> [n, 40, T]
+ * (ortho DCT-II over the mel axis, first 40 rows, then ortho DCT-II over time).  Device buffers. */
+int  bpc_modspec(bpc_handle* h, const float* mel_db, int64_t n, float* out, void* stream);
+
 /* Dataset-level statistics accumulated over every bpc_precompute* call since the last reset:
  * stats[(9 + nscal)][5] doubles = {count, sum, sum of squares, min, max}, first the 9 channels (sorted order, over all
  * 128*T values of each plane), then each scalar.  Host output.  bpc_channel_stats_device returns the device pointer
@@ -130,8 +134,19 @@ int  bpc_set_debug(bpc_handle* h, int on);
  * Writes float32 unless noted; returns the element count or a negative status. */
 int64_t bpc_table_copy(const bpc_params* p, const char* name, int tuning_idx, void* out, int64_t cap_elems);
 
+/* Segments processed per internal chunk (= per kernel launch); env BPC_CHUNK overrides the default at create time. */
+int  bpc_chunk_size(const bpc_handle* h);
+
 /* Kernel launches issued by this handle since creation (bench.py's `gpu_launches`). */
 int64_t bpc_launch_count(const bpc_handle* h);
+
+/* Per-kernel device times (CUDA events around every launch of the full path) for bench.py's roofline leg.
+ * ids: 0 ingest, 1 stft512, 2 spec512 consumers, 3 spec2048, 4 even2048, 5 cens, 6 time_basic+autocorr, 7 hilbert,
+ * 8 lpc, 9 stats.  bpc_kernel_times synchronises, sums the elapsed ms / launch counts since the last call. */
+#define BPC_NUM_KERNEL_IDS 10
+int  bpc_set_kernel_timing(bpc_handle* h, int on);
+int  bpc_kernel_times(bpc_handle* h, double* ms_out, int64_t* launches_out, int n_ids);
+const char* bpc_kernel_name(int id);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,205 @@
+"""CPU tests of the host side: C-ABI exports, constant tables against the oracle shim, mirrors of the reference helpers,
+the .npz / Dataset contract, the gloo (world_size 2) statistics exchange.  No compute call is made here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import bpc_b200
+from bpc_b200 import _lib as L
+from bpc_b200.precompute import methods as M, process as PR, core as CO
+from oracle import pipeline as P
+from librosa import filters as F, _core as C
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "bpc.h")).read()
+    declared = set(re.findall(r"\b(bpc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(bpc_b200.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/bpc.h but not exported"
+    assert declared == set(bpc_b200.EXPORTS), declared ^ set(bpc_b200.EXPORTS)
+    assert bpc_b200.lib().bpc_abi_version() == 1
+
+
+def test_default_params_are_the_reference_constants():
+    p = bpc_b200.default_params()
+    assert (p.sr, p.n_fft, p.hop, p.n_mels, p.n_mfcc, p.n_gammatone, p.n_lpc, p.expected_len) == \
+           (16000, 512, 256, 128, 40, 64, 12, 16000)
+    assert p.fmax == 4500.0 and p.pad_scalars_to == 0
+    assert bpc_b200.lib().bpc_num_frames(ctypes.byref(p)) == 63
+    assert bpc_b200.lib().bpc_num_scalars(ctypes.byref(p)) == 36
+    p.pad_scalars_to = 39
+    assert bpc_b200.lib().bpc_num_scalars(ctypes.byref(p)) == 39
+    assert (M.SR, M.N_FFT, M.HOP_LENGTH, M.N_MELS, M.N_MFCC, M.FMAX, M.N_GAMMATONE, M.N_LPC) == \
+           (16000, 512, 256, 128, 40, 4500, 64, 12)
+
+
+def test_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(bpc_b200.BpcError, match="no CUDA device|CPU fallback"):
+        bpc_b200.Engine(device=0)
+
+
+def test_unsupported_params_are_rejected():
+    p = bpc_b200.default_params(expected_len=32000)
+    h = ctypes.c_void_p()
+    rc = bpc_b200.lib().bpc_create(ctypes.byref(h), ctypes.byref(p), 0, 16)
+    assert rc == -4 and not h.value
+    assert b"expected_len" in bpc_b200.lib().bpc_last_error(None)
+
+
+@pytest.mark.parametrize("name,args", [("mel_a", (512, 128, 4500.0)), ("mel_b", (512, 128, 8000.0)),
+                                        ("mel_c", (512, 64, 8000.0)), ("mel_d", (2048, 128, 8000.0))])
+def test_mel_tables_bit_exact(name, args):
+    n_fft, n_mels, fmax = args
+    assert np.array_equal(bpc_b200.table(name), F.mel(sr=16000, n_fft=n_fft, n_mels=n_mels, fmax=fmax))
+
+
+def test_window_and_misc_tables():
+    import scipy.fftpack
+    import scipy.signal
+    for n in (512, 2048, 384):
+        assert np.array_equal(bpc_b200.table(f"hann{n}"), scipy.signal.get_window("hann", n))
+    assert np.array_equal(bpc_b200.table("hamming400"), np.hamming(400))
+    assert np.array_equal(bpc_b200.table("hist_edges"), np.linspace(-0.5, 0.5, 101))
+    assert np.abs(bpc_b200.table("halfband") - C.default_halfband()).max() < 1e-14
+    d = scipy.fftpack.dct(np.eye(128), type=2, norm="ortho", axis=0)[:40]
+    assert np.abs(bpc_b200.table("dct_mel") - d).max() < 1e-7
+    d = scipy.fftpack.dct(np.eye(63), type=2, norm="ortho", axis=0)
+    assert np.abs(bpc_b200.table("dct_time") - d).max() < 1e-7
+
+
+@pytest.mark.parametrize("ti", [0, 13, 50, 99])
+def test_chroma_and_cqt_tables(ti):
+    edges = np.linspace(-0.5, 0.5, 101)
+    assert np.array_equal(bpc_b200.table("chroma", ti), F.chroma(sr=16000, n_fft=512, tuning=edges[ti]))
+    fmin = 440.0 * 2.0 ** ((24 - 69) / 12.0) * 2.0 ** (edges[ti] / 36)
+    ratios = 2.0 ** (np.arange(0, 36, dtype=float) / 36)
+    freqs = np.sort(np.multiply.outer(2.0 ** np.arange(7, dtype=float), ratios).flatten()) * fmin
+    alpha = F.relative_bandwidth(freqs=freqs)
+    lengths, _ = F.wavelet_lengths(freqs=freqs, sr=16000, alpha=alpha)
+    fb, _, _ = C._vqt_filter_fft(16000, freqs[-36:], 1, 1, 0.01, alpha=alpha[-36:])
+    mine = bpc_b200.table("cqt_basis", ti)
+    mine = mine[..., 0] + 1j * mine[..., 1]
+    ref = fb.toarray()
+    assert np.array_equal(mine != 0, ref != 0)
+    assert np.abs(mine - ref).max() < 1e-7
+    assert np.abs(bpc_b200.table("cqt_sqrt_len", ti) - np.sqrt(lengths)).max() < 1e-9
+
+
+def test_synth_generators_agree():
+    from bpc_b200.synth import synth_pcm16
+    for i in (0, 7, 1234):
+        q = synth_pcm16(i)
+        assert q.dtype == np.int16 and q.shape == (16000,)
+        assert np.array_equal(q.astype(np.float32) / np.float32(32768.0), P.synth_segment(i))
+
+
+def test_pad_helpers_match_reference_semantics():
+    a = np.arange(12, dtype=np.float32).reshape(3, 4) - 5
+    assert np.array_equal(M.pad_time(a, 3, 2), a[:, :2])
+    out = M.pad_time(a, 3, 6)
+    assert out.shape == (3, 6) and np.all(out[:, 4:] == a.min())
+    assert np.array_equal(M.pad_freq(a, 3, 2), a[:2])
+    out = M.pad_freq(a, 3, 5)
+    assert out.shape == (5, 4) and np.all(out[3:] == a.min()) and out.dtype == np.float32
+    y = np.ones(10, dtype=np.float32)
+    assert np.array_equal(M.pad_or_truncate(y, 4), y[:4])
+    z = M.pad_or_truncate(y, 13)
+    assert z.shape == (13,) and np.all(z[10:] == 0) and z.dtype == np.float32
+    assert np.array_equal(M.pad_time(a, 3, 6), P.fit_time(a, 3, 6)) and np.array_equal(M.pad_freq(a, 3, 5), P.fit_rows(a, 3, 5))
+
+
+def test_wav_name_mapping():
+    assert CO.wav_name_for("steth_20180814_09_37_11_I_004", "train") == "steth_20180814_09_37_11_004.wav"
+    assert CO.wav_name_for("steth_20180814_09_37_11_E_004", "train") == "steth_20180814_09_37_11_004.wav"
+    assert CO.wav_name_for("steth_20190713_09_58_25_007.wav", "test") == "steth_20190713_09_58_25_007.wav"
+    assert CO.wav_name_for("abc", "test") == "abc.wav"
+
+
+def test_npz_contract_and_dataset_order(tmp_path):
+    feats = np.arange(9 * 128 * 63, dtype=np.float32).reshape(9, 128, 63)
+    scal = np.arange(36, dtype=np.float32)
+    PR.save_npz(str(tmp_path), "id_1.wav", feats, scal)
+    d = np.load(tmp_path / "id_1.wav.npz")
+    assert set(d.files) == set(P.CHANNEL_KEYS) | {"scalars"}
+    excluded = {"scalars", "sr", "hop_length", "n_fft"}                 # dataset.py:8
+    names = sorted(k for k in d.files if k not in excluded)             # dataset.py:25-26
+    assert tuple(names) == bpc_b200.CHANNELS == P.SORTED_KEYS
+    stacked = np.stack([d[k] for k in names]).astype(np.float32)        # dataset.py:48
+    assert np.array_equal(stacked, feats) and d["scalars"].shape == (36,)
+    assert all(d[k].dtype == np.float32 and d[k].shape == (128, 63) for k in names)
+
+
+def test_fit_batch_and_load_wav(tmp_path):
+    import scipy.io.wavfile
+    q = (np.random.default_rng(0).standard_normal(12000) * 3000).astype(np.int16)
+    scipy.io.wavfile.write(tmp_path / "a.wav", 16000, q)
+    w = PR.load_wav(str(tmp_path / "a.wav"))
+    assert w.dtype == np.int16 and np.array_equal(w, q)
+    b = PR.fit_batch([w, np.concatenate([q, q])])
+    assert b.dtype == np.int16 and b.shape == (2, 16000)
+    assert np.array_equal(b[0, :12000], q) and np.all(b[0, 12000:] == 0) and np.array_equal(b[1], np.concatenate([q, q])[:16000])
+    mixed = PR.fit_batch([w, w.astype(np.float32) / 32768])
+    assert mixed.dtype == np.float32 and np.array_equal(mixed[0], mixed[1])
+    scipy.io.wavfile.write(tmp_path / "b.wav", 8000, q)
+    with pytest.raises(ValueError):
+        PR.load_wav(str(tmp_path / "b.wav"))
+    fid, ok, err = PR.process_and_save_npz(("nope", str(tmp_path / "missing.wav"), str(tmp_path)))
+    assert fid == "nope" and ok is False and isinstance(err, str)      # never raises (process.py:107-108)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from bpc_b200.stats import allreduce_stats, finalize_stats, shard_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    data = rng.standard_normal((10, 45, 7))                              # 10 "segments", 45 rows
+    lo, hi = shard_range(10, rank, world)
+    mine = data[lo:hi]
+    st = torch.zeros(45, 5, dtype=torch.float64)
+    st[:, 0] = mine.shape[0] * 7
+    st[:, 1] = torch.from_numpy(mine.sum(axis=(0, 2)))
+    st[:, 2] = torch.from_numpy((mine ** 2).sum(axis=(0, 2)))
+    st[:, 3] = torch.from_numpy(mine.min(axis=(0, 2)))
+    st[:, 4] = torch.from_numpy(mine.max(axis=(0, 2)))
+    allreduce_stats(st, dist)
+    f = finalize_stats(st)
+    ok = (np.allclose(f["mean"].numpy(), data.mean(axis=(0, 2))) and np.allclose(f["std"].numpy(), data.std(axis=(0, 2)))
+          and np.allclose(f["min"].numpy(), data.min(axis=(0, 2))) and np.allclose(f["max"].numpy(), data.max(axis=(0, 2)))
+          and float(f["count"][0]) == 70.0)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_stats_allreduce_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_shard_range_partitions():
+    from bpc_b200.stats import shard_range
+    for n, w in [(1000000, 8), (10, 3), (7, 8)]:
+        parts = [shard_range(n, r, w) for r in range(w)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
