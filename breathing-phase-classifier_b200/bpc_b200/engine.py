@@ -158,10 +158,11 @@ class Engine:
 
     def kernel_times(self):
         """{kernel name: (total ms, launches)} since the last call (synchronises the device)."""
-        ms = np.zeros(10, dtype=np.float64)
-        cnt = np.zeros(10, dtype=np.int64)
-        _check(self._h, self._lib.bpc_kernel_times(self._h, ms.ctypes.data, cnt.ctypes.data, 10), "bpc_kernel_times")
-        return {self._lib.bpc_kernel_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(10) if cnt[i]}
+        n = 11
+        ms = np.zeros(n, dtype=np.float64)
+        cnt = np.zeros(n, dtype=np.int64)
+        _check(self._h, self._lib.bpc_kernel_times(self._h, ms.ctypes.data, cnt.ctypes.data, n), "bpc_kernel_times")
+        return {self._lib.bpc_kernel_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
 
     def launch_count(self) -> int:
         return int(self._lib.bpc_launch_count(self._h))

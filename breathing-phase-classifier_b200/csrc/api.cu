@@ -103,6 +103,21 @@ int upload_bank(bpc_handle* h, const SparseBank& b, BankDev* out) {
     return BPC_OK;
 }
 
+// per-pass twiddle layout of fft.cuh::warp_fft_r4<M>
+std::vector<double2> twiddles_per_pass(int M) {
+    const int N = 1 << (2 * M);
+    std::vector<double2> t;
+    for (int p = 0; p < M - 1; ++p) {
+        const int q = N >> (2 * (p + 1)), ts = N / (4 * q);
+        for (int r = 1; r <= 3; ++r)
+            for (int pos = 0; pos < q; ++pos) {
+                const double ang = -2.0 * kPi * double(r * pos * ts) / double(N);
+                t.push_back(make_double2(std::cos(ang), std::sin(ang)));
+            }
+    }
+    return t;
+}
+
 std::vector<double2> twiddles(int n, int count) {
     std::vector<double2> t(count);
     for (int j = 0; j < count; ++j) {
@@ -139,6 +154,8 @@ int build_tables(bpc_handle* h) {
     if ((rc = upload(h, hamming_sym(400), &tb.hamming400))) return rc;
     if ((rc = upload(h, twiddles(256, 256), &tb.tw256))) return rc;
     if ((rc = upload(h, twiddles(1024, 1024), &tb.tw1024))) return rc;
+    if ((rc = upload(h, twiddles_per_pass(4), &tb.twp256))) return rc;
+    if ((rc = upload(h, twiddles_per_pass(5), &tb.twp1024))) return rc;
     if ((rc = upload(h, twiddles(512, 257), &tb.ptw512))) return rc;
     if ((rc = upload(h, twiddles(2048, 1025), &tb.ptw2048))) return rc;
     if ((rc = upload(h, twiddles(8000, 8000), &tb.tw8000))) return rc;
@@ -197,7 +214,9 @@ int build_workspace(bpc_handle* h) {
     w.cap = h->chunk;
     if ((rc = dalloc(h, C * g.L, &w.y))) return rc;
     if ((rc = dalloc(h, C * T * kMagStride, &w.mag512))) return rc;
-    if ((rc = dalloc(h, C * ((T + 1) / 2) * 1028, &w.mag2048_even))) return rc;
+    if ((rc = dalloc(h, C * T * kMag2048Stride, &w.mag2048))) return rc;
+    if ((rc = dalloc(h, C * T * 20, &w.frame_feat))) return rc;
+    if ((rc = dalloc(h, C * T * 128, &w.melD))) return rc;
     if ((rc = dalloc(h, C * 2, &w.tuning))) return rc;
     if ((rc = dalloc(h, C * 2, &w.chroma_min))) return rc;
     if ((rc = dalloc(h, C * 2, &w.ints))) return rc;
@@ -261,6 +280,7 @@ int run_chunk(bpc_handle* h, const void* wav, int wav_dtype, int64_t L_in, int n
     timed(2, [&] { launch_spec512_consumers(n, g, h->tb, ws, feats, scalars, status, true, st); });
     timed(3, [&] { launch_spec2048(y, n, g, h->tb, ws, feats, scalars, st); });
     timed(4, [&] { launch_even2048(n, g, h->tb, ws, scalars, status, st); });
+    timed(10, [&] { launch_seg2048(n, g, h->tb, ws, feats, scalars, st); });
     timed(5, [&] { launch_cens(y, n, g, h->tb, ws, feats, st); });
     timed(6, [&] { launch_time_scalars(y, n, g, h->tb, ws, scalars, status, st); });
     timed(7, [&] { launch_hilbert(y, n, g, h->tb, ws, scalars, st); });
@@ -627,9 +647,10 @@ int bpc_kernel_times(bpc_handle* h, double* ms_out, int64_t* launches_out, int n
 }
 
 const char* bpc_kernel_name(int id) {
-    static const char* names[BPC_NUM_KERNEL_IDS] = {"k_ingest", "k_stft512", "k_spec512_consumers", "k_spec2048",
-                                                    "k_even2048", "k_cens", "k_time_basic+k_autocorr", "k_hilbert",
-                                                    "k_lpc", "k_stats"};
+    static const char* names[BPC_NUM_KERNEL_IDS] = {"k_ingest", "k_stft512", "k_spec512_consumers",
+                                                    "k_fft2048+k_feat2048", "k_even2048", "k_cens",
+                                                    "k_time_basic+k_autocorr", "k_hilbert", "k_lpc", "k_stats",
+                                                    "k_seg2048"};
     return (id >= 0 && id < BPC_NUM_KERNEL_IDS) ? names[id] : "";
 }
 

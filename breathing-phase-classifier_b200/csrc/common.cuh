@@ -8,6 +8,7 @@ namespace bpc {
 
 constexpr int kPlaneRows = 128;
 constexpr int kMagStride = 260;          // |STFT512| workspace row stride (257 valid bins, 16-byte aligned rows)
+constexpr int kMag2048Stride = 1028;     // |STFT2048| workspace row stride (1025 valid bins)
 constexpr int kMaxFrames = 64;           // on-chip kernels of this build hold T <= 64 frames (1 s @ 16 kHz, hop 256)
 constexpr int kMaxLen = 16384;           // ... and L <= 16384 samples
 
@@ -86,6 +87,47 @@ __device__ __forceinline__ ZTerm make_zterm(double sum, double sumsq, double n) 
     ZTerm z;
     z.mean = (float)mean;
     z.denom = __fadd_rn((float)sqrt(var), 1e-8f);
+    return z;
+}
+
+// numpy's float32 add-reduce of a contiguous run of n <= 128 elements (pairwise_sum with its 8 strided accumulators),
+// reproduced operation for operation by one warp; every lane returns the sum.  Row-wise z-scores (process.py:47,55) take
+// their mean from this, which matters when a row is constant: numpy's rounded mean then differs from the value and the
+// "normalised" row becomes -1 / +1 instead of 0 (silent input -> MFCC row 0).
+__device__ __forceinline__ float np_sum_f32_warp(const float* a, int n, int lane) {
+    float res;
+    if (n < 8) {
+        res = 0.f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
+        return res;
+    }
+    const int body = n - (n & 7);
+    float r = 0.f;
+    if (lane < 8) {
+        r = a[lane];
+        for (int i = 8 + lane; i < body; i += 8) r = __fadd_rn(r, a[i]);
+    }
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+    res = __shfl_sync(0xffffffffu, r, 0);
+    for (int i = body; i < n; ++i) res = __fadd_rn(res, a[i]);
+    return res;
+}
+
+// Row-wise z-score terms the numpy way: float32 mean from np_sum_f32_warp, deviations in float32, population std.
+// `a` holds n <= 128 floats in shared memory; one warp per row.
+__device__ __forceinline__ ZTerm np_row_zterm(const float* a, int n, int lane) {
+    const float mean = __fdiv_rn(np_sum_f32_warp(a, n, lane), (float)n);
+    double q = 0.0;
+    for (int t = lane; t < n; t += 32) {
+        const float d = __fsub_rn(a[t], mean);
+        q += (double)__fmul_rn(d, d);
+    }
+    q = warp_sum(q);
+    ZTerm z;
+    z.mean = mean;
+    z.denom = __fadd_rn((float)sqrt(q / (double)n), 1e-8f);
     return z;
 }
 

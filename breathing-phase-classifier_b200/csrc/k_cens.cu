@@ -17,7 +17,6 @@ constexpr int kBinSpan = kBinHi - kBinLo + 1;
 struct CensSmem {
     float dec[8000 + 4000 + 2000 + 1000 + 500 + 250 + 64];   // decimated signals, octaves 1..6
     double2 fbuf[8][256];
-    double2 tw[256];
     float2 spec[8][kBinSpan + 3];
     float cqmag[8][kCqtBinsPerOct];
     float chroma[12 * kMaxFrames];
@@ -36,7 +35,6 @@ __global__ void __launch_bounds__(256) k_cens(const float* __restrict__ y, Geome
     const int b = blockIdx.x, L = g.L, T = g.T;
     const float* yb = y + (size_t)b * L;
 
-    S.tw[tid] = tb.tw256[tid];
     for (int i = tid; i < kHalfbandTaps; i += 256) S.hb[i] = tb.halfband[i];
     if (tid < 43) {
         // scipy.signal.get_window('hann', 43, fftbins=False), normalised to unit sum in the smoothing loop below
@@ -100,12 +98,12 @@ __global__ void __launch_bounds__(256) k_cens(const float* __restrict__ y, Geome
                 float x0 = 0.f, x1 = 0.f;
                 if (gi >= 0 && gi < lo) x0 = sg ? sg[gi] : __ldg(yb + gi);
                 if (gi + 1 >= 0 && gi + 1 < lo) x1 = sg ? sg[gi + 1] : __ldg(yb + gi + 1);
-                buf[m] = make_double2((double)x0, (double)x1);    // window = 'ones'
+                buf[swz(m)] = make_double2((double)x0, (double)x1);   // window = 'ones'
             }
             __syncwarp();
-            fft_r4_dif<4, 32>(buf, S.tw, lane, SyncWarp());
+            warp_fft_r4<4>(buf, tb.twp256, lane);
             for (int k = kBinLo + lane; k <= kBinHi; k += 32) {
-                const double2 X = rfft_bin<4>(buf, tb.ptw512, k);
+                const double2 X = rfft_bin<4, true>(buf, tb.ptw512, k);
                 S.spec[warp][k - kBinLo] = make_float2((float)X.x, (float)X.y);   // complex64 STFT
             }
             __syncwarp();
@@ -178,11 +176,7 @@ __global__ void __launch_bounds__(256) k_cens(const float* __restrict__ y, Geome
     float mn = FLT_MAX;
     float* o = plane_ptr(feats, b, BPC_CH_CHROMA, T);
     for (int r = warp; r < 12; r += 8) {
-        double s = 0.0, q = 0.0;
-        for (int t = lane; t < T; t += 32) { const double v = (double)S.quant[r * T + t]; s += v; q += v * v; }
-        s = warp_sum(s);
-        q = warp_sum(q);
-        const ZTerm z = make_zterm(s, q, (double)T);
+        const ZTerm z = np_row_zterm(S.quant + r * T, T, lane);
         for (int t = lane; t < T; t += 32) {
             const float v = z(S.quant[r * T + t]);
             o[(12 + r) * T + t] = v;

@@ -1,8 +1,14 @@
-// STFT-2048 group (librosa default n_fft, reached through methods.py:59-63,90 and process.py:74-75):
-//   k_spec2048  one CTA per segment: per frame FP64 real FFT-2048 -> |X| -> spectral centroid / bandwidth / flatness /
-//               contrast, mel-D power column; afterwards flux statistics, onset envelope, tempogram plane.
+// STFT-2048 group (librosa default n_fft, reached through methods.py:59-63,90 and process.py:74-75), r01 v1 layout:
+//   k_fft2048   one WARP per frame: Hann * samples -> FP64 real FFT-2048 (swizzled radix-4, no CTA barriers) -> |X|
+//               written to the mag2048 workspace [n, T, 1028]
+//   k_feat2048  one warp per frame: spectral centroid / bandwidth / flatness / contrast order statistics and the mel-D
+//               power column from that row
 //   k_even2048  the hop-512 frames (= even hop-256 frames): spectral_rolloff with numpy's sequential float32 cumsum and
-//               the 36-bins-per-octave tuning estimate chroma_cens needs.
+//               the 36-bins-per-octave tuning estimate chroma_cens needs
+//   k_seg2048   one CTA per segment: statistics of the per-frame features, mel-D dB -> flux + onset envelope ->
+//               tempogram plane
+// (v0 was one 256-thread CTA per segment doing all of this behind CTA-wide barriers: 36 % of the step, FP64 pipe 9 %,
+//  47 % of its shared wavefronts bank conflicts -- profiles/r01_*.)
 #include <cmath>
 #include "kernels.cuh"
 #include "fft.cuh"
@@ -10,28 +16,63 @@
 
 namespace bpc {
 
-constexpr int kMag2048Stride = 1028;         // even-frame |X| workspace row stride (1025 valid)
 constexpr int kTempoLags = 384;
+constexpr int kFrameFeat = 20;               // doubles per frame: cent, bw, flat, peak[7], valley[7] (+3 pad)
 
+// ================================================================================================= k_fft2048
+constexpr int kFftWarps = 4;
+
+__global__ void __launch_bounds__(32 * kFftWarps) k_fft2048(const float* __restrict__ y, Geometry g, Tables tb,
+                                                             float* __restrict__ mag, int total_frames) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* buf = reinterpret_cast<double2*>(smem_raw) + (threadIdx.x >> 5) * 1024;
+    const int lane = threadIdx.x & 31;
+    const int T = g.T, L = g.L, hop = g.hop;
+    const double2* win2 = reinterpret_cast<const double2*>(tb.hann2048);
+    for (int f = blockIdx.x * kFftWarps + (threadIdx.x >> 5); f < total_frames; f += gridDim.x * kFftWarps) {
+        const int b = f / T, t = f - b * T;
+        const float* yb = y + (size_t)b * L;
+        const int g0 = t * hop - 1024;
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            const int m = lane + 32 * i;
+            const int gi = g0 + 2 * m;                         // even; L is even, so the pair is in or out together
+            float2 v = make_float2(0.f, 0.f);
+            if (gi >= 0 && gi < L) v = __ldg(reinterpret_cast<const float2*>(yb + gi));
+            const double2 w = __ldg(win2 + m);
+            buf[swz(m)] = make_double2((double)v.x * w.x, (double)v.y * w.y);
+        }
+        __syncwarp();
+        warp_fft_r4<5>(buf, tb.twp1024, lane);
+        float* out = mag + (size_t)f * kMag2048Stride;
+#pragma unroll 3
+        for (int i = 0; i < 33; ++i) {
+            const int k = lane + 32 * i;
+            if (k <= 1024) out[k] = c64_abs(rfft_bin<5, true>(buf, tb.ptw2048, k));
+        }
+        __syncwarp();
+    }
+}
+
+// ================================================================================================ k_feat2048
 // spectral_contrast sub-bands (librosa, fmin=200, n_bands=6, sr=16000, n_fft=2048): first bin, length, order count
 __constant__ int c_band_lo[7] = {0, 25, 51, 102, 204, 409, 819};
 __constant__ int c_band_len[7] = {25, 26, 51, 102, 205, 410, 206};
 __constant__ int c_band_n[7] = {1, 1, 1, 2, 4, 8, 4};
 
-// mean of the n smallest and n largest of magbuf[lo .. lo+len) by one warp (len <= 416, n <= 8).
+// mean of the n smallest and n largest of row[lo .. lo+len) by one warp (len <= 416, n <= 8).
 // Ties are broken by position, so every element is selected at most once.
-__device__ void warp_band_extremes(const float* magbuf, int lo, int len, int n, int lane, double* valley,
+__device__ void warp_band_extremes(const float* row, int lo, int len, int n, int lane, double* valley,
                                    double* peak) {
     float v[13];
 #pragma unroll
     for (int i = 0; i < 13; ++i) {
         const int j = lane + 32 * i;
-        v[i] = j < len ? magbuf[lo + j] : -1.f;          // magnitudes are >= 0; -1 marks "absent"
+        v[i] = j < len ? row[lo + j] : -1.f;             // magnitudes are >= 0; -1 marks "absent"
     }
     unsigned taken_hi = 0, taken_lo = 0;
     double sum_hi = 0.0, sum_lo = 0.0;
     for (int r = 0; r < n; ++r) {
-        // largest remaining
         float best = -2.f;
         int bi = -1;
 #pragma unroll
@@ -48,7 +89,6 @@ __device__ void warp_band_extremes(const float* magbuf, int lo, int len, int n, 
         }
         if (wi == gidx && bi >= 0) taken_hi |= 1u << bi;
         sum_hi += (double)wb;
-        // smallest remaining
         best = 3.0e38f;
         bi = -1;
 #pragma unroll
@@ -66,143 +106,119 @@ __device__ void warp_band_extremes(const float* magbuf, int lo, int len, int n, 
         if (wi == gidx && bi >= 0) taken_lo |= 1u << bi;
         sum_lo += (double)wb;
     }
-    // np.mean of a float32 slice -> float32
-    *peak = (double)(float)(sum_hi / (double)n);
+    *peak = (double)(float)(sum_hi / (double)n);         // np.mean of a float32 slice -> float32
     *valley = (double)(float)(sum_lo / (double)n);
 }
 
-struct Spec2048Frames {                       // live during the frame loop and the flux / onset stage
-    double2 fbuf[1024];
-    double2 tw[1024];
-    float magbuf[1032];
-    float melD[kPlaneRows * kMaxFrames];      // mel-D power [m*T + t]
-    double cent[kMaxFrames], bw[kMaxFrames];
-    float flat[kMaxFrames];
-    double peak[7 * kMaxFrames], valley[7 * kMaxFrames];
-};
-struct Spec2048Smem {
-    union {
-        Spec2048Frames f;
-        float tg[kTempoLags * kMaxFrames];    // tempogram autocorrelations [lag*T + t]; f is dead by then
-    } u;
-    float onset[kMaxFrames + 2 * 192 + 8];    // onset envelope with the tempogram's 192-sample pads
-    float frame[kTempoLags + 8];
-    float colmax[kMaxFrames];
-    double dscratch[32];
-    float fscratch[32];
-};
-
-__global__ void __launch_bounds__(256) k_spec2048(const float* __restrict__ y, Geometry g, Tables tb, Workspace ws,
-                                                  float* feats, float* scalars) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Spec2048Smem& S = *reinterpret_cast<Spec2048Smem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x, T = g.T, L = g.L, hop = g.hop;
-    const float* yb = y + (size_t)b * L;
-
-    for (int j = tid; j < 1024; j += 256) S.u.f.tw[j] = tb.tw1024[j];
-    double w0[4], w1[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = tid + 256 * i;
-        w0[i] = tb.hann2048[2 * m];
-        w1[i] = tb.hann2048[2 * m + 1];
-    }
-    __syncthreads();
-
-    for (int t = 0; t < T; ++t) {
-        const int g0 = t * hop - 1024;
+__global__ void __launch_bounds__(256) k_feat2048(Geometry g, Tables tb, Workspace ws, int total_frames) {
+    __shared__ __align__(16) float s_mag[8][kMag2048Stride];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* row = s_mag[warp];
+    for (int f = blockIdx.x * 8 + warp; f < total_frames; f += gridDim.x * 8) {
+        const float4* src = reinterpret_cast<const float4*>(ws.mag2048 + (size_t)f * kMag2048Stride);
+        for (int i = lane; i < kMag2048Stride / 4; i += 32) reinterpret_cast<float4*>(row)[i] = __ldg(src + i);
+        __syncwarp();
+        // spectral_centroid / bandwidth (methods.py:59-60): moments of the L1-normalised column; flatness (:62)
+        double sm = 0.0, smf = 0.0, smf2 = 0.0, slog = 0.0, spow = 0.0;
+        for (int k = lane; k < 1025; k += 32) {
+            const float m = row[k];
+            const double fk = (double)k * 7.8125, dm = (double)m;
+            sm += dm;
+            smf += dm * fk;
+            smf2 += dm * fk * fk;
+            const float p = fmaxf(1e-10f, __fmul_rn(m, m));
+            slog += (double)logf(p);
+            spow += (double)p;
+        }
+        sm = warp_sum(sm); smf = warp_sum(smf); smf2 = warp_sum(smf2); slog = warp_sum(slog); spow = warp_sum(spow);
+        double* ff = ws.frame_feat + (size_t)f * kFrameFeat;
+        if (lane == 0) {
+            const double len = sm < 1.17549435e-38 ? 1.0 : sm;     // util.normalize(norm=1): tiny(float32) guard
+            const double c = smf / len;
+            ff[0] = c;
+            ff[1] = sqrt(fmax(0.0, smf2 / len - 2.0 * c * (smf / len) + c * c * (sm / len)));
+            const float gmean = expf((float)(slog / 1025.0));
+            const float amean = (float)(spow / 1025.0);
+            ff[2] = (double)__fdiv_rn(gmean, amean);
+        }
+        // spectral_contrast order statistics (methods.py:63)
+        for (int band = 0; band < 7; ++band) {
+            double va, pk;
+            warp_band_extremes(row, c_band_lo[band], c_band_len[band], c_band_n[band], lane, &va, &pk);
+            if (lane == 0) { ff[3 + band] = pk; ff[10 + band] = va; }
+        }
+        // mel-D power column (n_fft 2048, 128 mels, fmax 8000): methods.py:90 and process.py:74
+        float* md = ws.melD + (size_t)f * kPlaneRows;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int m = tid + 256 * i;
-            const int gi = g0 + 2 * m;
-            const float x0 = (gi >= 0 && gi < L) ? __ldg(yb + gi) : 0.f;
-            const float x1 = (gi + 1 >= 0 && gi + 1 < L) ? __ldg(yb + gi + 1) : 0.f;
-            S.u.f.fbuf[m] = make_double2((double)x0 * w0[i], (double)x1 * w1[i]);
-        }
-        __syncthreads();                      // also: previous frame's feature warps are done with magbuf
-        fft_r4_dif<5, 256>(S.u.f.fbuf, S.u.f.tw, tid, SyncBlock());
-        float* even_out = nullptr;
-        if ((t & 1) == 0) even_out = ws.mag2048_even + ((size_t)b * ((T + 1) / 2) + (t >> 1)) * kMag2048Stride;
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const int k = tid + 256 * i;
-            if (k <= 1024) {
-                const float m = c64_abs(rfft_bin<5>(S.u.f.fbuf, tb.ptw2048, k));
-                S.u.f.magbuf[k] = m;
-                if (even_out) even_out[k] = m;
-            }
-        }
-        __syncthreads();
-        // ---- per-frame features, warp-specialised; no trailing barrier (the next frame's load only touches fbuf)
-        if (warp == 0) {
-            // spectral_centroid / bandwidth (methods.py:59-60) + flatness (methods.py:62)
-            double sum = 0.0, slog = 0.0, spow = 0.0;
-            for (int k = lane; k < 1025; k += 32) {
-                const float m = S.u.f.magbuf[k];
-                sum += (double)m;
-                const float p = fmaxf(1e-10f, __fmul_rn(m, m));
-                slog += (double)logf(p);
-                spow += (double)p;
-            }
-            sum = warp_sum(sum);
-            slog = warp_sum(slog);
-            spow = warp_sum(spow);
-            const double len = sum < 1.17549435e-38 ? 1.0 : sum;       // util.normalize(norm=1) threshold tiny(f32)
-            double c = 0.0;
-            for (int k = lane; k < 1025; k += 32) c += (double)k * 7.8125 * (double)(float)((double)S.u.f.magbuf[k] / len);
-            c = warp_sum(c);
-            double v = 0.0;
-            for (int k = lane; k < 1025; k += 32) {
-                const double d = fabs((double)k * 7.8125 - c);
-                v += (double)(float)((double)S.u.f.magbuf[k] / len) * (d * d);
-            }
-            v = warp_sum(v);
-            if (lane == 0) {
-                S.u.f.cent[t] = c;
-                S.u.f.bw[t] = sqrt(v);
-                const float gmean = expf((float)(slog / 1025.0));
-                const float amean = (float)(spow / 1025.0);
-                S.u.f.flat[t] = __fdiv_rn(gmean, amean);
-            }
-        } else {
-            // spectral_contrast order statistics (methods.py:63): one band per warp 1..7
-            const int band = warp - 1;
-            double va, pk;
-            warp_band_extremes(S.u.f.magbuf, c_band_lo[band], c_band_len[band], c_band_n[band], lane, &va, &pk);
-            if (lane == 0) { S.u.f.peak[band * T + t] = pk; S.u.f.valley[band * T + t] = va; }
-        }
-        // mel-D power column (n_fft 2048, 128 mels, fmax 8000): threads 128..255 take one row each
-        if (tid >= 128) {
-            const int m = tid - 128;
+            const int m = lane + 32 * i;
             const int s = tb.mel_d.start[m], c = tb.mel_d.count[m];
             const float* w = tb.mel_d.w + (size_t)m * tb.mel_d.width;
             float acc = 0.f;
             for (int j = 0; j < c; ++j) {
-                const float mv = S.u.f.magbuf[s + j];
+                const float mv = row[s + j];
                 acc = fmaf(__ldg(w + j), __fmul_rn(mv, mv), acc);
             }
-            S.u.f.melD[m * T + t] = acc;
+            md[m] = acc;
+        }
+        __syncwarp();
+    }
+}
+
+// ================================================================================================= k_seg2048
+constexpr int kSegThreads = 192;             // 6 warps = two tempogram frames in flight (96 threads x 4 lags each)
+
+struct Seg2048Smem {
+    union {
+        float melD[kMaxFrames * kPlaneRows];          // [t][m] power -> 10 log10
+        float tg[kPlaneRows * kMaxFrames];            // tempogram rows 0..127, raw autocorrelation [lag][t]
+    } u;
+    double peak[7 * kMaxFrames], valley[7 * kMaxFrames];
+    double cent[kMaxFrames], bw[kMaxFrames], flat[kMaxFrames];
+    float onset[kMaxFrames + 2 * 192 + 8];            // onset envelope with the tempogram's 192-sample pads
+    __align__(16) float frame[2][kTempoLags + 8];
+    float flux[kMaxFrames];
+    double sumv[kMaxFrames], sumq[kMaxFrames];
+    float ac0[kMaxFrames];
+    double dscratch[32];
+    float fscratch[32];
+};
+
+__device__ __forceinline__ void group_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, Workspace ws, float* feats,
+                                                          float* scalars) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Seg2048Smem& S = *reinterpret_cast<Seg2048Smem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = kSegThreads, NW = kSegThreads / 32;
+    const int b = blockIdx.x, T = g.T, NP = kPlaneRows * T;
+    float* sc = scalars + (size_t)b * g.nscal;
+
+    {   // stage per-frame features and mel-D
+        const float4* src = reinterpret_cast<const float4*>(ws.melD + (size_t)b * T * kPlaneRows);
+        for (int i = tid; i < T * kPlaneRows / 4; i += NT) reinterpret_cast<float4*>(S.u.melD)[i] = __ldg(src + i);
+        const double* ff = ws.frame_feat + (size_t)b * T * kFrameFeat;
+        for (int i = tid; i < T * 17; i += NT) {
+            const int t = i / 17, j = i - t * 17;
+            const double v = ff[t * kFrameFeat + j];
+            if (j == 0) S.cent[t] = v;
+            else if (j == 1) S.bw[t] = v;
+            else if (j == 2) S.flat[t] = v;
+            else if (j < 10) S.peak[(j - 3) * T + t] = v;
+            else S.valley[(j - 10) * T + t] = v;
         }
     }
     __syncthreads();
-
-    float* sc = scalars + (size_t)b * g.nscal;
-    const int NP = kPlaneRows * T;
-    // ---- centroid / bandwidth / flatness statistics (methods.py:64-68), warp 0..2
+    // ---- centroid / bandwidth / flatness statistics (methods.py:64-68), warps 0..2
     if (warp < 3) {
-        double s = 0.0, q = 0.0;
-        for (int t = lane; t < T; t += 32) {
-            const double v = warp == 0 ? S.u.f.cent[t] : (warp == 1 ? S.u.f.bw[t] : (double)S.u.f.flat[t]);
-            s += v;
-            q += v * v;
-        }
+        const double* a = warp == 0 ? S.cent : (warp == 1 ? S.bw : S.flat);
+        double s = 0.0;
+        for (int t = lane; t < T; t += 32) s += a[t];
         s = warp_sum(s);
-        q = warp_sum(q);
         const double mean = s / T;
         double m2 = 0.0, m3 = 0.0;
         for (int t = lane; t < T; t += 32) {
-            const double d = (warp == 0 ? S.u.f.cent[t] : (warp == 1 ? S.u.f.bw[t] : (double)S.u.f.flat[t])) - mean;
+            const double d = a[t] - mean;
             m2 += d * d;
             m3 += d * d * d;
         }
@@ -226,19 +242,19 @@ __global__ void __launch_bounds__(256) k_spec2048(const float* __restrict__ y, G
     // ---- contrast = power_to_db(peak) - power_to_db(valley), each clamped at its own max - 80 (float64 arrays)
     {
         double pmax = -1e300, vmax = -1e300;
-        for (int i = tid; i < 7 * T; i += 256) {
-            const double p = 10.0 * log10(fmax(1e-10, S.u.f.peak[i]));
-            const double v = 10.0 * log10(fmax(1e-10, S.u.f.valley[i]));
-            S.u.f.peak[i] = p;
-            S.u.f.valley[i] = v;
+        for (int i = tid; i < 7 * T; i += NT) {
+            const double p = 10.0 * log10(fmax(1e-10, S.peak[i]));
+            const double v = 10.0 * log10(fmax(1e-10, S.valley[i]));
+            S.peak[i] = p;
+            S.valley[i] = v;
             pmax = fmax(pmax, p);
             vmax = fmax(vmax, v);
         }
         pmax = block_reduce(pmax, -1e300, OpMaxD(), S.dscratch);
         vmax = block_reduce(vmax, -1e300, OpMaxD(), S.dscratch);
         double s = 0.0, q = 0.0;
-        for (int i = tid; i < 7 * T; i += 256) {
-            const double c = fmax(S.u.f.peak[i], pmax - 80.0) - fmax(S.u.f.valley[i], vmax - 80.0);
+        for (int i = tid; i < 7 * T; i += NT) {
+            const double c = fmax(S.peak[i], pmax - 80.0) - fmax(S.valley[i], vmax - 80.0);
             s += c;
             q += c * c;
         }
@@ -252,26 +268,24 @@ __global__ void __launch_bounds__(256) k_spec2048(const float* __restrict__ y, G
     }
     // ---- mel-D: L = 10 log10(max(1e-10, P)); flux uses ref=max (methods.py:90-92), onset uses ref=1 (process.py:74)
     float pmx = -FLT_MAX;
-    for (int i = tid; i < NP; i += 256) pmx = fmaxf(pmx, S.u.f.melD[i]);
+    for (int i = tid; i < NP; i += NT) pmx = fmaxf(pmx, S.u.melD[i]);
     pmx = block_max(pmx, S.fscratch);
     const float ref_db = (float)(10.0 * log10((double)fmaxf(1e-10f, pmx)));
     float lmax = -FLT_MAX;
-    for (int i = tid; i < NP; i += 256) {
-        const float l = __fmul_rn(10.0f, log10f(fmaxf(1e-10f, S.u.f.melD[i])));
-        S.u.f.melD[i] = l;
+    for (int i = tid; i < NP; i += NT) {
+        const float l = __fmul_rn(10.0f, log10f(fmaxf(1e-10f, S.u.melD[i])));
+        S.u.melD[i] = l;
         lmax = fmaxf(lmax, l);
     }
     lmax = block_max(lmax, S.fscratch);                                     // barrier inside: melD complete
     const float floor1 = __fsub_rn(lmax, 80.0f);                            // ref = 1.0 variant
     const float floorm = __fsub_rn(__fsub_rn(lmax, ref_db), 80.0f);         // ref = max variant
-    // one warp per time step: flux[t] and onset difference d[t], t = 0..T-2
-    float* flux = S.frame;                                                  // reuse (T-1 <= 384)
-    for (int j = tid; j < T + 2 * 192 + 8; j += 256) S.onset[j] = 0.f;
+    for (int j = tid; j < T + 2 * 192 + 8; j += NT) S.onset[j] = 0.f;
     __syncthreads();
-    for (int t = warp; t < T - 1; t += 8) {
+    for (int t = warp; t < T - 1; t += NW) {
         double f2 = 0.0, on = 0.0;
         for (int m = lane; m < kPlaneRows; m += 32) {
-            const float l0 = S.u.f.melD[m * T + t], l1 = S.u.f.melD[m * T + t + 1];
+            const float l0 = S.u.melD[t * kPlaneRows + m], l1 = S.u.melD[(t + 1) * kPlaneRows + m];
             const float a0 = fmaxf(__fsub_rn(l0, ref_db), floorm), a1 = fmaxf(__fsub_rn(l1, ref_db), floorm);
             const float d = __fsub_rn(a1, a0);
             f2 += (double)__fmul_rn(d, d);
@@ -281,7 +295,7 @@ __global__ void __launch_bounds__(256) k_spec2048(const float* __restrict__ y, G
         f2 = warp_sum(f2);
         on = warp_sum(on);
         if (lane == 0) {
-            flux[t] = sqrtf((float)f2);
+            S.flux[t] = sqrtf((float)f2);
             // onset_env = pad(mean over mels, (1 + 2048 // (2 * 256), 0))[:T]; stored at offset 192 (left tempogram pad)
             if (t + 5 < T) S.onset[192 + t + 5] = (float)(on / (double)kPlaneRows);
         }
@@ -291,9 +305,9 @@ __global__ void __launch_bounds__(256) k_spec2048(const float* __restrict__ y, G
         double s = 0.0, q = 0.0;
         float mx = -FLT_MAX;
         for (int t = lane; t < T - 1; t += 32) {
-            s += (double)flux[t];
-            q += (double)flux[t] * (double)flux[t];
-            mx = fmaxf(mx, flux[t]);
+            s += (double)S.flux[t];
+            q += (double)S.flux[t] * (double)S.flux[t];
+            mx = fmaxf(mx, S.flux[t]);
         }
         s = warp_sum(s);
         q = warp_sum(q);
@@ -306,73 +320,69 @@ __global__ void __launch_bounds__(256) k_spec2048(const float* __restrict__ y, G
         }
     }
     if (ws.dbg_onset)
-        for (int t = tid; t < T; t += 256) ws.dbg_onset[(size_t)b * T + t] = S.onset[192 + t];
+        for (int t = tid; t < T; t += NT) ws.dbg_onset[(size_t)b * T + t] = S.onset[192 + t];
     // ---- tempogram (process.py:75): linear-ramp pad 192, 384-sample Hann frames at hop 1, autocorrelation, /max
     if (tid < 192) {
         const float edge = S.onset[192 + T - 1];
         const float step = __fdiv_rn(edge, 192.0f);
         S.onset[192 + T + tid] = __fmul_rn((float)(191 - tid), step);       // np.pad(mode='linear_ramp', end 0)
     }
+    for (int t = tid; t < T; t += NT) { S.sumv[t] = 0.0; S.sumq[t] = 0.0; }
     __syncthreads();
-    float* TG = S.u.tg;                                                    // [384 * T], aliases the FFT buffers
-    for (int t = 0; t < T; ++t) {
-        for (int n = tid; n < kTempoLags; n += 256) S.frame[n] = (float)((double)S.onset[t + n] * tb.hann384[n]);
-        if (tid < 8) S.frame[kTempoLags + tid] = 0.f;
-        __syncthreads();
-        // structural zeros: onset[0..4] == 0 and the left pad is 0, so frame[n] == 0 for n < 197 - t
-        const int n0 = (197 - t) > 0 ? (197 - t) : 0;
-        for (int lag = tid; lag < kTempoLags; lag += 256) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            int n = n0;
-            const int nend = kTempoLags - lag;
-            for (; n + 3 < nend; n += 4) {
-                a0 = fmaf(S.frame[n], S.frame[n + lag], a0);
-                a1 = fmaf(S.frame[n + 1], S.frame[n + 1 + lag], a1);
-                a2 = fmaf(S.frame[n + 2], S.frame[n + 2 + lag], a2);
-                a3 = fmaf(S.frame[n + 3], S.frame[n + 3 + lag], a3);
-            }
-            for (; n < nend; ++n) a0 = fmaf(S.frame[n], S.frame[n + lag], a0);
-            TG[lag * T + t] = (a0 + a1) + (a2 + a3);
+    // two frames in flight: group gidx (96 threads) owns frames gidx, gidx + 2, ...; thread j owns lags 4j .. 4j + 3.
+    const int gidx = tid / 96, j = tid - gidx * 96, l0 = 4 * j;
+    float* F = S.frame[gidx];
+    for (int t = gidx; t < T + (T & 1); t += 2) {
+        const bool live = t < T;
+        if (live) {
+            for (int n = j; n < kTempoLags + 8; n += 96)
+                F[n] = n < kTempoLags ? (float)((double)S.onset[t + n] * __ldg(tb.hann384 + n)) : 0.f;
         }
-        __syncthreads();
-    }
-    // column max |.| (util.normalize norm=inf), then whole-array z-score over all 384 rows (process.py:76)
-    for (int t = warp; t < T; t += 8) {
-        float mx = 0.f;
-        for (int lag = lane; lag < kTempoLags; lag += 32) mx = fmaxf(mx, fabsf(TG[lag * T + t]));
-        mx = warp_max(mx);
-        if (lane == 0) S.colmax[t] = mx;
+        group_bar(1 + gidx, 96);
+        if (live) {
+            // structural zeros: onset[0..4] == 0 and the left pad is 0, so F[n] == 0 for n < 197 - t
+            int n = (197 - t) > 0 ? ((197 - t) & ~3) : 0;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (; n + l0 < kTempoLags; n += 4) {
+                const float4 A = *reinterpret_cast<const float4*>(F + n);
+                const float4 B0 = *reinterpret_cast<const float4*>(F + n + l0);
+                const float4 B1 = *reinterpret_cast<const float4*>(F + n + l0 + 4);
+                a0 = fmaf(A.x, B0.x, a0); a0 = fmaf(A.y, B0.y, a0); a0 = fmaf(A.z, B0.z, a0); a0 = fmaf(A.w, B0.w, a0);
+                a1 = fmaf(A.x, B0.y, a1); a1 = fmaf(A.y, B0.z, a1); a1 = fmaf(A.z, B0.w, a1); a1 = fmaf(A.w, B1.x, a1);
+                a2 = fmaf(A.x, B0.z, a2); a2 = fmaf(A.y, B0.w, a2); a2 = fmaf(A.z, B1.x, a2); a2 = fmaf(A.w, B1.y, a2);
+                a3 = fmaf(A.x, B0.w, a3); a3 = fmaf(A.y, B1.x, a3); a3 = fmaf(A.z, B1.y, a3); a3 = fmaf(A.w, B1.z, a3);
+            }
+            if (j == 0) S.ac0[t] = a0;
+            if (l0 < kPlaneRows) {
+                S.u.tg[(l0 + 0) * T + t] = a0; S.u.tg[(l0 + 1) * T + t] = a1;
+                S.u.tg[(l0 + 2) * T + t] = a2; S.u.tg[(l0 + 3) * T + t] = a3;
+            }
+            double sv = (double)a0 + (double)a1 + (double)a2 + (double)a3;
+            double sq = (double)a0 * a0 + (double)a1 * a1 + (double)a2 * a2 + (double)a3 * a3;
+            sv = warp_sum(sv);
+            sq = warp_sum(sq);
+            if (lane == 0) { atomicAdd(&S.sumv[t], sv); atomicAdd(&S.sumq[t], sq); }
+        }
+        group_bar(1 + gidx, 96);
     }
     __syncthreads();
+    // util.normalize(norm=inf) divides each column by max |.| (= lag 0); z-score over all 384 x T values (process.py:76)
     double s = 0.0, q = 0.0;
-    for (int i = tid; i < kTempoLags * T; i += 256) {
-        const int t = i % T;
-        const double len = (double)S.colmax[t] < 2.2250738585072014e-308 ? 1.0 : (double)S.colmax[t];
-        const double v = (double)TG[i] / len;
-        s += v;
-        q += v * v;
+    for (int t = tid; t < T; t += NT) {
+        const double c = (double)S.ac0[t] < 2.2250738585072014e-308 ? 1.0 : (double)S.ac0[t];
+        s += S.sumv[t] / c;
+        q += S.sumq[t] / (c * c);
     }
     s = block_sum(s, S.dscratch);
     q = block_sum(q, S.dscratch);
     const double mean = s / (double)(kTempoLags * T);
     const double sd = sqrt(fmax(0.0, q / (double)(kTempoLags * T) - mean * mean));
     float* o = plane_ptr(feats, b, BPC_CH_TEMPOGRAM, T);
-    for (int i = tid; i < NP; i += 256) {                                    // pad_freq truncates to the first 128 lags
+    for (int i = tid; i < NP; i += NT) {                                     // pad_freq truncates to the first 128 lags
         const int t = i % T;
-        const double len = (double)S.colmax[t] < 2.2250738585072014e-308 ? 1.0 : (double)S.colmax[t];
-        o[i] = (float)(((double)TG[i] / len - mean) / (sd + 1e-8));
+        const double c = (double)S.ac0[t] < 2.2250738585072014e-308 ? 1.0 : (double)S.ac0[t];
+        o[i] = (float)(((double)S.u.tg[i] / c - mean) / (sd + 1e-8));
     }
-}
-
-void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
-                     float* scalars, cudaStream_t st) {
-    static bool done = false;
-    if (!done) {
-        cudaFuncSetAttribute(k_spec2048, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Spec2048Smem));
-        done = true;
-    }
-    k_spec2048<<<n, 256, sizeof(Spec2048Smem), st>>>(y, g, tb, ws, feats, scalars);
-    note_launch();
 }
 
 // ------------------------------------------------------------------------------------ even frames: rolloff + tuning36
@@ -402,20 +412,20 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
     __shared__ int s_ncand;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x, T = g.T, TE = (T + 1) / 2;
-    const float* mag_b = ws.mag2048_even + (size_t)b * TE * kMag2048Stride;
+    // even frame f is row 2 f of the segment's mag2048 block
+    const float* mag_b = ws.mag2048 + (size_t)b * T * kMag2048Stride;
+    const size_t fstride = 2 * (size_t)kMag2048Stride;
     if (tid == 0) s_ncand = 0;
-    // column maxima (piptrack threshold) -- warps 1..7
     if (warp > 0) {
         for (int f = warp - 1; f < TE; f += 7) {
             float mx = 0.f;
-            for (int k = lane; k < 1025; k += 32) mx = fmaxf(mx, __ldg(mag_b + (size_t)f * kMag2048Stride + k));
+            for (int k = lane; k < 1025; k += 32) mx = fmaxf(mx, __ldg(mag_b + f * fstride + k));
             mx = warp_max(mx);
             if (lane == 0) colmax[f] = mx;
         }
     } else {
-        // rolloff chains -- warp 0, one frame per lane (TE <= 32)
         for (int f = lane; f < TE; f += 32) {
-            const float* col = mag_b + (size_t)f * kMag2048Stride;
+            const float* col = mag_b + f * fstride;
             float c = 0.f;
             for (int k = 0; k < 1025; ++k) c = __fadd_rn(c, __ldg(col + k));
             const float thr = __fmul_rn(0.85f, c);
@@ -445,7 +455,7 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
     const int nb = 492;
     for (int idx = tid; idx < nb * TE; idx += 256) {
         const int f = idx / nb, k = 20 + idx - f * nb;
-        const float* col = mag_b + (size_t)f * kMag2048Stride;
+        const float* col = mag_b + f * fstride;
         float pitch, mv;
         if (piptrack_candidate(__ldg(col + k - 1), __ldg(col + k), __ldg(col + k + 1), __fmul_rn(0.1f, colmax[f]), k,
                                7.8125, &pitch, &mv)) {
@@ -464,6 +474,35 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
         ws.tuning[b * 2 + 1] = tbin;
         if (status && flags) atomicOr((unsigned int*)&status[b], flags);
     }
+}
+
+// ==================================================================================================== launchers
+void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
+                     float* scalars, cudaStream_t st) {
+    static bool done = false;
+    static int sms = 148;
+    if (!done) {
+        cudaFuncSetAttribute(k_fft2048, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftWarps * 1024 * 16);
+        cudaFuncSetAttribute(k_seg2048, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Seg2048Smem));
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        done = true;
+    }
+    const int total = n * g.T;
+    int grid = (total + kFftWarps - 1) / kFftWarps;
+    if (grid > sms * 3 * 4) grid = sms * 3 * 4;
+    k_fft2048<<<grid, 32 * kFftWarps, kFftWarps * 1024 * 16, st>>>(y, g, tb, ws.mag2048, total);
+    int grid2 = (total + 7) / 8;
+    if (grid2 > sms * 6 * 4) grid2 = sms * 6 * 4;
+    k_feat2048<<<grid2, 256, 0, st>>>(g, tb, ws, total);
+    note_launch(2);
+}
+
+void launch_seg2048(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats, float* scalars,
+                    cudaStream_t st) {
+    k_seg2048<<<n, kSegThreads, sizeof(Seg2048Smem), st>>>(g, tb, ws, feats, scalars);
+    note_launch();
 }
 
 void launch_even2048(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* scalars,

@@ -43,48 +43,43 @@ void launch_ingest(const void* wav, int wav_dtype, int64_t L_in, float* y, int n
 // ------------------------------------------------------------------------------------------------ STFT-512
 // One CTA per segment, one warp per frame (8 frames in flight).  librosa.stft semantics: zero centre padding,
 // periodic Hann (float64) * float32 samples, float64 FFT, complex64 rounding, |.| as hypotf.
-__global__ void __launch_bounds__(256) k_stft512(const float* __restrict__ y, int L, int T, int hop,
-                                                 const double* __restrict__ win, const double2* __restrict__ tw_g,
-                                                 const double2* __restrict__ ptw, float* __restrict__ mag) {
-    __shared__ double2 s_tw[256];
+__global__ void __launch_bounds__(256) k_stft512(const float* __restrict__ y, Geometry g, Tables tb,
+                                                 float* __restrict__ mag, int total_frames) {
     __shared__ double2 s_buf[8][256];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x;
-    s_tw[tid] = tw_g[tid];
-    double w0[8], w1[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int m = lane + 32 * i;
-        w0[i] = win[2 * m];
-        w1[i] = win[2 * m + 1];
-    }
-    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int T = g.T, L = g.L, hop = g.hop;
     double2* buf = s_buf[warp];
-    const float* yb = y + (size_t)b * L;
-    for (int t = warp; t < T; t += 8) {
+    const double2* win2 = reinterpret_cast<const double2*>(tb.hann512);
+    for (int f = blockIdx.x * 8 + warp; f < total_frames; f += gridDim.x * 8) {
+        const int b = f / T, t = f - b * T;
+        const float* yb = y + (size_t)b * L;
         const int g0 = t * hop - 256;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int m = lane + 32 * i;
-            const int g = g0 + 2 * m;
-            const float x0 = (g >= 0 && g < L) ? __ldg(yb + g) : 0.f;
-            const float x1 = (g + 1 >= 0 && g + 1 < L) ? __ldg(yb + g + 1) : 0.f;
-            buf[m] = make_double2((double)x0 * w0[i], (double)x1 * w1[i]);
+            const int gi = g0 + 2 * m;                         // even; L is even
+            float2 v = make_float2(0.f, 0.f);
+            if (gi >= 0 && gi < L) v = __ldg(reinterpret_cast<const float2*>(yb + gi));
+            const double2 w = __ldg(win2 + m);
+            buf[swz(m)] = make_double2((double)v.x * w.x, (double)v.y * w.y);
         }
         __syncwarp();
-        fft_r4_dif<4, 32>(buf, s_tw, lane, SyncWarp());
-        float* out = mag + ((size_t)b * T + t) * kMagStride;
+        warp_fft_r4<4>(buf, tb.twp256, lane);
+        float* out = mag + (size_t)f * kMagStride;
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
             const int k = lane + 32 * i;
-            if (k <= 256) out[k] = c64_abs(rfft_bin<4>(buf, ptw, k));
+            if (k <= 256) out[k] = c64_abs(rfft_bin<4, true>(buf, tb.ptw512, k));
         }
         __syncwarp();
     }
 }
 
 void launch_stft512(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, cudaStream_t st) {
-    k_stft512<<<n, 256, 0, st>>>(y, g.L, g.T, g.hop, tb.hann512, tb.tw256, tb.ptw512, ws.mag512);
+    const int total = n * g.T;
+    int grid = (total + 7) / 8;
+    if (grid > 148 * 8 * 4) grid = 148 * 8 * 4;
+    k_stft512<<<grid, 256, 0, st>>>(y, g, tb, ws.mag512, total);
     note_launch();
 }
 
@@ -287,16 +282,10 @@ __device__ void role_mfcc(int b, const Geometry g, const Tables& tb, const Works
     float mn = FLT_MAX;
     for (int r = warp; r < 120; r += nw) {
         const int src = r % 40, ord = r / 40;
-        double s = 0.0, q = 0.0;
-        for (int t = lane; t < T; t += 32) {
-            const float v = ord == 0 ? MF[src * T + t] : delta_at(MF + src * T, t, T, ord);
-            OUT[r * T + t] = v;
-            s += (double)v;
-            q += (double)v * (double)v;
-        }
-        s = warp_sum(s);
-        q = warp_sum(q);
-        const ZTerm z = make_zterm(s, q, (double)T);
+        for (int t = lane; t < T; t += 32)
+            OUT[r * T + t] = ord == 0 ? MF[src * T + t] : delta_at(MF + src * T, t, T, ord);
+        __syncwarp();
+        const ZTerm z = np_row_zterm(OUT + r * T, T, lane);
         __syncwarp();
         for (int t = lane; t < T; t += 32) {
             const float v = z(OUT[r * T + t]);
@@ -426,15 +415,7 @@ __device__ void role_chroma_stft(int b, const Geometry g, const Tables& tb, cons
     float mn = FLT_MAX;
     float* o = plane_ptr(feats, b, BPC_CH_CHROMA, T);
     for (int r = warp; r < 12; r += nw) {
-        double s = 0.0, q = 0.0;
-        for (int t = lane; t < T; t += 32) {
-            const double v = (double)raw[r * T + t];
-            s += v;
-            q += v * v;
-        }
-        s = warp_sum(s);
-        q = warp_sum(q);
-        const ZTerm z = make_zterm(s, q, (double)T);
+        const ZTerm z = np_row_zterm(raw + r * T, T, lane);
         for (int t = lane; t < T; t += 32) {
             const float v = z(raw[r * T + t]);
             o[r * T + t] = v;

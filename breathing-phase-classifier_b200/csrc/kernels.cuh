@@ -22,6 +22,8 @@ struct Tables {
     const double2* tw1024;        // exp(-2 pi i j / 1024), j < 1024
     const double2* ptw512;        // exp(-2 pi i k / 512),  k <= 256
     const double2* ptw2048;       // exp(-2 pi i k / 2048), k <= 1024
+    const double2* twp256;        // per-pass twiddles of warp_fft_r4<4> (fft.cuh::twp_size(4) entries)
+    const double2* twp1024;       // per-pass twiddles of warp_fft_r4<5>
     // filterbanks
     BankDev mel_a, mel_b, mel_c, mel_d;
     const float* dct_mel;         // [40, 128]
@@ -47,7 +49,9 @@ struct Workspace {            // per chunk of `cap` segments
     int cap;
     float* y;                 // [cap, L]   float32 waveform after pad_or_truncate (only when ingest is needed)
     float* mag512;            // [cap, T, kMagStride]
-    float* mag2048_even;      // [cap, 1025, 32]  |STFT2048| of the hop-512 frames (rolloff + tuning-36)
+    float* mag2048;           // [cap, T, kMag2048Stride]  |STFT2048| (1025 valid bins per row)
+    double* frame_feat;       // [cap, T, 20]  per-frame centroid, bandwidth, flatness, contrast peaks / valleys
+    float* melD;              // [cap, T, 128] mel-D power columns
     int* tuning;              // [cap, 2]   tuning bin for 12 / 36 bins per octave
     float* chroma_min;        // [cap, 2]   min of the normalised chroma_stft / chroma_cens rows
     int* ints;                // [cap, 2]   n_peaks, first-min index
@@ -84,6 +88,8 @@ void launch_stft_db(int n, const Geometry& g, const Workspace& ws, float* stft_d
 void launch_logmel_only(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* mel3, cudaStream_t st);
 void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
                      float* scalars, cudaStream_t st);
+void launch_seg2048(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats, float* scalars,
+                    cudaStream_t st);
 void launch_even2048(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* scalars,
                      int32_t* status, cudaStream_t st);
 void launch_time_scalars(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws,

@@ -141,9 +141,9 @@ int  bpc_chunk_size(const bpc_handle* h);
 int64_t bpc_launch_count(const bpc_handle* h);
 
 /* Per-kernel device times (CUDA events around every launch of the full path) for bench.py's roofline leg.
- * ids: 0 ingest, 1 stft512, 2 spec512 consumers, 3 spec2048, 4 even2048, 5 cens, 6 time_basic+autocorr, 7 hilbert,
- * 8 lpc, 9 stats.  bpc_kernel_times synchronises, sums the elapsed ms / launch counts since the last call. */
-#define BPC_NUM_KERNEL_IDS 10
+ * ids: 0 ingest, 1 stft512, 2 spec512 consumers, 3 fft2048+feat2048, 4 even2048, 5 cens, 6 time_basic+autocorr,
+ * 7 hilbert, 8 lpc, 9 stats, 10 seg2048.  bpc_kernel_times synchronises, sums the elapsed ms / launch counts since the last call. */
+#define BPC_NUM_KERNEL_IDS 11
 int  bpc_set_kernel_timing(bpc_handle* h, int on);
 int  bpc_kernel_times(bpc_handle* h, double* ms_out, int64_t* launches_out, int n_ids);
 const char* bpc_kernel_name(int id);

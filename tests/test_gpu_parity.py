@@ -173,11 +173,23 @@ def test_silent_and_constant_segments(engine, torch_cuda):
     f, s, st = engine.precompute(torch.from_numpy(Y).cuda())
     f = f.cpu().numpy(); s = s.cpu().numpy(); st = st.cpu().numpy()
     assert st[0] & 8 and not (st[1] & 8)
-    ch, sc = P.segment_features(Y[0])
+    dbg = {}
+    ch, sc = P.segment_features(Y[0], debug=dbg)
     ref = P.stack_sorted(ch)
     assert np.all(np.isfinite(f[0]))
     for c, k in enumerate(bpc_b200.CHANNELS):
-        assert np.abs(f[0, c] - ref[c]).max() < 2e-4, k
+        rows = np.ones(128, dtype=bool)
+        if k == "mfcc":
+            # MFCC row 0 of silence is the constant -100 * sqrt(128); numpy's rounded float32 mean makes its z-score
+            # -0.99997 (reproduced).  Its delta / delta2 rows are scipy savgol rounding noise (1e-14 .. 2e-5) divided
+            # by ~1e-5, i.e. numerically undefined in the reference; they and the pad rows (filled with the plane
+            # minimum, which one of those noise rows supplies) are excluded.
+            raw = dbg["mfcc_raw"]
+            noise = np.array([0 < np.ptp(raw[r]) < 1e-3 for r in range(120)])
+            assert noise.sum() == 2
+            rows[:120] = ~noise
+            rows[120:] = False
+        assert np.abs(f[0, c][rows] - ref[c][rows]).max() < 2e-4, k
     assert np.array_equal(np.isnan(s[0]), np.isnan(sc))
     assert s[0, 22] == sc[22] == 0 and s[0, 35] == sc[35] == 0
 
