@@ -156,6 +156,15 @@ int build_tables(bpc_handle* h) {
     if ((rc = upload(h, twiddles(1024, 1024), &tb.tw1024))) return rc;
     if ((rc = upload(h, twiddles_per_pass(4), &tb.twp256))) return rc;
     if ((rc = upload(h, twiddles_per_pass(5), &tb.twp1024))) return rc;
+    {
+        std::vector<double2> t(32 * 32);
+        for (int k1 = 0; k1 < 32; ++k1)
+            for (int hh = 0; hh < 32; ++hh) {
+                const double ang = -2.0 * kPi * double(hh * k1) / 1024.0;
+                t[k1 * 32 + hh] = make_double2(std::cos(ang), std::sin(ang));
+            }
+        if ((rc = upload(h, t, &tb.twa1024))) return rc;
+    }
     if ((rc = upload(h, twiddles(512, 257), &tb.ptw512))) return rc;
     if ((rc = upload(h, twiddles(2048, 1025), &tb.ptw2048))) return rc;
     if ((rc = upload(h, twiddles(8000, 8000), &tb.tw8000))) return rc;
@@ -187,11 +196,15 @@ int build_tables(bpc_handle* h) {
         std::vector<int16_t> col;
         std::vector<float> re, im;
         std::vector<double> sl;
+        int ell_used = 1;
         for (int i = 0; i < kNumTunings; ++i) {
             CqtBasisEll e = cqt_basis(p.sr, edges[i]);
             if (e.col.empty()) { h->err = "CQT basis row wider than the ELL width"; return BPC_ERR_UNSUPPORTED; }
             for (int16_t c : e.col)
                 if (c >= 0 && (c < 60 || c > 144)) { h->err = "CQT basis support outside the staged bin window"; return BPC_ERR_UNSUPPORTED; }
+            for (int r = 0; r < kCqtBinsPerOct; ++r)
+                for (int j = 0; j < kCqtEllWidth; ++j)
+                    if (e.col[r * kCqtEllWidth + j] >= 0) ell_used = std::max(ell_used, j + 1);
             col.insert(col.end(), e.col.begin(), e.col.end());
             re.insert(re.end(), e.re.begin(), e.re.end());
             im.insert(im.end(), e.im.begin(), e.im.end());
@@ -201,8 +214,18 @@ int build_tables(bpc_handle* h) {
         if ((rc = upload(h, re, &tb.cqt_re))) return rc;
         if ((rc = upload(h, im, &tb.cqt_im))) return rc;
         if ((rc = upload(h, sl, &tb.cqt_sqrt_len))) return rc;
+        tb.cqt_ell_used = ell_used;
     }
-    if ((rc = upload(h, halfband_taps(), &tb.halfband))) return rc;
+    {
+        std::vector<double> hb = halfband_taps();
+        for (int d = 1; d <= 63; ++d)
+            if (hb[63 + d] != hb[63 - d] || ((d & 1) == 0 && std::fabs(hb[63 + d]) > 1e-15)) {
+                h->err = "half-band taps are not symmetric / half-band";
+                return BPC_ERR_UNSUPPORTED;
+            }
+        upload_cens_constants(hb.data());
+        if ((rc = upload(h, hb, &tb.halfband))) return rc;
+    }
     return BPC_OK;
 }
 
@@ -214,7 +237,7 @@ int build_workspace(bpc_handle* h) {
     w.cap = h->chunk;
     if ((rc = dalloc(h, C * g.L, &w.y))) return rc;
     if ((rc = dalloc(h, C * T * kMagStride, &w.mag512))) return rc;
-    if ((rc = dalloc(h, C * T * kMag2048Stride, &w.mag2048))) return rc;
+    if ((rc = dalloc(h, C * ((T + 1) / 2) * kMag2048Stride, &w.mag_even))) return rc;
     if ((rc = dalloc(h, C * T * 20, &w.frame_feat))) return rc;
     if ((rc = dalloc(h, C * T * 128, &w.melD))) return rc;
     if ((rc = dalloc(h, C * 2, &w.tuning))) return rc;

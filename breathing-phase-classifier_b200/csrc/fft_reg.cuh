@@ -1,0 +1,176 @@
+// Register-resident FP64 FFTs for sm_100a: every lane keeps R complex points in registers, does a radix-R DFT on them
+// with compile-time twiddles, and the lanes of a team exchange data ONCE through shared memory (four-step FFT:
+// N = R x R).  Compared with the shared-memory radix-4 passes of fft.cuh this moves 2 * 16 B per point through the
+// shared-memory pipe instead of 2 * 16 B per point per pass (5 passes for N = 1024) and has no per-butterfly index
+// arithmetic -- the r01 v1 profile showed those kernels bound by shared-memory wavefronts / issue slots with the FP64
+// pipe 10-20 % busy.
+//
+//   team_fft<16>  N = 256   16 lanes x 16 points  (two independent transforms per warp)   real FFT-512  (STFT-512, CQT)
+//   team_fft<32>  N = 1024  32 lanes x 32 points  (one transform per warp)                real FFT-2048 (STFT-2048, autocorr)
+//
+// Everything is __host__ __device__ and lane-explicit so tests/fft_host_test.cpp can run the exact index logic on the
+// CPU (there is no GPU in the build container).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace bpc {
+
+#ifndef BPC_HD
+#define BPC_HD __host__ __device__ __forceinline__
+#endif
+
+// cos(2 pi i / 64), i = 0..16 (quarter wave); everything else by symmetry.
+BPC_HD constexpr double cos64_q(int i) {
+    switch (i) {
+        case 0: return 1.0;
+        case 1: return 0.99518472667219688624;
+        case 2: return 0.98078528040323044913;
+        case 3: return 0.95694033573220886494;
+        case 4: return 0.92387953251128675613;
+        case 5: return 0.88192126434835502971;
+        case 6: return 0.83146961230254523708;
+        case 7: return 0.77301045336273696081;
+        case 8: return 0.70710678118654752440;
+        case 9: return 0.63439328416364549822;
+        case 10: return 0.55557023301960222474;
+        case 11: return 0.47139673682599764856;
+        case 12: return 0.38268343236508977173;
+        case 13: return 0.29028467725446236764;
+        case 14: return 0.19509032201612826785;
+        case 15: return 0.09801714032956060199;
+        default: return 0.0;
+    }
+}
+// cos / sin of 2 pi i / 64 for any integer i >= 0
+BPC_HD constexpr double cos64(int i) {
+    i &= 63;
+    return i <= 16 ? cos64_q(i) : (i <= 32 ? -cos64_q(32 - i) : (i <= 48 ? -cos64_q(i - 32) : cos64_q(64 - i)));
+}
+BPC_HD constexpr double sin64(int i) { return cos64(i + 48); }   // sin(x) = cos(x - pi/2) = cos(x + 3 pi / 2)
+
+BPC_HD double2 c_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+BPC_HD double2 c_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+BPC_HD double2 c_mul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+}
+
+// d * exp(-2 pi i * I / R) with a compile-time twiddle
+template <int R, int I>
+BPC_HD double2 mul_tw(double2 d) {
+    constexpr int q = (I * (64 / R)) & 63;                  // position on the 64-point circle
+    if (q == 0) return d;
+    if (q == 16) return make_double2(d.y, -d.x);            // -i
+    if (q == 32) return make_double2(-d.x, -d.y);
+    if (q == 48) return make_double2(-d.y, d.x);            // +i
+    constexpr double c = cos64(q), s = -sin64(q);           // exp(-i th) = c + i s
+    return make_double2(fma(d.x, c, -(d.y * s)), fma(d.x, s, d.y * c));
+}
+
+// In-place radix-2 decimation-in-frequency DFT of R register-resident points a[OFF .. OFF + R).
+// On return a[OFF + bitrev_R(k)] = X[k].
+template <int R, int OFF>
+struct DifR {
+    template <int I>
+    static BPC_HD void bfly(double2* a) {
+        const double2 u = a[OFF + I], v = a[OFF + I + R / 2];
+        a[OFF + I] = c_add(u, v);
+        a[OFF + I + R / 2] = mul_tw<R, I>(c_sub(u, v));
+    }
+    template <int I>
+    static BPC_HD void loop(double2* a) {
+        if constexpr (I < R / 2) {
+            bfly<I>(a);
+            loop<I + 1>(a);
+        }
+    }
+    static BPC_HD void run(double2* a) {
+        loop<0>(a);
+        DifR<R / 2, OFF>::run(a);
+        DifR<R / 2, OFF + R / 2>::run(a);
+    }
+};
+template <int OFF>
+struct DifR<1, OFF> {
+    static BPC_HD void run(double2*) {}
+};
+
+template <int R>
+BPC_HD constexpr int bitrev(int k) {
+    int r = 0;
+    for (int b = 1; b < R; b <<= 1) { r = (r << 1) | (k & 1); k >>= 1; }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ team FFT
+// N = R * R points, a team of R lanes (lane id h in [0, R)), R points per lane.
+//   in : a[j]            = x[h + R j]
+//   out: a[bitrev_R(k2)] = X[h + R k2]
+// xch: shared-memory exchange buffer of R * (R + 1) double2 per team (row pitch R + 1 keeps both the row-major stores
+//      and the column reads free of bank conflicts);  tw: per-lane inter-stage twiddles, tw[k1] = exp(-2 pi i h k1 / N),
+//      k1 = 1 .. R-1 (index 0 unused), typically registers filled once per kernel by team_fft_twiddles().
+// The caller provides the team-wide execution barrier between the two halves (`__syncwarp()` on the device; the host
+// test simply runs all lanes of stage A before stage B).
+// tw points at this lane's first twiddle, element k1 is tw[k1 * tws]: a register array (tws = 1) or a table laid out
+// [k1][h] (tw = table + h, tws = R).
+template <int R>
+BPC_HD void team_fft_stage_a(double2* a, const double2* tw, int tws, double2* xch, int h) {
+    DifR<R, 0>::run(a);
+#pragma unroll
+    for (int k1 = 0; k1 < R; ++k1) {
+        double2 v = a[bitrev<R>(k1)];
+        if (k1 > 0) v = c_mul(v, tw[k1 * tws]);
+        xch[k1 * (R + 1) + h] = v;
+    }
+}
+template <int R>
+BPC_HD void team_fft_stage_b(double2* a, const double2* xch, int h) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) a[j] = xch[h * (R + 1) + j];
+    DifR<R, 0>::run(a);
+}
+
+// ------------------------------------------------------------------------------- real-input split (rfft of 2N reals)
+// The 2N real samples were packed as z[m] = x[2m] + i x[2m+1]; Z = FFT_N(z) sits in the team's registers as left by
+// team_fft_stage_b.  X[k] = (Z[k] + conj(Z[N-k])) / 2 - i w^k (Z[k] - conj(Z[N-k])) / 2,  w = exp(-2 pi i / 2N).
+// Bin k = h + R k2 pairs with N - k, which lives in lane (R - h) % R at k2' = R - 1 - k2 (h != 0) or (R - k2) % R (h == 0).
+// rsplit_term<R, K2>(zk, zn, wl) returns 2 X[h + R K2] given zn = Z[N - k]; wl = -i * exp(-2 pi i h / 2N) (per lane).
+template <int R, int K2>
+BPC_HD double2 rsplit_term(double2 zk, double2 zn, double2 wl) {
+    const double2 s = make_double2(zk.x + zn.x, zk.y - zn.y);           // zk + conj(zn)
+    const double2 d = make_double2(zk.x - zn.x, zk.y + zn.y);           // zk - conj(zn)
+    const double2 w = mul_tw<2 * R, K2>(wl);                            // -i * exp(-2 pi i (h + R K2) / 2N)
+    return make_double2(s.x + fma(w.x, d.x, -(w.y * d.y)), s.y + fma(w.x, d.y, w.y * d.x));
+}
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------ device wrappers
+// Full transform for a team of R lanes inside one warp (R = 16: two teams per warp, R = 32: the warp).  All 32 lanes of
+// the warp must call it together.  `xch` is the team's exchange buffer (R * (R + 1) double2).
+template <int R>
+__device__ __forceinline__ void team_fft(double2* a, const double2* tw, int tws, double2* xch, int h) {
+    team_fft_stage_a<R>(a, tw, tws, xch, h);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < R; ++j) a[j] = xch[h * (R + 1) + j];
+    __syncwarp();                       // the buffer may be rewritten (next frame) once every lane has read its row
+    DifR<R, 0>::run(a);
+}
+
+// Real-input split over bins k = h + R k2, k2 in [K2, K2HI]: calls emit(k, 2 X[k]).  `partner` is the warp lane that
+// holds row (R - h) % R of the same team.  Must be called by all 32 lanes (shuffles).
+template <int R, int K2, int K2HI, class Emit>
+__device__ __forceinline__ void team_rsplit(const double2* a, double2 wl, int h, int partner, Emit& emit) {
+    if constexpr (K2 <= K2HI) {
+        const double2 zk = a[bitrev<R>(K2)];
+        const double2 src = a[bitrev<R>(R - 1 - K2)];
+        double2 zn;
+        zn.x = __shfl_sync(0xffffffffu, src.x, partner);
+        zn.y = __shfl_sync(0xffffffffu, src.y, partner);
+        if (h == 0) zn = a[bitrev<R>((R - K2) % R)];
+        emit(h + R * K2, rsplit_term<R, K2>(zk, zn, wl));
+        team_rsplit<R, K2 + 1, K2HI>(a, wl, h, partner, emit);
+    }
+}
+#endif
+
+}  // namespace bpc

@@ -2,141 +2,238 @@
 //   = 7-octave / 36-bins-per-octave constant-Q transform (multi-rate recursion: rectangular-window STFT-512 of the
 //     signal decimated by 2 per octave, times one sparse complex basis that is the same for every octave),
 //     |.| / sqrt(filter length), fold 252 -> 12, L1 normalise, 4-level quantise, 41-tap Hann smoothing, L2 normalise.
-// One CTA per segment; one warp owns a frame t and walks the 7 octaves, so the 12 chroma sums stay in registers.
+// One CTA per segment (r01 v2 layout):
+//   phase 1  six cascaded 2:1 half-band decimations, each thread producing 4 consecutive outputs from a register
+//            window of FP64 samples (the signals live in shared memory de-interleaved into even / odd samples, which is
+//            also the complex packing the real FFT wants);
+//   phase 2  one half-warp per frame walks the 7 octaves: team_fft<16> (fft_reg.cuh) on 512 samples, real split of the
+//            85 bins the sparsified bases touch, FP32 sparse complex product, fold to 12 chroma sums kept in registers;
+//   phase 3  CENS post-processing on the [12, T] tile.
 // The decimator stands in for soxr_hq (absent library): the same 127-tap Kaiser half-band the oracle uses.
 #include <cmath>
 #include "kernels.cuh"
 #include "fft.cuh"
+#include "fft_reg.cuh"
 #include "tables.hpp"
 
 namespace bpc {
 
 constexpr int kBinLo = 60, kBinHi = 144;               // rfft bins the sparsified bases can touch (measured 62..141)
 constexpr int kBinSpan = kBinHi - kBinLo + 1;
+constexpr int kCensThreads = 256, kCensTeams = kCensThreads / 16;
+constexpr int kOutPerThread = 4;
+constexpr int kWin = 63 + kOutPerThread;                // odd-sample window of one thread
+
+// half-band taps in constant memory: centre tap and the 32 odd-offset taps g[m] = h[63 + 2m + 1] (the even offsets of
+// a half-band filter are zero, the filter is symmetric)
+__constant__ double c_hb_centre;
+__constant__ double c_hb_odd[32];
+
+void upload_cens_constants(const double* taps127) {
+    double odd[32];
+    for (int m = 0; m < 32; ++m) odd[m] = taps127[63 + 2 * m + 1];
+    cudaMemcpyToSymbol(c_hb_centre, taps127 + 63, sizeof(double));
+    cudaMemcpyToSymbol(c_hb_odd, odd, sizeof(odd));
+}
+
+// padded position of sample q in a de-interleaved array: one pad word per 32 keeps the stride-4 accesses of the
+// decimator (thread i reads q = 4 i + c) on 32 distinct banks
+__device__ __forceinline__ int ppos(int q) { return q + (q >> 5); }
+__host__ __device__ constexpr int plen(int n) { return n + (n >> 5) + 1; }
+
+// de-interleaved signals of octaves 1..6 (lengths 8000 .. 250 -> halves 4000 .. 125)
+constexpr int kHalf1 = 4000, kHalf2 = 2000, kHalf3 = 1000, kHalf4 = 500, kHalf5 = 250, kHalf6 = 125;
+constexpr int kDecFloats = 2 * (plen(kHalf1) + plen(kHalf2) + plen(kHalf3) + plen(kHalf4) + plen(kHalf5) + plen(kHalf6));
 
 struct CensSmem {
-    float dec[8000 + 4000 + 2000 + 1000 + 500 + 250 + 64];   // decimated signals, octaves 1..6
-    double2 fbuf[8][256];
-    float2 spec[8][kBinSpan + 3];
-    float cqmag[8][kCqtBinsPerOct];
+    union {
+        double2 xch[kCensTeams][16 * 17];              // phase 2: FFT exchange buffers
+        float y0[2 * plen(8000)];                      // phase 1: the input, de-interleaved (even | odd)
+    } u;
+    float dec[kDecFloats];                             // octaves 1..6: [even | odd] per octave
+    float2 spec[kCensTeams][kBinSpan + 3];
+    float cqmag[kCensTeams][kCqtBinsPerOct + 4];
+    float2 basis[2][kCqtBinsPerOct * kCqtEllWidth];    // [0]: basis, [1]: basis * sqrt(2) (odd octaves), (re, im)
+    short bcol[kCqtBinsPerOct * kCqtEllWidth];         // column - kBinLo; padding entries point at 0 with weight 0
+    double inv_sl[kCqtBins];                           // 1 / sqrt(lengths)
     float chroma[12 * kMaxFrames];
     float quant[12 * kMaxFrames];
-    double hb[kHalfbandTaps];
     double swin[43];
     double dscratch[32];
     float fscratch[32];
 };
 
-__global__ void __launch_bounds__(256) k_cens(const float* __restrict__ y, Geometry g, Tables tb, Workspace ws,
-                                              float* feats) {
+// One decimation stage: in (de-interleaved, half-length hin, i.e. 2 hin samples) -> out (de-interleaved, hin samples).
+// out[n] = f32( (h63 * E[n] + sum_m g[m] * (O[n-1-m] + O[n+m])) / sqrt(0.5) ),  E[q] = in[2q], O[q] = in[2q+1].
+__device__ __forceinline__ void decimate_stage(const float* __restrict__ inE, const float* __restrict__ inO, int hin,
+                                               float* __restrict__ outE, float* __restrict__ outO, int tid) {
+    const double inv_s = 1.0 / sqrt(0.5);
+    for (int n0 = kOutPerThread * tid; n0 < hin; n0 += kOutPerThread * kCensThreads) {
+        double w[kWin];
+#pragma unroll
+        for (int q = 0; q < kWin; ++q) {
+            const int qq = n0 - 32 + q;
+            w[q] = (qq >= 0 && qq < hin) ? (double)inO[ppos(qq)] : 0.0;
+        }
+#pragma unroll
+        for (int p = 0; p < kOutPerThread; ++p) {
+            const int n = n0 + p;
+            if (n < hin) {
+                double acc = c_hb_centre * (double)inE[ppos(n)];
+#pragma unroll
+                for (int m = 0; m < 32; ++m) acc = fma(c_hb_odd[m], w[p + 31 - m] + w[p + 32 + m], acc);
+                const float v = (float)(acc * inv_s);
+                if (n & 1) outO[ppos(n >> 1)] = v;
+                else outE[ppos(n >> 1)] = v;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kCensThreads, 1) k_cens(const float* __restrict__ y, Geometry g, Tables tb,
+                                                          Workspace ws, float* feats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CensSmem& S = *reinterpret_cast<CensSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x, L = g.L, T = g.T;
     const float* yb = y + (size_t)b * L;
+    const float2* y2 = reinterpret_cast<const float2*>(yb);
 
-    for (int i = tid; i < kHalfbandTaps; i += 256) S.hb[i] = tb.halfband[i];
+    // ---- stage the input (even | odd), the basis of this segment's tuning, the smoothing window
+    {
+        float* E0 = S.u.y0;
+        float* O0 = S.u.y0 + plen(8000);
+        for (int m = tid; m < 8000; m += kCensThreads) {
+            float2 v = make_float2(0.f, 0.f);
+            if (2 * m < L) v = __ldg(y2 + m);
+            E0[ppos(m)] = v.x;
+            O0[ppos(m)] = v.y;
+        }
+    }
+    const int tun = ws.tuning[b * 2 + 1];
+    {
+        const int16_t* bcol = tb.cqt_col + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
+        const float* bre = tb.cqt_re + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
+        const float* bim = tb.cqt_im + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
+        const double sqrt2 = sqrt(2.0);
+        for (int i = tid; i < kCqtBinsPerOct * kCqtEllWidth; i += kCensThreads) {
+            const int c = bcol[i];
+            const float re = c < 0 ? 0.f : bre[i], im = c < 0 ? 0.f : bim[i];
+            S.bcol[i] = (short)(c < 0 ? 0 : c - kBinLo);
+            S.basis[0][i] = make_float2(re, im);
+            // fft_basis *= sqrt(sr / my_sr) rounded to complex64: odd octaves carry a factor sqrt(2); the remaining
+            // power of two is applied to the (linear) response, which is exact
+            S.basis[1][i] = make_float2((float)((double)re * sqrt2), (float)((double)im * sqrt2));
+        }
+        const double* slen = tb.cqt_sqrt_len + (size_t)tun * kCqtBins;
+        for (int i = tid; i < kCqtBins; i += kCensThreads) S.inv_sl[i] = 1.0 / slen[i];
+    }
     if (tid < 43) {
         // scipy.signal.get_window('hann', 43, fftbins=False), normalised to unit sum in the smoothing loop below
         S.swin[tid] = 0.5 - 0.5 * cos(2.0 * 3.14159265358979323846 * (double)tid / 42.0);
     }
     __syncthreads();
 
-    // ---- six cascaded 2:1 decimations: out[n] = f32( sum_k h[k] * in[2n + 63 - k] / sqrt(0.5) ), zero extension
-    int len_in = L, off_out = 0;
-    const float* in_g = yb;
-    const float* in_s = nullptr;
-    int offs[7], lens[7];
-    offs[0] = -1; lens[0] = L;
-    const double inv_s = 1.0 / sqrt(0.5);
-    for (int o = 1; o <= 6; ++o) {
-        const int len_out = (len_in + 1) / 2;
-        for (int n = tid; n < len_out; n += 256) {
-            const int c0 = 2 * n;
-            double acc = 0.0;
-            // centre tap
-            {
-                const float v = c0 < len_in ? (in_s ? in_s[c0] : __ldg(in_g + c0)) : 0.f;
-                acc = S.hb[63] * (double)v;
-            }
-            // odd offsets (the even-offset taps of a half-band filter vanish)
-#pragma unroll 4
-            for (int d = 1; d <= 63; d += 2) {
-                const int i0 = c0 - d, i1 = c0 + d;
-                const float v0 = (i0 >= 0 && i0 < len_in) ? (in_s ? in_s[i0] : __ldg(in_g + i0)) : 0.f;
-                const float v1 = (i1 >= 0 && i1 < len_in) ? (in_s ? in_s[i1] : __ldg(in_g + i1)) : 0.f;
-                acc += S.hb[63 + d] * (double)v0 + S.hb[63 - d] * (double)v1;
-            }
-            S.dec[off_out + n] = (float)(acc * inv_s);
+    // ---- phase 1: six cascaded 2:1 decimations
+    const int halves[7] = {8000, kHalf1, kHalf2, kHalf3, kHalf4, kHalf5, kHalf6};
+    int offE[7], offO[7];                                   // offsets into S.dec (octaves 1..6)
+    {
+        int p = 0;
+#pragma unroll
+        for (int o = 1; o <= 6; ++o) {
+            offE[o] = p;
+            offO[o] = p + plen(halves[o]);
+            p += 2 * plen(halves[o]);
         }
+        offE[0] = offO[0] = 0;
+    }
+    decimate_stage(S.u.y0, S.u.y0 + plen(8000), halves[0], S.dec + offE[1], S.dec + offO[1], tid);
+    __syncthreads();
+#pragma unroll
+    for (int o = 2; o <= 6; ++o) {
+        decimate_stage(S.dec + offE[o - 1], S.dec + offO[o - 1], halves[o - 1], S.dec + offE[o], S.dec + offO[o], tid);
         __syncthreads();
-        offs[o] = off_out; lens[o] = len_out;
-        in_s = S.dec + off_out;
-        in_g = nullptr;
-        off_out += len_out;
-        len_in = len_out;
     }
 
-    // ---- CQT -> chroma fold, one warp per frame
-    const int tun = ws.tuning[b * 2 + 1];
-    const int16_t* bcol = tb.cqt_col + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
-    const float* bre = tb.cqt_re + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
-    const float* bim = tb.cqt_im + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
-    const double* slen = tb.cqt_sqrt_len + (size_t)tun * kCqtBins;
-    double2* buf = S.fbuf[warp];
-    for (int t = warp; t < T; t += 8) {
-        float csum = 0.f;                                        // lanes 0..11: chroma c = lane
-        for (int o = 0; o < kCqtOctaves; ++o) {
-            const int hop = g.hop >> o;
-            const int lo = lens[o];
-            const float* sg = o == 0 ? nullptr : S.dec + offs[o];
-            const int g0 = t * hop - 256;
+    // ---- phase 2: CQT -> chroma fold, one half-warp per frame, 7 octaves each
+    const int h = lane & 15, team = tid >> 4;
+    const int partner = (lane & 16) | ((16 - h) & 15);
+    double2* xch = S.u.xch[team];
+    double2 tw[16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int m = lane + 32 * i;
-                const int gi = g0 + 2 * m;
-                float x0 = 0.f, x1 = 0.f;
-                if (gi >= 0 && gi < lo) x0 = sg ? sg[gi] : __ldg(yb + gi);
-                if (gi + 1 >= 0 && gi + 1 < lo) x1 = sg ? sg[gi + 1] : __ldg(yb + gi + 1);
-                buf[swz(m)] = make_double2((double)x0, (double)x1);   // window = 'ones'
-            }
-            __syncwarp();
-            warp_fft_r4<4>(buf, tb.twp256, lane);
-            for (int k = kBinLo + lane; k <= kBinHi; k += 32) {
-                const double2 X = rfft_bin<4, true>(buf, tb.ptw512, k);
-                S.spec[warp][k - kBinLo] = make_float2((float)X.x, (float)X.y);   // complex64 STFT
-            }
-            __syncwarp();
-            const double scale = sqrt((double)(1 << o));           // fft_basis *= sqrt(sr / my_sr)
-            for (int r = lane; r < kCqtBinsPerOct; r += 32) {
-                double cr = 0.0, ci = 0.0;
-                for (int j = 0; j < kCqtEllWidth; ++j) {
-                    const int col = bcol[r * kCqtEllWidth + j];
-                    if (col < 0) break;
-                    const float br = (float)((double)bre[r * kCqtEllWidth + j] * scale);
-                    const float bi = (float)((double)bim[r * kCqtEllWidth + j] * scale);
-                    const float2 d = S.spec[warp][col - kBinLo];
-                    cr += (double)br * (double)d.x - (double)bi * (double)d.y;
-                    ci += (double)br * (double)d.y + (double)bi * (double)d.x;
+    for (int k1 = 0; k1 < 16; ++k1) tw[k1] = __ldg(tb.tw256 + ((h * k1) & 255));
+    const double2 wp = __ldg(tb.ptw512 + h);
+    const double2 wl = make_double2(wp.y, -wp.x);                         // -i * exp(-2 pi i h / 512)
+    float2* spec = S.spec[team];
+    float* cqmag = S.cqmag[team];
+    const int ell_used = tb.cqt_ell_used;
+    for (int t0 = 2 * warp; t0 < T; t0 += kCensTeams) {
+        const int t = t0 + (lane >> 4);
+        const bool valid = t < T;
+        float csum = 0.f;                                        // lanes h < 12: chroma c = h
+#pragma unroll 1
+        for (int o = 0; o < kCqtOctaves; ++o) {
+            const int c0 = (valid ? t : 0) * (128 >> o) - 128;   // first complex sample of the frame
+            double2 a[16];
+            if (o == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int q = c0 + h + 16 * j;
+                    float2 v = make_float2(0.f, 0.f);
+                    if (q >= 0 && 2 * q < L) v = __ldg(y2 + q);
+                    a[j] = make_double2((double)v.x, (double)v.y);   // window = 'ones'
                 }
-                // complex64 response, then V /= sqrt(lengths) (complex128 math, complex64 store), then |V|
-                const float r32 = (float)cr, i32 = (float)ci;
-                const double sl = slen[kCqtBins - kCqtBinsPerOct * (o + 1) + r];
-                S.cqmag[warp][r] = c64_abs(make_double2((double)r32 / sl, (double)i32 / sl));
+            } else {
+                const float* E = S.dec + offE[o];
+                const float* O = S.dec + offO[o];
+                const int hin = halves[o];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int q = c0 + h + 16 * j;
+                    float vx = 0.f, vy = 0.f;
+                    if (q >= 0 && q < hin) { vx = E[ppos(q)]; vy = O[ppos(q)]; }
+                    a[j] = make_double2((double)vx, (double)vy);
+                }
+            }
+            team_fft<16>(a, tw, 1, xch, h);
+            auto emit = [&](int k, double2 t2) {
+                if (k >= kBinLo && k <= kBinHi)
+                    spec[k - kBinLo] = make_float2((float)(0.5 * t2.x), (float)(0.5 * t2.y));   // complex64 STFT
+            };
+            team_rsplit<16, 3, 9>(a, wl, h, partner, emit);
+            __syncwarp();
+            const float2* bas = S.basis[o & 1];
+            const float pow2 = (float)(1 << (o >> 1));
+            const double* isl = S.inv_sl + (kCqtBins - kCqtBinsPerOct * (o + 1));
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+                const int r = h + 16 * rr;
+                if (r < kCqtBinsPerOct) {
+                    float cr = 0.f, ci = 0.f;
+                    for (int j = 0; j < ell_used; ++j) {
+                        const float2 w = bas[r * kCqtEllWidth + j];
+                        const float2 d = spec[S.bcol[r * kCqtEllWidth + j]];
+                        cr = fmaf(w.x, d.x, cr); cr = fmaf(-w.y, d.y, cr);
+                        ci = fmaf(w.x, d.y, ci); ci = fmaf(w.y, d.x, ci);
+                    }
+                    // complex64 response, then V /= sqrt(lengths) (complex128 math, complex64 store), then |V|
+                    const double sl = isl[r];
+                    cqmag[r] = c64_abs(make_double2((double)(cr * pow2) * sl, (double)(ci * pow2) * sl));
+                }
             }
             __syncwarp();
-            if (lane < 12) {
+            if (h < 12) {
                 // cq_to_chroma: chroma c sums bins {3c-1, 3c, 3c+1} (mod 36) of every octave
-                const int j0 = (3 * lane + 35) % 36;
-                csum += S.cqmag[warp][j0] + S.cqmag[warp][3 * lane] + S.cqmag[warp][3 * lane + 1];
+                const int j0 = (3 * h + 35) % 36;
+                csum += cqmag[j0] + cqmag[3 * h] + cqmag[3 * h + 1];
             }
             __syncwarp();
         }
-        if (lane < 12) S.chroma[lane * T + t] = csum;
+        if (h < 12 && valid) S.chroma[h * T + t] = csum;
     }
     __syncthreads();
     // ---- CENS post-processing per column: L1 normalise, quantise
-    for (int t = tid; t < T; t += 256) {
+    for (int t = tid; t < T; t += kCensThreads) {
         double l1 = 0.0;
         for (int c = 0; c < 12; ++c) l1 += fabs((double)S.chroma[c * T + t]);
         if (l1 < 1.17549435e-38) l1 = 1.0;
@@ -149,7 +246,7 @@ __global__ void __launch_bounds__(256) k_cens(const float* __restrict__ y, Geome
     // 41 non-zero taps of hann(43) / sum, scipy.ndimage.convolve(mode='constant') along time
     double wsum = 0.0;
     for (int j = 0; j < 43; ++j) wsum += S.swin[j];
-    for (int i = tid; i < 12 * T; i += 256) {
+    for (int i = tid; i < 12 * T; i += kCensThreads) {
         const int c = i / T, t = i - c * T;
         double acc = 0.0;
         for (int j = 0; j < 43; ++j) {
@@ -160,7 +257,7 @@ __global__ void __launch_bounds__(256) k_cens(const float* __restrict__ y, Geome
     }
     __syncthreads();
     // L2 normalise each column
-    for (int t = tid; t < T; t += 256) {
+    for (int t = tid; t < T; t += kCensThreads) {
         double l2 = 0.0;
         for (int c = 0; c < 12; ++c) l2 += (double)S.chroma[c * T + t] * (double)S.chroma[c * T + t];
         l2 = sqrt(l2);
@@ -170,12 +267,12 @@ __global__ void __launch_bounds__(256) k_cens(const float* __restrict__ y, Geome
     __syncthreads();
     if (ws.dbg_chroma_cens) {
         float* d = ws.dbg_chroma_cens + (size_t)b * 12 * T;
-        for (int i = tid; i < 12 * T; i += 256) d[i] = S.quant[i];
+        for (int i = tid; i < 12 * T; i += kCensThreads) d[i] = S.quant[i];
     }
     // ---- row-wise z-score -> rows 12..23; pad rows 24..127 with the min over all 24 normalised rows
     float mn = FLT_MAX;
     float* o = plane_ptr(feats, b, BPC_CH_CHROMA, T);
-    for (int r = warp; r < 12; r += 8) {
+    for (int r = warp; r < 12; r += kCensThreads / 32) {
         const ZTerm z = np_row_zterm(S.quant + r * T, T, lane);
         for (int t = lane; t < T; t += 32) {
             const float v = z(S.quant[r * T + t]);
@@ -185,7 +282,7 @@ __global__ void __launch_bounds__(256) k_cens(const float* __restrict__ y, Geome
     }
     mn = block_min(mn, S.fscratch);
     const float fill = fminf(mn, ws.chroma_min[b * 2 + 0]);
-    for (int i = 24 * T + tid; i < kPlaneRows * T; i += 256) o[i] = fill;
+    for (int i = 24 * T + tid; i < kPlaneRows * T; i += kCensThreads) o[i] = fill;
     if (tid == 0) ws.chroma_min[b * 2 + 1] = mn;
 }
 
@@ -196,7 +293,7 @@ void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, con
         cudaFuncSetAttribute(k_cens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CensSmem));
         done = true;
     }
-    k_cens<<<n, 256, sizeof(CensSmem), st>>>(y, g, tb, ws, feats);
+    k_cens<<<n, kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats);
     note_launch();
 }
 

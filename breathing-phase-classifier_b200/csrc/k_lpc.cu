@@ -7,92 +7,121 @@
 namespace bpc {
 
 constexpr int kLpcFrame = 400, kLpcShift = 160, kLpcOrder = 12, kLpcMaxFrames = 112;
+constexpr int kLpcThreads = 128;
+constexpr int kLpcPer = 13;                            // samples per lane: 13 * 31 = 403 >= 400
 
 struct LpcSmem {
-    double fa[8][kLpcFrame];          // forward errors, indexed by sample
-    double ba[8][kLpcFrame];          // backward errors
     float coef[kLpcOrder * kLpcMaxFrames];
     double dscratch[32];
     float fscratch[32];
 };
 
-__global__ void __launch_bounds__(256) k_lpc(const float* __restrict__ y, Geometry g, Tables tb, Workspace ws,
-                                             float* feats) {
+// Burg iteration I on register-resident error signals (r01 v2: v1 kept them in shared memory and was bound by its
+// 94 %-busy load/store pipe).  Lane l owns samples n = 13 l + q.  B[q] = bwd[n]; the forward error that pairs with it,
+// fwd[n + 1 + I], sits in F[(q + I) % 13]: the per-iteration shift fwd = fwd[1:] is a renaming plus one element handed
+// down from the next lane.
+template <int I>
+__device__ __forceinline__ void burg_step(double (&F)[kLpcPer], double (&B)[kLpcPer], double& a_lane, double& den,
+                                          int lane) {
+    constexpr int len = kLpcFrame - 1 - I;              // valid pairs: n < len
+    const double eps = 2.2250738585072014e-308;         // util.tiny(float64)
+    const int nv = len - kLpcPer * lane;                 // q < nv is valid in this lane
+    double num = 0.0;
+#pragma unroll
+    for (int q = 0; q < kLpcPer; ++q) num = fma(q < nv ? B[q] : 0.0, F[(q + I) % kLpcPer], num);
+    num = warp_sum(num);
+    const double k = (num * -2.0) / (den + eps);
+    // Levinson update a[j] = a_prev[j] + k * a_prev[I - j + 1], j = 1 .. I + 1; lane j holds a[j] (a[0] = 1, rest 0)
+    {
+        const int src = I + 1 - lane;
+        const double mirror = __shfl_sync(0xffffffffu, a_lane, src & 31);
+        if (lane >= 1 && lane <= I + 1) a_lane = a_lane + k * mirror;
+    }
+#pragma unroll
+    for (int q = 0; q < kLpcPer; ++q) {
+        if (q < nv) {
+            const double f = F[(q + I) % kLpcPer], bw = B[q];
+            F[(q + I) % kLpcPer] = f + k * bw;
+            B[q] = bw + k * f;
+        }
+    }
+    // den = (1 - k^2) den - bwd[-1]^2 - fwd[0]^2 with the updated errors
+    const double f0 = __shfl_sync(0xffffffffu, F[I % kLpcPer], 0);
+    const double bl = __shfl_sync(0xffffffffu, B[(len - 1) % kLpcPer], (len - 1) / kLpcPer);
+    den = (1.0 - k * k) * den - bl * bl - f0 * f0;
+    // fwd = fwd[1:]: the slot of this lane's first element receives the next lane's first element
+    F[I % kLpcPer] = __shfl_down_sync(0xffffffffu, F[I % kLpcPer], 1);
+}
+
+template <int I>
+__device__ __forceinline__ void burg_all(double (&F)[kLpcPer], double (&B)[kLpcPer], double& a_lane, double& den,
+                                         int lane) {
+    if constexpr (I < kLpcOrder) {
+        burg_step<I>(F, B, a_lane, den, lane);
+        burg_all<I + 1>(F, B, a_lane, den, lane);
+    }
+}
+
+__global__ void __launch_bounds__(kLpcThreads, 3) k_lpc(const float* __restrict__ y, Geometry g, Tables tb, Workspace ws,
+                                                float* feats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LpcSmem& S = *reinterpret_cast<LpcSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x, L = g.L, T = g.T, F = g.lpc_frames;
+    const int b = blockIdx.x, L = g.L, T = g.T, F_ = g.lpc_frames;
     const float* yb = y + (size_t)b * L;
-    double* FA = S.fa[warp];
-    double* BA = S.ba[warp];
-    const double eps = 2.2250738585072014e-308;             // util.tiny(float64)
 
-    for (int fr = warp; fr < F; fr += 8) {
+    for (int fr = warp; fr < F_; fr += kLpcThreads / 32) {
         const int start = fr * kLpcShift;
-        for (int n = lane; n < kLpcFrame; n += 32) {
-            const int gi = start + n;
-            // y_emph = append(y[0], y[1:] - 0.97 * y[:-1])   (float32)
-            const float e = gi == 0 ? __ldg(yb) : __fsub_rn(__ldg(yb + gi), __fmul_rn(0.97f, __ldg(yb + gi - 1)));
-            const double x = (double)e * tb.hamming400[n];
-            FA[n] = x;
-            BA[n] = x;
-        }
-        __syncwarp();
-        // fwd[j] = FA[j + 1 + i], bwd[j] = BA[j], j in [0, 399 - i) at iteration i
-        double den = 0.0;
-        for (int j = lane; j < kLpcFrame - 1; j += 32) den += FA[j + 1] * FA[j + 1] + BA[j] * BA[j];
-        den = warp_sum(den);
-        double a_cur[kLpcOrder + 1], a_prev[kLpcOrder + 1];
+        double Bv[kLpcPer], Fv[kLpcPer];
 #pragma unroll
-        for (int j = 0; j <= kLpcOrder; ++j) { a_cur[j] = j == 0 ? 1.0 : 0.0; a_prev[j] = a_cur[j]; }
-#pragma unroll
-        for (int i = 0; i < kLpcOrder; ++i) {
-            const int len = kLpcFrame - 1 - i;
-            double num = 0.0;
-            for (int j = lane; j < len; j += 32) num += BA[j] * FA[j + 1 + i];
-            num = warp_sum(num);
-            const double k = (num * -2.0) / (den + eps);
-            // ar_coeffs_prev, ar_coeffs = ar_coeffs, ar_coeffs_prev ; then the Levinson update
-#pragma unroll
-            for (int j = 0; j <= kLpcOrder; ++j) { const double tmp = a_prev[j]; a_prev[j] = a_cur[j]; a_cur[j] = tmp; }
-#pragma unroll
-            for (int j = 1; j <= i + 1; ++j) a_cur[j] = a_prev[j] + k * a_prev[i - j + 1];
-            for (int j = lane; j < len; j += 32) {
-                const double f = FA[j + 1 + i], bw = BA[j];
-                FA[j + 1 + i] = f + k * bw;
-                BA[j] = bw + k * f;
+        for (int q = 0; q < kLpcPer; ++q) {
+            const int n = kLpcPer * lane + q, gi = start + n;
+            double x = 0.0;
+            if (n < kLpcFrame) {
+                // y_emph = append(y[0], y[1:] - 0.97 * y[:-1])   (float32)
+                const float e = gi == 0 ? __ldg(yb) : __fsub_rn(__ldg(yb + gi), __fmul_rn(0.97f, __ldg(yb + gi - 1)));
+                x = (double)e * __ldg(tb.hamming400 + n);
             }
-            __syncwarp();
-            const double q = 1.0 - k * k;
-            const double bl = BA[len - 1], f0 = FA[1 + i];
-            den = q * den - bl * bl - f0 * f0;
-            __syncwarp();
+            Bv[q] = x;
         }
-        if (lane == 0) {
+        // fwd[n] pairs with bwd[n]: F[q] = x[n + 1]
+        const double nxt = __shfl_down_sync(0xffffffffu, Bv[0], 1);
 #pragma unroll
-            for (int c = 0; c < kLpcOrder; ++c) S.coef[c * F + fr] = (float)a_cur[c + 1];
+        for (int q = 0; q < kLpcPer - 1; ++q) Fv[q] = Bv[q + 1];
+        Fv[kLpcPer - 1] = lane < 31 ? nxt : 0.0;
+        double den = 0.0;
+        {
+            const int nv = (kLpcFrame - 1) - kLpcPer * lane;
+#pragma unroll
+            for (int q = 0; q < kLpcPer; ++q)
+                if (q < nv) den += Fv[q] * Fv[q] + Bv[q] * Bv[q];
         }
+        den = warp_sum(den);
+        double a_lane = lane == 0 ? 1.0 : 0.0;
+        burg_all<0>(Fv, Bv, a_lane, den, lane);
+        if (lane >= 1 && lane <= kLpcOrder) S.coef[(lane - 1) * F_ + fr] = (float)a_lane;
     }
     __syncthreads();
+    const int F = F_;
     if (ws.dbg_lpc) {
         float* d = ws.dbg_lpc + (size_t)b * kLpcOrder * F;
-        for (int i = tid; i < kLpcOrder * F; i += 256) d[i] = S.coef[i];
+        for (int i = tid; i < kLpcOrder * F; i += kLpcThreads) d[i] = S.coef[i];
     }
     // whole-array z over all F frames (process.py:65); pad_time keeps the first T columns; pad value = min of those
     double s = 0.0, q = 0.0;
-    for (int i = tid; i < kLpcOrder * F; i += 256) { const double v = (double)S.coef[i]; s += v; q += v * v; }
+    for (int i = tid; i < kLpcOrder * F; i += kLpcThreads) { const double v = (double)S.coef[i]; s += v; q += v * v; }
     s = block_sum(s, S.dscratch);
     q = block_sum(q, S.dscratch);
     const ZTerm z = make_zterm(s, q, (double)(kLpcOrder * F));
     const int Tk = T < F ? T : F;
     float mn = FLT_MAX;
-    for (int i = tid; i < kLpcOrder * Tk; i += 256) {
+    for (int i = tid; i < kLpcOrder * Tk; i += kLpcThreads) {
         const int c = i / Tk, t = i - c * Tk;
         mn = fminf(mn, z(S.coef[c * F + t]));
     }
     mn = block_min(mn, S.fscratch);
     float* o = plane_ptr(feats, b, BPC_CH_LPC, T);
-    for (int i = tid; i < kPlaneRows * T; i += 256) {
+    for (int i = tid; i < kPlaneRows * T; i += kLpcThreads) {
         const int c = i / T, t = i - c * T;
         o[i] = (c < kLpcOrder && t < Tk) ? z(S.coef[c * F + t]) : mn;
     }
@@ -105,7 +134,7 @@ void launch_lpc(const float* y, int n, const Geometry& g, const Tables& tb, cons
         cudaFuncSetAttribute(k_lpc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpcSmem));
         done = true;
     }
-    k_lpc<<<n, 256, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats);
+    k_lpc<<<n, kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats);
     note_launch();
 }
 

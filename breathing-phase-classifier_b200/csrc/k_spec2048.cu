@@ -1,8 +1,7 @@
 // STFT-2048 group (librosa default n_fft, reached through methods.py:59-63,90 and process.py:74-75), r01 v1 layout:
-//   k_fft2048   one WARP per frame: Hann * samples -> FP64 real FFT-2048 (swizzled radix-4, no CTA barriers) -> |X|
-//               written to the mag2048 workspace [n, T, 1028]
-//   k_feat2048  one warp per frame: spectral centroid / bandwidth / flatness / contrast order statistics and the mel-D
-//               power column from that row
+//   k_frame2048 one WARP per frame: Hann * samples -> FP64 real FFT-2048 with register-resident radix-32 stages -> |X| row
+//               in shared memory -> spectral centroid / bandwidth / flatness / contrast order statistics and the mel-D
+//               power column from that row (v1 split this in two kernels around a 259 KB/segment HBM workspace)
 //   k_even2048  the hop-512 frames (= even hop-256 frames): spectral_rolloff with numpy's sequential float32 cumsum and
 //               the 36-bins-per-octave tuning estimate chroma_cens needs
 //   k_seg2048   one CTA per segment: statistics of the per-frame features, mel-D dB -> flux + onset envelope ->
@@ -12,47 +11,13 @@
 #include <cmath>
 #include "kernels.cuh"
 #include "fft.cuh"
+#include "fft_reg.cuh"
 #include "tuning.cuh"
 
 namespace bpc {
 
 constexpr int kTempoLags = 384;
 constexpr int kFrameFeat = 20;               // doubles per frame: cent, bw, flat, peak[7], valley[7] (+3 pad)
-
-// ================================================================================================= k_fft2048
-constexpr int kFftWarps = 4;
-
-__global__ void __launch_bounds__(32 * kFftWarps) k_fft2048(const float* __restrict__ y, Geometry g, Tables tb,
-                                                             float* __restrict__ mag, int total_frames) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* buf = reinterpret_cast<double2*>(smem_raw) + (threadIdx.x >> 5) * 1024;
-    const int lane = threadIdx.x & 31;
-    const int T = g.T, L = g.L, hop = g.hop;
-    const double2* win2 = reinterpret_cast<const double2*>(tb.hann2048);
-    for (int f = blockIdx.x * kFftWarps + (threadIdx.x >> 5); f < total_frames; f += gridDim.x * kFftWarps) {
-        const int b = f / T, t = f - b * T;
-        const float* yb = y + (size_t)b * L;
-        const int g0 = t * hop - 1024;
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-            const int m = lane + 32 * i;
-            const int gi = g0 + 2 * m;                         // even; L is even, so the pair is in or out together
-            float2 v = make_float2(0.f, 0.f);
-            if (gi >= 0 && gi < L) v = __ldg(reinterpret_cast<const float2*>(yb + gi));
-            const double2 w = __ldg(win2 + m);
-            buf[swz(m)] = make_double2((double)v.x * w.x, (double)v.y * w.y);
-        }
-        __syncwarp();
-        warp_fft_r4<5>(buf, tb.twp1024, lane);
-        float* out = mag + (size_t)f * kMag2048Stride;
-#pragma unroll 3
-        for (int i = 0; i < 33; ++i) {
-            const int k = lane + 32 * i;
-            if (k <= 1024) out[k] = c64_abs(rfft_bin<5, true>(buf, tb.ptw2048, k));
-        }
-        __syncwarp();
-    }
-}
 
 // ================================================================================================ k_feat2048
 // spectral_contrast sub-bands (librosa, fmin=200, n_bands=6, sr=16000, n_fft=2048): first bin, length, order count
@@ -110,14 +75,57 @@ __device__ void warp_band_extremes(const float* row, int lo, int len, int n, int
     *valley = (double)(float)(sum_lo / (double)n);
 }
 
-__global__ void __launch_bounds__(256) k_feat2048(Geometry g, Tables tb, Workspace ws, int total_frames) {
-    __shared__ __align__(16) float s_mag[8][kMag2048Stride];
+// ================================================================================================ k_frame2048
+// One warp per frame: Hann * samples -> team_fft<32> (fft_reg.cuh: 32 lanes x 32 register-resident complex points, one
+// shared-memory exchange) -> real split -> |X| row (float32, 1025 bins) in the same shared memory -> every per-frame
+// consumer of that row.  Nothing but the per-frame results leaves the SM (v1 wrote the 259 KB/segment |STFT2048|
+// workspace to HBM and read it back in a second kernel); the even (hop-512) frames additionally store their row for
+// k_even2048.
+constexpr int kF2Warps = 4;
+constexpr int kF2RowBytes = 32 * 33 * 16;            // exchange buffer, later the |X| row (1028 floats)
+
+__global__ void __launch_bounds__(32 * kF2Warps, 2) k_frame2048(const float* __restrict__ y, Geometry g, Tables tb,
+                                                                 Workspace ws, int total_frames) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* row = s_mag[warp];
-    for (int f = blockIdx.x * 8 + warp; f < total_frames; f += gridDim.x * 8) {
-        const float4* src = reinterpret_cast<const float4*>(ws.mag2048 + (size_t)f * kMag2048Stride);
-        for (int i = lane; i < kMag2048Stride / 4; i += 32) reinterpret_cast<float4*>(row)[i] = __ldg(src + i);
+    double2* xch = reinterpret_cast<double2*>(smem_raw + (size_t)warp * kF2RowBytes);
+    float* row = reinterpret_cast<float*>(xch);
+    const int T = g.T, L = g.L, hop = g.hop, TE = (T + 1) / 2;
+    const int partner = (32 - lane) & 31;
+    const double2 wp = __ldg(tb.ptw2048 + lane);
+    const double2 wl = make_double2(wp.y, -wp.x);                         // -i * exp(-2 pi i lane / 2048)
+    const double2* win2 = reinterpret_cast<const double2*>(tb.hann2048);
+    const double2* twa = tb.twa1024 + lane;                               // [k1][lane]
+    for (int f = blockIdx.x * kF2Warps + warp; f < total_frames; f += gridDim.x * kF2Warps) {
+        const int b = f / T, t = f - b * T;
+        const float* yb = y + (size_t)b * L;
+        const int g0 = t * hop - 1024;
+        {
+            double2 a[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int m = lane + 32 * j;
+                const int gi = g0 + 2 * m;                     // even; L is even, so the pair is in or out together
+                float2 v = make_float2(0.f, 0.f);
+                if (gi >= 0 && gi < L) v = __ldg(reinterpret_cast<const float2*>(yb + gi));
+                const double2 w = __ldg(win2 + m);
+                a[j] = make_double2((double)v.x * w.x, (double)v.y * w.y);
+            }
+            team_fft<32>(a, twa, 32, xch, lane);
+            const double z0 = a[0].x - a[0].y;                 // lane 0: X[1024] = Re Z[0] - Im Z[0]
+            auto emit = [&](int k, double2 t2) { row[k] = c64_abs(make_double2(0.5 * t2.x, 0.5 * t2.y)); };
+            team_rsplit<32, 0, 31>(a, wl, lane, partner, emit);
+            if (lane == 0) row[1024] = fabsf((float)z0);
+        }
         __syncwarp();
+        if ((t & 1) == 0) {                                    // hop-512 frame: keep the row for rolloff / tuning-36
+            float4* dst = reinterpret_cast<float4*>(ws.mag_even + ((size_t)b * TE + (t >> 1)) * kMag2048Stride);
+            for (int i = lane; i < kMag2048Stride / 4; i += 32) {
+                float4 v = reinterpret_cast<const float4*>(row)[i];
+                if (i == kMag2048Stride / 4 - 1) { v.y = 0.f; v.z = 0.f; v.w = 0.f; }
+                dst[i] = v;
+            }
+        }
         // spectral_centroid / bandwidth (methods.py:59-60): moments of the L1-normalised column; flatness (:62)
         double sm = 0.0, smf = 0.0, smf2 = 0.0, slog = 0.0, spow = 0.0;
         for (int k = lane; k < 1025; k += 32) {
@@ -152,16 +160,16 @@ __global__ void __launch_bounds__(256) k_feat2048(Geometry g, Tables tb, Workspa
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int m = lane + 32 * i;
-            const int s = tb.mel_d.start[m], c = tb.mel_d.count[m];
+            const int s0 = tb.mel_d.start[m], c = tb.mel_d.count[m];
             const float* w = tb.mel_d.w + (size_t)m * tb.mel_d.width;
             float acc = 0.f;
             for (int j = 0; j < c; ++j) {
-                const float mv = row[s + j];
+                const float mv = row[s0 + j];
                 acc = fmaf(__ldg(w + j), __fmul_rn(mv, mv), acc);
             }
             md[m] = acc;
         }
-        __syncwarp();
+        __syncwarp();                                          // the row is the next frame's exchange buffer
     }
 }
 
@@ -412,9 +420,9 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
     __shared__ int s_ncand;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x, T = g.T, TE = (T + 1) / 2;
-    // even frame f is row 2 f of the segment's mag2048 block
-    const float* mag_b = ws.mag2048 + (size_t)b * T * kMag2048Stride;
-    const size_t fstride = 2 * (size_t)kMag2048Stride;
+    // even frame f is row f of the segment's mag_even block (written by k_frame2048)
+    const float* mag_b = ws.mag_even + (size_t)b * TE * kMag2048Stride;
+    const size_t fstride = (size_t)kMag2048Stride;
     if (tid == 0) s_ncand = 0;
     if (warp > 0) {
         for (int f = warp - 1; f < TE; f += 7) {
@@ -482,7 +490,7 @@ void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb,
     static bool done = false;
     static int sms = 148;
     if (!done) {
-        cudaFuncSetAttribute(k_fft2048, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftWarps * 1024 * 16);
+        cudaFuncSetAttribute(k_frame2048, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2Warps * kF2RowBytes);
         cudaFuncSetAttribute(k_seg2048, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Seg2048Smem));
         int dev = 0;
         cudaGetDevice(&dev);
@@ -490,13 +498,10 @@ void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb,
         done = true;
     }
     const int total = n * g.T;
-    int grid = (total + kFftWarps - 1) / kFftWarps;
-    if (grid > sms * 3 * 4) grid = sms * 3 * 4;
-    k_fft2048<<<grid, 32 * kFftWarps, kFftWarps * 1024 * 16, st>>>(y, g, tb, ws.mag2048, total);
-    int grid2 = (total + 7) / 8;
-    if (grid2 > sms * 6 * 4) grid2 = sms * 6 * 4;
-    k_feat2048<<<grid2, 256, 0, st>>>(g, tb, ws, total);
-    note_launch(2);
+    int grid = (total + kF2Warps - 1) / kF2Warps;
+    if (grid > sms * 2 * 8) grid = sms * 2 * 8;
+    k_frame2048<<<grid, 32 * kF2Warps, kF2Warps * kF2RowBytes, st>>>(y, g, tb, ws, total);
+    note_launch();
 }
 
 void launch_seg2048(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats, float* scalars,

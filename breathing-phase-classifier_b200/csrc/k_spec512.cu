@@ -8,6 +8,7 @@
 #include <cmath>
 #include "kernels.cuh"
 #include "fft.cuh"
+#include "fft_reg.cuh"
 #include "tuning.cuh"
 
 namespace bpc {
@@ -41,45 +42,60 @@ void launch_ingest(const void* wav, int wav_dtype, int64_t L_in, float* y, int n
 }
 
 // ------------------------------------------------------------------------------------------------ STFT-512
-// One CTA per segment, one warp per frame (8 frames in flight).  librosa.stft semantics: zero centre padding,
-// periodic Hann (float64) * float32 samples, float64 FFT, complex64 rounding, |.| as hypotf.
-__global__ void __launch_bounds__(256) k_stft512(const float* __restrict__ y, Geometry g, Tables tb,
-                                                 float* __restrict__ mag, int total_frames) {
-    __shared__ double2 s_buf[8][256];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// One half-warp ("team") per frame: 16 lanes x 16 register-resident complex points, one shared-memory exchange
+// (fft_reg.cuh).  librosa.stft semantics: zero centre padding, periodic Hann (float64) * float32 samples, float64 FFT,
+// complex64 rounding, |.| as hypotf.
+constexpr int kS512Threads = 128;
+
+__global__ void __launch_bounds__(kS512Threads, 4) k_stft512(const float* __restrict__ y, Geometry g, Tables tb,
+                                                          float* __restrict__ mag, int total_frames) {
+    __shared__ double2 s_xch[kS512Threads / 16][16 * 17];
+    const int lane = threadIdx.x & 31, h = lane & 15, team = threadIdx.x >> 4;
+    const int partner = (lane & 16) | ((16 - h) & 15);
     const int T = g.T, L = g.L, hop = g.hop;
-    double2* buf = s_buf[warp];
+    double2* xch = s_xch[team];
+    double2 tw[16];
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) tw[k1] = __ldg(tb.tw256 + ((h * k1) & 255));
+    const double2 wp = __ldg(tb.ptw512 + h);
+    const double2 wl = make_double2(wp.y, -wp.x);                         // -i * exp(-2 pi i h / 512)
     const double2* win2 = reinterpret_cast<const double2*>(tb.hann512);
-    for (int f = blockIdx.x * 8 + warp; f < total_frames; f += gridDim.x * 8) {
-        const int b = f / T, t = f - b * T;
+    const int per_iter = gridDim.x * (kS512Threads / 16);
+    for (int f0 = blockIdx.x * (kS512Threads / 16) + (team & ~1); f0 < total_frames; f0 += per_iter) {
+        const int f = f0 + (team & 1);
+        const bool valid = f < total_frames;
+        const int fc = valid ? f : total_frames - 1;
+        const int b = fc / T, t = fc - b * T;
         const float* yb = y + (size_t)b * L;
         const int g0 = t * hop - 256;
+        double2 a[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int m = lane + 32 * i;
+        for (int j = 0; j < 16; ++j) {
+            const int m = h + 16 * j;
             const int gi = g0 + 2 * m;                         // even; L is even
             float2 v = make_float2(0.f, 0.f);
             if (gi >= 0 && gi < L) v = __ldg(reinterpret_cast<const float2*>(yb + gi));
             const double2 w = __ldg(win2 + m);
-            buf[swz(m)] = make_double2((double)v.x * w.x, (double)v.y * w.y);
+            a[j] = make_double2((double)v.x * w.x, (double)v.y * w.y);
         }
-        __syncwarp();
-        warp_fft_r4<4>(buf, tb.twp256, lane);
-        float* out = mag + (size_t)f * kMagStride;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            const int k = lane + 32 * i;
-            if (k <= 256) out[k] = c64_abs(rfft_bin<4, true>(buf, tb.ptw512, k));
-        }
-        __syncwarp();
+        team_fft<16>(a, tw, 1, xch, h);
+        float* out = mag + (size_t)fc * kMagStride;
+        auto emit = [&](int k, double2 t2) {
+            const float v = c64_abs(make_double2(0.5 * t2.x, 0.5 * t2.y));
+            if (valid) out[k] = v;
+        };
+        const double z0 = a[0].x - a[0].y;                    // lane h == 0: X[256] = Re Z[0] - Im Z[0]
+        team_rsplit<16, 0, 15>(a, wl, h, partner, emit);
+        if (h == 0 && valid) out[256] = fabsf((float)z0);
     }
 }
 
 void launch_stft512(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, cudaStream_t st) {
     const int total = n * g.T;
-    int grid = (total + 7) / 8;
-    if (grid > 148 * 8 * 4) grid = 148 * 8 * 4;
-    k_stft512<<<grid, 256, 0, st>>>(y, g, tb, ws.mag512, total);
+    const int per_cta = kS512Threads / 16;
+    int grid = (total + per_cta - 1) / per_cta;
+    if (grid > 148 * 16) grid = 148 * 16;
+    k_stft512<<<grid, kS512Threads, 0, st>>>(y, g, tb, ws.mag512, total);
     note_launch();
 }
 

@@ -24,6 +24,7 @@ struct Tables {
     const double2* ptw2048;       // exp(-2 pi i k / 2048), k <= 1024
     const double2* twp256;        // per-pass twiddles of warp_fft_r4<4> (fft.cuh::twp_size(4) entries)
     const double2* twp1024;       // per-pass twiddles of warp_fft_r4<5>
+    const double2* twa1024;       // [k1][h] = exp(-2 pi i h k1 / 1024), 32 x 32: inter-stage twiddles of team_fft<32>
     // filterbanks
     BankDev mel_a, mel_b, mel_c, mel_d;
     const float* dct_mel;         // [40, 128]
@@ -35,6 +36,7 @@ struct Tables {
     const float* cqt_re;          // [100, 36, W]
     const float* cqt_im;          // [100, 36, W]
     const double* cqt_sqrt_len;   // [100, 252]
+    int cqt_ell_used;             // max non-zeros per basis row over all tunings (<= kCqtEllWidth)
     const double* halfband;       // [127]
     // LPC
     const double* hamming400;     // [400]
@@ -49,7 +51,7 @@ struct Workspace {            // per chunk of `cap` segments
     int cap;
     float* y;                 // [cap, L]   float32 waveform after pad_or_truncate (only when ingest is needed)
     float* mag512;            // [cap, T, kMagStride]
-    float* mag2048;           // [cap, T, kMag2048Stride]  |STFT2048| (1025 valid bins per row)
+    float* mag_even;          // [cap, (T+1)/2, kMag2048Stride]  |STFT2048| rows of the hop-512 frames (1025 valid bins)
     double* frame_feat;       // [cap, T, 20]  per-frame centroid, bandwidth, flatness, contrast peaks / valleys
     float* melD;              // [cap, T, 128] mel-D power columns
     int* tuning;              // [cap, 2]   tuning bin for 12 / 36 bins per octave
@@ -104,6 +106,7 @@ void launch_stats(int n, const Geometry& g, const float* feats, const float* sca
 void launch_modspec(int n, const Geometry& g, const Tables& tb, const float* mel_db, float* out, cudaStream_t st);
 void launch_pad_scalars(int n, const Geometry& g, float* scalars, cudaStream_t st);
 
+void upload_cens_constants(const double* taps127);
 int64_t launches_issued();   // process-wide counter bumped by every launcher
 void note_launch(int n = 1);
 
