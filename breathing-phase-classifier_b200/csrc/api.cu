@@ -99,7 +99,12 @@ int upload_bank(bpc_handle* h, const SparseBank& b, BankDev* out) {
     if ((rc = upload(h, b.start, &s))) return rc;
     if ((rc = upload(h, b.count, &c))) return rc;
     if ((rc = upload(h, b.w, &w))) return rc;
-    out->start = s; out->count = c; out->w = w; out->rows = b.rows; out->width = b.width;
+    std::vector<float> t((size_t)b.rows * b.width);
+    for (int r = 0; r < b.rows; ++r)
+        for (int j = 0; j < b.width; ++j) t[(size_t)j * b.rows + r] = b.w[(size_t)r * b.width + j];
+    const float* wt;
+    if ((rc = upload(h, t, &wt))) return rc;
+    out->start = s; out->count = c; out->w = w; out->wt = wt; out->rows = b.rows; out->width = b.width;
     return BPC_OK;
 }
 

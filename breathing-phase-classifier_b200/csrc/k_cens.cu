@@ -36,14 +36,17 @@ void upload_cens_constants(const double* taps127) {
     cudaMemcpyToSymbol(c_hb_odd, odd, sizeof(odd));
 }
 
-// padded position of sample q in a de-interleaved array: one pad word per 32 keeps the stride-4 accesses of the
-// decimator (thread i reads q = 4 i + c) on 32 distinct banks
-__device__ __forceinline__ int ppos(int q) { return q + (q >> 5); }
-__host__ __device__ constexpr int plen(int n) { return n + (n >> 5) + 1; }
+// Position of sample q (q >= -kZPad) in a de-interleaved array: kZPad zeros on either side stand in for librosa's
+// zero centre-padding (no bounds checks in the loaders), and one pad word per 32 keeps the stride-4 accesses of the
+// decimator (thread i reads q = 4 i + c) on 32 distinct banks.
+constexpr int kZPad = 128;
+__device__ __forceinline__ int ppos(int q) { return (q + kZPad) + ((q + kZPad) >> 5); }
+__host__ __device__ constexpr int plen(int n) { return (n + 2 * kZPad) + ((n + 2 * kZPad) >> 5) + 1; }
 
 // de-interleaved signals of octaves 1..6 (lengths 8000 .. 250 -> halves 4000 .. 125)
 constexpr int kHalf1 = 4000, kHalf2 = 2000, kHalf3 = 1000, kHalf4 = 500, kHalf5 = 250, kHalf6 = 125;
 constexpr int kDecFloats = 2 * (plen(kHalf1) + plen(kHalf2) + plen(kHalf3) + plen(kHalf4) + plen(kHalf5) + plen(kHalf6));
+static_assert(2 * plen(8000) * 4 <= kCensTeams * 16 * 17 * 16, "the staged input must fit the exchange buffers it aliases");
 
 struct CensSmem {
     union {
@@ -58,7 +61,7 @@ struct CensSmem {
     double inv_sl[kCqtBins];                           // 1 / sqrt(lengths)
     float chroma[12 * kMaxFrames];
     float quant[12 * kMaxFrames];
-    double swin[43];
+    double swin[43];                                   // hann(43) / sum
     double dscratch[32];
     float fscratch[32];
 };
@@ -72,8 +75,7 @@ __device__ __forceinline__ void decimate_stage(const float* __restrict__ inE, co
         double w[kWin];
 #pragma unroll
         for (int q = 0; q < kWin; ++q) {
-            const int qq = n0 - 32 + q;
-            w[q] = (qq >= 0 && qq < hin) ? (double)inO[ppos(qq)] : 0.0;
+            w[q] = (double)inO[ppos(n0 - 32 + q)];           // zero pads cover q < 0 and q >= hin
         }
 #pragma unroll
         for (int p = 0; p < kOutPerThread; ++p) {
@@ -100,6 +102,9 @@ __global__ void __launch_bounds__(kCensThreads, 1) k_cens(const float* __restric
     const float2* y2 = reinterpret_cast<const float2*>(yb);
 
     // ---- stage the input (even | odd), the basis of this segment's tuning, the smoothing window
+    for (int i = tid; i < 2 * plen(8000); i += kCensThreads) S.u.y0[i] = 0.f;
+    for (int i = tid; i < kDecFloats; i += kCensThreads) S.dec[i] = 0.f;
+    __syncthreads();
     {
         float* E0 = S.u.y0;
         float* O0 = S.u.y0 + plen(8000);
@@ -129,8 +134,11 @@ __global__ void __launch_bounds__(kCensThreads, 1) k_cens(const float* __restric
         for (int i = tid; i < kCqtBins; i += kCensThreads) S.inv_sl[i] = 1.0 / slen[i];
     }
     if (tid < 43) {
-        // scipy.signal.get_window('hann', 43, fftbins=False), normalised to unit sum in the smoothing loop below
-        S.swin[tid] = 0.5 - 0.5 * cos(2.0 * 3.14159265358979323846 * (double)tid / 42.0);
+        // scipy.signal.get_window('hann', 43, fftbins=False) normalised to unit sum (sum = 21 exactly in real arithmetic;
+        // accumulated here the way the reference does, in index order)
+        double wsum = 0.0;
+        for (int j = 0; j < 43; ++j) wsum += 0.5 - 0.5 * cos(2.0 * 3.14159265358979323846 * (double)j / 42.0);
+        S.swin[tid] = (0.5 - 0.5 * cos(2.0 * 3.14159265358979323846 * (double)tid / 42.0)) / wsum;
     }
     __syncthreads();
 
@@ -186,13 +194,10 @@ __global__ void __launch_bounds__(kCensThreads, 1) k_cens(const float* __restric
             } else {
                 const float* E = S.dec + offE[o];
                 const float* O = S.dec + offO[o];
-                const int hin = halves[o];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int q = c0 + h + 16 * j;
-                    float vx = 0.f, vy = 0.f;
-                    if (q >= 0 && q < hin) { vx = E[ppos(q)]; vy = O[ppos(q)]; }
-                    a[j] = make_double2((double)vx, (double)vy);
+                    const int pq = ppos(c0 + h + 16 * j);            // c0 >= -kZPad; the zero pads are the centre padding
+                    a[j] = make_double2((double)E[pq], (double)O[pq]);
                 }
             }
             team_fft<16>(a, tw, 1, xch, h);
@@ -210,9 +215,12 @@ __global__ void __launch_bounds__(kCensThreads, 1) k_cens(const float* __restric
                 const int r = h + 16 * rr;
                 if (r < kCqtBinsPerOct) {
                     float cr = 0.f, ci = 0.f;
+                    const float2* wr = bas + r * kCqtEllWidth;
+                    const short* cc = S.bcol + r * kCqtEllWidth;
+#pragma unroll 4
                     for (int j = 0; j < ell_used; ++j) {
-                        const float2 w = bas[r * kCqtEllWidth + j];
-                        const float2 d = spec[S.bcol[r * kCqtEllWidth + j]];
+                        const float2 w = wr[j];
+                        const float2 d = spec[cc[j]];
                         cr = fmaf(w.x, d.x, cr); cr = fmaf(-w.y, d.y, cr);
                         ci = fmaf(w.x, d.y, ci); ci = fmaf(w.y, d.x, ci);
                     }
@@ -244,15 +252,11 @@ __global__ void __launch_bounds__(kCensThreads, 1) k_cens(const float* __restric
     }
     __syncthreads();
     // 41 non-zero taps of hann(43) / sum, scipy.ndimage.convolve(mode='constant') along time
-    double wsum = 0.0;
-    for (int j = 0; j < 43; ++j) wsum += S.swin[j];
     for (int i = tid; i < 12 * T; i += kCensThreads) {
         const int c = i / T, t = i - c * T;
         double acc = 0.0;
-        for (int j = 0; j < 43; ++j) {
-            const int tt = t + 21 - j;
-            if (tt >= 0 && tt < T) acc += (S.swin[j] / wsum) * (double)S.quant[c * T + tt];
-        }
+        const int jlo = max(0, t + 21 - (T - 1)), jhi = min(42, t + 21);
+        for (int j = jlo; j <= jhi; ++j) acc += S.swin[j] * (double)S.quant[c * T + t + 21 - j];
         S.chroma[i] = (float)acc;
     }
     __syncthreads();

@@ -23,12 +23,13 @@ struct LpcSmem {
 template <int I>
 __device__ __forceinline__ void burg_step(double (&F)[kLpcPer], double (&B)[kLpcPer], double& a_lane, double& den,
                                           int lane) {
-    constexpr int len = kLpcFrame - 1 - I;              // valid pairs: n < len
+    constexpr int len = kLpcFrame - 1 - I;              // pairs n < len are live
     const double eps = 2.2250738585072014e-308;         // util.tiny(float64)
-    const int nv = len - kLpcPer * lane;                 // q < nv is valid in this lane
+    // No per-element masks: every backward error with n >= len is zero (dropped below) and every forward slot beyond
+    // sample 399 is zero, so dead pairs contribute 0 to the sums and stay 0 under the update.
     double num = 0.0;
 #pragma unroll
-    for (int q = 0; q < kLpcPer; ++q) num = fma(q < nv ? B[q] : 0.0, F[(q + I) % kLpcPer], num);
+    for (int q = 0; q < kLpcPer; ++q) num = fma(B[q], F[(q + I) % kLpcPer], num);
     num = warp_sum(num);
     const double k = (num * -2.0) / (den + eps);
     // Levinson update a[j] = a_prev[j] + k * a_prev[I - j + 1], j = 1 .. I + 1; lane j holds a[j] (a[0] = 1, rest 0)
@@ -39,16 +40,16 @@ __device__ __forceinline__ void burg_step(double (&F)[kLpcPer], double (&B)[kLpc
     }
 #pragma unroll
     for (int q = 0; q < kLpcPer; ++q) {
-        if (q < nv) {
-            const double f = F[(q + I) % kLpcPer], bw = B[q];
-            F[(q + I) % kLpcPer] = f + k * bw;
-            B[q] = bw + k * f;
-        }
+        const double f = F[(q + I) % kLpcPer], bw = B[q];
+        F[(q + I) % kLpcPer] = fma(k, bw, f);
+        B[q] = fma(k, f, bw);
     }
     // den = (1 - k^2) den - bwd[-1]^2 - fwd[0]^2 with the updated errors
     const double f0 = __shfl_sync(0xffffffffu, F[I % kLpcPer], 0);
     const double bl = __shfl_sync(0xffffffffu, B[(len - 1) % kLpcPer], (len - 1) / kLpcPer);
     den = (1.0 - k * k) * den - bl * bl - f0 * f0;
+    // bwd = bwd[:-1]: the last live backward error is dropped
+    if (lane == (len - 1) / kLpcPer) B[(len - 1) % kLpcPer] = 0.0;
     // fwd = fwd[1:]: the slot of this lane's first element receives the next lane's first element
     F[I % kLpcPer] = __shfl_down_sync(0xffffffffu, F[I % kLpcPer], 1);
 }
@@ -62,7 +63,7 @@ __device__ __forceinline__ void burg_all(double (&F)[kLpcPer], double (&B)[kLpcP
     }
 }
 
-__global__ void __launch_bounds__(kLpcThreads, 3) k_lpc(const float* __restrict__ y, Geometry g, Tables tb, Workspace ws,
+__global__ void __launch_bounds__(kLpcThreads, 4) k_lpc(const float* __restrict__ y, Geometry g, Tables tb, Workspace ws,
                                                 float* feats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LpcSmem& S = *reinterpret_cast<LpcSmem*>(smem_raw);
@@ -89,13 +90,11 @@ __global__ void __launch_bounds__(kLpcThreads, 3) k_lpc(const float* __restrict_
 #pragma unroll
         for (int q = 0; q < kLpcPer - 1; ++q) Fv[q] = Bv[q + 1];
         Fv[kLpcPer - 1] = lane < 31 ? nxt : 0.0;
+        // bwd = x[:-1]: sample 399 is never a backward error
+        if (lane == (kLpcFrame - 1) / kLpcPer) Bv[(kLpcFrame - 1) % kLpcPer] = 0.0;
         double den = 0.0;
-        {
-            const int nv = (kLpcFrame - 1) - kLpcPer * lane;
 #pragma unroll
-            for (int q = 0; q < kLpcPer; ++q)
-                if (q < nv) den += Fv[q] * Fv[q] + Bv[q] * Bv[q];
-        }
+        for (int q = 0; q < kLpcPer; ++q) den = fma(Fv[q], Fv[q], fma(Bv[q], Bv[q], den));
         den = warp_sum(den);
         double a_lane = lane == 0 ? 1.0 : 0.0;
         burg_all<0>(Fv, Bv, a_lane, den, lane);

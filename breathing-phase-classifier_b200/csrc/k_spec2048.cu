@@ -21,58 +21,99 @@ constexpr int kFrameFeat = 20;               // doubles per frame: cent, bw, fla
 
 // ================================================================================================ k_feat2048
 // spectral_contrast sub-bands (librosa, fmin=200, n_bands=6, sr=16000, n_fft=2048): first bin, length, order count
-__constant__ int c_band_lo[7] = {0, 25, 51, 102, 204, 409, 819};
-__constant__ int c_band_len[7] = {25, 26, 51, 102, 205, 410, 206};
-__constant__ int c_band_n[7] = {1, 1, 1, 2, 4, 8, 4};
+// Batcher odd-even merge sort network on C register-resident floats (ascending), written for the power of two P >= C
+// with the elements C .. P-1 taken as +inf: every compare-exchange that touches them is a no-op and is dropped.
+template <int P, int C>
+__device__ __forceinline__ void sort_net_asc(float (&a)[C]) {
+#pragma unroll
+    for (int p = 1; p < P; p <<= 1)
+#pragma unroll
+        for (int k = p; k >= 1; k >>= 1)
+#pragma unroll
+            for (int j = k % p; j + k < P; j += 2 * k)
+#pragma unroll
+                for (int i = 0; i < k; ++i)
+                    if (i + j + k < C && (i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+                        const float lo = fminf(a[i + j], a[i + j + k]), hi = fmaxf(a[i + j], a[i + j + k]);
+                        a[i + j] = lo;
+                        a[i + j + k] = hi;
+                    }
+}
 
-// mean of the n smallest and n largest of row[lo .. lo+len) by one warp (len <= 416, n <= 8).
-// Ties are broken by position, so every element is selected at most once.
-__device__ void warp_band_extremes(const float* row, int lo, int len, int n, int lane, double* valley,
-                                   double* peak) {
-    float v[13];
+// Mean of the N smallest and of the N largest of row[lo .. lo+len) by one warp; C = ceil(len / 32) elements per lane.
+// Every lane sorts its own elements once (registers); the N extraction rounds then only compare the lanes' current
+// heads (one REDUX + one ballot per round).  Ties carry equal values, so which of them is taken does not matter.
+// (v1 rescanned all 13 elements per lane in every round: 45 % of the executed instructions of this kernel.)
+template <int P, int C, int N>
+__device__ __forceinline__ void warp_band_extremes(const float* row, int lo, int len, int lane, double* valley,
+                                                   double* peak) {
+    static_assert(C > N, "every lane must hold more elements than are extracted");
+    float s[C];
 #pragma unroll
-    for (int i = 0; i < 13; ++i) {
+    for (int i = 0; i < C; ++i) {
         const int j = lane + 32 * i;
-        v[i] = j < len ? row[lo + j] : -1.f;             // magnitudes are >= 0; -1 marks "absent"
+        s[i] = j < len ? row[lo + j] : __int_as_float(0x7f800000);       // +inf marks "absent" (only the last row)
     }
-    unsigned taken_hi = 0, taken_lo = 0;
-    double sum_hi = 0.0, sum_lo = 0.0;
-    for (int r = 0; r < n; ++r) {
-        float best = -2.f;
-        int bi = -1;
+    sort_net_asc<P, C>(s);
+    const bool full = lane + 32 * (C - 1) < len;
+    unsigned L[N], H[N];                                                 // magnitudes are >= 0: bit patterns order like the values
 #pragma unroll
-        for (int i = 0; i < 13; ++i)
-            if (v[i] >= 0.f && !((taken_hi >> i) & 1u) && v[i] > best) { best = v[i]; bi = i; }
-        int gidx = bi < 0 ? 0x7fffffff : lane + 32 * bi;
-        float wb = best;
-        int wi = gidx;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, wb, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-            if (ob > wb || (ob == wb && oi < wi)) { wb = ob; wi = oi; }
-        }
-        if (wi == gidx && bi >= 0) taken_hi |= 1u << bi;
-        sum_hi += (double)wb;
-        best = 3.0e38f;
-        bi = -1;
-#pragma unroll
-        for (int i = 0; i < 13; ++i)
-            if (v[i] >= 0.f && !((taken_lo >> i) & 1u) && v[i] < best) { best = v[i]; bi = i; }
-        gidx = bi < 0 ? 0x7fffffff : lane + 32 * bi;
-        wb = best;
-        wi = gidx;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, wb, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-            if (ob < wb || (ob == wb && oi < wi)) { wb = ob; wi = oi; }
-        }
-        if (wi == gidx && bi >= 0) taken_lo |= 1u << bi;
-        sum_lo += (double)wb;
+    for (int r = 0; r < N; ++r) {
+        L[r] = __float_as_uint(s[r]);
+        H[r] = __float_as_uint(full ? s[C - 1 - r] : s[C - 2 - r]);
     }
-    *peak = (double)(float)(sum_hi / (double)n);         // np.mean of a float32 slice -> float32
-    *valley = (double)(float)(sum_lo / (double)n);
+    double sum_lo = 0.0, sum_hi = 0.0;
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        const unsigned mlo = __reduce_min_sync(0xffffffffu, L[0]);
+        const unsigned blo = __ballot_sync(0xffffffffu, L[0] == mlo);
+        if (lane == __ffs(blo) - 1) {
+#pragma unroll
+            for (int q = 0; q + 1 < N; ++q) L[q] = L[q + 1];
+            L[N - 1] = 0x7f800000u;
+        }
+        sum_lo += (double)__uint_as_float(mlo);
+        const unsigned mhi = __reduce_max_sync(0xffffffffu, H[0]);
+        const unsigned bhi = __ballot_sync(0xffffffffu, H[0] == mhi);
+        if (lane == __ffs(bhi) - 1) {
+#pragma unroll
+            for (int q = 0; q + 1 < N; ++q) H[q] = H[q + 1];
+            H[N - 1] = 0u;
+        }
+        sum_hi += (double)__uint_as_float(mhi);
+    }
+    *peak = (double)(float)(sum_hi / (double)N);         // np.mean of a float32 slice -> float32
+    *valley = (double)(float)(sum_lo / (double)N);
+}
+
+// bands whose order count is 1: plain min / max
+__device__ __forceinline__ void warp_band_minmax(const float* row, int lo, int len, int lane, double* valley,
+                                                 double* peak) {
+    unsigned mn = 0x7f800000u, mx = 0u;
+    for (int j = lane; j < len; j += 32) {
+        const unsigned v = __float_as_uint(row[lo + j]);
+        mn = min(mn, v);
+        mx = max(mx, v);
+    }
+    *valley = (double)__uint_as_float(__reduce_min_sync(0xffffffffu, mn));
+    *peak = (double)__uint_as_float(__reduce_max_sync(0xffffffffu, mx));
+}
+
+// |re + i im| of a complex64 the way numpy / glibc do it: (float)sqrt((double)re * re + (double)im * im), evaluated in
+// float32 pairs: s = hi + lo exactly (error-free products and sum), r = sqrt(hi) corrected by the residual.  The
+// result differs from the double-precision evaluation only when the exact value lies within ~1e-13 (relative) of a
+// float32 rounding boundary.  (The DSQRT sequence of c64_abs was 6 % of this kernel's instructions.)
+__device__ __forceinline__ float c64_abs_f32(float re, float im) {
+    const float a = fabsf(re), b = fabsf(im);
+    const float x = fmaxf(a, b), y = fminf(a, b);
+    if (!(x > 1e-18f && x < 1e18f)) return (float)sqrt((double)re * (double)re + (double)im * (double)im);
+    const float p = __fmul_rn(x, x), pe = __fmaf_rn(x, x, -p);          // x^2 = p + pe
+    const float q = __fmul_rn(y, y), qe = __fmaf_rn(y, y, -q);          // y^2 = q + qe
+    const float hi = __fadd_rn(p, q);
+    const float lo = __fadd_rn(__fadd_rn(__fsub_rn(p, hi), q), __fadd_rn(pe, qe));   // p >= q: fast two-sum
+    const float r = __fsqrt_rn(hi);
+    const float res = __fadd_rn(__fmaf_rn(-r, r, hi), lo);              // (hi + lo) - r^2
+    return __fadd_rn(r, __fdiv_rn(res, __fadd_rn(r, r)));
 }
 
 // ================================================================================================ k_frame2048
@@ -113,7 +154,7 @@ __global__ void __launch_bounds__(32 * kF2Warps, 2) k_frame2048(const float* __r
             }
             team_fft<32>(a, twa, 32, xch, lane);
             const double z0 = a[0].x - a[0].y;                 // lane 0: X[1024] = Re Z[0] - Im Z[0]
-            auto emit = [&](int k, double2 t2) { row[k] = c64_abs(make_double2(0.5 * t2.x, 0.5 * t2.y)); };
+            auto emit = [&](int k, double2 t2) { row[k] = c64_abs_f32((float)(0.5 * t2.x), (float)(0.5 * t2.y)); };
             team_rsplit<32, 0, 31>(a, wl, lane, partner, emit);
             if (lane == 0) row[1024] = fabsf((float)z0);
         }
@@ -126,46 +167,77 @@ __global__ void __launch_bounds__(32 * kF2Warps, 2) k_frame2048(const float* __r
                 dst[i] = v;
             }
         }
-        // spectral_centroid / bandwidth (methods.py:59-60): moments of the L1-normalised column; flatness (:62)
-        double sm = 0.0, smf = 0.0, smf2 = 0.0, slog = 0.0, spow = 0.0;
-        for (int k = lane; k < 1025; k += 32) {
-            const float m = row[k];
-            const double fk = (double)k * 7.8125, dm = (double)m;
-            sm += dm;
-            smf += dm * fk;
-            smf2 += dm * fk * fk;
-            const float p = fmaxf(1e-10f, __fmul_rn(m, m));
-            slog += (double)logf(p);
-            spow += (double)p;
+        // spectral_centroid / bandwidth (methods.py:59-60): moments of the L1-normalised column; flatness (:62) needs
+        // sum(log(p)): the logs of up to 17 powers (each >= 1e-10) are taken as one double-precision log of their product
+        double sm = 0.0, smk = 0.0, smk2 = 0.0, spow = 0.0, prod0 = 1.0, prod1 = 1.0;
+        {
+            double kd = (double)lane;
+#pragma unroll 4
+            for (int i = 0; i < 33; ++i) {
+                const int k = lane + 32 * i;
+                if (k < 1025) {
+                    const float m = row[k];
+                    const double dm = (double)m;
+                    sm += dm;
+                    const double t = dm * kd;
+                    smk += t;
+                    smk2 = fma(t, kd, smk2);
+                    const double p = (double)fmaxf(1e-10f, __fmul_rn(m, m));
+                    spow += p;
+                    if (i < 17) prod0 *= p; else prod1 *= p;
+                }
+                kd += 32.0;
+            }
         }
-        sm = warp_sum(sm); smf = warp_sum(smf); smf2 = warp_sum(smf2); slog = warp_sum(slog); spow = warp_sum(spow);
+        double slog = log(prod0) + log(prod1);
+        const double smf = smk * 7.8125, smf2 = smk2 * (7.8125 * 7.8125);
+        sm = warp_sum(sm);
+        const double smf_w = warp_sum(smf), smf2_w = warp_sum(smf2);
+        slog = warp_sum(slog);
+        spow = warp_sum(spow);
         double* ff = ws.frame_feat + (size_t)f * kFrameFeat;
         if (lane == 0) {
             const double len = sm < 1.17549435e-38 ? 1.0 : sm;     // util.normalize(norm=1): tiny(float32) guard
-            const double c = smf / len;
+            const double c = smf_w / len;
             ff[0] = c;
-            ff[1] = sqrt(fmax(0.0, smf2 / len - 2.0 * c * (smf / len) + c * c * (sm / len)));
+            ff[1] = sqrt(fmax(0.0, smf2_w / len - 2.0 * c * (smf_w / len) + c * c * (sm / len)));
             const float gmean = expf((float)(slog / 1025.0));
             const float amean = (float)(spow / 1025.0);
             ff[2] = (double)__fdiv_rn(gmean, amean);
         }
-        // spectral_contrast order statistics (methods.py:63)
-        for (int band = 0; band < 7; ++band) {
-            double va, pk;
-            warp_band_extremes(row, c_band_lo[band], c_band_len[band], c_band_n[band], lane, &va, &pk);
-            if (lane == 0) { ff[3 + band] = pk; ff[10 + band] = va; }
+        // spectral_contrast order statistics (methods.py:63); band table: first bin, length, order count
+        //   {0,25,1} {25,26,1} {51,51,1} {102,102,2} {204,205,4} {409,410,8} {819,206,4}
+        {
+            double va[7], pk[7];
+            warp_band_minmax(row, 0, 25, lane, &va[0], &pk[0]);
+            warp_band_minmax(row, 25, 26, lane, &va[1], &pk[1]);
+            warp_band_minmax(row, 51, 51, lane, &va[2], &pk[2]);
+            warp_band_extremes<4, 4, 2>(row, 102, 102, lane, &va[3], &pk[3]);
+            warp_band_extremes<8, 7, 4>(row, 204, 205, lane, &va[4], &pk[4]);
+            warp_band_extremes<16, 13, 8>(row, 409, 410, lane, &va[5], &pk[5]);
+            warp_band_extremes<8, 7, 4>(row, 819, 206, lane, &va[6], &pk[6]);
+            if (lane < 7) {
+                double p = pk[0], v = va[0];
+#pragma unroll
+                for (int bnd = 1; bnd < 7; ++bnd) if (lane == bnd) { p = pk[bnd]; v = va[bnd]; }
+                ff[3 + lane] = p;
+                ff[10 + lane] = v;
+            }
         }
-        // mel-D power column (n_fft 2048, 128 mels, fmax 8000): methods.py:90 and process.py:74
+        // mel-D power column (n_fft 2048, 128 mels, fmax 8000): methods.py:90 and process.py:74.  Weights are read
+        // from the transposed band table ([tap][mel]: one coalesced request per tap); the squares are formed on the fly.
         float* md = ws.melD + (size_t)f * kPlaneRows;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int m = lane + 32 * i;
-            const int s0 = tb.mel_d.start[m], c = tb.mel_d.count[m];
-            const float* w = tb.mel_d.w + (size_t)m * tb.mel_d.width;
+            const int s0 = __ldg(tb.mel_d.start + m), c = __ldg(tb.mel_d.count + m);
+            const int cmax = __reduce_max_sync(0xffffffffu, c);
+            const float* wt = tb.mel_d.wt + m;
             float acc = 0.f;
-            for (int j = 0; j < c; ++j) {
-                const float mv = row[s0 + j];
-                acc = fmaf(__ldg(w + j), __fmul_rn(mv, mv), acc);
+            for (int j = 0; j < cmax; ++j) {
+                const float w = __ldg(wt + j * kPlaneRows);          // zero beyond this row's count
+                const float mv = row[min(s0 + j, 1024)];
+                acc = fmaf(w, __fmul_rn(mv, mv), acc);
             }
             md[m] = acc;
         }

@@ -11,6 +11,7 @@ struct BankDev {            // band-form triangular filterbank (see tables.hpp::
     const int* start;       // [rows]
     const int* count;       // [rows]
     const float* w;         // [rows, width]
+    const float* wt;        // [width, rows]  (transposed: lanes that own consecutive rows read consecutive words)
     int rows, width;
 };
 
