@@ -35,10 +35,14 @@ __device__ __forceinline__ int swz(int i) { return i ^ ((i >> 3) & 7); }
 struct SyncWarp { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
 struct SyncBlock { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
 
-// One radix-4 DIF butterfly at `base` with quarter-span q; twiddle index step `ts` (= N / span).
-template <bool kTwiddle>
+// One radix-4 DIF butterfly at `base` with quarter-span q; twiddle index step `ts` (= N / span).  kSwz: the buffer uses
+// the XOR-swizzled layout (swz()), which keeps the four accesses of every pass, including quarter-spans 4 and 1, on
+// distinct banks.
+template <bool kTwiddle, bool kSwz = false>
 __device__ __forceinline__ void r4_butterfly(double2* x, int base, int q, const double2* tw, int pos_ts) {
-    const double2 a0 = x[base], a1 = x[base + q], a2 = x[base + 2 * q], a3 = x[base + 3 * q];
+    const int i0 = kSwz ? swz(base) : base, i1 = kSwz ? swz(base + q) : base + q;
+    const int i2 = kSwz ? swz(base + 2 * q) : base + 2 * q, i3 = kSwz ? swz(base + 3 * q) : base + 3 * q;
+    const double2 a0 = x[i0], a1 = x[i1], a2 = x[i2], a3 = x[i3];
     const double2 b0 = cadd(a0, a2), b1 = csub(a0, a2), b2 = cadd(a1, a3);
     const double2 d = csub(a1, a3);
     const double2 b3 = make_double2(d.y, -d.x);            // -i * (a1 - a3)
@@ -48,14 +52,14 @@ __device__ __forceinline__ void r4_butterfly(double2* x, int base, int q, const 
         y2 = cmul(y2, tw[2 * pos_ts]);
         y3 = cmul(y3, tw[3 * pos_ts]);
     }
-    x[base] = y0;
-    x[base + q] = y1;
-    x[base + 2 * q] = y2;
-    x[base + 3 * q] = y3;
+    x[i0] = y0;
+    x[i1] = y1;
+    x[i2] = y2;
+    x[i3] = y3;
 }
 
 // Forward complex FFT of N = 4^M points by a team of NT threads (tid in [0, NT)); `sync` separates the passes.
-template <int M, int NT, class Sync>
+template <int M, int NT, class Sync, bool kSwz = false>
 __device__ __forceinline__ void fft_r4_dif(double2* x, const double2* tw, int tid, Sync sync) {
     constexpr int N = 1 << (2 * M);
 #pragma unroll
@@ -69,8 +73,8 @@ __device__ __forceinline__ void fft_r4_dif(double2* x, const double2* tw, int ti
             if ((N / 4) % NT == 0 || j < N / 4) {
                 const int pos = j & (q - 1);
                 const int base = ((j - pos) << 2) + pos;
-                if (p == M - 1) r4_butterfly<false>(x, base, q, tw, 0);
-                else r4_butterfly<true>(x, base, q, tw, pos * ts);
+                if (p == M - 1) r4_butterfly<false, kSwz>(x, base, q, tw, 0);
+                else r4_butterfly<true, kSwz>(x, base, q, tw, pos * ts);
             }
         }
         sync();

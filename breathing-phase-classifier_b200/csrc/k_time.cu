@@ -151,18 +151,24 @@ __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y,
         __syncthreads();
         const unsigned p0 = S.prefix[0], p1 = S.prefix[1], p2 = S.prefix[2], p3 = S.prefix[3];
         const unsigned hi_mask = pass == 0 ? 0u : (pass == 1 ? 0xffe00000u : 0xfffffc00u);
-        for (int i = tid; i < L; i += 256) {
-            const unsigned key = __float_as_uint(fabsf(S.y[i]));
-            const unsigned hi = key & hi_mask, d = (key >> shifts[pass]) & masks[pass];
-            if (hi == p0) atomicAdd(&S.hist[0][d], 1u);
-            if (hi == p1) atomicAdd(&S.hist[1][d], 1u);
-            if (hi == p2) atomicAdd(&S.hist[2][d], 1u);
-            if (hi == p3) atomicAdd(&S.hist[3][d], 1u);
+        if (pass == 0) {
+            // all four targets still share the empty prefix: one histogram serves them (4x fewer shared atomics)
+            for (int i = tid; i < L; i += 256)
+                atomicAdd(&S.hist[0][__float_as_uint(fabsf(S.y[i])) >> 21], 1u);
+        } else {
+            for (int i = tid; i < L; i += 256) {
+                const unsigned key = __float_as_uint(fabsf(S.y[i]));
+                const unsigned hi = key & hi_mask, d = (key >> shifts[pass]) & masks[pass];
+                if (hi == p0) atomicAdd(&S.hist[0][d], 1u);
+                if (hi == p1) atomicAdd(&S.hist[1][d], 1u);
+                if (hi == p2) atomicAdd(&S.hist[2][d], 1u);
+                if (hi == p3) atomicAdd(&S.hist[3][d], 1u);
+            }
         }
         __syncthreads();
         if (warp < 4) {
             // find the digit whose cumulative count first exceeds rank; 64 bins per lane
-            const unsigned* h = S.hist[warp];
+            const unsigned* h = S.hist[pass == 0 ? 0 : warp];
             const int nb = (int)masks[pass] + 1, per = nb / 32;
             unsigned local = 0;
             for (int i = 0; i < per; ++i) local += h[lane * per + i];
@@ -236,15 +242,15 @@ __global__ void __launch_bounds__(256) k_autocorr(const float* __restrict__ y, G
                 v.x = gi < L ? (double)__ldg(yb + gi) : 0.0;
                 v.y = gi + 1 < L ? (double)__ldg(yb + gi + 1) : 0.0;
             }
-            S.fbuf[m] = v;
+            S.fbuf[swz(m)] = v;
         }
         __syncthreads();
-        fft_r4_dif<5, 256>(S.fbuf, S.tw, tid, SyncBlock());
+        fft_r4_dif<5, 256, SyncBlock, true>(S.fbuf, S.tw, tid, SyncBlock());
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
             const int k = tid + 256 * i;
             if (k <= 1024) {
-                const double2 F = rfft_bin<5>(S.fbuf, tb.ptw2048, k);
+                const double2 F = rfft_bin<5, true>(S.fbuf, tb.ptw2048, k);
                 const double2 P = S.prev[k];
                 const double sgn = (k & 1) ? -1.0 : 1.0;
                 double2 acc = S.R[k];
@@ -265,12 +271,12 @@ __global__ void __launch_bounds__(256) k_autocorr(const float* __restrict__ y, G
         const double2 w = tb.ptw2048[k];                       // exp(-i th); need exp(+i th) = conj
         const double2 o = make_double2(d.x * w.x + d.y * w.y, d.y * w.x - d.x * w.y);
         const double2 z = make_double2(e.x - o.y, e.y + o.x);  // e + i o
-        S.fbuf[k] = make_double2(z.x, -z.y);
+        S.fbuf[swz(k)] = make_double2(z.x, -z.y);
     }
     __syncthreads();
-    fft_r4_dif<5, 256>(S.fbuf, S.tw, tid, SyncBlock());
+    fft_r4_dif<5, 256, SyncBlock, true>(S.fbuf, S.tw, tid, SyncBlock());
     for (int m = tid; m < 512; m += 256) {
-        const double2 o = S.fbuf[rev4<5>(m)];
+        const double2 o = S.fbuf[swz(rev4<5>(m))];
         S.r[2 * m] = o.x / 1024.0;
         S.r[2 * m + 1] = -o.y / 1024.0;
     }
@@ -440,7 +446,6 @@ __global__ void __launch_bounds__(kHilbertThreads) k_hilbert(const float* __rest
     mixed_pass<5, true>(X, 8000, tw, tid);
     // h[2m] = Re(conj(out[m])) / N, h[2m+1] = Im(conj(out[m])) / N; envelope = |y + i h| (float32 like complex64 abs)
     float* env = reinterpret_cast<float*>(smem_raw);                           // [16000], first half of X's storage
-    unsigned char* cand = smem_raw + sizeof(float) * 16000;                    // [16000] flags, second half
     {
         float e0[16], e1[16];
 #pragma unroll
@@ -468,8 +473,11 @@ __global__ void __launch_bounds__(kHilbertThreads) k_hilbert(const float* __rest
     q = block_sum(q, S.dscratch);
     const float emean = (float)(s / L);
     const float estd = (float)sqrt(fmax(0.0, q / L - (s / L) * (s / L)));
-    // scipy.signal.find_peaks(env, height=emean, distance=1600): local maxima (plateau mid-points), height filter
-    for (int i = tid; i < L; i += kHilbertThreads) cand[i] = 0;
+    // scipy.signal.find_peaks(env, height=emean, distance=1600): local maxima (plateau mid-points), height filter.
+    // Candidates are compacted into a list (r01 v3: the selection rounds rescanned all 16000 flags, 20 % of the kernel).
+    int* clist = reinterpret_cast<int*>(smem_raw + sizeof(float) * 16000);    // second half of X's storage
+    constexpr int kMaxList = 16000;                                            // 64 KB: every sample could be listed
+    if (tid == 0) S.best_i = 0;                                                // list length
     __syncthreads();
     for (int i = tid + 1; i < L - 1; i += kHilbertThreads) {
         if (env[i - 1] < env[i]) {
@@ -477,10 +485,15 @@ __global__ void __launch_bounds__(kHilbertThreads) k_hilbert(const float* __rest
             while (ahead < L - 1 && env[ahead] == env[i]) ++ahead;
             if (env[ahead] < env[i]) {
                 const int mid = (i + ahead - 1) / 2;
-                if (env[mid] >= emean) cand[mid] = 1;
+                if (env[mid] >= emean) {
+                    const int slot = atomicAdd(&S.best_i, 1);
+                    if (slot < kMaxList) clist[slot] = mid;
+                }
             }
         }
     }
+    __syncthreads();
+    const int nc = min(S.best_i, kMaxList);
     __syncthreads();
     int n_peaks = 0;
     double hs = 0.0, hq = 0.0;
@@ -488,8 +501,10 @@ __global__ void __launch_bounds__(kHilbertThreads) k_hilbert(const float* __rest
         // highest-priority remaining candidate (ties: later position first, as a stable ascending argsort would)
         float bv = -1.f;
         int bi = -1;
-        for (int i = tid; i < L; i += kHilbertThreads)
-            if (cand[i] && (env[i] > bv || (env[i] == bv && i > bi))) { bv = env[i]; bi = i; }
+        for (int j = tid; j < nc; j += kHilbertThreads) {
+            const int i = clist[j];
+            if (i >= 0 && (env[i] > bv || (env[i] == bv && i > bi))) { bv = env[i]; bi = i; }
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float ob = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -511,7 +526,10 @@ __global__ void __launch_bounds__(kHilbertThreads) k_hilbert(const float* __rest
         ++n_peaks;
         hs += (double)pv;
         hq += (double)pv * (double)pv;
-        for (int i = max(0, pi - 1599) + tid; i <= min(L - 1, pi + 1599); i += kHilbertThreads) cand[i] = 0;
+        for (int j = tid; j < nc; j += kHilbertThreads) {
+            const int i = clist[j];
+            if (i >= 0 && i > pi - 1600 && i < pi + 1600) clist[j] = -1;
+        }
         __syncthreads();
     }
     if (tid == 0) {
