@@ -245,6 +245,8 @@ int build_workspace(bpc_handle* h) {
     if ((rc = dalloc(h, C * ((T + 1) / 2) * kMag2048Stride, &w.mag_even))) return rc;
     if ((rc = dalloc(h, C * T * 20, &w.frame_feat))) return rc;
     if ((rc = dalloc(h, C * T * 128, &w.melD))) return rc;
+    w.dec_stride = cens_dec_floats_per_segment();
+    if ((rc = dalloc(h, C * (size_t)w.dec_stride, &w.dec))) return rc;
     if ((rc = dalloc(h, C * 2, &w.tuning))) return rc;
     if ((rc = dalloc(h, C * 2, &w.chroma_min))) return rc;
     if ((rc = dalloc(h, C * 2, &w.ints))) return rc;

@@ -20,7 +20,6 @@ namespace bpc {
 
 constexpr int kBinLo = 60, kBinHi = 144;               // rfft bins the sparsified bases can touch (measured 62..141)
 constexpr int kBinSpan = kBinHi - kBinLo + 1;
-constexpr int kCensThreads = 256, kCensTeams = kCensThreads / 16;
 constexpr int kOutPerThread = 4;
 constexpr int kWin = 63 + kOutPerThread;                // odd-sample window of one thread
 
@@ -40,20 +39,111 @@ void upload_cens_constants(const double* taps127) {
 // zero centre-padding (no bounds checks in the loaders), and one pad word per 32 keeps the stride-4 accesses of the
 // decimator (thread i reads q = 4 i + c) on 32 distinct banks.
 constexpr int kZPad = 128;
+__device__ __forceinline__ int cens_dec_stride(const Workspace& ws) { return ws.dec_stride; }
 __device__ __forceinline__ int ppos(int q) { return (q + kZPad) + ((q + kZPad) >> 5); }
 __host__ __device__ constexpr int plen(int n) { return (n + 2 * kZPad) + ((n + 2 * kZPad) >> 5) + 1; }
 
 // de-interleaved signals of octaves 1..6 (lengths 8000 .. 250 -> halves 4000 .. 125)
 constexpr int kHalf1 = 4000, kHalf2 = 2000, kHalf3 = 1000, kHalf4 = 500, kHalf5 = 250, kHalf6 = 125;
-constexpr int kDecFloats = 2 * (plen(kHalf1) + plen(kHalf2) + plen(kHalf3) + plen(kHalf4) + plen(kHalf5) + plen(kHalf6));
-static_assert(2 * plen(8000) * 4 <= kCensTeams * 16 * 17 * 16, "the staged input must fit the exchange buffers it aliases");
+
+// Global layout of the decimated signals of one segment (workspace `dec`): octave o = 1..6 in natural sample order,
+// kGPad zero samples on either side (librosa's centre padding; the workspace is zeroed once at allocation and the pads
+// are never written), so the CQT frame loader needs no bounds checks.
+constexpr int kGPad = 256;
+__host__ __device__ constexpr int goff(int o) {          // offset of octave o's first pad sample
+    int off = 0;
+    for (int i = 1; i < o; ++i) off += (16000 >> i) + 2 * kGPad;
+    return off;
+}
+constexpr int kDecGlobalFloats = goff(7);                // 18,822 floats per segment
+int cens_dec_floats_per_segment() { return (kDecGlobalFloats + 3) & ~3; }
+
+// ---------------------------------------------------------------------------------------------- k_cens_dec
+struct DecSmem {
+    float a[2 * plen(8000)];                           // input (even | odd); later octaves 2..6
+    float o1[2 * plen(kHalf1)];                        // octave 1
+};
+constexpr int kDecThreads = 128;
+
+// One decimation stage: in (de-interleaved, half-length hin, i.e. 2 hin samples) -> out (de-interleaved, hin samples)
+// and to global memory in natural order.
+// out[n] = f32( (h63 * E[n] + sum_m g[m] * (O[n-1-m] + O[n+m])) / sqrt(0.5) ),  E[q] = in[2q], O[q] = in[2q+1].
+__device__ __forceinline__ void decimate_stage(const float* __restrict__ inE, const float* __restrict__ inO, int hin,
+                                               float* __restrict__ outE, float* __restrict__ outO,
+                                               float* __restrict__ outG, int tid) {
+    const double inv_s = 1.0 / sqrt(0.5);
+    for (int n0 = kOutPerThread * tid; n0 < hin; n0 += kOutPerThread * kDecThreads) {
+        double w[kWin];
+#pragma unroll
+        for (int q = 0; q < kWin; ++q) w[q] = (double)inO[ppos(n0 - 32 + q)];   // zero pads cover q < 0 and q >= hin
+        float v[kOutPerThread];
+#pragma unroll
+        for (int p = 0; p < kOutPerThread; ++p) {
+            double acc = c_hb_centre * (double)inE[ppos(n0 + p)];
+#pragma unroll
+            for (int m = 0; m < 32; ++m) acc = fma(c_hb_odd[m], w[p + 31 - m] + w[p + 32 + m], acc);
+            v[p] = (float)(acc * inv_s);
+        }
+        // hin is a multiple of 4 for every stage but the last (250 outputs): guard per pair
+#pragma unroll
+        for (int p = 0; p < kOutPerThread; p += 2) {
+            const int n = n0 + p;
+            if (n < hin) {
+                outE[ppos(n >> 1)] = v[p];
+                if (n + 1 < hin) outO[ppos(n >> 1)] = v[p + 1];
+                if (n + 1 < hin) *reinterpret_cast<float2*>(outG + n) = make_float2(v[p], v[p + 1]);
+                else outG[n] = v[p];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kDecThreads, 2) k_cens_dec(const float* __restrict__ y, Geometry g, Workspace ws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DecSmem& S = *reinterpret_cast<DecSmem*>(smem_raw);
+    const int tid = threadIdx.x, b = blockIdx.x, L = g.L;
+    const float2* y2 = reinterpret_cast<const float2*>(y + (size_t)b * L);
+    float* G = ws.dec + (size_t)b * cens_dec_stride(ws);
+    for (int i = tid; i < 2 * plen(8000); i += kDecThreads) S.a[i] = 0.f;
+    for (int i = tid; i < 2 * plen(kHalf1); i += kDecThreads) S.o1[i] = 0.f;
+    __syncthreads();
+    {
+        float* E0 = S.a;
+        float* O0 = S.a + plen(8000);
+        for (int m = tid; m < 8000; m += kDecThreads) {
+            float2 v = make_float2(0.f, 0.f);
+            if (2 * m < L) v = __ldg(y2 + m);
+            E0[ppos(m)] = v.x;
+            O0[ppos(m)] = v.y;
+        }
+    }
+    __syncthreads();
+    decimate_stage(S.a, S.a + plen(8000), 8000, S.o1, S.o1 + plen(kHalf1), G + goff(1) + kGPad, tid);
+    __syncthreads();
+    // octaves 2..6 reuse the input's storage (dead after stage 1); each needs its pads zeroed again
+    for (int i = tid; i < 2 * plen(8000); i += kDecThreads) S.a[i] = 0.f;
+    __syncthreads();
+    float* E2 = S.a;                 float* O2 = E2 + plen(kHalf2);
+    float* E3 = O2 + plen(kHalf2);   float* O3 = E3 + plen(kHalf3);
+    float* E4 = O3 + plen(kHalf3);   float* O4 = E4 + plen(kHalf4);
+    float* E5 = O4 + plen(kHalf4);   float* O5 = E5 + plen(kHalf5);
+    float* E6 = O5 + plen(kHalf5);   float* O6 = E6 + plen(kHalf6);
+    decimate_stage(S.o1, S.o1 + plen(kHalf1), kHalf1, E2, O2, G + goff(2) + kGPad, tid);
+    __syncthreads();
+    decimate_stage(E2, O2, kHalf2, E3, O3, G + goff(3) + kGPad, tid);
+    __syncthreads();
+    decimate_stage(E3, O3, kHalf3, E4, O4, G + goff(4) + kGPad, tid);
+    __syncthreads();
+    decimate_stage(E4, O4, kHalf4, E5, O5, G + goff(5) + kGPad, tid);
+    __syncthreads();
+    decimate_stage(E5, O5, kHalf5, E6, O6, G + goff(6) + kGPad, tid);
+}
+
+// ---------------------------------------------------------------------------------------------- k_cens (CQT)
+constexpr int kCensThreads = 128, kCensTeams = kCensThreads / 16;
 
 struct CensSmem {
-    union {
-        double2 xch[kCensTeams][16 * 17];              // phase 2: FFT exchange buffers
-        float y0[2 * plen(8000)];                      // phase 1: the input, de-interleaved (even | odd)
-    } u;
-    float dec[kDecFloats];                             // octaves 1..6: [even | odd] per octave
+    double2 xch[kCensTeams][16 * 17];                  // FFT exchange buffers
     float2 spec[kCensTeams][kBinSpan + 3];
     float cqmag[kCensTeams][kCqtBinsPerOct + 4];
     float2 basis[2][kCqtBinsPerOct * kCqtEllWidth];    // [0]: basis, [1]: basis * sqrt(2) (odd octaves), (re, im)
@@ -66,33 +156,7 @@ struct CensSmem {
     float fscratch[32];
 };
 
-// One decimation stage: in (de-interleaved, half-length hin, i.e. 2 hin samples) -> out (de-interleaved, hin samples).
-// out[n] = f32( (h63 * E[n] + sum_m g[m] * (O[n-1-m] + O[n+m])) / sqrt(0.5) ),  E[q] = in[2q], O[q] = in[2q+1].
-__device__ __forceinline__ void decimate_stage(const float* __restrict__ inE, const float* __restrict__ inO, int hin,
-                                               float* __restrict__ outE, float* __restrict__ outO, int tid) {
-    const double inv_s = 1.0 / sqrt(0.5);
-    for (int n0 = kOutPerThread * tid; n0 < hin; n0 += kOutPerThread * kCensThreads) {
-        double w[kWin];
-#pragma unroll
-        for (int q = 0; q < kWin; ++q) {
-            w[q] = (double)inO[ppos(n0 - 32 + q)];           // zero pads cover q < 0 and q >= hin
-        }
-#pragma unroll
-        for (int p = 0; p < kOutPerThread; ++p) {
-            const int n = n0 + p;
-            if (n < hin) {
-                double acc = c_hb_centre * (double)inE[ppos(n)];
-#pragma unroll
-                for (int m = 0; m < 32; ++m) acc = fma(c_hb_odd[m], w[p + 31 - m] + w[p + 32 + m], acc);
-                const float v = (float)(acc * inv_s);
-                if (n & 1) outO[ppos(n >> 1)] = v;
-                else outE[ppos(n >> 1)] = v;
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kCensThreads, 1) k_cens(const float* __restrict__ y, Geometry g, Tables tb,
+__global__ void __launch_bounds__(kCensThreads, 3) k_cens(const float* __restrict__ y, Geometry g, Tables tb,
                                                           Workspace ws, float* feats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CensSmem& S = *reinterpret_cast<CensSmem*>(smem_raw);
@@ -100,21 +164,9 @@ __global__ void __launch_bounds__(kCensThreads, 1) k_cens(const float* __restric
     const int b = blockIdx.x, L = g.L, T = g.T;
     const float* yb = y + (size_t)b * L;
     const float2* y2 = reinterpret_cast<const float2*>(yb);
+    const float* G = ws.dec + (size_t)b * cens_dec_stride(ws);
 
-    // ---- stage the input (even | odd), the basis of this segment's tuning, the smoothing window
-    for (int i = tid; i < 2 * plen(8000); i += kCensThreads) S.u.y0[i] = 0.f;
-    for (int i = tid; i < kDecFloats; i += kCensThreads) S.dec[i] = 0.f;
-    __syncthreads();
-    {
-        float* E0 = S.u.y0;
-        float* O0 = S.u.y0 + plen(8000);
-        for (int m = tid; m < 8000; m += kCensThreads) {
-            float2 v = make_float2(0.f, 0.f);
-            if (2 * m < L) v = __ldg(y2 + m);
-            E0[ppos(m)] = v.x;
-            O0[ppos(m)] = v.y;
-        }
-    }
+    // ---- stage the basis of this segment's tuning and the smoothing window
     const int tun = ws.tuning[b * 2 + 1];
     {
         const int16_t* bcol = tb.cqt_col + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
@@ -134,39 +186,17 @@ __global__ void __launch_bounds__(kCensThreads, 1) k_cens(const float* __restric
         for (int i = tid; i < kCqtBins; i += kCensThreads) S.inv_sl[i] = 1.0 / slen[i];
     }
     if (tid < 43) {
-        // scipy.signal.get_window('hann', 43, fftbins=False) normalised to unit sum (sum = 21 exactly in real arithmetic;
-        // accumulated here the way the reference does, in index order)
+        // scipy.signal.get_window('hann', 43, fftbins=False) normalised to unit sum (accumulated in index order)
         double wsum = 0.0;
         for (int j = 0; j < 43; ++j) wsum += 0.5 - 0.5 * cos(2.0 * 3.14159265358979323846 * (double)j / 42.0);
         S.swin[tid] = (0.5 - 0.5 * cos(2.0 * 3.14159265358979323846 * (double)tid / 42.0)) / wsum;
     }
     __syncthreads();
 
-    // ---- phase 1: six cascaded 2:1 decimations
-    const int halves[7] = {8000, kHalf1, kHalf2, kHalf3, kHalf4, kHalf5, kHalf6};
-    int offE[7], offO[7];                                   // offsets into S.dec (octaves 1..6)
-    {
-        int p = 0;
-#pragma unroll
-        for (int o = 1; o <= 6; ++o) {
-            offE[o] = p;
-            offO[o] = p + plen(halves[o]);
-            p += 2 * plen(halves[o]);
-        }
-        offE[0] = offO[0] = 0;
-    }
-    decimate_stage(S.u.y0, S.u.y0 + plen(8000), halves[0], S.dec + offE[1], S.dec + offO[1], tid);
-    __syncthreads();
-#pragma unroll
-    for (int o = 2; o <= 6; ++o) {
-        decimate_stage(S.dec + offE[o - 1], S.dec + offO[o - 1], halves[o - 1], S.dec + offE[o], S.dec + offO[o], tid);
-        __syncthreads();
-    }
-
-    // ---- phase 2: CQT -> chroma fold, one half-warp per frame, 7 octaves each
+    // ---- CQT -> chroma fold, one half-warp per frame, 7 octaves each
     const int h = lane & 15, team = tid >> 4;
     const int partner = (lane & 16) | ((16 - h) & 15);
-    double2* xch = S.u.xch[team];
+    double2* xch = S.xch[team];
     double2 tw[16];
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) tw[k1] = __ldg(tb.tw256 + ((h * k1) & 255));
@@ -192,12 +222,12 @@ __global__ void __launch_bounds__(kCensThreads, 1) k_cens(const float* __restric
                     a[j] = make_double2((double)v.x, (double)v.y);   // window = 'ones'
                 }
             } else {
-                const float* E = S.dec + offE[o];
-                const float* O = S.dec + offO[o];
+                // c0 >= -128 complex samples = -kGPad samples: the zero pads are the centre padding
+                const float2* src = reinterpret_cast<const float2*>(G + goff(o) + kGPad) + c0 + h;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int pq = ppos(c0 + h + 16 * j);            // c0 >= -kZPad; the zero pads are the centre padding
-                    a[j] = make_double2((double)E[pq], (double)O[pq]);
+                    const float2 v = __ldg(src + 16 * j);
+                    a[j] = make_double2((double)v.x, (double)v.y);
                 }
             }
             team_fft<16>(a, tw, 1, xch, h);
@@ -294,11 +324,13 @@ void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, con
                  cudaStream_t st) {
     static bool done = false;
     if (!done) {
+        cudaFuncSetAttribute(k_cens_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
         cudaFuncSetAttribute(k_cens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CensSmem));
         done = true;
     }
+    k_cens_dec<<<n, kDecThreads, sizeof(DecSmem), st>>>(y, g, ws);
     k_cens<<<n, kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats);
-    note_launch();
+    note_launch(2);
 }
 
 }  // namespace bpc

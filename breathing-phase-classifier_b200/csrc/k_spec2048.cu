@@ -106,14 +106,18 @@ __device__ __forceinline__ void warp_band_minmax(const float* row, int lo, int l
 __device__ __forceinline__ float c64_abs_f32(float re, float im) {
     const float a = fabsf(re), b = fabsf(im);
     const float x = fmaxf(a, b), y = fminf(a, b);
-    if (!(x > 1e-18f && x < 1e18f)) return (float)sqrt((double)re * (double)re + (double)im * (double)im);
     const float p = __fmul_rn(x, x), pe = __fmaf_rn(x, x, -p);          // x^2 = p + pe
     const float q = __fmul_rn(y, y), qe = __fmaf_rn(y, y, -q);          // y^2 = q + qe
     const float hi = __fadd_rn(p, q);
     const float lo = __fadd_rn(__fadd_rn(__fsub_rn(p, hi), q), __fadd_rn(pe, qe));   // p >= q: fast two-sum
-    const float r = __fsqrt_rn(hi);
-    const float res = __fadd_rn(__fmaf_rn(-r, r, hi), lo);              // (hi + lo) - r^2
-    return __fadd_rn(r, __fdiv_rn(res, __fadd_rn(r, r)));
+    float rs;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(hi));           // ~2 ulp: the residual step absorbs it
+    const float r0 = __fmul_rn(hi, rs);
+    const float res = __fadd_rn(__fmaf_rn(-r0, r0, hi), lo);            // (hi + lo) - r0^2
+    float out = __fmaf_rn(res, __fmul_rn(0.5f, rs), r0);
+    if (!(x > 1e-18f && x < 1e18f))                                     // zero / denormal squares / overflow: exact path
+        out = (float)sqrt((double)re * (double)re + (double)im * (double)im);
+    return out;
 }
 
 // ================================================================================================ k_frame2048
@@ -125,7 +129,7 @@ __device__ __forceinline__ float c64_abs_f32(float re, float im) {
 constexpr int kF2Warps = 4;
 constexpr int kF2RowBytes = 32 * 33 * 16;            // exchange buffer, later the |X| row (1028 floats)
 
-__global__ void __launch_bounds__(32 * kF2Warps, 2) k_frame2048(const float* __restrict__ y, Geometry g, Tables tb,
+__global__ void __launch_bounds__(32 * kF2Warps, 3) k_frame2048(const float* __restrict__ y, Geometry g, Tables tb,
                                                                  Workspace ws, int total_frames) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(32 * kF2Warps, 2) k_frame2048(const float* __r
             }
             team_fft<32>(a, twa, 32, xch, lane);
             const double z0 = a[0].x - a[0].y;                 // lane 0: X[1024] = Re Z[0] - Im Z[0]
-            auto emit = [&](int k, double2 t2) { row[k] = c64_abs_f32((float)(0.5 * t2.x), (float)(0.5 * t2.y)); };
+            auto emit = [&](int k, double2 t2) { row[k] = c64_abs_f32(0.5f * (float)t2.x, 0.5f * (float)t2.y); };
             team_rsplit<32, 0, 31>(a, wl, lane, partner, emit);
             if (lane == 0) row[1024] = fabsf((float)z0);
         }

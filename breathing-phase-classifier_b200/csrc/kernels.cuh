@@ -55,6 +55,8 @@ struct Workspace {            // per chunk of `cap` segments
     float* mag_even;          // [cap, (T+1)/2, kMag2048Stride]  |STFT2048| rows of the hop-512 frames (1025 valid bins)
     double* frame_feat;       // [cap, T, 20]  per-frame centroid, bandwidth, flatness, contrast peaks / valleys
     float* melD;              // [cap, T, 128] mel-D power columns
+    float* dec;               // [cap, dec_stride]  half-band decimated signals of the CQT octaves 1..6 (zero padded)
+    int dec_stride;
     int* tuning;              // [cap, 2]   tuning bin for 12 / 36 bins per octave
     float* chroma_min;        // [cap, 2]   min of the normalised chroma_stft / chroma_cens rows
     int* ints;                // [cap, 2]   n_peaks, first-min index
@@ -108,6 +110,7 @@ void launch_modspec(int n, const Geometry& g, const Tables& tb, const float* mel
 void launch_pad_scalars(int n, const Geometry& g, float* scalars, cudaStream_t st);
 
 void upload_cens_constants(const double* taps127);
+int cens_dec_floats_per_segment();
 int64_t launches_issued();   // process-wide counter bumped by every launcher
 void note_launch(int n = 1);
 
