@@ -174,6 +174,15 @@ int build_tables(bpc_handle* h) {
     if ((rc = upload(h, twiddles(2048, 1025), &tb.ptw2048))) return rc;
     if ((rc = upload(h, twiddles(8000, 8000), &tb.tw8000))) return rc;
     if ((rc = upload(h, twiddles(16000, 8001), &tb.ptw16000))) return rc;
+    {
+        auto to_f = [](const std::vector<double2>& d) {
+            std::vector<float2> f(d.size());
+            for (size_t i = 0; i < d.size(); ++i) f[i] = make_float2((float)d[i].x, (float)d[i].y);
+            return f;
+        };
+        if ((rc = upload(h, to_f(twiddles(8000, 8000)), &tb.tw8000f))) return rc;
+        if ((rc = upload(h, to_f(twiddles(16000, 8001)), &tb.ptw16000f))) return rc;
+    }
     if ((rc = upload_bank(h, mel_bank(p.sr, 512, 128, 0.0, p.fmax), &tb.mel_a))) return rc;
     if ((rc = upload_bank(h, mel_bank(p.sr, 512, 128, 0.0, p.sr / 2.0), &tb.mel_b))) return rc;
     if ((rc = upload_bank(h, mel_bank(p.sr, 512, 64, 0.0, p.sr / 2.0), &tb.mel_c))) return rc;

@@ -140,62 +140,110 @@ __device__ __forceinline__ float delta_at(const float* row, int t, int T, int or
 }
 
 // Band-form filterbank applied to |X| (power = false) or |X|^2 (power = true): out[m*T + t], float32 accumulate.
+// ROWS (a power of two) consecutive threads own consecutive mel rows of one frame; the weights come from the transposed
+// band table ([tap][row], one coalesced request per tap, zero beyond a row's count), the loop runs to the largest count
+// of the warp's rows.
+template <int ROWS>
 __device__ void apply_bank(const BankDev& bank, const float* __restrict__ mag_b, int T, bool power, float* out) {
-    const int total = bank.rows * T;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int m = idx % bank.rows, t = idx / bank.rows;
-        const int s = bank.start[m], c = bank.count[m];
-        const float* src = mag_b + (size_t)t * kMagStride + s;
-        const float* w = bank.w + (size_t)m * bank.width;
+    const int total = ROWS * T;
+    const int iters = (total + blockDim.x - 1) / blockDim.x;
+    for (int it = 0; it < iters; ++it) {
+        const int idx = it * blockDim.x + threadIdx.x;
+        const bool live = idx < total;
+        const int m = idx & (ROWS - 1), t = live ? idx / ROWS : 0;
+        const int s = __ldg(bank.start + m), c = live ? __ldg(bank.count + m) : 0;
+        const int cmax = __reduce_max_sync(0xffffffffu, c);
+        const float* src = mag_b + (size_t)t * kMagStride;
+        const float* wt = bank.wt + m;
         float acc = 0.f;
-        for (int j = 0; j < c; ++j) {
-            const float v = __ldg(src + j);
-            acc = fmaf(__ldg(w + j), power ? __fmul_rn(v, v) : v, acc);
+        for (int j = 0; j < cmax; ++j) {
+            const float v = __ldg(src + min(s + j, 256));
+            acc = fmaf(__ldg(wt + j * ROWS), power ? __fmul_rn(v, v) : v, acc);
         }
-        out[m * T + t] = acc;
+        if (live) out[m * T + t] = acc;
     }
     __syncthreads();
 }
 
 // C[k*T + t] = sum_n D[k*128 + n] * P[n*T + t], k < 40 (ortho DCT-II along the mel axis, first 40 rows).
-// 4 rows per work item; 4 float32 partial sums per row combined in float64.
-__device__ void dct_mel40(const float* __restrict__ D, const float* P, int T, float* C) {
-    const int items = 10 * T;
-    for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        const int t = it % T, k0 = (it / T) * 4;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+// 256 threads = 8 row groups (5 rows, warp-uniform: D is read as broadcast float4) x 32 column pairs; float32 partial
+// sums over 32 n combined in float64.  Ds: the [40, 128] matrix staged in shared memory.
+__device__ void dct_mel40(const float* Ds, const float* P, int T, float* C) {
+    const int kb = threadIdx.x >> 5, tp = threadIdx.x & 31;
+    const int t0 = 2 * tp, t1 = min(2 * tp + 1, T - 1);
+    if (kb < 8 && t0 < T) {
+        double acc[5][2];
 #pragma unroll
+        for (int i = 0; i < 5; ++i) acc[i][0] = acc[i][1] = 0.0;
+#pragma unroll 1
         for (int blk = 0; blk < 4; ++blk) {
-            float part[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-            for (int n = blk * 32; n < blk * 32 + 32; ++n) {
-                const float p = P[n * T + t];
+            float part[5][2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) part[i] = fmaf(__ldg(D + (k0 + i) * 128 + n), p, part[i]);
+            for (int i = 0; i < 5; ++i) part[i][0] = part[i][1] = 0.f;
+#pragma unroll 2
+            for (int n = blk * 32; n < blk * 32 + 32; n += 4) {
+                float p0[4], p1[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { p0[q] = P[(n + q) * T + t0]; p1[q] = P[(n + q) * T + t1]; }
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    const float4 d = *reinterpret_cast<const float4*>(Ds + (5 * kb + i) * 128 + n);
+                    part[i][0] = fmaf(d.x, p0[0], part[i][0]); part[i][1] = fmaf(d.x, p1[0], part[i][1]);
+                    part[i][0] = fmaf(d.y, p0[1], part[i][0]); part[i][1] = fmaf(d.y, p1[1], part[i][1]);
+                    part[i][0] = fmaf(d.z, p0[2], part[i][0]); part[i][1] = fmaf(d.z, p1[2], part[i][1]);
+                    part[i][0] = fmaf(d.w, p0[3], part[i][0]); part[i][1] = fmaf(d.w, p1[3], part[i][1]);
+                }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] += (double)part[i];
+            for (int i = 0; i < 5; ++i) { acc[i][0] += (double)part[i][0]; acc[i][1] += (double)part[i][1]; }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) C[(k0 + i) * T + t] = (float)acc[i];
+        for (int i = 0; i < 5; ++i) {
+            C[(5 * kb + i) * T + t0] = (float)acc[i][0];
+            if (2 * tp + 1 < T) C[(5 * kb + i) * T + t0 + 1] = (float)acc[i][1];
+        }
     }
     __syncthreads();
 }
 
-// C2[k*T + u] = sum_t DT[u][t] * C1[k*T + t] (ortho DCT-II along time); DTt is stored transposed, [t][u].
-__device__ void dct_time40(const float* __restrict__ DTt, const float* C1, int T, float* C2) {
-    for (int idx = threadIdx.x; idx < 40 * T; idx += blockDim.x) {
-        const int u = idx % T, k = idx / T;
-        double acc = 0.0;
-        float part = 0.f;
+// C2[k*T + u] = sum_t DT[u][t] * C1[k*T + t] (ortho DCT-II along time); DTs is the transposed matrix [t][u] staged in
+// shared memory.  Same 5 x 2 register tile; float32 partial sums over 16 t combined in float64.
+__device__ void dct_time40(const float* DTs, const float* C1, int T, float* C2) {
+    const int kb = threadIdx.x >> 5, up = threadIdx.x & 31;
+    const int u0 = 2 * up, u1 = min(2 * up + 1, T - 1);
+    if (kb < 8 && u0 < T) {
+        double acc[5][2];
+        float part[5][2];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { acc[i][0] = acc[i][1] = 0.0; part[i][0] = part[i][1] = 0.f; }
         for (int t = 0; t < T; ++t) {
-            part = fmaf(__ldg(DTt + t * T + u), C1[k * T + t], part);
-            if ((t & 15) == 15) { acc += (double)part; part = 0.f; }
+            const float d0 = DTs[t * T + u0], d1 = DTs[t * T + u1];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const float c = C1[(5 * kb + i) * T + t];
+                part[i][0] = fmaf(d0, c, part[i][0]);
+                part[i][1] = fmaf(d1, c, part[i][1]);
+            }
+            if ((t & 15) == 15) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    acc[i][0] += (double)part[i][0]; acc[i][1] += (double)part[i][1];
+                    part[i][0] = part[i][1] = 0.f;
+                }
+            }
         }
-        acc += (double)part;
-        C2[idx] = (float)acc;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            C2[(5 * kb + i) * T + u0] = (float)(acc[i][0] + (double)part[i][0]);
+            if (2 * up + 1 < T) C2[(5 * kb + i) * T + u0 + 1] = (float)(acc[i][1] + (double)part[i][1]);
+        }
     }
     __syncthreads();
+}
+
+// copy a constant matrix into shared memory (all threads; caller syncs)
+__device__ __forceinline__ void stage_matrix(float* dst, const float* __restrict__ src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
 // whole-array statistics of a shared-memory array
@@ -221,21 +269,37 @@ __device__ void role_mel(int b, const Geometry g, const Tables& tb, const Worksp
     float* P = smem;                 // [128*T] mel power -> mel_db
     float* C1 = P + NP;              // [40*T]
     float* C2 = C1 + 40 * T;         // [40*T]
+    float* Ds = C2 + 40 * T;         // [40*128] DCT matrix (mel axis)
+    float* DTs = Ds + 40 * 128;      // [T*T] DCT matrix (time axis), transposed
     const float* mag_b = ws.mag512 + (size_t)b * T * kMagStride;
 
-    apply_bank(tb.mel_a, mag_b, T, true, P);
+    if (!mel3) {
+        stage_matrix(Ds, tb.dct_mel, 40 * 128);
+        stage_matrix(DTs, tb.dct_time, T * T);
+    }
+    apply_bank<128>(tb.mel_a, mag_b, T, true, P);
     power_to_db_inplace(P, NP, true, fscratch);                      // process.py:33
     if (ws.dbg_mel_db) {
         float* d = ws.dbg_mel_db + (size_t)b * NP;
         for (int i = threadIdx.x; i < NP; i += blockDim.x) d[i] = P[i];
     }
-    // statistics of mel_db, delta, delta2 (process.py:34-38)
+    float *o0, *o1, *o2;
+    if (mel3) {
+        o0 = mel3 + (size_t)b * 3 * NP; o1 = o0 + NP; o2 = o1 + NP;
+    } else {
+        o0 = plane_ptr(feats, b, BPC_CH_MEL, T);
+        o1 = plane_ptr(feats, b, BPC_CH_MEL_DELTA, T);
+        o2 = plane_ptr(feats, b, BPC_CH_MEL_DELTA2, T);
+    }
+    // statistics of mel_db, delta, delta2 (process.py:34-38).  The raw deltas are parked in their output planes and
+    // normalised in place by the thread that wrote them (v1 evaluated the FP64 stencils twice).
     double s0 = 0, q0 = 0, s1 = 0, q1 = 0, s2 = 0, q2 = 0;
     for (int i = threadIdx.x; i < NP; i += blockDim.x) {
         const int m = i / T, t = i - m * T;
-        const double v0 = (double)P[i];
-        const double v1 = (double)delta_at(P + m * T, t, T, 1);
-        const double v2 = (double)delta_at(P + m * T, t, T, 2);
+        const float d1 = delta_at(P + m * T, t, T, 1), d2 = delta_at(P + m * T, t, T, 2);
+        o1[i] = d1;
+        o2[i] = d2;
+        const double v0 = (double)P[i], v1 = (double)d1, v2 = (double)d2;
         s0 += v0; q0 += v0 * v0;
         s1 += v1; q1 += v1 * v1;
         s2 += v2; q2 += v2 * v2;
@@ -245,25 +309,16 @@ __device__ void role_mel(int b, const Geometry g, const Tables& tb, const Worksp
     s2 = block_sum(s2, dscratch); q2 = block_sum(q2, dscratch);
     const ZTerm z0 = make_zterm(s0, q0, (double)NP), z1 = make_zterm(s1, q1, (double)NP),
                 z2 = make_zterm(s2, q2, (double)NP);
-    float *o0, *o1, *o2;
-    if (mel3) {
-        o0 = mel3 + (size_t)b * 3 * NP; o1 = o0 + NP; o2 = o1 + NP;
-    } else {
-        o0 = plane_ptr(feats, b, BPC_CH_MEL, T);
-        o1 = plane_ptr(feats, b, BPC_CH_MEL_DELTA, T);
-        o2 = plane_ptr(feats, b, BPC_CH_MEL_DELTA2, T);
-    }
     for (int i = threadIdx.x; i < NP; i += blockDim.x) {
-        const int m = i / T, t = i - m * T;
         o0[i] = z0(P[i]);
-        o1[i] = z1(delta_at(P + m * T, t, T, 1));
-        o2[i] = z2(delta_at(P + m * T, t, T, 2));
+        o1[i] = z1(o1[i]);
+        o2[i] = z2(o2[i]);
     }
     if (mel3) return;
 
     // mod_spec (methods.py:142-143): DCT-II ortho over mel (keep 40), then over time
-    dct_mel40(tb.dct_mel, P, T, C1);
-    dct_time40(tb.dct_time, C1, T, C2);
+    dct_mel40(Ds, P, T, C1);
+    dct_time40(DTs, C1, T, C2);
     if (ws.dbg_mod) {
         float* d = ws.dbg_mod + (size_t)b * 40 * T;
         for (int i = threadIdx.x; i < 40 * T; i += blockDim.x) d[i] = C2[i];
@@ -282,10 +337,12 @@ __device__ void role_mfcc(int b, const Geometry g, const Tables& tb, const Works
     float* P = smem;                 // [128*T]
     float* MF = P + NP;              // [40*T]
     float* OUT = MF + 40 * T;        // [120*T]
+    float* Ds = OUT + 120 * T;       // [40*128]
     const float* mag_b = ws.mag512 + (size_t)b * T * kMagStride;
-    apply_bank(tb.mel_b, mag_b, T, true, P);
+    stage_matrix(Ds, tb.dct_mel, 40 * 128);
+    apply_bank<128>(tb.mel_b, mag_b, T, true, P);
     power_to_db_inplace(P, NP, false, fscratch);                      // librosa.feature.mfcc: power_to_db(ref=1.0)
-    dct_mel40(tb.dct_mel, P, T, MF);
+    dct_mel40(Ds, P, T, MF);
     if (ws.dbg_mfcc) {
         float* d = ws.dbg_mfcc + (size_t)b * 120 * T;
         for (int i = threadIdx.x; i < 120 * T; i += blockDim.x) {
@@ -321,7 +378,7 @@ __device__ void role_gammatone(int b, const Geometry g, const Tables& tb, const 
     const int T = g.T, NP = kPlaneRows * T, NG = tb.mel_c.rows * T;
     float* G = smem;
     const float* mag_b = ws.mag512 + (size_t)b * T * kMagStride;
-    apply_bank(tb.mel_c, mag_b, T, false, G);
+    apply_bank<64>(tb.mel_c, mag_b, T, false, G);
     for (int i = threadIdx.x; i < NG; i += blockDim.x) G[i] = log1pf(G[i]);
     __syncthreads();
     if (ws.dbg_gam) {
@@ -443,7 +500,8 @@ __device__ void role_chroma_stft(int b, const Geometry g, const Tables& tb, cons
 }
 
 // ----------------------------------------------------------------------------------------------- the kernel
-constexpr int kConsumerSmemFloats = kPlaneRows * kMaxFrames + 40 * kMaxFrames + 120 * kMaxFrames + 64;
+constexpr int kConsumerSmemFloats = kPlaneRows * kMaxFrames + 40 * kMaxFrames + 120 * kMaxFrames + 40 * 128 + 64;
+static_assert(kPlaneRows * kMaxFrames + 80 * kMaxFrames + 40 * 128 + kMaxFrames * kMaxFrames <= kConsumerSmemFloats, "role_mel layout");
 
 __global__ void __launch_bounds__(256) k_spec512_consumers(Geometry g, Tables tb, Workspace ws, float* feats,
                                                            float* scalars, int32_t* status, float* mel3,
@@ -523,10 +581,14 @@ __global__ void __launch_bounds__(256) k_modspec(Geometry g, Tables tb, const fl
     float* P = smem;
     float* C1 = P + NP;
     float* C2 = C1 + 40 * T;
+    float* Ds = C2 + 40 * T;
+    float* DTs = Ds + 40 * 128;
+    stage_matrix(Ds, tb.dct_mel, 40 * 128);
+    stage_matrix(DTs, tb.dct_time, T * T);
     for (int i = threadIdx.x; i < NP; i += blockDim.x) P[i] = mel_db[(size_t)b * NP + i];
     __syncthreads();
-    dct_mel40(tb.dct_mel, P, T, C1);
-    dct_time40(tb.dct_time, C1, T, C2);
+    dct_mel40(Ds, P, T, C1);
+    dct_time40(DTs, C1, T, C2);
     for (int i = threadIdx.x; i < 40 * T; i += blockDim.x) out[(size_t)b * 40 * T + i] = C2[i];
 }
 

@@ -319,37 +319,45 @@ __global__ void __launch_bounds__(256) k_autocorr(const float* __restrict__ y, G
 constexpr int kHN = 8000;
 constexpr int kHilbertThreads = 512;
 
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+
+
 template <int R>
-__device__ __forceinline__ void dft_small(double2* a) {
+__device__ __forceinline__ void dft_small(float2* a) {
     if (R == 4) {
-        const double2 b0 = cadd(a[0], a[2]), b1 = csub(a[0], a[2]), b2 = cadd(a[1], a[3]);
-        const double2 d = csub(a[1], a[3]);
-        const double2 b3 = make_double2(d.y, -d.x);
+        const float2 b0 = cadd(a[0], a[2]), b1 = csub(a[0], a[2]), b2 = cadd(a[1], a[3]);
+        const float2 d = csub(a[1], a[3]);
+        const float2 b3 = make_float2(d.y, -d.x);
         a[0] = cadd(b0, b2); a[1] = cadd(b1, b3); a[2] = csub(b0, b2); a[3] = csub(b1, b3);
     } else {
-        const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
-        const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
-        const double2 t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]), t3 = csub(a[1], a[4]), t4 = csub(a[2], a[3]);
-        const double2 m1 = make_double2(a[0].x + c1 * t1.x + c2 * t2.x, a[0].y + c1 * t1.y + c2 * t2.y);
-        const double2 m2 = make_double2(a[0].x + c2 * t1.x + c1 * t2.x, a[0].y + c2 * t1.y + c1 * t2.y);
-        const double2 n1 = make_double2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-        const double2 n2 = make_double2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
-        a[0] = make_double2(a[0].x + t1.x + t2.x, a[0].y + t1.y + t2.y);
-        a[1] = make_double2(m1.x + n1.y, m1.y - n1.x);      // m1 - i n1
-        a[4] = make_double2(m1.x - n1.y, m1.y + n1.x);      // m1 + i n1
-        a[2] = make_double2(m2.x + n2.y, m2.y - n2.x);
-        a[3] = make_double2(m2.x - n2.y, m2.y + n2.x);
+        const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+        const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+        const float2 t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]), t3 = csub(a[1], a[4]), t4 = csub(a[2], a[3]);
+        const float2 m1 = make_float2(a[0].x + c1 * t1.x + c2 * t2.x, a[0].y + c1 * t1.y + c2 * t2.y);
+        const float2 m2 = make_float2(a[0].x + c2 * t1.x + c1 * t2.x, a[0].y + c2 * t1.y + c1 * t2.y);
+        const float2 n1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+        const float2 n2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+        a[0] = make_float2(a[0].x + t1.x + t2.x, a[0].y + t1.y + t2.y);
+        a[1] = make_float2(m1.x + n1.y, m1.y - n1.x);      // m1 - i n1
+        a[4] = make_float2(m1.x - n1.y, m1.y + n1.x);      // m1 + i n1
+        a[2] = make_float2(m2.x + n2.y, m2.y - n2.x);
+        a[3] = make_float2(m2.x - n2.y, m2.y + n2.x);
     }
 }
 
 // one pass over all N/R butterflies with the given span; DIF: twiddle after the small DFT, DIT: before.
 template <int R, bool kDit>
-__device__ __forceinline__ void mixed_pass(double2* x, int span, const double2* __restrict__ tw, int tid) {
+__device__ __forceinline__ void mixed_pass(float2* x, int span, const float2* __restrict__ tw, int tid) {
     const int q = span / R, ts = kHN / span;
     for (int j = tid; j < kHN / R; j += kHilbertThreads) {
         const int blk = j / q, pos = j - blk * q;
         const int base = blk * span + pos;
-        double2 a[R];
+        float2 a[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) a[r] = x[base + r * q];
         if (kDit && pos != 0) {
@@ -388,20 +396,20 @@ struct HilbertTail {
     int best_i;
 };
 
-__global__ void __launch_bounds__(kHilbertThreads) k_hilbert(const float* __restrict__ y, Geometry g, Tables tb,
+__global__ void __launch_bounds__(kHilbertThreads, 2) k_hilbert(const float* __restrict__ y, Geometry g, Tables tb,
                                                               Workspace ws, float* scalars) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* X = reinterpret_cast<double2*>(smem_raw);                       // [8000]
-    HilbertTail& S = *reinterpret_cast<HilbertTail*>(smem_raw + sizeof(double2) * kHN);
+    float2* X = reinterpret_cast<float2*>(smem_raw);                         // [8000]; later env [16000] floats
+    HilbertTail& S = *reinterpret_cast<HilbertTail*>(smem_raw + sizeof(float) * 16000 + sizeof(unsigned short) * 16000);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x, L = g.L;                                        // L == 16000 (checked on the host)
     const float* yb = y + (size_t)b * L;
     for (int m = tid; m < kHN; m += kHilbertThreads) {
         const float2 v = __ldg(reinterpret_cast<const float2*>(yb) + m);
-        X[m] = make_double2((double)v.x, (double)v.y);
+        X[m] = v;
     }
     __syncthreads();
-    const double2* tw = tb.tw8000;
+    const float2* tw = tb.tw8000f;
     mixed_pass<5, false>(X, 8000, tw, tid);
     mixed_pass<5, false>(X, 1600, tw, tid);
     mixed_pass<5, false>(X, 320, tw, tid);
@@ -412,28 +420,28 @@ __global__ void __launch_bounds__(kHilbertThreads) k_hilbert(const float* __rest
     for (int k = tid; k <= kHN / 2; k += kHilbertThreads) {
         const int kn = (kHN - k) % kHN;
         const int pk = hilbert_pos(k), pn = hilbert_pos(kn);
-        const double2 zk = X[pk], zn = X[pn];
-        const double2 w = tb.ptw16000[k];                                      // exp(-2 pi i k / 16000)
+        const float2 zk = X[pk], zn = X[pn];
+        const float2 w = tb.ptw16000f[k];                                      // exp(-2 pi i k / 16000)
         // Y[k] = E + w O ; Y[N-k] = conj(E) - conj(w) conj(O) = conj(E - w O)
-        const double2 e = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));
-        const double2 o = make_double2(0.5 * (zk.y + zn.y), -0.5 * (zk.x - zn.x));
-        const double2 wo = cmul(w, o);
-        double2 yk = cadd(e, wo);
-        double2 yn = cconj(csub(e, wo));
+        const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+        const float2 wo = cmul(w, o);
+        float2 yk = cadd(e, wo);
+        float2 yn = cconj(csub(e, wo));
         // G = -i Y on 0 < k < N (bins k and N-k of the half spectrum), 0 at k = 0 and k = N (both live in pair k = 0)
-        double2 gk = make_double2(yk.y, -yk.x), gn = make_double2(yn.y, -yn.x);
-        if (k == 0) { gk = make_double2(0.0, 0.0); gn = make_double2(0.0, 0.0); }
+        float2 gk = make_float2(yk.y, -yk.x), gn = make_float2(yn.y, -yn.x);
+        if (k == 0) { gk = make_float2(0.f, 0.f); gn = make_float2(0.f, 0.f); }
         // for k == 0: X_half[0] = gk, X_half[N] = gn (the "N-k" partner of bin 0 is bin N)
         // inverse split: E' = (G[k] + conj(G[N-k]))/2, O' = (G[k] - conj(G[N-k]))/2 * conj(w), Z = E' + i O'
-        const double2 e2 = make_double2(0.5 * (gk.x + gn.x), 0.5 * (gk.y - gn.y));
-        const double2 d2 = make_double2(0.5 * (gk.x - gn.x), 0.5 * (gk.y + gn.y));
-        const double2 o2 = cmul(d2, cconj(w));
-        const double2 z = make_double2(e2.x - o2.y, e2.y + o2.x);
+        const float2 e2 = make_float2(0.5f * (gk.x + gn.x), 0.5f * (gk.y - gn.y));
+        const float2 d2 = make_float2(0.5f * (gk.x - gn.x), 0.5f * (gk.y + gn.y));
+        const float2 o2 = cmul(d2, cconj(w));
+        const float2 z = make_float2(e2.x - o2.y, e2.y + o2.x);
         // partner bin: Z[N-k] = conj(E') + i * conj(O') * (-1) ... derive from the same quantities:
         // E'[N-k] = conj(E'[k]); O'[N-k] = (G[N-k] - conj(G[k]))/2 * conj(w[N-k]) with w[N-k] = -conj(w[k])
-        const double2 dn = make_double2(0.5 * (gn.x - gk.x), 0.5 * (gn.y + gk.y));
-        const double2 on = cmul(dn, make_double2(-w.x, -w.y));                 // conj(w[N-k]) = -w[k]
-        const double2 zn2 = make_double2(e2.x - on.y, -e2.y + on.x);
+        const float2 dn = make_float2(0.5f * (gn.x - gk.x), 0.5f * (gn.y + gk.y));
+        const float2 on = cmul(dn, make_float2(-w.x, -w.y));                 // conj(w[N-k]) = -w[k]
+        const float2 zn2 = make_float2(e2.x - on.y, -e2.y + on.x);
         X[pk] = cconj(z);
         if (kn != k && k != 0) X[pn] = cconj(zn2);
     }
@@ -452,11 +460,11 @@ __global__ void __launch_bounds__(kHilbertThreads) k_hilbert(const float* __rest
         for (int i = 0; i < 16; ++i) {
             const int m = tid + kHilbertThreads * i;
             if (m < kHN) {
-                const double2 o = X[m];
+                const float2 o = X[m];
                 const float2 v = __ldg(reinterpret_cast<const float2*>(yb) + m);
-                const double h0 = o.x / (double)kHN, h1 = -o.y / (double)kHN;
-                e0[i] = (float)sqrt((double)v.x * (double)v.x + h0 * h0);
-                e1[i] = (float)sqrt((double)v.y * (double)v.y + h1 * h1);
+                const float h0 = o.x * (1.0f / (float)kHN), h1 = -o.y * (1.0f / (float)kHN);
+                e0[i] = (float)sqrt((double)v.x * (double)v.x + (double)h0 * (double)h0);   // np.abs(complex64)
+                e1[i] = (float)sqrt((double)v.y * (double)v.y + (double)h1 * (double)h1);
             }
         }
         __syncthreads();
@@ -475,8 +483,9 @@ __global__ void __launch_bounds__(kHilbertThreads) k_hilbert(const float* __rest
     const float estd = (float)sqrt(fmax(0.0, q / L - (s / L) * (s / L)));
     // scipy.signal.find_peaks(env, height=emean, distance=1600): local maxima (plateau mid-points), height filter.
     // Candidates are compacted into a list (r01 v3: the selection rounds rescanned all 16000 flags, 20 % of the kernel).
-    int* clist = reinterpret_cast<int*>(smem_raw + sizeof(float) * 16000);    // second half of X's storage
-    constexpr int kMaxList = 16000;                                            // 64 KB: every sample could be listed
+    unsigned short* clist = reinterpret_cast<unsigned short*>(smem_raw + sizeof(float) * 16000);   // after env
+    constexpr int kMaxList = 16000;                                            // 32 KB: every sample could be listed
+    constexpr int kGone = 0xffff;
     if (tid == 0) S.best_i = 0;                                                // list length
     __syncthreads();
     for (int i = tid + 1; i < L - 1; i += kHilbertThreads) {
@@ -487,7 +496,7 @@ __global__ void __launch_bounds__(kHilbertThreads) k_hilbert(const float* __rest
                 const int mid = (i + ahead - 1) / 2;
                 if (env[mid] >= emean) {
                     const int slot = atomicAdd(&S.best_i, 1);
-                    if (slot < kMaxList) clist[slot] = mid;
+                    if (slot < kMaxList) clist[slot] = (unsigned short)mid;
                 }
             }
         }
@@ -503,7 +512,7 @@ __global__ void __launch_bounds__(kHilbertThreads) k_hilbert(const float* __rest
         int bi = -1;
         for (int j = tid; j < nc; j += kHilbertThreads) {
             const int i = clist[j];
-            if (i >= 0 && (env[i] > bv || (env[i] == bv && i > bi))) { bv = env[i]; bi = i; }
+            if (i != kGone && (env[i] > bv || (env[i] == bv && i > bi))) { bv = env[i]; bi = i; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -528,7 +537,7 @@ __global__ void __launch_bounds__(kHilbertThreads) k_hilbert(const float* __rest
         hq += (double)pv * (double)pv;
         for (int j = tid; j < nc; j += kHilbertThreads) {
             const int i = clist[j];
-            if (i >= 0 && i > pi - 1600 && i < pi + 1600) clist[j] = -1;
+            if (i != kGone && i > pi - 1600 && i < pi + 1600) clist[j] = (unsigned short)kGone;
         }
         __syncthreads();
     }
@@ -561,7 +570,7 @@ void launch_time_scalars(const float* y, int n, const Geometry& g, const Tables&
 
 void launch_hilbert(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* scalars,
                     cudaStream_t st) {
-    const int bytes = (int)(sizeof(double2) * kHN + sizeof(HilbertTail));
+    const int bytes = (int)(sizeof(float) * 16000 + sizeof(unsigned short) * 16000 + sizeof(HilbertTail));
     static bool done = false;
     if (!done) {
         cudaFuncSetAttribute(k_hilbert, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);

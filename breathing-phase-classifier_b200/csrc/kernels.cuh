@@ -44,6 +44,8 @@ struct Tables {
     // Hilbert (FFT-8000 = 4^3 * 5^3)
     const double2* tw8000;        // exp(-2 pi i j / 8000), j < 8000
     const double2* ptw16000;      // exp(-2 pi i k / 16000), k <= 8000
+    const float2* tw8000f;        // float32 copies: scipy.signal.hilbert runs a float32 FFT on float32 input
+    const float2* ptw16000f;
     // tempogram
     const double* hann384;        // [384]
 };
