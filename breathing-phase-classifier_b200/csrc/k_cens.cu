@@ -140,23 +140,30 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_cens_dec(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------- k_cens (CQT)
-constexpr int kCensThreads = 128, kCensTeams = kCensThreads / 16;
+constexpr int kCensThreads = 256, kCensTeams = kCensThreads / 16;
 
+// ~101 KB and <= 128 registers: two 256-thread CTAs per SM, so a 592-segment chunk is exactly two full waves (at three
+// 128-thread CTAs per SM the second wave ran one third full)
 struct CensSmem {
-    double2 xch[kCensTeams][16 * 17];                  // FFT exchange buffers
+    union {
+        double2 xch[kCensTeams][16 * 17];              // FFT exchange buffers (CQT phase)
+        struct {                                       // CENS post-processing, after the CQT phase
+            float chroma[12 * kMaxFrames];
+            float quant[12 * kMaxFrames];
+        } post;
+    } u;
     float2 spec[kCensTeams][kBinSpan + 3];
     float cqmag[kCensTeams][kCqtBinsPerOct + 4];
+    float csum[12 * kMaxFrames];                       // folded chroma sums of the CQT phase
     float2 basis[2][kCqtBinsPerOct * kCqtEllWidth];    // [0]: basis, [1]: basis * sqrt(2) (odd octaves), (re, im)
     short bcol[kCqtBinsPerOct * kCqtEllWidth];         // column - kBinLo; padding entries point at 0 with weight 0
     double inv_sl[kCqtBins];                           // 1 / sqrt(lengths)
-    float chroma[12 * kMaxFrames];
-    float quant[12 * kMaxFrames];
     double swin[43];                                   // hann(43) / sum
     double dscratch[32];
     float fscratch[32];
 };
 
-__global__ void __launch_bounds__(kCensThreads, 3) k_cens(const float* __restrict__ y, Geometry g, Tables tb,
+__global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restrict__ y, Geometry g, Tables tb,
                                                           Workspace ws, float* feats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CensSmem& S = *reinterpret_cast<CensSmem*>(smem_raw);
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(kCensThreads, 3) k_cens(const float* __restric
     // ---- CQT -> chroma fold, one half-warp per frame, 7 octaves each
     const int h = lane & 15, team = tid >> 4;
     const int partner = (lane & 16) | ((16 - h) & 15);
-    double2* xch = S.xch[team];
+    double2* xch = S.u.xch[team];
     double2 tw[16];
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) tw[k1] = __ldg(tb.tw256 + ((h * k1) & 255));
@@ -267,17 +274,17 @@ __global__ void __launch_bounds__(kCensThreads, 3) k_cens(const float* __restric
             }
             __syncwarp();
         }
-        if (h < 12 && valid) S.chroma[h * T + t] = csum;
+        if (h < 12 && valid) S.csum[h * T + t] = csum;
     }
     __syncthreads();
     // ---- CENS post-processing per column: L1 normalise, quantise
     for (int t = tid; t < T; t += kCensThreads) {
         double l1 = 0.0;
-        for (int c = 0; c < 12; ++c) l1 += fabs((double)S.chroma[c * T + t]);
+        for (int c = 0; c < 12; ++c) l1 += fabs((double)S.csum[c * T + t]);
         if (l1 < 1.17549435e-38) l1 = 1.0;
         for (int c = 0; c < 12; ++c) {
-            const float v = (float)((double)S.chroma[c * T + t] / l1);
-            S.quant[c * T + t] = 0.25f * (float)((v > 0.4f) + (v > 0.2f) + (v > 0.1f) + (v > 0.05f));
+            const float v = (float)((double)S.csum[c * T + t] / l1);
+            S.u.post.quant[c * T + t] = 0.25f * (float)((v > 0.4f) + (v > 0.2f) + (v > 0.1f) + (v > 0.05f));
         }
     }
     __syncthreads();
@@ -286,30 +293,30 @@ __global__ void __launch_bounds__(kCensThreads, 3) k_cens(const float* __restric
         const int c = i / T, t = i - c * T;
         double acc = 0.0;
         const int jlo = max(0, t + 21 - (T - 1)), jhi = min(42, t + 21);
-        for (int j = jlo; j <= jhi; ++j) acc += S.swin[j] * (double)S.quant[c * T + t + 21 - j];
-        S.chroma[i] = (float)acc;
+        for (int j = jlo; j <= jhi; ++j) acc += S.swin[j] * (double)S.u.post.quant[c * T + t + 21 - j];
+        S.u.post.chroma[i] = (float)acc;
     }
     __syncthreads();
     // L2 normalise each column
     for (int t = tid; t < T; t += kCensThreads) {
         double l2 = 0.0;
-        for (int c = 0; c < 12; ++c) l2 += (double)S.chroma[c * T + t] * (double)S.chroma[c * T + t];
+        for (int c = 0; c < 12; ++c) l2 += (double)S.u.post.chroma[c * T + t] * (double)S.u.post.chroma[c * T + t];
         l2 = sqrt(l2);
         if (l2 < 1.17549435e-38) l2 = 1.0;
-        for (int c = 0; c < 12; ++c) S.quant[c * T + t] = (float)((double)S.chroma[c * T + t] / l2);
+        for (int c = 0; c < 12; ++c) S.u.post.quant[c * T + t] = (float)((double)S.u.post.chroma[c * T + t] / l2);
     }
     __syncthreads();
     if (ws.dbg_chroma_cens) {
         float* d = ws.dbg_chroma_cens + (size_t)b * 12 * T;
-        for (int i = tid; i < 12 * T; i += kCensThreads) d[i] = S.quant[i];
+        for (int i = tid; i < 12 * T; i += kCensThreads) d[i] = S.u.post.quant[i];
     }
     // ---- row-wise z-score -> rows 12..23; pad rows 24..127 with the min over all 24 normalised rows
     float mn = FLT_MAX;
     float* o = plane_ptr(feats, b, BPC_CH_CHROMA, T);
     for (int r = warp; r < 12; r += kCensThreads / 32) {
-        const ZTerm z = np_row_zterm(S.quant + r * T, T, lane);
+        const ZTerm z = np_row_zterm(S.u.post.quant + r * T, T, lane);
         for (int t = lane; t < T; t += 32) {
-            const float v = z(S.quant[r * T + t]);
+            const float v = z(S.u.post.quant[r * T + t]);
             o[(12 + r) * T + t] = v;
             mn = fminf(mn, v);
         }

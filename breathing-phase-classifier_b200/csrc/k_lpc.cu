@@ -144,25 +144,38 @@ __global__ void __launch_bounds__(256) k_stats(Geometry g, const float* __restri
     __shared__ double dscratch[32];
     const int b = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
     if (c < 9) {
-        const int NP = kPlaneRows * g.T;
-        const float* p = feats + ((size_t)b * 9 + c) * NP;
-        double s = 0.0, q = 0.0, mn = 1e300, mx = -1e300, cnt = 0.0;
-        for (int i = tid; i < NP; i += 256) {
-            const double v = (double)p[i];
-            if (isfinite(v)) { s += v; q += v * v; mn = fmin(mn, v); mx = fmax(mx, v); cnt += 1.0; }
+        const int NP = kPlaneRows * g.T;                       // 128 * T: a multiple of 4, planes are 16-byte aligned
+        const float4* p4 = reinterpret_cast<const float4*>(feats + ((size_t)b * 9 + c) * NP);
+        double s = 0.0, q = 0.0;
+        float mn = FLT_MAX, mx = -FLT_MAX;
+        int cnt = 0;
+        for (int i = tid; i < NP / 4; i += 256) {
+            const float4 v4 = __ldg(p4 + i);
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if ((__float_as_uint(v[e]) & 0x7f800000u) != 0x7f800000u) {
+                    const double d = (double)v[e];
+                    s += d;
+                    q = fma(d, d, q);
+                    mn = fminf(mn, v[e]);
+                    mx = fmaxf(mx, v[e]);
+                    ++cnt;
+                }
+            }
         }
         s = block_sum(s, dscratch);
         q = block_sum(q, dscratch);
-        cnt = block_sum(cnt, dscratch);
-        mn = block_reduce(mn, 1e300, OpMinD(), dscratch);
-        mx = block_reduce(mx, -1e300, OpMaxD(), dscratch);
-        if (tid == 0 && cnt > 0.0) {
+        const double cntd = block_sum((double)cnt, dscratch);
+        const double mnd = block_reduce((double)mn, 1e300, OpMinD(), dscratch);
+        const double mxd = block_reduce((double)mx, -1e300, OpMaxD(), dscratch);
+        if (tid == 0 && cntd > 0.0) {
             double* a = acc + (size_t)c * 5;
-            atomicAdd(a + 0, cnt);
+            atomicAdd(a + 0, cntd);
             atomicAdd(a + 1, s);
             atomicAdd(a + 2, q);
-            atomic_min_double(a + 3, mn);
-            atomic_max_double(a + 4, mx);
+            atomic_min_double(a + 3, mnd);
+            atomic_max_double(a + 4, mxd);
         }
     } else {
         for (int i = tid; i < g.nscal; i += 256) {

@@ -574,8 +574,9 @@ void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb,
         done = true;
     }
     const int total = n * g.T;
+    // persistent: exactly the 3 CTAs per SM that fit (168 registers, 67.6 KB), each warp strides over the frames
     int grid = (total + kF2Warps - 1) / kF2Warps;
-    if (grid > sms * 2 * 8) grid = sms * 2 * 8;
+    if (grid > sms * 3) grid = sms * 3;
     k_frame2048<<<grid, 32 * kF2Warps, kF2Warps * kF2RowBytes, st>>>(y, g, tb, ws, total);
     note_launch();
 }
