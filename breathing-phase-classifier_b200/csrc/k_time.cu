@@ -5,6 +5,7 @@
 #include <cmath>
 #include "kernels.cuh"
 #include "fft.cuh"
+#include "fft_reg.cuh"
 
 namespace bpc {
 
@@ -211,83 +212,118 @@ void launch_time_scalars(const float* y, int n, const Geometry& g, const Tables&
 // r[k] = sum_n y[n] y[n+k], k < 800 (methods.py:105-112; the reference computes all 2L-1 lags with np.correlate).
 // Blocked Wiener-Khinchin in FP64: with A_b = y[1024 b : 1024 b + 1024] zero-padded to 2048 and F_b = rfft(A_b),
 //   R[k] = sum_b conj(F_b[k]) * (F_b[k] + (-1)^k F_{b+1}[k]),   r = irfft(R)[0:1024]  (exact linear correlation).
+// r01 v8 layout: one 8-warp CTA per segment; every warp transforms one block with team_fft<32> (32 register-resident
+// points per lane, one exchange) and leaves its spectrum in its own exchange buffer, then all 256 threads fold the eight
+// spectra of the round into thread-private bins of R.  Two rounds cover the 16 blocks; warp 0 runs the inverse.
+// (v1..v7: 17 CTA-wide shared-memory radix-4 FFTs in sequence, 90 % of the shared-memory pipe, half of it bank conflicts.)
+constexpr int kAcWarps = 8, kAcThreads = 32 * kAcWarps;
+constexpr int kAcBins = (1025 + kAcThreads - 1) / kAcThreads;          // bins of R per thread (5)
+
 struct AutocorrSmem {
-    double2 fbuf[1024];
-    double2 tw[1024];
-    double2 prev[1025];
-    double2 R[1025];
-    double r[1024];
+    double2 xch[kAcWarps][32 * 33];       // exchange buffers; after a transform: the block's spectrum X[0..1024]
     double dscratch[32];
     int iscratch[32];
 };
 
-__global__ void __launch_bounds__(256) k_autocorr(const float* __restrict__ y, Geometry g, Tables tb, Workspace ws,
-                                                  float* scalars) {
+__global__ void __launch_bounds__(kAcThreads, 1) k_autocorr(const float* __restrict__ y, Geometry g, Tables tb,
+                                                            int* __restrict__ ints, float* scalars) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AutocorrSmem& S = *reinterpret_cast<AutocorrSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x, L = g.L;
     const float* yb = y + (size_t)b * L;
-    for (int j = tid; j < 1024; j += 256) S.tw[j] = tb.tw1024[j];
-    for (int k = tid; k < 1025; k += 256) { S.R[k] = make_double2(0.0, 0.0); S.prev[k] = make_double2(0.0, 0.0); }
-    __syncthreads();
-    const int nblk = (L + 1023) / 1024;
-    for (int blk = 0; blk < nblk; ++blk) {
+    const int partner = (32 - lane) & 31;
+    const double2 wp = __ldg(tb.ptw2048 + lane);
+    const double2 wl = make_double2(wp.y, -wp.x);                         // -i * exp(-2 pi i lane / 2048)
+    const double2* twa = tb.twa1024 + lane;
+    double2* xch = S.xch[warp];
+
+    double2 R[kAcBins], carry[kAcBins];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int m = tid + 256 * i;
-            double2 v = make_double2(0.0, 0.0);
-            if (m < 512) {
-                const int gi = blk * 1024 + 2 * m;
-                v.x = gi < L ? (double)__ldg(yb + gi) : 0.0;
-                v.y = gi + 1 < L ? (double)__ldg(yb + gi + 1) : 0.0;
+    for (int i = 0; i < kAcBins; ++i) { R[i] = make_double2(0.0, 0.0); carry[i] = make_double2(0.0, 0.0); }
+    const double sgn = (tid & 1) ? -1.0 : 1.0;                            // (-1)^k for k = tid + 256 i
+    const int nblk = (L + 1023) / 1024;
+    const int rounds = (nblk + kAcWarps - 1) / kAcWarps;
+    // blocks are taken from the top so that the spectrum of block b + 1 is known when block b is folded
+    for (int r = 0; r < rounds; ++r) {
+        const int base = nblk - kAcWarps * (r + 1);                       // lowest block of this round (may be < 0)
+        const int blk = base + warp;
+        {
+            double2 a[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float2 v = make_float2(0.f, 0.f);
+                if (j < 16 && blk >= 0) {
+                    const int gi = blk * 1024 + 2 * (lane + 32 * j);     // even; L is even
+                    if (gi < L) v = __ldg(reinterpret_cast<const float2*>(yb + gi));
+                }
+                a[j] = make_double2((double)v.x, (double)v.y);
             }
-            S.fbuf[swz(m)] = v;
+            team_fft<32>(a, twa, 32, xch, lane);
+            const double z0 = a[0].x - a[0].y;                            // lane 0: X[1024]
+            auto emit = [&](int k, double2 t2) { xch[k] = make_double2(0.5 * t2.x, 0.5 * t2.y); };
+            team_rsplit<32, 0, 31>(a, wl, lane, partner, emit);
+            if (lane == 0) xch[1024] = make_double2(z0, 0.0);
         }
         __syncthreads();
-        fft_r4_dif<5, 256, SyncBlock, true>(S.fbuf, S.tw, tid, SyncBlock());
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const int k = tid + 256 * i;
+        for (int i = 0; i < kAcBins; ++i) {
+            const int k = tid + kAcThreads * i;
             if (k <= 1024) {
-                const double2 F = rfft_bin<5, true>(S.fbuf, tb.ptw2048, k);
-                const double2 P = S.prev[k];
-                const double sgn = (k & 1) ? -1.0 : 1.0;
-                double2 acc = S.R[k];
-                // conj(P) * sgn * F  +  conj(F) * F
-                acc.x += sgn * (P.x * F.x + P.y * F.y) + (F.x * F.x + F.y * F.y);
-                acc.y += sgn * (P.x * F.y - P.y * F.x);
-                S.R[k] = acc;
-                S.prev[k] = F;
+                double2 nxt = carry[i];
+#pragma unroll
+                for (int w = kAcWarps - 1; w >= 0; --w) {
+                    const double2 F = S.xch[w][k];
+                    // conj(F) * (F + sgn * nxt)
+                    const double gx = F.x + sgn * nxt.x, gy = F.y + sgn * nxt.y;
+                    R[i].x += F.x * gx + F.y * gy;
+                    R[i].y += F.x * gy - F.y * gx;
+                    nxt = F;
+                }
+                carry[i] = nxt;
             }
         }
         __syncthreads();
     }
     // irfft(R, 2048) through one complex FFT-1024: Z[k] = E[k] + i O[k], feed conj(Z) to the forward transform
-    for (int k = tid; k < 1024; k += 256) {
-        const double2 xk = S.R[k], xn = S.R[1024 - k];
-        const double2 e = make_double2(0.5 * (xk.x + xn.x), 0.5 * (xk.y - xn.y));
-        const double2 d = make_double2(0.5 * (xk.x - xn.x), 0.5 * (xk.y + xn.y));
-        const double2 w = tb.ptw2048[k];                       // exp(-i th); need exp(+i th) = conj
-        const double2 o = make_double2(d.x * w.x + d.y * w.y, d.y * w.x - d.x * w.y);
-        const double2 z = make_double2(e.x - o.y, e.y + o.x);  // e + i o
-        S.fbuf[swz(k)] = make_double2(z.x, -z.y);
+#pragma unroll
+    for (int i = 0; i < kAcBins; ++i) {
+        const int k = tid + kAcThreads * i;
+        if (k <= 1024) S.xch[0][k] = R[i];
     }
     __syncthreads();
-    fft_r4_dif<5, 256, SyncBlock, true>(S.fbuf, S.tw, tid, SyncBlock());
-    for (int m = tid; m < 512; m += 256) {
-        const double2 o = S.fbuf[swz(rev4<5>(m))];
-        S.r[2 * m] = o.x / 1024.0;
-        S.r[2 * m + 1] = -o.y / 1024.0;
+    double* rr = reinterpret_cast<double*>(S.xch[2]);                     // r[0 .. 1023]
+    if (warp == 0) {
+        const double2* Rs = S.xch[0];
+        double2 a[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int k = lane + 32 * j;
+            const double2 xk = Rs[k], xn = Rs[1024 - k];
+            const double2 e = make_double2(0.5 * (xk.x + xn.x), 0.5 * (xk.y - xn.y));
+            const double2 d = make_double2(0.5 * (xk.x - xn.x), 0.5 * (xk.y + xn.y));
+            const double2 w = __ldg(tb.ptw2048 + k);                       // exp(-i th); need exp(+i th) = conj
+            const double2 o = make_double2(d.x * w.x + d.y * w.y, d.y * w.x - d.x * w.y);
+            a[j] = make_double2(e.x - o.y, -(e.y + o.x));                  // conj(e + i o)
+        }
+        team_fft<32>(a, twa, 32, S.xch[1], lane);
+#pragma unroll
+        for (int k2 = 0; k2 < 32; ++k2) {
+            const int m = lane + 32 * k2;                                  // output index: r[2m], r[2m+1]
+            if (m < 512) {
+                const double2 o = a[bitrev<32>(k2)];
+                *reinterpret_cast<double2*>(rr + 2 * m) = make_double2(o.x / 1024.0, -o.y / 1024.0);
+            }
+        }
     }
     __syncthreads();
     // normalise by r[0]; first index of the minimum over lags < sr // 20 (np.argmin; NaN -> first NaN)
-    const double r0 = S.r[0];
+    const double r0 = rr[0];
     const int nl = 800 < L ? 800 : L / 2;
     double best = 1e300;
     int bi = 0x7fffffff;
-    for (int k = tid; k < nl; k += 256) {
-        const float v = (float)(S.r[k] / r0);
+    for (int k = tid; k < nl; k += kAcThreads) {
+        const float v = (float)(rr[k] / r0);
         if ((double)v < best) { best = (double)v; bi = k; }
     }
     // block argmin (value, then smallest index)
@@ -300,14 +336,14 @@ __global__ void __launch_bounds__(256) k_autocorr(const float* __restrict__ y, G
     if (lane == 0) { S.dscratch[warp] = best; S.iscratch[warp] = bi; }
     __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < 8; ++w)
+        for (int w = 1; w < kAcWarps; ++w)
             if (S.dscratch[w] < best || (S.dscratch[w] == best && S.iscratch[w] < bi)) { best = S.dscratch[w]; bi = S.iscratch[w]; }
         if (!(r0 == r0) || r0 == 0.0 || bi == 0x7fffffff) bi = 0;          // all-NaN row: argmin returns 0
         float* sc = scalars + (size_t)b * g.nscal;
-        sc[33] = (float)(S.r[160] / r0);
-        sc[34] = (float)(S.r[320] / r0);
+        sc[33] = (float)(rr[160] / r0);
+        sc[34] = (float)(rr[320] / r0);
         sc[35] = (float)((double)bi / 16000.0);
-        ws.ints[b * 2 + 1] = bi;
+        ints[b * 2 + 1] = bi;
     }
 }
 
@@ -564,7 +600,7 @@ void launch_time_scalars(const float* y, int n, const Geometry& g, const Tables&
         done = true;
     }
     k_time_basic<<<n, 256, sizeof(TimeBasicSmem), st>>>(y, g, scalars, status);
-    k_autocorr<<<n, 256, sizeof(AutocorrSmem), st>>>(y, g, tb, ws, scalars);
+    k_autocorr<<<n, kAcThreads, sizeof(AutocorrSmem), st>>>(y, g, tb, ws.ints, scalars);
     note_launch(2);
 }
 
