@@ -77,8 +77,14 @@ __device__ __forceinline__ float block_min(float v, float* scratch) { return blo
 // ------------------------------------------------------------------------------------ numpy-style z-score terms
 // (x - mean) / (std + 1e-8) with mean / std already rounded to float32 (numpy float32 reductions), float32 ops.
 struct ZTerm {
-    float mean, denom;
-    __device__ __forceinline__ float operator()(float x) const { return __fdiv_rn(__fsub_rn(x, mean), denom); }
+    float mean, denom, rden;
+    // (x - mean) / denom: quotient from the reciprocal plus one residual correction (correctly rounded except in rare
+    // double-rounding cases; a plain IEEE division costs ~10 instructions per output element with its slow path)
+    __device__ __forceinline__ float operator()(float x) const {
+        const float d = __fsub_rn(x, mean);
+        const float q = __fmul_rn(d, rden);
+        return __fmaf_rn(__fmaf_rn(-q, denom, d), rden, q);
+    }
 };
 __device__ __forceinline__ ZTerm make_zterm(double sum, double sumsq, double n) {
     const double mean = sum / n;
@@ -87,6 +93,7 @@ __device__ __forceinline__ ZTerm make_zterm(double sum, double sumsq, double n) 
     ZTerm z;
     z.mean = (float)mean;
     z.denom = __fadd_rn((float)sqrt(var), 1e-8f);
+    z.rden = __frcp_rn(z.denom);
     return z;
 }
 
@@ -128,6 +135,7 @@ __device__ __forceinline__ ZTerm np_row_zterm(const float* a, int n, int lane) {
     ZTerm z;
     z.mean = mean;
     z.denom = __fadd_rn((float)sqrt(q / (double)n), 1e-8f);
+    z.rden = __frcp_rn(z.denom);
     return z;
 }
 

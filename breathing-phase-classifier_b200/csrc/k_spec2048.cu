@@ -502,23 +502,49 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
     if (tid == 0) s_ncand = 0;
     if (warp > 0) {
         for (int f = warp - 1; f < TE; f += 7) {
+            const float4* col4 = reinterpret_cast<const float4*>(mag_b + f * fstride);   // pad words 1025..1027 are 0
             float mx = 0.f;
-            for (int k = lane; k < 1025; k += 32) mx = fmaxf(mx, __ldg(mag_b + f * fstride + k));
+            for (int i = lane; i < kMag2048Stride / 4; i += 32) {
+                const float4 v = __ldg(col4 + i);
+                mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+            }
             mx = warp_max(mx);
             if (lane == 0) colmax[f] = mx;
         }
     } else {
+        // numpy's sequential float32 cumsum, one frame per lane; the loads run 32 elements ahead of the dependent adds
         for (int f = lane; f < TE; f += 32) {
             const float* col = mag_b + f * fstride;
+            const float4* col4 = reinterpret_cast<const float4*>(col);
             float c = 0.f;
-            for (int k = 0; k < 1025; ++k) c = __fadd_rn(c, __ldg(col + k));
+            for (int q = 0; q < 256; q += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(col4 + q + u);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    c = __fadd_rn(c, v[u].x); c = __fadd_rn(c, v[u].y); c = __fadd_rn(c, v[u].z); c = __fadd_rn(c, v[u].w);
+                }
+            }
+            c = __fadd_rn(c, __ldg(col + 1024));
             const float thr = __fmul_rn(0.85f, c);
             float c2 = 0.f;
-            int kk = 1024;
-            for (int k = 0; k < 1025; ++k) {
-                c2 = __fadd_rn(c2, __ldg(col + k));
-                if (!(c2 < thr)) { kk = k; break; }
+            int kk = -1;
+            for (int q = 0; q < 256 && kk < 0; q += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(col4 + q + u);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        c2 = __fadd_rn(c2, e[w]);
+                        if (kk < 0 && !(c2 < thr)) kk = 4 * (q + u) + w;
+                    }
+                }
             }
+            if (kk < 0) kk = 1024;
             roll[f] = (float)kk * 7.8125f;
         }
     }

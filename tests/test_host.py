@@ -203,3 +203,21 @@ def test_shard_range_partitions():
         parts = [shard_range(n, r, w) for r in range(w)]
         assert parts[0][0] == 0 and parts[-1][1] == n
         assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+
+
+def test_register_fft_index_logic_on_host(tmp_path):
+    """csrc/fft_reg.cuh is __host__ __device__ and lane-explicit: the four-step index logic, the compile-time twiddles
+    and the real-input split are run on the CPU for every lane of a team and compared with a long-double DFT."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = tmp_path / "fft_host_test"
+    src = os.path.join(ROOT, "tests", "host", "fft_host_test.cpp")
+    inc = os.path.join(ROOT, "breathing-phase-classifier_b200", "csrc")
+    subprocess.run([nvcc, "-x", "cu", "-std=c++20", "-Wno-deprecated-gpu-targets", "-I", inc, src, "-o", str(exe)],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    errs = [float(x.split()[-1]) for x in out.strip().splitlines()]
+    assert len(errs) == 2 and errs[0] < 1e-10 and errs[1] < 1e-9, out
