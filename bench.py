@@ -195,8 +195,6 @@ def run_ours(args):
         step()
     barrier()
     eng.reset_stats()
-    eng.kernel_times()                                   # drop anything recorded so far
-    eng.set_kernel_timing(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -213,6 +211,18 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - launches0
+    # Per-kernel durations for the roofline leg: the same K steps again with CUDA events around every launch.  The
+    # production step above forks independent kernels onto side streams, where in-stream events of overlapping
+    # kernels would not be attributable, so this instrumented pass runs the launch sequence on one stream.
+    eng.kernel_times()                                   # drop anything recorded so far
+    eng.set_kernel_timing(True)
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record()
+    for _ in range(args.steps):
+        step()
+    i1.record()
+    barrier()
+    serial_ms = i0.elapsed_time(i1) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     eng.set_kernel_timing(False)
     ktimes = eng.kernel_times()
@@ -256,7 +266,7 @@ def run_ours(args):
         step_gbs = value / world * ALG_BYTES_PER_SEG / 1e9
         cores = host_cores()
         cpu = None
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             n_cpu = max(cores, 96)
             v, n, dtc = cpu_port_throughput(n_cpu, cores)
             cpu = {"value": v, "unit": "segments/s", "cores": cores, "kind": "port",
@@ -277,6 +287,9 @@ def run_ours(args):
                          "segments_per_launch": segs_per_launch, "alg_bytes_per_segment": ALG_BYTES_PER_SEG,
                          "peak_source": peak_src,
                          "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak},
+                         "kernel_timing": "instrumented single-stream pass of the same steps, CUDA events around "
+                                          "every launch; the timed step overlaps independent kernels on side streams",
+                         "single_stream_ms_per_step": serial_ms,
                          "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": int(B * L * 2),
@@ -300,6 +313,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="segments per step per GPU")
     ap.add_argument("--distinct", type=int, default=512, help="distinct synthetic segments tiled to the batch")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (used under ncu only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -57,6 +57,11 @@ struct bpc_handle {
     int last_n = 0;
     int64_t launches0 = 0;
     bool timing = false;           // per-kernel CUDA-event timing (bench.py roofline leg)
+    // Fork / join inside a chunk: the STFT-512 branch, the time-domain branch and the per-segment STFT-2048 statistics
+    // run on side streams next to the STFT-2048 -> tuning -> CENS chain on the caller's stream (run_chunk).
+    bool multi_stream = true;      // env BPC_STREAMS=0 turns it off; the per-kernel timing leg always runs serially
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_spec512 = nullptr, ev_time = nullptr, ev_f2048 = nullptr, ev_seg = nullptr;
     struct Ev { int id; cudaEvent_t a, b; };
     std::vector<Ev> evs;
     std::string err;
@@ -315,15 +320,42 @@ int run_chunk(bpc_handle* h, const void* wav, int wav_dtype, int64_t L_in, int n
         cudaEventRecord(e.b, st);
         h->evs.push_back(e);
     };
-    timed(1, [&] { launch_stft512(y, n, g, h->tb, ws, st); });
-    timed(2, [&] { launch_spec512_consumers(n, g, h->tb, ws, feats, scalars, status, true, st); });
-    timed(3, [&] { launch_spec2048(y, n, g, h->tb, ws, feats, scalars, st); });
-    timed(4, [&] { launch_even2048(n, g, h->tb, ws, scalars, status, st); });
-    timed(10, [&] { launch_seg2048(n, g, h->tb, ws, feats, scalars, st); });
-    timed(5, [&] { launch_cens(y, n, g, h->tb, ws, feats, st); });
-    timed(6, [&] { launch_time_scalars(y, n, g, h->tb, ws, scalars, status, st); });
-    timed(7, [&] { launch_hilbert(y, n, g, h->tb, ws, scalars, st); });
-    timed(8, [&] { launch_lpc(y, n, g, h->tb, ws, feats, st); });
+    if (h->timing || !h->multi_stream) {
+        timed(1, [&] { launch_stft512(y, n, g, h->tb, ws, st); });
+        timed(2, [&] { launch_spec512_consumers(n, g, h->tb, ws, feats, scalars, status, true, st); });
+        timed(3, [&] { launch_spec2048(y, n, g, h->tb, ws, feats, scalars, st); });
+        timed(4, [&] { launch_even2048(n, g, h->tb, ws, scalars, status, st); });
+        timed(10, [&] { launch_seg2048(n, g, h->tb, ws, feats, scalars, st); });
+        timed(5, [&] { launch_cens(y, n, g, h->tb, ws, feats, st); });
+        timed(6, [&] { launch_time_scalars(y, n, g, h->tb, ws, scalars, status, st); });
+        timed(7, [&] { launch_hilbert(y, n, g, h->tb, ws, scalars, st); });
+        timed(8, [&] { launch_lpc(y, n, g, h->tb, ws, feats, st); });
+    } else {
+        // Dependencies: stft512 -> consumers (mag512); spec2048 -> {even2048, seg2048} (mag_even, frame_feat, melD);
+        // {consumers (chroma_min), even2048 (tuning-36)} -> cens; the time-domain kernels only read y.  Every branch
+        // joins before the statistics kernel, so consecutive chunks (one shared workspace) stay ordered.
+        cudaStream_t sA = h->side[0], sC = h->side[1], sD = h->side[2];
+        BPC_CUDA(h, cudaEventRecord(h->ev_fork, st));
+        BPC_CUDA(h, cudaStreamWaitEvent(sA, h->ev_fork, 0));
+        BPC_CUDA(h, cudaStreamWaitEvent(sC, h->ev_fork, 0));
+        launch_spec2048(y, n, g, h->tb, ws, feats, scalars, st);
+        BPC_CUDA(h, cudaEventRecord(h->ev_f2048, st));
+        launch_stft512(y, n, g, h->tb, ws, sA);
+        launch_spec512_consumers(n, g, h->tb, ws, feats, scalars, status, true, sA);
+        BPC_CUDA(h, cudaEventRecord(h->ev_spec512, sA));
+        launch_even2048(n, g, h->tb, ws, scalars, status, st);
+        BPC_CUDA(h, cudaStreamWaitEvent(sD, h->ev_f2048, 0));
+        launch_seg2048(n, g, h->tb, ws, feats, scalars, sD);
+        BPC_CUDA(h, cudaEventRecord(h->ev_seg, sD));
+        launch_lpc(y, n, g, h->tb, ws, feats, sC);
+        launch_time_scalars(y, n, g, h->tb, ws, scalars, status, sC);
+        launch_hilbert(y, n, g, h->tb, ws, scalars, sC);
+        BPC_CUDA(h, cudaEventRecord(h->ev_time, sC));
+        BPC_CUDA(h, cudaStreamWaitEvent(st, h->ev_spec512, 0));
+        launch_cens(y, n, g, h->tb, ws, feats, st);
+        BPC_CUDA(h, cudaStreamWaitEvent(st, h->ev_seg, 0));
+        BPC_CUDA(h, cudaStreamWaitEvent(st, h->ev_time, 0));
+    }
     launch_pad_scalars(n, g, scalars, st);
     timed(9, [&] { launch_stats(n, g, feats, scalars, h->stats_acc, st); });
     h->last_n = n;
@@ -421,6 +453,11 @@ int bpc_create(bpc_handle** out, const bpc_params* p, int device, int64_t max_ba
     if (chunk < 1) chunk = 592;
     h->chunk = (int)std::min<int64_t>(chunk, h->max_batch);
     h->launches0 = launches_issued();
+    const char* env_streams = std::getenv("BPC_STREAMS");
+    h->multi_stream = !(env_streams && std::atoi(env_streams) == 0);
+    for (auto& s : h->side) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    for (cudaEvent_t* e : {&h->ev_fork, &h->ev_spec512, &h->ev_time, &h->ev_f2048, &h->ev_seg})
+        cudaEventCreateWithFlags(e, cudaEventDisableTiming);
     if ((rc = build_tables(h)) || (rc = build_workspace(h)) || (rc = reset_stats(h, 0))) {
         g_create_error = h->err;
         bpc_destroy(h);
@@ -439,6 +476,8 @@ void bpc_destroy(bpc_handle* h) {
         if (h->slot[i].done) cudaEventDestroy(h->slot[i].done);
         if (h->slot[i].computed) cudaEventDestroy(h->slot[i].computed);
     }
+    for (auto& s : h->side) if (s) cudaStreamDestroy(s);
+    for (cudaEvent_t e : {h->ev_fork, h->ev_spec512, h->ev_time, h->ev_f2048, h->ev_seg}) if (e) cudaEventDestroy(e);
     for (void* d : h->dev_allocs) cudaFree(d);
     for (void* d : h->host_allocs) cudaFreeHost(d);
     delete h;
