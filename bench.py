@@ -250,6 +250,38 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_steps * B / float(t.item())
 
+    # ---- side measurements (not the headline): BASELINE configs[1] stage and the HBM-bound batch-assembly kernel
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        def timed(fn, reps):
+            fn(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        ms2 = timed(lambda: eng.stage_logmel(wav_f32, want_stft=True), 3)
+        bytes2 = L * 4 + 257 * T * 4 + 3 * 128 * T * 4                       # 225,532 B
+        extras["config2_logmel"] = {"segments_per_s": B / (ms2 * 1e-3), "ms_per_step": ms2, "batch": B,
+                                    "alg_bytes_per_segment": bytes2,
+                                    "achieved_gbs": B * bytes2 / (ms2 * 1e-3) / 1e9,
+                                    "outputs": "log-power STFT [B,257,63] + mel/mel_delta/mel_delta2 [B,3,128,63]"}
+        from bpc_b200.resident import ResidentDS
+        ds = ResidentDS(eng, feats, scal, torch.zeros(B, device=dev))
+        gen = torch.Generator().manual_seed(0)
+        nb = min(B, 2048)
+        idx = torch.randperm(B, generator=gen)[:nb].to(dev)
+        perm = torch.randperm(nb, generator=gen)
+        seg_bytes = 9 * 128 * T * 4
+        for name, kw, streams in (("gather", {}, 2), ("mixup", {"mix": "mixup", "perm": perm}, 3),
+                                  ("cutmix", {"mix": "cutmix", "perm": perm}, 2)):
+            msb = timed(lambda: ds.batch(idx, rng=np.random.RandomState(1), **kw), 10)
+            extras["collate_" + name] = {"batch": nb, "ms": msb, "segments_per_s": nb / (msb * 1e-3),
+                                         "alg_bytes": nb * seg_bytes * streams,
+                                         "achieved_gbs": nb * seg_bytes * streams / (msb * 1e-3) / 1e9}
+        del ds
+
     if rank == 0:
         peaks = {}
         try:
@@ -259,6 +291,14 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
         top = max(ktimes.items(), key=lambda kv: kv[1][0]) if ktimes else ("none", (0.0, 1))
+        traffic = None                                   # DRAM bytes per launch of that kernel from the committed ncu capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"]
+            parts = [tr[k]["dram_bytes_per_launch"] for k in top[0].split("+") if k in tr]
+            if parts:
+                traffic = float(sum(parts)) * min(B, eng.chunk) / tr[top[0].split("+")[0]]["segments_per_launch"]
+        except Exception:
+            pass
         total_k = sum(v[0] for v in ktimes.values()) or 1.0
         segs_per_launch = min(B, eng.chunk)
         avg_ms = top[1][0] / max(1, top[1][1])
@@ -282,7 +322,7 @@ def run_ours(args):
                                     "per step exceed the 126 MB L2",
                        "parallelism": f"dp{world} (batch-sharded, one NCCL all-reduce of channel statistics)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": top[0],
+                         "frac": achieved / peak, "traffic": traffic, "kernel": top[0],
                          "kernel_avg_ms": avg_ms, "kernel_share_of_step": top[1][0] / total_k,
                          "segments_per_launch": segs_per_launch, "alg_bytes_per_segment": ALG_BYTES_PER_SEG,
                          "peak_source": peak_src,
@@ -297,6 +337,7 @@ def run_ours(args):
                     "input": "pinned host PCM16 -> bpc_precompute_host -> pinned host float32"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "extras": extras,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -313,6 +354,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="segments per step per GPU")
     ap.add_argument("--distinct", type=int, default=512, help="distinct synthetic segments tiled to the batch")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-2 / collate side measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (used under ncu only)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -14,6 +14,7 @@ WAV_F32, WAV_PCM16 = 0, 1
 # sorted .npz keys == channel order of the [B, 9, 128, T] tensor (reference src/dataset.py:26)
 CHANNELS = ("chroma", "gammatone", "lpc", "mel", "mel_delta", "mel_delta2", "mfcc", "mod_spec", "tempogram")
 SEG_NONFINITE, SEG_TUNING_EMPTY, SEG_CAND_OVERFLOW, SEG_SILENT = 1, 2, 4, 8
+MIX_NONE, MIX_MIXUP, MIX_CUTMIX = 0, 1, 2
 
 
 class Params(C.Structure):
@@ -55,6 +56,12 @@ _SIGS = {
     "bpc_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "bpc_kernel_times": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "bpc_kernel_name": (C.c_char_p, [C.c_int]),
+    "bpc_collate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                              C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bpc_npz_size": (C.c_int64, [C.c_int, C.c_int]),
+    "bpc_npz_pack": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64]),
+    "bpc_npz_write_batch": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGS)
 

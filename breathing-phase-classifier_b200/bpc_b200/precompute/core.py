@@ -3,7 +3,9 @@ target_dir, dataset_name)` with the same ID -> wav-path mapping, success / failu
 
 Instead of one Python call per file on two threads (core.py:33-34), rows are decoded by a small thread pool, stacked
 into [B, 16000] PCM16 batches and sent through ONE C-ABI call per batch (`bpc_precompute_host`, pinned double
-buffering); `.npz` files are written by the same pool.
+buffering); the `.npz` files are serialised by the C++ writer pool of the library (`bpc_npz_write_batch`).  With
+`packed=True` the same rows go into one packed shard instead (bpc_b200/shards.py), which `PackedDS` reads in place of
+the reference `DS`.
 """
 from __future__ import annotations
 
@@ -14,7 +16,8 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 
 from . import methods as _m
-from .process import load_wav, fit_batch, save_npz
+from .process import load_wav, fit_batch
+from ..shards import ShardWriter, write_npz_batch
 
 SR = 16000                      # core.py:9-17
 DURATION = 1.0
@@ -59,11 +62,12 @@ def _try_load(path):
         return None, str(e)
 
 
-def process_dataset_threaded(df, audio_dir, target_dir, dataset_name, engine=None, batch=BATCH):
+def process_dataset_threaded(df, audio_dir, target_dir, dataset_name, engine=None, batch=BATCH, packed=False):
     items = [(row["ID"], os.path.join(audio_dir, wav_name_for(row["ID"], dataset_name))) for _, row in df.iterrows()]
     eng = engine if engine is not None else _m._get_engine()
     successful = failed = 0
     results = []
+    shard_rows = []                                   # packed mode: rows are collected and written at the end
     with ThreadPoolExecutor(max_workers=IO_THREADS) as pool:
         for lo in range(0, len(items), batch):
             part = items[lo:lo + batch]
@@ -75,17 +79,19 @@ def process_dataset_threaded(df, audio_dir, target_dir, dataset_name, engine=Non
             if not good:
                 continue
             feats, scal, status = eng.precompute_host(fit_batch([w for _, w in good], eng.L))
-
-            def _write(i):
-                fid = good[i][0]
-                try:
-                    if status[i] & 1:
-                        raise ValueError("non-finite samples in input")
-                    save_npz(target_dir, fid, feats[i], scal[i])
-                    return fid, True, None
-                except Exception as e:  # noqa: BLE001
-                    return fid, False, str(e)
-            results.extend(pool.map(_write, range(len(good))))
+            ids = [fid for fid, _ in good]
+            if packed:
+                keep = [i for i in range(len(ids)) if not (status[i] & 1)]
+                results.extend((ids[i], False, "non-finite samples in input") for i in range(len(ids)) if status[i] & 1)
+                shard_rows.append(([ids[i] for i in keep], feats[keep], scal[keep], status[keep]))
+                results.extend((ids[i], True, None) for i in keep)
+            else:
+                results.extend(write_npz_batch(target_dir, ids, feats, scal, status, threads=IO_THREADS))
+    if packed and shard_rows:
+        shard_dir = os.path.join(target_dir, dataset_name)
+        with ShardWriter(shard_dir, sum(len(r[0]) for r in shard_rows), eng.T, eng.nscal) as w:
+            for ids, f, s, st in shard_rows:
+                w.append(ids, f, s, st)
     for fid, ok, err in results:
         if ok:
             successful += 1
@@ -96,12 +102,12 @@ def process_dataset_threaded(df, audio_dir, target_dir, dataset_name, engine=Non
     return results
 
 
-def precompute():
+def precompute(packed=False):
     """core.py:47-56."""
     import pandas as pd
     os.makedirs(PRECOMP_DIR, exist_ok=True)
     train_df = pd.read_csv(TRAIN_CSV_PATH)
     test_df = pd.read_csv(TEST_CSV_PATH)
-    process_dataset_threaded(train_df, TRAIN_AUDIO_DIR, PRECOMP_DIR, "train")
-    process_dataset_threaded(test_df, TEST_AUDIO_DIR, PRECOMP_DIR, "test")
+    process_dataset_threaded(train_df, TRAIN_AUDIO_DIR, PRECOMP_DIR, "train", packed=packed)
+    process_dataset_threaded(test_df, TEST_AUDIO_DIR, PRECOMP_DIR, "test", packed=packed)
     _print_success("완료")

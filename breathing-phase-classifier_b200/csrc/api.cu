@@ -605,6 +605,35 @@ int bpc_modspec(bpc_handle* h, const float* mel_db, int64_t n, float* out, void*
     return BPC_OK;
 }
 
+int bpc_collate(bpc_handle* h, const float* store_feats, const float* store_scalars, int64_t N, const int64_t* idx_a,
+                const int64_t* idx_b, int64_t n, int mode, double lam, int y1, int y2, int x1, int x2,
+                float* out_feats, float* out_scalars, void* stream) {
+    if (!h) return BPC_ERR_ARG;
+    const Geometry& g = h->g;
+    if (!store_feats || !idx_a || !out_feats || N <= 0 || n < 0 || n > 65535 || mode < BPC_MIX_NONE ||
+        mode > BPC_MIX_CUTMIX || (mode != BPC_MIX_NONE && !idx_b) || (out_scalars && !store_scalars)) {
+        h->err = "bpc_collate: bad argument (n <= 65535 per call)";
+        return BPC_ERR_ARG;
+    }
+    if (mode == BPC_MIX_CUTMIX && (y1 < 0 || y2 > kPlaneRows || x1 < 0 || x2 > g.T)) {
+        h->err = "bpc_collate: cut box outside the [128, T] plane";
+        return BPC_ERR_ARG;
+    }
+    if ((reinterpret_cast<uintptr_t>(store_feats) | reinterpret_cast<uintptr_t>(out_feats)) & 15) {
+        h->err = "bpc_collate: feature buffers must be 16-byte aligned";
+        return BPC_ERR_ARG;
+    }
+    BPC_CUDA(h, cudaSetDevice(h->device));
+    // lam stays a double until here, like the Python float of the reference; torch multiplies a float32 tensor by it
+    // after rounding it to float32, and (1 - lam) is formed in double first
+    if (n > 0)
+        launch_collate(store_feats, store_scalars, reinterpret_cast<const long long*>(idx_a),
+                       reinterpret_cast<const long long*>(idx_b), (int)n, mode, (float)lam, (float)(1.0 - lam), y1, y2,
+                       x1, x2, g.T, g.nscal, out_feats, out_scalars, static_cast<cudaStream_t>(stream));
+    BPC_CUDA(h, cudaGetLastError());
+    return BPC_OK;
+}
+
 int bpc_channel_stats(bpc_handle* h, double* stats_host) {
     if (!h || !stats_host) return BPC_ERR_ARG;
     BPC_CUDA(h, cudaSetDevice(h->device));
@@ -726,7 +755,7 @@ int bpc_kernel_times(bpc_handle* h, double* ms_out, int64_t* launches_out, int n
 
 const char* bpc_kernel_name(int id) {
     static const char* names[BPC_NUM_KERNEL_IDS] = {"k_ingest", "k_stft512", "k_spec512_consumers",
-                                                    "k_fft2048+k_feat2048", "k_even2048", "k_cens",
+                                                    "k_frame2048", "k_even2048", "k_cens_dec+k_cens",
                                                     "k_time_basic+k_autocorr", "k_hilbert", "k_lpc", "k_stats",
                                                     "k_seg2048"};
     return (id >= 0 && id < BPC_NUM_KERNEL_IDS) ? names[id] : "";

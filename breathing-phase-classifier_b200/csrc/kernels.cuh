@@ -111,6 +111,10 @@ void launch_stats(int n, const Geometry& g, const float* feats, const float* sca
 void launch_modspec(int n, const Geometry& g, const Tables& tb, const float* mel_db, float* out, cudaStream_t st);
 void launch_pad_scalars(int n, const Geometry& g, float* scalars, cudaStream_t st);
 
+void launch_collate(const float* store_feats, const float* store_scalars, const long long* ia, const long long* ib,
+                    int n, int mode, float lam, float oml, int y1, int y2, int x1, int x2, int T, int nscal,
+                    float* out_feats, float* out_scalars, cudaStream_t st);
+
 void upload_cens_constants(const double* taps127);
 int cens_dec_floats_per_segment();
 int64_t launches_issued();   // process-wide counter bumped by every launcher

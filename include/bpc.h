@@ -134,6 +134,33 @@ int  bpc_set_debug(bpc_handle* h, int on);
  * Writes float32 unless noted; returns the element count or a negative status. */
 int64_t bpc_table_copy(const bpc_params* p, const char* name, int tuning_idx, void* out, int64_t cap_elems);
 
+/* ---- batch assembly on a device-resident feature store -------------------------------------
+ * dataset.py:59-73 collate_fn (stack features / scalars of the drawn items) fused with augmentation.py:5-44 /
+ * train.py:76-89.  store_feats [N, 9, 128, T], store_scalars [N, S] (S = bpc_num_scalars), idx_a / idx_b [n] int64
+ * device arrays of store rows; out_feats [n, 9, 128, T], out_scalars [n, S] (may be NULL).
+ *   BPC_MIX_NONE    out[i] = store[idx_a[i]]
+ *   BPC_MIX_MIXUP   out[i] = lam * store[idx_a[i]] + (1 - lam) * store[idx_b[i]], features and scalars (float32 multiply,
+ *                   multiply, add -- the rounding of the torch expression in train.py:84-85)
+ *   BPC_MIX_CUTMIX  rows [y1, y2) x columns [x1, x2) of every plane come from store[idx_b[i]] (augmentation.py:27-28);
+ *                   scalars are those of idx_a
+ * The random draws (permutation, lam, box) stay with the caller, as in the reference. */
+enum bpc_mix_mode { BPC_MIX_NONE = 0, BPC_MIX_MIXUP = 1, BPC_MIX_CUTMIX = 2 };
+int  bpc_collate(bpc_handle* h, const float* store_feats, const float* store_scalars, int64_t N,
+                 const int64_t* idx_a, const int64_t* idx_b, int64_t n, int mode, double lam,
+                 int y1, int y2, int x1, int x2, float* out_feats, float* out_scalars, void* stream);
+
+/* ---- host-side output writer (no GPU involved) ---------------------------------------------------
+ * process.py:92-103: np.savez(<target_dir>/<file_id>.npz, mel=..., mfcc=..., chroma=..., mel_delta=..., mel_delta2=...,
+ * gammatone=..., lpc=..., mod_spec=..., tempogram=..., scalars=...), an uncompressed zip of ten .npy members.
+ * feats is the [9, 128, T] sorted-key slab of one segment, scalars its [nscal] vector.
+ * bpc_npz_size: bytes of one such archive.  bpc_npz_pack: serialise into `out` (returns bytes written).
+ * bpc_npz_write_batch: write n archives with n_threads host threads; ok[i] = 1 written, -1 skipped because
+ * status[i] has BPC_SEG_NONFINITE (status may be NULL), -2 cannot open, -3 short write. */
+int64_t bpc_npz_size(int T, int nscal);
+int64_t bpc_npz_pack(const float* feats, const float* scalars, int T, int nscal, void* out, int64_t cap);
+int  bpc_npz_write_batch(const char* target_dir, const char* const* file_ids, const float* feats, const float* scalars,
+                         const int32_t* status, int64_t n, int T, int nscal, int n_threads, int32_t* ok);
+
 /* Segments processed per internal chunk (= per kernel launch); env BPC_CHUNK overrides the default at create time. */
 int  bpc_chunk_size(const bpc_handle* h);
 
@@ -141,7 +168,7 @@ int  bpc_chunk_size(const bpc_handle* h);
 int64_t bpc_launch_count(const bpc_handle* h);
 
 /* Per-kernel device times (CUDA events around every launch of the full path) for bench.py's roofline leg.
- * ids: 0 ingest, 1 stft512, 2 spec512 consumers, 3 fft2048+feat2048, 4 even2048, 5 cens, 6 time_basic+autocorr,
+ * ids: 0 ingest, 1 stft512, 2 spec512 consumers, 3 frame2048, 4 even2048, 5 cens_dec+cens, 6 time_basic+autocorr,
  * 7 hilbert, 8 lpc, 9 stats, 10 seg2048.  bpc_kernel_times synchronises, sums the elapsed ms / launch counts since the last call. */
 #define BPC_NUM_KERNEL_IDS 11
 int  bpc_set_kernel_timing(bpc_handle* h, int on);

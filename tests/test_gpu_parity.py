@@ -289,3 +289,77 @@ def test_full_batch_properties(torch_cuda):
     m = f[0, :, 3:6].double()
     assert float(m.mean(dim=(2, 3)).abs().max()) < 1e-4 and float((m.std(dim=(2, 3), unbiased=False) - 1).abs().max()) < 1e-4
     eng.close()
+
+
+def test_resident_collate_cutmix_mixup_bit_exact(torch_cuda):
+    """bpc_collate (gather + CutMix / MixUp on a device-resident store) against the torch expressions of
+    dataset.py:59-73, augmentation.py:5-44 and train.py:80-86 evaluated on the same draws: bit-exact."""
+    torch = torch_cuda
+    import bpc_b200
+    from bpc_b200.resident import ResidentDS, cutmix_data, mixup_data, rand_bbox
+    eng = bpc_b200.Engine(device=0, max_batch=64)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    N = 37
+    store_f = torch.randn((N, 9, 128, 63), generator=g).cuda()
+    store_s = torch.randn((N, 36), generator=g).cuda()
+    labels = (torch.rand(N, generator=g) > 0.5).float().cuda()
+    ds = ResidentDS(eng, store_f, store_s, labels)
+    idx = torch.tensor([5, 0, 36, 36, 12, 7, 1, 30, 2])
+    f, s, y = ds.batch(idx)
+    assert torch.equal(f, store_f[idx.cuda()]) and torch.equal(s, store_s[idx.cuda()]) and torch.equal(y, labels[idx.cuda()])
+    perm = torch.tensor([3, 2, 1, 0, 8, 7, 6, 5, 4])
+    # MixUp (train.py:80-86): features, scalars and labels
+    rs = np.random.RandomState(11)
+    f, s, y = ds.batch(idx, mix="mixup", alpha=0.4, rng=rs, perm=perm)
+    lam = np.random.RandomState(11).beta(0.4, 0.4)
+    bf, bs, bl = store_f[idx.cuda()], store_s[idx.cuda()], labels[idx.cuda()]
+    assert torch.equal(f, lam * bf + (1 - lam) * bf[perm.cuda()])
+    assert torch.equal(s, lam * bs + (1 - lam) * bs[perm.cuda()])
+    assert torch.equal(y, lam * bl + (1 - lam) * bl[perm.cuda()])
+    # CutMix (augmentation.py:5-33): features only
+    for seed in range(6):
+        rs = np.random.RandomState(seed)
+        f, s, y = ds.batch(idx, mix="cutmix", alpha=1.0, rng=rs, perm=perm)
+        rs = np.random.RandomState(seed)
+        lam = rs.beta(1.0, 1.0)
+        x1, y1, x2, y2 = rand_bbox(63, 128, lam, rs)
+        want = bf.clone()
+        want[:, :, y1:y2, x1:x2] = bf[perm.cuda()][:, :, y1:y2, x1:x2]
+        lam2 = 1 - ((x2 - x1) * (y2 - y1) / (63 * 128))
+        assert torch.equal(f, want) and torch.equal(s, bs)
+        assert torch.equal(y, lam2 * bl + (1 - lam2) * bl[perm.cuda()])
+    # drop-in signatures of augmentation.py on an already collated batch
+    m, ym, ind, lam = mixup_data(bf, bl, alpha=1.0, engine=eng, indices=perm.cuda(), rng=np.random.RandomState(3))
+    lam0 = np.random.RandomState(3).beta(1.0, 1.0)
+    assert lam == lam0 and torch.equal(m, lam0 * bf + (1 - lam0) * bf[perm.cuda()]) and torch.equal(ind, perm.cuda())
+    m, ym, ind, lam = cutmix_data(bf, bl, alpha=1.0, engine=eng, indices=perm.cuda(), rng=np.random.RandomState(4))
+    assert m.shape == bf.shape and 0.0 <= lam <= 1.0
+    # epoch iterator: every row exactly once, DataLoader(shuffle=False) order
+    seen = torch.cat([b[0][:, 0, 0, 0] for b in ds.batches(8)])
+    assert torch.equal(seen, store_f[:, 0, 0, 0])
+    eng.close()
+
+
+def test_precompute_to_packed_shard_roundtrip(tmp_path, torch_cuda):
+    """process_dataset_threaded(packed=True) -> PackedDS gives the items the per-file path + reference DS would."""
+    import pandas as pd
+    import scipy.io.wavfile
+    from bpc_b200.precompute import core as CO
+    from bpc_b200.shards import PackedDS
+    from bpc_b200.synth import synth_pcm16
+    audio = tmp_path / "test"; audio.mkdir()
+    ids = [f"steth_t_{i:03d}.wav" for i in range(6)]
+    for i, fid in enumerate(ids):
+        scipy.io.wavfile.write(audio / fid, 16000, synth_pcm16(900 + i))
+    df = pd.DataFrame({"ID": ids})
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    r1 = CO.process_dataset_threaded(df, str(audio), str(tmp_path / "a"), "test")
+    r2 = CO.process_dataset_threaded(df, str(audio), str(tmp_path / "b"), "test", packed=True)
+    assert all(ok for _, ok, _ in r1) and all(ok for _, ok, _ in r2)
+    ds = PackedDS(df, str(tmp_path / "b" / "test"), is_training=False)
+    for i, fid in enumerate(ids):
+        d = np.load(tmp_path / "a" / (fid + ".npz"))
+        f, s, got_id = ds[i]
+        assert got_id == fid and np.array_equal(s.numpy(), d["scalars"])
+        for c, k in enumerate(ds.feature_names):
+            assert np.array_equal(f[c].numpy(), d[k]), k

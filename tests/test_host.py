@@ -221,3 +221,103 @@ def test_register_fft_index_logic_on_host(tmp_path):
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     errs = [float(x.split()[-1]) for x in out.strip().splitlines()]
     assert len(errs) == 2 and errs[0] < 1e-10 and errs[1] < 1e-9, out
+
+
+# ------------------------------------------------------------------------------------- output writer / packed shard
+def _fake_rows(n, T=63, S=36, seed=3):
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal((n, 9, 128, T)).astype(np.float32), rng.standard_normal((n, S)).astype(np.float32))
+
+
+def test_cpp_npz_writer_is_readable_by_numpy_and_zipfile(tmp_path):
+    """bpc_npz_pack / bpc_npz_write_batch against np.savez of the same arrays (process.py:92-103)."""
+    import io
+    import zipfile
+    from bpc_b200 import shards
+    F, S = _fake_rows(5)
+    raw = shards.npz_bytes(F[0], S[0])
+    assert len(raw) == bpc_b200.lib().bpc_npz_size(63, 36)
+    z = zipfile.ZipFile(io.BytesIO(raw))
+    assert z.testzip() is None                                            # CRC-32 of every member checks out
+    assert [i.filename for i in z.infolist()] == [k + ".npy" for k in PR.NPZ_KEYS] + ["scalars.npy"]
+    ref = io.BytesIO()
+    np.savez(ref, **{k: F[0, bpc_b200.CHANNELS.index(k)] for k in PR.NPZ_KEYS}, scalars=S[0])
+    a, b = np.load(io.BytesIO(raw)), np.load(io.BytesIO(ref.getvalue()))
+    assert a.files == b.files
+    for k in a.files:
+        assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape and np.array_equal(a[k], b[k])
+    for m in z.infolist():                                                # same .npy bytes as numpy writes
+        assert z.read(m.filename) == zipfile.ZipFile(io.BytesIO(ref.getvalue())).read(m.filename)
+    status = np.array([0, 0, 1, 0, 2], dtype=np.int32)                    # bit 0 = non-finite input -> failure tuple
+    res = shards.write_npz_batch(str(tmp_path), [f"id_{i}" for i in range(5)], F, S, status, threads=3)
+    assert [ok for _, ok, _ in res] == [True, True, False, True, True] and "non-finite" in res[2][2]
+    assert not (tmp_path / "id_2.npz").exists()
+    d = np.load(tmp_path / "id_4.npz")
+    assert np.array_equal(d["tempogram"], F[4, 8]) and np.array_equal(d["scalars"], S[4])
+    res = shards.write_npz_batch(str(tmp_path / "missing_dir"), ["x"], F[:1], S[:1])
+    assert res[0][1] is False and "open" in res[0][2]
+    odd = shards.npz_bytes(F[1, :, :, :7].copy(), S[1, :5].copy())       # other shapes keep the 64-byte npy alignment
+    d = np.load(io.BytesIO(odd))
+    assert d["mel"].shape == (128, 7) and d["scalars"].shape == (5,) and np.array_equal(d["lpc"], F[1, 2, :, :7])
+
+
+def _reference_ds_items(df, feature_dir, is_training):
+    """What dataset.py:16-57 does for every row (restated: np.load per item, sorted non-excluded keys, stack)."""
+    import torch
+    out = []
+    for _, row in df.iterrows():
+        d = np.load(os.path.join(feature_dir, row["ID"] + ".npz"))
+        names = sorted(k for k in d.keys() if k not in {"scalars", "sr", "hop_length", "n_fft"})
+        f = torch.from_numpy(np.stack([d[k] for k in names], axis=0).astype(np.float32))
+        s = torch.from_numpy(d["scalars"].astype(np.float32))
+        out.append((f, s, torch.tensor(1.0 if row["Target"] == "E" else 0.0) if is_training else row["ID"]))
+    return out
+
+
+@pytest.mark.parametrize("is_training", [True, False])
+def test_packed_shard_ds_matches_per_file_ds(tmp_path, is_training):
+    import pandas as pd
+    import torch
+    from bpc_b200 import shards
+    F, S = _fake_rows(12, seed=5)
+    ids = [f"steth_{i:03d}_{'EI'[i % 2]}_1" for i in range(12)]
+    per_file = tmp_path / "npz"; per_file.mkdir()
+    shards.write_npz_batch(str(per_file), ids, F, S)
+    with shards.ShardWriter(str(tmp_path / "packed"), 12, 63, 36) as w:
+        w.append(ids[:7], F[:7], S[:7])
+        w.append(ids[7:], F[7:], S[7:], np.zeros(5, np.int32))
+    assert shards.is_packed(str(tmp_path / "packed")) and not shards.is_packed(str(per_file))
+    order = [5, 0, 11, 3, 3, 8]                                           # a shuffled subset, as a split would give
+    df = pd.DataFrame({"ID": [ids[i] for i in order], "Target": ["EI"[i % 2] for i in order]})
+    ds = shards.PackedDS(df, str(tmp_path / "packed"), is_training)
+    assert ds.feature_names == list(bpc_b200.CHANNELS) and ds.n_features == 9 and ds.scalar_dim == 36
+    ref = _reference_ds_items(df, str(per_file), is_training)
+    assert len(ds) == len(ref)
+    for i, (f, s, y) in enumerate(ref):
+        g = ds[i]
+        assert torch.equal(g[0], f) and torch.equal(g[1], s)
+        assert (torch.equal(g[2], y) if is_training else g[2] == y)
+    fb, sb, yb = shards.collate_fn([ds[i] for i in range(4)])
+    assert fb.shape == (4, 9, 128, 63) and sb.shape == (4, 36)
+    assert (yb.shape == (4,)) if is_training else (yb == [ids[i] for i in order[:4]])
+    loader = torch.utils.data.DataLoader(ds, batch_size=4, shuffle=False, collate_fn=shards.collate_fn)
+    fb2 = next(iter(loader))[0]
+    assert torch.equal(fb2, fb)
+    with pytest.raises(ValueError):
+        with shards.ShardWriter(str(tmp_path / "short"), 3, 63, 36) as w:
+            w.append(ids[:2], F[:2], S[:2])
+
+
+def test_rand_bbox_matches_reference_expression():
+    """augmentation.py:11-25 restated with the same numpy calls and the same RNG order."""
+    from bpc_b200.resident import rand_bbox
+    for seed in range(20):
+        lam = float(np.random.RandomState(seed).beta(1.0, 1.0))
+        rs = np.random.RandomState(seed + 100)
+        got = rand_bbox(63, 128, lam, rs)
+        rs = np.random.RandomState(seed + 100)
+        cut_rat = np.sqrt(1. - lam); cut_w = np.int32(63 * cut_rat); cut_h = np.int32(128 * cut_rat)
+        cx = rs.randint(63); cy = rs.randint(128)
+        want = (np.clip(cx - cut_w // 2, 0, 63), np.clip(cy - cut_h // 2, 0, 128),
+                np.clip(cx + cut_w // 2, 0, 63), np.clip(cy + cut_h // 2, 0, 128))
+        assert got == tuple(int(v) for v in want)
