@@ -282,6 +282,8 @@ def run_ours(args):
                                          "achieved_gbs": nb * seg_bytes * streams / (msb * 1e-3) / 1e9}
         del ds
 
+    compact = os.environ.get("BPC_COMPACT_D2H", "1") != "0"
+    d2h_rows = 772 if compact else 9 * 128
     if rank == 0:
         peaks = {}
         try:
@@ -333,8 +335,12 @@ def run_ours(args):
                          "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": int(B * L * 2),
-                    "d2h_bytes_per_step": int(B * (9 * 128 * T * 4 + eng.nscal * 4 + 4)), "steps": e2e_steps,
-                    "input": "pinned host PCM16 -> bpc_precompute_host -> pinned host float32"},
+                    "d2h_bytes_per_step": int(B * (d2h_rows * T * 4 + (9 * 4 if compact else 0) + eng.nscal * 4 + 4)),
+                    "steps": e2e_steps,
+                    "input": "pinned host PCM16 -> bpc_precompute_host -> pinned host float32 [B,9,128,63]",
+                    "d2h_note": ("only the 772 data rows of each segment cross PCIe; the 380 constant pad rows "
+                                 "(pad_freq) are re-created on the host by the library's thread pool from one value per "
+                                 "plane" if compact else "whole planes")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "extras": extras,

@@ -8,7 +8,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/bpc.h"
@@ -22,6 +27,8 @@ namespace {
 thread_local std::string g_create_error;
 const double kPi = 3.141592653589793238462643383279502884;
 
+constexpr int kSlots = 3;          // chunks in flight in the host-buffer path: one computing, one in D2H, one in host fill
+
 struct Slot {                      // one in-flight chunk of the host-buffer path
     void* d_wav = nullptr;         // [chunk, L_in_max] raw input (f32 or pcm16)
     float* d_feats = nullptr;
@@ -33,7 +40,72 @@ struct Slot {                      // one in-flight chunk of the host-buffer pat
     int32_t* h_status = nullptr;
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
-    cudaEvent_t computed = nullptr;   // kernels of this chunk finished (the two slots share one workspace)
+    cudaEvent_t computed = nullptr;   // kernels of this chunk finished (the slots share one workspace)
+    cudaEvent_t fill_ready = nullptr; // the pad values of this chunk are in h_fill
+    float* d_fill = nullptr;          // [chunk, 9] pad value of every plane (host path: pad rows are not transferred)
+    float* h_fill = nullptr;
+};
+
+// Rows of each plane that carry data; rows live..127 are one constant per plane (pad_freq, methods.py:39-46):
+// chroma 12 + 12 (process.py:54-57), gammatone N_GAMMATONE, lpc N_LPC, mel x3 full, mfcc 3 * N_MFCC, mod_spec N_MFCC,
+// tempogram full (truncated from 384 rows, process.py:78).
+const int kLiveRows[9] = {24, 64, 12, 128, 128, 128, 120, 40, 128};
+
+struct RowRun { int start, end; };     // [start, end) in the flattened 9 * 128 rows of one segment
+
+std::vector<RowRun> live_runs() {
+    std::vector<RowRun> r;
+    for (int c = 0; c < 9; ++c) {
+        const int s = c * kPlaneRows, e = s + kLiveRows[c];
+        if (!r.empty() && r.back().end == s) r.back().end = e;
+        else r.push_back({s, e});
+    }
+    return r;
+}
+
+// Minimal fork-join pool for the host-side work of the host path (pad-row fill, staging copies).
+class HostPool {
+public:
+    explicit HostPool(int n) {
+        for (int i = 0; i < n; ++i) th_.emplace_back([this, i] { loop(i); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    int size() const { return (int)th_.size() + 1; }
+    // runs fn(part, parts) on every worker and on the caller; returns when all are done
+    void run(const std::function<void(int, int)>& fn) {
+        { std::lock_guard<std::mutex> l(m_); fn_ = &fn; pending_ = (int)th_.size(); ++gen_; }
+        cv_.notify_all();
+        fn((int)th_.size(), size());
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return pending_ == 0; });
+    }
+private:
+    void loop(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int, int)>* fn;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            (*fn)(id, size());
+            { std::lock_guard<std::mutex> l(m_); if (--pending_ == 0) done_.notify_one(); }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int, int)>* fn_ = nullptr;
+    uint64_t gen_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
 };
 
 }  // namespace
@@ -51,9 +123,15 @@ struct bpc_handle {
     double* stats_acc = nullptr;   // [(9 + nscal), 5]
     std::vector<void*> dev_allocs;
     std::vector<void*> host_allocs;
-    Slot slot[2];
+    Slot slot[kSlots];
     bool slots_ready = false;
     size_t slot_wav_bytes = 0;
+    int* live_dev = nullptr;       // kLiveRows on the device
+    HostPool* pool = nullptr;      // host threads of the host path (env BPC_HOST_THREADS, default 8)
+    bool compact_d2h = true;       // host path transfers live rows only (env BPC_COMPACT_D2H=0: whole planes)
+    int host_chunk = 0;            // piece size of the host path (env BPC_HOST_CHUNK, default chunk / 2: the D2H of a piece
+                                   // can only start when its kernels are done, so smaller pieces shorten the ramp)
+    bool taper_tail = true;        // host path halves the last pieces of a call (env BPC_TAPER=0: equal chunks)
     int last_n = 0;
     int64_t launches0 = 0;
     bool timing = false;           // per-kernel CUDA-event timing (bench.py roofline leg)
@@ -369,7 +447,7 @@ int ensure_slots(bpc_handle* h) {
     const size_t C = (size_t)h->chunk;
     h->slot_wav_bytes = C * (size_t)g.L * 4 * 2;                        // room for L_in up to 2 * L of float32
     const size_t feats_bytes = C * 9 * kPlaneRows * (size_t)g.T * 4, scal_bytes = C * (size_t)g.nscal * 4;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
         Slot& s = h->slot[i];
         BPC_CUDA(h, cudaMalloc(&s.d_wav, h->slot_wav_bytes));
         BPC_CUDA(h, cudaMalloc((void**)&s.d_feats, feats_bytes));
@@ -381,12 +459,32 @@ int ensure_slots(bpc_handle* h) {
         BPC_CUDA(h, cudaMallocHost((void**)&s.h_feats, feats_bytes));
         BPC_CUDA(h, cudaMallocHost((void**)&s.h_scalars, scal_bytes));
         BPC_CUDA(h, cudaMallocHost((void**)&s.h_status, C * 4));
+        BPC_CUDA(h, cudaMalloc((void**)&s.d_fill, C * 9 * 4));
+        BPC_CUDA(h, cudaMallocHost((void**)&s.h_fill, C * 9 * 4));
+        h->dev_allocs.push_back(s.d_fill); h->host_allocs.push_back(s.h_fill);
         h->host_allocs.push_back(s.h_wav); h->host_allocs.push_back(s.h_feats);
         h->host_allocs.push_back(s.h_scalars); h->host_allocs.push_back(s.h_status);
         BPC_CUDA(h, cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
         BPC_CUDA(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         BPC_CUDA(h, cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
+        BPC_CUDA(h, cudaEventCreateWithFlags(&s.fill_ready, cudaEventDisableTiming));
     }
+    BPC_CUDA(h, cudaMalloc((void**)&h->live_dev, sizeof(kLiveRows)));
+    h->dev_allocs.push_back(h->live_dev);
+    BPC_CUDA(h, cudaMemcpy(h->live_dev, kLiveRows, sizeof(kLiveRows), cudaMemcpyHostToDevice));
+    const char* env_t = std::getenv("BPC_HOST_THREADS");
+    int nt = env_t ? std::atoi(env_t) : 8;
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && nt > hw) nt = hw;
+    if (nt < 1) nt = 1;
+    h->pool = new HostPool(nt - 1);
+    const char* env_c = std::getenv("BPC_COMPACT_D2H");
+    h->compact_d2h = !(env_c && std::atoi(env_c) == 0);
+    const char* env_hc = std::getenv("BPC_HOST_CHUNK");
+    h->host_chunk = env_hc ? std::atoi(env_hc) : std::max(1, h->chunk / 2);
+    if (h->host_chunk < 1 || h->host_chunk > h->chunk) h->host_chunk = h->chunk;
+    const char* env_tp = std::getenv("BPC_TAPER");
+    h->taper_tail = !(env_tp && std::atoi(env_tp) == 0);
     h->slots_ready = true;
     return BPC_OK;
 }
@@ -471,11 +569,13 @@ void bpc_destroy(bpc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
         if (h->slot[i].st) cudaStreamDestroy(h->slot[i].st);
         if (h->slot[i].done) cudaEventDestroy(h->slot[i].done);
         if (h->slot[i].computed) cudaEventDestroy(h->slot[i].computed);
+        if (h->slot[i].fill_ready) cudaEventDestroy(h->slot[i].fill_ready);
     }
+    delete h->pool;
     for (auto& s : h->side) if (s) cudaStreamDestroy(s);
     for (cudaEvent_t e : {h->ev_fork, h->ev_spec512, h->ev_time, h->ev_f2048, h->ev_seg}) if (e) cudaEventDestroy(e);
     for (void* d : h->dev_allocs) cudaFree(d);
@@ -531,12 +631,44 @@ int bpc_precompute_host(bpc_handle* h, const void* wav, int wav_dtype, int64_t B
     if ((size_t)h->chunk * L_in * esz > h->slot_wav_bytes) { h->err = "L_in too large for the staging buffers"; return BPC_ERR_ARG; }
     const size_t seg_feats = (size_t)9 * kPlaneRows * g.T;
     const bool pin_in = is_pinned(wav), pin_f = is_pinned(feats), pin_s = is_pinned(scalars);
-    const int64_t nchunks = (B + h->chunk - 1) / h->chunk;
-    for (int64_t i = 0; i <= nchunks; ++i) {
+    const std::vector<RowRun> runs = live_runs();
+    double t_wait = 0.0, t_fill = 0.0;
+    const auto t_call = std::chrono::steady_clock::now();
+    // Chunk schedule: full chunks, then the last <= chunk segments in halves (not below 128 segments, about one CTA wave): what is
+    // exposed at the end of a call is the D2H + host fill of the LAST piece only, so it should be small.
+    struct Piece { int64_t off; int n; };
+    std::vector<Piece> sched;
+    {
+        int64_t off = 0;
+        while (off < B) {
+            int64_t rem = B - off, n = std::min<int64_t>(h->host_chunk, rem);
+            if (rem <= h->host_chunk && h->taper_tail && rem >= 256) n = std::max<int64_t>(128, rem / 2);
+            sched.push_back({off, (int)n});
+            off += n;
+        }
+    }
+    const int64_t nchunks = (int64_t)sched.size();
+    const bool compact = h->compact_d2h;
+    const int T = g.T;
+    auto wait_on = [&](cudaEvent_t ev) -> cudaError_t {
+        const auto t_a = std::chrono::steady_clock::now();
+        const cudaError_t e = cudaEventSynchronize(ev);
+        t_wait += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count();
+        return e;
+    };
+    auto host_job = [&](const std::function<void(int, int)>& job) {
+        const auto t_a = std::chrono::steady_clock::now();
+        h->pool->run(job);
+        t_fill += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count();
+    };
+    // Software pipeline over the pieces: iteration i enqueues piece i, writes the pad rows of piece i - 1 (needs only its
+    // nine pad values, which leave the device before the bulk rows, so this overlaps that piece's D2H and piece i's
+    // kernels) and retires piece i - 2 (bulk D2H finished).  The GPU always has the next piece queued.
+    for (int64_t i = 0; i <= nchunks + 1; ++i) {
         if (i < nchunks) {
-            Slot& s = h->slot[i & 1];
-            const int64_t off = i * h->chunk;
-            const int n = (int)std::min<int64_t>(h->chunk, B - off);
+            Slot& s = h->slot[i % kSlots];
+            const int64_t off = sched[i].off;
+            const int n = sched[i].n;
             const char* src = static_cast<const char*>(wav) + (size_t)off * L_in * esz;
             const size_t in_bytes = (size_t)n * L_in * esz;
             if (pin_in) {
@@ -545,30 +677,79 @@ int bpc_precompute_host(bpc_handle* h, const void* wav, int wav_dtype, int64_t B
                 std::memcpy(s.h_wav, src, in_bytes);
                 BPC_CUDA(h, cudaMemcpyAsync(s.d_wav, s.h_wav, in_bytes, cudaMemcpyHostToDevice, s.st));
             }
-            // H2D of this chunk overlaps the previous chunk's kernels; the kernels themselves are serialised because
-            // both slots use the handle's single workspace.
-            if (i >= 1) BPC_CUDA(h, cudaStreamWaitEvent(s.st, h->slot[(i - 1) & 1].computed, 0));
+            // H2D of this piece overlaps the previous piece's kernels; the kernels themselves are serialised because
+            // all slots use the handle's single workspace.
+            if (i >= 1) BPC_CUDA(h, cudaStreamWaitEvent(s.st, h->slot[(i - 1) % kSlots].computed, 0));
             rc = run_chunk(h, s.d_wav, wav_dtype, L_in, n, s.d_feats, s.d_scalars, s.d_status, s.st);
             if (rc) return rc;
+            if (compact) launch_pad_values(s.d_feats, T, n, h->live_dev, s.d_fill, s.st);
             BPC_CUDA(h, cudaEventRecord(s.computed, s.st));
             float* fdst = pin_f ? feats + (size_t)off * seg_feats : s.h_feats;
             float* sdst = pin_s ? scalars + (size_t)off * g.nscal : s.h_scalars;
-            BPC_CUDA(h, cudaMemcpyAsync(fdst, s.d_feats, (size_t)n * seg_feats * 4, cudaMemcpyDeviceToHost, s.st));
+            if (compact) {
+                // PCIe carries only the rows that hold data (772 of the 1152 rows of a segment); the constant pad rows
+                // are re-created on the host from one value per plane.
+                BPC_CUDA(h, cudaMemcpyAsync(s.h_fill, s.d_fill, (size_t)n * 9 * 4, cudaMemcpyDeviceToHost, s.st));
+                BPC_CUDA(h, cudaEventRecord(s.fill_ready, s.st));
+                const size_t pitch = seg_feats * 4;
+                for (const RowRun& r : runs)
+                    BPC_CUDA(h, cudaMemcpy2DAsync(fdst + (size_t)r.start * T, pitch, s.d_feats + (size_t)r.start * T,
+                                                  pitch, (size_t)(r.end - r.start) * T * 4, (size_t)n,
+                                                  cudaMemcpyDeviceToHost, s.st));
+            } else {
+                BPC_CUDA(h, cudaMemcpyAsync(fdst, s.d_feats, (size_t)n * seg_feats * 4, cudaMemcpyDeviceToHost, s.st));
+            }
             BPC_CUDA(h, cudaMemcpyAsync(sdst, s.d_scalars, (size_t)n * g.nscal * 4, cudaMemcpyDeviceToHost, s.st));
             BPC_CUDA(h, cudaMemcpyAsync(s.h_status, s.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, s.st));
             BPC_CUDA(h, cudaEventRecord(s.done, s.st));
         }
-        if (i >= 1) {
+        if (compact && i >= 1 && i - 1 < nchunks) {                   // pad rows of piece i - 1 (disjoint from the D2H rows)
             const int64_t j = i - 1;
-            Slot& s = h->slot[j & 1];
-            const int64_t off = j * h->chunk;
-            const int n = (int)std::min<int64_t>(h->chunk, B - off);
-            BPC_CUDA(h, cudaEventSynchronize(s.done));
-            if (!pin_f) std::memcpy(feats + (size_t)off * seg_feats, s.h_feats, (size_t)n * seg_feats * 4);
+            Slot& s = h->slot[j % kSlots];
+            const int n = sched[j].n;
+            float* user = feats + (size_t)sched[j].off * seg_feats;
+            BPC_CUDA(h, wait_on(s.fill_ready));
+            host_job([&](int part, int parts) {
+                for (int b = part; b < n; b += parts) {
+                    float* dst = user + (size_t)b * seg_feats;
+                    for (int c = 0; c < 9; ++c)
+                        if (kLiveRows[c] < kPlaneRows)
+                            std::fill(dst + ((size_t)c * kPlaneRows + kLiveRows[c]) * T,
+                                      dst + (size_t)(c + 1) * kPlaneRows * T, s.h_fill[(size_t)b * 9 + c]);
+                }
+            });
+        }
+        if (i >= 2) {                                                  // retire piece i - 2
+            const int64_t j = i - 2;
+            Slot& s = h->slot[j % kSlots];
+            const int64_t off = sched[j].off;
+            const int n = sched[j].n;
+            BPC_CUDA(h, wait_on(s.done));
+            if (!pin_f) {                                              // pageable output: staging -> user buffer
+                float* user = feats + (size_t)off * seg_feats;
+                host_job([&](int part, int parts) {
+                    for (int b = part; b < n; b += parts) {
+                        float* dst = user + (size_t)b * seg_feats;
+                        const float* src = s.h_feats + (size_t)b * seg_feats;
+                        if (compact) {
+                            for (const RowRun& r : runs)
+                                std::memcpy(dst + (size_t)r.start * T, src + (size_t)r.start * T,
+                                            (size_t)(r.end - r.start) * T * 4);
+                        } else {
+                            std::memcpy(dst, src, seg_feats * 4);
+                        }
+                    }
+                });
+            }
             if (!pin_s) std::memcpy(scalars + (size_t)off * g.nscal, s.h_scalars, (size_t)n * g.nscal * 4);
             if (status) std::memcpy(status + off, s.h_status, (size_t)n * 4);
         }
     }
+    if (std::getenv("BPC_HOST_TRACE"))
+        std::fprintf(stderr, "[bpc host] B=%lld chunks=%lld total %.2f ms, waiting on GPU/PCIe %.2f ms, host copy/fill %.2f ms (%d threads)\n",
+                     (long long)B, (long long)nchunks,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(), t_wait,
+                     t_fill, h->pool->size());
     return BPC_OK;
 }
 

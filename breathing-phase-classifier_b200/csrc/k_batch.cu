@@ -80,4 +80,20 @@ void launch_collate(const float* store_feats, const float* store_scalars, const 
     }
 }
 
+// Pad values of a chunk: fill[b * 9 + c] = first element of the first pad row of plane c (pad_freq fills rows
+// live[c]..127 with one constant per plane, methods.py:39-46); planes without pad rows get 0.  Used by the host path,
+// which transfers only the live rows over PCIe and re-creates the constant rows on the host.
+__global__ void k_pad_values(const float* __restrict__ feats, int T, int n, const int* __restrict__ live,
+                             float* __restrict__ fill) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 9) return;
+    const int b = i / 9, c = i - b * 9, lv = live[c];
+    fill[i] = lv < kPlaneRows ? feats[((size_t)b * 9 + c) * kPlaneRows * T + (size_t)lv * T] : 0.f;
+}
+
+void launch_pad_values(const float* feats, int T, int n, const int* live_dev, float* fill, cudaStream_t st) {
+    k_pad_values<<<(n * 9 + 255) / 256, 256, 0, st>>>(feats, T, n, live_dev, fill);
+    note_launch();
+}
+
 }  // namespace bpc

@@ -115,6 +115,8 @@ void launch_collate(const float* store_feats, const float* store_scalars, const 
                     int n, int mode, float lam, float oml, int y1, int y2, int x1, int x2, int T, int nscal,
                     float* out_feats, float* out_scalars, cudaStream_t st);
 
+void launch_pad_values(const float* feats, int T, int n, const int* live_dev, float* fill, cudaStream_t st);
+
 void upload_cens_constants(const double* taps127);
 int cens_dec_floats_per_segment();
 int64_t launches_issued();   // process-wide counter bumped by every launcher

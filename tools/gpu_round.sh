@@ -5,7 +5,7 @@ tag=$1
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$tag.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_$tag.log
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"
-BPC_STREAMS=0 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${tag}_serial.json 2> gpurun_out/bench_${tag}_serial.err
+BPC_STREAMS=0 BPC_COMPACT_D2H=0 python bench.py --steps 5 --warmup 3 --no-extras --no-cpu > gpurun_out/bench_${tag}_serial.json 2> gpurun_out/bench_${tag}_serial.err
 python - <<PY
 import json
 for f in ("gpurun_out/bench_$tag.json", "gpurun_out/bench_${tag}_serial.json"):
