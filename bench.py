@@ -281,6 +281,29 @@ def run_ours(args):
                                          "alg_bytes": nb * seg_bytes * streams,
                                          "achieved_gbs": nb * seg_bytes * streams / (msb * 1e-3) / 1e9}
         del ds
+        # BASELINE configs[4]: precompute of 1024 segments feeding CNN8 / VGG forward (eval mode, random-init weights of
+        # the reference architectures rebuilt in tools/consumer_models.py; fp32 and bf16-autocast forwards)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import consumer_models as CM
+            nb5 = min(B, 1024)
+            w5 = wav_f32[:nb5].contiguous()
+            f5, s5, _ = eng.precompute(w5)
+            ms_pre = timed(lambda: eng.precompute(w5, feats[:nb5], scal[:nb5], status[:nb5]), 5)
+            c5 = {"batch": nb5, "precompute_ms": ms_pre, "precompute_segments_per_s": nb5 / (ms_pre * 1e-3)}
+            for name in ("CNN8", "VGG"):
+                net = getattr(CM, name)(9, eng.nscal).to(dev).eval()
+                with torch.no_grad():
+                    ms_f = timed(lambda: net(f5, s5), 5)
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        ms_a = timed(lambda: net(f5, s5), 5)
+                    ok = bool(torch.isfinite(net(f5, s5)).all())
+                c5[name] = {"params": CM.n_params(net), "forward_ms_fp32": ms_f, "forward_ms_bf16_autocast": ms_a,
+                            "finite": ok}
+                del net
+            extras["config5_precompute_plus_forward"] = c5
+        except Exception as e:                           # the side measurement must not take the bench line down
+            extras["config5_precompute_plus_forward"] = {"error": repr(e)}
 
     compact = os.environ.get("BPC_COMPACT_D2H", "1") != "0"
     d2h_rows = 772 if compact else 9 * 128

@@ -5,6 +5,8 @@ pad helpers are pure data movement and stay on the host exactly as in the refere
 """
 from __future__ import annotations
 
+import threading
+
 import numpy as np
 
 SR = 16000                      # methods.py:10-22
@@ -22,14 +24,19 @@ N_GAMMATONE = 64
 N_LPC = 12
 
 _engine = None
+# The reference calls process_and_save_npz from N_WORKERS threads at once (core.py:33-34) and the function is
+# re-entrant.  Calls on one bpc_handle must be serialised (include/bpc.h), so the per-file mirrors share one engine
+# behind this lock; batched callers (core.process_dataset_threaded) own their engine and never take it.
+ENGINE_LOCK = threading.RLock()
 
 
 def _get_engine():
     global _engine
-    if _engine is None:
-        from ..engine import Engine
-        _engine = Engine(device=0, max_batch=64, debug=True)
-    return _engine
+    with ENGINE_LOCK:
+        if _engine is None:
+            from ..engine import Engine
+            _engine = Engine(device=0, max_batch=64, debug=True)
+        return _engine
 
 
 def pad_or_truncate(waveform: np.ndarray, target_len: int) -> np.ndarray:
@@ -68,7 +75,8 @@ def extract_enhanced_scalar_features(y: np.ndarray, sr: int = SR) -> np.ndarray:
     """methods.py:48-114 -> float32[36] (the code emits 36 values although README / model defaults say 39)."""
     if sr != SR:
         raise ValueError("this build implements the reference sample rate (16000) only")
-    _, scal, _ = _get_engine().precompute_host(_one(y))
+    with ENGINE_LOCK:
+        _, scal, _ = _get_engine().precompute_host(_one(y))
     return scal[0, :36].copy()
 
 
@@ -76,20 +84,23 @@ def extract_lpc_features(y: np.ndarray, order: int = N_LPC) -> np.ndarray:
     """methods.py:116-134 -> float32 [order, n_frames] (Burg, 25 ms Hamming frames every 10 ms)."""
     if order != N_LPC:
         raise ValueError("this build implements order 12 only")
-    eng = _get_engine()
-    eng.precompute_host(_one(y))
-    return eng.debug("lpc_raw", 1)[0]
+    with ENGINE_LOCK:
+        eng = _get_engine()
+        eng.precompute_host(_one(y))
+        return eng.debug("lpc_raw", 1)[0]
 
 
 def extract_gammatone_features(y: np.ndarray, sr: int = SR, n_filters: int = N_GAMMATONE) -> np.ndarray:
     """methods.py:136-140 -> float32 [64, T] = log1p(mel64 @ |STFT512|)."""
     if sr != SR or n_filters != N_GAMMATONE:
         raise ValueError("this build implements sr 16000 / 64 filters only")
-    eng = _get_engine()
-    eng.precompute_host(_one(y))
-    return eng.debug("gammatone_raw", 1)[0]
+    with ENGINE_LOCK:
+        eng = _get_engine()
+        eng.precompute_host(_one(y))
+        return eng.debug("gammatone_raw", 1)[0]
 
 
 def extract_spectral_modulation_features(mel_db: np.ndarray) -> np.ndarray:
     """methods.py:142-143 -> float32 [40, T]: ortho DCT-II over mel (first 40), then over time."""
-    return _get_engine().modspec(np.asarray(mel_db, dtype=np.float32)[None])[0]
+    with ENGINE_LOCK:
+        return _get_engine().modspec(np.asarray(mel_db, dtype=np.float32)[None])[0]

@@ -60,7 +60,8 @@ def process_and_save_npz(args):
     try:
         y = load_wav(wav_path)
         wav = fit_batch([y])
-        feats, scal, status = _m._get_engine().precompute_host(wav)
+        with _m.ENGINE_LOCK:                      # the reference runs this function on two threads (core.py:33-34)
+            feats, scal, status = _m._get_engine().precompute_host(wav)
         if status[0] & 1:
             raise ValueError("non-finite samples in input")
         save_npz(target_dir, file_id, feats[0], scal[0])

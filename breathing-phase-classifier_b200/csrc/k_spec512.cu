@@ -123,18 +123,19 @@ __device__ void power_to_db_inplace(float* P, int n, bool ref_is_max, float* fsc
 
 // librosa.feature.delta(width=9, order, mode='interp') == scipy savgol_filter(9, polyorder=order, deriv=order):
 // interior correlation; the 4 edge samples on each side take the (constant) order-th derivative of the edge fit,
-// i.e. the interior value at t=4 / t=T-5.  float64 accumulate, float32 store.
+// i.e. the interior value at t=4 / t=T-5.  float64 accumulate (scaled by the reciprocal of the normaliser: the
+// difference to a float64 division disappears in the float32 rounding), float32 store.
 __device__ __forceinline__ float delta_at(const float* row, int t, int T, int order) {
     const int tc = t < 4 ? 4 : (t > T - 5 ? T - 5 : t);
     const float* r = row + tc;
     double acc;
     if (order == 1) {
         acc = (4.0 * ((double)r[4] - (double)r[-4]) + 3.0 * ((double)r[3] - (double)r[-3]) +
-               2.0 * ((double)r[2] - (double)r[-2]) + ((double)r[1] - (double)r[-1])) / 60.0;
+               2.0 * ((double)r[2] - (double)r[-2]) + ((double)r[1] - (double)r[-1])) * (1.0 / 60.0);
     } else {
         acc = (28.0 * ((double)r[4] + (double)r[-4]) + 7.0 * ((double)r[3] + (double)r[-3]) -
-               8.0 * ((double)r[2] + (double)r[-2]) - 17.0 * ((double)r[1] + (double)r[-1]) - 20.0 * (double)r[0]) /
-              462.0;
+               8.0 * ((double)r[2] + (double)r[-2]) - 17.0 * ((double)r[1] + (double)r[-1]) - 20.0 * (double)r[0]) *
+              (1.0 / 462.0);
     }
     return (float)acc;
 }
@@ -145,22 +146,31 @@ __device__ __forceinline__ float delta_at(const float* row, int t, int T, int or
 // of the warp's rows.
 template <int ROWS>
 __device__ void apply_bank(const BankDev& bank, const float* __restrict__ mag_b, int T, bool power, float* out) {
-    const int total = ROWS * T;
+    // every thread owns one mel row of TWO frames (t, t + half): the tap weight is loaded once for both and the two
+    // accumulation chains are independent
+    const int half = (T + 1) >> 1;
+    const int total = ROWS * half;
     const int iters = (total + blockDim.x - 1) / blockDim.x;
     for (int it = 0; it < iters; ++it) {
         const int idx = it * blockDim.x + threadIdx.x;
         const bool live = idx < total;
-        const int m = idx & (ROWS - 1), t = live ? idx / ROWS : 0;
+        const int m = idx & (ROWS - 1), t0 = live ? idx / ROWS : 0, t1 = t0 + half;
+        const bool live1 = live && t1 < T;
         const int s = __ldg(bank.start + m), c = live ? __ldg(bank.count + m) : 0;
         const int cmax = __reduce_max_sync(0xffffffffu, c);
-        const float* src = mag_b + (size_t)t * kMagStride;
+        const float* src0 = mag_b + (size_t)t0 * kMagStride;
+        const float* src1 = mag_b + (size_t)(live1 ? t1 : t0) * kMagStride;
         const float* wt = bank.wt + m;
-        float acc = 0.f;
+        float acc0 = 0.f, acc1 = 0.f;
         for (int j = 0; j < cmax; ++j) {
-            const float v = __ldg(src + min(s + j, 256));
-            acc = fmaf(__ldg(wt + j * ROWS), power ? __fmul_rn(v, v) : v, acc);
+            const int k = min(s + j, 256);
+            const float w = __ldg(wt + j * ROWS);
+            const float v0 = __ldg(src0 + k), v1 = __ldg(src1 + k);
+            acc0 = fmaf(w, power ? __fmul_rn(v0, v0) : v0, acc0);
+            acc1 = fmaf(w, power ? __fmul_rn(v1, v1) : v1, acc1);
         }
-        if (live) out[m * T + t] = acc;
+        if (live) out[m * T + t0] = acc0;
+        if (live1) out[m * T + t1] = acc1;
     }
     __syncthreads();
 }

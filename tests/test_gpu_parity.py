@@ -363,3 +363,27 @@ def test_precompute_to_packed_shard_roundtrip(tmp_path, torch_cuda):
         assert got_id == fid and np.array_equal(s.numpy(), d["scalars"])
         for c, k in enumerate(ds.feature_names):
             assert np.array_equal(f[c].numpy(), d[k]), k
+
+
+def test_process_and_save_npz_from_two_threads(tmp_path, torch_cuda):
+    """core.py:33-34: the reference maps process_and_save_npz over a 2-worker thread pool; the mirror must give the
+    same files as sequential calls when used that way."""
+    import scipy.io.wavfile
+    from concurrent.futures import ThreadPoolExecutor
+    from bpc_b200.precompute import process as PR
+    from bpc_b200.synth import synth_pcm16
+    audio = tmp_path / "wav"; a = tmp_path / "seq"; b = tmp_path / "par"
+    for d in (audio, a, b):
+        d.mkdir()
+    ids = [f"seg_{i}" for i in range(8)]
+    for i, fid in enumerate(ids):
+        scipy.io.wavfile.write(audio / (fid + ".wav"), 16000, synth_pcm16(950 + i))
+    seq = [PR.process_and_save_npz((fid, str(audio / (fid + ".wav")), str(a))) for fid in ids]
+    with ThreadPoolExecutor(max_workers=2) as ex:
+        par = list(ex.map(PR.process_and_save_npz, [(fid, str(audio / (fid + ".wav")), str(b)) for fid in ids]))
+    assert seq == par == [(fid, True, None) for fid in ids]
+    for fid in ids:
+        x, y = np.load(a / (fid + ".npz")), np.load(b / (fid + ".npz"))
+        assert all(np.array_equal(x[k], y[k]) for k in x.files)
+    fid, ok, err = PR.process_and_save_npz(("nope", str(audio / "nope.wav"), str(b)))     # process.py:107-108
+    assert fid == "nope" and ok is False and isinstance(err, str) and err
