@@ -6,6 +6,7 @@
 //   role 3  chroma_stft rows + low-frequency ratio      (process.py:51-52; methods.py:84-88)
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include "kernels.cuh"
 #include "fft.cuh"
 #include "fft_reg.cuh"
@@ -177,8 +178,9 @@ __device__ void apply_bank(const BankDev& bank, const float* __restrict__ mag_b,
 
 // C[k*T + t] = sum_n D[k*128 + n] * P[n*T + t], k < 40 (ortho DCT-II along the mel axis, first 40 rows).
 // 256 threads = 8 row groups (5 rows, warp-uniform: D is read as broadcast float4) x 32 column pairs; float32 partial
-// sums over 32 n combined in float64.  Ds: the [40, 128] matrix staged in shared memory.
-__device__ void dct_mel40(const float* Ds, const float* P, int T, float* C) {
+// sums over 32 n combined in float64.  Dg: the [40, 128] matrix in global memory (every load is warp-uniform, i.e. one
+// broadcast sector out of L1; staging it in shared memory cost 20 KB per CTA and one resident CTA per SM).
+__device__ void dct_mel40(const float* __restrict__ Dg, const float* P, int T, float* C) {
     const int kb = threadIdx.x >> 5, tp = threadIdx.x & 31;
     const int t0 = 2 * tp, t1 = min(2 * tp + 1, T - 1);
     if (kb < 8 && t0 < T) {
@@ -197,7 +199,7 @@ __device__ void dct_mel40(const float* Ds, const float* P, int T, float* C) {
                 for (int q = 0; q < 4; ++q) { p0[q] = P[(n + q) * T + t0]; p1[q] = P[(n + q) * T + t1]; }
 #pragma unroll
                 for (int i = 0; i < 5; ++i) {
-                    const float4 d = *reinterpret_cast<const float4*>(Ds + (5 * kb + i) * 128 + n);
+                    const float4 d = __ldg(reinterpret_cast<const float4*>(Dg + (5 * kb + i) * 128 + n));
                     part[i][0] = fmaf(d.x, p0[0], part[i][0]); part[i][1] = fmaf(d.x, p1[0], part[i][1]);
                     part[i][0] = fmaf(d.y, p0[1], part[i][0]); part[i][1] = fmaf(d.y, p1[1], part[i][1]);
                     part[i][0] = fmaf(d.z, p0[2], part[i][0]); part[i][1] = fmaf(d.z, p1[2], part[i][1]);
@@ -279,14 +281,10 @@ __device__ void role_mel(int b, const Geometry g, const Tables& tb, const Worksp
     float* P = smem;                 // [128*T] mel power -> mel_db
     float* C1 = P + NP;              // [40*T]
     float* C2 = C1 + 40 * T;         // [40*T]
-    float* Ds = C2 + 40 * T;         // [40*128] DCT matrix (mel axis)
-    float* DTs = Ds + 40 * 128;      // [T*T] DCT matrix (time axis), transposed
+    float* DTs = C2 + 40 * T;        // [T*T] DCT matrix (time axis), transposed
     const float* mag_b = ws.mag512 + (size_t)b * T * kMagStride;
 
-    if (!mel3) {
-        stage_matrix(Ds, tb.dct_mel, 40 * 128);
-        stage_matrix(DTs, tb.dct_time, T * T);
-    }
+    if (!mel3) stage_matrix(DTs, tb.dct_time, T * T);
     apply_bank<128>(tb.mel_a, mag_b, T, true, P);
     power_to_db_inplace(P, NP, true, fscratch);                      // process.py:33
     if (ws.dbg_mel_db) {
@@ -327,7 +325,7 @@ __device__ void role_mel(int b, const Geometry g, const Tables& tb, const Worksp
     if (mel3) return;
 
     // mod_spec (methods.py:142-143): DCT-II ortho over mel (keep 40), then over time
-    dct_mel40(Ds, P, T, C1);
+    dct_mel40(tb.dct_mel, P, T, C1);
     dct_time40(DTs, C1, T, C2);
     if (ws.dbg_mod) {
         float* d = ws.dbg_mod + (size_t)b * 40 * T;
@@ -347,12 +345,10 @@ __device__ void role_mfcc(int b, const Geometry g, const Tables& tb, const Works
     float* P = smem;                 // [128*T]
     float* MF = P + NP;              // [40*T]
     float* OUT = MF + 40 * T;        // [120*T]
-    float* Ds = OUT + 120 * T;       // [40*128]
     const float* mag_b = ws.mag512 + (size_t)b * T * kMagStride;
-    stage_matrix(Ds, tb.dct_mel, 40 * 128);
     apply_bank<128>(tb.mel_b, mag_b, T, true, P);
     power_to_db_inplace(P, NP, false, fscratch);                      // librosa.feature.mfcc: power_to_db(ref=1.0)
-    dct_mel40(Ds, P, T, MF);
+    dct_mel40(tb.dct_mel, P, T, MF);
     if (ws.dbg_mfcc) {
         float* d = ws.dbg_mfcc + (size_t)b * 120 * T;
         for (int i = threadIdx.x; i < 120 * T; i += blockDim.x) {
@@ -510,8 +506,11 @@ __device__ void role_chroma_stft(int b, const Geometry g, const Tables& tb, cons
 }
 
 // ----------------------------------------------------------------------------------------------- the kernel
-constexpr int kConsumerSmemFloats = kPlaneRows * kMaxFrames + 40 * kMaxFrames + 120 * kMaxFrames + 40 * 128 + 64;
-static_assert(kPlaneRows * kMaxFrames + 80 * kMaxFrames + 40 * 128 + kMaxFrames * kMaxFrames <= kConsumerSmemFloats, "role_mel layout");
+// roles 0 / 1 (three CTAs per SM) and roles 2 / 3 (four per SM) are launched separately with their own footprints
+constexpr int kConsumerSmemFloats = kPlaneRows * kMaxFrames + 40 * kMaxFrames + 120 * kMaxFrames;             // role_mfcc
+static_assert(kPlaneRows * kMaxFrames + 80 * kMaxFrames + kMaxFrames * kMaxFrames <= kConsumerSmemFloats, "role_mel layout");
+constexpr int kLightSmemFloats = 3 * kMaxCand + 64 + 12 * kMaxFrames + 100 + 28;                             // role_chroma_stft
+static_assert(64 * kMaxFrames <= kLightSmemFloats, "role_gammatone layout");
 
 __global__ void __launch_bounds__(256) k_spec512_consumers(Geometry g, Tables tb, Workspace ws, float* feats,
                                                            float* scalars, int32_t* status, float* mel3,
@@ -541,10 +540,19 @@ static void set_consumer_smem() {
 void launch_spec512_consumers(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
                               float* scalars, int32_t* status, bool with_chroma, cudaStream_t st) {
     set_consumer_smem();
-    dim3 grid(n, with_chroma ? 4 : 3);
-    k_spec512_consumers<<<grid, 256, kConsumerSmemFloats * sizeof(float), st>>>(g, tb, ws, feats, scalars, status,
-                                                                                 nullptr, 0);
-    note_launch();
+    static const char* only = std::getenv("BPC_ONLY_ROLE");      // profiling aid: time one role (outputs incomplete)
+    if (only) {
+        const int r = std::atoi(only);
+        k_spec512_consumers<<<dim3(n, 1), 256, (r < 2 ? kConsumerSmemFloats : kLightSmemFloats) * sizeof(float), st>>>(
+            g, tb, ws, feats, scalars, status, nullptr, r);
+        note_launch();
+        return;
+    }
+    k_spec512_consumers<<<dim3(n, 2), 256, kConsumerSmemFloats * sizeof(float), st>>>(g, tb, ws, feats, scalars, status,
+                                                                                       nullptr, 0);
+    k_spec512_consumers<<<dim3(n, with_chroma ? 2 : 1), 256, kLightSmemFloats * sizeof(float), st>>>(
+        g, tb, ws, feats, scalars, status, nullptr, 2);
+    note_launch(2);
 }
 
 void launch_logmel_only(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* mel3, cudaStream_t st) {
@@ -591,13 +599,11 @@ __global__ void __launch_bounds__(256) k_modspec(Geometry g, Tables tb, const fl
     float* P = smem;
     float* C1 = P + NP;
     float* C2 = C1 + 40 * T;
-    float* Ds = C2 + 40 * T;
-    float* DTs = Ds + 40 * 128;
-    stage_matrix(Ds, tb.dct_mel, 40 * 128);
+    float* DTs = C2 + 40 * T;
     stage_matrix(DTs, tb.dct_time, T * T);
     for (int i = threadIdx.x; i < NP; i += blockDim.x) P[i] = mel_db[(size_t)b * NP + i];
     __syncthreads();
-    dct_mel40(Ds, P, T, C1);
+    dct_mel40(tb.dct_mel, P, T, C1);
     dct_time40(DTs, C1, T, C2);
     for (int i = threadIdx.x; i < 40 * T; i += blockDim.x) out[(size_t)b * 40 * T + i] = C2[i];
 }
