@@ -153,9 +153,13 @@ __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y,
         const unsigned p0 = S.prefix[0], p1 = S.prefix[1], p2 = S.prefix[2], p3 = S.prefix[3];
         const unsigned hi_mask = pass == 0 ? 0u : (pass == 1 ? 0xffe00000u : 0xfffffc00u);
         if (pass == 0) {
-            // all four targets still share the empty prefix: one histogram serves them (4x fewer shared atomics)
+            // all four targets still share the empty prefix: one histogram serves them (4x fewer shared atomics).  It
+            // is kept as four partial histograms (one per warp pair): |y| of a breath sits in a handful of exponent
+            // bins, and same-address shared atomics serialise
             for (int i = tid; i < L; i += 256)
-                atomicAdd(&S.hist[0][__float_as_uint(fabsf(S.y[i])) >> 21], 1u);
+                atomicAdd(&S.hist[warp & 3][__float_as_uint(fabsf(S.y[i])) >> 21], 1u);
+            __syncthreads();
+            for (int i = tid; i < 2048; i += 256) S.hist[0][i] += S.hist[1][i] + S.hist[2][i] + S.hist[3][i];
         } else {
             for (int i = tid; i < L; i += 256) {
                 const unsigned key = __float_as_uint(fabsf(S.y[i]));
@@ -171,8 +175,10 @@ __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y,
             // find the digit whose cumulative count first exceeds rank; 64 bins per lane
             const unsigned* h = S.hist[pass == 0 ? 0 : warp];
             const int nb = (int)masks[pass] + 1, per = nb / 32;
+            // each lane sums its `per` consecutive bins starting at a lane-dependent rotation: lane * per alone is a
+            // multiple of 32 words, i.e. all 32 lanes on one bank (this loop was 80 % of the kernel's shared wavefronts)
             unsigned local = 0;
-            for (int i = 0; i < per; ++i) local += h[lane * per + i];
+            for (int i = 0; i < per; ++i) local += h[lane * per + ((i + lane) & (per - 1))];
             unsigned incl = local;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {

@@ -47,7 +47,7 @@ __device__ inline int tuning_from_candidates(const float* cand_mag, const float*
             const unsigned* hc = cnt + 256 * w;
             unsigned local = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) local += hc[ln * 8 + i];
+            for (int i = 0; i < 8; ++i) local += hc[ln * 8 + ((i + (ln >> 2)) & 7)];   // rotation: conflict-free banks
             unsigned incl = local;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
