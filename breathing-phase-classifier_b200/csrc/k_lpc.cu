@@ -138,11 +138,13 @@ void launch_lpc(const float* y, int n, const Geometry& g, const Tables& tb, cons
 }
 
 // ------------------------------------------------------------------------------- dataset-level statistics + padding
-// acc layout: [(9 + nscal)][5] doubles = {count, sum, sumsq, min, max}
-__global__ void __launch_bounds__(256) k_stats(Geometry g, const float* __restrict__ feats,
-                                               const float* __restrict__ scalars, double* __restrict__ acc) {
-    __shared__ double dscratch[32];
-    const int b = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+// acc layout: [(9 + nscal)][5] doubles = {count, sum, sumsq, min, max}.  One CTA per segment, one WARP per plane (warp 9:
+// the scalars): only warp shuffles, no block barriers; lane 0 of each warp issues the five atomics of its plane.
+constexpr int kStatsThreads = 320;
+
+__global__ void __launch_bounds__(kStatsThreads) k_stats(Geometry g, const float* __restrict__ feats,
+                                                         const float* __restrict__ scalars, double* __restrict__ acc) {
+    const int b = blockIdx.x, c = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (c < 9) {
         // rows that carry data (api.cu::kLiveRows); rows live..127 of a plane repeat one pad value (pad_freq), which is
         // accounted for analytically instead of being read back: 772 of 1152 rows cross HBM
@@ -154,7 +156,8 @@ __global__ void __launch_bounds__(256) k_stats(Geometry g, const float* __restri
         double s = 0.0, q = 0.0;
         float mn = FLT_MAX, mx = -FLT_MAX;
         int cnt = 0;
-        for (int i = tid; i < NP / 4; i += 256) {
+#pragma unroll 4
+        for (int i = lane; i < NP / 4; i += 32) {
             const float4 v4 = __ldg(p4 + i);
             const float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(256) k_stats(Geometry g, const float* __restri
                 }
             }
         }
-        if (tid == 0 && live < kPlaneRows) {
+        if (lane == 0 && live < kPlaneRows) {
             const float pv = __ldg(plane + NP);
             if ((__float_as_uint(pv) & 0x7f800000u) != 0x7f800000u) {
                 const int m = (kPlaneRows - live) * g.T;
@@ -180,21 +183,21 @@ __global__ void __launch_bounds__(256) k_stats(Geometry g, const float* __restri
                 cnt += m;
             }
         }
-        s = block_sum(s, dscratch);
-        q = block_sum(q, dscratch);
-        const double cntd = block_sum((double)cnt, dscratch);
-        const double mnd = block_reduce((double)mn, 1e300, OpMinD(), dscratch);
-        const double mxd = block_reduce((double)mx, -1e300, OpMaxD(), dscratch);
-        if (tid == 0 && cntd > 0.0) {
+        s = warp_sum(s);
+        q = warp_sum(q);
+        cnt = warp_sum(cnt);
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        if (lane == 0 && cnt > 0) {
             double* a = acc + (size_t)c * 5;
-            atomicAdd(a + 0, cntd);
+            atomicAdd(a + 0, (double)cnt);
             atomicAdd(a + 1, s);
             atomicAdd(a + 2, q);
-            atomic_min_double(a + 3, mnd);
-            atomic_max_double(a + 4, mxd);
+            atomic_min_double(a + 3, (double)mn);
+            atomic_max_double(a + 4, (double)mx);
         }
     } else {
-        for (int i = tid; i < g.nscal; i += 256) {
+        for (int i = lane; i < g.nscal; i += 32) {
             const double v = (double)scalars[(size_t)b * g.nscal + i];
             if (isfinite(v)) {
                 double* a = acc + (size_t)(9 + i) * 5;
@@ -209,8 +212,7 @@ __global__ void __launch_bounds__(256) k_stats(Geometry g, const float* __restri
 }
 
 void launch_stats(int n, const Geometry& g, const float* feats, const float* scalars, double* acc, cudaStream_t st) {
-    dim3 grid(n, 10);
-    k_stats<<<grid, 256, 0, st>>>(g, feats, scalars, acc);
+    k_stats<<<n, kStatsThreads, 0, st>>>(g, feats, scalars, acc);
     note_launch();
 }
 
