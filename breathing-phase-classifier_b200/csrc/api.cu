@@ -16,6 +16,10 @@
 #include <thread>
 #include <vector>
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
 #include "../../include/bpc.h"
 #include "kernels.cuh"
 #include "tables.hpp"
@@ -61,6 +65,18 @@ std::vector<RowRun> live_runs() {
         else r.push_back({s, e});
     }
     return r;
+}
+
+// Constant fill with streaming (non-temporal) stores: the pad rows are written once and not read by this process, and
+// a write-allocate fill would first READ every cache line it overwrites, doubling the host-memory traffic that the
+// ranks of a multi-GPU box share.
+inline void fill_stream(float* p, float* e, float v) {
+#if defined(__SSE2__)
+    while (p < e && (reinterpret_cast<uintptr_t>(p) & 15)) *p++ = v;
+    const __m128 x = _mm_set1_ps(v);
+    for (; p + 4 <= e; p += 4) _mm_stream_ps(p, x);
+#endif
+    while (p < e) *p++ = v;
 }
 
 // Minimal fork-join pool for the host-side work of the host path (pad-row fill, staging copies).
@@ -127,7 +143,7 @@ struct bpc_handle {
     bool slots_ready = false;
     size_t slot_wav_bytes = 0;
     int* live_dev = nullptr;       // kLiveRows on the device
-    HostPool* pool = nullptr;      // host threads of the host path (env BPC_HOST_THREADS, default 8)
+    HostPool* pool = nullptr;      // host threads of the host path (env BPC_HOST_THREADS, default 4)
     bool compact_d2h = true;       // host path transfers live rows only (env BPC_COMPACT_D2H=0: whole planes)
     int host_chunk = 0;            // piece size of the host path (env BPC_HOST_CHUNK, default chunk / 2: the D2H of a piece
                                    // can only start when its kernels are done, so smaller pieces shorten the ramp)
@@ -473,7 +489,7 @@ int ensure_slots(bpc_handle* h) {
     h->dev_allocs.push_back(h->live_dev);
     BPC_CUDA(h, cudaMemcpy(h->live_dev, kLiveRows, sizeof(kLiveRows), cudaMemcpyHostToDevice));
     const char* env_t = std::getenv("BPC_HOST_THREADS");
-    int nt = env_t ? std::atoi(env_t) : 8;
+    int nt = env_t ? std::atoi(env_t) : 4;
     const int hw = (int)std::thread::hardware_concurrency();
     if (hw > 0 && nt > hw) nt = hw;
     if (nt < 1) nt = 1;
@@ -714,9 +730,12 @@ int bpc_precompute_host(bpc_handle* h, const void* wav, int wav_dtype, int64_t B
                     float* dst = user + (size_t)b * seg_feats;
                     for (int c = 0; c < 9; ++c)
                         if (kLiveRows[c] < kPlaneRows)
-                            std::fill(dst + ((size_t)c * kPlaneRows + kLiveRows[c]) * T,
-                                      dst + (size_t)(c + 1) * kPlaneRows * T, s.h_fill[(size_t)b * 9 + c]);
+                            fill_stream(dst + ((size_t)c * kPlaneRows + kLiveRows[c]) * T,
+                                        dst + (size_t)(c + 1) * kPlaneRows * T, s.h_fill[(size_t)b * 9 + c]);
                 }
+#if defined(__SSE2__)
+                _mm_sfence();
+#endif
             });
         }
         if (i >= 2) {                                                  // retire piece i - 2
