@@ -305,6 +305,36 @@ def run_ours(args):
         except Exception as e:                           # the side measurement must not take the bench line down
             extras["config5_precompute_plus_forward"] = {"error": repr(e)}
 
+        # BASELINE configs[0] through OUR entry point: wav files + CSV rows -> process_dataset_threaded -> .npz files
+        # (reader pool -> bpc_precompute_host -> writer pool), next to the same rows into one packed shard
+        try:
+            import contextlib, shutil, tempfile
+            import pandas as pd
+            import scipy.io.wavfile
+            from bpc_b200.precompute import core as CO
+            nf = 1024
+            root = tempfile.mkdtemp(prefix="bpc_cfg1_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            try:
+                wdir = os.path.join(root, "train"); os.makedirs(wdir)
+                ids = [f"steth_{i:05d}_{'EI'[i % 2]}_001" for i in range(nf)]
+                for i, fid in enumerate(ids):
+                    scipy.io.wavfile.write(os.path.join(wdir, CO.wav_name_for(fid, "train")), 16000, pcm[i % len(pcm)])
+                df = pd.DataFrame({"ID": ids, "Target": ["EI"[i % 2] for i in range(nf)]})
+                c1 = {"files": nf, "storage": "tmpfs" if root.startswith("/dev/shm") else "tmp"}
+                for mode, packed in (("npz", False), ("packed_shard", True)):
+                    out = os.path.join(root, "out_" + mode); os.makedirs(out)
+                    with contextlib.redirect_stdout(sys.stderr):
+                        CO.process_dataset_threaded(df.iloc[:64], wdir, out, "train", engine=eng, packed=packed)   # warm
+                        t0 = time.perf_counter()
+                        res = CO.process_dataset_threaded(df, wdir, out, "train", engine=eng, packed=packed)
+                        dtf = time.perf_counter() - t0
+                    c1[mode] = {"files_per_s": nf / dtf, "ok": int(sum(1 for r in res if r[1]))}
+                extras["config1_files_through_process_dataset_threaded"] = c1
+            finally:
+                shutil.rmtree(root, ignore_errors=True)
+        except Exception as e:
+            extras["config1_files_through_process_dataset_threaded"] = {"error": repr(e)}
+
     compact = os.environ.get("BPC_COMPACT_D2H", "1") != "0"
     d2h_rows = 772 if compact else 9 * 128
     if rank == 0:

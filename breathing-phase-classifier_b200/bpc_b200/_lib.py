@@ -58,6 +58,8 @@ _SIGS = {
     "bpc_kernel_name": (C.c_char_p, [C.c_int]),
     "bpc_collate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                               C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bpc_wav_load_batch": (C.c_int, [C.POINTER(C.c_char_p), C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int]),
     "bpc_npz_size": (C.c_int64, [C.c_int, C.c_int]),
     "bpc_npz_pack": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64]),
     "bpc_npz_write_batch": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

@@ -127,6 +127,10 @@ class Engine:
             scalars = np.empty((B, self.nscal), dtype=np.float32)
         if status is None:
             status = np.empty((B,), dtype=np.int32)
+        for name, a, shape, dtp in (("feats", feats, (B, L.NUM_CHANNELS, L.PLANE_ROWS, self.T), np.float32),
+                                    ("scalars", scalars, (B, self.nscal), np.float32), ("status", status, (B,), np.int32)):
+            if tuple(a.shape) != shape or a.dtype != dtp or not a.flags.c_contiguous or not a.flags.writeable:
+                raise ValueError(f"{name} must be a writable C-contiguous {np.dtype(dtp).name} array of shape {shape}")
         rc = self._lib.bpc_precompute_host(self._h, wav.ctypes.data, dt, B, L_in, feats.ctypes.data,
                                            scalars.ctypes.data, status.ctypes.data)
         _check(self._h, rc, "bpc_precompute_host")

@@ -1,8 +1,8 @@
 """Mirror of reference `src/precompute/core.py`: `precompute()` and `process_dataset_threaded(df, audio_dir,
 target_dir, dataset_name)` with the same ID -> wav-path mapping, success / failure tally and messages.
 
-Instead of one Python call per file on two threads (core.py:33-34), rows are decoded by a small thread pool, stacked
-into [B, 16000] PCM16 batches and sent through ONE C-ABI call per batch (`bpc_precompute_host`, pinned double
+Instead of one Python call per file on two threads (core.py:33-34), rows are decoded by a reader pool, stacked
+into [B, 16000] PCM16 batches (`bpc_wav_load_batch`, the C++ reader pool of the library) and sent through ONE C-ABI call per batch (`bpc_precompute_host`, pinned double
 buffering); the `.npz` files are serialised by the C++ writer pool of the library (`bpc_npz_write_batch`).  With
 `packed=True` the same rows go into one packed shard instead (bpc_b200/shards.py), which `PackedDS` reads in place of
 the reference `DS`.
@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 
 from . import methods as _m
-from .process import load_wav, fit_batch
+from .process import load_wav, fit_batch, load_wav_batch
 from ..shards import ShardWriter, write_npz_batch
 
 SR = 16000                      # core.py:9-17
@@ -28,7 +28,7 @@ TEST_CSV_PATH = "input/test.csv"
 TRAIN_AUDIO_DIR = "input/train"
 TEST_AUDIO_DIR = "input/test"
 PRECOMP_DIR = "input/precomputed/"
-BATCH = 1024
+BATCH = 512
 IO_THREADS = 8
 
 
@@ -63,35 +63,67 @@ def _try_load(path):
 
 
 def process_dataset_threaded(df, audio_dir, target_dir, dataset_name, engine=None, batch=BATCH, packed=False):
-    items = [(row["ID"], os.path.join(audio_dir, wav_name_for(row["ID"], dataset_name))) for _, row in df.iterrows()]
+    """core.py:19-45.  Returns the (file_id, success, error) tuples in row order (the reference prints / tallies them).
+
+    Three stages run concurrently, one batch apart: the C++ reader pool decodes batch k+1, the GPU path computes batch k
+    and the C++ writer pool serialises batch k-1 (ctypes releases the GIL during all three)."""
+    items = [(fid, os.path.join(audio_dir, wav_name_for(fid, dataset_name))) for fid in df["ID"].tolist()]
     eng = engine if engine is not None else _m._get_engine()
-    successful = failed = 0
-    results = []
-    shard_rows = []                                   # packed mode: rows are collected and written at the end
-    with ThreadPoolExecutor(max_workers=IO_THREADS) as pool:
-        for lo in range(0, len(items), batch):
-            part = items[lo:lo + batch]
-            loaded = list(pool.map(_try_load, [p for _, p in part]))
-            good = [(fid, w) for (fid, _), (w, err) in zip(part, loaded) if w is not None]
-            for (fid, _), (w, err) in zip(part, loaded):
-                if w is None:
-                    results.append((fid, False, err))
-            if not good:
+    results = [None] * len(items)
+    starts = list(range(0, len(items), batch))
+    shard = ShardWriter(os.path.join(target_dir, dataset_name), len(items), eng.T, eng.nscal) if packed and items else None
+
+    def _load(lo):
+        return load_wav_batch([p for _, p in items[lo:lo + batch]], eng.L, threads=IO_THREADS)
+
+    def _write(pos, ids, feats, scal, status):
+        for p, r in zip(pos, write_npz_batch(target_dir, ids, feats, scal, status, threads=IO_THREADS)):
+            results[p] = r
+
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        nxt = pool.submit(_load, starts[0]) if starts else None
+        pending_write = None
+        for k, lo in enumerate(starts):
+            wavs, errs = nxt.result()
+            nxt = pool.submit(_load, starts[k + 1]) if k + 1 < len(starts) else None
+            good_rows = [i for i, e in enumerate(errs) if e is None]
+            for i, e in enumerate(errs):
+                if e is not None:
+                    results[lo + i] = (items[lo + i][0], False, e)
+            if not good_rows:
                 continue
-            feats, scal, status = eng.precompute_host(fit_batch([w for _, w in good], eng.L))
-            ids = [fid for fid, _ in good]
+            batch_wav = wavs if len(good_rows) == len(errs) else np.ascontiguousarray(wavs[good_rows])
+            pos = [lo + i for i in good_rows]
+            ids = [items[p][0] for p in pos]
             if packed:
-                keep = [i for i in range(len(ids)) if not (status[i] & 1)]
-                results.extend((ids[i], False, "non-finite samples in input") for i in range(len(ids)) if status[i] & 1)
-                shard_rows.append(([ids[i] for i in keep], feats[keep], scal[keep], status[keep]))
-                results.extend((ids[i], True, None) for i in keep)
+                # the library writes this batch straight into the shard's memory-mapped arrays
+                n = len(ids)
+                f_out, s_out, st_out = shard.reserve(n)
+                with _m.ENGINE_LOCK:
+                    eng.precompute_host(batch_wav, f_out, s_out, st_out)
+                bad = np.flatnonzero(np.asarray(st_out) & 1)
+                if len(bad):                          # rare: drop the rows whose input was not finite
+                    keep = [i for i in range(n) if not (st_out[i] & 1)]
+                    shard.unreserve(n)
+                    f2, s2, st2 = shard.reserve(len(keep))
+                    f2[:] = np.asarray(f_out)[keep]; s2[:] = np.asarray(s_out)[keep]; st2[:] = np.asarray(st_out)[keep]
+                    shard.commit([ids[i] for i in keep])
+                else:
+                    shard.commit(ids)
+                badset = set(int(i) for i in bad)
+                for i in range(n):
+                    results[pos[i]] = (ids[i], False, "non-finite samples in input") if i in badset else (ids[i], True, None)
             else:
-                results.extend(write_npz_batch(target_dir, ids, feats, scal, status, threads=IO_THREADS))
-    if packed and shard_rows:
-        shard_dir = os.path.join(target_dir, dataset_name)
-        with ShardWriter(shard_dir, sum(len(r[0]) for r in shard_rows), eng.T, eng.nscal) as w:
-            for ids, f, s, st in shard_rows:
-                w.append(ids, f, s, st)
+                with _m.ENGINE_LOCK:
+                    feats, scal, status = eng.precompute_host(batch_wav)
+                if pending_write is not None:
+                    pending_write.result()
+                pending_write = pool.submit(_write, pos, ids, feats, scal, status)
+        if pending_write is not None:
+            pending_write.result()
+    if shard is not None:
+        shard.close()
+    successful = failed = 0
     for fid, ok, err in results:
         if ok:
             successful += 1

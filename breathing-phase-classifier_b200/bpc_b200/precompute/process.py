@@ -34,6 +34,51 @@ def load_wav(path: str):
     return data.astype(np.float32)
 
 
+WAV_ERR_OPEN, WAV_ERR_FORMAT, WAV_ERR_UNSUPPORTED = -10, -11, -12        # include/bpc.h: bpc_wav_code
+
+
+def load_wav_batch(paths, length=EXPECTED_LEN, threads=8):
+    """`librosa.load(p, sr=16000)` + `pad_or_truncate` (process.py:28-29) for many files at once.
+
+    The library's C++ reader pool handles what the reference is fed (RIFF PCM16 mono 16 kHz) straight into one
+    [n, length] int16 batch; a file it reports as unsupported (stereo, other sample formats) is decoded by `load_wav`,
+    which switches the whole batch to float32.  Returns (batch, errors) with errors[i] = None or the failure message
+    (the row of a failed file is zero; the caller reports it as `(id, False, err)`)."""
+    import ctypes as C
+    from .._lib import lib
+    n = len(paths)
+    out = np.zeros((n, length), dtype=np.int16)
+    sr = np.zeros(n, dtype=np.int32); frames = np.zeros(n, dtype=np.int32); code = np.zeros(n, dtype=np.int32)
+    arr = (C.c_char_p * n)(*[os.fsencode(p) for p in paths])
+    rc = lib().bpc_wav_load_batch(arr, n, SR, length, out.ctypes.data, sr.ctypes.data, frames.ctypes.data,
+                                  code.ctypes.data, int(threads))
+    if rc != 0:
+        raise RuntimeError(f"bpc_wav_load_batch failed ({rc})")
+    errors = [None] * n
+    slow = {}
+    for i in np.flatnonzero(code):
+        if code[i] == WAV_ERR_UNSUPPORTED and sr[i] == SR:
+            try:
+                slow[i] = load_wav(paths[i])
+            except Exception as e:  # noqa: BLE001
+                errors[i] = str(e)
+        elif code[i] == WAV_ERR_UNSUPPORTED:
+            errors[i] = f"{paths[i]}: sample rate {sr[i]} != {SR}; resampling is not part of this build"
+        elif code[i] == WAV_ERR_OPEN:
+            errors[i] = f"[Errno 2] No such file or directory: '{paths[i]}'"
+        else:
+            errors[i] = f"{paths[i]}: not a RIFF/WAVE file"
+    if slow:
+        outf = out.astype(np.float32) / np.float32(32768.0)
+        for i, w in slow.items():
+            w = w.astype(np.float32) / np.float32(32768.0) if w.dtype == np.int16 else w.astype(np.float32)
+            m = min(len(w), length)
+            outf[i] = 0
+            outf[i, :m] = w[:m]
+        return outf, errors
+    return out, errors
+
+
 def fit_batch(waves, length=EXPECTED_LEN):
     """Stack waveforms into one [B, length] array (pad_or_truncate on the host for ragged inputs).
     Returns int16 when every input is int16, else float32."""

@@ -81,21 +81,39 @@ class ShardWriter:
         self.params = params or {}
 
     def append(self, file_ids, feats, scalars, status=None):
-        n, lo = len(file_ids), len(self.ids)
+        n = len(file_ids)
+        f, s, st = self.reserve(n)
+        f[:] = feats
+        s[:] = scalars
+        st[:] = 0 if status is None else status
+        self.commit(file_ids)
+
+    def reserve(self, n: int):
+        """Views of the next n rows (feats, scalars, status) for a producer that writes in place; follow with commit()."""
+        lo = len(self.ids)
         if lo + n > self.capacity:
             raise ValueError("shard capacity exceeded")
-        self.feats[lo:lo + n] = feats
-        self.scalars[lo:lo + n] = scalars
-        self.status[lo:lo + n] = 0 if status is None else status
-        self.ids.extend(str(f) for f in file_ids)
+        self._reserved = n
+        return self.feats[lo:lo + n], self.scalars[lo:lo + n], self.status[lo:lo + n]
 
-    def close(self):
-        if len(self.ids) != self.capacity:
+    def unreserve(self, n: int):
+        self._reserved = 0
+
+    def commit(self, file_ids):
+        if len(file_ids) != getattr(self, "_reserved", -1):
+            raise ValueError("commit() must name exactly the reserved rows")
+        self.ids.extend(str(f) for f in file_ids)
+        self._reserved = 0
+
+    def close(self, allow_short: bool = True):
+        """Write the index.  A shard may hold fewer rows than its capacity (failed files): readers use the first
+        len(ids) rows of the arrays."""
+        if len(self.ids) > self.capacity or (not allow_short and len(self.ids) != self.capacity):
             raise ValueError(f"shard holds {len(self.ids)} of {self.capacity} segments")
         for a in (self.feats, self.scalars, self.status):
             a.flush()
         with open(os.path.join(self.dir, INDEX_NAME), "w") as f:
-            json.dump({"ids": self.ids, "channels": list(L.CHANNELS), "T": self.T, "S": self.S,
+            json.dump({"ids": self.ids, "rows": len(self.ids), "channels": list(L.CHANNELS), "T": self.T, "S": self.S,
                        "params": self.params, "format": "bpc_b200 packed shard v1"}, f)
         del self.feats, self.scalars, self.status
 
@@ -104,7 +122,7 @@ class ShardWriter:
 
     def __exit__(self, et, ev, tb):
         if et is None:
-            self.close()
+            self.close(allow_short=False)
 
 
 class PackedShard:
@@ -116,9 +134,10 @@ class PackedShard:
         self.ids = self.index["ids"]
         self.row = {fid: i for i, fid in enumerate(self.ids)}
         self.channels = list(self.index["channels"])
-        self.feats = np.load(os.path.join(shard_dir, "feats.npy"), mmap_mode="r")
-        self.scalars = np.load(os.path.join(shard_dir, "scalars.npy"), mmap_mode="r")
-        self.status = np.load(os.path.join(shard_dir, "status.npy"), mmap_mode="r")
+        n = len(self.ids)
+        self.feats = np.load(os.path.join(shard_dir, "feats.npy"), mmap_mode="r")[:n]
+        self.scalars = np.load(os.path.join(shard_dir, "scalars.npy"), mmap_mode="r")[:n]
+        self.status = np.load(os.path.join(shard_dir, "status.npy"), mmap_mode="r")[:n]
 
     def __len__(self):
         return len(self.ids)

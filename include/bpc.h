@@ -161,6 +161,16 @@ int64_t bpc_npz_pack(const float* feats, const float* scalars, int T, int nscal,
 int  bpc_npz_write_batch(const char* target_dir, const char* const* file_ids, const float* feats, const float* scalars,
                          const int32_t* status, int64_t n, int T, int nscal, int n_threads, int32_t* ok);
 
+/* ---- host-side ingest (no GPU involved) ----------------------------------------------------------
+ * process.py:28-29: `y, _ = librosa.load(wav_path, sr=SR); y = pad_or_truncate(y, EXPECTED_LEN)` for a batch of files.
+ * Reads RIFF/WAVE PCM16 mono files of sample rate expected_sr with n_threads host threads into out[n, L] (int16, zero
+ * padded / truncated to L; feed it to bpc_precompute* as BPC_WAV_PCM16, the device applies soundfile's 1/32768).
+ * Per file: sr[i], frames[i] (frames in the file) and code[i] = 0 or a bpc_wav_code; rows of failed files are zeroed.
+ * BPC_WAV_ERR_UNSUPPORTED (stereo, other rates or sample formats) means "decode this one with a general reader". */
+enum bpc_wav_code { BPC_WAV_ERR_OPEN = -10, BPC_WAV_ERR_FORMAT = -11, BPC_WAV_ERR_UNSUPPORTED = -12 };
+int  bpc_wav_load_batch(const char* const* paths, int64_t n, int expected_sr, int64_t L, int16_t* out,
+                        int32_t* sr, int32_t* frames, int32_t* code, int n_threads);
+
 /* Segments processed per internal chunk (= per kernel launch); env BPC_CHUNK overrides the default at create time. */
 int  bpc_chunk_size(const bpc_handle* h);
 

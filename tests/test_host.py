@@ -321,3 +321,39 @@ def test_rand_bbox_matches_reference_expression():
         want = (np.clip(cx - cut_w // 2, 0, 63), np.clip(cy - cut_h // 2, 0, 128),
                 np.clip(cx + cut_w // 2, 0, 63), np.clip(cy + cut_h // 2, 0, 128))
         assert got == tuple(int(v) for v in want)
+
+
+def test_cpp_wav_reader_matches_scipy_and_reports_per_file(tmp_path):
+    """bpc_wav_load_batch + pad_or_truncate against scipy.io.wavfile (what the oracle's librosa.load shim reads)."""
+    import scipy.io.wavfile
+    rng = np.random.default_rng(1)
+    sig = {n: (rng.standard_normal(n) * 4000).astype(np.int16) for n in (16000, 12345, 20000, 1)}
+    paths = []
+    for n, q in sig.items():
+        scipy.io.wavfile.write(tmp_path / f"m{n}.wav", 16000, q)
+        paths.append(str(tmp_path / f"m{n}.wav"))
+    scipy.io.wavfile.write(tmp_path / "stereo.wav", 16000, np.stack([sig[16000], sig[16000] // 2], axis=1))
+    scipy.io.wavfile.write(tmp_path / "sr8k.wav", 8000, sig[12345])
+    scipy.io.wavfile.write(tmp_path / "f32.wav", 16000, (sig[12345] / 32768.0).astype(np.float32))
+    (tmp_path / "junk.wav").write_bytes(b"not a wave file at all")
+    # a file with an extra chunk before "data" and an odd-sized chunk (must be skipped with its pad byte)
+    raw = open(paths[0], "rb").read()
+    extra = b"LIST" + (5).to_bytes(4, "little") + b"abcde\x00"
+    patched = raw[:12] + raw[12:36] + extra + raw[36:]
+    patched = patched[:4] + (len(patched) - 8).to_bytes(4, "little") + patched[8:]
+    (tmp_path / "chunks.wav").write_bytes(patched)
+    paths += [str(tmp_path / k) for k in ("stereo.wav", "sr8k.wav", "f32.wav", "junk.wav", "missing.wav", "chunks.wav")]
+    batch, errs = PR.load_wav_batch(paths, 16000, threads=3)
+    assert batch.dtype == np.float32                                       # stereo / float rows forced the float path
+    for i, n in enumerate(sig):
+        want = M.pad_or_truncate(sig[n].astype(np.float32) / np.float32(32768.0), 16000)
+        assert errs[i] is None and np.array_equal(batch[i], want), n
+    st = PR.load_wav(paths[4])                                              # librosa.load(mono=True): channel mean
+    assert errs[4] is None and np.array_equal(batch[4], st[:16000])
+    assert "sample rate 8000" in errs[5]
+    assert errs[6] is None and np.array_equal(batch[6], M.pad_or_truncate((sig[12345] / 32768.0).astype(np.float32), 16000))
+    assert "RIFF" in errs[7] and "No such file" in errs[8]
+    assert errs[9] is None and np.array_equal(batch[9], batch[0])
+    only16, errs = PR.load_wav_batch(paths[:4], 16000)
+    assert only16.dtype == np.int16 and errs == [None] * 4 and np.array_equal(only16[0], sig[16000])
+    assert np.array_equal(only16[1, :12345], sig[12345]) and not only16[1, 12345:].any()
