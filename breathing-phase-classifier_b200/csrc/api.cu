@@ -240,9 +240,16 @@ int check_params(const bpc_params* p, std::string* why) {
         return BPC_ERR_UNSUPPORTED;
     }
     if (!(p->fmax > 0.f && p->fmax <= 8000.f)) { *why = "fmax out of range"; return BPC_ERR_ARG; }
-    if (p->expected_len != 16000) {
-        *why = "this build keeps a whole segment on-chip and supports expected_len == 16000 (DURATION 1.0 s) only";
-        return BPC_ERR_UNSUPPORTED;
+    {
+        // DURATION 1.0 s is the reference's constant (process.py:13-14) and the on-chip path.  Whole multiples up to 32 s
+        // run the same kernels in "long mode" (BASELINE config 4) with their per-segment arrays in a global scratch
+        // region; the Hilbert FFT of length 8000 d is mixed-radix 2/3/5, so d must factor into those.
+        int d = p->expected_len / 16000, r = d;
+        for (int f : {2, 3, 5}) while (r > 1 && r % f == 0) r /= f;
+        if (p->expected_len <= 0 || p->expected_len % 16000 != 0 || d < 1 || d > 32 || r != 1) {
+            *why = "expected_len must be 16000 * d with d = 2^a 3^b 5^c <= 32 (DURATION 1.0 s is the reference's value)";
+            return BPC_ERR_UNSUPPORTED;
+        }
     }
     if (p->pad_scalars_to != 0 && p->pad_scalars_to < BPC_NUM_SCALARS) { *why = "pad_scalars_to < 36"; return BPC_ERR_ARG; }
     return BPC_OK;
@@ -353,11 +360,20 @@ int build_workspace(bpc_handle* h) {
     if ((rc = dalloc(h, C * ((T + 1) / 2) * kMag2048Stride, &w.mag_even))) return rc;
     if ((rc = dalloc(h, C * T * 20, &w.frame_feat))) return rc;
     if ((rc = dalloc(h, C * T * 128, &w.melD))) return rc;
-    w.dec_stride = cens_dec_floats_per_segment();
+    w.dec_stride = cens_dec_floats_per_segment(g.L);
     if ((rc = dalloc(h, C * (size_t)w.dec_stride, &w.dec))) return rc;
     if ((rc = dalloc(h, C * 2, &w.tuning))) return rc;
     if ((rc = dalloc(h, C * 2, &w.chroma_min))) return rc;
     if ((rc = dalloc(h, C * 2, &w.ints))) return rc;
+    w.scratch = nullptr;
+    w.scratch_stride = 0;
+    if (g.long_mode) {
+        // per-segment scratch of the kernel that needs most (kernels of a chunk run one after the other in long mode)
+        size_t need = consumer_scratch_floats(g.T);
+        need = std::max(need, (size_t)1200 * T + 8192);
+        w.scratch_stride = (need + 63) & ~size_t(63);
+        if ((rc = dalloc(h, C * w.scratch_stride, &w.scratch))) return rc;
+    }
     if ((rc = dalloc(h, (size_t)(9 + g.nscal) * 5, &h->stats_acc))) return rc;
     w.dbg_mel_db = w.dbg_mfcc = w.dbg_gam = w.dbg_mod = w.dbg_chroma_stft = w.dbg_chroma_cens = w.dbg_lpc =
         w.dbg_onset = nullptr;
@@ -414,7 +430,16 @@ int run_chunk(bpc_handle* h, const void* wav, int wav_dtype, int64_t L_in, int n
         cudaEventRecord(e.b, st);
         h->evs.push_back(e);
     };
-    if (h->timing || !h->multi_stream) {
+    if (g.long_mode) {
+        // long mode: one stream (the kernels share the scratch region)
+        timed(1, [&] { launch_stft512(y, n, g, h->tb, ws, st); });
+        timed(2, [&] { launch_spec512_consumers(n, g, h->tb, ws, feats, scalars, status, true, st); });
+        timed(3, [&] { launch_spec2048(y, n, g, h->tb, ws, feats, scalars, st); });
+        timed(4, [&] { launch_even2048(n, g, h->tb, ws, scalars, status, st); });
+        timed(10, [&] { launch_seg2048(n, g, h->tb, ws, feats, scalars, st); });
+        timed(5, [&] { launch_cens(y, n, g, h->tb, ws, feats, st); });
+        timed(8, [&] { launch_lpc(y, n, g, h->tb, ws, feats, st); });
+    } else if (h->timing || !h->multi_stream) {
         timed(1, [&] { launch_stft512(y, n, g, h->tb, ws, st); });
         timed(2, [&] { launch_spec512_consumers(n, g, h->tb, ws, feats, scalars, status, true, st); });
         timed(3, [&] { launch_spec2048(y, n, g, h->tb, ws, feats, scalars, st); });
@@ -562,9 +587,11 @@ int bpc_create(bpc_handle** out, const bpc_params* p, int device, int64_t max_ba
     h->g.T = p->expected_len / p->hop + 1;
     h->g.nscal = bpc_num_scalars(p);
     h->g.lpc_frames = (p->expected_len - 400 + 159) / 160;
+    h->g.long_mode = p->expected_len > 16000 ? 1 : 0;
     const char* env_chunk = std::getenv("BPC_CHUNK");
     int chunk = env_chunk ? std::atoi(env_chunk) : 592;               // 4 waves of 148 single-CTA-per-segment kernels
     if (chunk < 1) chunk = 592;
+    if (h->g.long_mode) chunk = std::max(1, chunk / (p->expected_len / 16000));   // same samples (and workspace) per chunk
     h->chunk = (int)std::min<int64_t>(chunk, h->max_batch);
     h->launches0 = launches_issued();
     const char* env_streams = std::getenv("BPC_STREAMS");

@@ -101,7 +101,7 @@ __device__ __forceinline__ ZTerm make_zterm(double sum, double sumsq, double n) 
 // reproduced operation for operation by one warp; every lane returns the sum.  Row-wise z-scores (process.py:47,55) take
 // their mean from this, which matters when a row is constant: numpy's rounded mean then differs from the value and the
 // "normalised" row becomes -1 / +1 instead of 0 (silent input -> MFCC row 0).
-__device__ __forceinline__ float np_sum_f32_warp(const float* a, int n, int lane) {
+__device__ __forceinline__ float np_sum_f32_warp128(const float* a, int n, int lane) {
     float res;
     if (n < 8) {
         res = 0.f;
@@ -122,8 +122,40 @@ __device__ __forceinline__ float np_sum_f32_warp(const float* a, int n, int lane
     return res;
 }
 
+// Any n: numpy's pairwise_sum recursion above 128 elements (n2 = n / 2 rounded down to a multiple of 8, left + right),
+// walked with an explicit stack (uniform across the warp).  Rows longer than 128 only occur in long mode.
+__device__ inline float np_sum_f32_warp(const float* a, int n, int lane) {
+    if (n <= 128) return np_sum_f32_warp128(a, n, lane);
+    float vals[12];
+    int off[12], len[12], state[12];
+    int sp = 0, tp = 0;
+    off[0] = 0; len[0] = n; state[0] = 0; tp = 1;
+    while (tp > 0) {
+        const int f = tp - 1;
+        if (len[f] <= 128) {
+            vals[sp++] = np_sum_f32_warp128(a + off[f], len[f], lane);
+            --tp;
+        } else {
+            int n2 = len[f] / 2;
+            n2 -= n2 % 8;
+            if (state[f] == 0) {
+                state[f] = 1;
+                off[tp] = off[f]; len[tp] = n2; state[tp] = 0; ++tp;
+            } else if (state[f] == 1) {
+                state[f] = 2;
+                off[tp] = off[f] + n2; len[tp] = len[f] - n2; state[tp] = 0; ++tp;
+            } else {
+                const float r = vals[--sp], l = vals[--sp];
+                vals[sp++] = __fadd_rn(l, r);
+                --tp;
+            }
+        }
+    }
+    return vals[0];
+}
+
 // Row-wise z-score terms the numpy way: float32 mean from np_sum_f32_warp, deviations in float32, population std.
-// `a` holds n <= 128 floats in shared memory; one warp per row.
+// `a` holds n floats (shared memory, or global scratch in long mode); one warp per row.
 __device__ __forceinline__ ZTerm np_row_zterm(const float* a, int n, int lane) {
     const float mean = __fdiv_rn(np_sum_f32_warp(a, n, lane), (float)n);
     double q = 0.0;

@@ -10,6 +10,7 @@
 //            85 bins the sparsified bases touch, FP32 sparse complex product, fold to 12 chroma sums kept in registers;
 //   phase 3  CENS post-processing on the [12, T] tile.
 // The decimator stands in for soxr_hq (absent library): the same 127-tap Kaiser half-band the oracle uses.
+#include <algorithm>
 #include <cmath>
 #include "kernels.cuh"
 #include "fft.cuh"
@@ -56,7 +57,13 @@ __host__ __device__ constexpr int goff(int o) {          // offset of octave o's
     return off;
 }
 constexpr int kDecGlobalFloats = goff(7);                // 18,822 floats per segment
-int cens_dec_floats_per_segment() { return (kDecGlobalFloats + 3) & ~3; }
+// same layout for a segment of L samples (long mode; L >> 6 is even for L = 16000 d)
+__host__ __device__ inline int goff_len(int o, int L) {
+    int off = 0;
+    for (int i = 1; i < o; ++i) off += (L >> i) + 2 * kGPad;
+    return off;
+}
+int cens_dec_floats_per_segment(int L) { return (goff_len(7, L) + 3) & ~3; }
 
 // ---------------------------------------------------------------------------------------------- k_cens_dec
 struct DecSmem {
@@ -139,6 +146,26 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_cens_dec(const float* __rest
     decimate_stage(E5, O5, kHalf5, E6, O6, G + goff(6) + kGPad, tid);
 }
 
+// Long mode: one launch per decimation stage, a thread per output sample, signals in global memory in natural order
+// (same taps, same pairing and accumulation order as decimate_stage).  in: n_in samples starting at in[0] (no pads are
+// assumed: out-of-range samples read as 0); out: n_in / 2 samples.
+__global__ void __launch_bounds__(256) k_dec_stage_long(const float* __restrict__ in_base, size_t in_stride, int in_off,
+                                                        int n_in, float* __restrict__ out_base, size_t out_stride,
+                                                        int out_off) {
+    const int b = blockIdx.y;
+    const float* in = in_base + (size_t)b * in_stride + in_off;
+    float* out = out_base + (size_t)b * out_stride + out_off;
+    const double inv_s = 1.0 / sqrt(0.5);
+    const int n_out = n_in >> 1;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_out; n += gridDim.x * blockDim.x) {
+        auto O = [&](int q) -> double { const int i = 2 * q + 1; return (i >= 0 && i < n_in) ? (double)__ldg(in + i) : 0.0; };
+        double acc = c_hb_centre * (double)__ldg(in + 2 * n);
+#pragma unroll 4
+        for (int m = 0; m < 32; ++m) acc = fma(c_hb_odd[m], O(n - 1 - m) + O(n + m), acc);
+        out[n] = (float)(acc * inv_s);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- k_cens (CQT)
 constexpr int kCensThreads = 256, kCensTeams = kCensThreads / 16;
 
@@ -172,6 +199,11 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
     const float* yb = y + (size_t)b * L;
     const float2* y2 = reinterpret_cast<const float2*>(yb);
     const float* G = ws.dec + (size_t)b * cens_dec_stride(ws);
+    // [12, T] tiles: shared memory (1 s), the segment's global scratch region in long mode
+    float* lbase = ws.scratch + (size_t)b * ws.scratch_stride;
+    float* p_csum = g.long_mode ? lbase : S.csum;
+    float* p_chroma = g.long_mode ? lbase + 12 * (size_t)T : S.u.post.chroma;
+    float* p_quant = g.long_mode ? lbase + 24 * (size_t)T : S.u.post.quant;
 
     // ---- stage the basis of this segment's tuning and the smoothing window
     const int tun = ws.tuning[b * 2 + 1];
@@ -230,7 +262,7 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
                 }
             } else {
                 // c0 >= -128 complex samples = -kGPad samples: the zero pads are the centre padding
-                const float2* src = reinterpret_cast<const float2*>(G + goff(o) + kGPad) + c0 + h;
+                const float2* src = reinterpret_cast<const float2*>(G + (g.long_mode ? goff_len(o, L) : goff(o)) + kGPad) + c0 + h;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float2 v = __ldg(src + 16 * j);
@@ -274,17 +306,17 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
             }
             __syncwarp();
         }
-        if (h < 12 && valid) S.csum[h * T + t] = csum;
+        if (h < 12 && valid) p_csum[h * T + t] = csum;
     }
     __syncthreads();
     // ---- CENS post-processing per column: L1 normalise, quantise
     for (int t = tid; t < T; t += kCensThreads) {
         double l1 = 0.0;
-        for (int c = 0; c < 12; ++c) l1 += fabs((double)S.csum[c * T + t]);
+        for (int c = 0; c < 12; ++c) l1 += fabs((double)p_csum[c * T + t]);
         if (l1 < 1.17549435e-38) l1 = 1.0;
         for (int c = 0; c < 12; ++c) {
-            const float v = (float)((double)S.csum[c * T + t] / l1);
-            S.u.post.quant[c * T + t] = 0.25f * (float)((v > 0.4f) + (v > 0.2f) + (v > 0.1f) + (v > 0.05f));
+            const float v = (float)((double)p_csum[c * T + t] / l1);
+            p_quant[c * T + t] = 0.25f * (float)((v > 0.4f) + (v > 0.2f) + (v > 0.1f) + (v > 0.05f));
         }
     }
     __syncthreads();
@@ -293,30 +325,30 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
         const int c = i / T, t = i - c * T;
         double acc = 0.0;
         const int jlo = max(0, t + 21 - (T - 1)), jhi = min(42, t + 21);
-        for (int j = jlo; j <= jhi; ++j) acc += S.swin[j] * (double)S.u.post.quant[c * T + t + 21 - j];
-        S.u.post.chroma[i] = (float)acc;
+        for (int j = jlo; j <= jhi; ++j) acc += S.swin[j] * (double)p_quant[c * T + t + 21 - j];
+        p_chroma[i] = (float)acc;
     }
     __syncthreads();
     // L2 normalise each column
     for (int t = tid; t < T; t += kCensThreads) {
         double l2 = 0.0;
-        for (int c = 0; c < 12; ++c) l2 += (double)S.u.post.chroma[c * T + t] * (double)S.u.post.chroma[c * T + t];
+        for (int c = 0; c < 12; ++c) l2 += (double)p_chroma[c * T + t] * (double)p_chroma[c * T + t];
         l2 = sqrt(l2);
         if (l2 < 1.17549435e-38) l2 = 1.0;
-        for (int c = 0; c < 12; ++c) S.u.post.quant[c * T + t] = (float)((double)S.u.post.chroma[c * T + t] / l2);
+        for (int c = 0; c < 12; ++c) p_quant[c * T + t] = (float)((double)p_chroma[c * T + t] / l2);
     }
     __syncthreads();
     if (ws.dbg_chroma_cens) {
         float* d = ws.dbg_chroma_cens + (size_t)b * 12 * T;
-        for (int i = tid; i < 12 * T; i += kCensThreads) d[i] = S.u.post.quant[i];
+        for (int i = tid; i < 12 * T; i += kCensThreads) d[i] = p_quant[i];
     }
     // ---- row-wise z-score -> rows 12..23; pad rows 24..127 with the min over all 24 normalised rows
     float mn = FLT_MAX;
     float* o = plane_ptr(feats, b, BPC_CH_CHROMA, T);
     for (int r = warp; r < 12; r += kCensThreads / 32) {
-        const ZTerm z = np_row_zterm(S.u.post.quant + r * T, T, lane);
+        const ZTerm z = np_row_zterm(p_quant + r * T, T, lane);
         for (int t = lane; t < T; t += 32) {
-            const float v = z(S.u.post.quant[r * T + t]);
+            const float v = z(p_quant[r * T + t]);
             o[(12 + r) * T + t] = v;
             mn = fminf(mn, v);
         }
@@ -335,7 +367,22 @@ void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, con
         cudaFuncSetAttribute(k_cens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CensSmem));
         done = true;
     }
-    k_cens_dec<<<n, kDecThreads, sizeof(DecSmem), st>>>(y, g, ws);
+    if (g.long_mode) {
+        const int L = g.L;
+        for (int o = 1; o <= 6; ++o) {
+            const int n_in = L >> (o - 1);
+            const int blocks = std::min(64, (n_in / 2 + 255) / 256);
+            if (o == 1)
+                k_dec_stage_long<<<dim3(blocks, n), 256, 0, st>>>(y, (size_t)L, 0, n_in, ws.dec, (size_t)ws.dec_stride,
+                                                                  goff_len(1, L) + kGPad);
+            else
+                k_dec_stage_long<<<dim3(blocks, n), 256, 0, st>>>(ws.dec, (size_t)ws.dec_stride, goff_len(o - 1, L) + kGPad,
+                                                                  n_in, ws.dec, (size_t)ws.dec_stride, goff_len(o, L) + kGPad);
+        }
+        note_launch(5);
+    } else {
+        k_cens_dec<<<n, kDecThreads, sizeof(DecSmem), st>>>(y, g, ws);
+    }
     k_cens<<<n, kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats);
     note_launch(2);
 }

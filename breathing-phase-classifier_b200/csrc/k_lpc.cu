@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(kLpcThreads, 4) k_lpc(const float* __restrict_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x, L = g.L, T = g.T, F_ = g.lpc_frames;
     const float* yb = y + (size_t)b * L;
+    // [12, F] coefficients: shared memory (1 s: F = 98), the segment's global scratch region in long mode
+    float* coef = g.long_mode ? ws.scratch + (size_t)b * ws.scratch_stride : S.coef;
 
     for (int fr = warp; fr < F_; fr += kLpcThreads / 32) {
         const int start = fr * kLpcShift;
@@ -98,17 +100,17 @@ __global__ void __launch_bounds__(kLpcThreads, 4) k_lpc(const float* __restrict_
         den = warp_sum(den);
         double a_lane = lane == 0 ? 1.0 : 0.0;
         burg_all<0>(Fv, Bv, a_lane, den, lane);
-        if (lane >= 1 && lane <= kLpcOrder) S.coef[(lane - 1) * F_ + fr] = (float)a_lane;
+        if (lane >= 1 && lane <= kLpcOrder) coef[(lane - 1) * F_ + fr] = (float)a_lane;
     }
     __syncthreads();
     const int F = F_;
     if (ws.dbg_lpc) {
         float* d = ws.dbg_lpc + (size_t)b * kLpcOrder * F;
-        for (int i = tid; i < kLpcOrder * F; i += kLpcThreads) d[i] = S.coef[i];
+        for (int i = tid; i < kLpcOrder * F; i += kLpcThreads) d[i] = coef[i];
     }
     // whole-array z over all F frames (process.py:65); pad_time keeps the first T columns; pad value = min of those
     double s = 0.0, q = 0.0;
-    for (int i = tid; i < kLpcOrder * F; i += kLpcThreads) { const double v = (double)S.coef[i]; s += v; q += v * v; }
+    for (int i = tid; i < kLpcOrder * F; i += kLpcThreads) { const double v = (double)coef[i]; s += v; q += v * v; }
     s = block_sum(s, S.dscratch);
     q = block_sum(q, S.dscratch);
     const ZTerm z = make_zterm(s, q, (double)(kLpcOrder * F));
@@ -116,13 +118,13 @@ __global__ void __launch_bounds__(kLpcThreads, 4) k_lpc(const float* __restrict_
     float mn = FLT_MAX;
     for (int i = tid; i < kLpcOrder * Tk; i += kLpcThreads) {
         const int c = i / Tk, t = i - c * Tk;
-        mn = fminf(mn, z(S.coef[c * F + t]));
+        mn = fminf(mn, z(coef[c * F + t]));
     }
     mn = block_min(mn, S.fscratch);
     float* o = plane_ptr(feats, b, BPC_CH_LPC, T);
     for (int i = tid; i < kPlaneRows * T; i += kLpcThreads) {
         const int c = i / T, t = i - c * T;
-        o[i] = (c < kLpcOrder && t < Tk) ? z(S.coef[c * F + t]) : mn;
+        o[i] = (c < kLpcOrder && t < Tk) ? z(coef[c * F + t]) : mn;
     }
 }
 

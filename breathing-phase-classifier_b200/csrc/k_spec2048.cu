@@ -277,25 +277,38 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = kSegThreads, NW = kSegThreads / 32;
     const int b = blockIdx.x, T = g.T, NP = kPlaneRows * T;
     float* sc = scalars + (size_t)b * g.nscal;
+    // per-segment arrays: shared memory for 1 s segments, the segment's global scratch region in long mode
+    struct { float *melD, *tg; double *peak, *valley, *cent, *bw, *flat, *sumv, *sumq; float *onset, *flux, *ac0; } V;
+    if (g.long_mode) {
+        double* d = reinterpret_cast<double*>(ws.scratch + (size_t)b * ws.scratch_stride);
+        V.peak = d; d += 7 * T; V.valley = d; d += 7 * T; V.cent = d; d += T; V.bw = d; d += T; V.flat = d; d += T;
+        V.sumv = d; d += T; V.sumq = d; d += T;
+        float* f = reinterpret_cast<float*>(d + (T & 1));                      // keep 16-byte alignment for the float4 staging
+        V.melD = f; V.tg = f; f += (size_t)kPlaneRows * T;
+        V.onset = f; f += T + 2 * 192 + 8; V.flux = f; f += T; V.ac0 = f;
+    } else {
+        V.melD = S.u.melD; V.tg = S.u.tg; V.peak = S.peak; V.valley = S.valley; V.cent = S.cent; V.bw = S.bw;
+        V.flat = S.flat; V.sumv = S.sumv; V.sumq = S.sumq; V.onset = S.onset; V.flux = S.flux; V.ac0 = S.ac0;
+    }
 
     {   // stage per-frame features and mel-D
         const float4* src = reinterpret_cast<const float4*>(ws.melD + (size_t)b * T * kPlaneRows);
-        for (int i = tid; i < T * kPlaneRows / 4; i += NT) reinterpret_cast<float4*>(S.u.melD)[i] = __ldg(src + i);
+        for (int i = tid; i < T * kPlaneRows / 4; i += NT) reinterpret_cast<float4*>(V.melD)[i] = __ldg(src + i);
         const double* ff = ws.frame_feat + (size_t)b * T * kFrameFeat;
         for (int i = tid; i < T * 17; i += NT) {
             const int t = i / 17, j = i - t * 17;
             const double v = ff[t * kFrameFeat + j];
-            if (j == 0) S.cent[t] = v;
-            else if (j == 1) S.bw[t] = v;
-            else if (j == 2) S.flat[t] = v;
-            else if (j < 10) S.peak[(j - 3) * T + t] = v;
-            else S.valley[(j - 10) * T + t] = v;
+            if (j == 0) V.cent[t] = v;
+            else if (j == 1) V.bw[t] = v;
+            else if (j == 2) V.flat[t] = v;
+            else if (j < 10) V.peak[(j - 3) * T + t] = v;
+            else V.valley[(j - 10) * T + t] = v;
         }
     }
     __syncthreads();
     // ---- centroid / bandwidth / flatness statistics (methods.py:64-68), warps 0..2
     if (warp < 3) {
-        const double* a = warp == 0 ? S.cent : (warp == 1 ? S.bw : S.flat);
+        const double* a = warp == 0 ? V.cent : (warp == 1 ? V.bw : V.flat);
         double s = 0.0;
         for (int t = lane; t < T; t += 32) s += a[t];
         s = warp_sum(s);
@@ -327,10 +340,10 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
     {
         double pmax = -1e300, vmax = -1e300;
         for (int i = tid; i < 7 * T; i += NT) {
-            const double p = 10.0 * log10(fmax(1e-10, S.peak[i]));
-            const double v = 10.0 * log10(fmax(1e-10, S.valley[i]));
-            S.peak[i] = p;
-            S.valley[i] = v;
+            const double p = 10.0 * log10(fmax(1e-10, V.peak[i]));
+            const double v = 10.0 * log10(fmax(1e-10, V.valley[i]));
+            V.peak[i] = p;
+            V.valley[i] = v;
             pmax = fmax(pmax, p);
             vmax = fmax(vmax, v);
         }
@@ -338,7 +351,7 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
         vmax = block_reduce(vmax, -1e300, OpMaxD(), S.dscratch);
         double s = 0.0, q = 0.0;
         for (int i = tid; i < 7 * T; i += NT) {
-            const double c = fmax(S.peak[i], pmax - 80.0) - fmax(S.valley[i], vmax - 80.0);
+            const double c = fmax(V.peak[i], pmax - 80.0) - fmax(V.valley[i], vmax - 80.0);
             s += c;
             q += c * c;
         }
@@ -352,24 +365,24 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
     }
     // ---- mel-D: L = 10 log10(max(1e-10, P)); flux uses ref=max (methods.py:90-92), onset uses ref=1 (process.py:74)
     float pmx = -FLT_MAX;
-    for (int i = tid; i < NP; i += NT) pmx = fmaxf(pmx, S.u.melD[i]);
+    for (int i = tid; i < NP; i += NT) pmx = fmaxf(pmx, V.melD[i]);
     pmx = block_max(pmx, S.fscratch);
     const float ref_db = (float)(10.0 * log10((double)fmaxf(1e-10f, pmx)));
     float lmax = -FLT_MAX;
     for (int i = tid; i < NP; i += NT) {
-        const float l = __fmul_rn(10.0f, log10f(fmaxf(1e-10f, S.u.melD[i])));
-        S.u.melD[i] = l;
+        const float l = __fmul_rn(10.0f, log10f(fmaxf(1e-10f, V.melD[i])));
+        V.melD[i] = l;
         lmax = fmaxf(lmax, l);
     }
     lmax = block_max(lmax, S.fscratch);                                     // barrier inside: melD complete
     const float floor1 = __fsub_rn(lmax, 80.0f);                            // ref = 1.0 variant
     const float floorm = __fsub_rn(__fsub_rn(lmax, ref_db), 80.0f);         // ref = max variant
-    for (int j = tid; j < T + 2 * 192 + 8; j += NT) S.onset[j] = 0.f;
+    for (int j = tid; j < T + 2 * 192 + 8; j += NT) V.onset[j] = 0.f;
     __syncthreads();
     for (int t = warp; t < T - 1; t += NW) {
         double f2 = 0.0, on = 0.0;
         for (int m = lane; m < kPlaneRows; m += 32) {
-            const float l0 = S.u.melD[t * kPlaneRows + m], l1 = S.u.melD[(t + 1) * kPlaneRows + m];
+            const float l0 = V.melD[t * kPlaneRows + m], l1 = V.melD[(t + 1) * kPlaneRows + m];
             const float a0 = fmaxf(__fsub_rn(l0, ref_db), floorm), a1 = fmaxf(__fsub_rn(l1, ref_db), floorm);
             const float d = __fsub_rn(a1, a0);
             f2 += (double)__fmul_rn(d, d);
@@ -379,9 +392,9 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
         f2 = warp_sum(f2);
         on = warp_sum(on);
         if (lane == 0) {
-            S.flux[t] = sqrtf((float)f2);
+            V.flux[t] = sqrtf((float)f2);
             // onset_env = pad(mean over mels, (1 + 2048 // (2 * 256), 0))[:T]; stored at offset 192 (left tempogram pad)
-            if (t + 5 < T) S.onset[192 + t + 5] = (float)(on / (double)kPlaneRows);
+            if (t + 5 < T) V.onset[192 + t + 5] = (float)(on / (double)kPlaneRows);
         }
     }
     __syncthreads();
@@ -389,9 +402,9 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
         double s = 0.0, q = 0.0;
         float mx = -FLT_MAX;
         for (int t = lane; t < T - 1; t += 32) {
-            s += (double)S.flux[t];
-            q += (double)S.flux[t] * (double)S.flux[t];
-            mx = fmaxf(mx, S.flux[t]);
+            s += (double)V.flux[t];
+            q += (double)V.flux[t] * (double)V.flux[t];
+            mx = fmaxf(mx, V.flux[t]);
         }
         s = warp_sum(s);
         q = warp_sum(q);
@@ -404,14 +417,14 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
         }
     }
     if (ws.dbg_onset)
-        for (int t = tid; t < T; t += NT) ws.dbg_onset[(size_t)b * T + t] = S.onset[192 + t];
+        for (int t = tid; t < T; t += NT) ws.dbg_onset[(size_t)b * T + t] = V.onset[192 + t];
     // ---- tempogram (process.py:75): linear-ramp pad 192, 384-sample Hann frames at hop 1, autocorrelation, /max
     if (tid < 192) {
-        const float edge = S.onset[192 + T - 1];
+        const float edge = V.onset[192 + T - 1];
         const float step = __fdiv_rn(edge, 192.0f);
-        S.onset[192 + T + tid] = __fmul_rn((float)(191 - tid), step);       // np.pad(mode='linear_ramp', end 0)
+        V.onset[192 + T + tid] = __fmul_rn((float)(191 - tid), step);       // np.pad(mode='linear_ramp', end 0)
     }
-    for (int t = tid; t < T; t += NT) { S.sumv[t] = 0.0; S.sumq[t] = 0.0; }
+    for (int t = tid; t < T; t += NT) { V.sumv[t] = 0.0; V.sumq[t] = 0.0; }
     __syncthreads();
     // two frames in flight: group gidx (96 threads) owns frames gidx, gidx + 2, ...; thread j owns lags 4j .. 4j + 3.
     const int gidx = tid / 96, j = tid - gidx * 96, l0 = 4 * j;
@@ -420,7 +433,7 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
         const bool live = t < T;
         if (live) {
             for (int n = j; n < kTempoLags + 8; n += 96)
-                F[n] = n < kTempoLags ? (float)((double)S.onset[t + n] * __ldg(tb.hann384 + n)) : 0.f;
+                F[n] = n < kTempoLags ? (float)((double)V.onset[t + n] * __ldg(tb.hann384 + n)) : 0.f;
         }
         group_bar(1 + gidx, 96);
         if (live) {
@@ -436,16 +449,16 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
                 a2 = fmaf(A.x, B0.z, a2); a2 = fmaf(A.y, B0.w, a2); a2 = fmaf(A.z, B1.x, a2); a2 = fmaf(A.w, B1.y, a2);
                 a3 = fmaf(A.x, B0.w, a3); a3 = fmaf(A.y, B1.x, a3); a3 = fmaf(A.z, B1.y, a3); a3 = fmaf(A.w, B1.z, a3);
             }
-            if (j == 0) S.ac0[t] = a0;
+            if (j == 0) V.ac0[t] = a0;
             if (l0 < kPlaneRows) {
-                S.u.tg[(l0 + 0) * T + t] = a0; S.u.tg[(l0 + 1) * T + t] = a1;
-                S.u.tg[(l0 + 2) * T + t] = a2; S.u.tg[(l0 + 3) * T + t] = a3;
+                V.tg[(l0 + 0) * T + t] = a0; V.tg[(l0 + 1) * T + t] = a1;
+                V.tg[(l0 + 2) * T + t] = a2; V.tg[(l0 + 3) * T + t] = a3;
             }
             double sv = (double)a0 + (double)a1 + (double)a2 + (double)a3;
             double sq = (double)a0 * a0 + (double)a1 * a1 + (double)a2 * a2 + (double)a3 * a3;
             sv = warp_sum(sv);
             sq = warp_sum(sq);
-            if (lane == 0) { atomicAdd(&S.sumv[t], sv); atomicAdd(&S.sumq[t], sq); }
+            if (lane == 0) { atomicAdd(&V.sumv[t], sv); atomicAdd(&V.sumq[t], sq); }
         }
         group_bar(1 + gidx, 96);
     }
@@ -453,9 +466,9 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
     // util.normalize(norm=inf) divides each column by max |.| (= lag 0); z-score over all 384 x T values (process.py:76)
     double s = 0.0, q = 0.0;
     for (int t = tid; t < T; t += NT) {
-        const double c = (double)S.ac0[t] < 2.2250738585072014e-308 ? 1.0 : (double)S.ac0[t];
-        s += S.sumv[t] / c;
-        q += S.sumq[t] / (c * c);
+        const double c = (double)V.ac0[t] < 2.2250738585072014e-308 ? 1.0 : (double)V.ac0[t];
+        s += V.sumv[t] / c;
+        q += V.sumq[t] / (c * c);
     }
     s = block_sum(s, S.dscratch);
     q = block_sum(q, S.dscratch);
@@ -464,8 +477,8 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
     float* o = plane_ptr(feats, b, BPC_CH_TEMPOGRAM, T);
     for (int i = tid; i < NP; i += NT) {                                     // pad_freq truncates to the first 128 lags
         const int t = i % T;
-        const double c = (double)S.ac0[t] < 2.2250738585072014e-308 ? 1.0 : (double)S.ac0[t];
-        o[i] = (float)(((double)S.u.tg[i] / c - mean) / (sd + 1e-8));
+        const double c = (double)V.ac0[t] < 2.2250738585072014e-308 ? 1.0 : (double)V.ac0[t];
+        o[i] = (float)(((double)V.tg[i] / c - mean) / (sd + 1e-8));
     }
 }
 
@@ -487,15 +500,18 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
                                                   int32_t* status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Even2048Smem& E = *reinterpret_cast<Even2048Smem*>(smem_raw);
-    float* cand_mag = E.cand_mag;
-    float* cand_pitch = E.cand_pitch;
-    float* sortbuf = E.sortbuf;
-    float* colmax = E.colmax;
-    float* roll = E.roll;
-    int* hist = E.hist;
-    __shared__ int s_ncand;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x, T = g.T, TE = (T + 1) / 2;
+    // candidate lists and per-frame arrays: shared memory (1 s), the segment's global scratch region in long mode
+    const int cap = g.long_mode ? 492 * TE : kMaxCand;
+    float* lbase = ws.scratch + (size_t)b * ws.scratch_stride;
+    float* cand_mag = g.long_mode ? lbase : E.cand_mag;
+    float* cand_pitch = g.long_mode ? lbase + cap : E.cand_pitch;
+    float* colmax = g.long_mode ? lbase + 2 * (size_t)cap : E.colmax;
+    float* roll = g.long_mode ? colmax + TE : E.roll;
+    float* sortbuf = E.sortbuf;
+    int* hist = E.hist;
+    __shared__ int s_ncand;
     // even frame f is row f of the segment's mag_even block (written by k_frame2048)
     const float* mag_b = ws.mag_even + (size_t)b * TE * kMag2048Stride;
     const size_t fstride = (size_t)kMag2048Stride;
@@ -570,13 +586,13 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
         if (piptrack_candidate(__ldg(col + k - 1), __ldg(col + k), __ldg(col + k + 1), __fmul_rn(0.1f, colmax[f]), k,
                                7.8125, &pitch, &mv)) {
             const int slot = atomicAdd(&s_ncand, 1);
-            if (slot < kMaxCand) { cand_mag[slot] = mv; cand_pitch[slot] = pitch; }
+            if (slot < cap) { cand_mag[slot] = mv; cand_pitch[slot] = pitch; }
         }
     }
     __syncthreads();
     int n = s_ncand;
     unsigned flags = 0;
-    if (n > kMaxCand) { n = kMaxCand; flags |= BPC_SEG_CAND_OVERFLOW; }
+    if (n > cap) { n = cap; flags |= BPC_SEG_CAND_OVERFLOW; }
     bool empty = false;
     const int tbin = tuning_from_candidates(cand_mag, cand_pitch, n, sortbuf, hist, tb.hist_edges, 36, &empty);
     if (empty) flags |= BPC_SEG_TUNING_EMPTY;

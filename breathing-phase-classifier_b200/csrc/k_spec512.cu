@@ -182,37 +182,39 @@ __device__ void apply_bank(const BankDev& bank, const float* __restrict__ mag_b,
 // broadcast sector out of L1; staging it in shared memory cost 20 KB per CTA and one resident CTA per SM).
 __device__ void dct_mel40(const float* __restrict__ Dg, const float* P, int T, float* C) {
     const int kb = threadIdx.x >> 5, tp = threadIdx.x & 31;
-    const int t0 = 2 * tp, t1 = min(2 * tp + 1, T - 1);
-    if (kb < 8 && t0 < T) {
-        double acc[5][2];
+    for (int tb0 = 0; tb0 < T; tb0 += 64) {                    // one pass per 64 columns (a single pass when T <= 64)
+        const int t0 = tb0 + 2 * tp, t1 = min(t0 + 1, T - 1);
+        if (kb < 8 && t0 < T) {
+            double acc[5][2];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) acc[i][0] = acc[i][1] = 0.0;
+            for (int i = 0; i < 5; ++i) acc[i][0] = acc[i][1] = 0.0;
 #pragma unroll 1
-        for (int blk = 0; blk < 4; ++blk) {
-            float part[5][2];
+            for (int blk = 0; blk < 4; ++blk) {
+                float part[5][2];
 #pragma unroll
-            for (int i = 0; i < 5; ++i) part[i][0] = part[i][1] = 0.f;
+                for (int i = 0; i < 5; ++i) part[i][0] = part[i][1] = 0.f;
 #pragma unroll 2
-            for (int n = blk * 32; n < blk * 32 + 32; n += 4) {
-                float p0[4], p1[4];
+                for (int n = blk * 32; n < blk * 32 + 32; n += 4) {
+                    float p0[4], p1[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { p0[q] = P[(n + q) * T + t0]; p1[q] = P[(n + q) * T + t1]; }
+                    for (int q = 0; q < 4; ++q) { p0[q] = P[(n + q) * T + t0]; p1[q] = P[(n + q) * T + t1]; }
 #pragma unroll
-                for (int i = 0; i < 5; ++i) {
-                    const float4 d = __ldg(reinterpret_cast<const float4*>(Dg + (5 * kb + i) * 128 + n));
-                    part[i][0] = fmaf(d.x, p0[0], part[i][0]); part[i][1] = fmaf(d.x, p1[0], part[i][1]);
-                    part[i][0] = fmaf(d.y, p0[1], part[i][0]); part[i][1] = fmaf(d.y, p1[1], part[i][1]);
-                    part[i][0] = fmaf(d.z, p0[2], part[i][0]); part[i][1] = fmaf(d.z, p1[2], part[i][1]);
-                    part[i][0] = fmaf(d.w, p0[3], part[i][0]); part[i][1] = fmaf(d.w, p1[3], part[i][1]);
+                    for (int i = 0; i < 5; ++i) {
+                        const float4 d = __ldg(reinterpret_cast<const float4*>(Dg + (5 * kb + i) * 128 + n));
+                        part[i][0] = fmaf(d.x, p0[0], part[i][0]); part[i][1] = fmaf(d.x, p1[0], part[i][1]);
+                        part[i][0] = fmaf(d.y, p0[1], part[i][0]); part[i][1] = fmaf(d.y, p1[1], part[i][1]);
+                        part[i][0] = fmaf(d.z, p0[2], part[i][0]); part[i][1] = fmaf(d.z, p1[2], part[i][1]);
+                        part[i][0] = fmaf(d.w, p0[3], part[i][0]); part[i][1] = fmaf(d.w, p1[3], part[i][1]);
+                    }
                 }
+#pragma unroll
+                for (int i = 0; i < 5; ++i) { acc[i][0] += (double)part[i][0]; acc[i][1] += (double)part[i][1]; }
             }
 #pragma unroll
-            for (int i = 0; i < 5; ++i) { acc[i][0] += (double)part[i][0]; acc[i][1] += (double)part[i][1]; }
-        }
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            C[(5 * kb + i) * T + t0] = (float)acc[i][0];
-            if (2 * tp + 1 < T) C[(5 * kb + i) * T + t0 + 1] = (float)acc[i][1];
+            for (int i = 0; i < 5; ++i) {
+                C[(5 * kb + i) * T + t0] = (float)acc[i][0];
+                if (t0 + 1 < T) C[(5 * kb + i) * T + t0 + 1] = (float)acc[i][1];
+            }
         }
     }
     __syncthreads();
@@ -222,32 +224,34 @@ __device__ void dct_mel40(const float* __restrict__ Dg, const float* P, int T, f
 // shared memory.  Same 5 x 2 register tile; float32 partial sums over 16 t combined in float64.
 __device__ void dct_time40(const float* DTs, const float* C1, int T, float* C2) {
     const int kb = threadIdx.x >> 5, up = threadIdx.x & 31;
-    const int u0 = 2 * up, u1 = min(2 * up + 1, T - 1);
-    if (kb < 8 && u0 < T) {
-        double acc[5][2];
-        float part[5][2];
+    for (int ub0 = 0; ub0 < T; ub0 += 64) {                    // one pass per 64 output columns
+        const int u0 = ub0 + 2 * up, u1 = min(u0 + 1, T - 1);
+        if (kb < 8 && u0 < T) {
+            double acc[5][2];
+            float part[5][2];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) { acc[i][0] = acc[i][1] = 0.0; part[i][0] = part[i][1] = 0.f; }
-        for (int t = 0; t < T; ++t) {
-            const float d0 = DTs[t * T + u0], d1 = DTs[t * T + u1];
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const float c = C1[(5 * kb + i) * T + t];
-                part[i][0] = fmaf(d0, c, part[i][0]);
-                part[i][1] = fmaf(d1, c, part[i][1]);
-            }
-            if ((t & 15) == 15) {
+            for (int i = 0; i < 5; ++i) { acc[i][0] = acc[i][1] = 0.0; part[i][0] = part[i][1] = 0.f; }
+            for (int t = 0; t < T; ++t) {
+                const float d0 = DTs[(size_t)t * T + u0], d1 = DTs[(size_t)t * T + u1];
 #pragma unroll
                 for (int i = 0; i < 5; ++i) {
-                    acc[i][0] += (double)part[i][0]; acc[i][1] += (double)part[i][1];
-                    part[i][0] = part[i][1] = 0.f;
+                    const float c = C1[(5 * kb + i) * T + t];
+                    part[i][0] = fmaf(d0, c, part[i][0]);
+                    part[i][1] = fmaf(d1, c, part[i][1]);
+                }
+                if ((t & 15) == 15) {
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        acc[i][0] += (double)part[i][0]; acc[i][1] += (double)part[i][1];
+                        part[i][0] = part[i][1] = 0.f;
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            C2[(5 * kb + i) * T + u0] = (float)(acc[i][0] + (double)part[i][0]);
-            if (2 * up + 1 < T) C2[(5 * kb + i) * T + u0 + 1] = (float)(acc[i][1] + (double)part[i][1]);
+            for (int i = 0; i < 5; ++i) {
+                C2[(5 * kb + i) * T + u0] = (float)(acc[i][0] + (double)part[i][0]);
+                if (u0 + 1 < T) C2[(5 * kb + i) * T + u0 + 1] = (float)(acc[i][1] + (double)part[i][1]);
+            }
         }
     }
     __syncthreads();
@@ -277,14 +281,16 @@ __device__ ZTerm zterm_of(const float* a, int n, double* dscratch, float* fscrat
 // ------------------------------------------------------------------------------------------- role 0: mel3+mod
 __device__ void role_mel(int b, const Geometry g, const Tables& tb, const Workspace& ws, float* feats, float* mel3,
                          float* smem, double* dscratch, float* fscratch) {
+    // `smem` is the role's private array space: shared memory for 1 s segments, a per-segment global scratch region in
+    // long mode (g.long_mode), where the time DCT matrix is also read from its global table instead of being staged
     const int T = g.T, NP = kPlaneRows * T;
     float* P = smem;                 // [128*T] mel power -> mel_db
     float* C1 = P + NP;              // [40*T]
     float* C2 = C1 + 40 * T;         // [40*T]
-    float* DTs = C2 + 40 * T;        // [T*T] DCT matrix (time axis), transposed
+    const float* DTs = g.long_mode ? tb.dct_time : C2 + 40 * T;      // [T*T] DCT matrix (time axis), transposed
     const float* mag_b = ws.mag512 + (size_t)b * T * kMagStride;
 
-    if (!mel3) stage_matrix(DTs, tb.dct_time, T * T);
+    if (!mel3 && !g.long_mode) stage_matrix(C2 + 40 * T, tb.dct_time, T * T);
     apply_bank<128>(tb.mel_a, mag_b, T, true, P);
     power_to_db_inplace(P, NP, true, fscratch);                      // process.py:33
     if (ws.dbg_mel_db) {
@@ -403,11 +409,13 @@ __device__ void role_chroma_stft(int b, const Geometry g, const Tables& tb, cons
                                  float* scalars, int32_t* status, float* smem, double* dscratch, float* fscratch) {
     const int T = g.T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    float* cand_mag = smem;                       // [kMaxCand]
-    float* cand_pitch = cand_mag + kMaxCand;      // [kMaxCand]
-    float* sortbuf = cand_pitch + kMaxCand;       // [kMaxCand]
-    float* colmax = sortbuf + kMaxCand;           // [64]
-    float* raw = colmax + 64;                     // [12*T]
+    // candidate capacity: kMaxCand in shared memory, every (bin, frame) pair in long mode (global scratch)
+    const int cap = g.long_mode ? 123 * T : kMaxCand;
+    float* cand_mag = smem;                       // [cap]
+    float* cand_pitch = cand_mag + cap;           // [cap]
+    float* sortbuf = cand_pitch + cap;            // [kMaxCand] (the selection needs 516 words)
+    float* colmax = sortbuf + kMaxCand;           // [T] (64 in shared memory)
+    float* raw = colmax + (g.long_mode ? T : 64); // [12*T]
     int* hist = (int*)(raw + 12 * T);             // [100]
     __shared__ int s_ncand;
     const float* mag_b = ws.mag512 + (size_t)b * T * kMagStride;
@@ -444,13 +452,13 @@ __device__ void role_chroma_stft(int b, const Geometry g, const Tables& tb, cons
         if (piptrack_candidate(__ldg(col + k - 1), __ldg(col + k), __ldg(col + k + 1), __fmul_rn(0.1f, colmax[t]), k,
                                31.25, &pitch, &mv)) {
             const int slot = atomicAdd(&s_ncand, 1);
-            if (slot < kMaxCand) { cand_mag[slot] = mv; cand_pitch[slot] = pitch; }
+            if (slot < cap) { cand_mag[slot] = mv; cand_pitch[slot] = pitch; }
         }
     }
     __syncthreads();
     int n = s_ncand;
     uint32_t flags = 0;
-    if (n > kMaxCand) { n = kMaxCand; flags |= BPC_SEG_CAND_OVERFLOW; }
+    if (n > cap) { n = cap; flags |= BPC_SEG_CAND_OVERFLOW; }
     bool empty = false;
     const int tbin = tuning_from_candidates(cand_mag, cand_pitch, n, sortbuf, hist, tb.hist_edges, 12, &empty);
     if (empty) flags |= BPC_SEG_TUNING_EMPTY;
@@ -512,14 +520,25 @@ static_assert(kPlaneRows * kMaxFrames + 80 * kMaxFrames + kMaxFrames * kMaxFrame
 constexpr int kLightSmemFloats = 3 * kMaxCand + 64 + 12 * kMaxFrames + 100 + 28;                             // role_chroma_stft
 static_assert(64 * kMaxFrames <= kLightSmemFloats, "role_gammatone layout");
 
+// per-segment scratch floats of the four roles in long mode (each role owns a disjoint region)
+__host__ __device__ inline size_t consumer_role_offset(int role, int T) {
+    const size_t t = (size_t)T;
+    const size_t o1 = 208 * t, o2 = o1 + 288 * t, o3 = o2 + 64 * t;
+    return role == 0 ? 0 : (role == 1 ? o1 : (role == 2 ? o2 : o3));
+}
+size_t consumer_scratch_floats(int T) {
+    return consumer_role_offset(3, T) + (size_t)2 * 123 * T + kMaxCand + (size_t)13 * T + 128;
+}
+
 __global__ void __launch_bounds__(256) k_spec512_consumers(Geometry g, Tables tb, Workspace ws, float* feats,
                                                            float* scalars, int32_t* status, float* mel3,
                                                            int role_base) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(16) float smem_dyn[];
     __shared__ double dscratch[32];
     __shared__ float fscratch[32];
     const int b = blockIdx.x;
     const int role = blockIdx.y + role_base;
+    float* smem = g.long_mode ? ws.scratch + (size_t)b * ws.scratch_stride + consumer_role_offset(role, g.T) : smem_dyn;
     switch (role) {
         case 0: role_mel(b, g, tb, ws, feats, mel3, smem, dscratch, fscratch); break;
         case 1: role_mfcc(b, g, tb, ws, feats, smem, dscratch, fscratch); break;
@@ -543,14 +562,14 @@ void launch_spec512_consumers(int n, const Geometry& g, const Tables& tb, const 
     static const char* only = std::getenv("BPC_ONLY_ROLE");      // profiling aid: time one role (outputs incomplete)
     if (only) {
         const int r = std::atoi(only);
-        k_spec512_consumers<<<dim3(n, 1), 256, (r < 2 ? kConsumerSmemFloats : kLightSmemFloats) * sizeof(float), st>>>(
+        k_spec512_consumers<<<dim3(n, 1), 256, g.long_mode ? 0 : (r < 2 ? kConsumerSmemFloats : kLightSmemFloats) * sizeof(float), st>>>(
             g, tb, ws, feats, scalars, status, nullptr, r);
         note_launch();
         return;
     }
-    k_spec512_consumers<<<dim3(n, 2), 256, kConsumerSmemFloats * sizeof(float), st>>>(g, tb, ws, feats, scalars, status,
-                                                                                       nullptr, 0);
-    k_spec512_consumers<<<dim3(n, with_chroma ? 2 : 1), 256, kLightSmemFloats * sizeof(float), st>>>(
+    k_spec512_consumers<<<dim3(n, 2), 256, g.long_mode ? 0 : kConsumerSmemFloats * sizeof(float), st>>>(
+        g, tb, ws, feats, scalars, status, nullptr, 0);
+    k_spec512_consumers<<<dim3(n, with_chroma ? 2 : 1), 256, g.long_mode ? 0 : kLightSmemFloats * sizeof(float), st>>>(
         g, tb, ws, feats, scalars, status, nullptr, 2);
     note_launch(2);
 }
@@ -558,8 +577,8 @@ void launch_spec512_consumers(int n, const Geometry& g, const Tables& tb, const 
 void launch_logmel_only(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* mel3, cudaStream_t st) {
     set_consumer_smem();
     dim3 grid(n, 1);
-    k_spec512_consumers<<<grid, 256, kConsumerSmemFloats * sizeof(float), st>>>(g, tb, ws, nullptr, nullptr, nullptr,
-                                                                                 mel3, 0);
+    k_spec512_consumers<<<grid, 256, g.long_mode ? 0 : kConsumerSmemFloats * sizeof(float), st>>>(g, tb, ws, nullptr, nullptr,
+                                                                                                    nullptr, mel3, 0);
     note_launch();
 }
 

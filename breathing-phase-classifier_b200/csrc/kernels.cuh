@@ -62,6 +62,8 @@ struct Workspace {            // per chunk of `cap` segments
     int* tuning;              // [cap, 2]   tuning bin for 12 / 36 bins per octave
     float* chroma_min;        // [cap, 2]   min of the normalised chroma_stft / chroma_cens rows
     int* ints;                // [cap, 2]   n_peaks, first-min index
+    float* scratch;           // [cap, scratch_stride]  long mode: what the 1 s kernels keep in shared memory
+    size_t scratch_stride;
     // debug (raw, un-normalised stages of the last chunk)
     float* dbg_mel_db;        // [cap, 128, T]
     float* dbg_mfcc;          // [cap, 120, T]
@@ -79,6 +81,7 @@ struct Geometry {
     int hop;                  // 256
     int nscal;                // scalars per segment in the output (36 or padded)
     int lpc_frames;           // len(range(0, L - 400, 160))
+    int long_mode;            // L > 16000 (BASELINE config 4): per-segment arrays live in Workspace::scratch, not on chip
 };
 
 // feats layout: [B, 9, 128, T]; plane pointer of channel c of segment b
@@ -117,8 +120,10 @@ void launch_collate(const float* store_feats, const float* store_scalars, const 
 
 void launch_pad_values(const float* feats, int T, int n, const int* live_dev, float* fill, cudaStream_t st);
 
+size_t consumer_scratch_floats(int T);
+
 void upload_cens_constants(const double* taps127);
-int cens_dec_floats_per_segment();
+int cens_dec_floats_per_segment(int L);
 int64_t launches_issued();   // process-wide counter bumped by every launcher
 void note_launch(int n = 1);
 

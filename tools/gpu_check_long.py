@@ -1,0 +1,66 @@
+"""Long-mode parity report (BASELINE config 4): CUDA path with expected_len = 16000 * d vs the CPU oracle run with
+Params(duration=d).  usage: python tools/gpu_check_long.py [d] [n_segments]"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "breathing-phase-classifier_b200"))
+
+
+def long_segment(i, d):
+    from oracle import pipeline as P
+    return np.concatenate([P.synth_segment(7000 + 37 * i + k) for k in range(d)]).astype(np.float32)
+
+
+def compare(d=2, n=4, verbose=True):
+    import torch, bpc_b200
+    from oracle import pipeline as P
+    p = P.Params(duration=float(d))
+    Y = np.stack([long_segment(i, d) for i in range(n)])
+    eng = bpc_b200.Engine(device=0, max_batch=max(n, 4), params=bpc_b200.default_params(expected_len=16000 * d), debug=True)
+    feats, scal, status = eng.precompute(torch.from_numpy(Y).cuda())
+    torch.cuda.synchronize()
+    feats = feats.cpu().numpy(); scal = scal.cpu().numpy(); status = status.cpu().numpy()
+    keys = ("mel_db", "mfcc_raw", "gammatone_raw", "mod_spec_raw", "chroma_stft_raw", "chroma_cens_raw", "lpc_raw",
+            "onset_env", "tuning", "ints")
+    dbg = {k: eng.debug(k, n) for k in keys}
+    worst, edges = {}, np.linspace(-0.5, 0.5, 101)
+    scal_rel = np.zeros(36); tun = [0, 0]; ints_ok = 0
+
+    def upd(name, a, b):
+        a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+        if a.shape != b.shape:
+            worst[name] = float("inf"); return
+        dd = np.abs(a - b); dd = np.where(np.isnan(a) & np.isnan(b), 0.0, dd)
+        worst[name] = max(worst.get(name, 0.0), float(np.nanmax(np.where(np.isfinite(dd), dd, np.inf))))
+
+    for i in range(n):
+        dd = {}
+        ch, sc = P.segment_features(Y[i], p, debug=dd)
+        ref = P.stack_sorted(ch)
+        t12 = int(np.argmin(np.abs(edges[:100] - dd["tuning12"]))); t36 = int(np.argmin(np.abs(edges[:100] - dd["tuning36"])))
+        ok12 = t12 == dbg["tuning"][i, 0]; ok36 = t36 == dbg["tuning"][i, 1]
+        tun[0] += ok12; tun[1] += ok36
+        for k in ("mel_db", "mfcc_raw", "gammatone_raw", "mod_spec_raw", "lpc_raw", "onset_env"):
+            upd(k, dbg[k][i], dd[k])
+        if ok12: upd("chroma_stft_raw", dbg["chroma_stft_raw"][i], dd["chroma_stft_raw"])
+        if ok36: upd("chroma_cens_raw", dbg["chroma_cens_raw"][i], dd["chroma_cens_raw"])
+        for c, key in enumerate(P.SORTED_KEYS):
+            if key == "chroma" and not (ok12 and ok36): continue
+            upd("ch:" + key, feats[i, c], ref[c])
+        ints_ok += int(dbg["ints"][i, 0] == dd["n_peaks"] and dbg["ints"][i, 1] == dd["first_min_idx"])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rel = np.abs(scal[i, :36].astype(np.float64) - sc.astype(np.float64)) / np.maximum(np.abs(sc.astype(np.float64)), 1e-30)
+        rel = np.where(sc == scal[i, :36], 0.0, rel)
+        scal_rel = np.maximum(scal_rel, np.nan_to_num(rel, nan=np.inf))
+        if verbose and i == 0:
+            print("tuning gpu", dbg["tuning"][i].tolist(), "ref", [t12, t36], "ints gpu", dbg["ints"][i].tolist(), "ref", [dd["n_peaks"], dd["first_min_idx"]], "status", status[i])
+    if verbose:
+        print(f"d={d} T={eng.T} n={n}")
+        for k, v in worst.items(): print(f"{k:20s} max abs err {v:.3e}")
+        print("scalar max rel err per index:"); print(np.array2string(scal_rel, precision=1, max_line_width=220))
+        print(f"tuning agreement {tun[0]}/{n} {tun[1]}/{n}; integer outputs exact {ints_ok}/{n}")
+    return dict(worst=worst, scal_rel=scal_rel, tun=tun, ints_ok=ints_ok, n=n, status=status)
+
+
+if __name__ == "__main__":
+    compare(int(sys.argv[1]) if len(sys.argv) > 1 else 2, int(sys.argv[2]) if len(sys.argv) > 2 else 4)
