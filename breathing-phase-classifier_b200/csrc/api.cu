@@ -289,6 +289,22 @@ int build_tables(bpc_handle* h) {
         if ((rc = upload(h, to_f(twiddles(8000, 8000)), &tb.tw8000f))) return rc;
         if ((rc = upload(h, to_f(twiddles(16000, 8001)), &tb.ptw16000f))) return rc;
     }
+    tb.tw_long = nullptr;
+    tb.ptw_long = nullptr;
+    if (h->g.long_mode) {
+        const int N = h->g.L / 2;
+        std::vector<float2> a((size_t)N), b((size_t)N + 1);
+        for (int j = 0; j < N; ++j) {
+            const double ang = -2.0 * kPi * double(j) / double(N);
+            a[j] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+        for (int k = 0; k <= N; ++k) {
+            const double ang = -2.0 * kPi * double(k) / double(2 * N);
+            b[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+        if ((rc = upload(h, a, &tb.tw_long))) return rc;
+        if ((rc = upload(h, b, &tb.ptw_long))) return rc;
+    }
     if ((rc = upload_bank(h, mel_bank(p.sr, 512, 128, 0.0, p.fmax), &tb.mel_a))) return rc;
     if ((rc = upload_bank(h, mel_bank(p.sr, 512, 128, 0.0, p.sr / 2.0), &tb.mel_b))) return rc;
     if ((rc = upload_bank(h, mel_bank(p.sr, 512, 64, 0.0, p.sr / 2.0), &tb.mel_c))) return rc;
@@ -439,6 +455,8 @@ int run_chunk(bpc_handle* h, const void* wav, int wav_dtype, int64_t L_in, int n
         timed(10, [&] { launch_seg2048(n, g, h->tb, ws, feats, scalars, st); });
         timed(5, [&] { launch_cens(y, n, g, h->tb, ws, feats, st); });
         timed(8, [&] { launch_lpc(y, n, g, h->tb, ws, feats, st); });
+        timed(6, [&] { launch_time_scalars(y, n, g, h->tb, ws, scalars, status, st); });
+        timed(7, [&] { launch_hilbert(y, n, g, h->tb, ws, scalars, st); });
     } else if (h->timing || !h->multi_stream) {
         timed(1, [&] { launch_stft512(y, n, g, h->tb, ws, st); });
         timed(2, [&] { launch_spec512_consumers(n, g, h->tb, ws, feats, scalars, status, true, st); });

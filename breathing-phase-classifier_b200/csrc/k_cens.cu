@@ -56,7 +56,7 @@ __host__ __device__ constexpr int goff(int o) {          // offset of octave o's
     for (int i = 1; i < o; ++i) off += (16000 >> i) + 2 * kGPad;
     return off;
 }
-constexpr int kDecGlobalFloats = goff(7);                // 18,822 floats per segment
+static_assert(goff(7) == 18822, "1 s layout: 18,822 floats per segment");
 // same layout for a segment of L samples (long mode; L >> 6 is even for L = 16000 d)
 __host__ __device__ inline int goff_len(int o, int L) {
     int off = 0;

@@ -30,14 +30,23 @@ __device__ __forceinline__ float lerp_q(float a, float b, double g) {
     return (float)(g >= 0.5 ? db - (db - da) * (1.0 - g) : da + (db - da) * g);
 }
 
-__global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y, Geometry g, float* scalars,
-                                                    int32_t* status) {
+__global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y, Geometry g, Workspace ws,
+                                                    float* scalars, int32_t* status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TimeBasicSmem& S = *reinterpret_cast<TimeBasicSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x, L = g.L, T = g.T;
     const float* yb = y + (size_t)b * L;
-    if ((L & 3) == 0 && ((size_t)yb & 15) == 0) {
+    // 1 s: the segment is staged in shared memory (TMA bulk copy); long mode reads it from global memory (L2) and keeps
+    // the per-block / per-frame arrays in the segment's scratch region
+    const float* ys = S.y;
+    double* sqv = S.sq; int* czv = S.cz; float* rmsv = S.rms; double* zcrv = S.zcr;
+    if (g.long_mode) {
+        ys = yb;
+        double* d = reinterpret_cast<double*>(ws.scratch + (size_t)b * ws.scratch_stride);
+        sqv = d; d += T + 8; zcrv = d; d += T;
+        czv = reinterpret_cast<int*>(d); rmsv = reinterpret_cast<float*>(czv + T + 8);
+    } else if ((L & 3) == 0 && ((size_t)yb & 15) == 0) {
         stage_segment_tma(S.y, yb, L, (uint64_t*)&S.bar);
     } else {
         for (int i = tid; i < L; i += 256) S.y[i] = yb[i];
@@ -48,7 +57,7 @@ __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y,
     double s1 = 0.0;
     int bad = 0, nonzero = 0;
     for (int i = tid; i < L; i += 256) {
-        const float v = S.y[i];
+        const float v = ys[i];
         s1 += (double)v;
         bad |= !isfinite(v);
         nonzero |= (v != 0.f);
@@ -59,7 +68,7 @@ __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y,
     const double mean = s1 / L;
     double m2 = 0.0, m3 = 0.0, m4 = 0.0;
     for (int i = tid; i < L; i += 256) {
-        const double d = (double)S.y[i] - mean;
+        const double d = (double)ys[i] - mean;
         const double d2 = d * d;
         m2 += d2;
         m3 += d2 * d;
@@ -86,19 +95,19 @@ __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y,
         double sq = 0.0;
         int cz = 0;
         for (int i = 256 * j + lane; i < 256 * j + 256 && i < L; i += 32) {
-            const float v = S.y[i];
+            const float v = ys[i];
             sq += (double)__fmul_rn(v, v);
             if (i >= 1) {
                 // librosa.zero_crossings: values within +-1e-10 are clipped to +0, then signbit comparison
                 const float a = fabsf(v) <= 1e-10f ? 0.f : v;
-                const float pv = S.y[i - 1];
+                const float pv = ys[i - 1];
                 const float p = fabsf(pv) <= 1e-10f ? 0.f : pv;
                 cz += (signbit(a) != signbit(p)) ? 1 : 0;
             }
         }
         sq = warp_sum(sq);
         cz = warp_sum(cz);
-        if (lane == 0) { S.sq[j] = sq; S.cz[j] = cz; }
+        if (lane == 0) { sqv[j] = sq; czv[j] = cz; }
     }
     __syncthreads();
     // frame t covers y[256 (t-4), 256 (t+4)) (frame_length 2048 centred, hop 256)
@@ -106,21 +115,21 @@ __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y,
         double sq = 0.0;
         int cz = 0;
         for (int j = t - 4; j < t + 4; ++j)
-            if (j >= 0 && j < nblk) { sq += S.sq[j]; cz += S.cz[j]; }
+            if (j >= 0 && j < nblk) { sq += sqv[j]; cz += czv[j]; }
         const int first = 256 * (t - 4);                  // first sample of the frame never counts as a crossing
         if (first >= 1 && first < L) {
-            const float v = S.y[first], pv = S.y[first - 1];
+            const float v = ys[first], pv = ys[first - 1];
             const float a = fabsf(v) <= 1e-10f ? 0.f : v, p = fabsf(pv) <= 1e-10f ? 0.f : pv;
             cz -= (signbit(a) != signbit(p)) ? 1 : 0;
         }
-        S.rms[t] = sqrtf((float)(sq / 2048.0));
-        S.zcr[t] = (double)cz / 2048.0;
+        rmsv[t] = sqrtf((float)(sq / 2048.0));
+        zcrv[t] = (double)cz / 2048.0;
     }
     __syncthreads();
     if (warp < 2) {
         double s = 0.0, q = 0.0, mx = -1e300, mn = 1e300;
         for (int t = lane; t < T; t += 32) {
-            const double v = warp == 0 ? (double)S.rms[t] : S.zcr[t];
+            const double v = warp == 0 ? (double)rmsv[t] : zcrv[t];
             s += v;
             q += v * v;
             mx = fmax(mx, v);
@@ -157,12 +166,12 @@ __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y,
             // is kept as four partial histograms (one per warp pair): |y| of a breath sits in a handful of exponent
             // bins, and same-address shared atomics serialise
             for (int i = tid; i < L; i += 256)
-                atomicAdd(&S.hist[warp & 3][__float_as_uint(fabsf(S.y[i])) >> 21], 1u);
+                atomicAdd(&S.hist[warp & 3][__float_as_uint(fabsf(ys[i])) >> 21], 1u);
             __syncthreads();
             for (int i = tid; i < 2048; i += 256) S.hist[0][i] += S.hist[1][i] + S.hist[2][i] + S.hist[3][i];
         } else {
             for (int i = tid; i < L; i += 256) {
-                const unsigned key = __float_as_uint(fabsf(S.y[i]));
+                const unsigned key = __float_as_uint(fabsf(ys[i]));
                 const unsigned hi = key & hi_mask, d = (key >> shifts[pass]) & masks[pass];
                 if (hi == p0) atomicAdd(&S.hist[0][d], 1u);
                 if (hi == p1) atomicAdd(&S.hist[1][d], 1u);
@@ -596,6 +605,212 @@ __global__ void __launch_bounds__(kHilbertThreads, 2) k_hilbert(const float* __r
     }
 }
 
+// =============================================================================================== k_hilbert_long
+// Long mode (L = 16000 d): the same algorithm with the transform in the segment's global scratch region (L2-resident)
+// and a run-time radix plan: N = L / 2 = 2^a 3^b 5^c is walked with radix-5, radix-3, radix-4 and at most one radix-2
+// pass (decimation in frequency forward, the transposed decimation-in-time network for the inverse, so the spectrum
+// is processed where it lies, in digit-reversed order).  float32 throughout, like scipy's transform of float32 input.
+struct HilbertPlan {
+    int n;                 // N = L / 2
+    int npass;
+    int radix[16];
+};
+
+__device__ __forceinline__ void dft2(float2* a) {
+    const float2 t = a[0];
+    a[0] = cadd(t, a[1]);
+    a[1] = csub(t, a[1]);
+}
+__device__ __forceinline__ void dft3(float2* a) {
+    const float c = -0.5f, sn = 0.86602540378443864676f;
+    const float2 t1 = cadd(a[1], a[2]), t2 = csub(a[1], a[2]);
+    const float2 m = make_float2(a[0].x + c * t1.x, a[0].y + c * t1.y);
+    const float2 n = make_float2(sn * t2.x, sn * t2.y);
+    a[0] = cadd(a[0], t1);
+    a[1] = make_float2(m.x + n.y, m.y - n.x);              // m - i n
+    a[2] = make_float2(m.x - n.y, m.y + n.x);              // m + i n
+}
+
+template <int R, bool kDit>
+__device__ __forceinline__ void long_pass(float2* x, int N, int span, const float2* __restrict__ tw, int tid, int nthr) {
+    const int q = span / R, ts = N / span;
+    for (int j = tid; j < N / R; j += nthr) {
+        const int blk = j / q, pos = j - blk * q;
+        const int base = blk * span + pos;
+        float2 a[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) a[r] = x[base + r * q];
+        if (kDit && pos != 0) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) a[r] = cmul(a[r], __ldg(tw + (size_t)r * pos * ts));
+        }
+        if (R == 2) dft2(a);
+        else if (R == 3) dft3(a);
+        else dft_small<R>(a);
+        if (!kDit && pos != 0) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) a[r] = cmul(a[r], __ldg(tw + (size_t)r * pos * ts));
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[base + r * q] = a[r];
+    }
+    __syncthreads();
+}
+
+template <bool kDit>
+__device__ __forceinline__ void long_pass_rt(float2* x, int N, int R, int span, const float2* tw, int tid, int nthr) {
+    switch (R) {
+        case 5: long_pass<5, kDit>(x, N, span, tw, tid, nthr); break;
+        case 4: long_pass<4, kDit>(x, N, span, tw, tid, nthr); break;
+        case 3: long_pass<3, kDit>(x, N, span, tw, tid, nthr); break;
+        default: long_pass<2, kDit>(x, N, span, tw, tid, nthr); break;
+    }
+}
+
+// position of output bin k after the DIF passes of the plan
+__device__ __forceinline__ int plan_pos(const HilbertPlan& P, int k) {
+    int p = 0, s = P.n;
+    for (int i = 0; i < P.npass - 1; ++i) {
+        const int r = P.radix[i];
+        const int d = k % r;
+        k /= r; s /= r;
+        p += d * s;
+    }
+    return p + k;
+}
+
+__global__ void __launch_bounds__(kHilbertThreads) k_hilbert_long(const float* __restrict__ y, Geometry g, Tables tb,
+                                                                  Workspace ws, HilbertPlan P, float* scalars) {
+    __shared__ HilbertTail S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = kHilbertThreads;
+    const int b = blockIdx.x, L = g.L, N = P.n;
+    const float* yb = y + (size_t)b * L;
+    float* base = ws.scratch + (size_t)b * ws.scratch_stride;
+    float2* X = reinterpret_cast<float2*>(base);                               // [N]; later env [L] floats in place
+    int* clist = reinterpret_cast<int*>(base + L);                             // [L / 2] candidate peaks
+    for (int m = tid; m < N; m += NT) X[m] = __ldg(reinterpret_cast<const float2*>(yb) + m);
+    __syncthreads();
+    const float2* tw = tb.tw_long;
+    {
+        int span = N;
+        for (int i = 0; i < P.npass; ++i) { long_pass_rt<false>(X, N, P.radix[i], span, tw, tid, NT); span /= P.radix[i]; }
+    }
+    // same pair processing as k_hilbert: split, G = -i Y on 0 < k < N, inverse split, conj for the forward-as-inverse trick
+    for (int k = tid; k <= N / 2; k += NT) {
+        const int kn = (N - k) % N;
+        const int pk = plan_pos(P, k), pn = plan_pos(P, kn);
+        const float2 zk = X[pk], zn = X[pn];
+        const float2 w = __ldg(tb.ptw_long + k);                               // exp(-2 pi i k / L)
+        const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+        const float2 wo = cmul(w, o);
+        float2 yk = cadd(e, wo);
+        float2 yn = cconj(csub(e, wo));
+        float2 gk = make_float2(yk.y, -yk.x), gn = make_float2(yn.y, -yn.x);
+        if (k == 0) { gk = make_float2(0.f, 0.f); gn = make_float2(0.f, 0.f); }
+        const float2 e2 = make_float2(0.5f * (gk.x + gn.x), 0.5f * (gk.y - gn.y));
+        const float2 d2 = make_float2(0.5f * (gk.x - gn.x), 0.5f * (gk.y + gn.y));
+        const float2 o2 = cmul(d2, cconj(w));
+        const float2 z = make_float2(e2.x - o2.y, e2.y + o2.x);
+        const float2 dn = make_float2(0.5f * (gn.x - gk.x), 0.5f * (gn.y + gk.y));
+        const float2 on = cmul(dn, make_float2(-w.x, -w.y));
+        const float2 zn2 = make_float2(e2.x - on.y, -e2.y + on.x);
+        X[pk] = cconj(z);
+        if (kn != k && k != 0) X[pn] = cconj(zn2);
+    }
+    __syncthreads();
+    {
+        int span = 1;
+        for (int i = P.npass - 1; i >= 0; --i) { span *= P.radix[i]; long_pass_rt<true>(X, N, P.radix[i], span, tw, tid, NT); }
+    }
+    float* env = base;
+    const float inv_n = 1.0f / (float)N;
+    for (int m = tid; m < N; m += NT) {                                         // in place: X[m] -> env[2m], env[2m+1]
+        const float2 o = X[m];
+        const float2 v = __ldg(reinterpret_cast<const float2*>(yb) + m);
+        const float h0 = o.x * inv_n, h1 = -o.y * inv_n;
+        const float e0 = (float)sqrt((double)v.x * (double)v.x + (double)h0 * (double)h0);
+        const float e1 = (float)sqrt((double)v.y * (double)v.y + (double)h1 * (double)h1);
+        env[2 * m] = e0;
+        env[2 * m + 1] = e1;
+    }
+    __syncthreads();
+    double s = 0.0, q = 0.0;
+    for (int i = tid; i < L; i += NT) { const double v = (double)env[i]; s += v; q += v * v; }
+    s = block_sum(s, S.dscratch);
+    q = block_sum(q, S.dscratch);
+    const float emean = (float)(s / L);
+    const float estd = (float)sqrt(fmax(0.0, q / L - (s / L) * (s / L)));
+    constexpr int kGone = -1;
+    const int max_list = L / 2;
+    if (tid == 0) S.best_i = 0;
+    __syncthreads();
+    for (int i = tid + 1; i < L - 1; i += NT) {
+        if (env[i - 1] < env[i]) {
+            int ahead = i + 1;
+            while (ahead < L - 1 && env[ahead] == env[i]) ++ahead;
+            if (env[ahead] < env[i]) {
+                const int mid = (i + ahead - 1) / 2;
+                if (env[mid] >= emean) {
+                    const int slot = atomicAdd(&S.best_i, 1);
+                    if (slot < max_list) clist[slot] = mid;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int nc = min(S.best_i, max_list);
+    __syncthreads();
+    int n_peaks = 0;
+    double hs = 0.0, hq = 0.0;
+    const int max_iter = L / 1600 + 2;                                          // peaks are >= 1600 samples apart
+    for (int iter = 0; iter < max_iter; ++iter) {
+        float bv = -1.f;
+        int bi = -1;
+        for (int j = tid; j < nc; j += NT) {
+            const int i = clist[j];
+            if (i != kGone && (env[i] > bv || (env[i] == bv && i > bi))) { bv = env[i]; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > bv || (ob == bv && oi > bi)) { bv = ob; bi = oi; }
+        }
+        if (lane == 0) { S.fscratch[warp] = bv; S.iscratch[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < NT / 32; ++w)
+                if (S.fscratch[w] > bv || (S.fscratch[w] == bv && S.iscratch[w] > bi)) { bv = S.fscratch[w]; bi = S.iscratch[w]; }
+            S.best_v = bv;
+            S.best_i = bi;
+        }
+        __syncthreads();
+        const int pi = S.best_i;
+        if (pi < 0) break;
+        const float pv = S.best_v;
+        ++n_peaks;
+        hs += (double)pv;
+        hq += (double)pv * (double)pv;
+        for (int j = tid; j < nc; j += NT) {
+            const int i = clist[j];
+            if (i != kGone && i > pi - 1600 && i < pi + 1600) clist[j] = kGone;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        float* sc = scalars + (size_t)b * g.nscal;
+        sc[19] = emean;
+        sc[20] = estd;
+        sc[21] = __fdiv_rn(emean, __fadd_rn(estd, 1e-8f));
+        sc[22] = (float)n_peaks;
+        const double hm = n_peaks > 0 ? hs / n_peaks : 0.0;
+        sc[23] = (float)hm;
+        sc[24] = n_peaks > 1 ? (float)sqrt(fmax(0.0, hq / n_peaks - hm * hm)) : 0.f;
+        ws.ints[b * 2 + 0] = n_peaks;
+    }
+}
+
 // ==================================================================================================== launchers
 void launch_time_scalars(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws,
                          float* scalars, int32_t* status, cudaStream_t st) {
@@ -605,13 +820,24 @@ void launch_time_scalars(const float* y, int n, const Geometry& g, const Tables&
         cudaFuncSetAttribute(k_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AutocorrSmem));
         done = true;
     }
-    k_time_basic<<<n, 256, sizeof(TimeBasicSmem), st>>>(y, g, scalars, status);
+    k_time_basic<<<n, 256, sizeof(TimeBasicSmem), st>>>(y, g, ws, scalars, status);
     k_autocorr<<<n, kAcThreads, sizeof(AutocorrSmem), st>>>(y, g, tb, ws.ints, scalars);
     note_launch(2);
 }
 
 void launch_hilbert(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* scalars,
                     cudaStream_t st) {
+    if (g.long_mode) {
+        HilbertPlan P{};
+        P.n = g.L / 2;
+        int r = P.n;
+        for (int f : {5, 3}) while (r % f == 0) { P.radix[P.npass++] = f; r /= f; }
+        while (r % 4 == 0) { P.radix[P.npass++] = 4; r /= 4; }
+        if (r == 2) { P.radix[P.npass++] = 2; r = 1; }
+        k_hilbert_long<<<n, kHilbertThreads, 0, st>>>(y, g, tb, ws, P, scalars);
+        note_launch();
+        return;
+    }
     const int bytes = (int)(sizeof(float) * 16000 + sizeof(unsigned short) * 16000 + sizeof(HilbertTail));
     static bool done = false;
     if (!done) {

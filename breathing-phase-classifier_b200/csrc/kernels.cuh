@@ -46,6 +46,9 @@ struct Tables {
     const double2* ptw16000;      // exp(-2 pi i k / 16000), k <= 8000
     const float2* tw8000f;        // float32 copies: scipy.signal.hilbert runs a float32 FFT on float32 input
     const float2* ptw16000f;
+    // long mode Hilbert (FFT-N, N = L / 2 = 2^a 3^b 5^c): exp(-2 pi i j / N), j < N and exp(-2 pi i k / L), k <= N
+    const float2* tw_long;
+    const float2* ptw_long;
     // tempogram
     const double* hann384;        // [384]
 };
