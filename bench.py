@@ -305,6 +305,28 @@ def run_ours(args):
         except Exception as e:                           # the side measurement must not take the bench line down
             extras["config5_precompute_plus_forward"] = {"error": repr(e)}
 
+        # BASELINE configs[3]: long-segment sweep, equal total samples per point (B = 4096 / d segments of d seconds)
+        try:
+            sweep = {}
+            for d in (1, 2, 5, 10, 30):
+                Bd = max(1, B // d)
+                e_d = eng if d == 1 else bpc_b200.Engine(device=local, max_batch=Bd,
+                                                         params=bpc_b200.default_params(expected_len=L * d))
+                wd = wav_f32[:Bd * d].reshape(Bd, d * L).contiguous()
+                fd = torch.empty((Bd, 9, 128, e_d.T), dtype=torch.float32, device=dev)
+                sd = torch.empty((Bd, e_d.nscal), dtype=torch.float32, device=dev)
+                td = torch.empty((Bd,), dtype=torch.int32, device=dev)
+                msd = timed(lambda: e_d.precompute(wd, fd, sd, td), 2)
+                sweep[f"{d}s"] = {"segments": Bd, "frames": e_d.T, "ms": msd, "segments_per_s": Bd / (msd * 1e-3),
+                                  "audio_seconds_per_s": Bd * d / (msd * 1e-3),
+                                  "alg_bytes_per_segment": 4 * L * d + 9 * 128 * e_d.T * 4 + 144}
+                if d != 1:
+                    e_d.close()
+                del fd, sd, td
+            extras["config4_long_segment_sweep"] = sweep
+        except Exception as e:
+            extras["config4_long_segment_sweep"] = {"error": repr(e)}
+
         # BASELINE configs[0] through OUR entry point: wav files + CSV rows -> process_dataset_threaded -> .npz files
         # (reader pool -> bpc_precompute_host -> writer pool), next to the same rows into one packed shard
         try:

@@ -503,7 +503,10 @@ int run_chunk(bpc_handle* h, const void* wav, int wav_dtype, int64_t L_in, int n
 int ensure_slots(bpc_handle* h) {
     if (h->slots_ready) return BPC_OK;
     const Geometry& g = h->g;
-    const size_t C = (size_t)h->chunk;
+    const char* env_hc = std::getenv("BPC_HOST_CHUNK");
+    h->host_chunk = env_hc ? std::atoi(env_hc) : std::max(1, h->chunk / 2);
+    if (h->host_chunk < 1 || h->host_chunk > h->chunk) h->host_chunk = h->chunk;
+    const size_t C = (size_t)h->host_chunk;                             // the host path moves pieces of host_chunk segments
     h->slot_wav_bytes = C * (size_t)g.L * 4 * 2;                        // room for L_in up to 2 * L of float32
     const size_t feats_bytes = C * 9 * kPlaneRows * (size_t)g.T * 4, scal_bytes = C * (size_t)g.nscal * 4;
     for (int i = 0; i < kSlots; ++i) {
@@ -539,9 +542,6 @@ int ensure_slots(bpc_handle* h) {
     h->pool = new HostPool(nt - 1);
     const char* env_c = std::getenv("BPC_COMPACT_D2H");
     h->compact_d2h = !(env_c && std::atoi(env_c) == 0);
-    const char* env_hc = std::getenv("BPC_HOST_CHUNK");
-    h->host_chunk = env_hc ? std::atoi(env_hc) : std::max(1, h->chunk / 2);
-    if (h->host_chunk < 1 || h->host_chunk > h->chunk) h->host_chunk = h->chunk;
     const char* env_tp = std::getenv("BPC_TAPER");
     h->taper_tail = !(env_tp && std::atoi(env_tp) == 0);
     h->slots_ready = true;
@@ -609,7 +609,9 @@ int bpc_create(bpc_handle** out, const bpc_params* p, int device, int64_t max_ba
     const char* env_chunk = std::getenv("BPC_CHUNK");
     int chunk = env_chunk ? std::atoi(env_chunk) : 592;               // 4 waves of 148 single-CTA-per-segment kernels
     if (chunk < 1) chunk = 592;
-    if (h->g.long_mode) chunk = std::max(1, chunk / (p->expected_len / 16000));   // same samples (and workspace) per chunk
+    // long mode: about the same samples per chunk, but never below one CTA-per-segment wave of the 148 SMs (workspace:
+    // ~18 MB per 30 s segment)
+    if (h->g.long_mode && !env_chunk) chunk = std::max(148, chunk / (p->expected_len / 16000));
     h->chunk = (int)std::min<int64_t>(chunk, h->max_batch);
     h->launches0 = launches_issued();
     const char* env_streams = std::getenv("BPC_STREAMS");
@@ -689,7 +691,7 @@ int bpc_precompute_host(bpc_handle* h, const void* wav, int wav_dtype, int64_t B
     if (rc) return rc;
     const Geometry& g = h->g;
     const size_t esz = wav_dtype == BPC_WAV_F32 ? 4 : 2;
-    if ((size_t)h->chunk * L_in * esz > h->slot_wav_bytes) { h->err = "L_in too large for the staging buffers"; return BPC_ERR_ARG; }
+    if ((size_t)h->host_chunk * L_in * esz > h->slot_wav_bytes) { h->err = "L_in too large for the staging buffers"; return BPC_ERR_ARG; }
     const size_t seg_feats = (size_t)9 * kPlaneRows * g.T;
     const bool pin_in = is_pinned(wav), pin_f = is_pinned(feats), pin_s = is_pinned(scalars);
     const std::vector<RowRun> runs = live_runs();
@@ -845,7 +847,7 @@ int bpc_modspec(bpc_handle* h, const float* mel_db, int64_t n, float* out, void*
     if (!h) return BPC_ERR_ARG;
     if (!mel_db || !out || n < 0) { h->err = "bpc_modspec: bad argument"; return BPC_ERR_ARG; }
     BPC_CUDA(h, cudaSetDevice(h->device));
-    if (n > 0) launch_modspec((int)n, h->g, h->tb, mel_db, out, static_cast<cudaStream_t>(stream));
+    if (n > 0) launch_modspec((int)n, h->g, h->tb, h->ws, mel_db, out, static_cast<cudaStream_t>(stream));
     BPC_CUDA(h, cudaGetLastError());
     return BPC_OK;
 }

@@ -222,38 +222,40 @@ __device__ void dct_mel40(const float* __restrict__ Dg, const float* P, int T, f
 
 // C2[k*T + u] = sum_t DT[u][t] * C1[k*T + t] (ortho DCT-II along time); DTs is the transposed matrix [t][u] staged in
 // shared memory.  Same 5 x 2 register tile; float32 partial sums over 16 t combined in float64.
-__device__ void dct_time40(const float* DTs, const float* C1, int T, float* C2) {
+__device__ __forceinline__ void dct_time40_tile(const float* DTs, const float* C1, int T, float* C2, int ub0) {
     const int kb = threadIdx.x >> 5, up = threadIdx.x & 31;
-    for (int ub0 = 0; ub0 < T; ub0 += 64) {                    // one pass per 64 output columns
-        const int u0 = ub0 + 2 * up, u1 = min(u0 + 1, T - 1);
-        if (kb < 8 && u0 < T) {
-            double acc[5][2];
-            float part[5][2];
+    const int u0 = ub0 + 2 * up, u1 = min(u0 + 1, T - 1);
+    if (kb < 8 && u0 < T) {
+        double acc[5][2];
+        float part[5][2];
 #pragma unroll
-            for (int i = 0; i < 5; ++i) { acc[i][0] = acc[i][1] = 0.0; part[i][0] = part[i][1] = 0.f; }
-            for (int t = 0; t < T; ++t) {
-                const float d0 = DTs[(size_t)t * T + u0], d1 = DTs[(size_t)t * T + u1];
-#pragma unroll
-                for (int i = 0; i < 5; ++i) {
-                    const float c = C1[(5 * kb + i) * T + t];
-                    part[i][0] = fmaf(d0, c, part[i][0]);
-                    part[i][1] = fmaf(d1, c, part[i][1]);
-                }
-                if ((t & 15) == 15) {
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) {
-                        acc[i][0] += (double)part[i][0]; acc[i][1] += (double)part[i][1];
-                        part[i][0] = part[i][1] = 0.f;
-                    }
-                }
-            }
+        for (int i = 0; i < 5; ++i) { acc[i][0] = acc[i][1] = 0.0; part[i][0] = part[i][1] = 0.f; }
+        for (int t = 0; t < T; ++t) {
+            const float d0 = DTs[(size_t)t * T + u0], d1 = DTs[(size_t)t * T + u1];
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
-                C2[(5 * kb + i) * T + u0] = (float)(acc[i][0] + (double)part[i][0]);
-                if (u0 + 1 < T) C2[(5 * kb + i) * T + u0 + 1] = (float)(acc[i][1] + (double)part[i][1]);
+                const float c = C1[(5 * kb + i) * T + t];
+                part[i][0] = fmaf(d0, c, part[i][0]);
+                part[i][1] = fmaf(d1, c, part[i][1]);
+            }
+            if ((t & 15) == 15) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    acc[i][0] += (double)part[i][0]; acc[i][1] += (double)part[i][1];
+                    part[i][0] = part[i][1] = 0.f;
+                }
             }
         }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            C2[(5 * kb + i) * T + u0] = (float)(acc[i][0] + (double)part[i][0]);
+            if (u0 + 1 < T) C2[(5 * kb + i) * T + u0 + 1] = (float)(acc[i][1] + (double)part[i][1]);
+        }
     }
+}
+
+__device__ void dct_time40(const float* DTs, const float* C1, int T, float* C2) {
+    for (int ub0 = 0; ub0 < T; ub0 += 64) dct_time40_tile(DTs, C1, T, C2, ub0);   // one pass per 64 output columns
     __syncthreads();
 }
 
@@ -332,6 +334,8 @@ __device__ void role_mel(int b, const Geometry g, const Tables& tb, const Worksp
 
     // mod_spec (methods.py:142-143): DCT-II ortho over mel (keep 40), then over time
     dct_mel40(tb.dct_mel, P, T, C1);
+    // long mode: the [40 x T] . [T x T] time DCT is spread over a (column tile, segment) grid by the next two kernels
+    if (g.long_mode) return;
     dct_time40(DTs, C1, T, C2);
     if (ws.dbg_mod) {
         float* d = ws.dbg_mod + (size_t)b * 40 * T;
@@ -547,6 +551,29 @@ __global__ void __launch_bounds__(256) k_spec512_consumers(Geometry g, Tables tb
     }
 }
 
+// long mode: C2[40, 64-column tile] = C1[40, T] . DT[T, tile]; C1 / C2 live in role 0's scratch region
+__global__ void __launch_bounds__(256) k_modspec_time_long(Geometry g, Tables tb, Workspace ws) {
+    const int b = blockIdx.y, T = g.T;
+    float* base = ws.scratch + (size_t)b * ws.scratch_stride + consumer_role_offset(0, T);
+    dct_time40_tile(tb.dct_time, base + (size_t)kPlaneRows * T, T, base + (size_t)(kPlaneRows + 40) * T, 64 * blockIdx.x);
+}
+
+__global__ void __launch_bounds__(256) k_modspec_finish_long(Geometry g, Workspace ws, float* feats) {
+    __shared__ double dscratch[32];
+    __shared__ float fscratch[32];
+    const int b = blockIdx.x, T = g.T, NP = kPlaneRows * T;
+    const float* C2 = ws.scratch + (size_t)b * ws.scratch_stride + consumer_role_offset(0, T) + (size_t)(kPlaneRows + 40) * T;
+    if (ws.dbg_mod) {
+        float* d = ws.dbg_mod + (size_t)b * 40 * T;
+        for (int i = threadIdx.x; i < 40 * T; i += blockDim.x) d[i] = C2[i];
+    }
+    float mn;
+    const ZTerm zm = zterm_of(C2, 40 * T, dscratch, fscratch, &mn);
+    const float fill = zm(mn);                                         // pad_freq: min of the normalised array
+    float* om = plane_ptr(feats, b, BPC_CH_MOD_SPEC, T);
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) om[i] = (i < 40 * T) ? zm(C2[i]) : fill;
+}
+
 static void set_consumer_smem() {
     static bool done = false;
     if (!done) {
@@ -572,6 +599,11 @@ void launch_spec512_consumers(int n, const Geometry& g, const Tables& tb, const 
     k_spec512_consumers<<<dim3(n, with_chroma ? 2 : 1), 256, g.long_mode ? 0 : kLightSmemFloats * sizeof(float), st>>>(
         g, tb, ws, feats, scalars, status, nullptr, 2);
     note_launch(2);
+    if (g.long_mode) {
+        k_modspec_time_long<<<dim3((g.T + 63) / 64, n), 256, 0, st>>>(g, tb, ws);
+        k_modspec_finish_long<<<n, 256, 0, st>>>(g, ws, feats);
+        note_launch(2);
+    }
 }
 
 void launch_logmel_only(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* mel3, cudaStream_t st) {
@@ -599,7 +631,36 @@ __global__ void __launch_bounds__(256) k_stft_db(Geometry g, const float* __rest
     for (int i = threadIdx.x; i < 257 * T; i += blockDim.x) o[i] = sP[i];
 }
 
+// long mode: the [257, T] tile does not fit on chip; two sweeps over the magnitudes (L2-resident) instead.  Same float32
+// operations as power_to_db_inplace (the clamp floor follows from the maximum power because 10 log10 is monotone).
+__global__ void __launch_bounds__(256) k_stft_db_long(Geometry g, const float* __restrict__ mag, float* __restrict__ out) {
+    __shared__ float fscratch[32];
+    const int b = blockIdx.x, T = g.T;
+    const float* mag_b = mag + (size_t)b * T * kMagStride;
+    float mx = -FLT_MAX;
+    for (int idx = threadIdx.x; idx < 257 * T; idx += blockDim.x) {
+        const int t = idx / 257, k = idx - t * 257;
+        const float v = __ldg(mag_b + (size_t)t * kMagStride + k);
+        mx = fmaxf(mx, __fmul_rn(v, v));
+    }
+    mx = block_max(mx, fscratch);
+    const float ref_db = (float)(10.0 * log10((double)fmaxf(1e-10f, mx)));
+    const float vmax = __fsub_rn(__fmul_rn(10.0f, log10f(fmaxf(1e-10f, mx))), ref_db);
+    const float floor_db = __fsub_rn(vmax, 80.0f);
+    float* o = out + (size_t)b * 257 * T;
+    for (int i = threadIdx.x; i < 257 * T; i += blockDim.x) {
+        const int k = i / T, t = i - k * T;
+        const float v = __ldg(mag_b + (size_t)t * kMagStride + k);
+        o[i] = fmaxf(__fsub_rn(__fmul_rn(10.0f, log10f(fmaxf(1e-10f, __fmul_rn(v, v)))), ref_db), floor_db);
+    }
+}
+
 void launch_stft_db(int n, const Geometry& g, const Workspace& ws, float* stft_db, cudaStream_t st) {
+    if (g.long_mode) {
+        k_stft_db_long<<<n, 256, 0, st>>>(g, ws.mag512, stft_db);
+        note_launch();
+        return;
+    }
     const int bytes = 257 * g.T * (int)sizeof(float);
     static bool done = false;
     if (!done) {
@@ -627,7 +688,33 @@ __global__ void __launch_bounds__(256) k_modspec(Geometry g, Tables tb, const fl
     for (int i = threadIdx.x; i < 40 * T; i += blockDim.x) out[(size_t)b * 40 * T + i] = C2[i];
 }
 
-void launch_modspec(int n, const Geometry& g, const Tables& tb, const float* mel_db, float* out, cudaStream_t st) {
+// long mode: mel_db -> role 0's scratch region -> mel DCT there; the tiled time DCT follows; then C2 is copied out
+__global__ void __launch_bounds__(256) k_modspec_long_in(Geometry g, Tables tb, Workspace ws, const float* __restrict__ mel_db) {
+    const int T = g.T, NP = kPlaneRows * T, b = blockIdx.x;
+    float* P = ws.scratch + (size_t)b * ws.scratch_stride + consumer_role_offset(0, T);
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) P[i] = mel_db[(size_t)b * NP + i];
+    __syncthreads();
+    dct_mel40(tb.dct_mel, P, T, P + NP);
+}
+__global__ void __launch_bounds__(256) k_modspec_long_out(Geometry g, Workspace ws, float* __restrict__ out) {
+    const int T = g.T, b = blockIdx.x;
+    const float* C2 = ws.scratch + (size_t)b * ws.scratch_stride + consumer_role_offset(0, T) + (size_t)(kPlaneRows + 40) * T;
+    for (int i = threadIdx.x; i < 40 * T; i += blockDim.x) out[(size_t)b * 40 * T + i] = C2[i];
+}
+
+void launch_modspec(int n, const Geometry& g, const Tables& tb, const Workspace& ws, const float* mel_db, float* out,
+                    cudaStream_t st) {
+    if (g.long_mode) {
+        for (int off = 0; off < n; off += ws.cap) {                    // the scratch region holds ws.cap segments
+            const int m = n - off < ws.cap ? n - off : ws.cap;
+            const size_t NP = (size_t)kPlaneRows * g.T;
+            k_modspec_long_in<<<m, 256, 0, st>>>(g, tb, ws, mel_db + off * NP);
+            k_modspec_time_long<<<dim3((g.T + 63) / 64, m), 256, 0, st>>>(g, tb, ws);
+            k_modspec_long_out<<<m, 256, 0, st>>>(g, ws, out + (size_t)off * 40 * g.T);
+            note_launch(3);
+        }
+        return;
+    }
     set_consumer_smem();
     static bool done = false;
     if (!done) {

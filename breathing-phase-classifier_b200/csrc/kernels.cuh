@@ -114,7 +114,8 @@ void launch_lpc(const float* y, int n, const Geometry& g, const Tables& tb, cons
 void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
                  cudaStream_t st);
 void launch_stats(int n, const Geometry& g, const float* feats, const float* scalars, double* acc, cudaStream_t st);
-void launch_modspec(int n, const Geometry& g, const Tables& tb, const float* mel_db, float* out, cudaStream_t st);
+void launch_modspec(int n, const Geometry& g, const Tables& tb, const Workspace& ws, const float* mel_db, float* out,
+                    cudaStream_t st);
 void launch_pad_scalars(int n, const Geometry& g, float* scalars, cudaStream_t st);
 
 void launch_collate(const float* store_feats, const float* store_scalars, const long long* ia, const long long* ib,

@@ -387,3 +387,64 @@ def test_process_and_save_npz_from_two_threads(tmp_path, torch_cuda):
         assert all(np.array_equal(x[k], y[k]) for k in x.files)
     fid, ok, err = PR.process_and_save_npz(("nope", str(audio / "nope.wav"), str(b)))     # process.py:107-108
     assert fid == "nope" and ok is False and isinstance(err, str) and err
+
+
+@pytest.mark.parametrize("d,n", [(2, 4), (5, 2)])
+def test_long_segments_match_oracle(torch_cuda, d, n):
+    """BASELINE config 4: expected_len = 16000 d (long mode) against the oracle run with Params(duration=d); same
+    tolerances as the 1 s path."""
+    import gpu_check_long
+    r = gpu_check_long.compare(d, n, verbose=False)
+    w = r["worst"]
+    assert w["mel_db"] < 1e-3 and w["onset_env"] < 1e-4 and w["gammatone_raw"] < 1e-5 and w["lpc_raw"] < 1e-5
+    for k, v in w.items():
+        if k.startswith("ch:"):
+            assert v < 2e-4, (k, v)
+    assert r["ints_ok"] == n and r["tun"] == [n, n] and int(np.abs(r["status"]).sum()) == 0
+    assert float(np.max(r["scal_rel"])) < 1e-4, r["scal_rel"]
+
+
+def test_long_segments_30s_properties(torch_cuda):
+    """d = 30 (T = 1876, Hilbert FFT of length 240000 = 2^6 3 5^4): too slow for the oracle's O(L^2) correlate, so the
+    checks are size-independent: host and device paths agree bit for bit, a repeat is identical, planes are finite,
+    z-scored planes have zero mean / unit variance, a 30 s segment made of one tiled second has period-1 s statistics."""
+    torch = torch_cuda
+    import bpc_b200
+    from bpc_b200.synth import synth_batch_pcm16
+    d = 30
+    eng = bpc_b200.Engine(device=0, max_batch=8, params=bpc_b200.default_params(expected_len=16000 * d))
+    assert eng.T == 1876
+    sec = synth_batch_pcm16(300, 3 * d).reshape(3, d * 16000)
+    f, s, st = eng.precompute(torch.from_numpy(sec).cuda())
+    f2, s2, _ = eng.precompute(torch.from_numpy(sec).cuda())
+    assert torch.equal(f, f2) and torch.equal(s, s2) and int(st.abs().sum()) == 0
+    assert bool(torch.isfinite(f).all()) and bool(torch.isfinite(s).all())
+    hf, hs, hst = eng.precompute_host(sec)
+    assert np.array_equal(hf, f.cpu().numpy()) and np.array_equal(hs, s.cpu().numpy())
+    m = f[:, 3:6].double()
+    assert float(m.mean(dim=(2, 3)).abs().max()) < 1e-4 and float((m.std(dim=(2, 3), unbiased=False) - 1).abs().max()) < 1e-4
+    assert float(s[:, 22].min()) >= 1 and float(s[:, 22].max()) <= d * 10 + 1          # peaks are >= 0.1 s apart
+    assert float(s[:, 35].max()) < 800 / 16000
+    eng.close()
+
+
+def test_long_mode_stage_and_modspec_entry_points(torch_cuda):
+    """bpc_stage_logmel (config 2 outputs) and bpc_modspec on 3 s segments against the oracle."""
+    torch = torch_cuda
+    import bpc_b200
+    import gpu_check_long
+    from oracle import pipeline as P
+    d = 3
+    p = P.Params(duration=float(d))
+    eng = bpc_b200.Engine(device=0, max_batch=8, params=bpc_b200.default_params(expected_len=16000 * d))
+    Y = np.stack([gpu_check_long.long_segment(40 + i, d) for i in range(3)])
+    stft_db, mel3 = eng.stage_logmel(torch.from_numpy(Y).cuda(), want_stft=True)
+    for i in range(len(Y)):
+        ref_db, ref3 = P.logmel_stage(Y[i], p)
+        assert np.abs(stft_db[i].cpu().numpy() - ref_db).max() < 1e-3
+        assert np.abs(mel3[i].cpu().numpy() - ref3).max() < 2e-4
+        dbg = {}
+        P.segment_features(Y[i], p, debug=dbg)
+        got = eng.modspec(dbg["mel_db"][None])[0]
+        assert got.shape == (40, eng.T) and np.abs(got - P.modulation_frames(dbg["mel_db"])).max() < 1.2e-2
+    eng.close()

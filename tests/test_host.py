@@ -49,11 +49,15 @@ def test_create_fails_loudly_without_gpu():
 
 
 def test_unsupported_params_are_rejected():
+    # expected_len = 16000 d with d = 2^a 3^b 5^c <= 32 is the long mode (BASELINE config 4); anything else is refused
+    for bad in (16000 * 7, 16000 * 33, 24000, 0):
+        p = bpc_b200.default_params(expected_len=bad)
+        h = ctypes.c_void_p()
+        rc = bpc_b200.lib().bpc_create(ctypes.byref(h), ctypes.byref(p), 0, 16)
+        assert rc == -4 and not h.value, bad
+        assert b"expected_len" in bpc_b200.lib().bpc_last_error(None)
     p = bpc_b200.default_params(expected_len=32000)
-    h = ctypes.c_void_p()
-    rc = bpc_b200.lib().bpc_create(ctypes.byref(h), ctypes.byref(p), 0, 16)
-    assert rc == -4 and not h.value
-    assert b"expected_len" in bpc_b200.lib().bpc_last_error(None)
+    assert bpc_b200.lib().bpc_num_frames(ctypes.byref(p)) == 126
 
 
 @pytest.mark.parametrize("name,args", [("mel_a", (512, 128, 4500.0)), ("mel_b", (512, 128, 8000.0)),
