@@ -190,6 +190,7 @@ struct CensSmem {
     float fscratch[32];
 };
 
+template <bool LONG>
 __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restrict__ y, Geometry g, Tables tb,
                                                           Workspace ws, float* feats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -201,9 +202,9 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
     const float* G = ws.dec + (size_t)b * cens_dec_stride(ws);
     // [12, T] tiles: shared memory (1 s), the segment's global scratch region in long mode
     float* lbase = ws.scratch + (size_t)b * ws.scratch_stride;
-    float* p_csum = g.long_mode ? lbase : S.csum;
-    float* p_chroma = g.long_mode ? lbase + 12 * (size_t)T : S.u.post.chroma;
-    float* p_quant = g.long_mode ? lbase + 24 * (size_t)T : S.u.post.quant;
+    float* p_csum = LONG ? lbase : S.csum;
+    float* p_chroma = LONG ? lbase + 12 * (size_t)T : S.u.post.chroma;
+    float* p_quant = LONG ? lbase + 24 * (size_t)T : S.u.post.quant;
 
     // ---- stage the basis of this segment's tuning and the smoothing window
     const int tun = ws.tuning[b * 2 + 1];
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
                 }
             } else {
                 // c0 >= -128 complex samples = -kGPad samples: the zero pads are the centre padding
-                const float2* src = reinterpret_cast<const float2*>(G + (g.long_mode ? goff_len(o, L) : goff(o)) + kGPad) + c0 + h;
+                const float2* src = reinterpret_cast<const float2*>(G + (LONG ? goff_len(o, L) : goff(o)) + kGPad) + c0 + h;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float2 v = __ldg(src + 16 * j);
@@ -364,7 +365,8 @@ void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, con
     static bool done = false;
     if (!done) {
         cudaFuncSetAttribute(k_cens_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
-        cudaFuncSetAttribute(k_cens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CensSmem));
+        cudaFuncSetAttribute(k_cens<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CensSmem));
+        cudaFuncSetAttribute(k_cens<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CensSmem));
         done = true;
     }
     if (g.long_mode) {
@@ -383,7 +385,8 @@ void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, con
     } else {
         k_cens_dec<<<n, kDecThreads, sizeof(DecSmem), st>>>(y, g, ws);
     }
-    k_cens<<<n, kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats);
+    if (g.long_mode) k_cens<true><<<n, kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats);
+    else k_cens<false><<<n, kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats);
     note_launch(2);
 }
 

@@ -63,6 +63,7 @@ __device__ __forceinline__ void burg_all(double (&F)[kLpcPer], double (&B)[kLpcP
     }
 }
 
+template <bool LONG>
 __global__ void __launch_bounds__(kLpcThreads, 4) k_lpc(const float* __restrict__ y, Geometry g, Tables tb, Workspace ws,
                                                 float* feats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(kLpcThreads, 4) k_lpc(const float* __restrict_
     const int b = blockIdx.x, L = g.L, T = g.T, F_ = g.lpc_frames;
     const float* yb = y + (size_t)b * L;
     // [12, F] coefficients: shared memory (1 s: F = 98), the segment's global scratch region in long mode
-    float* coef = g.long_mode ? ws.scratch + (size_t)b * ws.scratch_stride : S.coef;
+    float* coef = LONG ? ws.scratch + (size_t)b * ws.scratch_stride : S.coef;
 
     for (int fr = warp; fr < F_; fr += kLpcThreads / 32) {
         const int start = fr * kLpcShift;
@@ -132,10 +133,12 @@ void launch_lpc(const float* y, int n, const Geometry& g, const Tables& tb, cons
                 cudaStream_t st) {
     static bool done = false;
     if (!done) {
-        cudaFuncSetAttribute(k_lpc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpcSmem));
+        cudaFuncSetAttribute(k_lpc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpcSmem));
+        cudaFuncSetAttribute(k_lpc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpcSmem));
         done = true;
     }
-    k_lpc<<<n, kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats);
+    if (g.long_mode) k_lpc<true><<<n, kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats);
+    else k_lpc<false><<<n, kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats);
     note_launch();
 }
 

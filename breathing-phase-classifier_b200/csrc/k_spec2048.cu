@@ -270,6 +270,7 @@ struct Seg2048Smem {
 
 __device__ __forceinline__ void group_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+template <bool LONG>
 __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, Workspace ws, float* feats,
                                                           float* scalars) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
     float* sc = scalars + (size_t)b * g.nscal;
     // per-segment arrays: shared memory for 1 s segments, the segment's global scratch region in long mode
     struct { float *melD, *tg; double *peak, *valley, *cent, *bw, *flat, *sumv, *sumq; float *onset, *flux, *ac0; } V;
-    if (g.long_mode) {
+    if (LONG) {
         double* d = reinterpret_cast<double*>(ws.scratch + (size_t)b * ws.scratch_stride);
         V.peak = d; d += 7 * T; V.valley = d; d += 7 * T; V.cent = d; d += T; V.bw = d; d += T; V.flat = d; d += T;
         V.sumv = d; d += T; V.sumq = d; d += T;
@@ -496,6 +497,7 @@ struct Even2048Smem {
     int hist[100];
 };
 
+template <bool LONG>
 __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspace ws, float* scalars,
                                                   int32_t* status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -503,12 +505,12 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x, T = g.T, TE = (T + 1) / 2;
     // candidate lists and per-frame arrays: shared memory (1 s), the segment's global scratch region in long mode
-    const int cap = g.long_mode ? 492 * TE : kMaxCand;
+    const int cap = LONG ? 492 * TE : kMaxCand;
     float* lbase = ws.scratch + (size_t)b * ws.scratch_stride;
-    float* cand_mag = g.long_mode ? lbase : E.cand_mag;
-    float* cand_pitch = g.long_mode ? lbase + cap : E.cand_pitch;
-    float* colmax = g.long_mode ? lbase + 2 * (size_t)cap : E.colmax;
-    float* roll = g.long_mode ? colmax + TE : E.roll;
+    float* cand_mag = LONG ? lbase : E.cand_mag;
+    float* cand_pitch = LONG ? lbase + cap : E.cand_pitch;
+    float* colmax = LONG ? lbase + 2 * (size_t)cap : E.colmax;
+    float* roll = LONG ? colmax + TE : E.roll;
     float* sortbuf = E.sortbuf;
     int* hist = E.hist;
     __shared__ int s_ncand;
@@ -609,7 +611,8 @@ void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb,
     static int sms = 148;
     if (!done) {
         cudaFuncSetAttribute(k_frame2048, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2Warps * kF2RowBytes);
-        cudaFuncSetAttribute(k_seg2048, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Seg2048Smem));
+        cudaFuncSetAttribute(k_seg2048<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Seg2048Smem));
+        cudaFuncSetAttribute(k_seg2048<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Seg2048Smem));
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -625,7 +628,8 @@ void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb,
 
 void launch_seg2048(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats, float* scalars,
                     cudaStream_t st) {
-    k_seg2048<<<n, kSegThreads, sizeof(Seg2048Smem), st>>>(g, tb, ws, feats, scalars);
+    if (g.long_mode) k_seg2048<true><<<n, kSegThreads, sizeof(Seg2048Smem), st>>>(g, tb, ws, feats, scalars);
+    else k_seg2048<false><<<n, kSegThreads, sizeof(Seg2048Smem), st>>>(g, tb, ws, feats, scalars);
     note_launch();
 }
 
@@ -633,10 +637,12 @@ void launch_even2048(int n, const Geometry& g, const Tables& tb, const Workspace
                      int32_t* status, cudaStream_t st) {
     static bool done = false;
     if (!done) {
-        cudaFuncSetAttribute(k_even2048, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Even2048Smem));
+        cudaFuncSetAttribute(k_even2048<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Even2048Smem));
+        cudaFuncSetAttribute(k_even2048<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Even2048Smem));
         done = true;
     }
-    k_even2048<<<n, 256, sizeof(Even2048Smem), st>>>(g, tb, ws, scalars, status);
+    if (g.long_mode) k_even2048<true><<<n, 256, sizeof(Even2048Smem), st>>>(g, tb, ws, scalars, status);
+    else k_even2048<false><<<n, 256, sizeof(Even2048Smem), st>>>(g, tb, ws, scalars, status);
     note_launch();
 }
 

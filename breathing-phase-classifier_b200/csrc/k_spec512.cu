@@ -230,8 +230,10 @@ __device__ __forceinline__ void dct_time40_tile(const float* DTs, const float* C
         float part[5][2];
 #pragma unroll
         for (int i = 0; i < 5; ++i) { acc[i][0] = acc[i][1] = 0.0; part[i][0] = part[i][1] = 0.f; }
-        for (int t = 0; t < T; ++t) {
-            const float d0 = DTs[(size_t)t * T + u0], d1 = DTs[(size_t)t * T + u1];
+        const float* dp = DTs + u0;
+        const int du = u1 - u0;
+        for (int t = 0; t < T; ++t, dp += T) {
+            const float d0 = dp[0], d1 = dp[du];
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
                 const float c = C1[(5 * kb + i) * T + t];
@@ -281,18 +283,19 @@ __device__ ZTerm zterm_of(const float* a, int n, double* dscratch, float* fscrat
 }
 
 // ------------------------------------------------------------------------------------------- role 0: mel3+mod
+template <bool LONG>
 __device__ void role_mel(int b, const Geometry g, const Tables& tb, const Workspace& ws, float* feats, float* mel3,
                          float* smem, double* dscratch, float* fscratch) {
     // `smem` is the role's private array space: shared memory for 1 s segments, a per-segment global scratch region in
-    // long mode (g.long_mode), where the time DCT matrix is also read from its global table instead of being staged
+    // long mode (LONG), where the time DCT matrix is also read from its global table instead of being staged
     const int T = g.T, NP = kPlaneRows * T;
     float* P = smem;                 // [128*T] mel power -> mel_db
     float* C1 = P + NP;              // [40*T]
     float* C2 = C1 + 40 * T;         // [40*T]
-    const float* DTs = g.long_mode ? tb.dct_time : C2 + 40 * T;      // [T*T] DCT matrix (time axis), transposed
+    const float* DTs = LONG ? tb.dct_time : C2 + 40 * T;      // [T*T] DCT matrix (time axis), transposed
     const float* mag_b = ws.mag512 + (size_t)b * T * kMagStride;
 
-    if (!mel3 && !g.long_mode) stage_matrix(C2 + 40 * T, tb.dct_time, T * T);
+    if (!mel3 && !LONG) stage_matrix(C2 + 40 * T, tb.dct_time, T * T);
     apply_bank<128>(tb.mel_a, mag_b, T, true, P);
     power_to_db_inplace(P, NP, true, fscratch);                      // process.py:33
     if (ws.dbg_mel_db) {
@@ -335,7 +338,7 @@ __device__ void role_mel(int b, const Geometry g, const Tables& tb, const Worksp
     // mod_spec (methods.py:142-143): DCT-II ortho over mel (keep 40), then over time
     dct_mel40(tb.dct_mel, P, T, C1);
     // long mode: the [40 x T] . [T x T] time DCT is spread over a (column tile, segment) grid by the next two kernels
-    if (g.long_mode) return;
+    if (LONG) return;
     dct_time40(DTs, C1, T, C2);
     if (ws.dbg_mod) {
         float* d = ws.dbg_mod + (size_t)b * 40 * T;
@@ -349,6 +352,7 @@ __device__ void role_mel(int b, const Geometry g, const Tables& tb, const Worksp
 }
 
 // ----------------------------------------------------------------------------------------------- role 1: mfcc
+template <bool LONG>
 __device__ void role_mfcc(int b, const Geometry g, const Tables& tb, const Workspace& ws, float* feats, float* smem,
                           double* dscratch, float* fscratch) {
     const int T = g.T, NP = kPlaneRows * T;
@@ -389,6 +393,7 @@ __device__ void role_mfcc(int b, const Geometry g, const Tables& tb, const Works
 }
 
 // ------------------------------------------------------------------------------------------ role 2: gammatone
+template <bool LONG>
 __device__ void role_gammatone(int b, const Geometry g, const Tables& tb, const Workspace& ws, float* feats,
                                float* smem, double* dscratch, float* fscratch) {
     const int T = g.T, NP = kPlaneRows * T, NG = tb.mel_c.rows * T;
@@ -409,17 +414,18 @@ __device__ void role_gammatone(int b, const Geometry g, const Tables& tb, const 
 }
 
 // ------------------------------------------------------------------------------------------ role 3: chroma_stft
+template <bool LONG>
 __device__ void role_chroma_stft(int b, const Geometry g, const Tables& tb, const Workspace& ws, float* feats,
                                  float* scalars, int32_t* status, float* smem, double* dscratch, float* fscratch) {
     const int T = g.T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     // candidate capacity: kMaxCand in shared memory, every (bin, frame) pair in long mode (global scratch)
-    const int cap = g.long_mode ? 123 * T : kMaxCand;
+    const int cap = LONG ? 123 * T : kMaxCand;
     float* cand_mag = smem;                       // [cap]
     float* cand_pitch = cand_mag + cap;           // [cap]
     float* sortbuf = cand_pitch + cap;            // [kMaxCand] (the selection needs 516 words)
     float* colmax = sortbuf + kMaxCand;           // [T] (64 in shared memory)
-    float* raw = colmax + (g.long_mode ? T : 64); // [12*T]
+    float* raw = colmax + (LONG ? T : 64); // [12*T]
     int* hist = (int*)(raw + 12 * T);             // [100]
     __shared__ int s_ncand;
     const float* mag_b = ws.mag512 + (size_t)b * T * kMagStride;
@@ -534,6 +540,7 @@ size_t consumer_scratch_floats(int T) {
     return consumer_role_offset(3, T) + (size_t)2 * 123 * T + kMaxCand + (size_t)13 * T + 128;
 }
 
+template <bool LONG>
 __global__ void __launch_bounds__(256) k_spec512_consumers(Geometry g, Tables tb, Workspace ws, float* feats,
                                                            float* scalars, int32_t* status, float* mel3,
                                                            int role_base) {
@@ -542,12 +549,13 @@ __global__ void __launch_bounds__(256) k_spec512_consumers(Geometry g, Tables tb
     __shared__ float fscratch[32];
     const int b = blockIdx.x;
     const int role = blockIdx.y + role_base;
-    float* smem = g.long_mode ? ws.scratch + (size_t)b * ws.scratch_stride + consumer_role_offset(role, g.T) : smem_dyn;
+    // LONG is a template parameter so that the 1 s instantiation keeps provable shared-memory addressing (LDS / STS)
+    float* smem = LONG ? ws.scratch + (size_t)b * ws.scratch_stride + consumer_role_offset(role, g.T) : smem_dyn;
     switch (role) {
-        case 0: role_mel(b, g, tb, ws, feats, mel3, smem, dscratch, fscratch); break;
-        case 1: role_mfcc(b, g, tb, ws, feats, smem, dscratch, fscratch); break;
-        case 2: role_gammatone(b, g, tb, ws, feats, smem, dscratch, fscratch); break;
-        default: role_chroma_stft(b, g, tb, ws, feats, scalars, status, smem, dscratch, fscratch); break;
+        case 0: role_mel<LONG>(b, g, tb, ws, feats, mel3, smem, dscratch, fscratch); break;
+        case 1: role_mfcc<LONG>(b, g, tb, ws, feats, smem, dscratch, fscratch); break;
+        case 2: role_gammatone<LONG>(b, g, tb, ws, feats, smem, dscratch, fscratch); break;
+        default: role_chroma_stft<LONG>(b, g, tb, ws, feats, scalars, status, smem, dscratch, fscratch); break;
     }
 }
 
@@ -577,7 +585,7 @@ __global__ void __launch_bounds__(256) k_modspec_finish_long(Geometry g, Workspa
 static void set_consumer_smem() {
     static bool done = false;
     if (!done) {
-        cudaFuncSetAttribute(k_spec512_consumers, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(k_spec512_consumers<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kConsumerSmemFloats * (int)sizeof(float));
         done = true;
     }
@@ -589,15 +597,21 @@ void launch_spec512_consumers(int n, const Geometry& g, const Tables& tb, const 
     static const char* only = std::getenv("BPC_ONLY_ROLE");      // profiling aid: time one role (outputs incomplete)
     if (only) {
         const int r = std::atoi(only);
-        k_spec512_consumers<<<dim3(n, 1), 256, g.long_mode ? 0 : (r < 2 ? kConsumerSmemFloats : kLightSmemFloats) * sizeof(float), st>>>(
+        if (g.long_mode) k_spec512_consumers<true><<<dim3(n, 1), 256, 0, st>>>(g, tb, ws, feats, scalars, status, nullptr, r);
+        else k_spec512_consumers<false><<<dim3(n, 1), 256, (r < 2 ? kConsumerSmemFloats : kLightSmemFloats) * sizeof(float), st>>>(
             g, tb, ws, feats, scalars, status, nullptr, r);
         note_launch();
         return;
     }
-    k_spec512_consumers<<<dim3(n, 2), 256, g.long_mode ? 0 : kConsumerSmemFloats * sizeof(float), st>>>(
-        g, tb, ws, feats, scalars, status, nullptr, 0);
-    k_spec512_consumers<<<dim3(n, with_chroma ? 2 : 1), 256, g.long_mode ? 0 : kLightSmemFloats * sizeof(float), st>>>(
-        g, tb, ws, feats, scalars, status, nullptr, 2);
+    if (g.long_mode) {
+        k_spec512_consumers<true><<<dim3(n, 2), 256, 0, st>>>(g, tb, ws, feats, scalars, status, nullptr, 0);
+        k_spec512_consumers<true><<<dim3(n, with_chroma ? 2 : 1), 256, 0, st>>>(g, tb, ws, feats, scalars, status, nullptr, 2);
+    } else {
+        k_spec512_consumers<false><<<dim3(n, 2), 256, kConsumerSmemFloats * sizeof(float), st>>>(
+            g, tb, ws, feats, scalars, status, nullptr, 0);
+        k_spec512_consumers<false><<<dim3(n, with_chroma ? 2 : 1), 256, kLightSmemFloats * sizeof(float), st>>>(
+            g, tb, ws, feats, scalars, status, nullptr, 2);
+    }
     note_launch(2);
     if (g.long_mode) {
         k_modspec_time_long<<<dim3((g.T + 63) / 64, n), 256, 0, st>>>(g, tb, ws);
@@ -609,8 +623,9 @@ void launch_spec512_consumers(int n, const Geometry& g, const Tables& tb, const 
 void launch_logmel_only(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* mel3, cudaStream_t st) {
     set_consumer_smem();
     dim3 grid(n, 1);
-    k_spec512_consumers<<<grid, 256, g.long_mode ? 0 : kConsumerSmemFloats * sizeof(float), st>>>(g, tb, ws, nullptr, nullptr,
-                                                                                                    nullptr, mel3, 0);
+    if (g.long_mode) k_spec512_consumers<true><<<grid, 256, 0, st>>>(g, tb, ws, nullptr, nullptr, nullptr, mel3, 0);
+    else k_spec512_consumers<false><<<grid, 256, kConsumerSmemFloats * sizeof(float), st>>>(g, tb, ws, nullptr, nullptr,
+                                                                                           nullptr, mel3, 0);
     note_launch();
 }
 

@@ -30,6 +30,7 @@ __device__ __forceinline__ float lerp_q(float a, float b, double g) {
     return (float)(g >= 0.5 ? db - (db - da) * (1.0 - g) : da + (db - da) * g);
 }
 
+template <bool LONG>
 __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y, Geometry g, Workspace ws,
                                                     float* scalars, int32_t* status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y,
     // the per-block / per-frame arrays in the segment's scratch region
     const float* ys = S.y;
     double* sqv = S.sq; int* czv = S.cz; float* rmsv = S.rms; double* zcrv = S.zcr;
-    if (g.long_mode) {
+    if (LONG) {
         ys = yb;
         double* d = reinterpret_cast<double*>(ws.scratch + (size_t)b * ws.scratch_stride);
         sqv = d; d += T + 8; zcrv = d; d += T;
@@ -816,11 +817,13 @@ void launch_time_scalars(const float* y, int n, const Geometry& g, const Tables&
                          float* scalars, int32_t* status, cudaStream_t st) {
     static bool done = false;
     if (!done) {
-        cudaFuncSetAttribute(k_time_basic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TimeBasicSmem));
+        cudaFuncSetAttribute(k_time_basic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TimeBasicSmem));
+        cudaFuncSetAttribute(k_time_basic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TimeBasicSmem));
         cudaFuncSetAttribute(k_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AutocorrSmem));
         done = true;
     }
-    k_time_basic<<<n, 256, sizeof(TimeBasicSmem), st>>>(y, g, ws, scalars, status);
+    if (g.long_mode) k_time_basic<true><<<n, 256, sizeof(TimeBasicSmem), st>>>(y, g, ws, scalars, status);
+    else k_time_basic<false><<<n, 256, sizeof(TimeBasicSmem), st>>>(y, g, ws, scalars, status);
     k_autocorr<<<n, kAcThreads, sizeof(AutocorrSmem), st>>>(y, g, tb, ws.ints, scalars);
     note_launch(2);
 }
