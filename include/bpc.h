@@ -49,7 +49,7 @@ enum bpc_status {
     BPC_ERR_ARG = -1,          /* bad argument / unsupported parameter combination */
     BPC_ERR_CUDA = -2,         /* CUDA runtime error (message has the cudaError string) */
     BPC_ERR_ALLOC = -3,
-    BPC_ERR_UNSUPPORTED = -4,  /* e.g. expected_len beyond what this build's kernels hold on-chip */
+    BPC_ERR_UNSUPPORTED = -4,  /* not sm_100, other constants than the reference's, expected_len not 16000 * 2^a 3^b 5^c */
     BPC_ERR_NCCL = -5
 };
 
@@ -69,7 +69,8 @@ typedef struct bpc_params {
     float   fmax;          /* 4500  */
     int32_t n_gammatone;   /* 64    */
     int32_t n_lpc;         /* 12    */
-    int32_t expected_len;  /* int(SR * DURATION) = 16000 */
+    int32_t expected_len;  /* int(SR * DURATION) = 16000; 16000 * d with d = 2^a 3^b 5^c <= 32 selects the long mode
+                              (BASELINE config 4): same outputs at T = expected_len / 256 + 1 frames */
     int32_t pad_scalars_to;/* 0 = emit the reference's 36 scalars; 39 = append zeros (README's "39") */
 } bpc_params;
 
