@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(Geometry g, const float
         double s = 0.0, q = 0.0;
         float mn = FLT_MAX, mx = -FLT_MAX;
         int cnt = 0;
-#pragma unroll 4
+#pragma unroll 8
         for (int i = lane; i < NP / 4; i += 32) {
             const float4 v4 = __ldg(p4 + i);
             const float v[4] = {v4.x, v4.y, v4.z, v4.w};
