@@ -19,6 +19,9 @@
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
+#if defined(__linux__)
+#include <sched.h>
+#endif
 
 #include "../../include/bpc.h"
 #include "kernels.cuh"
@@ -811,11 +814,17 @@ int bpc_precompute_host(bpc_handle* h, const void* wav, int wav_dtype, int64_t B
             if (status) std::memcpy(status + off, s.h_status, (size_t)n * 4);
         }
     }
-    if (std::getenv("BPC_HOST_TRACE"))
-        std::fprintf(stderr, "[bpc host] B=%lld chunks=%lld total %.2f ms, waiting on GPU/PCIe %.2f ms, host copy/fill %.2f ms (%d threads)\n",
+    if (std::getenv("BPC_HOST_TRACE")) {
+        int ncpu = -1;
+#if defined(__linux__)
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) ncpu = CPU_COUNT(&set);
+#endif
+        std::fprintf(stderr, "[bpc host] B=%lld chunks=%lld total %.2f ms, waiting on GPU/PCIe %.2f ms, host copy/fill %.2f ms (%d threads, %d cpus in the affinity mask)\n",
                      (long long)B, (long long)nchunks,
                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(), t_wait,
-                     t_fill, h->pool->size());
+                     t_fill, h->pool->size(), ncpu);
+    }
     return BPC_OK;
 }
 
