@@ -16,13 +16,15 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "breathing-phase-classifier_b200"))
 
 
-def compare(n_synth=8, verbose=True):
+def compare(n_synth=8, verbose=True, real_inputs=False):
     import torch
     import bpc_b200
     from oracle import pipeline as P
 
     gold = np.load(os.path.join(ROOT, "tests", "golden", "golden_segments.npz"))
     pcm = gold["pcm16"]
+    if real_inputs:                                     # 56 more real fixture segments, inputs only (tests/golden/README.md)
+        pcm = np.load(os.path.join(ROOT, "tests", "golden", "real_inputs_pcm16.npz"))["pcm16"]
     ys = [q.astype(np.float32) / np.float32(32768.0) for q in pcm]
     ys += [P.synth_segment(1000 + i) for i in range(n_synth)]
     Y = np.stack(ys)
