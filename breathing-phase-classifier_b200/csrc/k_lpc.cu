@@ -63,9 +63,11 @@ __device__ __forceinline__ void burg_all(double (&F)[kLpcPer], double (&B)[kLpcP
     }
 }
 
+// phase 0: everything (1 s).  Long mode: phase 1 = the Burg frames of this CTA's share (grid (segment, part)) into the
+// scratch region, phase 2 = statistics + plane (grid (segment)).
 template <bool LONG>
 __global__ void __launch_bounds__(kLpcThreads, 4) k_lpc(const float* __restrict__ y, Geometry g, Tables tb, Workspace ws,
-                                                float* feats) {
+                                                float* feats, int phase) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LpcSmem& S = *reinterpret_cast<LpcSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -74,7 +76,9 @@ __global__ void __launch_bounds__(kLpcThreads, 4) k_lpc(const float* __restrict_
     // [12, F] coefficients: shared memory (1 s: F = 98), the segment's global scratch region in long mode
     float* coef = LONG ? ws.scratch + (size_t)b * ws.scratch_stride : S.coef;
 
-    for (int fr = warp; fr < F_; fr += kLpcThreads / 32) {
+    const int fr0 = LONG ? blockIdx.y * (kLpcThreads / 32) + warp : warp;
+    const int frs = LONG ? gridDim.y * (kLpcThreads / 32) : kLpcThreads / 32;
+    for (int fr = fr0; fr < F_ && phase != 2; fr += frs) {
         const int start = fr * kLpcShift;
         double Bv[kLpcPer], Fv[kLpcPer];
 #pragma unroll
@@ -103,6 +107,7 @@ __global__ void __launch_bounds__(kLpcThreads, 4) k_lpc(const float* __restrict_
         burg_all<0>(Fv, Bv, a_lane, den, lane);
         if (lane >= 1 && lane <= kLpcOrder) coef[(lane - 1) * F_ + fr] = (float)a_lane;
     }
+    if (LONG && phase == 1) return;
     __syncthreads();
     const int F = F_;
     if (ws.dbg_lpc) {
@@ -137,8 +142,13 @@ void launch_lpc(const float* y, int n, const Geometry& g, const Tables& tb, cons
         cudaFuncSetAttribute(k_lpc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpcSmem));
         done = true;
     }
-    if (g.long_mode) k_lpc<true><<<n, kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats);
-    else k_lpc<false><<<n, kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats);
+    if (g.long_mode) {
+        k_lpc<true><<<dim3(n, 16), kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats, 1);
+        k_lpc<true><<<dim3(n, 1), kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats, 2);
+        note_launch();
+    } else {
+        k_lpc<false><<<n, kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats, 0);
+    }
     note_launch();
 }
 

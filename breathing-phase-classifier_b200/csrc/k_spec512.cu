@@ -541,7 +541,7 @@ size_t consumer_scratch_floats(int T) {
 }
 
 template <bool LONG>
-__global__ void __launch_bounds__(256) k_spec512_consumers(Geometry g, Tables tb, Workspace ws, float* feats,
+__global__ void __launch_bounds__(LONG ? 512 : 256) k_spec512_consumers(Geometry g, Tables tb, Workspace ws, float* feats,
                                                            float* scalars, int32_t* status, float* mel3,
                                                            int role_base) {
     extern __shared__ __align__(16) float smem_dyn[];
@@ -597,15 +597,16 @@ void launch_spec512_consumers(int n, const Geometry& g, const Tables& tb, const 
     static const char* only = std::getenv("BPC_ONLY_ROLE");      // profiling aid: time one role (outputs incomplete)
     if (only) {
         const int r = std::atoi(only);
-        if (g.long_mode) k_spec512_consumers<true><<<dim3(n, 1), 256, 0, st>>>(g, tb, ws, feats, scalars, status, nullptr, r);
+        if (g.long_mode) k_spec512_consumers<true><<<dim3(n, 1), 512, 0, st>>>(g, tb, ws, feats, scalars, status, nullptr, r);
         else k_spec512_consumers<false><<<dim3(n, 1), 256, (r < 2 ? kConsumerSmemFloats : kLightSmemFloats) * sizeof(float), st>>>(
             g, tb, ws, feats, scalars, status, nullptr, r);
         note_launch();
         return;
     }
     if (g.long_mode) {
-        k_spec512_consumers<true><<<dim3(n, 2), 256, 0, st>>>(g, tb, ws, feats, scalars, status, nullptr, 0);
-        k_spec512_consumers<true><<<dim3(n, with_chroma ? 2 : 1), 256, 0, st>>>(g, tb, ws, feats, scalars, status, nullptr, 2);
+        // 512 threads: with one CTA per (segment, role) and <= 148 segments a launch, more loads in flight per SM
+        k_spec512_consumers<true><<<dim3(n, 2), 512, 0, st>>>(g, tb, ws, feats, scalars, status, nullptr, 0);
+        k_spec512_consumers<true><<<dim3(n, with_chroma ? 2 : 1), 512, 0, st>>>(g, tb, ws, feats, scalars, status, nullptr, 2);
     } else {
         k_spec512_consumers<false><<<dim3(n, 2), 256, kConsumerSmemFloats * sizeof(float), st>>>(
             g, tb, ws, feats, scalars, status, nullptr, 0);
@@ -623,7 +624,7 @@ void launch_spec512_consumers(int n, const Geometry& g, const Tables& tb, const 
 void launch_logmel_only(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* mel3, cudaStream_t st) {
     set_consumer_smem();
     dim3 grid(n, 1);
-    if (g.long_mode) k_spec512_consumers<true><<<grid, 256, 0, st>>>(g, tb, ws, nullptr, nullptr, nullptr, mel3, 0);
+    if (g.long_mode) k_spec512_consumers<true><<<grid, 512, 0, st>>>(g, tb, ws, nullptr, nullptr, nullptr, mel3, 0);
     else k_spec512_consumers<false><<<grid, 256, kConsumerSmemFloats * sizeof(float), st>>>(g, tb, ws, nullptr, nullptr,
                                                                                            nullptr, mel3, 0);
     note_launch();

@@ -680,10 +680,11 @@ __device__ __forceinline__ int plan_pos(const HilbertPlan& P, int k) {
     return p + k;
 }
 
-__global__ void __launch_bounds__(kHilbertThreads) k_hilbert_long(const float* __restrict__ y, Geometry g, Tables tb,
+constexpr int kHilbertLongThreads = 1024;
+__global__ void __launch_bounds__(kHilbertLongThreads) k_hilbert_long(const float* __restrict__ y, Geometry g, Tables tb,
                                                                   Workspace ws, HilbertPlan P, float* scalars) {
     __shared__ HilbertTail S;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = kHilbertThreads;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = kHilbertLongThreads;
     const int b = blockIdx.x, L = g.L, N = P.n;
     const float* yb = y + (size_t)b * L;
     float* base = ws.scratch + (size_t)b * ws.scratch_stride;
@@ -837,7 +838,7 @@ void launch_hilbert(const float* y, int n, const Geometry& g, const Tables& tb, 
         for (int f : {5, 3}) while (r % f == 0) { P.radix[P.npass++] = f; r /= f; }
         while (r % 4 == 0) { P.radix[P.npass++] = 4; r /= 4; }
         if (r == 2) { P.radix[P.npass++] = 2; r = 1; }
-        k_hilbert_long<<<n, kHilbertThreads, 0, st>>>(y, g, tb, ws, P, scalars);
+        k_hilbert_long<<<n, kHilbertLongThreads, 0, st>>>(y, g, tb, ws, P, scalars);
         note_launch();
         return;
     }
