@@ -319,6 +319,8 @@ int build_tables(bpc_handle* h) {
         for (int u = 0; u < T; ++u)
             for (int t = 0; t < T; ++t) dt[size_t(t) * T + u] = d[size_t(u) * T + t];     // device wants [t][u]
         if ((rc = upload(h, dt, &tb.dct_time))) return rc;
+        tb.dct_time_n = nullptr;
+        if (h->g.long_mode && (rc = upload(h, d, &tb.dct_time_n))) return rc;
     }
     std::vector<double> edges = tuning_edges();
     if ((rc = upload(h, edges, &tb.hist_edges))) return rc;

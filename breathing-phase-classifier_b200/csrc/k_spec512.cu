@@ -615,9 +615,14 @@ void launch_spec512_consumers(int n, const Geometry& g, const Tables& tb, const 
     }
     note_launch(2);
     if (g.long_mode) {
-        k_modspec_time_long<<<dim3((g.T + 63) / 64, n), 256, 0, st>>>(g, tb, ws);
+        if (modspec_time_tc_enabled(tb)) {                     // tcgen05 3xTF32 (k_tc.cu); BPC_TC_DCT=0: FP32 SIMT tiles
+            launch_modspec_time_tc(n, g, tb, ws, consumer_role_offset(0, g.T), st);
+        } else {
+            k_modspec_time_long<<<dim3((g.T + 63) / 64, n), 256, 0, st>>>(g, tb, ws);
+            note_launch();
+        }
         k_modspec_finish_long<<<n, 256, 0, st>>>(g, ws, feats);
-        note_launch(2);
+        note_launch();
     }
 }
 
@@ -725,7 +730,8 @@ void launch_modspec(int n, const Geometry& g, const Tables& tb, const Workspace&
             const int m = n - off < ws.cap ? n - off : ws.cap;
             const size_t NP = (size_t)kPlaneRows * g.T;
             k_modspec_long_in<<<m, 256, 0, st>>>(g, tb, ws, mel_db + off * NP);
-            k_modspec_time_long<<<dim3((g.T + 63) / 64, m), 256, 0, st>>>(g, tb, ws);
+            if (modspec_time_tc_enabled(tb)) launch_modspec_time_tc(m, g, tb, ws, consumer_role_offset(0, g.T), st);
+            else k_modspec_time_long<<<dim3((g.T + 63) / 64, m), 256, 0, st>>>(g, tb, ws);
             k_modspec_long_out<<<m, 256, 0, st>>>(g, ws, out + (size_t)off * 40 * g.T);
             note_launch(3);
         }

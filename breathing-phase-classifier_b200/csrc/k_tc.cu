@@ -1,0 +1,160 @@
+// The one GEMM-shaped stage of the path on the 5th-generation tensor cores: the time-axis DCT of `mod_spec`
+// (methods.py:142-143, second `dct`) in long mode, C2[40 n_seg, T] = C1[40 n_seg, T] . D^T with D the [T, T] ortho DCT-II
+// matrix (T = 1876 at 30 s: 140 MFLOP per segment, one [5440 x 1876] x [1876 x 1876] product per 136-segment launch).
+//
+// tcgen05.mma kind::tf32, cta_group::1, M = 128 x N = 128 tiles, accumulator in TMEM (128 lanes x 128 columns), both
+// operands K-major in shared memory in the canonical no-swizzle layout (8-row x 16-byte core matrices), written by the
+// CTA's own threads (the A rows are scattered over the per-segment scratch regions, so there is no TMA tensor map).
+// Precision: 3xTF32 -- every float32 operand is split into hi = tf32(x) and lo = tf32(x - hi) and the product is
+// accumulated as lo*hi + hi*lo + hi*hi in the FP32 accumulator, which recovers float32-level products (a single TF32
+// pass has 10 mantissa bits: 1e-3 relative, two orders beyond the parity budget of this stage).
+#include <cstdlib>
+#include "kernels.cuh"
+
+namespace bpc {
+
+size_t consumer_scratch_floats(int T);
+constexpr int kTcM = 128, kTcN = 128, kTcK = 32;                 // CTA tile; K per stage (4 MMAs of K = 8)
+constexpr int kTcOpFloats = kTcM * kTcK;                         // one operand stage: 128 rows x 32 k = 16 KB
+
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// canonical K-major, no swizzle: [k / 4][row / 8][row % 8][k % 4] floats -> 128-byte core matrices; consecutive 8-row
+// groups are 128 B apart (SBO), the two 16-byte K chunks of one K = 8 MMA are rows/8 * 128 B apart (LBO)
+__device__ __forceinline__ int tc_idx(int row, int k) { return (((k >> 2) * (kTcM / 8) + (row >> 3)) << 5) + ((row & 7) << 2) + (k & 3); }
+
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr_bytes) {
+    constexpr uint32_t kLbo = (kTcM / 8) * 128, kSbo = 128;
+    uint64_t d = (uint64_t)((saddr_bytes >> 4) & 0x3FFFu);
+    d |= (uint64_t)((kLbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((kSbo >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;                                      // descriptor version 1 (sm_100); layout type 0 = no swizzle
+    return d;
+}
+
+// instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), both K-major, N >> 3 at bit 17,
+// M >> 4 at bit 24
+constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(kTcIdesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(128) k_modspec_time_tc(Geometry g, Tables tb, Workspace ws, int n_seg, size_t role0_off) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* Ahi = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* Alo = Ahi + kTcOpFloats;
+    uint32_t* Bhi = Alo + kTcOpFloats;
+    uint32_t* Blo = Bhi + kTcOpFloats;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = g.T, m0 = blockIdx.y * kTcM, n0 = blockIdx.x * kTcN, m_total = n_seg * 40;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTcN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) mbar_init(&bar, 1);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    // thread `tid` owns row tid of both operand tiles: A row m (segment m / 40, mel-DCT row m % 40 of C1), B row u of D
+    const int m = m0 + tid, u = n0 + tid;
+    const float* a_row = nullptr;
+    if (m < m_total) {
+        const int seg = m / 40, r = m - seg * 40;
+        a_row = ws.scratch + (size_t)seg * ws.scratch_stride + role0_off + (size_t)(kPlaneRows + r) * T;
+    }
+    const float* b_row = u < T ? tb.dct_time_n + (size_t)u * T : nullptr;
+
+    uint32_t phase = 0;
+    for (int k0 = 0; k0 < T; k0 += kTcK) {
+#pragma unroll 8
+        for (int kk = 0; kk < kTcK; ++kk) {
+            const int k = k0 + kk, idx = tc_idx(tid, kk);
+            const float a = (a_row && k < T) ? a_row[k] : 0.f;
+            const float b = (b_row && k < T) ? __ldg(b_row + k) : 0.f;
+            const uint32_t ah = tf32_rna(a), bh = tf32_rna(b);
+            Ahi[idx] = ah;
+            Alo[idx] = tf32_rna(a - __uint_as_float(ah));
+            Bhi[idx] = bh;
+            Blo[idx] = tf32_rna(b - __uint_as_float(bh));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA unit
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa_hi = smem_u32(Ahi), sa_lo = smem_u32(Alo), sb_hi = smem_u32(Bhi), sb_lo = smem_u32(Blo);
+            constexpr uint32_t kStep = 2 * (kTcM / 8) * 128;              // two K chunks = one K = 8 MMA
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {                        // small terms first: lo*hi, hi*lo, hi*hi
+                const uint32_t sa = term == 0 ? sa_lo : sa_hi, sb = term == 1 ? sb_lo : sb_hi;
+#pragma unroll
+                for (int j = 0; j < kTcK / 8; ++j)
+                    tc_mma(tmem, tc_desc(sa + j * kStep), tc_desc(sb + j * kStep), (k0 | term | j) != 0);
+            }
+            // arrives on the barrier when every MMA issued so far has completed (implies fence::before_thread_sync)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        }
+        mbar_wait(&bar, phase);                                           // the operand buffers may be refilled
+        phase ^= 1u;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: warp w reads TMEM lanes 32 w .. 32 w + 31 (= tile rows), 8 columns at a time
+    const int mrow = m0 + warp * 32 + lane;
+    float* c_row = nullptr;
+    if (mrow < m_total) {
+        const int seg = mrow / 40, r = mrow - seg * 40;
+        c_row = ws.scratch + (size_t)seg * ws.scratch_stride + role0_off + (size_t)(kPlaneRows + 40 + r) * T;
+    }
+#pragma unroll 1
+    for (int c = 0; c < kTcN; c += 8) {
+        uint32_t v[8];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c_row) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (n0 + c + q < T) c_row[n0 + c + q] = __uint_as_float(v[q]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcN));
+}
+
+bool modspec_time_tc_enabled(const Tables& tb) {
+    static const char* env = std::getenv("BPC_TC_DCT");
+    return tb.dct_time_n != nullptr && !(env && std::atoi(env) == 0);
+}
+
+void launch_modspec_time_tc(int n, const Geometry& g, const Tables& tb, const Workspace& ws, size_t role0_off,
+                            cudaStream_t st) {
+    static bool done = false;
+    const int bytes = 4 * kTcOpFloats * (int)sizeof(uint32_t);
+    if (!done) {
+        cudaFuncSetAttribute(k_modspec_time_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        done = true;
+    }
+    dim3 grid((g.T + kTcN - 1) / kTcN, (n * 40 + kTcM - 1) / kTcM);
+    k_modspec_time_tc<<<grid, 128, bytes, st>>>(g, tb, ws, n, role0_off);
+    note_launch();
+}
+
+}  // namespace bpc

@@ -29,7 +29,8 @@ struct Tables {
     // filterbanks
     BankDev mel_a, mel_b, mel_c, mel_d;
     const float* dct_mel;         // [40, 128]
-    const float* dct_time;        // [T, T]
+    const float* dct_time;        // [T, T]  transposed: [t][u]
+    const float* dct_time_n;      // [T, T]  [u][t] (K-major B operand of the tensor-core time DCT; long mode only)
     const float* chroma;          // [100, 12, 257]
     const double* hist_edges;     // [101]
     // CQT
@@ -125,6 +126,9 @@ void launch_collate(const float* store_feats, const float* store_scalars, const 
 void launch_pad_values(const float* feats, int T, int n, const int* live_dev, float* fill, cudaStream_t st);
 
 size_t consumer_scratch_floats(int T);
+bool modspec_time_tc_enabled(const Tables& tb);
+void launch_modspec_time_tc(int n, const Geometry& g, const Tables& tb, const Workspace& ws, size_t role0_off,
+                            cudaStream_t st);
 
 void upload_cens_constants(const double* taps127);
 int cens_dec_floats_per_segment(int L);
