@@ -320,7 +320,15 @@ int build_tables(bpc_handle* h) {
             for (int t = 0; t < T; ++t) dt[size_t(t) * T + u] = d[size_t(u) * T + t];     // device wants [t][u]
         if ((rc = upload(h, dt, &tb.dct_time))) return rc;
         tb.dct_time_n = nullptr;
-        if (h->g.long_mode && (rc = upload(h, d, &tb.dct_time_n))) return rc;
+        tb.dct_tiles = nullptr;
+        if (h->g.long_mode) {
+            if ((rc = upload(h, d, &tb.dct_time_n))) return rc;
+            uint32_t* tiles = nullptr;
+            if ((rc = dalloc(h, tc_tile_words(T, T), &tiles))) return rc;
+            launch_tc_prep_b(h->g, tb, tiles, 0);
+            BPC_CUDA(h, cudaDeviceSynchronize());
+            tb.dct_tiles = tiles;
+        }
     }
     std::vector<double> edges = tuning_edges();
     if ((rc = upload(h, edges, &tb.hist_edges))) return rc;
@@ -388,6 +396,8 @@ int build_workspace(bpc_handle* h) {
     if ((rc = dalloc(h, C * 2, &w.ints))) return rc;
     w.scratch = nullptr;
     w.scratch_stride = 0;
+    w.tc_a = nullptr;
+    if (g.long_mode && (rc = dalloc(h, tc_tile_words(h->chunk * 40, g.T), &w.tc_a))) return rc;
     if (g.long_mode) {
         // per-segment scratch of the kernel that needs most (kernels of a chunk run one after the other in long mode)
         size_t need = consumer_scratch_floats(g.T);

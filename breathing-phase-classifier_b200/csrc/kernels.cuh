@@ -31,6 +31,7 @@ struct Tables {
     const float* dct_mel;         // [40, 128]
     const float* dct_time;        // [T, T]  transposed: [t][u]
     const float* dct_time_n;      // [T, T]  [u][t] (K-major B operand of the tensor-core time DCT; long mode only)
+    const uint32_t* dct_tiles;    // the same matrix split into tf32 hi / lo halves, pre-tiled in the canonical UMMA layout
     const float* chroma;          // [100, 12, 257]
     const double* hist_edges;     // [101]
     // CQT
@@ -66,6 +67,7 @@ struct Workspace {            // per chunk of `cap` segments
     int* tuning;              // [cap, 2]   tuning bin for 12 / 36 bins per octave
     float* chroma_min;        // [cap, 2]   min of the normalised chroma_stft / chroma_cens rows
     int* ints;                // [cap, 2]   n_peaks, first-min index
+    uint32_t* tc_a;           // long mode: C1 split into tf32 hi / lo tiles for the tensor-core time DCT (k_tc.cu)
     float* scratch;           // [cap, scratch_stride]  long mode: what the 1 s kernels keep in shared memory
     size_t scratch_stride;
     // debug (raw, un-normalised stages of the last chunk)
@@ -127,6 +129,8 @@ void launch_pad_values(const float* feats, int T, int n, const int* live_dev, fl
 
 size_t consumer_scratch_floats(int T);
 bool modspec_time_tc_enabled(const Tables& tb);
+size_t tc_tile_words(int rows, int T);
+void launch_tc_prep_b(const Geometry& g, const Tables& tb, uint32_t* out, cudaStream_t st);
 void launch_modspec_time_tc(int n, const Geometry& g, const Tables& tb, const Workspace& ws, size_t role0_off,
                             cudaStream_t st);
 
