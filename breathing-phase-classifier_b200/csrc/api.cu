@@ -210,21 +210,6 @@ int upload_bank(bpc_handle* h, const SparseBank& b, BankDev* out) {
     return BPC_OK;
 }
 
-// per-pass twiddle layout of fft.cuh::warp_fft_r4<M>
-std::vector<double2> twiddles_per_pass(int M) {
-    const int N = 1 << (2 * M);
-    std::vector<double2> t;
-    for (int p = 0; p < M - 1; ++p) {
-        const int q = N >> (2 * (p + 1)), ts = N / (4 * q);
-        for (int r = 1; r <= 3; ++r)
-            for (int pos = 0; pos < q; ++pos) {
-                const double ang = -2.0 * kPi * double(r * pos * ts) / double(N);
-                t.push_back(make_double2(std::cos(ang), std::sin(ang)));
-            }
-    }
-    return t;
-}
-
 std::vector<double2> twiddles(int n, int count) {
     std::vector<double2> t(count);
     for (int j = 0; j < count; ++j) {
@@ -267,9 +252,6 @@ int build_tables(bpc_handle* h) {
     if ((rc = upload(h, hann_periodic(384), &tb.hann384))) return rc;
     if ((rc = upload(h, hamming_sym(400), &tb.hamming400))) return rc;
     if ((rc = upload(h, twiddles(256, 256), &tb.tw256))) return rc;
-    if ((rc = upload(h, twiddles(1024, 1024), &tb.tw1024))) return rc;
-    if ((rc = upload(h, twiddles_per_pass(4), &tb.twp256))) return rc;
-    if ((rc = upload(h, twiddles_per_pass(5), &tb.twp1024))) return rc;
     {
         std::vector<double2> t(32 * 32);
         for (int k1 = 0; k1 < 32; ++k1)
@@ -281,8 +263,6 @@ int build_tables(bpc_handle* h) {
     }
     if ((rc = upload(h, twiddles(512, 257), &tb.ptw512))) return rc;
     if ((rc = upload(h, twiddles(2048, 1025), &tb.ptw2048))) return rc;
-    if ((rc = upload(h, twiddles(8000, 8000), &tb.tw8000))) return rc;
-    if ((rc = upload(h, twiddles(16000, 8001), &tb.ptw16000))) return rc;
     {
         auto to_f = [](const std::vector<double2>& d) {
             std::vector<float2> f(d.size());
@@ -373,7 +353,6 @@ int build_tables(bpc_handle* h) {
                 return BPC_ERR_UNSUPPORTED;
             }
         upload_cens_constants(hb.data());
-        if ((rc = upload(h, hb, &tb.halfband))) return rc;
     }
     return BPC_OK;
 }

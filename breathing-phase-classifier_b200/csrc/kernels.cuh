@@ -20,11 +20,8 @@ struct Tables {
     const double* hann512;        // [512]
     const double* hann2048;       // [2048]
     const double2* tw256;         // exp(-2 pi i j / 256), j < 256
-    const double2* tw1024;        // exp(-2 pi i j / 1024), j < 1024
     const double2* ptw512;        // exp(-2 pi i k / 512),  k <= 256
     const double2* ptw2048;       // exp(-2 pi i k / 2048), k <= 1024
-    const double2* twp256;        // per-pass twiddles of warp_fft_r4<4> (fft.cuh::twp_size(4) entries)
-    const double2* twp1024;       // per-pass twiddles of warp_fft_r4<5>
     const double2* twa1024;       // [k1][h] = exp(-2 pi i h k1 / 1024), 32 x 32: inter-stage twiddles of team_fft<32>
     // filterbanks
     BankDev mel_a, mel_b, mel_c, mel_d;
@@ -40,14 +37,11 @@ struct Tables {
     const float* cqt_im;          // [100, 36, W]
     const double* cqt_sqrt_len;   // [100, 252]
     int cqt_ell_used;             // max non-zeros per basis row over all tunings (<= kCqtEllWidth)
-    const double* halfband;       // [127]
     // LPC
     const double* hamming400;     // [400]
     // Hilbert (FFT-8000 = 4^3 * 5^3)
-    const double2* tw8000;        // exp(-2 pi i j / 8000), j < 8000
-    const double2* ptw16000;      // exp(-2 pi i k / 16000), k <= 8000
-    const float2* tw8000f;        // float32 copies: scipy.signal.hilbert runs a float32 FFT on float32 input
-    const float2* ptw16000f;
+    const float2* tw8000f;        // exp(-2 pi i j / 8000), j < 8000, float32: scipy.signal.hilbert runs a float32 FFT on float32 input
+    const float2* ptw16000f;      // exp(-2 pi i k / 16000), k <= 8000
     // long mode Hilbert (FFT-N, N = L / 2 = 2^a 3^b 5^c): exp(-2 pi i j / N), j < N and exp(-2 pi i k / L), k <= N
     const float2* tw_long;
     const float2* ptw_long;
