@@ -465,3 +465,36 @@ def test_real_fixture_segments_match_oracle(torch_cuda):
             assert v < 2e-4, (k, v)
     rel = r["scal_rel"].copy()
     assert float(np.max(np.delete(rel, [10, 29, 30, 33, 34]))) < 1e-4, rel  # near-cancelling ones: see the module docstring
+
+
+def test_c_abi_error_codes_on_device(torch_cuda):
+    """Fatal problems are return codes + bpc_last_error, never exceptions or crashes (include/bpc.h conventions)."""
+    import ctypes as C
+    torch = torch_cuda
+    import bpc_b200
+    lib = bpc_b200.lib()
+    h = C.c_void_p()
+    p = bpc_b200.default_params()
+    assert lib.bpc_create(C.byref(h), C.byref(p), 99, 16) == -1 and b"device" in lib.bpc_last_error(None)
+    eng = bpc_b200.Engine(device=0, max_batch=8)
+    wav = torch.zeros((2, 16000), device="cuda")
+    f = torch.empty((2, 9, 128, 63), device="cuda"); s = torch.empty((2, 36), device="cuda")
+    assert lib.bpc_precompute(eng._h, None, 0, 2, 16000, f.data_ptr(), s.data_ptr(), None, None) == -1
+    assert lib.bpc_precompute(eng._h, wav.data_ptr(), 7, 2, 16000, f.data_ptr(), s.data_ptr(), None, None) == -1
+    assert b"bad argument" in lib.bpc_last_error(eng._h)
+    assert lib.bpc_precompute(eng._h, wav.data_ptr(), 0, 0, 16000, f.data_ptr(), s.data_ptr(), None, None) == 0   # empty batch
+    idx = torch.zeros(2, dtype=torch.int64, device="cuda")
+    assert lib.bpc_collate(eng._h, f.data_ptr(), s.data_ptr(), 2, idx.data_ptr(), None, 2, 1, 0.5, 0, 0, 0, 0,
+                           f.data_ptr(), s.data_ptr(), None) == -1          # mixing needs idx_b
+    assert lib.bpc_collate(eng._h, f.data_ptr(), s.data_ptr(), 2, idx.data_ptr(), idx.data_ptr(), 2, 2, 0.5, 0, 200, 0, 10,
+                           f.data_ptr(), s.data_ptr(), None) == -1 and b"box" in lib.bpc_last_error(eng._h)
+    got = C.c_int64()
+    buf = np.zeros(4, np.float32)
+    assert lib.bpc_debug_copy(eng._h, b"nonsense", buf.ctypes.data, buf.nbytes, C.byref(got)) == -1
+    assert lib.bpc_debug_copy(eng._h, b"mel_db", buf.ctypes.data, buf.nbytes, C.byref(got)) == -1   # debug buffers are off
+    with pytest.raises(ValueError):
+        eng.precompute_host(np.zeros((2, 16000), np.float32), feats=np.zeros((2, 9, 128, 62), np.float32))
+    with pytest.raises(TypeError):
+        eng.precompute_host(np.zeros((2, 16000), np.float64))
+    eng.close()
+    eng.close()                                                           # idempotent

@@ -361,3 +361,26 @@ def test_cpp_wav_reader_matches_scipy_and_reports_per_file(tmp_path):
     only16, errs = PR.load_wav_batch(paths[:4], 16000)
     assert only16.dtype == np.int16 and errs == [None] * 4 and np.array_equal(only16[0], sig[16000])
     assert np.array_equal(only16[1, :12345], sig[12345]) and not only16[1, 12345:].any()
+
+
+def test_host_only_entry_points_reject_bad_arguments(tmp_path):
+    """No exceptions cross the ABI: bad arguments come back as BPC_ERR_ARG (-1) / per-file codes."""
+    import ctypes as C
+    lib = bpc_b200.lib()
+    f = np.zeros((9, 128, 63), np.float32); s = np.zeros(36, np.float32); out = np.zeros(16, np.uint8)
+    assert lib.bpc_npz_size(0, 36) == -1 and lib.bpc_npz_size(63, 0) == -1
+    assert lib.bpc_npz_pack(f.ctypes.data, s.ctypes.data, 63, 36, out.ctypes.data, out.nbytes) == -1     # buffer too small
+    assert lib.bpc_npz_pack(None, s.ctypes.data, 63, 36, out.ctypes.data, out.nbytes) == -1
+    ok = np.zeros(1, np.int32)
+    ids = (C.c_char_p * 1)(b"x")
+    assert lib.bpc_npz_write_batch(None, ids, f.ctypes.data, s.ctypes.data, None, 1, 63, 36, 2, ok.ctypes.data) == -1
+    sr = np.zeros(1, np.int32); fr = np.zeros(1, np.int32); code = np.zeros(1, np.int32); pcm = np.zeros(16000, np.int16)
+    assert lib.bpc_wav_load_batch(None, 1, 16000, 16000, pcm.ctypes.data, sr.ctypes.data, fr.ctypes.data, code.ctypes.data, 2) == -1
+    paths = (C.c_char_p * 1)(str(tmp_path / "nope.wav").encode())
+    assert lib.bpc_wav_load_batch(paths, 1, 16000, 0, pcm.ctypes.data, sr.ctypes.data, fr.ctypes.data, code.ctypes.data, 2) == -1
+    assert lib.bpc_wav_load_batch(paths, 1, 16000, 16000, pcm.ctypes.data, sr.ctypes.data, fr.ctypes.data, code.ctypes.data, 2) == 0
+    assert code[0] == -10                                                  # BPC_WAV_ERR_OPEN, reported per file
+    assert lib.bpc_table_copy(C.byref(bpc_b200.default_params()), b"no_such_table", 0, out.ctypes.data, 16) < 0
+    assert lib.bpc_num_frames(None) == -1 and lib.bpc_num_scalars(None) == -1
+    assert lib.bpc_create(None, C.byref(bpc_b200.default_params()), 0, 16) == -1
+    assert b"NULL" in lib.bpc_last_error(None)
