@@ -192,7 +192,7 @@ struct CensSmem {
 
 template <bool LONG>
 __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restrict__ y, Geometry g, Tables tb,
-                                                          Workspace ws, float* feats) {
+                                                          Workspace ws, float* feats, int phase) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CensSmem& S = *reinterpret_cast<CensSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -245,7 +245,10 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
     float2* spec = S.spec[team];
     float* cqmag = S.cqmag[team];
     const int ell_used = tb.cqt_ell_used;
-    for (int t0 = 2 * warp; t0 < T; t0 += kCensTeams) {
+    // long mode: phase 1 = the CQT frames of this CTA's share (grid (segment, part)), phase 2 = post-processing
+    const int t_first = 2 * warp + (LONG ? (int)blockIdx.y * kCensTeams : 0);
+    const int t_step = kCensTeams * (LONG ? (int)gridDim.y : 1);
+    for (int t0 = t_first; t0 < T && phase != 2; t0 += t_step) {
         const int t = t0 + (lane >> 4);
         const bool valid = t < T;
         float csum = 0.f;                                        // lanes h < 12: chroma c = h
@@ -309,6 +312,7 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
         }
         if (h < 12 && valid) p_csum[h * T + t] = csum;
     }
+    if (LONG && phase == 1) return;
     __syncthreads();
     // ---- CENS post-processing per column: L1 normalise, quantise
     for (int t = tid; t < T; t += kCensThreads) {
@@ -385,8 +389,13 @@ void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, con
     } else {
         k_cens_dec<<<n, kDecThreads, sizeof(DecSmem), st>>>(y, g, ws);
     }
-    if (g.long_mode) k_cens<true><<<n, kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats);
-    else k_cens<false><<<n, kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats);
+    if (g.long_mode) {
+        k_cens<true><<<dim3(n, 16), kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats, 1);
+        k_cens<true><<<dim3(n, 1), kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats, 2);
+        note_launch();
+    } else {
+        k_cens<false><<<n, kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats, 0);
+    }
     note_launch(2);
 }
 

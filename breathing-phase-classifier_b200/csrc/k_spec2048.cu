@@ -272,7 +272,7 @@ __device__ __forceinline__ void group_bar(int id, int n) { asm volatile("bar.syn
 
 template <bool LONG>
 __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, Workspace ws, float* feats,
-                                                          float* scalars) {
+                                                          float* scalars, int phase) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Seg2048Smem& S = *reinterpret_cast<Seg2048Smem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = kSegThreads, NW = kSegThreads / 32;
@@ -292,6 +292,9 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
         V.flat = S.flat; V.sumv = S.sumv; V.sumq = S.sumq; V.onset = S.onset; V.flux = S.flux; V.ac0 = S.ac0;
     }
 
+    // long mode runs three launches: phase 1 = statistics / flux / onset envelope (grid (segment)), phase 2 = the
+    // tempogram frames of this CTA's share (grid (segment, part)), phase 3 = normalisation; phase 0 = all (1 s)
+    if (!LONG || phase == 1) {
     {   // stage per-frame features and mel-D
         const float4* src = reinterpret_cast<const float4*>(ws.melD + (size_t)b * T * kPlaneRows);
         for (int i = tid; i < T * kPlaneRows / 4; i += NT) reinterpret_cast<float4*>(V.melD)[i] = __ldg(src + i);
@@ -427,10 +430,14 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
     }
     for (int t = tid; t < T; t += NT) { V.sumv[t] = 0.0; V.sumq[t] = 0.0; }
     __syncthreads();
+    }
+    if (LONG && phase == 1) return;
+    if (!LONG || phase == 2) {
     // two frames in flight: group gidx (96 threads) owns frames gidx, gidx + 2, ...; thread j owns lags 4j .. 4j + 3.
     const int gidx = tid / 96, j = tid - gidx * 96, l0 = 4 * j;
     float* F = S.frame[gidx];
-    for (int t = gidx; t < T + (T & 1); t += 2) {
+    const int t_step = 2 * (LONG ? (int)gridDim.y : 1);
+    for (int t = gidx + (LONG ? 2 * (int)blockIdx.y : 0); t < T + (T & 1); t += t_step) {
         const bool live = t < T;
         if (live) {
             for (int n = j; n < kTempoLags + 8; n += 96)
@@ -463,6 +470,8 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
         }
         group_bar(1 + gidx, 96);
     }
+    }
+    if (LONG && phase == 2) return;
     __syncthreads();
     // util.normalize(norm=inf) divides each column by max |.| (= lag 0); z-score over all 384 x T values (process.py:76)
     double s = 0.0, q = 0.0;
@@ -628,8 +637,14 @@ void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb,
 
 void launch_seg2048(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats, float* scalars,
                     cudaStream_t st) {
-    if (g.long_mode) k_seg2048<true><<<n, kSegThreads, sizeof(Seg2048Smem), st>>>(g, tb, ws, feats, scalars);
-    else k_seg2048<false><<<n, kSegThreads, sizeof(Seg2048Smem), st>>>(g, tb, ws, feats, scalars);
+    if (g.long_mode) {
+        k_seg2048<true><<<dim3(n, 1), kSegThreads, sizeof(Seg2048Smem), st>>>(g, tb, ws, feats, scalars, 1);
+        k_seg2048<true><<<dim3(n, 16), kSegThreads, sizeof(Seg2048Smem), st>>>(g, tb, ws, feats, scalars, 2);
+        k_seg2048<true><<<dim3(n, 1), kSegThreads, sizeof(Seg2048Smem), st>>>(g, tb, ws, feats, scalars, 3);
+        note_launch(2);
+    } else {
+        k_seg2048<false><<<n, kSegThreads, sizeof(Seg2048Smem), st>>>(g, tb, ws, feats, scalars, 0);
+    }
     note_launch();
 }
 
