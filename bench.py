@@ -93,6 +93,12 @@ def run_reference_arm(args):
     dt = time.perf_counter() - t0
     pool.close()
     v = done / dt
+    # the reference's own degree of parallelism, N_WORKERS = 2 (core.py:12,33) -- two worker
+    # processes here (the reference uses two GIL-bound threads, which can only be slower)
+    pool2 = mp.get_context("fork").Pool(2)
+    pool2.map(_cpu_worker, [(0, 1)] * 2)
+    v2, n2, dt2 = cpu_port_throughput(16, 2, pool2)
+    pool2.close()
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "segments/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
@@ -101,7 +107,9 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": v, "unit": "segments/s", "cores": cores, "kind": "port",
                          "sample": f"{per_step} synthetic segments per step through oracle/pipeline.py "
                                    "(numpy/scipy restatement of the reference's librosa path; the reference itself "
-                                   "is Python and cannot travel to the GPU box)"},
+                                   "is Python and cannot travel to the GPU box)",
+                         "n_workers_2": {"value": v2, "segments": n2,
+                                         "note": "same port with the reference's N_WORKERS = 2 (core.py:12)"}},
         "e2e": {"value": v, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
