@@ -172,7 +172,8 @@ enum bpc_wav_code { BPC_WAV_ERR_OPEN = -10, BPC_WAV_ERR_FORMAT = -11, BPC_WAV_ER
 int  bpc_wav_load_batch(const char* const* paths, int64_t n, int expected_sr, int64_t L, int16_t* out,
                         int32_t* sr, int32_t* frames, int32_t* code, int n_threads);
 
-/* Segments processed per internal chunk (= per kernel launch); env BPC_CHUNK overrides the default at create time. */
+/* Segments processed per internal chunk (= per kernel launch; default min(4144, max_batch) for 1 s segments); env
+ * BPC_CHUNK overrides the default at create time. */
 int  bpc_chunk_size(const bpc_handle* h);
 
 /* Kernel launches issued by this handle since creation (bench.py's `gpu_launches`). */
