@@ -533,6 +533,10 @@ int ensure_slots(bpc_handle* h) {
     int nt = env_t ? std::atoi(env_t) : 4;
     const int hw = (int)std::thread::hardware_concurrency();
     if (hw > 0 && nt > hw) nt = hw;
+    // one process per GPU (torchrun exports LOCAL_WORLD_SIZE): leave every rank its share of the host cores
+    const char* env_lws = std::getenv("LOCAL_WORLD_SIZE");
+    const int lws = env_lws ? std::atoi(env_lws) : 1;
+    if (!env_t && hw > 0 && lws > 1) nt = std::min(nt, std::max(1, hw / lws - 1));
     if (nt < 1) nt = 1;
     h->pool = new HostPool(nt - 1);
     const char* env_c = std::getenv("BPC_COMPACT_D2H");
