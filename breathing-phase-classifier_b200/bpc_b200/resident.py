@@ -53,6 +53,28 @@ class ResidentDS:
     def __len__(self):
         return int(self.feats.shape[0])
 
+    @classmethod
+    def from_shard(cls, engine, data_frame, feature_dir: str, is_training: bool, chunk: int = 2048):
+        """Load the rows of `data_frame` (the reference's `DS(data_frame, feature_dir, is_training)` arguments,
+        dataset.py:10) from a packed shard into HBM, in data-frame order; labels as in dataset.py:52."""
+        import torch
+        from .shards import PackedShard
+        shard = PackedShard(feature_dir)
+        ids = data_frame["ID"].tolist()
+        rows = np.asarray([shard.row[i] for i in ids], dtype=np.int64)
+        dev = torch.device(f"cuda:{engine.device}")
+        feats = torch.empty((len(rows),) + tuple(shard.feats.shape[1:]), dtype=torch.float32, device=dev)
+        scal = torch.empty((len(rows), shard.scalars.shape[1]), dtype=torch.float32, device=dev)
+        for lo in range(0, len(rows), chunk):                      # staged through pinned memory chunk by chunk
+            sel = rows[lo:lo + chunk]
+            feats[lo:lo + len(sel)].copy_(torch.from_numpy(np.ascontiguousarray(shard.feats[sel])).pin_memory(), non_blocking=True)
+            scal[lo:lo + len(sel)].copy_(torch.from_numpy(np.ascontiguousarray(shard.scalars[sel])).pin_memory(), non_blocking=True)
+        torch.cuda.synchronize(dev)
+        labels = None
+        if is_training:
+            labels = torch.tensor([1.0 if t == "E" else 0.0 for t in data_frame["Target"].tolist()], dtype=torch.float32, device=dev)
+        return cls(engine, feats, scal, labels, ids)
+
     def _collate(self, ia, ib, mode, lam, box):
         import torch
         n = int(ia.numel())

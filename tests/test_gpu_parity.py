@@ -357,6 +357,12 @@ def test_precompute_to_packed_shard_roundtrip(tmp_path, torch_cuda):
     r2 = CO.process_dataset_threaded(df, str(audio), str(tmp_path / "b"), "test", packed=True)
     assert all(ok for _, ok, _ in r1) and all(ok for _, ok, _ in r2)
     ds = PackedDS(df, str(tmp_path / "b" / "test"), is_training=False)
+    from bpc_b200.resident import ResidentDS                              # shard -> HBM, data-frame order
+    sub = df.iloc[[4, 0, 2]]
+    rds = ResidentDS.from_shard(CO._m._get_engine(), sub, str(tmp_path / "b" / "test"), is_training=False)
+    f_r, s_r, ids_r = rds.batch([0, 1, 2])
+    assert ids_r == [ids[4], ids[0], ids[2]]
+    assert torch_cuda.equal(f_r[1].cpu(), ds[0][0]) and torch_cuda.equal(s_r[2].cpu(), ds[2][1])
     for i, fid in enumerate(ids):
         d = np.load(tmp_path / "a" / (fid + ".npz"))
         f, s, got_id = ds[i]
