@@ -395,7 +395,7 @@ def test_process_and_save_npz_from_two_threads(tmp_path, torch_cuda):
     assert fid == "nope" and ok is False and isinstance(err, str) and err
 
 
-@pytest.mark.parametrize("d,n", [(2, 4), (5, 2)])
+@pytest.mark.parametrize("d,n", [(2, 4), (3, 2), (5, 2)])       # Hilbert radix plans: 5^3 4^3 2 | 5^3 3 4^3 | 5^4 4^3
 def test_long_segments_match_oracle(torch_cuda, d, n):
     """BASELINE config 4: expected_len = 16000 d (long mode) against the oracle run with Params(duration=d); same
     tolerances as the 1 s path."""
