@@ -527,8 +527,11 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
     const float* mag_b = ws.mag_even + (size_t)b * TE * kMag2048Stride;
     const size_t fstride = (size_t)kMag2048Stride;
     if (tid == 0) s_ncand = 0;
-    if (warp > 0) {
-        for (int f = warp - 1; f < TE; f += 7) {
+    // 1 s (32 even frames): warp 0 runs the sequential cumsums, one frame per lane, while warps 1..7 take the column
+    // maxima.  Long mode (hundreds of frames): all eight warps do the maxima, then all 256 threads take one frame each.
+    const int mx_first = LONG ? warp : warp - 1, mx_step = LONG ? 8 : 7;
+    if (LONG || warp > 0) {
+        for (int f = mx_first; f < TE; f += mx_step) {
             const float4* col4 = reinterpret_cast<const float4*>(mag_b + f * fstride);   // pad words 1025..1027 are 0
             float mx = 0.f;
             for (int i = lane; i < kMag2048Stride / 4; i += 32) {
@@ -538,9 +541,10 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
             mx = warp_max(mx);
             if (lane == 0) colmax[f] = mx;
         }
-    } else {
+    }
+    if (LONG || warp == 0) {
         // numpy's sequential float32 cumsum, one frame per lane; the loads run 32 elements ahead of the dependent adds
-        for (int f = lane; f < TE; f += 32) {
+        for (int f = LONG ? tid : lane; f < TE; f += LONG ? 256 : 32) {
             const float* col = mag_b + f * fstride;
             const float4* col4 = reinterpret_cast<const float4*>(col);
             float c = 0.f;
