@@ -498,9 +498,9 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
 // one thread per frame (1025 dependent float32 adds).  chroma_cens (process.py:53) estimates its tuning from the same
 // frames (estimate_tuning(y=y, bins_per_octave=36) -> piptrack n_fft 2048, hop 512).
 struct Even2048Smem {
-    float cand_mag[kMaxCand];
-    float cand_pitch[kMaxCand];
-    float sortbuf[kMaxCand];
+    float cand_mag[kMaxCand2048];
+    float cand_pitch[kMaxCand2048];
+    float sortbuf[kSelectWords];
     float colmax[kMaxFrames];
     float roll[kMaxFrames];
     int hist[100];
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x, T = g.T, TE = (T + 1) / 2;
     // candidate lists and per-frame arrays: shared memory (1 s), the segment's global scratch region in long mode
-    const int cap = LONG ? 492 * TE : kMaxCand;
+    const int cap = LONG ? 492 * TE : kMaxCand2048;
     float* lbase = ws.scratch + (size_t)b * ws.scratch_stride;
     float* cand_mag = LONG ? lbase : E.cand_mag;
     float* cand_pitch = LONG ? lbase + cap : E.cand_pitch;

@@ -423,8 +423,8 @@ __device__ void role_chroma_stft(int b, const Geometry g, const Tables& tb, cons
     const int cap = LONG ? 123 * T : kMaxCand;
     float* cand_mag = smem;                       // [cap]
     float* cand_pitch = cand_mag + cap;           // [cap]
-    float* sortbuf = cand_pitch + cap;            // [kMaxCand] (the selection needs 516 words)
-    float* colmax = sortbuf + kMaxCand;           // [T] (64 in shared memory)
+    float* sortbuf = cand_pitch + cap;            // [kSelectWords]
+    float* colmax = sortbuf + kSelectWords;       // [T] (64 in shared memory)
     float* raw = colmax + (LONG ? T : 64); // [12*T]
     int* hist = (int*)(raw + 12 * T);             // [100]
     __shared__ int s_ncand;
@@ -527,7 +527,7 @@ __device__ void role_chroma_stft(int b, const Geometry g, const Tables& tb, cons
 // roles 0 / 1 (three CTAs per SM) and roles 2 / 3 (four per SM) are launched separately with their own footprints
 constexpr int kConsumerSmemFloats = kPlaneRows * kMaxFrames + 40 * kMaxFrames + 120 * kMaxFrames;             // role_mfcc
 static_assert(kPlaneRows * kMaxFrames + 80 * kMaxFrames + kMaxFrames * kMaxFrames <= kConsumerSmemFloats, "role_mel layout");
-constexpr int kLightSmemFloats = 3 * kMaxCand + 64 + 12 * kMaxFrames + 100 + 28;                             // role_chroma_stft
+constexpr int kLightSmemFloats = 2 * kMaxCand + kSelectWords + 64 + 12 * kMaxFrames + 100 + 28;              // role_chroma_stft
 static_assert(64 * kMaxFrames <= kLightSmemFloats, "role_gammatone layout");
 
 // per-segment scratch floats of the four roles in long mode (each role owns a disjoint region)
@@ -537,7 +537,7 @@ __host__ __device__ inline size_t consumer_role_offset(int role, int T) {
     return role == 0 ? 0 : (role == 1 ? o1 : (role == 2 ? o2 : o3));
 }
 size_t consumer_scratch_floats(int T) {
-    return consumer_role_offset(3, T) + (size_t)2 * 123 * T + kMaxCand + (size_t)13 * T + 128;
+    return consumer_role_offset(3, T) + (size_t)2 * 123 * T + kSelectWords + (size_t)13 * T + 128;
 }
 
 template <bool LONG>

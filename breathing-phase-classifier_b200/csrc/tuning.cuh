@@ -122,7 +122,13 @@ __device__ __forceinline__ bool piptrack_candidate(float sm1, float s0, float sp
     return true;
 }
 
+// Candidate capacities.  A piptrack candidate is a strict local maximum (S[k] > S[k-1], S[k] >= S[k+1]), so two
+// neighbouring bins never both qualify: at most ceil(bins / 2) per frame.
+//   STFT-512 : bins 5..127 (123) x 63 frames  -> <= 62 * 63 = 3906
+//   STFT-2048: bins 20..511 (492) x 32 frames -> <= 246 * 32 = 7872   (white noise reaches ~5200: r01 v27 overflowed 4096)
 constexpr int kMaxCand = 4096;
+constexpr int kMaxCand2048 = 7936;
+constexpr int kSelectWords = 1024;       // scratch of tuning_from_candidates (2 x 256 counters + 4 words of state)
 
 
 }  // namespace bpc

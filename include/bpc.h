@@ -56,7 +56,8 @@ enum bpc_status {
 /* per-segment status bits */
 #define BPC_SEG_NONFINITE      1u   /* input had NaN/Inf */
 #define BPC_SEG_TUNING_EMPTY   2u   /* pitch_tuning saw an empty frequency set -> tuning 0.0 (librosa warns) */
-#define BPC_SEG_CAND_OVERFLOW  4u   /* more piptrack candidates than the on-chip list holds (results for chroma invalid) */
+#define BPC_SEG_CAND_OVERFLOW  4u   /* more piptrack candidates than the list holds (chroma invalid); the lists hold the
+                                       combinatorial maximum, so this cannot occur for finite input */
 #define BPC_SEG_SILENT         8u   /* all-zero segment */
 
 /* process.py:12-23 / methods.py:10-22 module constants */

@@ -504,3 +504,27 @@ def test_c_abi_error_codes_on_device(torch_cuda):
         eng.precompute_host(np.zeros((2, 16000), np.float64))
     eng.close()
     eng.close()                                                           # idempotent
+
+
+def test_broadband_noise_never_overflows_the_candidate_lists(engine, torch_cuda):
+    """White noise has a piptrack candidate at about every third bin (r01 v27 overflowed its 4096-entry list on the
+    STFT-2048 path and flagged BPC_SEG_CAND_OVERFLOW); the lists now hold the combinatorial maximum, so noise segments
+    must come back with status 0 and the oracle's tuning bins and chroma plane."""
+    torch = torch_cuda
+    from oracle import pipeline as P
+    rng = np.random.default_rng(5)
+    Y = []
+    for i in range(6):
+        y = rng.standard_normal(16000) * (0.05 + 0.12 * i)
+        Y.append(np.round(np.clip(y, -0.95, 0.95) * 32768).astype(np.int16))
+    Y = np.stack(Y)
+    f, s, st = engine.precompute(torch.from_numpy(Y).cuda())
+    assert int(st.abs().sum()) == 0, st
+    tun = engine.debug("tuning", len(Y))
+    edges = np.linspace(-0.5, 0.5, 101)
+    for i in range(len(Y)):
+        d = {}
+        ch, sc = P.segment_features(Y[i].astype(np.float32) / np.float32(32768.0), debug=d)
+        t12 = int(np.argmin(np.abs(edges[:100] - d["tuning12"]))); t36 = int(np.argmin(np.abs(edges[:100] - d["tuning36"])))
+        assert tun[i].tolist() == [t12, t36]
+        assert np.abs(f[i].cpu().numpy() - P.stack_sorted(ch)).max() < 2e-4
