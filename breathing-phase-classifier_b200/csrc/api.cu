@@ -269,7 +269,16 @@ int build_tables(bpc_handle* h) {
             for (size_t i = 0; i < d.size(); ++i) f[i] = make_float2((float)d[i].x, (float)d[i].y);
             return f;
         };
-        if ((rc = upload(h, to_f(twiddles(8000, 8000)), &tb.tw8000f))) return rc;
+        for (int span : {8000, 400}) {                               // per-pass twiddles of the radix-20 FFT-8000
+            const int q = span / 20;
+            std::vector<float2> t((size_t)20 * q);
+            for (int k = 0; k < 20; ++k)
+                for (int pos = 0; pos < q; ++pos) {
+                    const double ang = -2.0 * kPi * double(k * pos) / double(span);
+                    t[(size_t)k * q + pos] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+                }
+            if ((rc = upload(h, t, span == 8000 ? &tb.tw20a : &tb.tw20b))) return rc;
+        }
         if ((rc = upload(h, to_f(twiddles(16000, 8001)), &tb.ptw16000f))) return rc;
     }
     tb.tw_long = nullptr;

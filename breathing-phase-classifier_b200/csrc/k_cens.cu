@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
                     }
                     // complex64 response, then V /= sqrt(lengths) (complex128 math, complex64 store), then |V|
                     const double sl = isl[r];
-                    cqmag[r] = c64_abs(make_double2((double)(cr * pow2) * sl, (double)(ci * pow2) * sl));
+                    cqmag[r] = c64_abs_f32((float)((double)(cr * pow2) * sl), (float)((double)(ci * pow2) * sl));
                 }
             }
             __syncwarp();

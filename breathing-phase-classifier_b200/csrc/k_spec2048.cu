@@ -99,27 +99,6 @@ __device__ __forceinline__ void warp_band_minmax(const float* row, int lo, int l
     *peak = (double)__uint_as_float(__reduce_max_sync(0xffffffffu, mx));
 }
 
-// |re + i im| of a complex64 the way numpy / glibc do it: (float)sqrt((double)re * re + (double)im * im), evaluated in
-// float32 pairs: s = hi + lo exactly (error-free products and sum), r = sqrt(hi) corrected by the residual.  The
-// result differs from the double-precision evaluation only when the exact value lies within ~1e-13 (relative) of a
-// float32 rounding boundary.  (The DSQRT sequence of c64_abs was 6 % of this kernel's instructions.)
-__device__ __forceinline__ float c64_abs_f32(float re, float im) {
-    const float a = fabsf(re), b = fabsf(im);
-    const float x = fmaxf(a, b), y = fminf(a, b);
-    const float p = __fmul_rn(x, x), pe = __fmaf_rn(x, x, -p);          // x^2 = p + pe
-    const float q = __fmul_rn(y, y), qe = __fmaf_rn(y, y, -q);          // y^2 = q + qe
-    const float hi = __fadd_rn(p, q);
-    const float lo = __fadd_rn(__fadd_rn(__fsub_rn(p, hi), q), __fadd_rn(pe, qe));   // p >= q: fast two-sum
-    float rs;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(hi));           // ~2 ulp: the residual step absorbs it
-    const float r0 = __fmul_rn(hi, rs);
-    const float res = __fadd_rn(__fmaf_rn(-r0, r0, hi), lo);            // (hi + lo) - r0^2
-    float out = __fmaf_rn(res, __fmul_rn(0.5f, rs), r0);
-    if (!(x > 1e-18f && x < 1e18f))                                     // zero / denormal squares / overflow: exact path
-        out = (float)sqrt((double)re * (double)re + (double)im * (double)im);
-    return out;
-}
-
 // ================================================================================================ k_frame2048
 // One warp per frame: Hann * samples -> team_fft<32> (fft_reg.cuh: 32 lanes x 32 register-resident complex points, one
 // shared-memory exchange) -> real split -> |X| row (float32, 1025 bins) in the same shared memory -> every per-frame

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kS512Threads, 4) k_stft512(const float* __rest
         team_fft<16>(a, tw, 1, xch, h);
         float* out = mag + (size_t)fc * kMagStride;
         auto emit = [&](int k, double2 t2) {
-            const float v = c64_abs(make_double2(0.5 * t2.x, 0.5 * t2.y));
+            const float v = c64_abs_f32(0.5f * (float)t2.x, 0.5f * (float)t2.y);
             if (valid) out[k] = v;
         };
         const double z0 = a[0].x - a[0].y;                    // lane h == 0: X[256] = Re Z[0] - Im Z[0]

@@ -6,6 +6,7 @@
 #include "kernels.cuh"
 #include "fft.cuh"
 #include "fft_reg.cuh"
+#include "fft20.cuh"
 
 namespace bpc {
 
@@ -364,12 +365,14 @@ __global__ void __launch_bounds__(kAcThreads, 1) k_autocorr(const float* __restr
 }
 
 // ================================================================================================== k_hilbert
-// scipy.signal.hilbert(y) for L = 16000 through two complex FFT-8000 (8000 = 4^3 * 5^3) in FP64:
-//   forward: real-FFT split of y;  G[k] = -i Y[k] (0 < k < 8000), G[0] = G[8000] = 0;  h = irfft(G).
-// The forward transform is decimation-in-frequency (natural in, digit-reversed out), the inverse runs the transposed
-// (decimation-in-time) network on the data where it lies, so no reordering pass is needed.
+// scipy.signal.hilbert(y) for L = 16000 through two float32 complex FFT-8000 (scipy runs float32 pocketfft on float32
+// input):  forward: real-FFT split of y;  G[k] = -i Y[k] (0 < k < 8000), G[0] = G[8000] = 0;  h = irfft(G).
+// 8000 = 20 x 20 x 20: three register-resident radix-20 passes each way (fft20.cuh; v0-v27 ran six radix-5 / radix-4
+// passes each way, 53 % of whose shared-memory wavefronts were bank conflicts).  The forward transform is decimation in
+// frequency (natural in, digit-reversed out), the inverse runs the transposed (decimation-in-time) network on the data
+// where it lies, so no reordering pass is needed.
 constexpr int kHN = 8000;
-constexpr int kHilbertThreads = 512;
+constexpr int kHilbertThreads = 416;        // 400 butterflies per pass; 2 CTAs / SM (shared memory) -> 78 registers
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -402,43 +405,7 @@ __device__ __forceinline__ void dft_small(float2* a) {
     }
 }
 
-// one pass over all N/R butterflies with the given span; DIF: twiddle after the small DFT, DIT: before.
-template <int R, bool kDit>
-__device__ __forceinline__ void mixed_pass(float2* x, int span, const float2* __restrict__ tw, int tid) {
-    const int q = span / R, ts = kHN / span;
-    for (int j = tid; j < kHN / R; j += kHilbertThreads) {
-        const int blk = j / q, pos = j - blk * q;
-        const int base = blk * span + pos;
-        float2 a[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) a[r] = x[base + r * q];
-        if (kDit && pos != 0) {
-#pragma unroll
-            for (int r = 1; r < R; ++r) a[r] = cmul(a[r], tw[r * pos * ts]);
-        }
-        dft_small<R>(a);
-        if (!kDit && pos != 0) {
-#pragma unroll
-            for (int r = 1; r < R; ++r) a[r] = cmul(a[r], tw[r * pos * ts]);
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) x[base + r * q] = a[r];
-    }
-    __syncthreads();
-}
-
-// position of output bin k after the DIF passes with radices 5,5,5,4,4,4 (spans 8000,1600,320,64,16,4)
-__device__ __forceinline__ int hilbert_pos(int k) {
-    int p = 0, s = kHN;
-    int d;
-    d = k % 5; k /= 5; s /= 5; p += d * s;
-    d = k % 5; k /= 5; s /= 5; p += d * s;
-    d = k % 5; k /= 5; s /= 5; p += d * s;
-    d = k & 3; k >>= 2; s >>= 2; p += d * s;
-    d = k & 3; k >>= 2; s >>= 2; p += d * s;
-    p += k;
-    return p;
-}
+constexpr int kHilbertXBytes = kH20Pitch * (int)sizeof(float2);      // 67200: padded FFT array, later the envelope
 
 struct HilbertTail {
     double dscratch[32];
@@ -451,79 +418,54 @@ struct HilbertTail {
 __global__ void __launch_bounds__(kHilbertThreads, 2) k_hilbert(const float* __restrict__ y, Geometry g, Tables tb,
                                                               Workspace ws, float* scalars) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* X = reinterpret_cast<float2*>(smem_raw);                         // [8000]; later env [16000] floats
-    HilbertTail& S = *reinterpret_cast<HilbertTail*>(smem_raw + sizeof(float) * 16000 + sizeof(unsigned short) * 16000);
+    float2* X = reinterpret_cast<float2*>(smem_raw);                         // [8400] padded; later env [16000] floats
+    HilbertTail& S = *reinterpret_cast<HilbertTail*>(smem_raw + kHilbertXBytes + sizeof(unsigned short) * 16000);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x, L = g.L;                                        // L == 16000 (checked on the host)
     const float* yb = y + (size_t)b * L;
     for (int m = tid; m < kHN; m += kHilbertThreads) {
         const float2 v = __ldg(reinterpret_cast<const float2*>(yb) + m);
-        X[m] = v;
+        X[h20_pad(m)] = v;
     }
     __syncthreads();
-    const float2* tw = tb.tw8000f;
-    mixed_pass<5, false>(X, 8000, tw, tid);
-    mixed_pass<5, false>(X, 1600, tw, tid);
-    mixed_pass<5, false>(X, 320, tw, tid);
-    mixed_pass<4, false>(X, 64, tw, tid);
-    mixed_pass<4, false>(X, 16, tw, tid);
-    mixed_pass<4, false>(X, 4, tw, tid);
+    const float2* twa = tb.tw20a;                                             // [20][400]: exp(-2 pi i k pos / 8000)
+    const float2* twb = tb.tw20b;                                             // [20][20]:  exp(-2 pi i k pos / 400)
+    if (tid < kH20Bfly) h20_butterfly<8000, false>(X, twa, tid);
+    __syncthreads();
+    if (tid < kH20Bfly) h20_butterfly<400, false>(X, twb, tid);
+    __syncthreads();
+    if (tid < kH20Bfly) h20_butterfly<20, false>(X, nullptr, tid);
+    __syncthreads();
     // pairs (k, N-k): real-FFT split -> Y[k], Y[N-k]; G = -i Y; inverse split -> conj(Z), written back in place
-    for (int k = tid; k <= kHN / 2; k += kHilbertThreads) {
-        const int kn = (kHN - k) % kHN;
-        const int pk = hilbert_pos(k), pn = hilbert_pos(kn);
-        const float2 zk = X[pk], zn = X[pn];
-        const float2 w = tb.ptw16000f[k];                                      // exp(-2 pi i k / 16000)
-        // Y[k] = E + w O ; Y[N-k] = conj(E) - conj(w) conj(O) = conj(E - w O)
-        const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-        const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
-        const float2 wo = cmul(w, o);
-        float2 yk = cadd(e, wo);
-        float2 yn = cconj(csub(e, wo));
-        // G = -i Y on 0 < k < N (bins k and N-k of the half spectrum), 0 at k = 0 and k = N (both live in pair k = 0)
-        float2 gk = make_float2(yk.y, -yk.x), gn = make_float2(yn.y, -yn.x);
-        if (k == 0) { gk = make_float2(0.f, 0.f); gn = make_float2(0.f, 0.f); }
-        // for k == 0: X_half[0] = gk, X_half[N] = gn (the "N-k" partner of bin 0 is bin N)
-        // inverse split: E' = (G[k] + conj(G[N-k]))/2, O' = (G[k] - conj(G[N-k]))/2 * conj(w), Z = E' + i O'
-        const float2 e2 = make_float2(0.5f * (gk.x + gn.x), 0.5f * (gk.y - gn.y));
-        const float2 d2 = make_float2(0.5f * (gk.x - gn.x), 0.5f * (gk.y + gn.y));
-        const float2 o2 = cmul(d2, cconj(w));
-        const float2 z = make_float2(e2.x - o2.y, e2.y + o2.x);
-        // partner bin: Z[N-k] = conj(E') + i * conj(O') * (-1) ... derive from the same quantities:
-        // E'[N-k] = conj(E'[k]); O'[N-k] = (G[N-k] - conj(G[k]))/2 * conj(w[N-k]) with w[N-k] = -conj(w[k])
-        const float2 dn = make_float2(0.5f * (gn.x - gk.x), 0.5f * (gn.y + gk.y));
-        const float2 on = cmul(dn, make_float2(-w.x, -w.y));                 // conj(w[N-k]) = -w[k]
-        const float2 zn2 = make_float2(e2.x - on.y, -e2.y + on.x);
-        X[pk] = cconj(z);
-        if (kn != k && k != 0) X[pn] = cconj(zn2);
-    }
+    for (int k = tid; k <= kHN / 2; k += kHilbertThreads) h20_split_pair(X, k, __ldg(tb.ptw16000f + k));
     __syncthreads();
-    mixed_pass<4, true>(X, 4, tw, tid);
-    mixed_pass<4, true>(X, 16, tw, tid);
-    mixed_pass<4, true>(X, 64, tw, tid);
-    mixed_pass<5, true>(X, 320, tw, tid);
-    mixed_pass<5, true>(X, 1600, tw, tid);
-    mixed_pass<5, true>(X, 8000, tw, tid);
+    if (tid < kH20Bfly) h20_butterfly<20, true>(X, nullptr, tid);
+    __syncthreads();
+    if (tid < kH20Bfly) h20_butterfly<400, true>(X, twb, tid);
+    __syncthreads();
+    if (tid < kH20Bfly) h20_butterfly<8000, true>(X, twa, tid);
+    __syncthreads();
     // h[2m] = Re(conj(out[m])) / N, h[2m+1] = Im(conj(out[m])) / N; envelope = |y + i h| (float32 like complex64 abs)
-    float* env = reinterpret_cast<float*>(smem_raw);                           // [16000], first half of X's storage
+    float* env = reinterpret_cast<float*>(smem_raw);                           // [16000], over X's storage
     {
-        float e0[16], e1[16];
+        constexpr int kPer = (kHN + kHilbertThreads - 1) / kHilbertThreads;   // 20
+        float e0[kPer], e1[kPer];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < kPer; ++i) {
             const int m = tid + kHilbertThreads * i;
             if (m < kHN) {
-                const float2 o = X[m];
+                const float2 o = X[h20_pad(m)];
                 const float2 v = __ldg(reinterpret_cast<const float2*>(yb) + m);
                 const float h0 = o.x * (1.0f / (float)kHN), h1 = -o.y * (1.0f / (float)kHN);
-                e0[i] = (float)sqrt((double)v.x * (double)v.x + (double)h0 * (double)h0);   // np.abs(complex64)
-                e1[i] = (float)sqrt((double)v.y * (double)v.y + (double)h1 * (double)h1);
+                e0[i] = c64_abs_f32(v.x, h0);                                  // np.abs(complex64)
+                e1[i] = c64_abs_f32(v.y, h1);
             }
         }
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < kPer; ++i) {
             const int m = tid + kHilbertThreads * i;
-            if (m < kHN) { env[2 * m] = e0[i]; env[2 * m + 1] = e1[i]; }
+            if (m < kHN) reinterpret_cast<float2*>(env)[m] = make_float2(e0[i], e1[i]);
         }
     }
     __syncthreads();
@@ -535,7 +477,7 @@ __global__ void __launch_bounds__(kHilbertThreads, 2) k_hilbert(const float* __r
     const float estd = (float)sqrt(fmax(0.0, q / L - (s / L) * (s / L)));
     // scipy.signal.find_peaks(env, height=emean, distance=1600): local maxima (plateau mid-points), height filter.
     // Candidates are compacted into a list (r01 v3: the selection rounds rescanned all 16000 flags, 20 % of the kernel).
-    unsigned short* clist = reinterpret_cast<unsigned short*>(smem_raw + sizeof(float) * 16000);   // after env
+    unsigned short* clist = reinterpret_cast<unsigned short*>(smem_raw + kHilbertXBytes);          // after X / env
     constexpr int kMaxList = 16000;                                            // 32 KB: every sample could be listed
     constexpr int kGone = 0xffff;
     if (tid == 0) S.best_i = 0;                                                // list length
@@ -842,7 +784,7 @@ void launch_hilbert(const float* y, int n, const Geometry& g, const Tables& tb, 
         note_launch();
         return;
     }
-    const int bytes = (int)(sizeof(float) * 16000 + sizeof(unsigned short) * 16000 + sizeof(HilbertTail));
+    const int bytes = (int)(kHilbertXBytes + sizeof(unsigned short) * 16000 + sizeof(HilbertTail));
     static bool done = false;
     if (!done) {
         cudaFuncSetAttribute(k_hilbert, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);

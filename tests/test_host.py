@@ -227,6 +227,33 @@ def test_register_fft_index_logic_on_host(tmp_path):
     assert len(errs) == 2 and errs[0] < 1e-10 and errs[1] < 1e-9, out
 
 
+def test_radix20_hilbert_fft_on_host(tmp_path):
+    """csrc/fft20.cuh (the three radix-20 passes each way of k_hilbert, padded storage, digit-reversed spectrum, pair
+    split) is __host__ __device__: run every butterfly on the CPU and compare with scipy.signal.hilbert (methods.py:72)."""
+    import shutil
+    import subprocess
+    import scipy.signal
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = tmp_path / "fft20_host_test"
+    src = os.path.join(ROOT, "tests", "host", "fft20_host_test.cpp")
+    inc = os.path.join(ROOT, "breathing-phase-classifier_b200", "csrc")
+    subprocess.run([nvcc, "-x", "cu", "-std=c++17", "-Wno-deprecated-gpu-targets", "-I", inc, src, "-o", str(exe)],
+                   check=True, capture_output=True)
+    rng = np.random.default_rng(5)
+    for trial in range(2):
+        y = (rng.standard_normal(16000) * (np.hanning(16000) if trial else 1.0)).astype(np.float32)
+        y.tofile(tmp_path / "in.f32")
+        subprocess.run([str(exe), str(tmp_path / "in.f32"), str(tmp_path / "out.f32")], check=True)
+        h = np.fromfile(tmp_path / "out.f32", dtype=np.float32)
+        ref = np.imag(scipy.signal.hilbert(y.astype(np.float64)))
+        ref32 = np.imag(scipy.signal.hilbert(y))                      # what the reference runs: float32 pocketfft
+        scale = np.abs(ref).max()
+        assert np.abs(h - ref).max() / scale < 6e-7
+        assert np.abs(h - ref).max() < 2.0 * np.abs(ref32 - ref).max() + 1e-7 * scale
+
+
 # ------------------------------------------------------------------------------------- output writer / packed shard
 def _fake_rows(n, T=63, S=36, seed=3):
     rng = np.random.default_rng(seed)
