@@ -26,6 +26,7 @@
 #include "../../include/bpc.h"
 #include "kernels.cuh"
 #include "tables.hpp"
+#include "fft20.cuh"
 
 using namespace bpc;
 
@@ -280,6 +281,11 @@ int build_tables(bpc_handle* h) {
             if ((rc = upload(h, t, span == 8000 ? &tb.tw20a : &tb.tw20b))) return rc;
         }
         if ((rc = upload(h, to_f(twiddles(16000, 8001)), &tb.ptw16000f))) return rc;
+        {
+            std::vector<unsigned short> pos(kH20N + 1);
+            for (int k = 0; k <= kH20N; ++k) pos[k] = (unsigned short)h20_pad(h20_pos(k % kH20N));
+            if ((rc = upload(h, pos, &tb.h20pos))) return rc;
+        }
     }
     tb.tw_long = nullptr;
     tb.ptw_long = nullptr;

@@ -110,9 +110,8 @@ BPC_HD void h20_butterfly(float2* x, const float2* __restrict__ tw, int j) {
 // real-FFT split -> Y[k], Y[N-k] (bins of the 16000-point real transform);  G = -i Y on 0 < k < 8000, 0 at k = 0 and
 // k = 8000;  inverse split -> the 8000-point spectrum whose inverse transform is h[2m] + i h[2m+1]; stored conjugated
 // (the inverse is run as a forward transform of the conjugate).  w = exp(-2 pi i k / 16000).
-BPC_HD void h20_split_pair(float2* x, int k, float2 w) {
-    const int kn = (kH20N - k) % kH20N;
-    const int pk = h20_pad(h20_pos(k)), pn = h20_pad(h20_pos(kn));
+// pk / pn: padded storage positions of bins k and (N - k) % N, h20_pad(h20_pos(.)) (the kernel reads them from a table).
+BPC_HD void h20_split_pair(float2* x, int k, int pk, int pn, float2 w) {
     const float2 zk = x[pk], zn = x[pn];
     // Y[k] = E + w O ; Y[N-k] = conj(E - w O)
     const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
@@ -133,7 +132,7 @@ BPC_HD void h20_split_pair(float2* x, int k, float2 w) {
     const float2 on = f2mul(dn, make_float2(-w.x, -w.y));
     const float2 zn2 = make_float2(e2.x - on.y, -e2.y + on.x);
     x[pk] = make_float2(z.x, -z.y);
-    if (kn != k && k != 0) x[pn] = make_float2(zn2.x, -zn2.y);
+    if (pn != pk) x[pn] = make_float2(zn2.x, -zn2.y);             // k == 0 and k == N / 2 pair with themselves
 }
 
 }  // namespace bpc

@@ -106,13 +106,13 @@ __device__ __forceinline__ void warp_band_minmax(const float* row, int lo, int l
 // workspace to HBM and read it back in a second kernel); the even (hop-512) frames additionally store their row for
 // k_even2048.
 constexpr int kF2Warps = 4;
-constexpr int kF2RowBytes = 32 * 33 * 16;            // exchange buffer, later the |X| row (1028 floats)
+constexpr int kF2RowBytes = 32 * 33 * 8;             // exchange buffer (one component at a time), later the |X| row (1028 floats)
 
 __global__ void __launch_bounds__(32 * kF2Warps, 3) k_frame2048(const float* __restrict__ y, Geometry g, Tables tb,
                                                                  Workspace ws, int total_frames) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double2* xch = reinterpret_cast<double2*>(smem_raw + (size_t)warp * kF2RowBytes);
+    double* xch = reinterpret_cast<double*>(smem_raw + (size_t)warp * kF2RowBytes);
     float* row = reinterpret_cast<float*>(xch);
     const int T = g.T, L = g.L, hop = g.hop, TE = (T + 1) / 2;
     const int partner = (32 - lane) & 31;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(32 * kF2Warps, 3) k_frame2048(const float* __r
                 const double2 w = __ldg(win2 + m);
                 a[j] = make_double2((double)v.x * w.x, (double)v.y * w.y);
             }
-            team_fft<32>(a, twa, 32, xch, lane);
+            team_fft_split<32>(a, twa, 32, xch, lane);
             const double z0 = a[0].x - a[0].y;                 // lane 0: X[1024] = Re Z[0] - Im Z[0]
             auto emit = [&](int k, double2 t2) { row[k] = c64_abs_f32(0.5f * (float)t2.x, 0.5f * (float)t2.y); };
             team_rsplit<32, 0, 31>(a, wl, lane, partner, emit);

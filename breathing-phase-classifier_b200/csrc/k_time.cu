@@ -437,7 +437,8 @@ __global__ void __launch_bounds__(kHilbertThreads, 2) k_hilbert(const float* __r
     if (tid < kH20Bfly) h20_butterfly<20, false>(X, nullptr, tid);
     __syncthreads();
     // pairs (k, N-k): real-FFT split -> Y[k], Y[N-k]; G = -i Y; inverse split -> conj(Z), written back in place
-    for (int k = tid; k <= kHN / 2; k += kHilbertThreads) h20_split_pair(X, k, __ldg(tb.ptw16000f + k));
+    for (int k = tid; k <= kHN / 2; k += kHilbertThreads)
+        h20_split_pair(X, k, __ldg(tb.h20pos + k), __ldg(tb.h20pos + kHN - k), __ldg(tb.ptw16000f + k));
     __syncthreads();
     if (tid < kH20Bfly) h20_butterfly<20, true>(X, nullptr, tid);
     __syncthreads();
@@ -470,7 +471,12 @@ __global__ void __launch_bounds__(kHilbertThreads, 2) k_hilbert(const float* __r
     }
     __syncthreads();
     double s = 0.0, q = 0.0;
-    for (int i = tid; i < L; i += kHilbertThreads) { const double v = (double)env[i]; s += v; q += v * v; }
+    for (int c = tid; c < L / 4; c += kHilbertThreads) {
+        const float4 v = reinterpret_cast<const float4*>(env)[c];
+        const double a = (double)v.x, b2 = (double)v.y, c2 = (double)v.z, d = (double)v.w;
+        s += (a + b2) + (c2 + d);
+        q += fma(a, a, b2 * b2) + fma(c2, c2, d * d);
+    }
     s = block_sum(s, S.dscratch);
     q = block_sum(q, S.dscratch);
     const float emean = (float)(s / L);
@@ -482,11 +488,21 @@ __global__ void __launch_bounds__(kHilbertThreads, 2) k_hilbert(const float* __r
     constexpr int kGone = 0xffff;
     if (tid == 0) S.best_i = 0;                                                // list length
     __syncthreads();
-    for (int i = tid + 1; i < L - 1; i += kHilbertThreads) {
-        if (env[i - 1] < env[i]) {
+    // four samples per thread and step; only rising edges that do not rise further (strict peaks and plateau starts)
+    // take the general path
+    for (int c = tid; c < L / 4; c += kHilbertThreads) {
+        const float4 v = reinterpret_cast<const float4*>(env)[c];
+        const int i0 = 4 * c;
+        const float lft = i0 > 0 ? env[i0 - 1] : FLT_MAX, rgt = i0 + 4 < L ? env[i0 + 4] : FLT_MAX;
+        unsigned m = (unsigned)(lft < v.x && v.x >= v.y) | ((unsigned)(v.x < v.y && v.y >= v.z) << 1) |
+                     ((unsigned)(v.y < v.z && v.z >= v.w) << 2) | ((unsigned)(v.z < v.w && v.w >= rgt) << 3);
+        while (m) {
+            const int i = i0 + __ffs(m) - 1;
+            m &= m - 1;
+            const float e = env[i];
             int ahead = i + 1;
-            while (ahead < L - 1 && env[ahead] == env[i]) ++ahead;
-            if (env[ahead] < env[i]) {
+            while (ahead < L - 1 && env[ahead] == e) ++ahead;
+            if (env[ahead] < e) {
                 const int mid = (i + ahead - 1) / 2;
                 if (env[mid] >= emean) {
                     const int slot = atomicAdd(&S.best_i, 1);

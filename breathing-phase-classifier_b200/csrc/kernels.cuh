@@ -41,6 +41,7 @@ struct Tables {
     const double* hamming400;     // [400]
     // Hilbert (FFT-8000 = 4^3 * 5^3)
     const float2* tw20a;          // [20][400] exp(-2 pi i k pos / 8000), float32: scipy.signal.hilbert runs a float32 FFT on float32 input
+    const unsigned short* h20pos; // [8001] padded storage position of bin k % 8000 after the forward passes (fft20.cuh)
     const float2* tw20b;          // [20][20]  exp(-2 pi i k pos / 400)  (radix-20 passes of the FFT-8000, fft20.cuh)
     const float2* ptw16000f;      // exp(-2 pi i k / 16000), k <= 8000
     // long mode Hilbert (FFT-N, N = L / 2 = 2^a 3^b 5^c): exp(-2 pi i j / N), j < N and exp(-2 pi i k / L), k <= N

@@ -33,7 +33,8 @@ int main(int argc, char** argv) {
     for (int j = 0; j < kH20Bfly; ++j) h20_butterfly<8000, false>(x.data(), twa.data(), j);
     for (int j = 0; j < kH20Bfly; ++j) h20_butterfly<400, false>(x.data(), twb.data(), j);
     for (int j = 0; j < kH20Bfly; ++j) h20_butterfly<20, false>(x.data(), nullptr, j);
-    for (int k = 0; k <= kH20N / 2; ++k) h20_split_pair(x.data(), k, ptw[k]);
+    for (int k = 0; k <= kH20N / 2; ++k)
+        h20_split_pair(x.data(), k, h20_pad(h20_pos(k)), h20_pad(h20_pos((kH20N - k) % kH20N)), ptw[k]);
     for (int j = 0; j < kH20Bfly; ++j) h20_butterfly<20, true>(x.data(), nullptr, j);
     for (int j = 0; j < kH20Bfly; ++j) h20_butterfly<400, true>(x.data(), twb.data(), j);
     for (int j = 0; j < kH20Bfly; ++j) h20_butterfly<8000, true>(x.data(), twa.data(), j);
