@@ -337,28 +337,45 @@ int build_tables(bpc_handle* h) {
         if ((rc = upload(h, all, &tb.chroma))) return rc;
     }
     {
-        std::vector<int16_t> col;
+        // The sparsified basis rows (util.sparsify_rows, 8..16 non-zeros) are stored as dense bands: row r covers the
+        // bins [start, start + kCqtEllWidth) with zeros in the few gaps, so the kernel walks a row without column
+        // indices (a zero weight adds +-0 to the accumulators: the sums stay bit-identical to the sparse product).
+        std::vector<int16_t> start;
         std::vector<float> re, im;
         std::vector<double> sl;
-        int ell_used = 1;
+        int gw[3] = {1, 1, 1};
         for (int i = 0; i < kNumTunings; ++i) {
             CqtBasisEll e = cqt_basis(p.sr, edges[i]);
             if (e.col.empty()) { h->err = "CQT basis row wider than the ELL width"; return BPC_ERR_UNSUPPORTED; }
-            for (int16_t c : e.col)
-                if (c >= 0 && (c < 60 || c > 144)) { h->err = "CQT basis support outside the staged bin window"; return BPC_ERR_UNSUPPORTED; }
-            for (int r = 0; r < kCqtBinsPerOct; ++r)
-                for (int j = 0; j < kCqtEllWidth; ++j)
-                    if (e.col[r * kCqtEllWidth + j] >= 0) ell_used = std::max(ell_used, j + 1);
-            col.insert(col.end(), e.col.begin(), e.col.end());
-            re.insert(re.end(), e.re.begin(), e.re.end());
-            im.insert(im.end(), e.im.begin(), e.im.end());
+            std::vector<float> bre((size_t)kCqtBinsPerOct * kCqtEllWidth, 0.f), bim(bre.size(), 0.f);
+            for (int r = 0; r < kCqtBinsPerOct; ++r) {
+                int lo = 1 << 30, hi = -1;
+                for (int j = 0; j < kCqtEllWidth; ++j) {
+                    const int c = e.col[r * kCqtEllWidth + j];
+                    if (c >= 0) { lo = std::min(lo, c); hi = std::max(hi, c); }
+                }
+                if (hi < 0) { lo = 64; hi = 64; }
+                if (lo < 60 || hi > 144) { h->err = "CQT basis support outside the staged bin window"; return BPC_ERR_UNSUPPORTED; }
+                if (hi - lo + 1 > kCqtEllWidth) { h->err = "CQT basis row wider than the band width"; return BPC_ERR_UNSUPPORTED; }
+                for (int j = 0; j < kCqtEllWidth; ++j) {
+                    const int c = e.col[r * kCqtEllWidth + j];
+                    if (c >= 0) {
+                        bre[(size_t)r * kCqtEllWidth + (c - lo)] = e.re[r * kCqtEllWidth + j];
+                        bim[(size_t)r * kCqtEllWidth + (c - lo)] = e.im[r * kCqtEllWidth + j];
+                    }
+                }
+                start.push_back((int16_t)lo);
+                gw[r / 16] = std::max(gw[r / 16], hi - lo + 1);
+            }
+            re.insert(re.end(), bre.begin(), bre.end());
+            im.insert(im.end(), bim.begin(), bim.end());
             sl.insert(sl.end(), e.sqrt_len.begin(), e.sqrt_len.end());
         }
-        if ((rc = upload(h, col, &tb.cqt_col))) return rc;
+        if ((rc = upload(h, start, &tb.cqt_start))) return rc;
         if ((rc = upload(h, re, &tb.cqt_re))) return rc;
         if ((rc = upload(h, im, &tb.cqt_im))) return rc;
         if ((rc = upload(h, sl, &tb.cqt_sqrt_len))) return rc;
-        tb.cqt_ell_used = ell_used;
+        for (int q = 0; q < 3; ++q) tb.cqt_gw[q] = gw[q];
     }
     {
         std::vector<double> hb = halfband_taps();

@@ -20,6 +20,13 @@ __device__ __forceinline__ float c64_abs(double2 x) {
 // float32 pairs: s = hi + lo exactly (error-free products and sum), r = sqrt(hi) corrected by the residual.  The
 // result differs from the double-precision evaluation only when the exact value lies within ~1e-13 (relative) of a
 // float32 rounding boundary.  (The DSQRT sequence of c64_abs was 6 % of this kernel's instructions.)
+// exact path of c64_abs_f32, out of line: its DSQRT sequence is ~32 instructions per call site, and k_frame2048 has 32
+// call sites -- inlined it pushed that kernel's code past the instruction cache (r01 v30: 180 KB of SASS, 11 of 12
+// issue slots lost to "no instruction" stalls)
+static __device__ __noinline__ float c64_abs_exact(float re, float im) {
+    return (float)sqrt((double)re * (double)re + (double)im * (double)im);
+}
+
 __device__ __forceinline__ float c64_abs_f32(float re, float im) {
     const float a = fabsf(re), b = fabsf(im);
     const float x = fmaxf(a, b), y = fminf(a, b);
@@ -32,8 +39,7 @@ __device__ __forceinline__ float c64_abs_f32(float re, float im) {
     const float r0 = __fmul_rn(hi, rs);
     const float res = __fadd_rn(__fmaf_rn(-r0, r0, hi), lo);            // (hi + lo) - r0^2
     float out = __fmaf_rn(res, __fmul_rn(0.5f, rs), r0);
-    if (!(x > 1e-18f && x < 1e18f))                                     // zero / denormal squares / overflow: exact path
-        out = (float)sqrt((double)re * (double)re + (double)im * (double)im);
+    if (!(x > 1e-18f && x < 1e18f)) out = c64_abs_exact(re, im);       // zero / denormal squares / overflow: exact path
     return out;
 }
 

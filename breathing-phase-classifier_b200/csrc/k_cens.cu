@@ -183,7 +183,7 @@ struct CensSmem {
     float cqmag[kCensTeams][kCqtBinsPerOct + 4];
     float csum[12 * kMaxFrames];                       // folded chroma sums of the CQT phase
     float2 basis[2][kCqtBinsPerOct * kCqtEllWidth];    // [0]: basis, [1]: basis * sqrt(2) (odd octaves), (re, im)
-    short bcol[kCqtBinsPerOct * kCqtEllWidth];         // column - kBinLo; padding entries point at 0 with weight 0
+    short bstart[kCqtBinsPerOct + 4];                  // first bin of each row's band - kBinLo
     double inv_sl[kCqtBins];                           // 1 / sqrt(lengths)
     double swin[43];                                   // hann(43) / sum
     double dscratch[32];
@@ -209,19 +209,17 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
     // ---- stage the basis of this segment's tuning and the smoothing window
     const int tun = ws.tuning[b * 2 + 1];
     {
-        const int16_t* bcol = tb.cqt_col + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
         const float* bre = tb.cqt_re + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
         const float* bim = tb.cqt_im + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
         const double sqrt2 = sqrt(2.0);
         for (int i = tid; i < kCqtBinsPerOct * kCqtEllWidth; i += kCensThreads) {
-            const int c = bcol[i];
-            const float re = c < 0 ? 0.f : bre[i], im = c < 0 ? 0.f : bim[i];
-            S.bcol[i] = (short)(c < 0 ? 0 : c - kBinLo);
+            const float re = bre[i], im = bim[i];
             S.basis[0][i] = make_float2(re, im);
             // fft_basis *= sqrt(sr / my_sr) rounded to complex64: odd octaves carry a factor sqrt(2); the remaining
             // power of two is applied to the (linear) response, which is exact
             S.basis[1][i] = make_float2((float)((double)re * sqrt2), (float)((double)im * sqrt2));
         }
+        if (tid < kCqtBinsPerOct) S.bstart[tid] = (short)(tb.cqt_start[tun * kCqtBinsPerOct + tid] - kBinLo);
         const double* slen = tb.cqt_sqrt_len + (size_t)tun * kCqtBins;
         for (int i = tid; i < kCqtBins; i += kCensThreads) S.inv_sl[i] = 1.0 / slen[i];
     }
@@ -244,7 +242,6 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
     const double2 wl = make_double2(wp.y, -wp.x);                         // -i * exp(-2 pi i h / 512)
     float2* spec = S.spec[team];
     float* cqmag = S.cqmag[team];
-    const int ell_used = tb.cqt_ell_used;
     // long mode: phase 1 = the CQT frames of this CTA's share (grid (segment, part)), phase 2 = post-processing
     const int t_first = 2 * warp + (LONG ? (int)blockIdx.y * kCensTeams : 0);
     const int t_step = kCensTeams * (LONG ? (int)gridDim.y : 1);
@@ -289,11 +286,12 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
                 if (r < kCqtBinsPerOct) {
                     float cr = 0.f, ci = 0.f;
                     const float2* wr = bas + r * kCqtEllWidth;
-                    const short* cc = S.bcol + r * kCqtEllWidth;
+                    const float2* sp = spec + S.bstart[r];
+                    const int wn = tb.cqt_gw[rr];
 #pragma unroll 4
-                    for (int j = 0; j < ell_used; ++j) {
+                    for (int j = 0; j < wn; ++j) {
                         const float2 w = wr[j];
-                        const float2 d = spec[cc[j]];
+                        const float2 d = sp[j];
                         cr = fmaf(w.x, d.x, cr); cr = fmaf(-w.y, d.y, cr);
                         ci = fmaf(w.x, d.y, ci); ci = fmaf(w.y, d.x, ci);
                     }

@@ -9,6 +9,7 @@
 // (v0 was one 256-thread CTA per segment doing all of this behind CTA-wide barriers: 36 % of the step, FP64 pipe 9 %,
 //  47 % of its shared wavefronts bank conflicts -- profiles/r01_*.)
 #include <cmath>
+#include <cstdlib>
 #include "kernels.cuh"
 #include "fft.cuh"
 #include "fft_reg.cuh"
@@ -63,7 +64,7 @@ __device__ __forceinline__ void warp_band_extremes(const float* row, int lo, int
         H[r] = __float_as_uint(full ? s[C - 1 - r] : s[C - 2 - r]);
     }
     double sum_lo = 0.0, sum_hi = 0.0;
-#pragma unroll
+#pragma unroll 1                     // code size: the loop body of k_frame2048 must stream through the instruction caches
     for (int r = 0; r < N; ++r) {
         const unsigned mlo = __reduce_min_sync(0xffffffffu, L[0]);
         const unsigned blo = __ballot_sync(0xffffffffu, L[0] == mlo);
@@ -105,6 +106,11 @@ __device__ __forceinline__ void warp_band_minmax(const float* row, int lo, int l
 // consumer of that row.  Nothing but the per-frame results leaves the SM (v1 wrote the 259 KB/segment |STFT2048|
 // workspace to HBM and read it back in a second kernel); the even (hop-512) frames additionally store their row for
 // k_even2048.
+// Instruction fetch: the loop body is ~95 KB of straight-line SASS and only runs at speed while the warps of an SM walk
+// it in lock-step (every frame costs the same, so they do).  r01 v30-v32 moved the hop-512 work in here: the even
+// frames then took longer than the odd ones, the warps drifted apart, and 11 of 12 issue slots went to "no
+// instruction" stalls (3.2 -> 9.8 ms); with a barrier per frame it ran at 3.7 ms -- slower than the two kernels.
+// (v34 also tried k_even2048 as one warp per staged row with a parallel exact-prefix rolloff: 0.50 vs 0.48 ms, dropped.)
 constexpr int kF2Warps = 4;
 constexpr int kF2RowBytes = 32 * 33 * 8;             // exchange buffer (one component at a time), later the |X| row (1028 floats)
 

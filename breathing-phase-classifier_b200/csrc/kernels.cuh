@@ -32,11 +32,11 @@ struct Tables {
     const float* chroma;          // [100, 12, 257]
     const double* hist_edges;     // [101]
     // CQT
-    const int16_t* cqt_col;       // [100, 36, W]
-    const float* cqt_re;          // [100, 36, W]
+    const int16_t* cqt_start;     // [100, 36]     first rfft bin of each basis row's band
+    const float* cqt_re;          // [100, 36, W]  band form: entry j of row r weighs bin cqt_start[r] + j (zeros in gaps)
     const float* cqt_im;          // [100, 36, W]
     const double* cqt_sqrt_len;   // [100, 252]
-    int cqt_ell_used;             // max non-zeros per basis row over all tunings (<= kCqtEllWidth)
+    int cqt_gw[3];                // band width needed by the rows 0-15 / 16-31 / 32-35 over all tunings (<= kCqtEllWidth)
     // LPC
     const double* hamming400;     // [400]
     // Hilbert (FFT-8000 = 4^3 * 5^3)
