@@ -20,6 +20,19 @@ struct LpcSmem {
 // 94 %-busy load/store pipe).  Lane l owns samples n = 13 l + q.  B[q] = bwd[n]; the forward error that pairs with it,
 // fwd[n + 1 + I], sits in F[(q + I) % 13]: the per-iteration shift fwd = fwd[1:] is a renaming plus one element handed
 // down from the next lane.
+// a / b to within an ulp (b > 0, normal): hardware reciprocal seed (2^-23), two Newton steps, one residual correction.
+// The IEEE division sequence with its slow-path check was 27 % of this kernel's instructions (one per Burg order).
+__device__ __forceinline__ double div_fast(double a, double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    const double q = a * r;
+    return fma(r, fma(-b, q, a), q);
+}
+
 template <int I>
 __device__ __forceinline__ void burg_step(double (&F)[kLpcPer], double (&B)[kLpcPer], double& a_lane, double& den,
                                           int lane) {
@@ -31,7 +44,7 @@ __device__ __forceinline__ void burg_step(double (&F)[kLpcPer], double (&B)[kLpc
 #pragma unroll
     for (int q = 0; q < kLpcPer; ++q) num = fma(B[q], F[(q + I) % kLpcPer], num);
     num = warp_sum(num);
-    const double k = (num * -2.0) / (den + eps);
+    const double k = div_fast(num * -2.0, den + eps);
     // Levinson update a[j] = a_prev[j] + k * a_prev[I - j + 1], j = 1 .. I + 1; lane j holds a[j] (a[0] = 1, rest 0)
     {
         const int src = I + 1 - lane;

@@ -433,14 +433,17 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
             // structural zeros: onset[0..4] == 0 and the left pad is 0, so F[n] == 0 for n < 197 - t
             int n = (197 - t) > 0 ? ((197 - t) & ~3) : 0;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            // the window F[n + l0 .. n + l0 + 7] slides by four per step: its upper half is carried over in registers
+            // (two shared-memory loads per 16 FMAs instead of three; the kernel is bound by shared-memory wavefronts)
+            float4 B0 = *reinterpret_cast<const float4*>(F + min(n + l0, kTempoLags + 4));
             for (; n + l0 < kTempoLags; n += 4) {
                 const float4 A = *reinterpret_cast<const float4*>(F + n);
-                const float4 B0 = *reinterpret_cast<const float4*>(F + n + l0);
                 const float4 B1 = *reinterpret_cast<const float4*>(F + n + l0 + 4);
                 a0 = fmaf(A.x, B0.x, a0); a0 = fmaf(A.y, B0.y, a0); a0 = fmaf(A.z, B0.z, a0); a0 = fmaf(A.w, B0.w, a0);
                 a1 = fmaf(A.x, B0.y, a1); a1 = fmaf(A.y, B0.z, a1); a1 = fmaf(A.z, B0.w, a1); a1 = fmaf(A.w, B1.x, a1);
                 a2 = fmaf(A.x, B0.z, a2); a2 = fmaf(A.y, B0.w, a2); a2 = fmaf(A.z, B1.x, a2); a2 = fmaf(A.w, B1.y, a2);
                 a3 = fmaf(A.x, B0.w, a3); a3 = fmaf(A.y, B1.x, a3); a3 = fmaf(A.z, B1.y, a3); a3 = fmaf(A.w, B1.z, a3);
+                B0 = B1;
             }
             if (j == 0) V.ac0[t] = a0;
             if (l0 < kPlaneRows) {
@@ -469,11 +472,17 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
     q = block_sum(q, S.dscratch);
     const double mean = s / (double)(kTempoLags * T);
     const double sd = sqrt(fmax(0.0, q / (double)(kTempoLags * T) - mean * mean));
+    const double inv_sd = 1.0 / (sd + 1e-8);
+    // one reciprocal per column instead of two FP64 divisions per element (they were 9 % of this kernel)
+    for (int t = tid; t < T; t += NT) V.sumv[t] = 1.0 / ((double)V.ac0[t] < 2.2250738585072014e-308 ? 1.0 : (double)V.ac0[t]);
+    __syncthreads();
     float* o = plane_ptr(feats, b, BPC_CH_TEMPOGRAM, T);
+    int t = tid % T;
+    const int tstep = NT % T;
     for (int i = tid; i < NP; i += NT) {                                     // pad_freq truncates to the first 128 lags
-        const int t = i % T;
-        const double c = (double)V.ac0[t] < 2.2250738585072014e-308 ? 1.0 : (double)V.ac0[t];
-        o[i] = (float)(((double)V.tg[i] / c - mean) / (sd + 1e-8));
+        o[i] = (float)(((double)V.tg[i] * V.sumv[t] - mean) * inv_sd);
+        t += tstep;
+        if (t >= T) t -= T;
     }
 }
 
