@@ -171,6 +171,11 @@ constexpr int kCensThreads = 256, kCensTeams = kCensThreads / 16;
 
 // ~101 KB and <= 128 registers: two 256-thread CTAs per SM, so a 592-segment chunk is exactly two full waves (at three
 // 128-thread CTAs per SM the second wave ran one third full)
+// row pitch of the basis bands in shared memory: 21 float2 = 42 words, so the 16 rows a half-warp reads together fall
+// into 16 different bank pairs (at the table's pitch of 20 they fell into 4: a 4-way conflict on every weight load,
+// a third of this kernel's shared-memory wavefronts)
+constexpr int kBasisPitch = kCqtEllWidth + 1;
+
 struct CensSmem {
     union {
         double2 xch[kCensTeams][16 * 17];              // FFT exchange buffers (CQT phase)
@@ -182,7 +187,7 @@ struct CensSmem {
     float2 spec[kCensTeams][kBinSpan + 3];
     float cqmag[kCensTeams][kCqtBinsPerOct + 4];
     float csum[12 * kMaxFrames];                       // folded chroma sums of the CQT phase
-    float2 basis[2][kCqtBinsPerOct * kCqtEllWidth];    // [0]: basis, [1]: basis * sqrt(2) (odd octaves), (re, im)
+    float2 basis[2][kCqtBinsPerOct * kBasisPitch];     // [0]: basis, [1]: basis * sqrt(2) (odd octaves), (re, im)
     short bstart[kCqtBinsPerOct + 4];                  // first bin of each row's band - kBinLo
     double inv_sl[kCqtBins];                           // 1 / sqrt(lengths)
     double swin[43];                                   // hann(43) / sum
@@ -214,10 +219,11 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
         const double sqrt2 = sqrt(2.0);
         for (int i = tid; i < kCqtBinsPerOct * kCqtEllWidth; i += kCensThreads) {
             const float re = bre[i], im = bim[i];
-            S.basis[0][i] = make_float2(re, im);
+            const int o = (i / kCqtEllWidth) * kBasisPitch + i % kCqtEllWidth;
+            S.basis[0][o] = make_float2(re, im);
             // fft_basis *= sqrt(sr / my_sr) rounded to complex64: odd octaves carry a factor sqrt(2); the remaining
             // power of two is applied to the (linear) response, which is exact
-            S.basis[1][i] = make_float2((float)((double)re * sqrt2), (float)((double)im * sqrt2));
+            S.basis[1][o] = make_float2((float)((double)re * sqrt2), (float)((double)im * sqrt2));
         }
         if (tid < kCqtBinsPerOct) S.bstart[tid] = (short)(tb.cqt_start[tun * kCqtBinsPerOct + tid] - kBinLo);
         const double* slen = tb.cqt_sqrt_len + (size_t)tun * kCqtBins;
@@ -285,7 +291,7 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
                 const int r = h + 16 * rr;
                 if (r < kCqtBinsPerOct) {
                     float cr = 0.f, ci = 0.f;
-                    const float2* wr = bas + r * kCqtEllWidth;
+                    const float2* wr = bas + r * kBasisPitch;
                     const float2* sp = spec + S.bstart[r];
                     const int wn = tb.cqt_gw[rr];
 #pragma unroll 4
