@@ -241,6 +241,7 @@ int check_params(const bpc_params* p, std::string* why) {
         }
     }
     if (p->pad_scalars_to != 0 && p->pad_scalars_to < BPC_NUM_SCALARS) { *why = "pad_scalars_to < 36"; return BPC_ERR_ARG; }
+    if (p->pad_scalars_to > 256) { *why = "pad_scalars_to > 256"; return BPC_ERR_ARG; }
     return BPC_OK;
 }
 
@@ -417,6 +418,13 @@ int build_workspace(bpc_handle* h) {
         if ((rc = dalloc(h, C * w.scratch_stride, &w.scratch))) return rc;
     }
     if ((rc = dalloc(h, (size_t)(9 + g.nscal) * 5, &h->stats_acc))) return rc;
+    // 1 s mode: the producers of the planes accumulate the dataset statistics themselves instead of k_stats re-reading
+    // the planes (0.8 GB less DRAM traffic per 4096-segment step; +0.15 ms in the producers against 0.18 ms of
+    // k_stats).  BPC_FUSED_STATS=0 and the long mode keep k_stats.
+    {
+        const char* fs = std::getenv("BPC_FUSED_STATS");
+        w.stats_acc = (!g.long_mode && !(fs && fs[0] == '0')) ? h->stats_acc : nullptr;
+    }
     w.dbg_mel_db = w.dbg_mfcc = w.dbg_gam = w.dbg_mod = w.dbg_chroma_stft = w.dbg_chroma_cens = w.dbg_lpc =
         w.dbg_onset = nullptr;
     h->ws_dbg = w;
@@ -520,7 +528,7 @@ int run_chunk(bpc_handle* h, const void* wav, int wav_dtype, int64_t L_in, int n
         BPC_CUDA(h, cudaStreamWaitEvent(st, h->ev_time, 0));
     }
     launch_pad_scalars(n, g, scalars, st);
-    timed(9, [&] { launch_stats(n, g, feats, scalars, h->stats_acc, st); });
+    timed(9, [&] { launch_stats(n, g, feats, scalars, h->stats_acc, ws.stats_acc == nullptr, st); });
     h->last_n = n;
     BPC_CUDA(h, cudaGetLastError());
     return BPC_OK;

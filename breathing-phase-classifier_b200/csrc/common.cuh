@@ -246,4 +246,64 @@ __device__ __forceinline__ void atomic_min_double(double* addr, double v) {
     } while (assumed != old);
 }
 
+// ------------------------------------------------------------------------------ dataset statistics, fused (r01 v37)
+// Running statistics of the values a thread stores into one output plane; flushed per CTA into the handle's
+// [(9 + S), 5] accumulator {count, sum, sum of squares, min, max} (bpc_channel_stats; BASELINE config 3's all-reduce
+// payload).  Up to v36 a separate kernel re-read the 0.8 GB of planes of every 4096-segment step for this.
+struct StatAcc {
+    double s, q;
+    float mn, mx;
+    int cnt;
+    __device__ __forceinline__ void init() { s = 0.0; q = 0.0; mn = FLT_MAX; mx = -FLT_MAX; cnt = 0; }
+    __device__ __forceinline__ void add(float v) {
+        if ((__float_as_uint(v) & 0x7f800000u) != 0x7f800000u) {
+            const double d = (double)v;
+            s += d;
+            q = fma(d, d, q);
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+            ++cnt;
+        }
+    }
+    __device__ __forceinline__ void add_n(float v, int m) {          // the same value m times (pad_freq rows)
+        if ((__float_as_uint(v) & 0x7f800000u) != 0x7f800000u && m > 0) {
+            const double d = (double)v;
+            s += (double)m * d;
+            q += (double)m * (d * d);
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+            cnt += m;
+        }
+    }
+};
+// Call from all threads of a CTA of at most 10 warps; dscratch / fscratch: the CTA's 32-element reduction scratch arrays.
+__device__ __forceinline__ void stat_flush_block(const StatAcc& a, double* acc_c, double* dscratch, float* fscratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const double s = warp_sum(a.s), q = warp_sum(a.q);
+    const int cnt = warp_sum(a.cnt);
+    const float mn = warp_min(a.mn), mx = warp_max(a.mx);
+    __syncthreads();
+    if (lane == 0) {
+        dscratch[w] = s; dscratch[10 + w] = q; dscratch[20 + w] = (double)cnt;
+        fscratch[w] = mn; fscratch[16 + w] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double S = 0.0, Q = 0.0, C = 0.0;
+        float MN = FLT_MAX, MX = -FLT_MAX;
+        for (int i = 0; i < nw; ++i) {
+            S += dscratch[i]; Q += dscratch[10 + i]; C += dscratch[20 + i];
+            MN = fminf(MN, fscratch[i]); MX = fmaxf(MX, fscratch[16 + i]);
+        }
+        if (C > 0.0) {
+            atomicAdd(acc_c + 0, C);
+            atomicAdd(acc_c + 1, S);
+            atomicAdd(acc_c + 2, Q);
+            atomic_min_double(acc_c + 3, (double)MN);
+            atomic_max_double(acc_c + 4, (double)MX);
+        }
+    }
+    __syncthreads();
+}
+
 }  // namespace bpc

@@ -354,18 +354,26 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
     // ---- row-wise z-score -> rows 12..23; pad rows 24..127 with the min over all 24 normalised rows
     float mn = FLT_MAX;
     float* o = plane_ptr(feats, b, BPC_CH_CHROMA, T);
+    const bool stats = !LONG && ws.stats_acc != nullptr;
+    StatAcc ac;
+    ac.init();
     for (int r = warp; r < 12; r += kCensThreads / 32) {
         const ZTerm z = np_row_zterm(p_quant + r * T, T, lane);
         for (int t = lane; t < T; t += 32) {
             const float v = z(p_quant[r * T + t]);
             o[(12 + r) * T + t] = v;
             mn = fminf(mn, v);
+            if (stats) ac.add(v);
         }
     }
     mn = block_min(mn, S.fscratch);
     const float fill = fminf(mn, ws.chroma_min[b * 2 + 0]);
     for (int i = 24 * T + tid; i < kPlaneRows * T; i += kCensThreads) o[i] = fill;
     if (tid == 0) ws.chroma_min[b * 2 + 1] = mn;
+    if (stats) {                                                   // rows 0..11 were counted by the chroma_stft role
+        if (tid == 0) ac.add_n(fill, (kPlaneRows - 24) * T);
+        stat_flush_block(ac, ws.stats_acc + 5 * BPC_CH_CHROMA, S.dscratch, S.fscratch);
+    }
 }
 
 void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,

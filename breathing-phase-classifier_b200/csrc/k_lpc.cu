@@ -141,9 +141,19 @@ __global__ void __launch_bounds__(kLpcThreads, 4) k_lpc(const float* __restrict_
     }
     mn = block_min(mn, S.fscratch);
     float* o = plane_ptr(feats, b, BPC_CH_LPC, T);
+    const bool stats = !LONG && ws.stats_acc != nullptr;
+    StatAcc al;
+    al.init();
     for (int i = tid; i < kPlaneRows * T; i += kLpcThreads) {
         const int c = i / T, t = i - c * T;
-        o[i] = (c < kLpcOrder && t < Tk) ? z(coef[c * F + t]) : mn;
+        const bool live = c < kLpcOrder && t < Tk;
+        const float v = live ? z(coef[c * F + t]) : mn;
+        o[i] = v;
+        if (stats && live) al.add(v);
+    }
+    if (stats) {
+        if (tid == 0) al.add_n(mn, kPlaneRows * T - kLpcOrder * Tk);
+        stat_flush_block(al, ws.stats_acc + 5 * BPC_CH_LPC, S.dscratch, S.fscratch);
     }
 }
 
@@ -168,12 +178,12 @@ void launch_lpc(const float* y, int n, const Geometry& g, const Tables& tb, cons
 // ------------------------------------------------------------------------------- dataset-level statistics + padding
 // acc layout: [(9 + nscal)][5] doubles = {count, sum, sumsq, min, max}.  One CTA per segment, one WARP per plane (warp 9:
 // the scalars): only warp shuffles, no block barriers; lane 0 of each warp issues the five atomics of its plane.
-constexpr int kStatsThreads = 320;
+constexpr int kStatsThreads = 288;         // nine warps: one per plane
 
 __global__ void __launch_bounds__(kStatsThreads) k_stats(Geometry g, const float* __restrict__ feats,
-                                                         const float* __restrict__ scalars, double* __restrict__ acc) {
+                                                         double* __restrict__ acc) {
     const int b = blockIdx.x, c = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (c < 9) {
+    {
         // rows that carry data (api.cu::kLiveRows); rows live..127 of a plane repeat one pad value (pad_freq), which is
         // accounted for analytically instead of being read back: 772 of 1152 rows cross HBM
         constexpr int kLive[9] = {24, 64, 12, 128, 128, 128, 120, 40, 128};
@@ -224,23 +234,65 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(Geometry g, const float
             atomic_min_double(a + 3, (double)mn);
             atomic_max_double(a + 4, (double)mx);
         }
-    } else {
-        for (int i = lane; i < g.nscal; i += 32) {
-            const double v = (double)scalars[(size_t)b * g.nscal + i];
-            if (isfinite(v)) {
-                double* a = acc + (size_t)(9 + i) * 5;
-                atomicAdd(a + 0, 1.0);
-                atomicAdd(a + 1, v);
-                atomicAdd(a + 2, v * v);
-                atomic_min_double(a + 3, v);
-                atomic_max_double(a + 4, v);
+    }
+}
+
+// Statistics of the scalar vectors: thread (group, i) walks scalar i of every kStatGroups-th segment of this CTA's
+// share, the groups are combined in shared memory, and each CTA issues five atomics per scalar.  (Up to v36 every
+// segment issued them - 737 k atomics on 180 addresses per 4096-segment step, which took longer (0.14 ms) than the
+// 0.8 GB the plane warps read.)
+constexpr int kStatScalThreads = 256;
+__global__ void __launch_bounds__(kStatScalThreads) k_stats_scalars(Geometry g, const float* __restrict__ scalars, int n,
+                                                                    double* __restrict__ acc) {
+    __shared__ double sh_s[kStatScalThreads], sh_q[kStatScalThreads];
+    __shared__ float sh_mn[kStatScalThreads], sh_mx[kStatScalThreads];
+    __shared__ int sh_c[kStatScalThreads];
+    const int S = g.nscal, G = kStatScalThreads / S;            // S <= 64 (checked on the host)
+    const int tid = threadIdx.x, grp = tid / S, i = tid - grp * S;
+    double s = 0.0, q = 0.0;
+    float mn = FLT_MAX, mx = -FLT_MAX;
+    int cnt = 0;
+    if (grp < G) {
+        for (int b = blockIdx.x * G + grp; b < n; b += gridDim.x * G) {
+            const float v = __ldg(scalars + (size_t)b * S + i);
+            if ((__float_as_uint(v) & 0x7f800000u) != 0x7f800000u) {
+                const double d = (double)v;
+                s += d;
+                q = fma(d, d, q);
+                mn = fminf(mn, v);
+                mx = fmaxf(mx, v);
+                ++cnt;
             }
+        }
+    }
+    sh_s[tid] = s; sh_q[tid] = q; sh_mn[tid] = mn; sh_mx[tid] = mx; sh_c[tid] = cnt;
+    __syncthreads();
+    if (tid < S) {
+        for (int k = 1; k < G; ++k) {
+            const int o = k * S + tid;
+            s += sh_s[o]; q += sh_q[o]; mn = fminf(mn, sh_mn[o]); mx = fmaxf(mx, sh_mx[o]); cnt += sh_c[o];
+        }
+        if (cnt > 0) {
+            double* a = acc + (size_t)(9 + tid) * 5;
+            atomicAdd(a + 0, (double)cnt);
+            atomicAdd(a + 1, s);
+            atomicAdd(a + 2, q);
+            atomic_min_double(a + 3, (double)mn);
+            atomic_max_double(a + 4, (double)mx);
         }
     }
 }
 
-void launch_stats(int n, const Geometry& g, const float* feats, const float* scalars, double* acc, cudaStream_t st) {
-    k_stats<<<n, kStatsThreads, 0, st>>>(g, feats, scalars, acc);
+void launch_stats(int n, const Geometry& g, const float* feats, const float* scalars, double* acc, bool planes,
+                  cudaStream_t st) {
+    if (planes) {                                              // fused mode: the producers did the planes
+        k_stats<<<n, kStatsThreads, 0, st>>>(g, feats, acc);
+        note_launch();
+    }
+    const int G = kStatScalThreads / g.nscal;
+    int grid = (n + G - 1) / G;
+    if (grid > 148) grid = 148;
+    k_stats_scalars<<<grid, kStatScalThreads, 0, st>>>(g, scalars, n, acc);
     note_launch();
 }
 

@@ -479,11 +479,17 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
     float* o = plane_ptr(feats, b, BPC_CH_TEMPOGRAM, T);
     int t = tid % T;
     const int tstep = NT % T;
+    const bool stats = !LONG && ws.stats_acc != nullptr;
+    StatAcc at;
+    at.init();
     for (int i = tid; i < NP; i += NT) {                                     // pad_freq truncates to the first 128 lags
-        o[i] = (float)(((double)V.tg[i] * V.sumv[t] - mean) * inv_sd);
+        const float v = (float)(((double)V.tg[i] * V.sumv[t] - mean) * inv_sd);
+        o[i] = v;
+        if (stats) at.add(v);
         t += tstep;
         if (t >= T) t -= T;
     }
+    if (stats) stat_flush_block(at, ws.stats_acc + 5 * BPC_CH_TEMPOGRAM, S.dscratch, S.fscratch);
 }
 
 // ------------------------------------------------------------------------------------ even frames: rolloff + tuning36

@@ -328,10 +328,20 @@ __device__ void role_mel(int b, const Geometry g, const Tables& tb, const Worksp
     s2 = block_sum(s2, dscratch); q2 = block_sum(q2, dscratch);
     const ZTerm z0 = make_zterm(s0, q0, (double)NP), z1 = make_zterm(s1, q1, (double)NP),
                 z2 = make_zterm(s2, q2, (double)NP);
+    const bool stats = !LONG && !mel3 && ws.stats_acc != nullptr;
+    StatAcc a0, a1, a2;
+    a0.init(); a1.init(); a2.init();
     for (int i = threadIdx.x; i < NP; i += blockDim.x) {
-        o0[i] = z0(P[i]);
-        o1[i] = z1(o1[i]);
-        o2[i] = z2(o2[i]);
+        const float v0 = z0(P[i]), v1 = z1(o1[i]), v2 = z2(o2[i]);
+        o0[i] = v0;
+        o1[i] = v1;
+        o2[i] = v2;
+        if (stats) { a0.add(v0); a1.add(v1); a2.add(v2); }
+    }
+    if (stats) {
+        stat_flush_block(a0, ws.stats_acc + 5 * BPC_CH_MEL, dscratch, fscratch);
+        stat_flush_block(a1, ws.stats_acc + 5 * BPC_CH_MEL_DELTA, dscratch, fscratch);
+        stat_flush_block(a2, ws.stats_acc + 5 * BPC_CH_MEL_DELTA2, dscratch, fscratch);
     }
     if (mel3) return;
 
@@ -348,7 +358,17 @@ __device__ void role_mel(int b, const Geometry g, const Tables& tb, const Worksp
     const ZTerm zm = zterm_of(C2, 40 * T, dscratch, fscratch, &mn);
     const float fill = zm(mn);                                         // pad_freq: min of the normalised array
     float* om = plane_ptr(feats, b, BPC_CH_MOD_SPEC, T);
-    for (int i = threadIdx.x; i < NP; i += blockDim.x) om[i] = (i < 40 * T) ? zm(C2[i]) : fill;
+    StatAcc am;
+    am.init();
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) {
+        const float v = (i < 40 * T) ? zm(C2[i]) : fill;
+        om[i] = v;
+        if (stats && i < 40 * T) am.add(v);
+    }
+    if (stats) {
+        if (threadIdx.x == 0) am.add_n(fill, NP - 40 * T);
+        stat_flush_block(am, ws.stats_acc + 5 * BPC_CH_MOD_SPEC, dscratch, fscratch);
+    }
 }
 
 // ----------------------------------------------------------------------------------------------- role 1: mfcc
@@ -389,7 +409,18 @@ __device__ void role_mfcc(int b, const Geometry g, const Tables& tb, const Works
     mn = block_min(mn, fscratch);
     __syncthreads();
     float* o = plane_ptr(feats, b, BPC_CH_MFCC, T);
-    for (int i = threadIdx.x; i < NP; i += blockDim.x) o[i] = (i < 120 * T) ? OUT[i] : mn;
+    const bool stats = !LONG && ws.stats_acc != nullptr;
+    StatAcc am;
+    am.init();
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) {
+        const float v = (i < 120 * T) ? OUT[i] : mn;
+        o[i] = v;
+        if (stats && i < 120 * T) am.add(v);
+    }
+    if (stats) {
+        if (threadIdx.x == 0) am.add_n(mn, NP - 120 * T);
+        stat_flush_block(am, ws.stats_acc + 5 * BPC_CH_MFCC, dscratch, fscratch);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ role 2: gammatone
@@ -410,7 +441,18 @@ __device__ void role_gammatone(int b, const Geometry g, const Tables& tb, const 
     const ZTerm z = zterm_of(G, NG, dscratch, fscratch, &mn);
     const float fill = z(mn);
     float* o = plane_ptr(feats, b, BPC_CH_GAMMATONE, T);
-    for (int i = threadIdx.x; i < NP; i += blockDim.x) o[i] = (i < NG) ? z(G[i]) : fill;
+    const bool stats = !LONG && ws.stats_acc != nullptr;
+    StatAcc ag;
+    ag.init();
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) {
+        const float v = (i < NG) ? z(G[i]) : fill;
+        o[i] = v;
+        if (stats && i < NG) ag.add(v);
+    }
+    if (stats) {
+        if (threadIdx.x == 0) ag.add_n(fill, NP - NG);
+        stat_flush_block(ag, ws.stats_acc + 5 * BPC_CH_GAMMATONE, dscratch, fscratch);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ role 3: chroma_stft
@@ -511,16 +553,21 @@ __device__ void role_chroma_stft(int b, const Geometry g, const Tables& tb, cons
     // row-wise z-score (process.py:55), rows 0..11 of the chroma plane; the pad rows are filled by the CENS kernel
     float mn = FLT_MAX;
     float* o = plane_ptr(feats, b, BPC_CH_CHROMA, T);
+    const bool stats = !LONG && ws.stats_acc != nullptr;
+    StatAcc ac;
+    ac.init();
     for (int r = warp; r < 12; r += nw) {
         const ZTerm z = np_row_zterm(raw + r * T, T, lane);
         for (int t = lane; t < T; t += 32) {
             const float v = z(raw[r * T + t]);
             o[r * T + t] = v;
             mn = fminf(mn, v);
+            if (stats) ac.add(v);
         }
     }
     mn = block_min(mn, fscratch);
     if (tid == 0) ws.chroma_min[b * 2 + 0] = mn;
+    if (stats) stat_flush_block(ac, ws.stats_acc + 5 * BPC_CH_CHROMA, dscratch, fscratch);   // rows 12..127: k_cens
 }
 
 // ----------------------------------------------------------------------------------------------- the kernel

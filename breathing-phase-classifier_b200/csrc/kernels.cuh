@@ -64,6 +64,7 @@ struct Workspace {            // per chunk of `cap` segments
     float* chroma_min;        // [cap, 2]   min of the normalised chroma_stft / chroma_cens rows
     int* ints;                // [cap, 2]   n_peaks, first-min index
     uint32_t* tc_a;           // long mode: C1 split into tf32 hi / lo tiles for the tensor-core time DCT (k_tc.cu)
+    double* stats_acc;        // [(9 + S), 5] dataset statistics accumulated by the producers (1 s mode; nullptr: k_stats does it)
     float* scratch;           // [cap, scratch_stride]  long mode: what the 1 s kernels keep in shared memory
     size_t scratch_stride;
     // debug (raw, un-normalised stages of the last chunk)
@@ -112,7 +113,8 @@ void launch_lpc(const float* y, int n, const Geometry& g, const Tables& tb, cons
                 cudaStream_t st);
 void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
                  cudaStream_t st);
-void launch_stats(int n, const Geometry& g, const float* feats, const float* scalars, double* acc, cudaStream_t st);
+void launch_stats(int n, const Geometry& g, const float* feats, const float* scalars, double* acc, bool planes,
+                  cudaStream_t st);
 void launch_modspec(int n, const Geometry& g, const Tables& tb, const Workspace& ws, const float* mel_db, float* out,
                     cudaStream_t st);
 void launch_pad_scalars(int n, const Geometry& g, float* scalars, cudaStream_t st);
