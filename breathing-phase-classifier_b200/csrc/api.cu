@@ -27,6 +27,7 @@
 #include "kernels.cuh"
 #include "tables.hpp"
 #include "fft20.cuh"
+#include "tuning.cuh"
 
 using namespace bpc;
 
@@ -399,6 +400,8 @@ int build_workspace(bpc_handle* h) {
     if ((rc = dalloc(h, C * g.L, &w.y))) return rc;
     if ((rc = dalloc(h, C * T * kMagStride, &w.mag512))) return rc;
     if ((rc = dalloc(h, C * ((T + 1) / 2) * kMag2048Stride, &w.mag_even))) return rc;
+    w.cand36 = nullptr;
+    if (!g.long_mode && (rc = dalloc(h, C * 2 * (size_t)kMaxCand2048, &w.cand36))) return rc;
     if ((rc = dalloc(h, C * T * 20, &w.frame_feat))) return rc;
     if ((rc = dalloc(h, C * T * 128, &w.melD))) return rc;
     w.dec_stride = cens_dec_floats_per_segment(g.L);

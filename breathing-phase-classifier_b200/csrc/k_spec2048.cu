@@ -497,9 +497,9 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
 // `cumsum(S) < 0.85 * cumsum(S)[-1]` is taken on numpy's *sequential float32* cumsum, which is reproduced here with
 // one thread per frame (1025 dependent float32 adds).  chroma_cens (process.py:53) estimates its tuning from the same
 // frames (estimate_tuning(y=y, bins_per_octave=36) -> piptrack n_fft 2048, hop 512).
+// The candidate lists (worst case 7936 entries, typically a few hundred) live in global memory: as 63.5 KB of shared
+// memory they held this latency-bound kernel at three CTAs per SM (r01 v40).
 struct Even2048Smem {
-    float cand_mag[kMaxCand2048];
-    float cand_pitch[kMaxCand2048];
     float sortbuf[kSelectWords];
     float colmax[kMaxFrames];
     float roll[kMaxFrames];
@@ -516,8 +516,8 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
     // candidate lists and per-frame arrays: shared memory (1 s), the segment's global scratch region in long mode
     const int cap = LONG ? 492 * TE : kMaxCand2048;
     float* lbase = ws.scratch + (size_t)b * ws.scratch_stride;
-    float* cand_mag = LONG ? lbase : E.cand_mag;
-    float* cand_pitch = LONG ? lbase + cap : E.cand_pitch;
+    float* cand_mag = LONG ? lbase : ws.cand36 + (size_t)b * 2 * kMaxCand2048;
+    float* cand_pitch = cand_mag + cap;
     float* colmax = LONG ? lbase + 2 * (size_t)cap : E.colmax;
     float* roll = LONG ? colmax + TE : E.roll;
     float* sortbuf = E.sortbuf;

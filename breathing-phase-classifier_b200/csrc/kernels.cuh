@@ -56,6 +56,7 @@ struct Workspace {            // per chunk of `cap` segments
     float* y;                 // [cap, L]   float32 waveform after pad_or_truncate (only when ingest is needed)
     float* mag512;            // [cap, T, kMagStride]
     float* mag_even;          // [cap, (T+1)/2, kMag2048Stride]  |STFT2048| rows of the hop-512 frames (1025 valid bins)
+    float* cand36;            // [cap, 2, kMaxCand2048]  1 s mode: piptrack candidates (magnitude, pitch) of k_even2048
     double* frame_feat;       // [cap, T, 20]  per-frame centroid, bandwidth, flatness, contrast peaks / valleys
     float* melD;              // [cap, T, 128] mel-D power columns
     float* dec;               // [cap, dec_stride]  half-band decimated signals of the CQT octaves 1..6 (zero padded)

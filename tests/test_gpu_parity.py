@@ -194,10 +194,14 @@ def test_silent_and_constant_segments(engine, torch_cuda):
     assert s[0, 22] == sc[22] == 0 and s[0, 35] == sc[35] == 0
 
 
-def test_dataset_statistics(torch_cuda):
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_dataset_statistics(torch_cuda, fused, monkeypatch):
+    """[(9 + 36), 5] dataset statistics against numpy over the outputs: accumulated by the producers of the planes
+    (default) and by the separate statistics kernel (BPC_FUSED_STATS=0, read when the handle is created)."""
     torch = torch_cuda
     import bpc_b200
     from bpc_b200.synth import synth_batch_pcm16
+    monkeypatch.setenv("BPC_FUSED_STATS", fused)
     eng = bpc_b200.Engine(device=0, max_batch=64)
     pcm = synth_batch_pcm16(40, 9)
     f, s, _ = eng.precompute(torch.from_numpy(pcm).cuda())
@@ -209,7 +213,10 @@ def test_dataset_statistics(torch_cuda):
         assert np.isclose(st[c, 1], f[:, c].sum(), rtol=1e-9, atol=1e-6) and np.isclose(st[c, 2], (f[:, c] ** 2).sum(), rtol=1e-9)
         assert st[c, 3] == f[:, c].min() and st[c, 4] == f[:, c].max()
     for i in range(36):
+        assert st[9 + i, 0] == s.shape[0]
         assert np.isclose(st[9 + i, 1], s[:, i].sum(), rtol=1e-9, atol=1e-12)
+        assert np.isclose(st[9 + i, 2], (s[:, i] ** 2).sum(), rtol=1e-9, atol=1e-12)
+        assert st[9 + i, 3] == s[:, i].min() and st[9 + i, 4] == s[:, i].max()
     dev = eng.channel_stats_device()
     assert dev.shape == (45, 5) and np.array_equal(dev.cpu().numpy(), st)
     eng.reset_stats()
