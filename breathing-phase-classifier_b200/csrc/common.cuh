@@ -71,6 +71,18 @@ struct OpMaxD { __device__ double operator()(double a, double b) const { return 
 struct OpMinD { __device__ double operator()(double a, double b) const { return fmin(a, b); } };
 
 __device__ __forceinline__ double block_sum(double v, double* scratch) { return block_reduce(v, 0.0, OpAdd(), scratch); }
+// two sums behind one pair of barriers (blockDim.x <= 512: 2 x 16 partials in the 32-element scratch array)
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) { scratch[w] = a; scratch[16 + w] = b; }
+    __syncthreads();
+    double ra = (lane < nw) ? scratch[lane] : 0.0, rb = (lane < nw) ? scratch[16 + lane] : 0.0;
+    a = warp_sum(ra);
+    b = warp_sum(rb);
+}
 __device__ __forceinline__ float block_max(float v, float* scratch) { return block_reduce(v, -FLT_MAX, OpMaxF(), scratch); }
 __device__ __forceinline__ float block_min(float v, float* scratch) { return block_reduce(v, FLT_MAX, OpMinF(), scratch); }
 

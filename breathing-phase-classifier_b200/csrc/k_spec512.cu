@@ -276,8 +276,7 @@ __device__ ZTerm zterm_of(const float* a, int n, double* dscratch, float* fscrat
         q += v * v;
         mn = fminf(mn, a[i]);
     }
-    s = block_sum(s, dscratch);
-    q = block_sum(q, dscratch);
+    block_sum2(s, q, dscratch);
     if (min_out) *min_out = block_min(mn, fscratch);
     return make_zterm(s, q, (double)n);
 }
@@ -323,9 +322,9 @@ __device__ void role_mel(int b, const Geometry g, const Tables& tb, const Worksp
         s1 += v1; q1 += v1 * v1;
         s2 += v2; q2 += v2 * v2;
     }
-    s0 = block_sum(s0, dscratch); q0 = block_sum(q0, dscratch);
-    s1 = block_sum(s1, dscratch); q1 = block_sum(q1, dscratch);
-    s2 = block_sum(s2, dscratch); q2 = block_sum(q2, dscratch);
+    block_sum2(s0, q0, dscratch);
+    block_sum2(s1, q1, dscratch);
+    block_sum2(s2, q2, dscratch);
     const ZTerm z0 = make_zterm(s0, q0, (double)NP), z1 = make_zterm(s1, q1, (double)NP),
                 z2 = make_zterm(s2, q2, (double)NP);
     const bool stats = !LONG && !mel3 && ws.stats_acc != nullptr;
@@ -487,8 +486,7 @@ __device__ void role_chroma_stft(int b, const Geometry g, const Tables& tb, cons
         mx = warp_max(mx);
         if (lane == 0) colmax[t] = mx;
     }
-    e_low = block_sum(e_low, dscratch);
-    e_tot = block_sum(e_tot, dscratch);
+    block_sum2(e_low, e_tot, dscratch);
     if (tid == 0) {
         const float lo = (float)e_low, tot = (float)e_tot;                  // np.sum of float32 arrays
         scalars[(size_t)b * g.nscal + 25] = __fdiv_rn(lo, __fadd_rn(tot, 1e-8f));
