@@ -31,8 +31,11 @@ __device__ __forceinline__ float lerp_q(float a, float b, double g) {
     return (float)(g >= 0.5 ? db - (db - da) * (1.0 - g) : da + (db - da) * g);
 }
 
+// 512 threads: the kernel is latency-bound and shared memory (the staged segment + four histograms) allows two CTAs
+// per SM, so the CTA size sets the occupancy (r01 v41: 256 -> 512 threads)
+constexpr int kTimeBasicThreads = 512;
 template <bool LONG>
-__global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y, Geometry g, Workspace ws,
+__global__ void __launch_bounds__(kTimeBasicThreads) k_time_basic(const float* __restrict__ y, Geometry g, Workspace ws,
                                                     float* scalars, int32_t* status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TimeBasicSmem& S = *reinterpret_cast<TimeBasicSmem*>(smem_raw);
@@ -51,14 +54,14 @@ __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y,
     } else if ((L & 3) == 0 && ((size_t)yb & 15) == 0) {
         stage_segment_tma(S.y, yb, L, (uint64_t*)&S.bar);
     } else {
-        for (int i = tid; i < L; i += 256) S.y[i] = yb[i];
+        for (int i = tid; i < L; i += kTimeBasicThreads) S.y[i] = yb[i];
     }
     __syncthreads();
 
     // ---- moments (scipy.stats.skew / kurtosis, biased) and input checks
     double s1 = 0.0;
     int bad = 0, nonzero = 0;
-    for (int i = tid; i < L; i += 256) {
+    for (int i = tid; i < L; i += kTimeBasicThreads) {
         const float v = ys[i];
         s1 += (double)v;
         bad |= !isfinite(v);
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y,
     nonzero = __syncthreads_or(nonzero);
     const double mean = s1 / L;
     double m2 = 0.0, m3 = 0.0, m4 = 0.0;
-    for (int i = tid; i < L; i += 256) {
+    for (int i = tid; i < L; i += kTimeBasicThreads) {
         const double d = (double)ys[i] - mean;
         const double d2 = d * d;
         m2 += d2;
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y,
 
     // ---- per-256-sample block sums: squares (rms) and zero crossings (zcr)
     const int nblk = (L + 255) / 256;
-    for (int j = warp; j < nblk; j += 8) {
+    for (int j = warp; j < nblk; j += kTimeBasicThreads / 32) {
         double sq = 0.0;
         int cz = 0;
         for (int i = 256 * j + lane; i < 256 * j + 256 && i < L; i += 32) {
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y,
     }
     __syncthreads();
     // frame t covers y[256 (t-4), 256 (t+4)) (frame_length 2048 centred, hop 256)
-    for (int t = tid; t < T; t += 256) {
+    for (int t = tid; t < T; t += kTimeBasicThreads) {
         double sq = 0.0;
         int cz = 0;
         for (int j = t - 4; j < t + 4; ++j)
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y,
     const int shifts[3] = {21, 10, 0};
     const unsigned masks[3] = {0x7ffu, 0x7ffu, 0x3ffu};
     for (int pass = 0; pass < 3; ++pass) {
-        for (int i = tid; i < 4 * 2048; i += 256) (&S.hist[0][0])[i] = 0u;
+        for (int i = tid; i < 4 * 2048; i += kTimeBasicThreads) (&S.hist[0][0])[i] = 0u;
         __syncthreads();
         const unsigned p0 = S.prefix[0], p1 = S.prefix[1], p2 = S.prefix[2], p3 = S.prefix[3];
         const unsigned hi_mask = pass == 0 ? 0u : (pass == 1 ? 0xffe00000u : 0xfffffc00u);
@@ -167,12 +170,12 @@ __global__ void __launch_bounds__(256) k_time_basic(const float* __restrict__ y,
             // all four targets still share the empty prefix: one histogram serves them (4x fewer shared atomics).  It
             // is kept as four partial histograms (one per warp pair): |y| of a breath sits in a handful of exponent
             // bins, and same-address shared atomics serialise
-            for (int i = tid; i < L; i += 256)
+            for (int i = tid; i < L; i += kTimeBasicThreads)
                 atomicAdd(&S.hist[warp & 3][__float_as_uint(fabsf(ys[i])) >> 21], 1u);
             __syncthreads();
-            for (int i = tid; i < 2048; i += 256) S.hist[0][i] += S.hist[1][i] + S.hist[2][i] + S.hist[3][i];
+            for (int i = tid; i < 2048; i += kTimeBasicThreads) S.hist[0][i] += S.hist[1][i] + S.hist[2][i] + S.hist[3][i];
         } else {
-            for (int i = tid; i < L; i += 256) {
+            for (int i = tid; i < L; i += kTimeBasicThreads) {
                 const unsigned key = __float_as_uint(fabsf(ys[i]));
                 const unsigned hi = key & hi_mask, d = (key >> shifts[pass]) & masks[pass];
                 if (hi == p0) atomicAdd(&S.hist[0][d], 1u);
@@ -781,8 +784,8 @@ void launch_time_scalars(const float* y, int n, const Geometry& g, const Tables&
         cudaFuncSetAttribute(k_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AutocorrSmem));
         done = true;
     }
-    if (g.long_mode) k_time_basic<true><<<n, 256, sizeof(TimeBasicSmem), st>>>(y, g, ws, scalars, status);
-    else k_time_basic<false><<<n, 256, sizeof(TimeBasicSmem), st>>>(y, g, ws, scalars, status);
+    if (g.long_mode) k_time_basic<true><<<n, kTimeBasicThreads, sizeof(TimeBasicSmem), st>>>(y, g, ws, scalars, status);
+    else k_time_basic<false><<<n, kTimeBasicThreads, sizeof(TimeBasicSmem), st>>>(y, g, ws, scalars, status);
     k_autocorr<<<n, kAcThreads, sizeof(AutocorrSmem), st>>>(y, g, tb, ws.ints, scalars);
     note_launch(2);
 }
