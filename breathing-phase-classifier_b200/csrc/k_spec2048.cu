@@ -235,7 +235,8 @@ __global__ void __launch_bounds__(32 * kF2Warps, 3) k_frame2048(const float* __r
 }
 
 // ================================================================================================= k_seg2048
-constexpr int kSegThreads = 192;             // 6 warps = two tempogram frames in flight (96 threads x 4 lags each)
+constexpr int kSegGroups = 3;                // tempogram frames in flight per CTA (96 threads x 4 lags each)
+constexpr int kSegThreads = 96 * kSegGroups; // 9 warps (v41: two groups; the kernel runs four CTAs per SM either way)
 
 struct Seg2048Smem {
     union {
@@ -245,7 +246,7 @@ struct Seg2048Smem {
     double peak[7 * kMaxFrames], valley[7 * kMaxFrames];
     double cent[kMaxFrames], bw[kMaxFrames], flat[kMaxFrames];
     float onset[kMaxFrames + 2 * 192 + 8];            // onset envelope with the tempogram's 192-sample pads
-    __align__(16) float frame[2][kTempoLags + 8];
+    __align__(16) float frame[kSegGroups][kTempoLags + 8];
     float flux[kMaxFrames];
     double sumv[kMaxFrames], sumq[kMaxFrames];
     float ac0[kMaxFrames];
@@ -418,11 +419,12 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
     }
     if (LONG && phase == 1) return;
     if (!LONG || phase == 2) {
-    // two frames in flight: group gidx (96 threads) owns frames gidx, gidx + 2, ...; thread j owns lags 4j .. 4j + 3.
+    // kSegGroups frames in flight: group gidx (96 threads) owns frames gidx, gidx + kSegGroups, ...; thread j owns lags
+    // 4j .. 4j + 3.
     const int gidx = tid / 96, j = tid - gidx * 96, l0 = 4 * j;
     float* F = S.frame[gidx];
-    const int t_step = 2 * (LONG ? (int)gridDim.y : 1);
-    for (int t = gidx + (LONG ? 2 * (int)blockIdx.y : 0); t < T + (T & 1); t += t_step) {
+    const int t_step = kSegGroups * (LONG ? (int)gridDim.y : 1);
+    for (int t = gidx + (LONG ? kSegGroups * (int)blockIdx.y : 0); t < T + kSegGroups - 1; t += t_step) {
         const bool live = t < T;
         if (live) {
             for (int n = j; n < kTempoLags + 8; n += 96)

@@ -627,6 +627,18 @@ __global__ void __launch_bounds__(256) k_modspec_finish_long(Geometry g, Workspa
     for (int i = threadIdx.x; i < NP; i += blockDim.x) om[i] = (i < 40 * T) ? zm(C2[i]) : fill;
 }
 
+// 1 s mode, roles 2 / 3 only (gammatone, chroma_stft + tuning): its own kernel so that the register tiles of the DCT
+// roles do not set its register count (80 -> at most 64: four CTAs per SM instead of three)
+__global__ void __launch_bounds__(256, 4) k_spec512_light(Geometry g, Tables tb, Workspace ws, float* feats, float* scalars,
+                                                          int32_t* status) {
+    extern __shared__ __align__(16) float smem_dyn[];
+    __shared__ double dscratch[32];
+    __shared__ float fscratch[32];
+    const int b = blockIdx.x;
+    if (blockIdx.y == 0) role_gammatone<false>(b, g, tb, ws, feats, smem_dyn, dscratch, fscratch);
+    else role_chroma_stft<false>(b, g, tb, ws, feats, scalars, status, smem_dyn, dscratch, fscratch);
+}
+
 static void set_consumer_smem() {
     static bool done = false;
     if (!done) {
@@ -655,8 +667,8 @@ void launch_spec512_consumers(int n, const Geometry& g, const Tables& tb, const 
     } else {
         k_spec512_consumers<false><<<dim3(n, 2), 256, kConsumerSmemFloats * sizeof(float), st>>>(
             g, tb, ws, feats, scalars, status, nullptr, 0);
-        k_spec512_consumers<false><<<dim3(n, with_chroma ? 2 : 1), 256, kLightSmemFloats * sizeof(float), st>>>(
-            g, tb, ws, feats, scalars, status, nullptr, 2);
+        k_spec512_light<<<dim3(n, with_chroma ? 2 : 1), 256, kLightSmemFloats * sizeof(float), st>>>(g, tb, ws, feats, scalars,
+                                                                                                    status);
     }
     note_launch(2);
     if (g.long_mode) {
