@@ -18,6 +18,6 @@ PY
 if [ "$2" = "full" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/ncu_l_$tag.log 2>&1; echo "ncu list rc=$?"
-  ncu --set full --clock-control none --import-source on --launch-skip 14 -c 14 -f -o gpurun_out/prof_$tag \
+  ncu --set full --clock-control none --import-source on --launch-skip 13 -c 13 -f -o gpurun_out/prof_$tag \
       python tools/profile_step.py --steps 2 --batch 4096 > gpurun_out/ncu_f_$tag.log 2>&1; echo "ncu full rc=$?"
 fi
