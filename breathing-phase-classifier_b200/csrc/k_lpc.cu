@@ -79,7 +79,7 @@ __device__ __forceinline__ void burg_all(double (&F)[kLpcPer], double (&B)[kLpcP
 // phase 0: everything (1 s).  Long mode: phase 1 = the Burg frames of this CTA's share (grid (segment, part)) into the
 // scratch region, phase 2 = statistics + plane (grid (segment)).
 template <bool LONG>
-__global__ void __launch_bounds__(kLpcThreads, 4) k_lpc(const float* __restrict__ y, Geometry g, Tables tb, Workspace ws,
+__global__ void __launch_bounds__(kLpcThreads, 5) k_lpc(const float* __restrict__ y, Geometry g, Tables tb, Workspace ws,
                                                 float* feats, int phase) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LpcSmem& S = *reinterpret_cast<LpcSmem*>(smem_raw);
