@@ -70,7 +70,7 @@ struct DecSmem {
     float a[2 * plen(8000)];                           // input (even | odd); later octaves 2..6
     float o1[2 * plen(kHalf1)];                        // octave 1
 };
-constexpr int kDecThreads = 128;
+constexpr int kDecThreads = 192;                    // 2 CTAs x 6 warps: what 156 registers per thread allow (v46; was 128)
 
 // One decimation stage: in (de-interleaved, half-length hin, i.e. 2 hin samples) -> out (de-interleaved, hin samples)
 // and to global memory in natural order.
