@@ -585,8 +585,10 @@ size_t consumer_scratch_floats(int T) {
     return consumer_role_offset(3, T) + (size_t)2 * 123 * T + kSelectWords + (size_t)13 * T + 128;
 }
 
+// 1 s mode, roles 0 / 1: three CTAs per SM by shared memory; 288 threads (nine warps) is what 72 registers allow
+constexpr int kHeavyThreads = 288;
 template <bool LONG>
-__global__ void __launch_bounds__(LONG ? 512 : 256) k_spec512_consumers(Geometry g, Tables tb, Workspace ws, float* feats,
+__global__ void __launch_bounds__(LONG ? 512 : kHeavyThreads, LONG ? 1 : 3) k_spec512_consumers(Geometry g, Tables tb, Workspace ws, float* feats,
                                                            float* scalars, int32_t* status, float* mel3,
                                                            int role_base) {
     extern __shared__ __align__(16) float smem_dyn[];
@@ -665,7 +667,7 @@ void launch_spec512_consumers(int n, const Geometry& g, const Tables& tb, const 
         k_spec512_consumers<true><<<dim3(n, 2), 512, 0, st>>>(g, tb, ws, feats, scalars, status, nullptr, 0);
         k_spec512_consumers<true><<<dim3(n, with_chroma ? 2 : 1), 512, 0, st>>>(g, tb, ws, feats, scalars, status, nullptr, 2);
     } else {
-        k_spec512_consumers<false><<<dim3(n, 2), 256, kConsumerSmemFloats * sizeof(float), st>>>(
+        k_spec512_consumers<false><<<dim3(n, 2), kHeavyThreads, kConsumerSmemFloats * sizeof(float), st>>>(
             g, tb, ws, feats, scalars, status, nullptr, 0);
         k_spec512_light<<<dim3(n, with_chroma ? 2 : 1), 256, kLightSmemFloats * sizeof(float), st>>>(g, tb, ws, feats, scalars,
                                                                                                     status);
@@ -687,7 +689,7 @@ void launch_logmel_only(int n, const Geometry& g, const Tables& tb, const Worksp
     set_consumer_smem();
     dim3 grid(n, 1);
     if (g.long_mode) k_spec512_consumers<true><<<grid, 512, 0, st>>>(g, tb, ws, nullptr, nullptr, nullptr, mel3, 0);
-    else k_spec512_consumers<false><<<grid, 256, kConsumerSmemFloats * sizeof(float), st>>>(g, tb, ws, nullptr, nullptr,
+    else k_spec512_consumers<false><<<grid, kHeavyThreads, kConsumerSmemFloats * sizeof(float), st>>>(g, tb, ws, nullptr, nullptr,
                                                                                            nullptr, mel3, 0);
     note_launch();
 }
