@@ -17,9 +17,11 @@ __device__ __forceinline__ float c64_abs(double2 x) {
 }
 
 // |re + i im| of a complex64 the way numpy / glibc do it: (float)sqrt((double)re * re + (double)im * im), evaluated in
-// float32 pairs: s = hi + lo exactly (error-free products and sum), r = sqrt(hi) corrected by the residual.  The
-// result differs from the double-precision evaluation only when the exact value lies within ~1e-13 (relative) of a
-// float32 rounding boundary.  (The DSQRT sequence of c64_abs was 6 % of this kernel's instructions.)
+// float32 pairs: s = hi + lo exactly (error-free products and sum), r = sqrt(hi) corrected by the residual.  With a
+// correctly rounded reciprocal square root the result equals the double-precision evaluation on every one of 2 M random
+// inputs; the hardware approximation (<= 2 ulp) leaves a second-order error of ~3e-14, i.e. a 1-ulp difference in about
+// one result per million (tests/test_host.py::test_c64_abs_f32_algorithm emulates both cases on the CPU).
+// (The DSQRT sequence of c64_abs was 6 % of k_frame2048's instructions.)
 // exact path of c64_abs_f32, out of line: its DSQRT sequence is ~32 instructions per call site, and k_frame2048 has 32
 // call sites -- inlined it pushed that kernel's code past the instruction cache (r01 v30: 180 KB of SASS, 11 of 12
 // issue slots lost to "no instruction" stalls)

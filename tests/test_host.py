@@ -254,6 +254,63 @@ def test_radix20_hilbert_fft_on_host(tmp_path):
         assert np.abs(h - ref).max() < 2.0 * np.abs(ref32 - ref).max() + 1e-7 * scale
 
 
+def test_c64_abs_f32_algorithm():
+    """csrc/fft.cuh::c64_abs_f32 (np.abs of a complex64 in float32 pairs, used by the STFT / CQT / Hilbert kernels) emulated
+    operation by operation in numpy (float32 FMAs are exact in float64): equal to (float)sqrt((double)re^2 + (double)im^2)
+    with a correctly rounded rsqrt, and within one ulp in <= 5 per million when the rsqrt is off by 2 ulp (the hardware
+    rsqrt.approx bound)."""
+    f32, f64 = np.float32, np.float64
+
+    def emul(re, im, ulps):
+        a, b = np.abs(re), np.abs(im)
+        x, y = np.maximum(a, b).astype(f64), np.minimum(a, b).astype(f64)
+        p = (x * x).astype(f32); pe = (x * x - p.astype(f64)).astype(f32)
+        q = (y * y).astype(f32); qe = (y * y - q.astype(f64)).astype(f32)
+        hi = (p + q).astype(f32)
+        lo = ((((p - hi).astype(f32) + q).astype(f32)) + (pe + qe).astype(f32)).astype(f32)
+        rs = (1.0 / np.sqrt(hi.astype(f64))).astype(f32)
+        for _ in range(abs(ulps)):
+            rs = np.nextafter(rs, f32(np.inf) if ulps > 0 else f32(0))
+        r0 = (hi * rs).astype(f32).astype(f64)
+        res = ((hi.astype(f64) - r0 * r0).astype(f32) + lo).astype(f32)
+        return (res.astype(f64) * (f32(0.5) * rs).astype(f32).astype(f64) + r0).astype(f32)
+
+    rng = np.random.default_rng(1)
+    n = 1_000_000
+    re = (rng.standard_normal(n) * 10.0 ** rng.uniform(-8, 4, n)).astype(f32)
+    for im in ((rng.standard_normal(n) * 10.0 ** rng.uniform(-8, 4, n)).astype(f32), (re * rng.uniform(0.5, 2.0, n)).astype(f32)):
+        ref = np.sqrt(re.astype(f64) ** 2 + im.astype(f64) ** 2).astype(f32)
+        assert np.array_equal(emul(re, im, 0), ref)
+        for u in (2, -2):
+            out = emul(re, im, u)
+            bad = out != ref
+            assert bad.sum() <= 5
+            assert np.all(np.abs(out[bad].astype(f64) - ref[bad]) <= np.spacing(ref[bad]).astype(f64))
+
+
+def test_div_fast_algorithm():
+    """csrc/k_lpc.cu::div_fast (the Burg reflection coefficient: reciprocal seed with 2^-23 relative error, two Newton
+    steps, one residual correction) emulated with exact rational FMAs: within one ulp of the IEEE quotient."""
+    from fractions import Fraction as Fr
+
+    def fma(a, b, c):
+        return float(Fr(a) * Fr(b) + Fr(c))
+
+    rng = np.random.default_rng(2)
+    worst = 0.0
+    for _ in range(3000):
+        a = float(rng.standard_normal() * 10.0 ** rng.uniform(-30, 30))
+        b = float(abs(rng.standard_normal()) * 10.0 ** rng.uniform(-30, 30)) + 1e-300
+        r = (1.0 / b) * (1.0 + float(rng.choice([-1.0, 1.0])) * 2.0 ** -23)
+        e = fma(-b, r, 1.0); r = fma(r, e, r)
+        e = fma(-b, r, 1.0); r = fma(r, e, r)
+        q = a * r
+        q = fma(r, fma(-b, q, a), q)
+        exact = a / b
+        worst = max(worst, abs(q - exact) / np.spacing(abs(exact)))
+    assert worst <= 1.0
+
+
 # ------------------------------------------------------------------------------------- output writer / packed shard
 def _fake_rows(n, T=63, S=36, seed=3):
     rng = np.random.default_rng(seed)
