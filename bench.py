@@ -182,7 +182,7 @@ def run_ours(args):
     eng = bpc_b200.Engine(device=local, max_batch=B)
 
     # synthetic input: `distinct` seeded segments (host generator == the parity-test generator), tiled to B, PCM16
-    distinct = min(B, args.distinct)
+    distinct = B if args.distinct <= 0 else min(B, args.distinct)
     base = synth_batch_pcm16(rank * 100000, distinct)
     pcm = np.tile(base, ((B + distinct - 1) // distinct, 1))[:B]
     wav_f32 = (torch.from_numpy(pcm).to(dev).float() / 32768.0).contiguous()      # resident in HBM before timing
@@ -240,23 +240,89 @@ def run_ours(args):
     ms_max = float(t.item())
     value = world * args.steps * B / (ms_max * 1e-3)
 
-    # ---- end-to-end through the reference-facing host call: pinned host PCM16 in, host float32 out
-    h_in = torch.from_numpy(pcm.copy()).pin_memory()
-    h_feats = torch.empty((B, 9, 128, T), dtype=torch.float32).pin_memory()
-    h_scal = torch.empty((B, eng.nscal), dtype=torch.float32).pin_memory()
-    h_stat = torch.empty((B,), dtype=torch.int32).pin_memory()
-    e2e_steps = max(1, min(args.steps, 3))
-    eng.precompute_host(h_in.numpy(), h_feats.numpy(), h_scal.numpy(), h_stat.numpy())     # warm-up (allocates slots)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.precompute_host(h_in.numpy(), h_feats.numpy(), h_scal.numpy(), h_stat.numpy())
+    # ---- multi-GPU parity probe (outside every timed region): all ranks precompute the SAME 64 segments; rank 0 checks
+    # that every rank produced bit-identical outputs and that 8 of them match the CPU oracle within the test gates
+    probe = synth_batch_pcm16(777000, 64)
+    pf, ps, pst = eng.precompute(torch.from_numpy(probe).to(dev))
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    chk = torch.cat([pf.view(torch.int32).to(torch.int64).sum(dim=(1, 2, 3)),
+                     ps.contiguous().view(torch.int32).to(torch.int64).sum(dim=1), pst.to(torch.int64)])
+    chks = [chk]
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps * B / float(t.item())
+        chks = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(chks, chk)
+    parity_probe = None
+    if rank == 0:
+        same = all(bool(torch.equal(c, chks[0])) for c in chks)
+        from oracle import pipeline as P_oracle           # the checker, never the thing measured
+        pf_h, ps_h = pf[:8].cpu().numpy(), ps[:8].cpu().numpy()
+        worst_plane, worst_excess, ints_ok = 0.0, -1.0, 0
+        for i in range(8):
+            ch, sc = P_oracle.segment_features(probe[i].astype(np.float32) / np.float32(32768.0))
+            ref = P_oracle.stack_sorted(ch)
+            worst_plane = max(worst_plane, float(np.abs(pf_h[i] - ref).max()))
+            d_abs = np.abs(ps_h[i, :36].astype(np.float64) - sc.astype(np.float64))
+            worst_excess = max(worst_excess, float(np.max(d_abs - (1e-4 * np.abs(sc.astype(np.float64)) + 2e-6))))
+            ints_ok += int(ps_h[i, 22] == sc[22] and ps_h[i, 35] == sc[35])
+        ok = same and worst_plane < 2e-4 and worst_excess <= 0.0 and ints_ok == 8 and int(pst.abs().sum()) == 0
+        parity_probe = {"result": "ok" if ok else "FAILED", "ranks_bit_identical": same, "ranks": world,
+                        "probe_segments": 64, "oracle_checked": 8, "worst_plane_abs": worst_plane,
+                        "scalars_inside_1e-4_rel_plus_2e-6": worst_excess <= 0.0, "integer_outputs_exact": ints_ok}
+    del pf, ps, pst
+
+    # ---- end-to-end through the reference-facing host calls: pinned host PCM16 in, pinned host float32 out.
+    # Headline: bpc_precompute_host_compact -- the compact host layout ([B,772,63] data rows + [B,9] pad values, what the
+    # packed shard / PackedDS consume; buffers from bpc_host_alloc, NUMA-local to the GPU).  Next to it the same call
+    # into the full [B,9,128,63] tensor (bpc_precompute_host: same bytes over PCIe + a host-side fill of the pad rows).
+    h_in = eng.host_empty((B, L), np.int16)
+    h_in[:] = pcm
+    h_rows = eng.host_empty((B, 772, T), np.float32)
+    h_pad = eng.host_empty((B, 9), np.float32)
+    h_scal = eng.host_empty((B, eng.nscal), np.float32)
+    h_stat = eng.host_empty((B,), np.int32)
+    e2e_steps = max(1, min(args.steps, 5))
+
+    def timed_host(fn):
+        fn()                                                              # warm-up (allocates the slots)
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    dt_c = timed_host(lambda: eng.precompute_host_compact(h_in, h_rows, h_pad, h_scal, h_stat))
+    e2e_value = world * e2e_steps * B / dt_c
+    d2h_step = int(B * (772 * T * 4 + 9 * 4 + eng.nscal * 4 + 4))
+    # the compact result must be the full-layout result: expand 16 segments on the host and compare with the device path
+    e2e_check = bool(np.array_equal(bpc_b200.expand_compact(h_rows[:16], h_pad[:16]), feats[:16].cpu().numpy())
+                     and np.array_equal(h_scal[:16], scal[:16].cpu().numpy()))
+    h_feats = eng.host_empty((B, 9, 128, T), np.float32)
+    dt_f = timed_host(lambda: eng.precompute_host(h_in, h_feats, h_scal, h_stat))
+    e2e_full = world * e2e_steps * B / dt_f
+    # concurrent D2H ceiling of this box, measured live: every rank copies the same bytes a step moves, no kernels
+    d_dummy = torch.empty(d2h_step // 4, dtype=torch.float32, device=dev)
+    h_dummy = torch.from_numpy(h_feats.reshape(-1)[: d2h_step // 4])
+    for _ in range(2):
+        h_dummy.copy_(d_dummy, non_blocking=True)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(5):
+        h_dummy.copy_(d_dummy, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    tt = torch.tensor([c0.elapsed_time(c1) / 5], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    d2h_ceiling_gbs = world * d2h_step / (float(tt.item()) * 1e-3) / 1e9
+    d2h_gbs = world * e2e_steps * d2h_step / dt_c / 1e9
+    del d_dummy
 
     # ---- side measurements (not the headline): BASELINE configs[1] stage and the HBM-bound batch-assembly kernel
     extras = {}
@@ -365,8 +431,6 @@ def run_ours(args):
         except Exception as e:
             extras["config1_files_through_process_dataset_threaded"] = {"error": repr(e)}
 
-    compact = os.environ.get("BPC_COMPACT_D2H", "1") != "0"
-    d2h_rows = 772 if compact else 9 * 128
     if rank == 0:
         peaks = {}
         try:
@@ -376,16 +440,55 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
         top = max(ktimes.items(), key=lambda kv: kv[1][0]) if ktimes else ("none", (0.0, 1))
-        traffic = None                                   # DRAM bytes per launch of that kernel from the committed ncu capture
+        # Counters of the committed ncu capture (tools/ncu_counters.py -> profiles/kernel_counters.json): DRAM bytes and
+        # FP64 thread instructions per segment and kernel.  They are properties of the code; the rates below combine
+        # them with the CUDA-event times of THIS run.
+        counters = {}
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"]
-            parts = [tr[k]["dram_bytes_per_launch"] for k in top[0].split("+") if k in tr]
-            if parts:
-                traffic = float(sum(parts)) * min(B, eng.chunk) / tr[top[0].split("+")[0]]["segments_per_launch"]
+            counters = json.load(open(os.path.join(ROOT, "profiles", "kernel_counters.json")))
         except Exception:
             pass
-        total_k = sum(v[0] for v in ktimes.values()) or 1.0
+        ck = counters.get("kernels", {})
+        timing_ids = {"k_stft512": ["k_stft512"], "k_spec512_consumers": ["k_spec512_consumers", "k_spec512_light"],
+                      "k_frame2048": ["k_frame2048"], "k_even2048": ["k_even2048"], "k_cens_dec+k_cens": ["k_cens_dec", "k_cens"],
+                      "k_time_basic+k_autocorr": ["k_time_basic", "k_autocorr", "k_time_fused"], "k_hilbert": ["k_hilbert"],
+                      "k_lpc": ["k_lpc"], "k_stats": ["k_stats_scalars", "k_stats"], "k_seg2048": ["k_seg2048"],
+                      "k_ingest": ["k_ingest"]}
         segs_per_launch = min(B, eng.chunk)
+        traffic = None
+        parts = [ck[k]["dram_bytes_per_segment"] for k in timing_ids.get(top[0], []) if k in ck]
+        if parts:
+            traffic = float(sum(parts)) * segs_per_launch
+        sm_clock_hz = 1e6 * float((clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+        fp64_peak_inst = 148 * 64 * sm_clock_hz                       # FP64 lanes: 64 thread instructions / clk / SM
+        fp64 = None
+        if ck:
+            seg_per_s_gpu = value / world
+            per_kernel = {}
+            for tname, (tms, tcnt) in ktimes.items():
+                names = [k for k in timing_ids.get(tname, []) if k in ck]
+                if not names or tms <= 0:
+                    continue
+                flop = sum(ck[k]["fp64_flop_per_segment"] for k in names)
+                inst = sum(sum(ck[k]["fp64_thread_inst_per_segment"].values()) for k in names)
+                sec = tms / args.steps * 1e-3
+                per_kernel[tname] = {"fp64_flop_per_segment": flop, "ms_per_step": tms / args.steps,
+                                     "achieved_tflops": flop * B / sec / 1e12,
+                                     "frac_of_fma_peak": flop * B / sec / (2 * fp64_peak_inst),
+                                     "pipe_busy_frac": inst * B / sec / fp64_peak_inst}
+            tot_flop = counters.get("total_fp64_flop_per_segment", 0.0)
+            tot_inst = counters.get("total_fp64_inst_per_segment", 0.0)
+            fp64 = {"bound": "fp64 pipe (the roofline that binds this step: every FFT, the Burg recursion and the "
+                             "decimator accumulate in FP64 because librosa / scipy do)",
+                    "flop_per_segment": tot_flop, "thread_inst_per_segment": tot_inst,
+                    "achieved_tflops": tot_flop * seg_per_s_gpu / 1e12,
+                    "peak_tflops": 2 * fp64_peak_inst / 1e12,
+                    "frac": tot_flop * seg_per_s_gpu / (2 * fp64_peak_inst),
+                    "pipe_busy_frac": tot_inst * seg_per_s_gpu / fp64_peak_inst,
+                    "peak_source": f"148 SMs x 64 FP64 lanes x {sm_clock_hz / 1e6:.0f} MHz x 2 (FMA); pipe_busy counts every "
+                                   "FP64 thread instruction (DFMA, DMUL or DADD) as one lane-slot",
+                    "counters_source": counters.get("source"), "per_kernel": per_kernel}
+        total_k = sum(v[0] for v in ktimes.values()) or 1.0
         avg_ms = top[1][0] / max(1, top[1][1])
         achieved = ALG_BYTES_PER_SEG * segs_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
         step_gbs = value / world * ALG_BYTES_PER_SEG / 1e9
@@ -416,18 +519,30 @@ def run_ours(args):
                          "segments_per_launch": segs_per_launch, "alg_bytes_per_segment": ALG_BYTES_PER_SEG,
                          "peak_source": peak_src,
                          "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak},
+                         "traffic_total": (counters.get("total_dram_bytes_per_segment", 0.0) * B) if ck else None,
+                         "traffic_total_over_algorithmic": (counters.get("total_dram_bytes_per_segment", 0.0) / ALG_BYTES_PER_SEG) if ck else None,
+                         "fp64": fp64,
                          "kernel_timing": "instrumented single-stream pass of the same steps, CUDA events around "
                                           "every launch; the timed step overlaps independent kernels on side streams",
                          "single_stream_ms_per_step": serial_ms,
                          "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": int(B * L * 2),
-                    "d2h_bytes_per_step": int(B * (d2h_rows * T * 4 + (9 * 4 if compact else 0) + eng.nscal * 4 + 4)),
-                    "steps": e2e_steps,
-                    "input": "pinned host PCM16 -> bpc_precompute_host -> pinned host float32 [B,9,128,63]",
-                    "d2h_note": ("only the 772 data rows of each segment cross PCIe; the 380 constant pad rows "
-                                 "(pad_freq) are re-created on the host by the library's thread pool from one value per "
-                                 "plane" if compact else "whole planes")},
+                    "d2h_bytes_per_step": d2h_step, "steps": e2e_steps,
+                    "input": "pinned host PCM16 [B,16000] -> bpc_precompute_host_compact -> pinned host float32 rows "
+                             "[B,772,63] + pad [B,9] + scalars [B,36] + status [B] (the compact host layout of "
+                             "include/bpc.h: every data row of the nine planes + one pad_freq constant per plane; "
+                             "bpc_expand_compact / PackedDS rebuild [9,128,63] bit-identically)",
+                    "host_buffers": f"bpc_host_alloc (NUMA node {getattr(eng, 'host_numa_node', -1)}; -1 = single-node box)",
+                    "d2h_gbs": d2h_gbs, "d2h_ceiling_gbs": d2h_ceiling_gbs,
+                    "d2h_frac_of_ceiling": d2h_gbs / d2h_ceiling_gbs if d2h_ceiling_gbs else None,
+                    "d2h_ceiling_how": "all ranks copy d2h_bytes_per_step device->pinned host concurrently, 5 times, no "
+                                       "kernels running; aggregate bytes / slowest rank (tools/d2h_ceiling.py is the long form)",
+                    "matches_device_path": e2e_check,
+                    "full_layout": {"value": e2e_full, "unit": "segments/s",
+                                    "call": "bpc_precompute_host -> pinned host float32 [B,9,128,63]: the same bytes over "
+                                            "PCIe, the 380 constant pad rows per segment written by the library's host threads"}},
+            "parity_probe": parity_probe,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "extras": extras,
@@ -446,7 +561,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="segments per step per GPU")
-    ap.add_argument("--distinct", type=int, default=512, help="distinct synthetic segments tiled to the batch")
+    ap.add_argument("--distinct", type=int, default=0,
+                    help="distinct synthetic segments tiled to the batch (0 = every segment of the batch is distinct)")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-2 / collate side measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (used under ncu only)")
     args = ap.parse_args()

@@ -10,6 +10,8 @@ LIB_PATH = os.path.join(_HERE, "libbpc_b200.so")
 NUM_CHANNELS = 9
 NUM_SCALARS = 36
 PLANE_ROWS = 128
+LIVE_ROWS = (24, 64, 12, 128, 128, 128, 120, 40, 128)     # data rows per plane (sorted-key order); the rest is one pad value
+LIVE_TOTAL = 772
 WAV_F32, WAV_PCM16 = 0, 1
 # sorted .npz keys == channel order of the [B, 9, 128, T] tensor (reference src/dataset.py:26)
 CHANNELS = ("chroma", "gammatone", "lpc", "mel", "mel_delta", "mel_delta2", "mfcc", "mod_spec", "tempogram")
@@ -42,6 +44,16 @@ _SIGS = {
                                  C.c_void_p, C.c_void_p]),
     "bpc_precompute_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                       C.c_void_p]),
+    "bpc_precompute_host_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bpc_live_rows": (C.c_int, [C.c_int]),
+    "bpc_expand_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int]),
+    "bpc_host_alloc": (C.c_void_p, [C.c_void_p, C.c_int64, C.POINTER(C.c_int)]),
+    "bpc_host_free": (None, [C.c_void_p, C.c_void_p]),
+    "bpc_resample_len": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
+    "bpc_resample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "bpc_resample_filter": (C.c_int64, [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                        C.POINTER(C.c_int)]),
     "bpc_stage_logmel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
     "bpc_modspec": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -108,6 +108,24 @@ class Engine:
                "bpc_modspec")
         return out.cpu().numpy() if is_np else out
 
+    def resample(self, y, sr_in: int, sr_out: int = 16000):
+        """librosa.load's rate conversion (process.py:28) on the device: numpy or cuda float32 [n] -> same kind,
+        [ceil(n * sr_out / sr_in)]."""
+        import torch
+        is_np = isinstance(y, np.ndarray)
+        x = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).cuda(self.device) if is_np else y.contiguous()
+        if x.dim() != 1 or x.dtype != torch.float32:
+            raise ValueError("y must be a 1-D float32 waveform")
+        n_out = int(self._lib.bpc_resample_len(int(x.numel()), int(sr_in), int(sr_out)))
+        if n_out < 0:
+            raise ValueError("bad sample rates")
+        out = torch.empty((n_out,), dtype=torch.float32, device=x.device)
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        rc = self._lib.bpc_resample(self._h, x.data_ptr(), int(x.numel()), int(sr_in), int(sr_out), out.data_ptr(), n_out,
+                                    C.c_void_p(st))
+        _check(self._h, rc, "bpc_resample")
+        return out.cpu().numpy() if is_np else out
+
     # ---------------------------------------------------------------------------------------------- host arrays
     def precompute_host(self, wav: np.ndarray, feats=None, scalars=None, status=None):
         """wav: numpy [B, L_in] float32 / int16 (pageable or pinned) -> numpy (feats, scalars, status)."""
@@ -135,6 +153,59 @@ class Engine:
                                            scalars.ctypes.data, status.ctypes.data)
         _check(self._h, rc, "bpc_precompute_host")
         return feats, scalars, status
+
+    def precompute_host_compact(self, wav: np.ndarray, rows=None, pad=None, scalars=None, status=None):
+        """wav: numpy [B, L_in] float32 / int16 -> (rows [B, 772, T], pad [B, 9], scalars, status): the compact host
+        layout of include/bpc.h (only the data rows of every plane + one pad value per plane; `expand_compact` or
+        `PackedDS` rebuild the [9, 128, T] planes).  One contiguous device->host copy per piece, no host fill."""
+        wav = np.ascontiguousarray(wav)
+        if wav.ndim != 2:
+            raise ValueError("wav must be [B, L_in]")
+        if wav.dtype == np.float32:
+            dt = L.WAV_F32
+        elif wav.dtype == np.int16:
+            dt = L.WAV_PCM16
+        else:
+            raise TypeError("wav must be float32 or int16")
+        B, L_in = wav.shape
+        if rows is None:
+            rows = np.empty((B, L.LIVE_TOTAL, self.T), dtype=np.float32)
+        if pad is None:
+            pad = np.empty((B, L.NUM_CHANNELS), dtype=np.float32)
+        if scalars is None:
+            scalars = np.empty((B, self.nscal), dtype=np.float32)
+        if status is None:
+            status = np.empty((B,), dtype=np.int32)
+        for name, a, shape, dtp in (("rows", rows, (B, L.LIVE_TOTAL, self.T), np.float32),
+                                    ("pad", pad, (B, L.NUM_CHANNELS), np.float32),
+                                    ("scalars", scalars, (B, self.nscal), np.float32), ("status", status, (B,), np.int32)):
+            if tuple(a.shape) != shape or a.dtype != dtp or not a.flags.c_contiguous or not a.flags.writeable:
+                raise ValueError(f"{name} must be a writable C-contiguous {np.dtype(dtp).name} array of shape {shape}")
+        rc = self._lib.bpc_precompute_host_compact(self._h, wav.ctypes.data, dt, B, L_in, rows.ctypes.data,
+                                                   pad.ctypes.data, scalars.ctypes.data, status.ctypes.data)
+        _check(self._h, rc, "bpc_precompute_host_compact")
+        return rows, pad, scalars, status
+
+    def host_empty(self, shape, dtype=np.float32) -> np.ndarray:
+        """Pinned host array on the NUMA node of this engine's GPU (bpc_host_alloc); lives as long as the engine or until
+        `host_free(arr)`.  `arr.bpc_numa_node` is not available on ndarrays, so the node is kept in `self.host_numa_node`."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        node = C.c_int(-1)
+        ptr = self._lib.bpc_host_alloc(self._h, max(n, 1), C.byref(node))
+        if not ptr:
+            raise L.BpcError("bpc_host_alloc failed")
+        self.host_numa_node = int(node.value)
+        buf = (C.c_char * max(n, 1)).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._host_ptrs = getattr(self, "_host_ptrs", {})
+        self._host_ptrs[arr.ctypes.data] = ptr
+        return arr
+
+    def host_free(self, arr: np.ndarray):
+        ptr = getattr(self, "_host_ptrs", {}).pop(arr.ctypes.data, None)
+        if ptr is not None and self._h.value:
+            self._lib.bpc_host_free(self._h, C.c_void_p(ptr))
 
     # ------------------------------------------------------------------------------------------------ statistics
     def channel_stats(self) -> np.ndarray:
@@ -192,6 +263,36 @@ class Engine:
         if got.value != out.nbytes:
             raise L.BpcError(f"debug {what}: wanted {out.nbytes} bytes, got {got.value}")
         return out
+
+
+def expand_compact(rows: np.ndarray, pad: np.ndarray, out: np.ndarray | None = None, threads: int = 4) -> np.ndarray:
+    """Compact host layout (rows [n, 772, T], pad [n, 9]) -> the full [n, 9, 128, T] tensor (bpc_expand_compact; host
+    only, no GPU involved).  Bit-identical to what `precompute_host` returns."""
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    pad = np.ascontiguousarray(pad, dtype=np.float32)
+    if rows.ndim != 3 or rows.shape[1] != L.LIVE_TOTAL or pad.shape != (rows.shape[0], L.NUM_CHANNELS):
+        raise ValueError("rows must be [n, 772, T] and pad [n, 9]")
+    n, _, T = rows.shape
+    if out is None:
+        out = np.empty((n, L.NUM_CHANNELS, L.PLANE_ROWS, T), dtype=np.float32)
+    if out.shape != (n, L.NUM_CHANNELS, L.PLANE_ROWS, T) or out.dtype != np.float32 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous float32 [n, 9, 128, T] array")
+    rc = L.lib().bpc_expand_compact(rows.ctypes.data, pad.ctypes.data, n, T, out.ctypes.data, int(threads))
+    if rc != 0:
+        raise L.BpcError(f"bpc_expand_compact failed ({rc})")
+    return out
+
+
+def resample_filter(sr_in: int, sr_out: int):
+    """Host-side polyphase table of bpc_resample (no GPU needed) -> (p, q, half, tab [p, 2 half] float64)."""
+    lib = L.lib()
+    p, q, half = C.c_int(), C.c_int(), C.c_int()
+    cap = 1 << 22
+    buf = np.empty(cap, dtype=np.float64)
+    n = lib.bpc_resample_filter(int(sr_in), int(sr_out), buf.ctypes.data, cap, C.byref(p), C.byref(q), C.byref(half))
+    if n < 0:
+        raise L.BpcError(f"bpc_resample_filter failed ({n})")
+    return p.value, q.value, half.value, buf[:n].reshape(p.value, 2 * half.value).copy()
 
 
 def table(name: str, tuning_idx: int = 50, params: L.Params | None = None) -> np.ndarray:

@@ -68,7 +68,13 @@ def process_dataset_threaded(df, audio_dir, target_dir, dataset_name, engine=Non
     Three stages run concurrently, one batch apart: the C++ reader pool decodes batch k+1, the GPU path computes batch k
     and the C++ writer pool serialises batch k-1 (ctypes releases the GIL during all three)."""
     items = [(fid, os.path.join(audio_dir, wav_name_for(fid, dataset_name))) for fid in df["ID"].tolist()]
-    eng = engine if engine is not None else _m._get_engine()
+    # A batched caller owns its engine (no debug planes, chunks of the batch size, no ENGINE_LOCK); the shared
+    # single-segment debug engine of methods.py serves the per-file mirrors only.
+    own_engine = engine is None
+    if own_engine:
+        from ..engine import Engine
+        engine = Engine(device=0, max_batch=max(1, min(batch, max(1, len(items)))), debug=False)
+    eng = engine
     results = [None] * len(items)
     starts = list(range(0, len(items), batch))
     shard = ShardWriter(os.path.join(target_dir, dataset_name), len(items), eng.T, eng.nscal) if packed and items else None
@@ -96,17 +102,18 @@ def process_dataset_threaded(df, audio_dir, target_dir, dataset_name, engine=Non
             pos = [lo + i for i in good_rows]
             ids = [items[p][0] for p in pos]
             if packed:
-                # the library writes this batch straight into the shard's memory-mapped arrays
+                # the library writes this batch straight into the shard's memory-mapped arrays, in the compact host
+                # layout (data rows + one pad value per plane: nothing is expanded on the way to disk)
                 n = len(ids)
-                f_out, s_out, st_out = shard.reserve(n)
-                with _m.ENGINE_LOCK:
-                    eng.precompute_host(batch_wav, f_out, s_out, st_out)
+                r_out, p_out, s_out, st_out = shard.reserve(n)
+                eng.precompute_host_compact(batch_wav, r_out, p_out, s_out, st_out)
                 bad = np.flatnonzero(np.asarray(st_out) & 1)
                 if len(bad):                          # rare: drop the rows whose input was not finite
                     keep = [i for i in range(n) if not (st_out[i] & 1)]
+                    kept = [np.asarray(a)[keep] for a in (r_out, p_out, s_out, st_out)]
                     shard.unreserve(n)
-                    f2, s2, st2 = shard.reserve(len(keep))
-                    f2[:] = np.asarray(f_out)[keep]; s2[:] = np.asarray(s_out)[keep]; st2[:] = np.asarray(st_out)[keep]
+                    for dst, src in zip(shard.reserve(len(keep)), kept):
+                        dst[:] = src
                     shard.commit([ids[i] for i in keep])
                 else:
                     shard.commit(ids)
@@ -114,8 +121,7 @@ def process_dataset_threaded(df, audio_dir, target_dir, dataset_name, engine=Non
                 for i in range(n):
                     results[pos[i]] = (ids[i], False, "non-finite samples in input") if i in badset else (ids[i], True, None)
             else:
-                with _m.ENGINE_LOCK:
-                    feats, scal, status = eng.precompute_host(batch_wav)
+                feats, scal, status = eng.precompute_host(batch_wav)
                 if pending_write is not None:
                     pending_write.result()
                 pending_write = pool.submit(_write, pos, ids, feats, scal, status)
@@ -123,6 +129,8 @@ def process_dataset_threaded(df, audio_dir, target_dir, dataset_name, engine=Non
             pending_write.result()
     if shard is not None:
         shard.close()
+    if own_engine:
+        eng.close()
     successful = failed = 0
     for fid, ok, err in results:
         if ok:

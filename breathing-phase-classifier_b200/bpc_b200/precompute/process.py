@@ -16,22 +16,33 @@ from . import methods as _m
 NPZ_KEYS = ("mel", "mfcc", "chroma", "mel_delta", "mel_delta2", "gammatone", "lpc", "mod_spec", "tempogram")
 
 
-def load_wav(path: str):
-    """librosa.load(path, sr=16000) for PCM wav files: int16 stays int16 (the engine scales by 1/32768 on device)."""
-    import scipy.io.wavfile
-    sr, data = scipy.io.wavfile.read(path)
-    if sr != SR:
-        raise ValueError(f"{path}: sample rate {sr} != {SR}; resampling is not part of this build")
-    if data.ndim > 1:                                   # librosa.load(mono=True): channel mean
-        data = data.astype(np.float32).mean(axis=1) / (32768.0 if data.dtype == np.int16 else 1.0)
-        return data.astype(np.float32)
+def _to_float32(data: np.ndarray) -> np.ndarray:
+    """soundfile's integer -> float32 scaling (what librosa.load sees): int16 / 2^15, int32 (and 24-bit, which scipy
+    widens to int32) / 2^31, unsigned 8-bit (x - 128) / 2^7, floats as they are."""
     if data.dtype == np.int16:
-        return data
+        return data.astype(np.float32) / np.float32(32768.0)
     if data.dtype == np.int32:
         return (data.astype(np.float64) / 2147483648.0).astype(np.float32)
     if data.dtype == np.uint8:
-        return ((data.astype(np.float32) - 128.0) / 128.0).astype(np.float32)
+        return (data.astype(np.float32) - np.float32(128.0)) / np.float32(128.0)
     return data.astype(np.float32)
+
+
+def load_wav(path: str):
+    """librosa.load(path, sr=16000) for PCM wav files (process.py:28): mono int16 at 16 kHz stays int16 (the engine
+    applies the 1/32768 on device); every other sample format is scaled by dtype first, multi-channel files are then
+    averaged over channels (librosa.to_mono), and any other sample rate is resampled to 16 kHz (resample.py)."""
+    import scipy.io.wavfile
+    sr, data = scipy.io.wavfile.read(path)
+    if data.ndim == 1 and data.dtype == np.int16 and sr == SR:
+        return data
+    y = _to_float32(data)
+    if y.ndim > 1:                                      # librosa.load(mono=True): channel mean, in float32
+        y = np.mean(y, axis=1, dtype=np.float32)
+    if sr != SR:
+        from .resample import resample
+        y = resample(y, sr, SR)
+    return np.ascontiguousarray(y, dtype=np.float32)
 
 
 WAV_ERR_OPEN, WAV_ERR_FORMAT, WAV_ERR_UNSUPPORTED = -10, -11, -12        # include/bpc.h: bpc_wav_code
@@ -57,13 +68,11 @@ def load_wav_batch(paths, length=EXPECTED_LEN, threads=8):
     errors = [None] * n
     slow = {}
     for i in np.flatnonzero(code):
-        if code[i] == WAV_ERR_UNSUPPORTED and sr[i] == SR:
+        if code[i] == WAV_ERR_UNSUPPORTED:              # stereo, other sample formats, other rates (resampled on the device)
             try:
                 slow[i] = load_wav(paths[i])
             except Exception as e:  # noqa: BLE001
                 errors[i] = str(e)
-        elif code[i] == WAV_ERR_UNSUPPORTED:
-            errors[i] = f"{paths[i]}: sample rate {sr[i]} != {SR}; resampling is not part of this build"
         elif code[i] == WAV_ERR_OPEN:
             errors[i] = f"[Errno 2] No such file or directory: '{paths[i]}'"
         else:

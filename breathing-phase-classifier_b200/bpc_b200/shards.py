@@ -5,12 +5,16 @@ re-opens one file per item (dataset.py:37-57).  At the 1M-segment scale of BASEL
 files and a million zip parses per epoch, so next to the drop-in per-segment writer (`write_npz_batch`, the C++ pool in
 csrc/npz.cpp) the path can write a *packed shard*:
 
-    <dir>/feats.npy      float32 [N, 9, 128, T]   channel axis in sorted-key order (== dataset.py:25-26)
+    <dir>/feats.npy      float32 [N, 9, 128, T]   channel axis in sorted-key order (== dataset.py:25-26)      (v1), or
+    <dir>/rows.npy       float32 [N, 772, T]      the data rows of the nine planes back to back  }  compact (v2, default):
+    <dir>/pad.npy        float32 [N, 9]           the constant of every plane's pad rows         }  what bpc_precompute_host_compact
+                                                  (pad_freq, methods.py:39-46)                       writes, 67 % of the bytes
     <dir>/scalars.npy    float32 [N, S]
     <dir>/status.npy     int32   [N]              per-segment status bits (include/bpc.h)
     <dir>/index.json     {"ids": [...], "channels": [...], "T": T, "S": S, "params": {...}}
 
-Both arrays are plain `.npy` files, so `np.load(mmap_mode="r")` maps them without a copy.  `PackedDS` has the
+All arrays are plain `.npy` files, so `np.load(mmap_mode="r")` maps them without a copy; a compact shard rebuilds the
+[9, 128, T] planes of an item when it is read (`PackedShard.feats[i]`, bit-identical to the full layout).  `PackedDS` has the
 constructor, attributes and item layout of the reference `DS` (dataset.py:7-57); `collate_fn` is dataset.py:59-73.
 """
 from __future__ import annotations
@@ -64,15 +68,39 @@ def write_npz_batch(target_dir: str, file_ids, feats: np.ndarray, scalars: np.nd
 
 
 # ------------------------------------------------------------------------------------------------ packed shard
-class ShardWriter:
-    """Append batches of precompute output to a packed shard of `capacity` segments; `close()` writes the index."""
+def compact_from_full(feats: np.ndarray):
+    """[n, 9, 128, T] -> (rows [n, 772, T], pad [n, 9]): keep the data rows, and the first pad row's first value."""
+    feats = np.asarray(feats, dtype=np.float32)
+    n, _, _, T = feats.shape
+    rows = np.empty((n, L.LIVE_TOTAL, T), dtype=np.float32)
+    pad = np.zeros((n, L.NUM_CHANNELS), dtype=np.float32)
+    r0 = 0
+    for c, lv in enumerate(L.LIVE_ROWS):
+        rows[:, r0:r0 + lv] = feats[:, c, :lv]
+        if lv < L.PLANE_ROWS:
+            pad[:, c] = feats[:, c, lv, 0]
+        r0 += lv
+    return rows, pad
 
-    def __init__(self, target_dir: str, capacity: int, T: int, S: int = L.NUM_SCALARS, params: dict | None = None):
+
+class ShardWriter:
+    """Append batches of precompute output to a packed shard of `capacity` segments; `close()` writes the index.
+    compact=True (default) stores the compact host layout (rows + pad), compact=False the full [N, 9, 128, T] tensor."""
+
+    def __init__(self, target_dir: str, capacity: int, T: int, S: int = L.NUM_SCALARS, params: dict | None = None,
+                 compact: bool = True):
         os.makedirs(target_dir, exist_ok=True)
         self.dir, self.capacity, self.T, self.S = target_dir, int(capacity), int(T), int(S)
+        self.compact = bool(compact)
         fmt = np.lib.format
-        self.feats = fmt.open_memmap(os.path.join(target_dir, "feats.npy"), mode="w+", dtype=np.float32,
-                                     shape=(self.capacity, L.NUM_CHANNELS, L.PLANE_ROWS, self.T))
+        if self.compact:
+            self.rows = fmt.open_memmap(os.path.join(target_dir, "rows.npy"), mode="w+", dtype=np.float32,
+                                        shape=(self.capacity, L.LIVE_TOTAL, self.T))
+            self.pad = fmt.open_memmap(os.path.join(target_dir, "pad.npy"), mode="w+", dtype=np.float32,
+                                       shape=(self.capacity, L.NUM_CHANNELS))
+        else:
+            self.feats = fmt.open_memmap(os.path.join(target_dir, "feats.npy"), mode="w+", dtype=np.float32,
+                                         shape=(self.capacity, L.NUM_CHANNELS, L.PLANE_ROWS, self.T))
         self.scalars = fmt.open_memmap(os.path.join(target_dir, "scalars.npy"), mode="w+", dtype=np.float32,
                                        shape=(self.capacity, self.S))
         self.status = fmt.open_memmap(os.path.join(target_dir, "status.npy"), mode="w+", dtype=np.int32,
@@ -81,19 +109,28 @@ class ShardWriter:
         self.params = params or {}
 
     def append(self, file_ids, feats, scalars, status=None):
+        """feats: full [n, 9, 128, T] planes (compacted here when the shard is compact)."""
         n = len(file_ids)
-        f, s, st = self.reserve(n)
-        f[:] = feats
-        s[:] = scalars
-        st[:] = 0 if status is None else status
+        views = self.reserve(n)
+        if self.compact:
+            r, p = compact_from_full(feats)
+            views[0][:] = r
+            views[1][:] = p
+        else:
+            views[0][:] = feats
+        views[-2][:] = scalars
+        views[-1][:] = 0 if status is None else status
         self.commit(file_ids)
 
     def reserve(self, n: int):
-        """Views of the next n rows (feats, scalars, status) for a producer that writes in place; follow with commit()."""
+        """Views of the next n rows for a producer that writes in place -- (rows, pad, scalars, status) for a compact
+        shard, (feats, scalars, status) otherwise; follow with commit()."""
         lo = len(self.ids)
         if lo + n > self.capacity:
             raise ValueError("shard capacity exceeded")
         self._reserved = n
+        if self.compact:
+            return self.rows[lo:lo + n], self.pad[lo:lo + n], self.scalars[lo:lo + n], self.status[lo:lo + n]
         return self.feats[lo:lo + n], self.scalars[lo:lo + n], self.status[lo:lo + n]
 
     def unreserve(self, n: int):
@@ -110,12 +147,19 @@ class ShardWriter:
         len(ids) rows of the arrays."""
         if len(self.ids) > self.capacity or (not allow_short and len(self.ids) != self.capacity):
             raise ValueError(f"shard holds {len(self.ids)} of {self.capacity} segments")
-        for a in (self.feats, self.scalars, self.status):
+        arrays = [self.rows, self.pad] if self.compact else [self.feats]
+        for a in arrays + [self.scalars, self.status]:
             a.flush()
         with open(os.path.join(self.dir, INDEX_NAME), "w") as f:
             json.dump({"ids": self.ids, "rows": len(self.ids), "channels": list(L.CHANNELS), "T": self.T, "S": self.S,
-                       "params": self.params, "format": "bpc_b200 packed shard v1"}, f)
-        del self.feats, self.scalars, self.status
+                       "params": self.params, "layout": "compact" if self.compact else "full",
+                       "live_rows": list(L.LIVE_ROWS),
+                       "format": "bpc_b200 packed shard v2" if self.compact else "bpc_b200 packed shard v1"}, f)
+        if self.compact:
+            del self.rows, self.pad
+        else:
+            del self.feats
+        del self.scalars, self.status
 
     def __enter__(self):
         return self
@@ -123,6 +167,27 @@ class ShardWriter:
     def __exit__(self, et, ev, tb):
         if et is None:
             self.close(allow_short=False)
+
+
+class CompactFeats:
+    """Read-only [N, 9, 128, T] view over a compact shard: indexing with an int, a slice or an index array rebuilds
+    the planes of the selected segments (bpc_expand_compact on the host)."""
+
+    def __init__(self, rows, pad):
+        self.rows, self.pad = rows, pad
+        self.shape = (rows.shape[0], L.NUM_CHANNELS, L.PLANE_ROWS, rows.shape[2])
+        self.dtype = np.dtype(np.float32)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, idx):
+        from .engine import expand_compact
+        one = isinstance(idx, (int, np.integer))
+        sel = [int(idx)] if one else idx
+        out = expand_compact(np.ascontiguousarray(self.rows[sel]), np.ascontiguousarray(self.pad[sel]),
+                             threads=1 if one else 4)
+        return out[0] if one else out
 
 
 class PackedShard:
@@ -135,7 +200,12 @@ class PackedShard:
         self.row = {fid: i for i, fid in enumerate(self.ids)}
         self.channels = list(self.index["channels"])
         n = len(self.ids)
-        self.feats = np.load(os.path.join(shard_dir, "feats.npy"), mmap_mode="r")[:n]
+        if self.index.get("layout", "full") == "compact":
+            self.rows = np.load(os.path.join(shard_dir, "rows.npy"), mmap_mode="r")[:n]
+            self.pad = np.load(os.path.join(shard_dir, "pad.npy"), mmap_mode="r")[:n]
+            self.feats = CompactFeats(self.rows, self.pad)
+        else:
+            self.feats = np.load(os.path.join(shard_dir, "feats.npy"), mmap_mode="r")[:n]
         self.scalars = np.load(os.path.join(shard_dir, "scalars.npy"), mmap_mode="r")[:n]
         self.status = np.load(os.path.join(shard_dir, "status.npy"), mmap_mode="r")[:n]
 

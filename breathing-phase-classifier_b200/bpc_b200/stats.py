@@ -2,8 +2,9 @@
 
 Per-segment normalisation in the reference is local to each segment (process.py:36-38,47,55,60,65,70,76), so these
 statistics never change the `.npz` contents; they are an extra summary a trainer may use.  The accumulator is a
-[(9 + S), 5] float64 tensor = {count, sum, sum of squares, min, max}; the exchange is one SUM all-reduce over the first
-three columns plus one MIN and one MAX over the last two (NCCL on GPUs, gloo in the CPU tests).
+[(9 + S), 5] float64 tensor = {count, sum, sum of squares, min, max}.  The exchange is ONE collective: an all-gather of
+the 1.8 KB accumulators (NCCL on GPUs, gloo in the CPU tests), after which every rank reduces the R copies locally --
+SUM over the first three columns, MIN and MAX over the last two, in rank order, so every rank holds bit-identical results.
 """
 from __future__ import annotations
 
@@ -14,15 +15,16 @@ def allreduce_stats(st, dist=None, group=None):
         import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return st
-    head = st[:, 0:3].contiguous()
-    mn = st[:, 3].contiguous()
-    mx = st[:, 4].contiguous()
-    dist.all_reduce(head, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
-    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-    st[:, 0:3] = head
-    st[:, 3] = mn
-    st[:, 4] = mx
+    world = dist.get_world_size(group)
+    src = st.contiguous()
+    parts = [src.new_empty(src.shape) for _ in range(world)]
+    dist.all_gather(parts, src, group=group)
+    allr = parts[0].new_empty((world,) + tuple(src.shape))
+    for r, p in enumerate(parts):
+        allr[r] = p
+    st[:, 0:3] = allr[:, :, 0:3].sum(dim=0)
+    st[:, 3] = allr[:, :, 3].min(dim=0).values
+    st[:, 4] = allr[:, :, 4].max(dim=0).values
     return st
 
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -21,6 +22,9 @@
 #endif
 #if defined(__linux__)
 #include <sched.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #endif
 
 #include "../../include/bpc.h"
@@ -53,12 +57,14 @@ struct Slot {                      // one in-flight chunk of the host-buffer pat
     cudaEvent_t fill_ready = nullptr; // the pad values of this chunk are in h_fill
     float* d_fill = nullptr;          // [chunk, 9] pad value of every plane (host path: pad rows are not transferred)
     float* h_fill = nullptr;
+    float* d_rows = nullptr;          // [chunk, 772, T] the data rows back to back (k_compact_rows): one contiguous D2H
 };
 
 // Rows of each plane that carry data; rows live..127 are one constant per plane (pad_freq, methods.py:39-46):
 // chroma 12 + 12 (process.py:54-57), gammatone N_GAMMATONE, lpc N_LPC, mel x3 full, mfcc 3 * N_MFCC, mod_spec N_MFCC,
 // tempogram full (truncated from 384 rows, process.py:78).
 const int kLiveRows[9] = {24, 64, 12, 128, 128, 128, 120, 40, 128};
+constexpr int kLiveTotal = BPC_LIVE_ROWS;
 
 struct RowRun { int start, end; };     // [start, end) in the flattened 9 * 128 rows of one segment
 
@@ -84,11 +90,120 @@ inline void fill_stream(float* p, float* e, float v) {
     while (p < e) *p++ = v;
 }
 
+
+// ---- NUMA placement of the host side (multi-GPU boxes are multi-socket: a device->host copy into memory of the other
+// socket crosses the inter-socket link and runs at a fraction of the PCIe rate; tools/d2h_ceiling.py measures it).
+struct NumaInfo {
+    int node = -1;                   // node of the GPU's PCIe root (-1: unknown / not NUMA)
+    std::vector<int> cpus;           // that node's CPUs that this process may run on
+};
+
+std::string read_small_file(const std::string& path) {
+    std::string out;
+    if (FILE* f = std::fopen(path.c_str(), "r")) {
+        char buf[4096];
+        const size_t n = std::fread(buf, 1, sizeof(buf) - 1, f);
+        buf[n] = 0;
+        out = buf;
+        std::fclose(f);
+    }
+    while (!out.empty() && (out.back() == '\n' || out.back() == ' ')) out.pop_back();
+    return out;
+}
+
+std::vector<int> parse_cpulist(const std::string& s) {
+    std::vector<int> cpus;
+    size_t i = 0;
+    while (i < s.size()) {
+        char* end = nullptr;
+        const long a = std::strtol(s.c_str() + i, &end, 10);
+        if (end == s.c_str() + i) break;
+        long b = a;
+        i = (size_t)(end - s.c_str());
+        if (i < s.size() && s[i] == '-') {
+            b = std::strtol(s.c_str() + i + 1, &end, 10);
+            i = (size_t)(end - s.c_str());
+        }
+        for (long c = a; c <= b && c < 4096; ++c) cpus.push_back((int)c);
+        if (i < s.size() && s[i] == ',') ++i;
+    }
+    return cpus;
+}
+
+NumaInfo numa_of_device(int device) {
+    NumaInfo info;
+#if defined(__linux__)
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return info; }
+    for (char* c = bus; *c; ++c) *c = (char)std::tolower((unsigned char)*c);
+    const std::string base = std::string("/sys/bus/pci/devices/") + bus;
+    const std::string node = read_small_file(base + "/numa_node");
+    if (!node.empty()) info.node = std::atoi(node.c_str());
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    const bool have_mask = sched_getaffinity(0, sizeof(allowed), &allowed) == 0;
+    for (int c : parse_cpulist(read_small_file(base + "/local_cpulist")))
+        if (!have_mask || (c < CPU_SETSIZE && CPU_ISSET(c, &allowed))) info.cpus.push_back(c);
+    // one node only (or the kernel does not know): nothing to place
+    if (read_small_file("/sys/devices/system/node/online").find_first_of(",-") == std::string::npos) info.node = -1;
+#endif
+    return info;
+}
+
+void bind_this_thread(const std::vector<int>& cpus) {
+#if defined(__linux__)
+    if (cpus.empty()) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    for (int c : cpus) if (c < CPU_SETSIZE) CPU_SET(c, &set);
+    sched_setaffinity(0, sizeof(set), &set);
+#endif
+}
+
+// Page-aligned host memory on `numa.node` (mbind; containers that filter the syscall still get first-touch placement
+// because the touching thread is bound to the node's CPUs), registered with CUDA.  Returns nullptr on failure.
+void* numa_pinned_alloc(const NumaInfo& numa, size_t bytes, bool place) {
+#if defined(__linux__)
+    const size_t len = (bytes + 4095) & ~size_t(4095);
+    void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return nullptr;
+    madvise(p, len, MADV_HUGEPAGE);
+    cpu_set_t old;
+    const bool restore = place && !numa.cpus.empty() && sched_getaffinity(0, sizeof(old), &old) == 0;
+    if (place && numa.node >= 0 && numa.node < 64) {
+        unsigned long mask = 1ul << numa.node;
+        syscall(SYS_mbind, p, len, 1 /* MPOL_PREFERRED */, &mask, 65ul, 0u);
+    }
+    if (restore) bind_this_thread(numa.cpus);
+    std::memset(p, 0, len);                                   // first touch
+    if (restore) sched_setaffinity(0, sizeof(old), &old);
+    if (cudaHostRegister(p, len, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        munmap(p, len);
+        return nullptr;
+    }
+    return p;
+#else
+    void* p = nullptr;
+    return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr;
+#endif
+}
+
+void numa_pinned_free(void* p, size_t bytes) {
+#if defined(__linux__)
+    cudaHostUnregister(p);
+    munmap(p, (bytes + 4095) & ~size_t(4095));
+#else
+    (void)bytes;
+    cudaFreeHost(p);
+#endif
+}
+
 // Minimal fork-join pool for the host-side work of the host path (pad-row fill, staging copies).
 class HostPool {
 public:
-    explicit HostPool(int n) {
-        for (int i = 0; i < n; ++i) th_.emplace_back([this, i] { loop(i); });
+    explicit HostPool(int n, std::vector<int> cpus = {}) : cpus_(std::move(cpus)) {
+        for (int i = 0; i < n; ++i) th_.emplace_back([this, i] { bind_this_thread(cpus_); loop(i); });
     }
     ~HostPool() {
         { std::lock_guard<std::mutex> l(m_); stop_ = true; ++gen_; }
@@ -120,6 +235,7 @@ private:
             { std::lock_guard<std::mutex> l(m_); if (--pending_ == 0) done_.notify_one(); }
         }
     }
+    std::vector<int> cpus_;
     std::vector<std::thread> th_;
     std::mutex m_;
     std::condition_variable cv_, done_;
@@ -148,7 +264,15 @@ struct bpc_handle {
     bool slots_ready = false;
     size_t slot_wav_bytes = 0;
     int* live_dev = nullptr;       // kLiveRows on the device
-    HostPool* pool = nullptr;      // host threads of the host path (env BPC_HOST_THREADS, default 4)
+    HostPool* pool = nullptr;      // host threads of the host path (env BPC_HOST_THREADS; default min(8, cores / ranks))
+    NumaInfo numa{};               // NUMA node / local CPUs of this GPU (env BPC_NUMA=0: no placement)
+    bool numa_place = true;
+    std::vector<std::pair<void*, size_t>> numa_allocs;   // numa_pinned_alloc blocks owned by the handle or handed out
+    bool contig_d2h = true;        // compact host layout: k_compact_rows + ONE copy per piece (env BPC_D2H_MODE=2d: row runs)
+    struct Resampler { int sr_in, sr_out, p, q, half; const double* tab; };
+    std::vector<Resampler> resamplers;   // polyphase tables uploaded so far (bpc_resample)
+    cudaEvent_t ws_free = nullptr; // end of the last enqueue that used the workspace (any stream)
+    bool ws_used = false;
     bool compact_d2h = true;       // host path transfers live rows only (env BPC_COMPACT_D2H=0: whole planes)
     int host_chunk = 0;            // piece size of the host path (env BPC_HOST_CHUNK, default chunk / 2: the D2H of a piece
                                    // can only start when its kernels are done, so smaller pieces shorten the ramp)
@@ -465,6 +589,9 @@ int run_chunk(bpc_handle* h, const void* wav, int wav_dtype, int64_t L_in, int n
               int32_t* status, cudaStream_t st) {
     const Geometry& g = h->g;
     const Workspace& ws = h->debug ? h->ws_dbg : h->ws;
+    // One workspace per handle: whatever stream the previous enqueue used, this one starts after it (calls on a handle
+    // are serialised by the caller on the host, not necessarily on one stream).
+    if (h->ws_used) BPC_CUDA(h, cudaStreamWaitEvent(st, h->ws_free, 0));
     const float* y;
     if (wav_dtype == BPC_WAV_F32 && L_in == g.L && (reinterpret_cast<uintptr_t>(wav) & 15) == 0) {
         y = static_cast<const float*>(wav);                   // pad_or_truncate is the identity: no copy
@@ -534,6 +661,16 @@ int run_chunk(bpc_handle* h, const void* wav, int wav_dtype, int64_t L_in, int n
     timed(9, [&] { launch_stats(n, g, feats, scalars, h->stats_acc, ws.stats_acc == nullptr, st); });
     h->last_n = n;
     BPC_CUDA(h, cudaGetLastError());
+    BPC_CUDA(h, cudaEventRecord(h->ws_free, st));
+    h->ws_used = true;
+    return BPC_OK;
+}
+
+int host_pinned(bpc_handle* h, size_t bytes, void** out) {
+    void* p = numa_pinned_alloc(h->numa, bytes, h->numa_place);
+    if (!p) { h->err = "pinned host allocation failed"; return BPC_ERR_ALLOC; }
+    h->numa_allocs.push_back({p, bytes});
+    *out = p;
     return BPC_OK;
 }
 
@@ -547,23 +684,24 @@ int ensure_slots(bpc_handle* h) {
     const size_t C = (size_t)h->host_chunk;                             // the host path moves pieces of host_chunk segments
     h->slot_wav_bytes = C * (size_t)g.L * 4 * 2;                        // room for L_in up to 2 * L of float32
     const size_t feats_bytes = C * 9 * kPlaneRows * (size_t)g.T * 4, scal_bytes = C * (size_t)g.nscal * 4;
+    const size_t rows_bytes = C * (size_t)kLiveTotal * (size_t)g.T * 4;
+    int rc;
     for (int i = 0; i < kSlots; ++i) {
         Slot& s = h->slot[i];
         BPC_CUDA(h, cudaMalloc(&s.d_wav, h->slot_wav_bytes));
         BPC_CUDA(h, cudaMalloc((void**)&s.d_feats, feats_bytes));
         BPC_CUDA(h, cudaMalloc((void**)&s.d_scalars, scal_bytes));
         BPC_CUDA(h, cudaMalloc((void**)&s.d_status, C * 4));
-        h->dev_allocs.push_back(s.d_wav); h->dev_allocs.push_back(s.d_feats);
-        h->dev_allocs.push_back(s.d_scalars); h->dev_allocs.push_back(s.d_status);
-        BPC_CUDA(h, cudaMallocHost(&s.h_wav, h->slot_wav_bytes));
-        BPC_CUDA(h, cudaMallocHost((void**)&s.h_feats, feats_bytes));
-        BPC_CUDA(h, cudaMallocHost((void**)&s.h_scalars, scal_bytes));
-        BPC_CUDA(h, cudaMallocHost((void**)&s.h_status, C * 4));
+        BPC_CUDA(h, cudaMalloc((void**)&s.d_rows, rows_bytes));
         BPC_CUDA(h, cudaMalloc((void**)&s.d_fill, C * 9 * 4));
-        BPC_CUDA(h, cudaMallocHost((void**)&s.h_fill, C * 9 * 4));
-        h->dev_allocs.push_back(s.d_fill); h->host_allocs.push_back(s.h_fill);
-        h->host_allocs.push_back(s.h_wav); h->host_allocs.push_back(s.h_feats);
-        h->host_allocs.push_back(s.h_scalars); h->host_allocs.push_back(s.h_status);
+        for (void* d : {(void*)s.d_wav, (void*)s.d_feats, (void*)s.d_scalars, (void*)s.d_status, (void*)s.d_rows, (void*)s.d_fill})
+            h->dev_allocs.push_back(d);
+        // pinned staging on the GPU's NUMA node (used when the caller's buffers are pageable)
+        if ((rc = host_pinned(h, h->slot_wav_bytes, &s.h_wav))) return rc;
+        if ((rc = host_pinned(h, feats_bytes, (void**)&s.h_feats))) return rc;
+        if ((rc = host_pinned(h, scal_bytes, (void**)&s.h_scalars))) return rc;
+        if ((rc = host_pinned(h, C * 4, (void**)&s.h_status))) return rc;
+        if ((rc = host_pinned(h, C * 9 * 4, (void**)&s.h_fill))) return rc;
         BPC_CUDA(h, cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
         BPC_CUDA(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         BPC_CUDA(h, cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
@@ -572,18 +710,20 @@ int ensure_slots(bpc_handle* h) {
     BPC_CUDA(h, cudaMalloc((void**)&h->live_dev, sizeof(kLiveRows)));
     h->dev_allocs.push_back(h->live_dev);
     BPC_CUDA(h, cudaMemcpy(h->live_dev, kLiveRows, sizeof(kLiveRows), cudaMemcpyHostToDevice));
+    // Host threads (pad-row fill of the full layout, staging copies of pageable buffers): this rank's share of the
+    // cores, at most 8 -- the fill of a 4096-segment call is 0.39 GB of streaming stores, ~10 GB/s per thread.
     const char* env_t = std::getenv("BPC_HOST_THREADS");
-    int nt = env_t ? std::atoi(env_t) : 4;
     const int hw = (int)std::thread::hardware_concurrency();
-    if (hw > 0 && nt > hw) nt = hw;
-    // one process per GPU (torchrun exports LOCAL_WORLD_SIZE): leave every rank its share of the host cores
     const char* env_lws = std::getenv("LOCAL_WORLD_SIZE");
-    const int lws = env_lws ? std::atoi(env_lws) : 1;
-    if (!env_t && hw > 0 && lws > 1) nt = std::min(nt, std::max(1, hw / lws - 1));
+    const int lws = std::max(1, env_lws ? std::atoi(env_lws) : 1);
+    int nt = env_t ? std::atoi(env_t) : std::min(8, std::max(1, (hw > 0 ? hw : 8) / lws));
+    if (hw > 0 && nt > hw) nt = hw;
     if (nt < 1) nt = 1;
-    h->pool = new HostPool(nt - 1);
+    h->pool = new HostPool(nt - 1, h->numa_place ? h->numa.cpus : std::vector<int>());
     const char* env_c = std::getenv("BPC_COMPACT_D2H");
     h->compact_d2h = !(env_c && std::atoi(env_c) == 0);
+    const char* env_m = std::getenv("BPC_D2H_MODE");
+    h->contig_d2h = !(env_m && std::string(env_m) == "2d");
     const char* env_tp = std::getenv("BPC_TAPER");
     h->taper_tail = !(env_tp && std::atoi(env_tp) == 0);
     h->slots_ready = true;
@@ -661,8 +801,13 @@ int bpc_create(bpc_handle** out, const bpc_params* p, int device, int64_t max_ba
     const char* env_streams = std::getenv("BPC_STREAMS");
     h->multi_stream = !(env_streams && std::atoi(env_streams) == 0);
     for (auto& s : h->side) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-    for (cudaEvent_t* e : {&h->ev_fork, &h->ev_spec512, &h->ev_time, &h->ev_f2048, &h->ev_seg})
+    for (cudaEvent_t* e : {&h->ev_fork, &h->ev_spec512, &h->ev_time, &h->ev_f2048, &h->ev_seg, &h->ws_free})
         cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+    {
+        const char* env_numa = std::getenv("BPC_NUMA");
+        h->numa_place = !(env_numa && std::atoi(env_numa) == 0);
+        h->numa = numa_of_device(device);
+    }
     if ((rc = build_tables(h)) || (rc = build_workspace(h)) || (rc = reset_stats(h, 0))) {
         g_create_error = h->err;
         bpc_destroy(h);
@@ -684,9 +829,10 @@ void bpc_destroy(bpc_handle* h) {
     }
     delete h->pool;
     for (auto& s : h->side) if (s) cudaStreamDestroy(s);
-    for (cudaEvent_t e : {h->ev_fork, h->ev_spec512, h->ev_time, h->ev_f2048, h->ev_seg}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->ev_fork, h->ev_spec512, h->ev_time, h->ev_f2048, h->ev_seg, h->ws_free}) if (e) cudaEventDestroy(e);
     for (void* d : h->dev_allocs) cudaFree(d);
     for (void* d : h->host_allocs) cudaFreeHost(d);
+    for (auto& a : h->numa_allocs) numa_pinned_free(a.first, a.second);
     delete h;
 }
 
@@ -723,26 +869,36 @@ int bpc_precompute(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int
     return BPC_OK;
 }
 
-int bpc_precompute_host(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in, float* feats,
-                        float* scalars, int32_t* status) {
-    if (!h) return BPC_ERR_ARG;
-    if (!wav || !feats || !scalars || B < 0 || L_in <= 0 || (wav_dtype != BPC_WAV_F32 && wav_dtype != BPC_WAV_PCM16)) {
-        h->err = "bpc_precompute_host: bad argument";
-        return BPC_ERR_ARG;
-    }
+}  // extern "C"
+
+namespace {
+
+struct HostOut {                   // exactly one of the two layouts
+    float* feats;                  // full  [B, 9, 128, T]
+    float* rows;                   // compact [B, 772, T] ...
+    float* pad;                    // ... + [B, 9]
+};
+
+// The host-buffer path: a three-stage software pipeline over pieces of host_chunk segments -- H2D of piece i+1 ||
+// kernels of piece i || D2H (+ host fill, full layout only) of piece i-1 -- on three slots with their own streams.
+int host_pipeline(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in, HostOut out, float* scalars,
+                  int32_t* status) {
     BPC_CUDA(h, cudaSetDevice(h->device));
     int rc = ensure_slots(h);
     if (rc) return rc;
     const Geometry& g = h->g;
     const size_t esz = wav_dtype == BPC_WAV_F32 ? 4 : 2;
     if ((size_t)h->host_chunk * L_in * esz > h->slot_wav_bytes) { h->err = "L_in too large for the staging buffers"; return BPC_ERR_ARG; }
-    const size_t seg_feats = (size_t)9 * kPlaneRows * g.T;
-    const bool pin_in = is_pinned(wav), pin_f = is_pinned(feats), pin_s = is_pinned(scalars);
+    const int T = g.T;
+    const size_t seg_feats = (size_t)9 * kPlaneRows * T, seg_rows = (size_t)kLiveTotal * T;
+    const bool to_rows = out.rows != nullptr;
+    const bool pin_in = is_pinned(wav), pin_f = is_pinned(to_rows ? out.rows : out.feats), pin_s = is_pinned(scalars);
+    const bool pin_p = to_rows && is_pinned(out.pad);
     const std::vector<RowRun> runs = live_runs();
     double t_wait = 0.0, t_fill = 0.0;
     const auto t_call = std::chrono::steady_clock::now();
-    // Chunk schedule: full chunks, then the last <= chunk segments in halves (not below 128 segments, about one CTA wave): what is
-    // exposed at the end of a call is the D2H + host fill of the LAST piece only, so it should be small.
+    // Piece schedule: full pieces, then the last <= host_chunk segments in halves (not below 128 segments, about one CTA
+    // wave): what is exposed at the end of a call is the D2H (+ fill) of the LAST piece only, so it should be small.
     struct Piece { int64_t off; int n; };
     std::vector<Piece> sched;
     {
@@ -755,8 +911,7 @@ int bpc_precompute_host(bpc_handle* h, const void* wav, int wav_dtype, int64_t B
         }
     }
     const int64_t nchunks = (int64_t)sched.size();
-    const bool compact = h->compact_d2h;
-    const int T = g.T;
+    const bool live_only = to_rows || h->compact_d2h;        // only the 772 data rows cross PCIe
     auto wait_on = [&](cudaEvent_t ev) -> cudaError_t {
         const auto t_a = std::chrono::steady_clock::now();
         const cudaError_t e = cudaEventSynchronize(ev);
@@ -768,92 +923,128 @@ int bpc_precompute_host(bpc_handle* h, const void* wav, int wav_dtype, int64_t B
         h->pool->run(job);
         t_fill += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count();
     };
-    // Software pipeline over the pieces: iteration i enqueues piece i, writes the pad rows of piece i - 1 (needs only its
-    // nine pad values, which leave the device before the bulk rows, so this overlaps that piece's D2H and piece i's
-    // kernels) and retires piece i - 2 (bulk D2H finished).  The GPU always has the next piece queued.
-    for (int64_t i = 0; i <= nchunks + 1; ++i) {
-        if (i < nchunks) {
-            Slot& s = h->slot[i % kSlots];
-            const int64_t off = sched[i].off;
-            const int n = sched[i].n;
-            const char* src = static_cast<const char*>(wav) + (size_t)off * L_in * esz;
-            const size_t in_bytes = (size_t)n * L_in * esz;
-            if (pin_in) {
-                BPC_CUDA(h, cudaMemcpyAsync(s.d_wav, src, in_bytes, cudaMemcpyHostToDevice, s.st));
-            } else {
-                std::memcpy(s.h_wav, src, in_bytes);
-                BPC_CUDA(h, cudaMemcpyAsync(s.d_wav, s.h_wav, in_bytes, cudaMemcpyHostToDevice, s.st));
-            }
-            // H2D of this piece overlaps the previous piece's kernels; the kernels themselves are serialised because
-            // all slots use the handle's single workspace.
-            if (i >= 1) BPC_CUDA(h, cudaStreamWaitEvent(s.st, h->slot[(i - 1) % kSlots].computed, 0));
-            rc = run_chunk(h, s.d_wav, wav_dtype, L_in, n, s.d_feats, s.d_scalars, s.d_status, s.st);
-            if (rc) return rc;
-            if (compact) launch_pad_values(s.d_feats, T, n, h->live_dev, s.d_fill, s.st);
-            BPC_CUDA(h, cudaEventRecord(s.computed, s.st));
-            float* fdst = pin_f ? feats + (size_t)off * seg_feats : s.h_feats;
-            float* sdst = pin_s ? scalars + (size_t)off * g.nscal : s.h_scalars;
-            if (compact) {
-                // PCIe carries only the rows that hold data (772 of the 1152 rows of a segment); the constant pad rows
-                // are re-created on the host from one value per plane.
-                BPC_CUDA(h, cudaMemcpyAsync(s.h_fill, s.d_fill, (size_t)n * 9 * 4, cudaMemcpyDeviceToHost, s.st));
-                BPC_CUDA(h, cudaEventRecord(s.fill_ready, s.st));
-                const size_t pitch = seg_feats * 4;
-                for (const RowRun& r : runs)
-                    BPC_CUDA(h, cudaMemcpy2DAsync(fdst + (size_t)r.start * T, pitch, s.d_feats + (size_t)r.start * T,
-                                                  pitch, (size_t)(r.end - r.start) * T * 4, (size_t)n,
-                                                  cudaMemcpyDeviceToHost, s.st));
-            } else {
-                BPC_CUDA(h, cudaMemcpyAsync(fdst, s.d_feats, (size_t)n * seg_feats * 4, cudaMemcpyDeviceToHost, s.st));
-            }
-            BPC_CUDA(h, cudaMemcpyAsync(sdst, s.d_scalars, (size_t)n * g.nscal * 4, cudaMemcpyDeviceToHost, s.st));
-            BPC_CUDA(h, cudaMemcpyAsync(s.h_status, s.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, s.st));
-            BPC_CUDA(h, cudaEventRecord(s.done, s.st));
-        }
-        if (compact && i >= 1 && i - 1 < nchunks) {                   // pad rows of piece i - 1 (disjoint from the D2H rows)
-            const int64_t j = i - 1;
-            Slot& s = h->slot[j % kSlots];
-            const int n = sched[j].n;
-            float* user = feats + (size_t)sched[j].off * seg_feats;
-            BPC_CUDA(h, wait_on(s.fill_ready));
-            host_job([&](int part, int parts) {
-                for (int b = part; b < n; b += parts) {
-                    float* dst = user + (size_t)b * seg_feats;
-                    for (int c = 0; c < 9; ++c)
-                        if (kLiveRows[c] < kPlaneRows)
-                            fill_stream(dst + ((size_t)c * kPlaneRows + kLiveRows[c]) * T,
-                                        dst + (size_t)(c + 1) * kPlaneRows * T, s.h_fill[(size_t)b * 9 + c]);
+    // Iteration i enqueues piece i, writes the pad rows of piece i - 1 (full layout: needs only its nine pad values,
+    // which leave the device before the bulk rows, so this overlaps that piece's D2H and piece i's kernels) and
+    // retires piece i - 2 (bulk D2H finished).  The GPU always has the next piece queued.
+    auto body = [&]() -> int {
+        for (int64_t i = 0; i <= nchunks + 1; ++i) {
+            if (i < nchunks) {
+                Slot& s = h->slot[i % kSlots];
+                const int64_t off = sched[i].off;
+                const int n = sched[i].n;
+                const char* src = static_cast<const char*>(wav) + (size_t)off * L_in * esz;
+                const size_t in_bytes = (size_t)n * L_in * esz;
+                if (pin_in) {
+                    BPC_CUDA(h, cudaMemcpyAsync(s.d_wav, src, in_bytes, cudaMemcpyHostToDevice, s.st));
+                } else {
+                    std::memcpy(s.h_wav, src, in_bytes);
+                    BPC_CUDA(h, cudaMemcpyAsync(s.d_wav, s.h_wav, in_bytes, cudaMemcpyHostToDevice, s.st));
                 }
-#if defined(__SSE2__)
-                _mm_sfence();
-#endif
-            });
-        }
-        if (i >= 2) {                                                  // retire piece i - 2
-            const int64_t j = i - 2;
-            Slot& s = h->slot[j % kSlots];
-            const int64_t off = sched[j].off;
-            const int n = sched[j].n;
-            BPC_CUDA(h, wait_on(s.done));
-            if (!pin_f) {                                              // pageable output: staging -> user buffer
-                float* user = feats + (size_t)off * seg_feats;
+                // The H2D above overlaps the previous piece's kernels; the kernels themselves are serialised by the
+                // handle's workspace event (run_chunk), because all slots share the one workspace.
+                int rc2 = run_chunk(h, s.d_wav, wav_dtype, L_in, n, s.d_feats, s.d_scalars, s.d_status, s.st);
+                if (rc2) return rc2;
+                float* sdst = pin_s ? scalars + (size_t)off * g.nscal : s.h_scalars;
+                if (to_rows) {
+                    launch_pad_values(s.d_feats, T, n, h->live_dev, s.d_fill, s.st);
+                    float* pdst = pin_p ? out.pad + (size_t)off * 9 : s.h_fill;
+                    float* rdst = pin_f ? out.rows + (size_t)off * seg_rows : s.h_feats;
+                    BPC_CUDA(h, cudaMemcpyAsync(pdst, s.d_fill, (size_t)n * 9 * 4, cudaMemcpyDeviceToHost, s.st));
+                    if (h->contig_d2h) {
+                        launch_compact_rows(s.d_feats, T, n, kLiveRows, s.d_rows, s.st);
+                        BPC_CUDA(h, cudaMemcpyAsync(rdst, s.d_rows, (size_t)n * seg_rows * 4, cudaMemcpyDeviceToHost, s.st));
+                    } else {
+                        size_t row0 = 0;                               // first compact row of the run
+                        for (const RowRun& r : runs) {
+                            BPC_CUDA(h, cudaMemcpy2DAsync(rdst + row0 * T, seg_rows * 4, s.d_feats + (size_t)r.start * T,
+                                                          seg_feats * 4, (size_t)(r.end - r.start) * T * 4, (size_t)n,
+                                                          cudaMemcpyDeviceToHost, s.st));
+                            row0 += (size_t)(r.end - r.start);
+                        }
+                    }
+                } else {
+                    float* fdst = pin_f ? out.feats + (size_t)off * seg_feats : s.h_feats;
+                    if (live_only) {
+                        // PCIe carries only the rows that hold data (772 of the 1152 rows of a segment); the constant
+                        // pad rows are re-created on the host from one value per plane.
+                        launch_pad_values(s.d_feats, T, n, h->live_dev, s.d_fill, s.st);
+                        BPC_CUDA(h, cudaMemcpyAsync(s.h_fill, s.d_fill, (size_t)n * 9 * 4, cudaMemcpyDeviceToHost, s.st));
+                        BPC_CUDA(h, cudaEventRecord(s.fill_ready, s.st));
+                        const size_t pitch = seg_feats * 4;
+                        for (const RowRun& r : runs)
+                            BPC_CUDA(h, cudaMemcpy2DAsync(fdst + (size_t)r.start * T, pitch, s.d_feats + (size_t)r.start * T,
+                                                          pitch, (size_t)(r.end - r.start) * T * 4, (size_t)n,
+                                                          cudaMemcpyDeviceToHost, s.st));
+                    } else {
+                        BPC_CUDA(h, cudaMemcpyAsync(fdst, s.d_feats, (size_t)n * seg_feats * 4, cudaMemcpyDeviceToHost, s.st));
+                    }
+                }
+                BPC_CUDA(h, cudaMemcpyAsync(sdst, s.d_scalars, (size_t)n * g.nscal * 4, cudaMemcpyDeviceToHost, s.st));
+                BPC_CUDA(h, cudaMemcpyAsync(s.h_status, s.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, s.st));
+                BPC_CUDA(h, cudaEventRecord(s.done, s.st));
+            }
+            if (!to_rows && live_only && i >= 1 && i - 1 < nchunks) {     // pad rows of piece i - 1 (disjoint from the D2H rows)
+                const int64_t j = i - 1;
+                Slot& s = h->slot[j % kSlots];
+                const int n = sched[j].n;
+                float* user = out.feats + (size_t)sched[j].off * seg_feats;
+                BPC_CUDA(h, wait_on(s.fill_ready));
                 host_job([&](int part, int parts) {
                     for (int b = part; b < n; b += parts) {
                         float* dst = user + (size_t)b * seg_feats;
-                        const float* src = s.h_feats + (size_t)b * seg_feats;
-                        if (compact) {
-                            for (const RowRun& r : runs)
-                                std::memcpy(dst + (size_t)r.start * T, src + (size_t)r.start * T,
-                                            (size_t)(r.end - r.start) * T * 4);
-                        } else {
-                            std::memcpy(dst, src, seg_feats * 4);
-                        }
+                        for (int c = 0; c < 9; ++c)
+                            if (kLiveRows[c] < kPlaneRows)
+                                fill_stream(dst + ((size_t)c * kPlaneRows + kLiveRows[c]) * T,
+                                            dst + (size_t)(c + 1) * kPlaneRows * T, s.h_fill[(size_t)b * 9 + c]);
                     }
+#if defined(__SSE2__)
+                    _mm_sfence();
+#endif
                 });
             }
-            if (!pin_s) std::memcpy(scalars + (size_t)off * g.nscal, s.h_scalars, (size_t)n * g.nscal * 4);
-            if (status) std::memcpy(status + off, s.h_status, (size_t)n * 4);
+            if (i >= 2) {                                                  // retire piece i - 2
+                const int64_t j = i - 2;
+                Slot& s = h->slot[j % kSlots];
+                const int64_t off = sched[j].off;
+                const int n = sched[j].n;
+                BPC_CUDA(h, wait_on(s.done));
+                if (!pin_f) {                                              // pageable output: staging -> user buffer
+                    if (to_rows) {
+                        float* user = out.rows + (size_t)off * seg_rows;
+                        host_job([&](int part, int parts) {
+                            for (int b = part; b < n; b += parts)
+                                std::memcpy(user + (size_t)b * seg_rows, s.h_feats + (size_t)b * seg_rows, seg_rows * 4);
+                        });
+                    } else {
+                        float* user = out.feats + (size_t)off * seg_feats;
+                        host_job([&](int part, int parts) {
+                            for (int b = part; b < n; b += parts) {
+                                float* dst = user + (size_t)b * seg_feats;
+                                const float* src = s.h_feats + (size_t)b * seg_feats;
+                                if (live_only) {
+                                    for (const RowRun& r : runs)
+                                        std::memcpy(dst + (size_t)r.start * T, src + (size_t)r.start * T,
+                                                    (size_t)(r.end - r.start) * T * 4);
+                                } else {
+                                    std::memcpy(dst, src, seg_feats * 4);
+                                }
+                            }
+                        });
+                    }
+                }
+                if (to_rows && !pin_p) std::memcpy(out.pad + (size_t)off * 9, s.h_fill, (size_t)n * 9 * 4);
+                if (!pin_s) std::memcpy(scalars + (size_t)off * g.nscal, s.h_scalars, (size_t)n * g.nscal * 4);
+                if (status) std::memcpy(status + off, s.h_status, (size_t)n * 4);
+            }
         }
+        return BPC_OK;
+    };
+    rc = body();
+    if (rc) {
+        // copies into the caller's buffers may still be in flight: let them land before the error is reported
+        for (int i = 0; i < kSlots; ++i) cudaStreamSynchronize(h->slot[i].st);
+        cudaGetLastError();
+        return rc;
     }
     if (std::getenv("BPC_HOST_TRACE")) {
         int ncpu = -1;
@@ -861,12 +1052,86 @@ int bpc_precompute_host(bpc_handle* h, const void* wav, int wav_dtype, int64_t B
         cpu_set_t set;
         if (sched_getaffinity(0, sizeof(set), &set) == 0) ncpu = CPU_COUNT(&set);
 #endif
-        std::fprintf(stderr, "[bpc host] B=%lld chunks=%lld total %.2f ms, waiting on GPU/PCIe %.2f ms, host copy/fill %.2f ms (%d threads, %d cpus in the affinity mask)\n",
-                     (long long)B, (long long)nchunks,
+        std::fprintf(stderr, "[bpc host] B=%lld pieces=%lld layout=%s total %.2f ms, waiting on GPU/PCIe %.2f ms, host copy/fill %.2f ms "
+                     "(%d threads, %d cpus in the affinity mask, GPU numa node %d with %d local cpus, placement %s)\n",
+                     (long long)B, (long long)nchunks, to_rows ? (h->contig_d2h ? "compact/contiguous" : "compact/2d") : "full",
                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(), t_wait,
-                     t_fill, h->pool->size(), ncpu);
+                     t_fill, h->pool->size(), ncpu, h->numa.node, (int)h->numa.cpus.size(), h->numa_place ? "on" : "off");
     }
     return BPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bpc_precompute_host(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in, float* feats,
+                        float* scalars, int32_t* status) {
+    if (!h) return BPC_ERR_ARG;
+    if (!wav || !feats || !scalars || B < 0 || L_in <= 0 || (wav_dtype != BPC_WAV_F32 && wav_dtype != BPC_WAV_PCM16)) {
+        h->err = "bpc_precompute_host: bad argument";
+        return BPC_ERR_ARG;
+    }
+    return host_pipeline(h, wav, wav_dtype, B, L_in, HostOut{feats, nullptr, nullptr}, scalars, status);
+}
+
+int bpc_precompute_host_compact(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in, float* rows,
+                                float* pad, float* scalars, int32_t* status) {
+    if (!h) return BPC_ERR_ARG;
+    if (!wav || !rows || !pad || !scalars || B < 0 || L_in <= 0 ||
+        (wav_dtype != BPC_WAV_F32 && wav_dtype != BPC_WAV_PCM16)) {
+        h->err = "bpc_precompute_host_compact: bad argument";
+        return BPC_ERR_ARG;
+    }
+    return host_pipeline(h, wav, wav_dtype, B, L_in, HostOut{nullptr, rows, pad}, scalars, status);
+}
+
+int bpc_live_rows(int channel) { return (channel >= 0 && channel < 9) ? kLiveRows[channel] : BPC_ERR_ARG; }
+
+int bpc_expand_compact(const float* rows, const float* pad, int64_t n, int T, float* feats, int n_threads) {
+    if (!rows || !pad || !feats || n < 0 || T <= 0) return BPC_ERR_ARG;
+    const size_t seg_feats = (size_t)9 * kPlaneRows * T, seg_rows = (size_t)kLiveTotal * T;
+    int nt = std::max(1, std::min(n_threads, 64));
+    if ((int64_t)nt > n) nt = (int)std::max<int64_t>(1, n);
+    auto work = [&](int part) {
+        for (int64_t b = part; b < n; b += nt) {
+            const float* src = rows + (size_t)b * seg_rows;
+            float* dst = feats + (size_t)b * seg_feats;
+            for (int c = 0; c < 9; ++c) {
+                const size_t live = (size_t)kLiveRows[c] * T;
+                std::memcpy(dst, src, live * 4);
+                const float v = pad[(size_t)b * 9 + c];
+                for (float* q = dst + live; q < dst + (size_t)kPlaneRows * T; ++q) *q = v;
+                src += live;
+                dst += (size_t)kPlaneRows * T;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+    return BPC_OK;
+}
+
+void* bpc_host_alloc(bpc_handle* h, int64_t bytes, int* numa_node) {
+    if (!h || bytes <= 0) return nullptr;
+    if (cudaSetDevice(h->device) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    void* p = nullptr;
+    if (host_pinned(h, (size_t)bytes, &p)) return nullptr;
+    if (numa_node) *numa_node = h->numa_place ? h->numa.node : -1;
+    return p;
+}
+
+void bpc_host_free(bpc_handle* h, void* p) {
+    if (!h || !p) return;
+    for (auto it = h->numa_allocs.begin(); it != h->numa_allocs.end(); ++it)
+        if (it->first == p) {
+            cudaSetDevice(h->device);
+            numa_pinned_free(it->first, it->second);
+            h->numa_allocs.erase(it);
+            return;
+        }
 }
 
 int bpc_stage_logmel(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in, float* stft_db,
@@ -1022,6 +1287,47 @@ int64_t bpc_table_copy(const bpc_params* p, const char* name, int tuning_idx, vo
         return put_f(flat);
     }
     return BPC_ERR_ARG;
+}
+
+int64_t bpc_resample_len(int64_t n_in, int sr_in, int sr_out) {
+    if (n_in < 0 || sr_in <= 0 || sr_out <= 0) return BPC_ERR_ARG;
+    return (n_in * (int64_t)sr_out + sr_in - 1) / sr_in;
+}
+
+int64_t bpc_resample_filter(int sr_in, int sr_out, double* out, int64_t cap, int* p, int* q, int* half) {
+    if (sr_in <= 0 || sr_out <= 0 || !out) return BPC_ERR_ARG;
+    const ResampleFilter f = resample_filter(sr_in, sr_out);
+    if ((int64_t)f.tab.size() > cap) return BPC_ERR_ARG;
+    std::memcpy(out, f.tab.data(), f.tab.size() * sizeof(double));
+    if (p) *p = f.p;
+    if (q) *q = f.q;
+    if (half) *half = f.half;
+    return (int64_t)f.tab.size();
+}
+
+int bpc_resample(bpc_handle* h, const float* in, int64_t n_in, int sr_in, int sr_out, float* out, int64_t out_cap,
+                 void* stream) {
+    if (!h) return BPC_ERR_ARG;
+    const int64_t n_out = bpc_resample_len(n_in, sr_in, sr_out);
+    if (!in || !out || n_out < 0 || out_cap < n_out || sr_in > 768000 || sr_out > 768000) {
+        h->err = "bpc_resample: bad argument";
+        return BPC_ERR_ARG;
+    }
+    BPC_CUDA(h, cudaSetDevice(h->device));
+    const bpc_handle::Resampler* r = nullptr;
+    for (const auto& e : h->resamplers) if (e.sr_in == sr_in && e.sr_out == sr_out) r = &e;
+    if (!r) {
+        const ResampleFilter f = resample_filter(sr_in, sr_out);
+        if (f.tab.size() > (size_t)64 << 20) { h->err = "bpc_resample: rate pair needs too large a polyphase table"; return BPC_ERR_UNSUPPORTED; }
+        const double* d = nullptr;
+        int rc = upload(h, f.tab, &d);
+        if (rc) return rc;
+        h->resamplers.push_back({sr_in, sr_out, f.p, f.q, f.half, d});
+        r = &h->resamplers.back();
+    }
+    launch_resample(in, n_in, r->tab, r->p, r->q, r->half, out, n_out, static_cast<cudaStream_t>(stream));
+    BPC_CUDA(h, cudaGetLastError());
+    return BPC_OK;
 }
 
 int64_t bpc_launch_count(const bpc_handle* h) { return h ? launches_issued() - h->launches0 : 0; }

@@ -3,8 +3,25 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cfloat>
+#include <mutex>
 
 namespace bpc {
+
+// Function attributes (the opt-in dynamic shared-memory size) are per DEVICE: a launcher runs its attribute block once
+// per device it is used on, under a lock (handles on different devices may be driven from different host threads).
+struct PerDeviceOnce {
+    std::mutex m;
+    unsigned long long mask = 0;
+    template <class F> void run(F&& f) {
+        int d = 0;
+        cudaGetDevice(&d);
+        std::lock_guard<std::mutex> l(m);
+        if ((mask >> (d & 63)) & 1ull) return;
+        f();
+        mask |= 1ull << (d & 63);
+    }
+};
+
 
 constexpr int kPlaneRows = 128;
 constexpr int kMagStride = 260;          // |STFT512| workspace row stride (257 valid bins, 16-byte aligned rows)

@@ -96,4 +96,36 @@ void launch_pad_values(const float* feats, int T, int n, const int* live_dev, fl
     note_launch();
 }
 
+// Compact copy of a chunk for the host path: out[b] = the 772 data rows of segment b back to back (chroma 24, gammatone
+// 64, lpc 12, mel / mel_delta / mel_delta2 128 each, mfcc 120, mod_spec 40, tempogram 128 -- every count a multiple of
+// four rows, so float4 granules never straddle a plane), so that ONE contiguous device->host copy per piece carries
+// exactly the bytes that have to cross PCIe.  772 T * 4 B read + written per segment (0.39 MB at T = 63).
+struct LiveLayout { int start4[10]; };          // prefix sums of live rows * T / 4 (float4 granules), 9 planes + total
+
+__global__ void __launch_bounds__(256) k_compact_rows(const float4* __restrict__ feats, int plane4, LiveLayout lay,
+                                                      float4* __restrict__ out) {
+    const int b = blockIdx.y, total4 = lay.start4[9];
+    const float4* src = feats + (size_t)b * 9 * plane4;
+    float4* dst = out + (size_t)b * total4;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < total4; v += gridDim.x * blockDim.x) {
+        int c = 0;
+#pragma unroll
+        for (int q = 1; q < 9; ++q) c += v >= lay.start4[q];
+        __stcs(dst + v, __ldcs(src + (size_t)c * plane4 + (v - lay.start4[c])));
+    }
+}
+
+void launch_compact_rows(const float* feats, int T, int n, const int* live_host, float* out, cudaStream_t st) {
+    LiveLayout lay;
+    lay.start4[0] = 0;
+    for (int c = 0; c < 9; ++c) lay.start4[c + 1] = lay.start4[c] + live_host[c] * T / 4;
+    int bx = (148 * 8 * 2 + n - 1) / n;
+    const int bx_max = (lay.start4[9] + 255) / 256;
+    if (bx > bx_max) bx = bx_max;
+    if (bx < 1) bx = 1;
+    k_compact_rows<<<dim3(bx, n), 256, 0, st>>>(reinterpret_cast<const float4*>(feats), kPlaneRows * T / 4, lay,
+                                               reinterpret_cast<float4*>(out));
+    note_launch();
+}
+
 }  // namespace bpc

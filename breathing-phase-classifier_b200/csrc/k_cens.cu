@@ -378,13 +378,12 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
 
 void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
                  cudaStream_t st) {
-    static bool done = false;
-    if (!done) {
+    static PerDeviceOnce once;
+    once.run([&] {
         cudaFuncSetAttribute(k_cens_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
         cudaFuncSetAttribute(k_cens<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CensSmem));
         cudaFuncSetAttribute(k_cens<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CensSmem));
-        done = true;
-    }
+    });
     if (g.long_mode) {
         const int L = g.L;
         for (int o = 1; o <= 6; ++o) {

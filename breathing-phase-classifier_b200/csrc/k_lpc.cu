@@ -159,12 +159,11 @@ __global__ void __launch_bounds__(kLpcThreads, 5) k_lpc(const float* __restrict_
 
 void launch_lpc(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
                 cudaStream_t st) {
-    static bool done = false;
-    if (!done) {
+    static PerDeviceOnce once;
+    once.run([&] {
         cudaFuncSetAttribute(k_lpc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpcSmem));
         cudaFuncSetAttribute(k_lpc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpcSmem));
-        done = true;
-    }
+    });
     if (g.long_mode) {
         k_lpc<true><<<dim3(n, 16), kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats, 1);
         k_lpc<true><<<dim3(n, 1), kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats, 2);

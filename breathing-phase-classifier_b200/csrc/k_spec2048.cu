@@ -622,17 +622,16 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
 // ==================================================================================================== launchers
 void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
                      float* scalars, cudaStream_t st) {
-    static bool done = false;
+    static PerDeviceOnce once;
     static int sms = 148;
-    if (!done) {
+    once.run([&] {
         cudaFuncSetAttribute(k_frame2048, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2Warps * kF2RowBytes);
         cudaFuncSetAttribute(k_seg2048<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Seg2048Smem));
         cudaFuncSetAttribute(k_seg2048<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Seg2048Smem));
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        done = true;
-    }
+    });
     const int total = n * g.T;
     // persistent: exactly the 3 CTAs per SM that fit (168 registers, 67.6 KB), each warp strides over the frames
     int grid = (total + kF2Warps - 1) / kF2Warps;
@@ -656,12 +655,11 @@ void launch_seg2048(int n, const Geometry& g, const Tables& tb, const Workspace&
 
 void launch_even2048(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* scalars,
                      int32_t* status, cudaStream_t st) {
-    static bool done = false;
-    if (!done) {
+    static PerDeviceOnce once;
+    once.run([&] {
         cudaFuncSetAttribute(k_even2048<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Even2048Smem));
         cudaFuncSetAttribute(k_even2048<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Even2048Smem));
-        done = true;
-    }
+    });
     if (g.long_mode) k_even2048<true><<<n, 256, sizeof(Even2048Smem), st>>>(g, tb, ws, scalars, status);
     else k_even2048<false><<<n, 256, sizeof(Even2048Smem), st>>>(g, tb, ws, scalars, status);
     note_launch();

@@ -642,12 +642,11 @@ __global__ void __launch_bounds__(256, 4) k_spec512_light(Geometry g, Tables tb,
 }
 
 static void set_consumer_smem() {
-    static bool done = false;
-    if (!done) {
+    static PerDeviceOnce once;
+    once.run([&] {
         cudaFuncSetAttribute(k_spec512_consumers<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kConsumerSmemFloats * (int)sizeof(float));
-        done = true;
-    }
+    });
 }
 
 void launch_spec512_consumers(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
@@ -742,11 +741,10 @@ void launch_stft_db(int n, const Geometry& g, const Workspace& ws, float* stft_d
         return;
     }
     const int bytes = 257 * g.T * (int)sizeof(float);
-    static bool done = false;
-    if (!done) {
+    static PerDeviceOnce once;
+    once.run([&] {
         cudaFuncSetAttribute(k_stft_db, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * kMaxFrames * 4);
-        done = true;
-    }
+    });
     k_stft_db<<<n, 256, bytes, st>>>(g, ws.mag512, stft_db);
     note_launch();
 }
@@ -797,12 +795,11 @@ void launch_modspec(int n, const Geometry& g, const Tables& tb, const Workspace&
         return;
     }
     set_consumer_smem();
-    static bool done = false;
-    if (!done) {
+    static PerDeviceOnce once;
+    once.run([&] {
         cudaFuncSetAttribute(k_modspec, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kConsumerSmemFloats * (int)sizeof(float));
-        done = true;
-    }
+    });
     k_modspec<<<n, 256, kConsumerSmemFloats * sizeof(float), st>>>(g, tb, mel_db, out);
     note_launch();
 }

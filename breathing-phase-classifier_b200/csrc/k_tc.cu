@@ -272,16 +272,15 @@ bool modspec_time_tc_enabled(const Tables& tb) {
 
 void launch_modspec_time_tc(int n, const Geometry& g, const Tables& tb, const Workspace& ws, size_t role0_off,
                             cudaStream_t st) {
-    static bool done = false;
+    static PerDeviceOnce once;
     static int mode = 2;                                          // BPC_TC_DCT: 2 = pipelined (default), 1 = single stage
     const int bytes1 = 4 * kTcOpFloats * (int)sizeof(uint32_t), bytes2 = kTcStages * kTcStageFloats * (int)sizeof(uint32_t);
-    if (!done) {
+    once.run([&] {
         cudaFuncSetAttribute(k_modspec_time_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes1);
         cudaFuncSetAttribute(k_modspec_time_tc_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes2);
         const char* env = std::getenv("BPC_TC_DCT");
         if (env && std::atoi(env) == 1) mode = 1;
-        done = true;
-    }
+    });
     const int KB = (g.T + kTcK - 1) / kTcK, MT = (n * 40 + kTcM - 1) / kTcM, NT = (g.T + kTcN - 1) / kTcN;
     if (mode == 1 || !ws.tc_a || !tb.dct_tiles) {
         k_modspec_time_tc<<<dim3(NT, MT), 128, bytes1, st>>>(g, tb, ws, n, role0_off);

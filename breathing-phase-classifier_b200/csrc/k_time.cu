@@ -777,13 +777,12 @@ __global__ void __launch_bounds__(kHilbertLongThreads) k_hilbert_long(const floa
 // ==================================================================================================== launchers
 void launch_time_scalars(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws,
                          float* scalars, int32_t* status, cudaStream_t st) {
-    static bool done = false;
-    if (!done) {
+    static PerDeviceOnce once;
+    once.run([&] {
         cudaFuncSetAttribute(k_time_basic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TimeBasicSmem));
         cudaFuncSetAttribute(k_time_basic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TimeBasicSmem));
         cudaFuncSetAttribute(k_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AutocorrSmem));
-        done = true;
-    }
+    });
     if (g.long_mode) k_time_basic<true><<<n, kTimeBasicThreads, sizeof(TimeBasicSmem), st>>>(y, g, ws, scalars, status);
     else k_time_basic<false><<<n, kTimeBasicThreads, sizeof(TimeBasicSmem), st>>>(y, g, ws, scalars, status);
     k_autocorr<<<n, kAcThreads, sizeof(AutocorrSmem), st>>>(y, g, tb, ws.ints, scalars);
@@ -804,11 +803,10 @@ void launch_hilbert(const float* y, int n, const Geometry& g, const Tables& tb, 
         return;
     }
     const int bytes = (int)(kHilbertXBytes + sizeof(unsigned short) * 16000 + sizeof(HilbertTail));
-    static bool done = false;
-    if (!done) {
+    static PerDeviceOnce once;
+    once.run([&] {
         cudaFuncSetAttribute(k_hilbert, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        done = true;
-    }
+    });
     k_hilbert<<<n, kHilbertThreads, bytes, st>>>(y, g, tb, ws, scalars);
     note_launch();
 }

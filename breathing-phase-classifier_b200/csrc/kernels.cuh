@@ -125,6 +125,7 @@ void launch_collate(const float* store_feats, const float* store_scalars, const 
                     float* out_feats, float* out_scalars, cudaStream_t st);
 
 void launch_pad_values(const float* feats, int T, int n, const int* live_dev, float* fill, cudaStream_t st);
+void launch_compact_rows(const float* feats, int T, int n, const int* live_host, float* out, cudaStream_t st);
 
 size_t consumer_scratch_floats(int T);
 bool modspec_time_tc_enabled(const Tables& tb);
@@ -132,6 +133,9 @@ size_t tc_tile_words(int rows, int T);
 void launch_tc_prep_b(const Geometry& g, const Tables& tb, uint32_t* out, cudaStream_t st);
 void launch_modspec_time_tc(int n, const Geometry& g, const Tables& tb, const Workspace& ws, size_t role0_off,
                             cudaStream_t st);
+
+void launch_resample(const float* x, long long n_in, const double* tab, int p, int q, int half, float* out,
+                     long long n_out, cudaStream_t st);
 
 void upload_cens_constants(const double* taps127);
 int cens_dec_floats_per_segment(int L);

@@ -161,6 +161,41 @@ std::vector<double> halfband_taps(int numtaps, double atten_db) {
     return h;
 }
 
+// ---- sample-rate converter (oracle/resample.py): Kaiser-windowed sinc, 150 dB, transition band [0.9125, 1] of the
+// lower of the two Nyquist rates (soxr HQ's pass band), as a polyphase table.
+ResampleFilter resample_filter(int sr_in, int sr_out) {
+    ResampleFilter f;
+    if (sr_in <= 0 || sr_out <= 0) return f;
+    int a = sr_in, b = sr_out;
+    while (b) { const int t = a % b; a = b; b = t; }
+    f.p = sr_out / a;
+    f.q = sr_in / a;
+    const double r = std::min(1.0, double(f.p) / double(f.q));
+    const double fc = 0.5 * 0.95625 * r;                            // cut-off in cycles per input sample
+    const double delta = 0.5 * 0.0875 * r;                          // transition width
+    const double atten = 150.0, beta = 0.1102 * (atten - 8.7);
+    const int ntaps = (int)std::ceil((atten - 7.95) / (14.36 * delta));
+    f.half = (ntaps + 1) / 2;
+    const double i0b = bessel_i0(beta);
+    f.tab.assign((size_t)f.p * 2 * f.half, 0.0);
+    for (int ph = 0; ph < f.p; ++ph) {
+        double* row = f.tab.data() + (size_t)ph * 2 * f.half;
+        double s = 0.0;
+        for (int j = 0; j < 2 * f.half; ++j) {
+            const double u = double(ph) / double(f.p) + double(f.half - 1 - j);
+            const double xr = u / double(f.half);
+            double w = 0.0;
+            if (std::fabs(xr) <= 1.0) w = bessel_i0(beta * std::sqrt(std::max(0.0, 1.0 - xr * xr))) / i0b;
+            const double z = 2.0 * fc * u;
+            const double sinc = (z == 0.0) ? 1.0 : std::sin(kPi * z) / (kPi * z);
+            row[j] = 2.0 * fc * sinc * w;
+            s += row[j];
+        }
+        for (int j = 0; j < 2 * f.half; ++j) row[j] /= s;
+    }
+    return f;
+}
+
 void fft_inplace(std::vector<std::complex<double>>& a) {
     const size_t n = a.size();
     for (size_t i = 1, j = 0; i < n; ++i) {

@@ -41,4 +41,11 @@ std::vector<double> halfband_taps(int numtaps = kHalfbandTaps, double atten_db =
 CqtBasisEll cqt_basis(int sr, double tuning, std::vector<std::complex<float>>* dense_out = nullptr);
 void fft_inplace(std::vector<std::complex<double>>& a);      // radix-2, power-of-two length, forward
 
+// Polyphase table of the sample-rate converter (oracle/resample.py::polyphase_table): p phases x 2 half taps.
+struct ResampleFilter {
+    int p = 0, q = 0, half = 0;      // sr_out / sr_in = p / q in lowest terms; taps span (-half, half] input samples
+    std::vector<double> tab;         // [p, 2 half]: tab[f][j] = h(f / p + half - 1 - j), every phase scaled to unit DC gain
+};
+ResampleFilter resample_filter(int sr_in, int sr_out);
+
 }  // namespace bpc

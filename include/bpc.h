@@ -49,8 +49,9 @@ enum bpc_status {
     BPC_ERR_ARG = -1,          /* bad argument / unsupported parameter combination */
     BPC_ERR_CUDA = -2,         /* CUDA runtime error (message has the cudaError string) */
     BPC_ERR_ALLOC = -3,
-    BPC_ERR_UNSUPPORTED = -4,  /* not sm_100, other constants than the reference's, expected_len not 16000 * 2^a 3^b 5^c */
-    BPC_ERR_NCCL = -5
+    BPC_ERR_UNSUPPORTED = -4   /* not sm_100, other constants than the reference's, expected_len not 16000 * 2^a 3^b 5^c */
+    /* -5 is retired: the path's one collective (the all-gather of the 1.8 KB statistics accumulator) is issued by the
+       host through torch.distributed on the pointer bpc_channel_stats_device returns, not by this library */
 };
 
 /* per-segment status bits */
@@ -101,6 +102,28 @@ int  bpc_precompute(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, in
 int  bpc_precompute_host(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in,
                          float* feats, float* scalars, int32_t* status);
 
+/* Compact host layout (what actually crosses PCIe).  pad_freq (methods.py:39-46) fills rows live..127 of a plane with
+ * ONE constant, so of the 9 * 128 = 1152 rows of a segment only BPC_LIVE_ROWS = 772 carry data:
+ *   chroma 24 (process.py:54-57), gammatone 64, lpc 12, mel / mel_delta / mel_delta2 128 each, mfcc 120, mod_spec 40,
+ *   tempogram 128 -- bpc_live_rows(channel).
+ * rows: [B, 772, T] float32, the data rows of the nine planes back to back in channel order; pad: [B, 9] float32, the
+ * constant of every plane's remaining rows (0 for planes without pad rows).  67 % of the bytes of the full tensor and
+ * no host-side fill: ONE contiguous device->host copy per internal piece.  bpc_expand_compact rebuilds the full
+ * [n, 9, 128, T] tensor on the host (n_threads host threads; bit-identical to bpc_precompute_host's output) for
+ * consumers that want it (the .npz writer); the packed shard and its Dataset keep the compact form. */
+#define BPC_LIVE_ROWS 772
+int  bpc_live_rows(int channel);
+int  bpc_precompute_host_compact(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in,
+                                 float* rows, float* pad, float* scalars, int32_t* status);
+int  bpc_expand_compact(const float* rows, const float* pad, int64_t n, int T, float* feats, int n_threads);
+
+/* Pinned host memory placed on the NUMA node the handle's GPU hangs off (sysfs numa_node of its PCI address; mbind +
+ * first touch from a thread bound to that node's CPUs, then cudaHostRegister).  Buffers passed to bpc_precompute_host*
+ * need not come from here, but on multi-socket boxes device<->host copies into remote-node memory run at a fraction
+ * of the PCIe rate.  *numa_node receives the node used (-1: unknown / single node).  Free with bpc_host_free. */
+void* bpc_host_alloc(bpc_handle* h, int64_t bytes, int* numa_node);
+void  bpc_host_free(bpc_handle* h, void* p);
+
 /* BASELINE config 2 stage: log-power STFT (power_to_db(|X|^2, ref=max), [B, 1+n_fft/2, T], may be NULL) and the
  * normalised mel / mel_delta / mel_delta2 planes ([B, 3, 128, T]).  Device buffers. */
 int  bpc_stage_logmel(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in,
@@ -113,7 +136,8 @@ int  bpc_modspec(bpc_handle* h, const float* mel_db, int64_t n, float* out, void
 /* Dataset-level statistics accumulated over every bpc_precompute* call since the last reset:
  * stats[(9 + nscal)][5] doubles = {count, sum, sum of squares, min, max}, first the 9 channels (sorted order, over all
  * 128*T values of each plane), then each scalar.  Host output.  bpc_channel_stats_device returns the device pointer
- * of the same accumulator so a caller can all-reduce it (NCCL sum over cols 0-2, min col 3, max col 4). */
+ * of the same accumulator so a caller can reduce it across ranks (one all-gather of the 1.8 KB, then sum over cols 0-2,
+ * min col 3, max col 4: bpc_b200/stats.py). */
 int  bpc_channel_stats(bpc_handle* h, double* stats_host);
 int  bpc_channel_stats_device(bpc_handle* h, double** stats_dev, int64_t* n_rows);
 int  bpc_channel_stats_reset(bpc_handle* h);
@@ -172,6 +196,19 @@ int  bpc_npz_write_batch(const char* target_dir, const char* const* file_ids, co
 enum bpc_wav_code { BPC_WAV_ERR_OPEN = -10, BPC_WAV_ERR_FORMAT = -11, BPC_WAV_ERR_UNSUPPORTED = -12 };
 int  bpc_wav_load_batch(const char* const* paths, int64_t n, int expected_sr, int64_t L, int16_t* out,
                         int32_t* sr, int32_t* frames, int32_t* code, int n_threads);
+
+/* ---- sample-rate conversion on load ---------------------------------------------------------------
+ * process.py:28 `librosa.load(wav_path, sr=SR)` resamples files of any other rate with libsoxr "HQ", an un-vendored
+ * dependency that cannot be restated bit for bit.  Stand-in (the same disclosure as the CQT's half-band decimator):
+ * a 150 dB Kaiser-windowed sinc with soxr HQ's pass band (flat to 0.9125 of the lower Nyquist), evaluated as a
+ * polyphase filter in FP64 on the device; oracle/resample.py is its CPU counterpart.
+ * bpc_resample_len: ceil(n_in * sr_out / sr_in) (librosa.resample's output length).
+ * bpc_resample: device buffers, in [n_in] float32 -> out [bpc_resample_len] float32 (out_cap elements available).
+ * bpc_resample_filter (host only, no GPU): the polyphase table [p, 2 half] as doubles; returns the element count. */
+int64_t bpc_resample_len(int64_t n_in, int sr_in, int sr_out);
+int  bpc_resample(bpc_handle* h, const float* in, int64_t n_in, int sr_in, int sr_out, float* out, int64_t out_cap,
+                  void* stream);
+int64_t bpc_resample_filter(int sr_in, int sr_out, double* out, int64_t cap, int* p, int* q, int* half);
 
 /* Segments processed per internal chunk (= per kernel launch; default min(4144, max_batch) for 1 s segments); env
  * BPC_CHUNK overrides the default at create time. */

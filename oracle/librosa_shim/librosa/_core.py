@@ -33,7 +33,9 @@ def load(path, *, sr=22050, mono=True, offset=0.0, duration=None, dtype=np.float
         if mono:
             y = np.mean(y, axis=0)
     if sr is not None and native_sr != sr:
-        raise NotImplementedError("oracle shim: resampling on load needs libsoxr (all fixtures are 16 kHz)")
+        # libsoxr "HQ" is not available: the shared Kaiser stand-in of oracle/resample.py (parity unpinned for this stage)
+        from oracle.resample import resample as _resample_on_load
+        y = _resample_on_load(np.asarray(y, dtype=np.float32), int(native_sr), int(sr))
     return np.asarray(y, dtype=dtype), (sr if sr is not None else native_sr)
 
 

@@ -3,10 +3,13 @@ vectors.  Tolerances (BASELINE.json north_star): bit-exact integer outputs (peak
 index), atol 1e-3 dB on log spectra, rtol 1e-4 on float scalars.
 
 Notes on the stated budgets
-  * MFCC / mod_spec are DCTs of dB spectra (sums of 128 dB values with gain up to ~11): their budget is 1e-3 dB scaled
-    by that gain, and values are O(700) where one float32 ulp is 6e-5.
-  * scalars that are differences of near-cancelling terms (skew, autocorrelation ratios near 0) get an absolute floor of
-    2e-6, the reference's own float32 noise for those quantities.
+  * MFCC / mod_spec are DCTs of dB spectra (sums of 128 dB values with gain up to ~11, mod_spec a second DCT over
+    time): their budget is 1e-3 dB scaled by that gain (1.1e-2 / 9e-2), and values are O(700) / O(5000) where one
+    float32 ulp is 6e-5 / 5e-4.  The gates are 2x the measured deviations (2.4e-4 / 2.0e-3), far inside that budget.
+  * every scalar, on every set, must satisfy |d| <= 1e-4 |ref| + 2e-6.  The 2e-6 floor only matters for the five
+    near-cancelling quantities (skew of the centroid [10], skew / kurtosis of y [29, 30], autocorrelation ratios
+    [33, 34]): the reference evaluates them in float32 and is itself only good to 5.7e-5 relative / 4.8e-7 absolute there
+    (tools/scalar_noise.py).  The other 31 are additionally held to a pure rtol of 1e-4.
   * chroma depends on librosa's data-dependent tuning estimate (a histogram arg-max): element-wise parity is asserted
     on the segments whose tuning bin agrees, and the agreement rate is asserted separately.
 """
@@ -47,7 +50,7 @@ def test_log_spectra_within_1e3_db(report):
     assert w["mel_db"] < 1e-3, w["mel_db"]
     assert w["stft512_mag"] < 1e-4
     assert w["gammatone_raw"] < 1e-5
-    assert w["mfcc_raw"] < 4e-3 and w["mod_spec_raw"] < 1.2e-2          # DCT gain, see module docstring
+    assert w["mfcc_raw"] < 5e-4 and w["mod_spec_raw"] < 4e-3            # DCT gain (module docstring); 2x the measured 2.4e-4 / 2.0e-3
     assert w["onset_env"] < 1e-4
     assert w["lpc_raw"] < 1e-6
 
@@ -56,13 +59,20 @@ def test_integer_outputs_bit_exact(report):
     assert report["ints_ok"] == report["B"]
 
 
-def test_float_scalars_rtol_1e4(report):
-    rel = report["scal_rel"]
-    loose = {10, 29, 30, 33, 34}                                          # near-cancelling quantities: see docstring
+NEAR_CANCELLING = (10, 29, 30, 33, 34)                                    # see the module docstring
+
+
+def assert_all_scalars(r):
+    """All 36 scalars inside |d| <= 1e-4 |ref| + 2e-6; the 31 well-conditioned ones inside rtol 1e-4 alone."""
+    rel, exc = r["scal_rel"], r["scal_excess"]
     for i in range(36):
-        if i in loose:
-            continue
-        assert rel[i] < 1e-4, (i, rel[i])
+        assert exc[i] <= 0.0, (i, exc[i], rel[i])
+        if i not in NEAR_CANCELLING:
+            assert rel[i] < 1e-4, (i, rel[i])
+
+
+def test_float_scalars_rtol_1e4(report):
+    assert_all_scalars(report)
 
 
 def test_channels_match_oracle(report):
@@ -74,7 +84,7 @@ def test_channels_match_oracle(report):
 
 def test_tuning_agreement_rate(report):
     B = report["B"]
-    assert report["tun_ok"][0] >= 0.9 * B and report["tun_ok"][1] >= 0.9 * B, report["tun_ok"]
+    assert report["tun_ok"] == [B, B], report["tun_ok"]                   # the committed sets agree 100 %: a regression shows
     assert int(np.abs(report["status"]).sum()) == 0
 
 
@@ -271,7 +281,7 @@ def test_reference_mirror_entry_points(tmp_path, torch_cuda):
     assert np.abs(M.extract_gammatone_features(y) - P.gammatone_frames(y)).max() < 1e-5
     d = {}
     P.segment_features(y, debug=d)
-    assert np.abs(M.extract_spectral_modulation_features(d["mel_db"]) - P.modulation_frames(d["mel_db"])).max() < 1.2e-2
+    assert np.abs(M.extract_spectral_modulation_features(d["mel_db"]) - P.modulation_frames(d["mel_db"])).max() < 4e-3
 
 
 def test_full_batch_properties(torch_cuda):
@@ -402,7 +412,7 @@ def test_process_and_save_npz_from_two_threads(tmp_path, torch_cuda):
     assert fid == "nope" and ok is False and isinstance(err, str) and err
 
 
-@pytest.mark.parametrize("d,n", [(2, 4), (3, 2), (5, 2)])       # Hilbert radix plans: 5^3 4^3 2 | 5^3 3 4^3 | 5^4 4^3
+@pytest.mark.parametrize("d,n", [(2, 4), (3, 2), (5, 2), (10, 1)])   # Hilbert radix plans: 5^3 4^3 2 | 5^3 3 4^3 | 5^4 4^3 | 5^4 4^3 2
 def test_long_segments_match_oracle(torch_cuda, d, n):
     """BASELINE config 4: expected_len = 16000 d (long mode) against the oracle run with Params(duration=d); same
     tolerances as the 1 s path."""
@@ -412,7 +422,9 @@ def test_long_segments_match_oracle(torch_cuda, d, n):
     assert w["mel_db"] < 1e-3 and w["onset_env"] < 1e-4 and w["gammatone_raw"] < 1e-5 and w["lpc_raw"] < 1e-5
     for k, v in w.items():
         if k.startswith("ch:"):
-            assert v < 2e-4, (k, v)
+            # mod_spec: 8 float32 ulps of its largest coefficient (which grows with sqrt(T)), see tools/gpu_check_long.py
+            assert v < (max(2e-4, r["mod_tol_plane"]) if k == "ch:mod_spec" else 2e-4), (k, v)
+    assert w["mod_spec_raw"] < r["mod_tol_raw"], (w["mod_spec_raw"], r["mod_tol_raw"])
     assert r["ints_ok"] == n and r["tun"] == [n, n] and int(np.abs(r["status"]).sum()) == 0
     assert float(np.max(r["scal_rel"])) < 1e-4, r["scal_rel"]
 
@@ -459,7 +471,9 @@ def test_long_mode_stage_and_modspec_entry_points(torch_cuda):
         dbg = {}
         P.segment_features(Y[i], p, debug=dbg)
         got = eng.modspec(dbg["mel_db"][None])[0]
-        assert got.shape == (40, eng.T) and np.abs(got - P.modulation_frames(dbg["mel_db"])).max() < 1.2e-2
+        ref_mod = P.modulation_frames(dbg["mel_db"])
+        assert got.shape == (40, eng.T)
+        assert np.abs(got - ref_mod).max() < 8 * np.spacing(np.float32(np.abs(ref_mod).max()))   # 8 ulp of the DC term
     eng.close()
 
 
@@ -472,12 +486,11 @@ def test_real_fixture_segments_match_oracle(torch_cuda):
     assert r["B"] == 56 and int(np.abs(r["status"]).sum()) == 0
     assert w["mel_db"] < 1e-3 and w["stft512_mag"] < 1e-5
     assert r["ints_ok"] == r["B"], "peak count / first-minimum index must be bit-exact"
-    assert r["tun_ok"][0] >= 0.9 * r["B"] and r["tun_ok"][1] >= 0.9 * r["B"]
+    assert r["tun_ok"] == [r["B"], r["B"]], r["tun_ok"]
     for k, v in w.items():
         if k.startswith("ch:"):
             assert v < 2e-4, (k, v)
-    rel = r["scal_rel"].copy()
-    assert float(np.max(np.delete(rel, [10, 29, 30, 33, 34]))) < 1e-4, rel  # near-cancelling ones: see the module docstring
+    assert_all_scalars(r)
 
 
 def test_c_abi_error_codes_on_device(torch_cuda):

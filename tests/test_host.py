@@ -154,11 +154,59 @@ def test_fit_batch_and_load_wav(tmp_path):
     assert np.array_equal(b[0, :12000], q) and np.all(b[0, 12000:] == 0) and np.array_equal(b[1], np.concatenate([q, q])[:16000])
     mixed = PR.fit_batch([w, w.astype(np.float32) / 32768])
     assert mixed.dtype == np.float32 and np.array_equal(mixed[0], mixed[1])
-    scipy.io.wavfile.write(tmp_path / "b.wav", 8000, q)
-    with pytest.raises(ValueError):
-        PR.load_wav(str(tmp_path / "b.wav"))
+    # librosa.load semantics for the other PCM layouts: scale by dtype first, then average the channels
+    st16 = np.stack([q, -q // 2], axis=1).astype(np.int16)
+    scipy.io.wavfile.write(tmp_path / "st16.wav", 16000, st16)
+    w = PR.load_wav(str(tmp_path / "st16.wav"))
+    assert w.dtype == np.float32 and np.array_equal(w, np.mean(st16.astype(np.float32) / np.float32(32768), axis=1, dtype=np.float32))
+    st32 = (st16.astype(np.int32) << 16)
+    scipy.io.wavfile.write(tmp_path / "st32.wav", 16000, st32)
+    assert np.array_equal(PR.load_wav(str(tmp_path / "st32.wav")), w)         # same samples at 32 bits: same waveform
+    u8 = np.stack([(q >> 8) + 128, 128 - (q >> 9)], axis=1).astype(np.uint8)
+    scipy.io.wavfile.write(tmp_path / "st8.wav", 16000, u8)
+    w8 = PR.load_wav(str(tmp_path / "st8.wav"))
+    assert np.abs(w8).max() <= 1.0 and np.array_equal(w8, np.mean((u8.astype(np.float32) - 128) / 128, axis=1, dtype=np.float32))
+    m32 = (q.astype(np.int32) << 16)
+    scipy.io.wavfile.write(tmp_path / "m32.wav", 16000, m32)
+    assert np.array_equal(PR.load_wav(str(tmp_path / "m32.wav")), q.astype(np.float32) / np.float32(32768))
     fid, ok, err = PR.process_and_save_npz(("nope", str(tmp_path / "missing.wav"), str(tmp_path)))
     assert fid == "nope" and ok is False and isinstance(err, str)      # never raises (process.py:107-108)
+
+
+def test_resample_filter_table_matches_oracle():
+    """process.py:28 resample-on-load: the C++ polyphase table of bpc_resample against oracle/resample.py (host only)."""
+    from oracle import resample as R
+    from bpc_b200.engine import resample_filter
+    for sr_in, sr_out in ((8000, 16000), (48000, 16000), (44100, 16000), (22050, 16000), (11025, 16000)):
+        p, q, half, tab = resample_filter(sr_in, sr_out)
+        rp, rq, rhalf, rtab = R.polyphase_table(sr_in, sr_out)
+        assert (p, q, half) == (rp, rq, rhalf) and tab.shape == rtab.shape
+        assert np.abs(tab - rtab).max() < 2e-14 and np.allclose(tab.sum(axis=1), 1.0, atol=1e-14)
+        assert bpc_b200.lib().bpc_resample_len(12345, sr_in, sr_out) == -((-12345 * sr_out) // sr_in)
+    # the oracle's own contract: pass band flat to float32 rounding, stop band rejected far below 16-bit PCM
+    t = np.arange(48000) / 48000.0
+    for f0, want in ((1000.0, 1.0), (7000.0, 1.0), (9000.0, 0.0)):
+        o = R.resample(np.sin(2 * np.pi * f0 * t).astype(np.float32), 48000, 16000)
+        assert len(o) == 16000
+        ref = want * np.sin(2 * np.pi * f0 * np.arange(16000) / 16000.0)
+        assert np.abs(o[2000:14000] - ref[2000:14000]).max() < 2e-7, f0
+    assert bpc_b200.lib().bpc_resample_filter(0, 16000, None, 0, None, None, None) == -1
+
+
+def test_expand_compact_and_live_rows():
+    """Compact host layout (include/bpc.h): 772 data rows + 9 pad values per segment <-> the full [9,128,T] planes."""
+    from bpc_b200 import shards
+    lib = bpc_b200.lib()
+    assert [lib.bpc_live_rows(c) for c in range(9)] == list(L.LIVE_ROWS) and sum(L.LIVE_ROWS) == L.LIVE_TOTAL == 772
+    assert lib.bpc_live_rows(9) == -1 and lib.bpc_live_rows(-1) == -1
+    for T, n, threads in ((63, 7, 3), (126, 2, 1), (63, 0, 2)):
+        F, _ = _fake_rows(n, T=T, seed=11)
+        rows, pad = shards.compact_from_full(F)
+        assert rows.shape == (n, 772, T) and pad.shape == (n, 9)
+        assert np.array_equal(bpc_b200.expand_compact(rows, pad, threads=threads), F)
+    with pytest.raises(ValueError):
+        bpc_b200.expand_compact(np.zeros((2, 700, 63), np.float32), np.zeros((2, 9), np.float32))
+    assert lib.bpc_expand_compact(None, None, 1, 63, None, 1) == -1
 
 
 def _gloo_worker(rank, world, port, q):
@@ -313,8 +361,13 @@ def test_div_fast_algorithm():
 
 # ------------------------------------------------------------------------------------- output writer / packed shard
 def _fake_rows(n, T=63, S=36, seed=3):
+    """Random planes with the structure the path produces: rows live[c]..127 of a plane hold its minimum (pad_freq)."""
     rng = np.random.default_rng(seed)
-    return (rng.standard_normal((n, 9, 128, T)).astype(np.float32), rng.standard_normal((n, S)).astype(np.float32))
+    F = rng.standard_normal((n, 9, 128, T)).astype(np.float32)
+    for c, lv in enumerate(L.LIVE_ROWS):
+        if lv < 128:
+            F[:, c, lv:] = F[:, c, :lv].min(axis=(1, 2))[:, None, None]
+    return F, rng.standard_normal((n, S)).astype(np.float32)
 
 
 def test_cpp_npz_writer_is_readable_by_numpy_and_zipfile(tmp_path):
@@ -362,8 +415,9 @@ def _reference_ds_items(df, feature_dir, is_training):
     return out
 
 
+@pytest.mark.parametrize("compact", [True, False])
 @pytest.mark.parametrize("is_training", [True, False])
-def test_packed_shard_ds_matches_per_file_ds(tmp_path, is_training):
+def test_packed_shard_ds_matches_per_file_ds(tmp_path, is_training, compact):
     import pandas as pd
     import torch
     from bpc_b200 import shards
@@ -371,10 +425,13 @@ def test_packed_shard_ds_matches_per_file_ds(tmp_path, is_training):
     ids = [f"steth_{i:03d}_{'EI'[i % 2]}_1" for i in range(12)]
     per_file = tmp_path / "npz"; per_file.mkdir()
     shards.write_npz_batch(str(per_file), ids, F, S)
-    with shards.ShardWriter(str(tmp_path / "packed"), 12, 63, 36) as w:
+    with shards.ShardWriter(str(tmp_path / "packed"), 12, 63, 36, compact=compact) as w:
         w.append(ids[:7], F[:7], S[:7])
         w.append(ids[7:], F[7:], S[7:], np.zeros(5, np.int32))
     assert shards.is_packed(str(tmp_path / "packed")) and not shards.is_packed(str(per_file))
+    assert os.path.exists(tmp_path / "packed" / ("rows.npy" if compact else "feats.npy"))
+    if compact:                                                           # 67 % of the bytes of the full layout
+        assert os.path.getsize(tmp_path / "packed" / "rows.npy") < 0.68 * 12 * 9 * 128 * 63 * 4
     order = [5, 0, 11, 3, 3, 8]                                           # a shuffled subset, as a split would give
     df = pd.DataFrame({"ID": [ids[i] for i in order], "Target": ["EI"[i % 2] for i in order]})
     ds = shards.PackedDS(df, str(tmp_path / "packed"), is_training)
@@ -438,7 +495,8 @@ def test_cpp_wav_reader_matches_scipy_and_reports_per_file(tmp_path):
         assert errs[i] is None and np.array_equal(batch[i], want), n
     st = PR.load_wav(paths[4])                                              # librosa.load(mono=True): channel mean
     assert errs[4] is None and np.array_equal(batch[4], st[:16000])
-    assert "sample rate 8000" in errs[5]
+    # an 8 kHz file is resampled on the device (bpc_resample); without a GPU that is a per-file error, never a raise
+    assert errs[5] is None or "CUDA" in errs[5] or "bpc_create" in errs[5], errs[5]
     assert errs[6] is None and np.array_equal(batch[6], M.pad_or_truncate((sig[12345] / 32768.0).astype(np.float32), 16000))
     assert "RIFF" in errs[7] and "No such file" in errs[8]
     assert errs[9] is None and np.array_equal(batch[9], batch[0])

@@ -52,6 +52,7 @@ def compare(n_synth=8, verbose=True, real_inputs=False):
     edges = np.linspace(-0.5, 0.5, 101)
     tun_ok = [0, 0]
     scal_rel = np.zeros(36)
+    scal_excess = np.full(36, -np.inf)          # max over segments of |d| - (1e-4 |ref| + 2e-6): <= 0 means inside the gate
     ints_ok = 0
     for i in range(B):
         d = {}
@@ -81,6 +82,10 @@ def compare(n_synth=8, verbose=True, real_inputs=False):
         rel = np.where(np.isnan(sc) & np.isnan(scal[i, :36]), 0.0, rel)
         rel = np.where(sc == scal[i, :36], 0.0, rel)
         scal_rel = np.maximum(scal_rel, rel)
+        ad = np.abs(scal[i, :36].astype(np.float64) - sc.astype(np.float64))
+        ad = np.where(np.isnan(sc) & np.isnan(scal[i, :36]), 0.0, ad)
+        ad = np.where(np.isfinite(ad), ad, np.inf)
+        scal_excess = np.maximum(scal_excess, ad - (1e-4 * np.abs(np.nan_to_num(sc.astype(np.float64))) + 2e-6))
         if verbose and i < 2:
             print(f"seg {i}: status={status[i]} tuning gpu={dbg['tuning'][i].tolist()} ref=[{t12},{t36}] "
                   f"ints gpu={dbg['ints'][i].tolist()} ref=[{d['n_peaks']},{d['first_min_idx']}]")
@@ -91,8 +96,10 @@ def compare(n_synth=8, verbose=True, real_inputs=False):
             print(f"{k:20s} max abs err {v:.3e}")
         print("scalar max rel err per index:")
         print(np.array2string(scal_rel, precision=2, max_line_width=200))
+        print("scalar max(|d| - (1e-4 |ref| + 2e-6)) per index (<= 0 passes):")
+        print(np.array2string(scal_excess, precision=2, max_line_width=200))
         print(f"tuning agreement: 12-bpo {tun_ok[0]}/{B}, 36-bpo {tun_ok[1]}/{B};  integer outputs exact: {ints_ok}/{B}")
-    return dict(worst=worst, scal_rel=scal_rel, tun_ok=tun_ok, ints_ok=ints_ok, B=B, status=status)
+    return dict(worst=worst, scal_rel=scal_rel, scal_excess=scal_excess, tun_ok=tun_ok, ints_ok=ints_ok, B=B, status=status)
 
 
 if __name__ == "__main__":
