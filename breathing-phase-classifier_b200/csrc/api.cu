@@ -52,6 +52,9 @@ struct Slot {                      // one in-flight chunk of the host-buffer pat
     float* h_scalars = nullptr;
     int32_t* h_status = nullptr;
     cudaStream_t st = nullptr;
+    cudaStream_t st_out = nullptr;    // highest-priority stream of the piece's output side: pad values, row compaction, D2H.
+                                      // On the compute stream those two small kernels queued behind the NEXT piece's
+                                      // kernels and every D2H started ~0.2 ms late (r02 timeline: 45 instead of 52 GB/s).
     cudaEvent_t done = nullptr;
     cudaEvent_t computed = nullptr;   // kernels of this chunk finished (the slots share one workspace)
     cudaEvent_t fill_ready = nullptr; // the pad values of this chunk are in h_fill
@@ -247,6 +250,20 @@ private:
 
 }  // namespace
 
+// Everything one in-flight chunk needs besides its inputs / outputs: the intermediate workspace, the side streams of
+// the fork / join inside a chunk and their events.  The device entry points use the handle's `main` context; the host
+// path gives each of its slots an own context so that consecutive pieces overlap on the GPU (the tail of piece i's
+// kernels runs next to the head of piece i + 1 instead of leaving SMs idle).
+struct ChunkCtx {
+    Workspace ws{};
+    Workspace ws_dbg{};            // same workspace with the debug pointers populated (main context only)
+    int cap = 0;
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_spec512 = nullptr, ev_time = nullptr, ev_f2048 = nullptr, ev_seg = nullptr;
+    cudaEvent_t ws_free = nullptr; // end of the last enqueue that used this workspace (any stream)
+    bool ws_used = false;
+};
+
 struct bpc_handle {
     bpc_params p{};
     Geometry g{};
@@ -254,8 +271,8 @@ struct bpc_handle {
     int64_t max_batch = 0;
     int chunk = 0;
     Tables tb{};
-    Workspace ws{};
-    Workspace ws_dbg{};            // same workspace with the debug pointers populated
+    ChunkCtx main;                 // context of the device entry points (and of the host path while debug is on)
+    ChunkCtx slot_ctx[kSlots];     // contexts of the host path's slots (allocated with the slots)
     bool debug = false;
     double* stats_acc = nullptr;   // [(9 + nscal), 5]
     std::vector<void*> dev_allocs;
@@ -271,20 +288,18 @@ struct bpc_handle {
     bool contig_d2h = true;        // compact host layout: k_compact_rows + ONE copy per piece (env BPC_D2H_MODE=2d: row runs)
     struct Resampler { int sr_in, sr_out, p, q, half; const double* tab; };
     std::vector<Resampler> resamplers;   // polyphase tables uploaded so far (bpc_resample)
-    cudaEvent_t ws_free = nullptr; // end of the last enqueue that used the workspace (any stream)
-    bool ws_used = false;
     bool compact_d2h = true;       // host path transfers live rows only (env BPC_COMPACT_D2H=0: whole planes)
     int host_chunk = 0;            // piece size of the host path (env BPC_HOST_CHUNK, default chunk / 2: the D2H of a piece
                                    // can only start when its kernels are done, so smaller pieces shorten the ramp)
     bool taper_tail = true;        // host path halves the last pieces of a call (env BPC_TAPER=0: equal chunks)
+    bool ramp_head = true;         // ... and starts with small pieces so that the first D2H starts early (env BPC_RAMP=0)
+    bool slot_ctx_on = false;      // env BPC_SLOT_CTX=1: every slot computes in its own workspace (pieces overlap on the GPU)
     int last_n = 0;
     int64_t launches0 = 0;
     bool timing = false;           // per-kernel CUDA-event timing (bench.py roofline leg)
     // Fork / join inside a chunk: the STFT-512 branch, the time-domain branch and the per-segment STFT-2048 statistics
     // run on side streams next to the STFT-2048 -> tuning -> CENS chain on the caller's stream (run_chunk).
     bool multi_stream = true;      // env BPC_STREAMS=0 turns it off; the per-kernel timing leg always runs serially
-    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_spec512 = nullptr, ev_time = nullptr, ev_f2048 = nullptr, ev_seg = nullptr;
     struct Ev { int id; cudaEvent_t a, b; };
     std::vector<Ev> evs;
     std::string err;
@@ -388,6 +403,15 @@ int build_tables(bpc_handle* h) {
             }
         if ((rc = upload(h, t, &tb.twa1024))) return rc;
     }
+    {
+        std::vector<double2> t(16 * 16);
+        for (int k1 = 0; k1 < 16; ++k1)
+            for (int hh = 0; hh < 16; ++hh) {
+                const double ang = -2.0 * kPi * double((hh * k1) & 255) / 256.0;
+                t[k1 * 16 + hh] = make_double2(std::cos(ang), std::sin(ang));
+            }
+        if ((rc = upload(h, t, &tb.twa256))) return rc;
+    }
     if ((rc = upload(h, twiddles(512, 257), &tb.ptw512))) return rc;
     if ((rc = upload(h, twiddles(2048, 1025), &tb.ptw2048))) return rc;
     {
@@ -442,8 +466,16 @@ int build_tables(bpc_handle* h) {
         if ((rc = upload(h, dt, &tb.dct_time))) return rc;
         tb.dct_time_n = nullptr;
         tb.dct_tiles = nullptr;
+        tb.dct_colsum = nullptr;
         if (h->g.long_mode) {
             if ((rc = upload(h, d, &tb.dct_time_n))) return rc;
+            std::vector<float> cs((size_t)T);
+            for (int u = 0; u < T; ++u) {
+                double acc = 0.0;
+                for (int t = 0; t < T; ++t) acc += (double)d[size_t(u) * T + t];
+                cs[u] = (float)acc;
+            }
+            if ((rc = upload(h, cs, &tb.dct_colsum))) return rc;
             uint32_t* tiles = nullptr;
             if ((rc = dalloc(h, tc_tile_words(T, T), &tiles))) return rc;
             launch_tc_prep_b(h->g, tb, tiles, 0);
@@ -515,12 +547,16 @@ int build_tables(bpc_handle* h) {
     return BPC_OK;
 }
 
-int build_workspace(bpc_handle* h) {
+int build_workspace(bpc_handle* h, ChunkCtx& ctx, int cap) {
     const Geometry& g = h->g;
-    Workspace& w = h->ws;
-    const size_t C = (size_t)h->chunk, T = (size_t)g.T;
+    Workspace& w = ctx.ws;
+    const size_t C = (size_t)cap, T = (size_t)g.T;
     int rc;
-    w.cap = h->chunk;
+    ctx.cap = cap;
+    w.cap = cap;
+    for (auto& s : ctx.side) BPC_CUDA(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&ctx.ev_fork, &ctx.ev_spec512, &ctx.ev_time, &ctx.ev_f2048, &ctx.ev_seg, &ctx.ws_free})
+        BPC_CUDA(h, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     if ((rc = dalloc(h, C * g.L, &w.y))) return rc;
     if ((rc = dalloc(h, C * T * kMagStride, &w.mag512))) return rc;
     if ((rc = dalloc(h, C * ((T + 1) / 2) * kMag2048Stride, &w.mag_even))) return rc;
@@ -536,7 +572,9 @@ int build_workspace(bpc_handle* h) {
     w.scratch = nullptr;
     w.scratch_stride = 0;
     w.tc_a = nullptr;
-    if (g.long_mode && (rc = dalloc(h, tc_tile_words(h->chunk * 40, g.T), &w.tc_a))) return rc;
+    if (g.long_mode && (rc = dalloc(h, tc_tile_words(cap * 40, g.T), &w.tc_a))) return rc;
+    w.tc_mean = nullptr;
+    if (g.long_mode && (rc = dalloc(h, (size_t)cap * 40, &w.tc_mean))) return rc;
     if (g.long_mode) {
         // per-segment scratch of the kernel that needs most (kernels of a chunk run one after the other in long mode)
         size_t need = consumer_scratch_floats(g.T);
@@ -544,7 +582,7 @@ int build_workspace(bpc_handle* h) {
         w.scratch_stride = (need + 63) & ~size_t(63);
         if ((rc = dalloc(h, C * w.scratch_stride, &w.scratch))) return rc;
     }
-    if ((rc = dalloc(h, (size_t)(9 + g.nscal) * 5, &h->stats_acc))) return rc;
+    if (!h->stats_acc && (rc = dalloc(h, (size_t)(9 + g.nscal) * 5, &h->stats_acc))) return rc;
     // 1 s mode: the producers of the planes accumulate the dataset statistics themselves instead of k_stats re-reading
     // the planes (0.8 GB less DRAM traffic per 4096-segment step; +0.15 ms in the producers against 0.18 ms of
     // k_stats).  BPC_FUSED_STATS=0 and the long mode keep k_stats.
@@ -554,12 +592,12 @@ int build_workspace(bpc_handle* h) {
     }
     w.dbg_mel_db = w.dbg_mfcc = w.dbg_gam = w.dbg_mod = w.dbg_chroma_stft = w.dbg_chroma_cens = w.dbg_lpc =
         w.dbg_onset = nullptr;
-    h->ws_dbg = w;
+    ctx.ws_dbg = w;
     return BPC_OK;
 }
 
 int ensure_debug(bpc_handle* h) {
-    Workspace& w = h->ws_dbg;
+    Workspace& w = h->main.ws_dbg;
     if (w.dbg_mel_db) return BPC_OK;
     const Geometry& g = h->g;
     const size_t C = (size_t)h->chunk, T = (size_t)g.T;
@@ -585,13 +623,13 @@ int reset_stats(bpc_handle* h, cudaStream_t st) {
 }
 
 // The launch sequence for one chunk of n <= chunk segments; inputs / outputs are device pointers for this chunk.
-int run_chunk(bpc_handle* h, const void* wav, int wav_dtype, int64_t L_in, int n, float* feats, float* scalars,
-              int32_t* status, cudaStream_t st) {
+int run_chunk(bpc_handle* h, ChunkCtx& cx, const void* wav, int wav_dtype, int64_t L_in, int n, float* feats,
+              float* scalars, int32_t* status, cudaStream_t st) {
     const Geometry& g = h->g;
-    const Workspace& ws = h->debug ? h->ws_dbg : h->ws;
+    const Workspace& ws = (h->debug && &cx == &h->main) ? cx.ws_dbg : cx.ws;
     // One workspace per handle: whatever stream the previous enqueue used, this one starts after it (calls on a handle
     // are serialised by the caller on the host, not necessarily on one stream).
-    if (h->ws_used) BPC_CUDA(h, cudaStreamWaitEvent(st, h->ws_free, 0));
+    if (cx.ws_used) BPC_CUDA(h, cudaStreamWaitEvent(st, cx.ws_free, 0));
     const float* y;
     if (wav_dtype == BPC_WAV_F32 && L_in == g.L && (reinterpret_cast<uintptr_t>(wav) & 15) == 0) {
         y = static_cast<const float*>(wav);                   // pad_or_truncate is the identity: no copy
@@ -635,34 +673,34 @@ int run_chunk(bpc_handle* h, const void* wav, int wav_dtype, int64_t L_in, int n
         // Dependencies: stft512 -> consumers (mag512); spec2048 -> {even2048, seg2048} (mag_even, frame_feat, melD);
         // {consumers (chroma_min), even2048 (tuning-36)} -> cens; the time-domain kernels only read y.  Every branch
         // joins before the statistics kernel, so consecutive chunks (one shared workspace) stay ordered.
-        cudaStream_t sA = h->side[0], sC = h->side[1], sD = h->side[2];
-        BPC_CUDA(h, cudaEventRecord(h->ev_fork, st));
-        BPC_CUDA(h, cudaStreamWaitEvent(sA, h->ev_fork, 0));
-        BPC_CUDA(h, cudaStreamWaitEvent(sC, h->ev_fork, 0));
+        cudaStream_t sA = cx.side[0], sC = cx.side[1], sD = cx.side[2];
+        BPC_CUDA(h, cudaEventRecord(cx.ev_fork, st));
+        BPC_CUDA(h, cudaStreamWaitEvent(sA, cx.ev_fork, 0));
+        BPC_CUDA(h, cudaStreamWaitEvent(sC, cx.ev_fork, 0));
         launch_spec2048(y, n, g, h->tb, ws, feats, scalars, st);
-        BPC_CUDA(h, cudaEventRecord(h->ev_f2048, st));
+        BPC_CUDA(h, cudaEventRecord(cx.ev_f2048, st));
         launch_stft512(y, n, g, h->tb, ws, sA);
         launch_spec512_consumers(n, g, h->tb, ws, feats, scalars, status, true, sA);
-        BPC_CUDA(h, cudaEventRecord(h->ev_spec512, sA));
+        BPC_CUDA(h, cudaEventRecord(cx.ev_spec512, sA));
         launch_even2048(n, g, h->tb, ws, scalars, status, st);
-        BPC_CUDA(h, cudaStreamWaitEvent(sD, h->ev_f2048, 0));
+        BPC_CUDA(h, cudaStreamWaitEvent(sD, cx.ev_f2048, 0));
         launch_seg2048(n, g, h->tb, ws, feats, scalars, sD);
-        BPC_CUDA(h, cudaEventRecord(h->ev_seg, sD));
+        BPC_CUDA(h, cudaEventRecord(cx.ev_seg, sD));
         launch_lpc(y, n, g, h->tb, ws, feats, sC);
         launch_time_scalars(y, n, g, h->tb, ws, scalars, status, sC);
         launch_hilbert(y, n, g, h->tb, ws, scalars, sC);
-        BPC_CUDA(h, cudaEventRecord(h->ev_time, sC));
-        BPC_CUDA(h, cudaStreamWaitEvent(st, h->ev_spec512, 0));
+        BPC_CUDA(h, cudaEventRecord(cx.ev_time, sC));
+        BPC_CUDA(h, cudaStreamWaitEvent(st, cx.ev_spec512, 0));
         launch_cens(y, n, g, h->tb, ws, feats, st);
-        BPC_CUDA(h, cudaStreamWaitEvent(st, h->ev_seg, 0));
-        BPC_CUDA(h, cudaStreamWaitEvent(st, h->ev_time, 0));
+        BPC_CUDA(h, cudaStreamWaitEvent(st, cx.ev_seg, 0));
+        BPC_CUDA(h, cudaStreamWaitEvent(st, cx.ev_time, 0));
     }
     launch_pad_scalars(n, g, scalars, st);
     timed(9, [&] { launch_stats(n, g, feats, scalars, h->stats_acc, ws.stats_acc == nullptr, st); });
     h->last_n = n;
     BPC_CUDA(h, cudaGetLastError());
-    BPC_CUDA(h, cudaEventRecord(h->ws_free, st));
-    h->ws_used = true;
+    BPC_CUDA(h, cudaEventRecord(cx.ws_free, st));
+    cx.ws_used = true;
     return BPC_OK;
 }
 
@@ -703,10 +741,25 @@ int ensure_slots(bpc_handle* h) {
         if ((rc = host_pinned(h, C * 4, (void**)&s.h_status))) return rc;
         if ((rc = host_pinned(h, C * 9 * 4, (void**)&s.h_fill))) return rc;
         BPC_CUDA(h, cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        {
+            int prio_lo = 0, prio_hi = 0;
+            BPC_CUDA(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            BPC_CUDA(h, cudaStreamCreateWithPriority(&s.st_out, cudaStreamNonBlocking, prio_hi));
+        }
         BPC_CUDA(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         BPC_CUDA(h, cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
         BPC_CUDA(h, cudaEventCreateWithFlags(&s.fill_ready, cudaEventDisableTiming));
     }
+    {
+        // r02: with a workspace per slot consecutive pieces overlap on the GPU, but then every piece FINISHES later and
+        // its D2H starts later -- measured 19-20.5 ms per 4096-segment call against 17.9-18.6 ms serialised.  Off by default.
+        const char* env_sc = std::getenv("BPC_SLOT_CTX");
+        h->slot_ctx_on = env_sc && std::atoi(env_sc) == 1;
+        const char* env_rp = std::getenv("BPC_RAMP");
+        h->ramp_head = !(env_rp && std::atoi(env_rp) == 0);
+    }
+    for (int i = 0; h->slot_ctx_on && i < kSlots; ++i)
+        if ((rc = build_workspace(h, h->slot_ctx[i], h->host_chunk))) return rc;
     BPC_CUDA(h, cudaMalloc((void**)&h->live_dev, sizeof(kLiveRows)));
     h->dev_allocs.push_back(h->live_dev);
     BPC_CUDA(h, cudaMemcpy(h->live_dev, kLiveRows, sizeof(kLiveRows), cudaMemcpyHostToDevice));
@@ -800,15 +853,12 @@ int bpc_create(bpc_handle** out, const bpc_params* p, int device, int64_t max_ba
     h->launches0 = launches_issued();
     const char* env_streams = std::getenv("BPC_STREAMS");
     h->multi_stream = !(env_streams && std::atoi(env_streams) == 0);
-    for (auto& s : h->side) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-    for (cudaEvent_t* e : {&h->ev_fork, &h->ev_spec512, &h->ev_time, &h->ev_f2048, &h->ev_seg, &h->ws_free})
-        cudaEventCreateWithFlags(e, cudaEventDisableTiming);
     {
         const char* env_numa = std::getenv("BPC_NUMA");
         h->numa_place = !(env_numa && std::atoi(env_numa) == 0);
         h->numa = numa_of_device(device);
     }
-    if ((rc = build_tables(h)) || (rc = build_workspace(h)) || (rc = reset_stats(h, 0))) {
+    if ((rc = build_tables(h)) || (rc = build_workspace(h, h->main, h->chunk)) || (rc = reset_stats(h, 0))) {
         g_create_error = h->err;
         bpc_destroy(h);
         return rc;
@@ -823,13 +873,16 @@ void bpc_destroy(bpc_handle* h) {
     cudaDeviceSynchronize();
     for (int i = 0; i < kSlots; ++i) {
         if (h->slot[i].st) cudaStreamDestroy(h->slot[i].st);
+        if (h->slot[i].st_out) cudaStreamDestroy(h->slot[i].st_out);
         if (h->slot[i].done) cudaEventDestroy(h->slot[i].done);
         if (h->slot[i].computed) cudaEventDestroy(h->slot[i].computed);
         if (h->slot[i].fill_ready) cudaEventDestroy(h->slot[i].fill_ready);
     }
     delete h->pool;
-    for (auto& s : h->side) if (s) cudaStreamDestroy(s);
-    for (cudaEvent_t e : {h->ev_fork, h->ev_spec512, h->ev_time, h->ev_f2048, h->ev_seg, h->ws_free}) if (e) cudaEventDestroy(e);
+    for (ChunkCtx* cx : {&h->main, &h->slot_ctx[0], &h->slot_ctx[1], &h->slot_ctx[2]}) {
+        for (auto& s : cx->side) if (s) cudaStreamDestroy(s);
+        for (cudaEvent_t e : {cx->ev_fork, cx->ev_spec512, cx->ev_time, cx->ev_f2048, cx->ev_seg, cx->ws_free}) if (e) cudaEventDestroy(e);
+    }
     for (void* d : h->dev_allocs) cudaFree(d);
     for (void* d : h->host_allocs) cudaFreeHost(d);
     for (auto& a : h->numa_allocs) numa_pinned_free(a.first, a.second);
@@ -861,7 +914,7 @@ int bpc_precompute(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int
     const size_t esz = wav_dtype == BPC_WAV_F32 ? 4 : 2;
     for (int64_t off = 0; off < B; off += h->chunk) {
         const int n = (int)std::min<int64_t>(h->chunk, B - off);
-        int rc = run_chunk(h, static_cast<const char*>(wav) + (size_t)off * L_in * esz, wav_dtype, L_in, n,
+        int rc = run_chunk(h, h->main, static_cast<const char*>(wav) + (size_t)off * L_in * esz, wav_dtype, L_in, n,
                            feats + (size_t)off * 9 * kPlaneRows * g.T, scalars + (size_t)off * g.nscal,
                            status ? status + off : nullptr, st);
         if (rc) return rc;
@@ -897,19 +950,32 @@ int host_pipeline(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int6
     const std::vector<RowRun> runs = live_runs();
     double t_wait = 0.0, t_fill = 0.0;
     const auto t_call = std::chrono::steady_clock::now();
+    const char* env_trace = std::getenv("BPC_HOST_TRACE");
+    const bool timeline = env_trace && std::atoi(env_trace) >= 2;      // per-piece device timeline (debugging aid)
+    struct Tl { cudaEvent_t a, c, d; int n; };
+    std::vector<Tl> tl;
     // Piece schedule: full pieces, then the last <= host_chunk segments in halves (not below 128 segments, about one CTA
     // wave): what is exposed at the end of a call is the D2H (+ fill) of the LAST piece only, so it should be small.
     struct Piece { int64_t off; int n; };
     std::vector<Piece> sched;
     {
+        // Ramp: the D2H engine idles until the first piece has been computed, so the call starts with pieces of about
+        // one and two CTA waves (148, 296 segments) before it settles at host_chunk.
         int64_t off = 0;
+        int ramp = (h->ramp_head && !h->g.long_mode && B >= 4 * (int64_t)h->host_chunk) ? 148 : h->host_chunk;
         while (off < B) {
-            int64_t rem = B - off, n = std::min<int64_t>(h->host_chunk, rem);
+            const int64_t cap = std::min<int64_t>(ramp, h->host_chunk);
+            int64_t rem = B - off, n = std::min<int64_t>(cap, rem);
             if (rem <= h->host_chunk && h->taper_tail && rem >= 256) n = std::max<int64_t>(128, rem / 2);
             sched.push_back({off, (int)n});
             off += n;
+            ramp = (int)std::min<int64_t>(2 * (int64_t)ramp, h->host_chunk);
         }
     }
+    if (to_rows && !h->contig_d2h)
+        for (int64_t b = 0; b < B; ++b)
+            for (int c = 0; c < 9; ++c)
+                if (kLiveRows[c] == kPlaneRows) out.pad[b * 9 + c] = 0.f;
     const int64_t nchunks = (int64_t)sched.size();
     const bool live_only = to_rows || h->compact_d2h;        // only the 772 data rows cross PCIe
     auto wait_on = [&](cudaEvent_t ev) -> cudaError_t {
@@ -934,6 +1000,12 @@ int host_pipeline(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int6
                 const int n = sched[i].n;
                 const char* src = static_cast<const char*>(wav) + (size_t)off * L_in * esz;
                 const size_t in_bytes = (size_t)n * L_in * esz;
+                if (timeline) {
+                    Tl e{nullptr, nullptr, nullptr, n};
+                    cudaEventCreate(&e.a); cudaEventCreate(&e.c); cudaEventCreate(&e.d);
+                    cudaEventRecord(e.a, s.st);
+                    tl.push_back(e);
+                }
                 if (pin_in) {
                     BPC_CUDA(h, cudaMemcpyAsync(s.d_wav, src, in_bytes, cudaMemcpyHostToDevice, s.st));
                 } else {
@@ -942,23 +1014,39 @@ int host_pipeline(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int6
                 }
                 // The H2D above overlaps the previous piece's kernels; the kernels themselves are serialised by the
                 // handle's workspace event (run_chunk), because all slots share the one workspace.
-                int rc2 = run_chunk(h, s.d_wav, wav_dtype, L_in, n, s.d_feats, s.d_scalars, s.d_status, s.st);
+                // debug on: the raw stages of the last chunk are read from the main context afterwards (bpc_debug_copy)
+                ChunkCtx& cx = (h->debug || !h->slot_ctx_on) ? h->main : h->slot_ctx[i % kSlots];
+                int rc2 = run_chunk(h, cx, s.d_wav, wav_dtype, L_in, n, s.d_feats, s.d_scalars, s.d_status, s.st);
                 if (rc2) return rc2;
+                if (timeline) cudaEventRecord(tl.back().c, s.st);
+                BPC_CUDA(h, cudaEventRecord(s.computed, s.st));
+                BPC_CUDA(h, cudaStreamWaitEvent(s.st_out, s.computed, 0));
+                cudaStream_t so = s.st_out;                                // everything below: the piece's output side
                 float* sdst = pin_s ? scalars + (size_t)off * g.nscal : s.h_scalars;
                 if (to_rows) {
-                    launch_pad_values(s.d_feats, T, n, h->live_dev, s.d_fill, s.st);
                     float* pdst = pin_p ? out.pad + (size_t)off * 9 : s.h_fill;
                     float* rdst = pin_f ? out.rows + (size_t)off * seg_rows : s.h_feats;
-                    BPC_CUDA(h, cudaMemcpyAsync(pdst, s.d_fill, (size_t)n * 9 * 4, cudaMemcpyDeviceToHost, s.st));
                     if (h->contig_d2h) {
-                        launch_compact_rows(s.d_feats, T, n, kLiveRows, s.d_rows, s.st);
-                        BPC_CUDA(h, cudaMemcpyAsync(rdst, s.d_rows, (size_t)n * seg_rows * 4, cudaMemcpyDeviceToHost, s.st));
+                        launch_pad_values(s.d_feats, T, n, h->live_dev, s.d_fill, so);
+                        BPC_CUDA(h, cudaMemcpyAsync(pdst, s.d_fill, (size_t)n * 9 * 4, cudaMemcpyDeviceToHost, so));
+                    } else {
+                        // copy-engine only (no kernel has to find a free SM next to the following piece's persistent
+                        // CTAs): the pad value of plane c is the first element of its first pad row, a 4-byte column
+                        // of the [n, 9 * 128 * T] matrix; planes without pad rows report 0 (memset once per call)
+                        for (int c = 0; c < 9; ++c)
+                            if (kLiveRows[c] < kPlaneRows)
+                                BPC_CUDA(h, cudaMemcpy2DAsync(pdst + c, 9 * 4, s.d_feats + ((size_t)c * kPlaneRows + kLiveRows[c]) * T,
+                                                              seg_feats * 4, 4, (size_t)n, cudaMemcpyDeviceToHost, so));
+                    }
+                    if (h->contig_d2h) {
+                        launch_compact_rows(s.d_feats, T, n, kLiveRows, s.d_rows, so);
+                        BPC_CUDA(h, cudaMemcpyAsync(rdst, s.d_rows, (size_t)n * seg_rows * 4, cudaMemcpyDeviceToHost, so));
                     } else {
                         size_t row0 = 0;                               // first compact row of the run
                         for (const RowRun& r : runs) {
                             BPC_CUDA(h, cudaMemcpy2DAsync(rdst + row0 * T, seg_rows * 4, s.d_feats + (size_t)r.start * T,
                                                           seg_feats * 4, (size_t)(r.end - r.start) * T * 4, (size_t)n,
-                                                          cudaMemcpyDeviceToHost, s.st));
+                                                          cudaMemcpyDeviceToHost, so));
                             row0 += (size_t)(r.end - r.start);
                         }
                     }
@@ -967,21 +1055,22 @@ int host_pipeline(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int6
                     if (live_only) {
                         // PCIe carries only the rows that hold data (772 of the 1152 rows of a segment); the constant
                         // pad rows are re-created on the host from one value per plane.
-                        launch_pad_values(s.d_feats, T, n, h->live_dev, s.d_fill, s.st);
-                        BPC_CUDA(h, cudaMemcpyAsync(s.h_fill, s.d_fill, (size_t)n * 9 * 4, cudaMemcpyDeviceToHost, s.st));
-                        BPC_CUDA(h, cudaEventRecord(s.fill_ready, s.st));
+                        launch_pad_values(s.d_feats, T, n, h->live_dev, s.d_fill, so);
+                        BPC_CUDA(h, cudaMemcpyAsync(s.h_fill, s.d_fill, (size_t)n * 9 * 4, cudaMemcpyDeviceToHost, so));
+                        BPC_CUDA(h, cudaEventRecord(s.fill_ready, so));
                         const size_t pitch = seg_feats * 4;
                         for (const RowRun& r : runs)
                             BPC_CUDA(h, cudaMemcpy2DAsync(fdst + (size_t)r.start * T, pitch, s.d_feats + (size_t)r.start * T,
                                                           pitch, (size_t)(r.end - r.start) * T * 4, (size_t)n,
-                                                          cudaMemcpyDeviceToHost, s.st));
+                                                          cudaMemcpyDeviceToHost, so));
                     } else {
-                        BPC_CUDA(h, cudaMemcpyAsync(fdst, s.d_feats, (size_t)n * seg_feats * 4, cudaMemcpyDeviceToHost, s.st));
+                        BPC_CUDA(h, cudaMemcpyAsync(fdst, s.d_feats, (size_t)n * seg_feats * 4, cudaMemcpyDeviceToHost, so));
                     }
                 }
-                BPC_CUDA(h, cudaMemcpyAsync(sdst, s.d_scalars, (size_t)n * g.nscal * 4, cudaMemcpyDeviceToHost, s.st));
-                BPC_CUDA(h, cudaMemcpyAsync(s.h_status, s.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, s.st));
-                BPC_CUDA(h, cudaEventRecord(s.done, s.st));
+                BPC_CUDA(h, cudaMemcpyAsync(sdst, s.d_scalars, (size_t)n * g.nscal * 4, cudaMemcpyDeviceToHost, so));
+                BPC_CUDA(h, cudaMemcpyAsync(s.h_status, s.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, so));
+                BPC_CUDA(h, cudaEventRecord(s.done, so));
+                if (timeline) cudaEventRecord(tl.back().d, so);
             }
             if (!to_rows && live_only && i >= 1 && i - 1 < nchunks) {     // pad rows of piece i - 1 (disjoint from the D2H rows)
                 const int64_t j = i - 1;
@@ -1046,7 +1135,19 @@ int host_pipeline(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int6
         cudaGetLastError();
         return rc;
     }
-    if (std::getenv("BPC_HOST_TRACE")) {
+    if (timeline) {
+        cudaDeviceSynchronize();
+        for (size_t i = 0; i < tl.size(); ++i) {
+            float a = 0.f, c = 0.f, d = 0.f;
+            cudaEventElapsedTime(&a, tl[0].a, tl[i].a);
+            cudaEventElapsedTime(&c, tl[0].a, tl[i].c);
+            cudaEventElapsedTime(&d, tl[0].a, tl[i].d);
+            std::fprintf(stderr, "[bpc host]   piece %2zu n=%4d  stream start %7.3f  computed %7.3f  d2h done %7.3f ms\n", i, tl[i].n, a, c, d);
+        }
+        for (auto& e : tl) { cudaEventDestroy(e.a); cudaEventDestroy(e.c); cudaEventDestroy(e.d); }
+        cudaGetLastError();
+    }
+    if (env_trace) {
         int ncpu = -1;
 #if defined(__linux__)
         cpu_set_t set;
@@ -1141,11 +1242,17 @@ int bpc_stage_logmel(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, i
     BPC_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Geometry& g = h->g;
-    const Workspace& ws = h->debug ? h->ws_dbg : h->ws;
+    const Workspace& ws = h->debug ? h->main.ws_dbg : h->main.ws;
     const size_t esz = wav_dtype == BPC_WAV_F32 ? 4 : 2;
     for (int64_t off = 0; off < B; off += h->chunk) {
         const int n = (int)std::min<int64_t>(h->chunk, B - off);
         const void* w = static_cast<const char*>(wav) + (size_t)off * L_in * esz;
+        if (L_in == g.L && !h->debug &&
+            launch_logmel_fused(w, wav_dtype, n, g, h->tb, stft_db ? stft_db + (size_t)off * 257 * g.T : nullptr,
+                                mel3 + (size_t)off * 3 * kPlaneRows * g.T, st)) {
+            h->last_n = n;
+            continue;
+        }
         const float* y;
         if (wav_dtype == BPC_WAV_F32 && L_in == g.L && (reinterpret_cast<uintptr_t>(w) & 15) == 0) y = static_cast<const float*>(w);
         else { launch_ingest(w, wav_dtype, L_in, ws.y, n, g, st); y = ws.y; }
@@ -1162,7 +1269,7 @@ int bpc_modspec(bpc_handle* h, const float* mel_db, int64_t n, float* out, void*
     if (!h) return BPC_ERR_ARG;
     if (!mel_db || !out || n < 0) { h->err = "bpc_modspec: bad argument"; return BPC_ERR_ARG; }
     BPC_CUDA(h, cudaSetDevice(h->device));
-    if (n > 0) launch_modspec((int)n, h->g, h->tb, h->ws, mel_db, out, static_cast<cudaStream_t>(stream));
+    if (n > 0) launch_modspec((int)n, h->g, h->tb, h->main.ws, mel_db, out, static_cast<cudaStream_t>(stream));
     BPC_CUDA(h, cudaGetLastError());
     return BPC_OK;
 }
@@ -1223,7 +1330,7 @@ int bpc_debug_copy(bpc_handle* h, const char* what, void* out, int64_t cap_bytes
     BPC_CUDA(h, cudaSetDevice(h->device));
     BPC_CUDA(h, cudaDeviceSynchronize());
     const Geometry& g = h->g;
-    const Workspace& w = h->ws_dbg;
+    const Workspace& w = h->main.ws_dbg;
     const size_t n = (size_t)h->last_n, T = (size_t)g.T;
     const void* src = nullptr;
     size_t bytes = 0;
@@ -1309,6 +1416,7 @@ int bpc_resample(bpc_handle* h, const float* in, int64_t n_in, int sr_in, int sr
                  void* stream) {
     if (!h) return BPC_ERR_ARG;
     const int64_t n_out = bpc_resample_len(n_in, sr_in, sr_out);
+    if (n_out == 0) return BPC_OK;                                    // empty waveform: nothing to write
     if (!in || !out || n_out < 0 || out_cap < n_out || sr_in > 768000 || sr_out > 768000) {
         h->err = "bpc_resample: bad argument";
         return BPC_ERR_ARG;

@@ -126,19 +126,68 @@ __device__ void power_to_db_inplace(float* P, int n, bool ref_is_max, float* fsc
 // interior correlation; the 4 edge samples on each side take the (constant) order-th derivative of the edge fit,
 // i.e. the interior value at t=4 / t=T-5.  float64 accumulate (scaled by the reciprocal of the normaliser: the
 // difference to a float64 division disappears in the float32 rounding), float32 store.
+__device__ __forceinline__ double delta1_taps(double m4, double m3, double m2, double m1, double p1, double p2,
+                                              double p3, double p4) {
+    return fma(4.0, p4 - m4, fma(3.0, p3 - m3, fma(2.0, p2 - m2, p1 - m1))) * (1.0 / 60.0);
+}
+__device__ __forceinline__ double delta2_taps(double m4, double m3, double m2, double m1, double c, double p1, double p2,
+                                              double p3, double p4) {
+    return fma(28.0, p4 + m4, fma(7.0, p3 + m3, fma(-8.0, p2 + m2, fma(-17.0, p1 + m1, -20.0 * c)))) * (1.0 / 462.0);
+}
 __device__ __forceinline__ float delta_at(const float* row, int t, int T, int order) {
     const int tc = t < 4 ? 4 : (t > T - 5 ? T - 5 : t);
     const float* r = row + tc;
-    double acc;
-    if (order == 1) {
-        acc = (4.0 * ((double)r[4] - (double)r[-4]) + 3.0 * ((double)r[3] - (double)r[-3]) +
-               2.0 * ((double)r[2] - (double)r[-2]) + ((double)r[1] - (double)r[-1])) * (1.0 / 60.0);
-    } else {
-        acc = (28.0 * ((double)r[4] + (double)r[-4]) + 7.0 * ((double)r[3] + (double)r[-3]) -
-               8.0 * ((double)r[2] + (double)r[-2]) - 17.0 * ((double)r[1] + (double)r[-1]) - 20.0 * (double)r[0]) *
-              (1.0 / 462.0);
+    if (order == 1)
+        return (float)delta1_taps((double)r[-4], (double)r[-3], (double)r[-2], (double)r[-1], (double)r[1], (double)r[2],
+                                  (double)r[3], (double)r[4]);
+    return (float)delta2_taps((double)r[-4], (double)r[-3], (double)r[-2], (double)r[-1], (double)r[0], (double)r[1],
+                              (double)r[2], (double)r[3], (double)r[4]);
+}
+
+// Both deltas of `rows` rows of length T (src[r * T + t]) by the whole CTA: a work item is one run of 8 consecutive
+// centres of one row, whose 16 samples are widened to double ONCE and slide through registers (delta_at widens nine
+// values per output and order: the quarter-rate F2F.F64.F32 conversions were a quarter of role_mel's stencil phase).
+// d1 / d2 receive [rows, T]; the four edge frames on either side repeat the value of centre 4 / T - 5 (see above).
+// If `sums` is set, sums[0..3] accumulate this thread's sum / sum of squares of the d1 and d2 values it stored.
+// No barrier inside: the caller synchronises before anyone else reads d1 / d2.
+__device__ __forceinline__ void delta_rows_block(const float* src, int rows, int T, float* d1, float* d2, double* sums) {
+    const int runs = (T - 8 + 7) >> 3;                           // centres 4 .. T - 5 in runs of 8
+    double s1 = 0.0, q1 = 0.0, s2 = 0.0, q2 = 0.0;
+    for (int item = threadIdx.x; item < rows * runs; item += blockDim.x) {
+        const int r = item / runs, run = item - r * runs;
+        const int c0 = 4 + 8 * run, nc = min(8, T - 4 - c0);    // centres c0 .. c0 + nc - 1
+        const float* row = src + (size_t)r * T;
+        double w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = (double)row[min(c0 - 4 + j, T - 1)];
+        float* o1 = d1 + (size_t)r * T;
+        float* o2 = d2 + (size_t)r * T;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < nc) {
+                const float v1 = (float)delta1_taps(w[j], w[j + 1], w[j + 2], w[j + 3], w[j + 5], w[j + 6], w[j + 7], w[j + 8]);
+                const float v2 = (float)delta2_taps(w[j], w[j + 1], w[j + 2], w[j + 3], w[j + 4], w[j + 5], w[j + 6], w[j + 7], w[j + 8]);
+                const int c = c0 + j;
+                int reps = 1;
+                o1[c] = v1;
+                o2[c] = v2;
+                if (c == 4) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { o1[e] = v1; o2[e] = v2; }
+                    reps += 4;
+                }
+                if (c == T - 5) {
+#pragma unroll
+                    for (int e = 1; e <= 4; ++e) { o1[T - 5 + e] = v1; o2[T - 5 + e] = v2; }
+                    reps += 4;
+                }
+                const double a = (double)v1, b = (double)v2, n = (double)reps;
+                s1 = fma(n, a, s1); q1 = fma(n * a, a, q1);
+                s2 = fma(n, b, s2); q2 = fma(n * b, b, q2);
+            }
+        }
     }
-    return (float)acc;
+    if (sums) { sums[0] = s1; sums[1] = q1; sums[2] = s2; sums[3] = q2; }
 }
 
 // Band-form filterbank applied to |X| (power = false) or |X|^2 (power = true): out[m*T + t], float32 accumulate.
@@ -311,16 +360,15 @@ __device__ void role_mel(int b, const Geometry g, const Tables& tb, const Worksp
     }
     // statistics of mel_db, delta, delta2 (process.py:34-38).  The raw deltas are parked in their output planes and
     // normalised in place by the thread that wrote them (v1 evaluated the FP64 stencils twice).
-    double s0 = 0, q0 = 0, s1 = 0, q1 = 0, s2 = 0, q2 = 0;
+    double s0 = 0, q0 = 0, s1, q1, s2, q2;
+    {
+        double sums[4];
+        delta_rows_block(P, kPlaneRows, T, o1, o2, sums);
+        s1 = sums[0]; q1 = sums[1]; s2 = sums[2]; q2 = sums[3];
+    }
     for (int i = threadIdx.x; i < NP; i += blockDim.x) {
-        const int m = i / T, t = i - m * T;
-        const float d1 = delta_at(P + m * T, t, T, 1), d2 = delta_at(P + m * T, t, T, 2);
-        o1[i] = d1;
-        o2[i] = d2;
-        const double v0 = (double)P[i], v1 = (double)d1, v2 = (double)d2;
+        const double v0 = (double)P[i];
         s0 += v0; q0 += v0 * v0;
-        s1 += v1; q1 += v1 * v1;
-        s2 += v2; q2 += v2 * v2;
     }
     block_sum2(s0, q0, dscratch);
     block_sum2(s1, q1, dscratch);
@@ -392,11 +440,10 @@ __device__ void role_mfcc(int b, const Geometry g, const Tables& tb, const Works
     // row-wise z-score of vstack([mfcc, delta, delta2]) (process.py:46-47): one warp per row
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     float mn = FLT_MAX;
+    for (int i = threadIdx.x; i < 40 * T; i += blockDim.x) OUT[i] = MF[i];
+    delta_rows_block(MF, 40, T, OUT + 40 * T, OUT + 80 * T, nullptr);
+    __syncthreads();
     for (int r = warp; r < 120; r += nw) {
-        const int src = r % 40, ord = r / 40;
-        for (int t = lane; t < T; t += 32)
-            OUT[r * T + t] = ord == 0 ? MF[src * T + t] : delta_at(MF + src * T, t, T, ord);
-        __syncwarp();
         const ZTerm z = np_row_zterm(OUT + r * T, T, lane);
         __syncwarp();
         for (int t = lane; t < T; t += 32) {
@@ -802,6 +849,222 @@ void launch_modspec(int n, const Geometry& g, const Tables& tb, const Workspace&
     });
     k_modspec<<<n, 256, kConsumerSmemFloats * sizeof(float), st>>>(g, tb, mel_db, out);
     note_launch();
+}
+
+// ================================================================= BASELINE config 2, fused (1 s mode): k_logmel_fused
+// log-power STFT [257, T] + mel / mel_delta / mel_delta2 [3, 128, T] of a segment in ONE kernel: nothing but the input
+// (32 KB of PCM16, or 64 KB of float32) is read from HBM and nothing but the two outputs is written (225,532 B per
+// segment with float32 input: SURVEY 8(d) config 2).  The three-kernel path it replaces moved the |X| workspace
+// through L2 / HBM twice more (k_stft512 -> k_stft_db + k_spec512_consumers role 0).
+//
+// Persistent: one 512-thread CTA per SM walks segments b = blockIdx.x, + gridDim.x, ...
+//   stage   the raw segment lands in shared memory by ONE bulk-TMA copy per <= 32 KB (cp.async.bulk + mbarrier,
+//           SASS: UBLKCP) between two permanent 256-sample zero pads (librosa's centre padding: no bounds checks in
+//           the frame loader); the copy for segment b + gridDim.x is issued as soon as the FFT phase of segment b has
+//           consumed the buffer, so it overlaps the dB / filterbank / stencil / store phases
+//   FFT     32 half-warp teams x 2 rounds: Hann * samples -> FP64 real FFT-512 (fft_reg.cuh, split exchange) ->
+//           |X|^2 as float32 into a [T][257] tile (stride 257: conflict-free for the frame-major writes here and the
+//           bin-major reads below); PCM16 samples become doubles by the 2^52 trick (one XOR + one DADD instead of two
+//           quarter-rate conversions) and their 2^-15 is folded, exactly, into the final complex64 rounding
+//   dB      power_to_db(ref = max, top_db = 80) from the tile, written once, 16-byte stores
+//   mel     band-form mel-A filterbank from the tile -> [128][T] (in the FFT exchange space), dB, Savitzky-Golay
+//           deltas into the (now dead) power tile, three whole-array z-scores, each plane written once
+constexpr int kLmThreads = 512;
+constexpr int kLmTeams = kLmThreads / 16;
+constexpr int kLmPStride = 257;
+constexpr int kLmPad = 256;                                   // n_fft / 2 zero samples on either side
+constexpr int kLmXchDoubles = 16 * 17;                        // split exchange: one component at a time
+constexpr int kLmRawBytesPcm = (2 * kLmPad + 16000) * 2, kLmRawBytesF32 = (2 * kLmPad + 16000) * 4;
+constexpr int kLmTileBytes = ((63 * kLmPStride * 4 + 15) / 16) * 16;
+constexpr int kLmXchBytes = kLmTeams * kLmXchDoubles * 8;
+static_assert(kLmXchBytes >= kPlaneRows * 63 * 4, "the mel tile reuses the exchange space");
+static_assert(kLmTileBytes >= 2 * kPlaneRows * 63 * 4, "the two delta tiles reuse the power tile");
+
+template <bool PCM>
+__global__ void __launch_bounds__(kLmThreads, 1) k_logmel_fused(const void* __restrict__ wav, int n, Geometry g, Tables tb,
+                                                               float* __restrict__ stft_db, float* __restrict__ mel3) {
+    extern __shared__ __align__(16) unsigned char lm_smem[];
+    __shared__ double dscratch[32];
+    __shared__ float fscratch[32];
+    __shared__ __align__(8) uint64_t bar;
+    constexpr int kRawBytes = PCM ? kLmRawBytesPcm : kLmRawBytesF32;
+    constexpr int kSampleBytes = PCM ? 2 : 4;
+    unsigned char* raw = lm_smem;
+    float* tile = reinterpret_cast<float*>(lm_smem + kRawBytes);                       // [T][257] |X|^2, later d1 | d2
+    double* xch_all = reinterpret_cast<double*>(lm_smem + kRawBytes + kLmTileBytes);   // exchange, later mel [128][T]
+    float* melP = reinterpret_cast<float*>(xch_all);
+    const int tid = threadIdx.x, lane = tid & 31, h = lane & 15, team = tid >> 4;
+    const int partner = (lane & 16) | ((16 - h) & 15);
+    const int T = 63, L = 16000, NP = kPlaneRows * T;
+    const uint32_t seg_bytes = (uint32_t)L * kSampleBytes;
+
+    // permanent zero pads; barrier; first copy
+    for (int i = tid; i < kLmPad * kSampleBytes / 4; i += kLmThreads) {
+        reinterpret_cast<uint32_t*>(raw)[i] = 0u;
+        reinterpret_cast<uint32_t*>(raw + kLmPad * kSampleBytes + seg_bytes)[i] = 0u;
+    }
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    auto issue = [&](int b) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic reads of the buffer precede the async write
+        mbar_expect_tx(&bar, seg_bytes);
+        const unsigned char* src = static_cast<const unsigned char*>(wav) + (size_t)b * seg_bytes;
+        for (uint32_t off = 0; off < seg_bytes; off += 32000u) {
+            const uint32_t len = seg_bytes - off < 32000u ? seg_bytes - off : 32000u;
+            tma_bulk_g2s(raw + kLmPad * kSampleBytes + off, src + off, len, &bar);
+        }
+    };
+    if (tid == 0 && (int)blockIdx.x < n) issue(blockIdx.x);
+
+    // inter-stage twiddles from the [k1][h] table (L1-resident, 4 KB): registers are the 512-thread CTA's scarce resource
+    const double2* twa = tb.twa256 + h;
+    const double2 wp = __ldg(tb.ptw512 + h);
+    const double2 wl = make_double2(wp.y, -wp.x);                         // -i * exp(-2 pi i h / 512)
+    const double2* win2 = reinterpret_cast<const double2*>(tb.hann512);
+    double* xr = xch_all + (size_t)team * kLmXchDoubles;
+    // 2 X[k] comes out of the split; complex64 = float32 rounding of X[k] (x 2^-15 for PCM16 samples: exact)
+    const float out_scale = PCM ? 0.5f / 32768.0f : 0.5f;
+    uint32_t parity = 0;
+
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+        // ---- FFT phase
+        float pmax = 0.f;
+        for (int t = team; t < T + (T & 1); t += kLmTeams) {              // both teams of a warp iterate together (shuffles)
+            const bool valid = t < T;
+            const int tt = valid ? t : T - 1;
+            double2 a[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int m = h + 16 * j;
+                const double2 w = __ldg(win2 + m);
+                double x0, x1;
+                if (PCM) {
+                    const uint32_t pr = *reinterpret_cast<const uint32_t*>(raw + ((size_t)tt * 256 + 2 * m) * 2);
+                    const int s0 = (int)(short)(pr & 0xffffu), s1 = (int)pr >> 16;
+                    x0 = __hiloint2double(0x43300000, s0 ^ (int)0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
+                    x1 = __hiloint2double(0x43300000, s1 ^ (int)0x80000000) - 4503601774854144.0;
+                } else {
+                    const float2 v = *reinterpret_cast<const float2*>(raw + ((size_t)tt * 256 + 2 * m) * 4);
+                    x0 = (double)v.x;
+                    x1 = (double)v.y;
+                }
+                a[j] = make_double2(x0 * w.x, x1 * w.y);
+            }
+            team_fft_split<16>(a, twa, 16, xr, h);
+            float* row = tile + tt * kLmPStride;
+            // every conjugate pair once (fft_reg.cuh::team_rsplit_pairs); bin 256 = X[N] is real: |.| without the hypot
+            auto emit = [&](int k, double2 t2) {
+                const float re = out_scale * (float)t2.x, im = out_scale * (float)t2.y;
+                const float v = k == 256 ? fabsf(re) : c64_abs_f32(re, im);
+                const float p = __fmul_rn(v, v);
+                if (valid) { row[k] = p; pmax = fmaxf(pmax, p); }
+            };
+            team_rsplit_pairs<16, 0>(a, wl, h, partner, emit);
+        }
+        const float mx = block_max(pmax, fscratch);               // has the barrier that ends the FFT phase
+        __syncthreads();
+        if (tid == 0 && b + (int)gridDim.x < n) issue(b + gridDim.x);   // the raw buffer is free: prefetch the next segment
+
+        // ---- log-power STFT (process.py:32-33 semantics of power_to_db: ref = max, amin 1e-10, top_db 80)
+        if (stft_db) {
+            const float ref_db = (float)(10.0 * log10((double)fmaxf(1e-10f, mx)));
+            const float vmax = __fsub_rn(__fmul_rn(10.0f, log10f(fmaxf(1e-10f, mx))), ref_db);
+            const float floor_db = __fsub_rn(vmax, 80.0f);
+            float* o = stft_db + (size_t)b * 257 * T;
+            auto db_at = [&](int i) {
+                const int k = i / T, t = i - k * T;
+                return fmaxf(__fsub_rn(__fmul_rn(10.0f, log10f(fmaxf(1e-10f, tile[t * kLmPStride + k]))), ref_db), floor_db);
+            };
+            const int total = 257 * T;
+            const int head = (int)((4 - ((reinterpret_cast<uintptr_t>(o) >> 2) & 3)) & 3);      // floats up to 16-byte alignment
+            const int body4 = (total - head) >> 2;
+            if (tid < head) o[tid] = db_at(tid);
+            for (int v = tid; v < body4; v += kLmThreads) {
+                const int i = head + 4 * v;
+                __stcs(reinterpret_cast<float4*>(o + i), make_float4(db_at(i), db_at(i + 1), db_at(i + 2), db_at(i + 3)));
+            }
+            for (int i = head + 4 * body4 + tid; i < total; i += kLmThreads) o[i] = db_at(i);
+        }
+
+        // ---- mel-A filterbank on the power tile (apply_bank<128> with the tile as its source: same taps, same order)
+        {
+            const BankDev& bank = tb.mel_a;
+            const int half = (T + 1) >> 1, total = kPlaneRows * half;
+            for (int idx = tid; idx < total; idx += kLmThreads) {
+                const int m = idx & (kPlaneRows - 1), t0 = idx / kPlaneRows, t1 = t0 + half;
+                const bool live1 = t1 < T;
+                const int s0 = __ldg(bank.start + m), c = __ldg(bank.count + m);
+                const int cmax = __reduce_max_sync(0xffffffffu, c);
+                const float* src0 = tile + t0 * kLmPStride;
+                const float* src1 = tile + (live1 ? t1 : t0) * kLmPStride;
+                const float* wt = bank.wt + m;
+                float acc0 = 0.f, acc1 = 0.f;
+                for (int j = 0; j < cmax; ++j) {
+                    const int k = min(s0 + j, 256);
+                    const float w = __ldg(wt + j * kPlaneRows);
+                    acc0 = fmaf(w, src0[k], acc0);
+                    acc1 = fmaf(w, src1[k], acc1);
+                }
+                melP[m * T + t0] = acc0;
+                if (live1) melP[m * T + t1] = acc1;
+            }
+        }
+        __syncthreads();                                           // mel tile complete; every reader of the power tile is done
+        power_to_db_inplace(melP, NP, true, fscratch);            // process.py:33
+        float* d1s = tile;                                         // the power tile is dead: park the raw deltas there
+        float* d2s = tile + NP;
+        double s0 = 0, q0 = 0, s1, q1, s2, q2;
+        {
+            double sums[4];
+            delta_rows_block(melP, kPlaneRows, T, d1s, d2s, sums);
+            s1 = sums[0]; q1 = sums[1]; s2 = sums[2]; q2 = sums[3];
+        }
+        for (int i = tid; i < NP; i += kLmThreads) {
+            const double v0 = (double)melP[i];
+            s0 += v0; q0 += v0 * v0;
+        }
+        block_sum2(s0, q0, dscratch);
+        block_sum2(s1, q1, dscratch);
+        block_sum2(s2, q2, dscratch);
+        const ZTerm z0 = make_zterm(s0, q0, (double)NP), z1 = make_zterm(s1, q1, (double)NP),
+                    z2 = make_zterm(s2, q2, (double)NP);
+        float4* o0 = reinterpret_cast<float4*>(mel3 + (size_t)b * 3 * NP);
+        float4* o1 = o0 + NP / 4;
+        float4* o2 = o1 + NP / 4;
+        for (int v = tid; v < NP / 4; v += kLmThreads) {           // every thread reads back what it wrote above or what
+            const float4 a = reinterpret_cast<const float4*>(melP)[v];     // the block_sum2 barriers have published
+            const float4 c1 = reinterpret_cast<const float4*>(d1s)[v], c2 = reinterpret_cast<const float4*>(d2s)[v];
+            __stcs(o0 + v, make_float4(z0(a.x), z0(a.y), z0(a.z), z0(a.w)));
+            __stcs(o1 + v, make_float4(z1(c1.x), z1(c1.y), z1(c1.z), z1(c1.w)));
+            __stcs(o2 + v, make_float4(z2(c2.x), z2(c2.y), z2(c2.z), z2(c2.w)));
+        }
+        __syncthreads();                                           // tiles are rewritten by the next segment's FFT phase
+    }
+}
+
+bool launch_logmel_fused(const void* wav, int wav_dtype, int n, const Geometry& g, const Tables& tb, float* stft_db,
+                         float* mel3, cudaStream_t st) {
+    static const char* env = std::getenv("BPC_FUSED_LOGMEL");
+    if (g.long_mode || g.T != 63 || g.L != 16000 || (env && env[0] == '0')) return false;
+    if ((reinterpret_cast<uintptr_t>(wav) | reinterpret_cast<uintptr_t>(mel3)) & 15) return false;
+    static PerDeviceOnce once;
+    static int sms = 148;
+    const int bytes_pcm = kLmRawBytesPcm + kLmTileBytes + kLmXchBytes, bytes_f32 = kLmRawBytesF32 + kLmTileBytes + kLmXchBytes;
+    once.run([&] {
+        cudaFuncSetAttribute(k_logmel_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_pcm);
+        cudaFuncSetAttribute(k_logmel_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_f32);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    });
+    const int grid = n < sms ? n : sms;
+    if (grid <= 0) return true;
+    if (wav_dtype == BPC_WAV_PCM16) k_logmel_fused<true><<<grid, kLmThreads, bytes_pcm, st>>>(wav, n, g, tb, stft_db, mel3);
+    else k_logmel_fused<false><<<grid, kLmThreads, bytes_f32, st>>>(wav, n, g, tb, stft_db, mel3);
+    note_launch();
+    return true;
 }
 
 }  // namespace bpc

@@ -8,6 +8,11 @@
 // Precision: 3xTF32 -- every float32 operand is split into hi = tf32(x) and lo = tf32(x - hi) and the product is
 // accumulated as lo*hi + hi*lo + hi*hi in the FP32 accumulator, which recovers float32-level products (a single TF32
 // pass has 10 mantissa bits: 1e-3 relative, two orders beyond the parity budget of this stage).
+// The TMEM accumulator adds with truncation, a bias that grows with the number of K steps when the products share a
+// sign -- and row 0 of C1 (the mel-axis DC term, ~ -600 dB-units in every frame) times the time-axis DC basis is exactly
+// that: r02 measured 16 float32 ulps at T = 188 and 48 at T = 313.  So the row means of C1 are removed before the product
+// (k_tc_row_means; the residual rows have mixed signs) and put back exactly in the epilogue as mean * sum_t D[u][t]
+// (a [T] table; zero up to rounding for every u > 0).
 #include <cstdlib>
 #include "kernels.cuh"
 
@@ -148,6 +153,18 @@ __global__ void __launch_bounds__(128) k_modspec_time_tc(Geometry g, Tables tb, 
 constexpr int kTcStages = 3;
 constexpr int kTcStageFloats = 4 * kTcOpFloats;                  // A hi, A lo, B hi, B lo
 
+// one warp per row of A: float32 mean (FP64 sum) of the T values of a C1 row
+__global__ void __launch_bounds__(128) k_tc_row_means(Geometry g, Workspace ws, int rows_total, size_t role0_off) {
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31, T = g.T;
+    if (row >= rows_total) return;
+    const int seg = row / 40, r = row - seg * 40;
+    const float* src = ws.scratch + (size_t)seg * ws.scratch_stride + role0_off + (size_t)(kPlaneRows + r) * T;
+    double acc = 0.0;
+    for (int t = lane; t < T; t += 32) acc += (double)src[t];
+    acc = warp_sum(acc);
+    if (lane == 0) ws.tc_mean[row] = (float)(acc / (double)T);
+}
+
 // rows of the operand: A (is_a): row m = segment m / 40, mel-DCT row m % 40 of C1 in the scratch regions; B: row u of D
 __global__ void __launch_bounds__(128) k_tc_prep_tiles(Geometry g, Tables tb, Workspace ws, int is_a, int rows_total,
                                                        size_t role0_off, uint32_t* __restrict__ out) {
@@ -164,13 +181,14 @@ __global__ void __launch_bounds__(128) k_tc_prep_tiles(Geometry g, Tables tb, Wo
     }
     uint32_t* hi = out + ((size_t)(rt * KB + kb) * 2) * kTcOpFloats;
     uint32_t* lo = hi + kTcOpFloats;
+    const float mean = (is_a && src) ? ws.tc_mean[row] : 0.f;
 #pragma unroll
     for (int c = 0; c < kTcK / 4; ++c) {                          // one 16-byte K chunk per store: coalesced across rows
         uint32_t h[4], l[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int k = kb * kTcK + 4 * c + q;
-            const float x = (src && k < T) ? src[k] : 0.f;
+            const float x = (src && k < T) ? __fsub_rn(src[k], mean) : 0.f;
             h[q] = tf32_rna(x);
             l[q] = tf32_rna(x - __uint_as_float(h[q]));
         }
@@ -180,7 +198,7 @@ __global__ void __launch_bounds__(128) k_tc_prep_tiles(Geometry g, Tables tb, Wo
     }
 }
 
-__global__ void __launch_bounds__(128, 1) k_modspec_time_tc_pipe(Geometry g, Workspace ws, const uint32_t* __restrict__ a_tiles,
+__global__ void __launch_bounds__(128, 1) k_modspec_time_tc_pipe(Geometry g, Tables tb, Workspace ws, const uint32_t* __restrict__ a_tiles,
                                                                  const uint32_t* __restrict__ b_tiles, int n_seg, size_t role0_off) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* stage0 = reinterpret_cast<uint32_t*>(smem_raw);
@@ -238,9 +256,11 @@ __global__ void __launch_bounds__(128, 1) k_modspec_time_tc_pipe(Geometry g, Wor
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int mrow = mt * kTcM + warp * 32 + lane, n0 = nt * kTcN;
     float* c_row = nullptr;
+    float mean = 0.f;
     if (mrow < m_total) {
         const int seg = mrow / 40, r = mrow - seg * 40;
         c_row = ws.scratch + (size_t)seg * ws.scratch_stride + role0_off + (size_t)(kPlaneRows + 40 + r) * T;
+        mean = ws.tc_mean[mrow];
     }
 #pragma unroll 1
     for (int c = 0; c < kTcN; c += 8) {
@@ -253,7 +273,8 @@ __global__ void __launch_bounds__(128, 1) k_modspec_time_tc_pipe(Geometry g, Wor
         if (c_row) {
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-                if (n0 + c + q < T) c_row[n0 + c + q] = __uint_as_float(v[q]);
+                if (n0 + c + q < T)                                // the row mean comes back: mean * sum_t D[u][t]
+                    c_row[n0 + c + q] = __fmaf_rn(mean, __ldg(tb.dct_colsum + n0 + c + q), __uint_as_float(v[q]));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -287,9 +308,10 @@ void launch_modspec_time_tc(int n, const Geometry& g, const Tables& tb, const Wo
         note_launch();
         return;
     }
+    k_tc_row_means<<<(n * 40 + 3) / 4, 128, 0, st>>>(g, ws, n * 40, role0_off);
     k_tc_prep_tiles<<<dim3(KB, MT), 128, 0, st>>>(g, tb, ws, 1, n * 40, role0_off, ws.tc_a);
-    k_modspec_time_tc_pipe<<<dim3(NT, MT), 128, bytes2, st>>>(g, ws, ws.tc_a, tb.dct_tiles, n, role0_off);
-    note_launch(2);
+    k_modspec_time_tc_pipe<<<dim3(NT, MT), 128, bytes2, st>>>(g, tb, ws, ws.tc_a, tb.dct_tiles, n, role0_off);
+    note_launch(3);
 }
 
 // D's hi / lo tiles, once per handle (after dct_time_n is uploaded)

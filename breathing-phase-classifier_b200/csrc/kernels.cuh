@@ -23,12 +23,14 @@ struct Tables {
     const double2* ptw512;        // exp(-2 pi i k / 512),  k <= 256
     const double2* ptw2048;       // exp(-2 pi i k / 2048), k <= 1024
     const double2* twa1024;       // [k1][h] = exp(-2 pi i h k1 / 1024), 32 x 32: inter-stage twiddles of team_fft<32>
+    const double2* twa256;        // [k1][h] = exp(-2 pi i h k1 / 256), 16 x 16: the same for team_fft<16> (k_logmel_fused)
     // filterbanks
     BankDev mel_a, mel_b, mel_c, mel_d;
     const float* dct_mel;         // [40, 128]
     const float* dct_time;        // [T, T]  transposed: [t][u]
     const float* dct_time_n;      // [T, T]  [u][t] (K-major B operand of the tensor-core time DCT; long mode only)
     const uint32_t* dct_tiles;    // the same matrix split into tf32 hi / lo halves, pre-tiled in the canonical UMMA layout
+    const float* dct_colsum;      // [T] sum_t D[u][t] (long mode: puts the removed row means back, k_tc.cu)
     const float* chroma;          // [100, 12, 257]
     const double* hist_edges;     // [101]
     // CQT
@@ -65,6 +67,7 @@ struct Workspace {            // per chunk of `cap` segments
     float* chroma_min;        // [cap, 2]   min of the normalised chroma_stft / chroma_cens rows
     int* ints;                // [cap, 2]   n_peaks, first-min index
     uint32_t* tc_a;           // long mode: C1 split into tf32 hi / lo tiles for the tensor-core time DCT (k_tc.cu)
+    float* tc_mean;           // long mode: [cap * 40] row means of C1, removed before the tensor-core product (k_tc.cu)
     double* stats_acc;        // [(9 + S), 5] dataset statistics accumulated by the producers (1 s mode; nullptr: k_stats does it)
     float* scratch;           // [cap, scratch_stride]  long mode: what the 1 s kernels keep in shared memory
     size_t scratch_stride;
@@ -100,6 +103,9 @@ void launch_spec512_consumers(int n, const Geometry& g, const Tables& tb, const 
                               float* scalars, int32_t* status, bool with_chroma, cudaStream_t st);
 void launch_stft_db(int n, const Geometry& g, const Workspace& ws, float* stft_db, cudaStream_t st);
 void launch_logmel_only(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* mel3, cudaStream_t st);
+// BASELINE config 2 in one kernel (1 s mode, L_in == expected_len, 16-byte aligned buffers); false: use the staged path
+bool launch_logmel_fused(const void* wav, int wav_dtype, int n, const Geometry& g, const Tables& tb, float* stft_db,
+                         float* mel3, cudaStream_t st);
 void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
                      float* scalars, cudaStream_t st);
 void launch_seg2048(int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats, float* scalars,
