@@ -391,6 +391,18 @@ int build_tables(bpc_handle* h) {
     int rc;
     if ((rc = upload(h, hann_periodic(512), &tb.hann512))) return rc;
     if ((rc = upload(h, hann_periodic(2048), &tb.hann2048))) return rc;
+    {
+        std::vector<double> hw = hann_periodic(2048);
+        for (double& v : hw) v *= 0.5;
+        if ((rc = upload(h, hw, &tb.hann2048h))) return rc;
+        std::vector<double2> t(544);
+        for (int k = 0; k < 544; ++k) {
+            const double th = 2.0 * kPi * double(k) / 2048.0;
+            const double wr = -std::sin(th), wi = -std::cos(th);          // -i exp(-i th)
+            t[k] = k < 256 ? make_double2(wi, wr / wi) : make_double2(wr, wi / wr);
+        }
+        if ((rc = upload(h, t, &tb.rs2048))) return rc;
+    }
     if ((rc = upload(h, hann_periodic(384), &tb.hann384))) return rc;
     if ((rc = upload(h, hamming_sym(400), &tb.hamming400))) return rc;
     if ((rc = upload(h, twiddles(256, 256), &tb.tw256))) return rc;

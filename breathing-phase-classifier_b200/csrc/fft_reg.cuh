@@ -101,6 +101,78 @@ BPC_HD constexpr int bitrev(int k) {
     return r;
 }
 
+// ------------------------------------------------------------------------------------ r02: decimation in time, FMA form
+// Same contract as DifR (natural-order input, a[OFF + S * bitrev_R(k)] = X[k] on return), but the twiddle is applied
+// BEFORE the butterfly, y = u +/- w v, and factored as w = c (1 + i t) (or c (t + i) when |Im w| > |Re w|) with
+// compile-time c and t = tan / cot of the angle (Linzer-Feig): p = v (1 + i t) is two FMAs, u +/- c p four more --
+// six FP64 instructions per butterfly instead of the eight of (u - v) w (4 DADD + 2 DMUL + 2 DFMA), all of them FMAs.
+// Radix 32: 388 instead of 456 FP64 instructions per lane and transform.  |t| <= 1, so nothing is amplified.
+template <int R, int OFF, int S>
+struct DitR {
+    template <int K>
+    static BPC_HD void bfly(double2* a) {
+        constexpr int pe = OFF + 2 * S * bitrev<R / 2>(K), po = pe + S;
+        constexpr int q = (K * (64 / R)) & 63;              // w = exp(-2 pi i q / 64), q in [0, 32)
+        const double2 u = a[pe], v = a[po];
+        if constexpr (q == 0) {
+            a[pe] = c_add(u, v);
+            a[po] = c_sub(u, v);
+        } else if constexpr (q == 16) {                     // w = -i: w v = (v.y, -v.x)
+            a[pe] = make_double2(u.x + v.y, u.y - v.x);
+            a[po] = make_double2(u.x - v.y, u.y + v.x);
+        } else if constexpr (q == 8) {                      // w = c (1 - i): w v = c (v.x + v.y, v.y - v.x)
+            constexpr double c = cos64(8);
+            const double px = v.x + v.y, py = v.y - v.x;
+            a[pe] = make_double2(fma(c, px, u.x), fma(c, py, u.y));
+            a[po] = make_double2(fma(-c, px, u.x), fma(-c, py, u.y));
+        } else if constexpr (q == 24) {                     // w = -c (1 + i): w v = -c (v.x - v.y, v.x + v.y)
+            constexpr double c = cos64(8);
+            const double px = v.x - v.y, py = v.x + v.y;
+            a[pe] = make_double2(fma(-c, px, u.x), fma(-c, py, u.y));
+            a[po] = make_double2(fma(c, px, u.x), fma(c, py, u.y));
+        } else {
+            constexpr double wr = cos64(q), wi = -sin64(q);
+            if constexpr ((wr < 0 ? -wr : wr) >= (wi < 0 ? -wi : wi)) {
+                constexpr double t = wi / wr;               // w = wr (1 + i t)
+                const double px = fma(-t, v.y, v.x), py = fma(t, v.x, v.y);
+                a[pe] = make_double2(fma(wr, px, u.x), fma(wr, py, u.y));
+                a[po] = make_double2(fma(-wr, px, u.x), fma(-wr, py, u.y));
+            } else {
+                constexpr double t = wr / wi;               // w = wi (t + i)
+                const double px = fma(t, v.x, -v.y), py = fma(t, v.y, v.x);
+                a[pe] = make_double2(fma(wi, px, u.x), fma(wi, py, u.y));
+                a[po] = make_double2(fma(-wi, px, u.x), fma(-wi, py, u.y));
+            }
+        }
+    }
+    template <int K>
+    static BPC_HD void loop(double2* a) {
+        if constexpr (K < R / 2) {
+            bfly<K>(a);
+            loop<K + 1>(a);
+        }
+    }
+    static BPC_HD void run(double2* a) {
+        DitR<R / 2, OFF, 2 * S>::run(a);
+        DitR<R / 2, OFF + S, 2 * S>::run(a);
+        loop<0>(a);
+    }
+};
+template <int OFF, int S>
+struct DitR<1, OFF, S> {
+    static BPC_HD void run(double2*) {}
+};
+
+// The register DFT every team transform below uses (BPC_FFT_DIF=1 selects the r01 decimation-in-frequency form for A/B runs)
+template <int R>
+BPC_HD void reg_dft(double2* a) {
+#ifdef BPC_FFT_DIF
+    DifR<R, 0>::run(a);
+#else
+    DitR<R, 0, 1>::run(a);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------ team FFT
 // N = R * R points, a team of R lanes (lane id h in [0, R)), R points per lane.
 //   in : a[j]            = x[h + R j]
@@ -114,7 +186,7 @@ BPC_HD constexpr int bitrev(int k) {
 // [k1][h] (tw = table + h, tws = R).
 template <int R>
 BPC_HD void team_fft_stage_a(double2* a, const double2* tw, int tws, double2* xch, int h) {
-    DifR<R, 0>::run(a);
+    reg_dft<R>(a);
 #pragma unroll
     for (int k1 = 0; k1 < R; ++k1) {
         double2 v = a[bitrev<R>(k1)];
@@ -126,7 +198,7 @@ template <int R>
 BPC_HD void team_fft_stage_b(double2* a, const double2* xch, int h) {
 #pragma unroll
     for (int j = 0; j < R; ++j) a[j] = xch[h * (R + 1) + j];
-    DifR<R, 0>::run(a);
+    reg_dft<R>(a);
 }
 
 // ------------------------------------------------------------------------------- real-input split (rfft of 2N reals)
@@ -153,7 +225,7 @@ __device__ __forceinline__ void team_fft(double2* a, const double2* tw, int tws,
 #pragma unroll
     for (int j = 0; j < R; ++j) a[j] = xch[h * (R + 1) + j];
     __syncwarp();                       // the buffer may be rewritten (next frame) once every lane has read its row
-    DifR<R, 0>::run(a);
+    reg_dft<R>(a);
 }
 
 // Same transform with the exchange done in two rounds (real parts, then imaginary parts) through a buffer of
@@ -161,7 +233,7 @@ __device__ __forceinline__ void team_fft(double2* a, const double2* tw, int tws,
 // (k_frame2048: 16.9 KB per warp left the L1 ~50 KB and a 68 % hit rate).  Same wavefront count, 2 R more instructions.
 template <int R>
 __device__ __forceinline__ void team_fft_split(double2* a, const double2* tw, int tws, double* xr, int h) {
-    DifR<R, 0>::run(a);
+    reg_dft<R>(a);
 #pragma unroll
     for (int k1 = 1; k1 < R; ++k1) a[bitrev<R>(k1)] = c_mul(a[bitrev<R>(k1)], tw[k1 * tws]);
 #pragma unroll
@@ -176,7 +248,7 @@ __device__ __forceinline__ void team_fft_split(double2* a, const double2* tw, in
 #pragma unroll
     for (int j = 0; j < R; ++j) a[j].y = xr[h * (R + 1) + j];
     __syncwarp();                       // the buffer may be rewritten once every lane has read its row
-    DifR<R, 0>::run(a);
+    reg_dft<R>(a);
 }
 
 // Real-input split over bins k = h + R k2, k2 in [K2, K2HI]: calls emit(k, 2 X[k]).  `partner` is the warp lane that

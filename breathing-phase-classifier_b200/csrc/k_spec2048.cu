@@ -101,32 +101,36 @@ __device__ __forceinline__ void warp_band_minmax(const float* row, int lo, int l
 }
 
 // ================================================================================================ k_frame2048
-// One warp per frame: Hann * samples -> team_fft<32> (fft_reg.cuh: 32 lanes x 32 register-resident complex points, one
-// shared-memory exchange) -> real split -> |X| row (float32, 1025 bins) in the same shared memory -> every per-frame
-// consumer of that row.  Nothing but the per-frame results leaves the SM (v1 wrote the 259 KB/segment |STFT2048|
-// workspace to HBM and read it back in a second kernel); the even (hop-512) frames additionally store their row for
-// k_even2048.
-// Instruction fetch: the loop body is ~95 KB of straight-line SASS and only runs at speed while the warps of an SM walk
-// it in lock-step (every frame costs the same, so they do).  r01 v30-v32 moved the hop-512 work in here: the even
-// frames then took longer than the odd ones, the warps drifted apart, and 11 of 12 issue slots went to "no
-// instruction" stalls (3.2 -> 9.8 ms); with a barrier per frame it ran at 3.7 ms -- slower than the two kernels.
-// (v34 also tried k_even2048 as one warp per staged row with a parallel exact-prefix rolloff: 0.50 vs 0.48 ms, dropped.)
-constexpr int kF2Warps = 4;
+// One WARP (= one 32-thread CTA) per frame: Hann * samples -> team_fft<32> (fft_reg.cuh: 32 lanes x 32 register-resident
+// complex points, one shared-memory exchange) -> real split -> |X| row (float32, 1025 bins) in the same shared memory ->
+// every per-frame consumer of that row.  Nothing but the per-frame results leaves the SM; the even (hop-512) frames
+// additionally store their row for k_even2048.
+// r02 rewrite (r01: 7200 warp instructions per frame, 28 % of them FP64, 168 registers with spills):
+//   * a CTA is ONE warp: the frame index depends on blockIdx only, so the compiler knows that every shuffle / barrier
+//     is convergent (the four-warp CTAs compiled each of them as WARPSYNC.COLLECTIVE + ENDCOLLECTIVE: 630 of 8200
+//     instructions of the loop body);
+//   * decimation-in-time register DFTs with six-FMA butterflies (DitR), the real split once per conjugate pair with
+//     the twiddle factored the same way (ten instead of twenty FP64 instructions per bin pair, table rs2048), the
+//     factor 1/2 of the split folded into the window table;
+//   * spectral moments with compile-time weights (sum m, sum i m, sum i^2 m per lane; k = lane + 32 i is put back
+//     once per frame).
+// Instruction fetch: the loop body is straight-line SASS that only runs at speed while the warps of an SM walk it in
+// lock-step (every frame costs the same, so they do).  r01 v30-v32 moved the hop-512 work in here: the even frames then
+// took longer than the odd ones, the warps drifted apart, and 11 of 12 issue slots went to "no instruction" stalls.
 constexpr int kF2RowBytes = 32 * 33 * 8;             // exchange buffer (one component at a time), later the |X| row (1028 floats)
-
-__global__ void __launch_bounds__(32 * kF2Warps, 3) k_frame2048(const float* __restrict__ y, Geometry g, Tables tb,
+template <int CTAS_PER_SM>                          // 12: 168 registers, no spills; 16: 128 registers (A/B: BPC_F2_CTAS)
+__global__ void __launch_bounds__(32, CTAS_PER_SM) k_frame2048(const float* __restrict__ y, Geometry g, Tables tb,
                                                                  Workspace ws, int total_frames) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* xch = reinterpret_cast<double*>(smem_raw + (size_t)warp * kF2RowBytes);
-    float* row = reinterpret_cast<float*>(xch);
+    __shared__ __align__(16) unsigned char smem_raw[kF2RowBytes];
+    const int lane = threadIdx.x;
+    double* xch = reinterpret_cast<double*>(smem_raw);
+    float* row = reinterpret_cast<float*>(smem_raw);
     const int T = g.T, L = g.L, hop = g.hop, TE = (T + 1) / 2;
     const int partner = (32 - lane) & 31;
-    const double2 wp = __ldg(tb.ptw2048 + lane);
-    const double2 wl = make_double2(wp.y, -wp.x);                         // -i * exp(-2 pi i lane / 2048)
-    const double2* win2 = reinterpret_cast<const double2*>(tb.hann2048);
+    const double2* win2 = reinterpret_cast<const double2*>(tb.hann2048h);   // 0.5 * Hann: the 1/2 of the real split
     const double2* twa = tb.twa1024 + lane;                               // [k1][lane]
-    for (int f = blockIdx.x * kF2Warps + warp; f < total_frames; f += gridDim.x * kF2Warps) {
+    const double2* rs = tb.rs2048 + lane;                                 // split twiddles as (scale, tan / cot)
+    for (int f = blockIdx.x; f < total_frames; f += gridDim.x) {
         const int b = f / T, t = f - b * T;
         const float* yb = y + (size_t)b * L;
         const int g0 = t * hop - 1024;
@@ -142,43 +146,82 @@ __global__ void __launch_bounds__(32 * kF2Warps, 3) k_frame2048(const float* __r
                 a[j] = make_double2((double)v.x * w.x, (double)v.y * w.y);
             }
             team_fft_split<32>(a, twa, 32, xch, lane);
-            const double z0 = a[0].x - a[0].y;                 // lane 0: X[1024] = Re Z[0] - Im Z[0]
-            auto emit = [&](int k, double2 t2) { row[k] = c64_abs_f32(0.5f * (float)t2.x, 0.5f * (float)t2.y); };
-            team_rsplit<32, 0, 31>(a, wl, lane, partner, emit);
-            if (lane == 0) row[1024] = fabsf((float)z0);
+            // real split, every conjugate pair once: with Z = FFT_1024 of the packed frame (already halved),
+            //   s = Z[k] + conj(Z[N-k]),  d = Z[k] - conj(Z[N-k]),  p = w d,  w = -i exp(-2 pi i k / 2048),
+            //   X[k] = s + p,  X[N-k] = conj(s - p);   w = c (t + i) for k < 256 and c (1 + i t) for k >= 256.
+            const double z0re = a[0].x, z0im = a[0].y;
+#pragma unroll
+            for (int K2 = 0; K2 <= 16; ++K2) {
+                const double2 zk = a[bitrev<32>(K2)];
+                double2 zn;
+                if (K2 < 16) {
+                    const double2 src = a[bitrev<32>(31 - K2)];
+                    zn.x = __shfl_sync(0xffffffffu, src.x, partner);
+                    zn.y = __shfl_sync(0xffffffffu, src.y, partner);
+                    if (lane == 0) zn = a[bitrev<32>((32 - K2) & 31)];
+                } else {
+                    zn = zk;                                   // k = 512 (lane 0) pairs with itself
+                }
+                const double2 ct = __ldg(rs + 32 * K2);
+                const double sx = zk.x + zn.x, sy = zk.y - zn.y, dx = zk.x - zn.x, dy = zk.y + zn.y;
+                double qx, qy;
+                if (K2 < 8) { qx = fma(ct.y, dx, -dy); qy = fma(ct.y, dy, dx); }
+                else        { qx = fma(-ct.y, dy, dx); qy = fma(ct.y, dx, dy); }
+                const double x0 = fma(ct.x, qx, sx), y0 = fma(ct.x, qy, sy);
+                const double x1 = fma(-ct.x, qx, sx), y1 = fma(ct.x, qy, -sy);
+                const int k = lane + 32 * K2;
+                if (K2 < 16) {
+                    row[k] = c64_abs_f32((float)x0, (float)y0);
+                    if (K2 > 0 || lane > 0) row[1024 - k] = c64_abs_f32((float)x1, (float)y1);
+                } else if (lane == 0) {
+                    row[512] = c64_abs_f32((float)x0, (float)y0);
+                }
+            }
+            if (lane == 0) row[1024] = fabsf((float)(2.0 * (z0re - z0im)));   // X[1024] = Re Z[0] - Im Z[0] (Z halved)
         }
         __syncwarp();
         if ((t & 1) == 0) {                                    // hop-512 frame: keep the row for rolloff / tuning-36
             float4* dst = reinterpret_cast<float4*>(ws.mag_even + ((size_t)b * TE + (t >> 1)) * kMag2048Stride);
-            for (int i = lane; i < kMag2048Stride / 4; i += 32) {
-                float4 v = reinterpret_cast<const float4*>(row)[i];
-                if (i == kMag2048Stride / 4 - 1) { v.y = 0.f; v.z = 0.f; v.w = 0.f; }
-                dst[i] = v;
+#pragma unroll
+            for (int q = 0; q < (kMag2048Stride / 4 + 31) / 32; ++q) {
+                const int i = lane + 32 * q;
+                if (i < kMag2048Stride / 4) {
+                    float4 v = reinterpret_cast<const float4*>(row)[i];
+                    if (i == kMag2048Stride / 4 - 1) { v.y = 0.f; v.z = 0.f; v.w = 0.f; }
+                    dst[i] = v;
+                }
             }
         }
         // spectral_centroid / bandwidth (methods.py:59-60): moments of the L1-normalised column; flatness (:62) needs
-        // sum(log(p)): the logs of up to 17 powers (each >= 1e-10) are taken as one double-precision log of their product
-        double sm = 0.0, smk = 0.0, smk2 = 0.0, spow = 0.0, prod0 = 1.0, prod1 = 1.0;
+        // sum(log(p)): the logs of up to 17 powers (each >= 1e-10) are taken as one double-precision log of their product.
+        // Bin k = lane + 32 i: the lane accumulates sum m, sum i m, sum i^2 m with compile-time weights.
+        double sm = 0.0, s1 = 0.0, s2 = 0.0, spow = 0.0, prod0 = 1.0, prod1 = 1.0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float m = row[lane + 32 * i];
+            const double dm = (double)m;
+            sm += dm;
+            if (i > 0) { s1 = fma(dm, (double)i, s1); s2 = fma(dm, (double)(i * i), s2); }
+            const double p = (double)fmaxf(1e-10f, __fmul_rn(m, m));
+            spow += p;
+            if (i < 16) prod0 *= p; else prod1 *= p;
+        }
         {
-            double kd = (double)lane;
-#pragma unroll 4
-            for (int i = 0; i < 33; ++i) {
-                const int k = lane + 32 * i;
-                if (k < 1025) {
-                    const float m = row[k];
-                    const double dm = (double)m;
-                    sm += dm;
-                    const double t = dm * kd;
-                    smk += t;
-                    smk2 = fma(t, kd, smk2);
-                    const double p = (double)fmaxf(1e-10f, __fmul_rn(m, m));
-                    spow += p;
-                    if (i < 17) prod0 *= p; else prod1 *= p;
-                }
-                kd += 32.0;
+            const float m = lane == 0 ? row[1024] : 0.f;       // the Nyquist bin (i = 32) exists for lane 0 only
+            const double dm = (double)m;
+            sm += dm;
+            s1 = fma(dm, 32.0, s1);
+            s2 = fma(dm, 1024.0, s2);
+            if (lane == 0) {
+                const double p = (double)fmaxf(1e-10f, __fmul_rn(m, m));
+                spow += p;
+                prod1 *= p;
             }
         }
         double slog = log(prod0) + log(prod1);
+        const double dl = (double)lane;
+        const double smk = fma(32.0, s1, dl * sm);                                      // sum m k
+        const double smk2 = fma(1024.0, s2, fma(64.0 * dl, s1, dl * dl * sm));          // sum m k^2
         const double smf = smk * 7.8125, smf2 = smk2 * (7.8125 * 7.8125);
         sm = warp_sum(sm);
         const double smf_w = warp_sum(smf), smf2_w = warp_sum(smf2);
@@ -623,20 +666,23 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
 void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
                      float* scalars, cudaStream_t st) {
     static PerDeviceOnce once;
-    static int sms = 148;
+    static int sms = 148, ctas = 12;
     once.run([&] {
-        cudaFuncSetAttribute(k_frame2048, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2Warps * kF2RowBytes);
         cudaFuncSetAttribute(k_seg2048<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Seg2048Smem));
         cudaFuncSetAttribute(k_seg2048<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Seg2048Smem));
+        cudaFuncSetAttribute(k_frame2048<12>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        cudaFuncSetAttribute(k_frame2048<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 66);
+        if (const char* e = getenv("BPC_F2_CTAS")) ctas = atoi(e) >= 16 ? 16 : 12;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     });
     const int total = n * g.T;
-    // persistent: exactly the 3 CTAs per SM that fit (168 registers, 67.6 KB), each warp strides over the frames
-    int grid = (total + kF2Warps - 1) / kF2Warps;
-    if (grid > sms * 3) grid = sms * 3;
-    k_frame2048<<<grid, 32 * kF2Warps, kF2Warps * kF2RowBytes, st>>>(y, g, tb, ws, total);
+    // persistent: exactly the one-warp CTAs that fit an SM (168 registers), each striding over the frames
+    int grid = total;
+    if (grid > sms * ctas) grid = sms * ctas;
+    if (ctas == 16) k_frame2048<16><<<grid, 32, 0, st>>>(y, g, tb, ws, total);
+    else k_frame2048<12><<<grid, 32, 0, st>>>(y, g, tb, ws, total);
     note_launch();
 }
 

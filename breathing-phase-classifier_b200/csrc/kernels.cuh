@@ -19,6 +19,9 @@ struct Tables {
     // FFT
     const double* hann512;        // [512]
     const double* hann2048;       // [2048]
+    const double* hann2048h;      // [2048] 0.5 * Hann (k_frame2048: the 1/2 of the real-input split folded into the window)
+    const double2* rs2048;        // [544] split twiddle w_k = -i exp(-2 pi i k / 2048) factored for FMA butterflies:
+                                  //       (c, t) with w = c (t + i) for k < 256 and w = c (1 + i t) for k >= 256
     const double2* tw256;         // exp(-2 pi i j / 256), j < 256
     const double2* ptw512;        // exp(-2 pi i k / 512),  k <= 256
     const double2* ptw2048;       // exp(-2 pi i k / 2048), k <= 1024
