@@ -342,7 +342,7 @@ int upload_bank(bpc_handle* h, const SparseBank& b, BankDev* out) {
     if ((rc = upload(h, b.start, &s))) return rc;
     if ((rc = upload(h, b.count, &c))) return rc;
     if ((rc = upload(h, b.w, &w))) return rc;
-    std::vector<float> t((size_t)b.rows * b.width);
+    std::vector<float> t((size_t)b.rows * (b.width + 4), 0.f);      // four zero taps past the widest row: readers may unroll by 4
     for (int r = 0; r < b.rows; ++r)
         for (int j = 0; j < b.width; ++j) t[(size_t)j * b.rows + r] = b.w[(size_t)r * b.width + j];
     const float* wt;

@@ -249,10 +249,11 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
     float2* spec = S.spec[team];
     float* cqmag = S.cqmag[team];
     // long mode: phase 1 = the CQT frames of this CTA's share (grid (segment, part)), phase 2 = post-processing
-    const int t_first = 2 * warp + (LONG ? (int)blockIdx.y * kCensTeams : 0);
+    // (trip count from blockIdx only, `valid` gates the result: the shuffles and warp barriers inside are convergent)
+    const int t_first = LONG ? (int)blockIdx.y * kCensTeams : 0;
     const int t_step = kCensTeams * (LONG ? (int)gridDim.y : 1);
     for (int t0 = t_first; t0 < T && phase != 2; t0 += t_step) {
-        const int t = t0 + (lane >> 4);
+        const int t = t0 + 2 * warp + (lane >> 4);
         const bool valid = t < T;
         float csum = 0.f;                                        // lanes h < 12: chroma c = h
 #pragma unroll 1

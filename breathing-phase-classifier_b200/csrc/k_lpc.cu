@@ -7,7 +7,7 @@
 namespace bpc {
 
 constexpr int kLpcFrame = 400, kLpcShift = 160, kLpcOrder = 12, kLpcMaxFrames = 112;
-constexpr int kLpcThreads = 128;
+constexpr int kLpcThreads = 224;                     // 7 warps: the 98 frames of a 1 s segment are 14 full rounds
 constexpr int kLpcPer = 13;                            // samples per lane: 13 * 31 = 403 >= 400
 
 struct LpcSmem {
@@ -79,7 +79,7 @@ __device__ __forceinline__ void burg_all(double (&F)[kLpcPer], double (&B)[kLpcP
 // phase 0: everything (1 s).  Long mode: phase 1 = the Burg frames of this CTA's share (grid (segment, part)) into the
 // scratch region, phase 2 = statistics + plane (grid (segment)).
 template <bool LONG>
-__global__ void __launch_bounds__(kLpcThreads, 5) k_lpc(const float* __restrict__ y, Geometry g, Tables tb, Workspace ws,
+__global__ void __launch_bounds__(kLpcThreads, 3) k_lpc(const float* __restrict__ y, Geometry g, Tables tb, Workspace ws,
                                                 float* feats, int phase) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LpcSmem& S = *reinterpret_cast<LpcSmem*>(smem_raw);
@@ -89,9 +89,14 @@ __global__ void __launch_bounds__(kLpcThreads, 5) k_lpc(const float* __restrict_
     // [12, F] coefficients: shared memory (1 s: F = 98), the segment's global scratch region in long mode
     float* coef = LONG ? ws.scratch + (size_t)b * ws.scratch_stride : S.coef;
 
-    const int fr0 = LONG ? blockIdx.y * (kLpcThreads / 32) + warp : warp;
+    // The trip count depends on blockIdx only and every warp runs every iteration (warps past the last frame redo it
+    // and drop the result): the compiler can then prove that the ~200 shuffles per frame are convergent.  With
+    // `fr = warp; fr < F; fr += 4` each of them was a WARPSYNC.COLLECTIVE / ENDCOLLECTIVE pair.
+    const int frb = LONG ? blockIdx.y * (kLpcThreads / 32) : 0;
     const int frs = LONG ? gridDim.y * (kLpcThreads / 32) : kLpcThreads / 32;
-    for (int fr = fr0; fr < F_ && phase != 2; fr += frs) {
+    for (int fr_base = frb; fr_base < F_ && phase != 2; fr_base += frs) {
+        const bool fr_valid = fr_base + warp < F_;
+        const int fr = fr_valid ? fr_base + warp : F_ - 1;
         const int start = fr * kLpcShift;
         double Bv[kLpcPer], Fv[kLpcPer];
 #pragma unroll
@@ -118,7 +123,7 @@ __global__ void __launch_bounds__(kLpcThreads, 5) k_lpc(const float* __restrict_
         den = warp_sum(den);
         double a_lane = lane == 0 ? 1.0 : 0.0;
         burg_all<0>(Fv, Bv, a_lane, den, lane);
-        if (lane >= 1 && lane <= kLpcOrder) coef[(lane - 1) * F_ + fr] = (float)a_lane;
+        if (fr_valid && lane >= 1 && lane <= kLpcOrder) coef[(lane - 1) * F_ + fr] = (float)a_lane;
     }
     if (LONG && phase == 1) return;
     __syncthreads();

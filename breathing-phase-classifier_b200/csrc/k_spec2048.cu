@@ -118,8 +118,10 @@ __device__ __forceinline__ void warp_band_minmax(const float* row, int lo, int l
 // lock-step (every frame costs the same, so they do).  r01 v30-v32 moved the hop-512 work in here: the even frames then
 // took longer than the odd ones, the warps drifted apart, and 11 of 12 issue slots went to "no instruction" stalls.
 constexpr int kF2RowBytes = 32 * 33 * 8;             // exchange buffer (one component at a time), later the |X| row (1028 floats)
-template <int CTAS_PER_SM>                          // 12: 168 registers, no spills; 16: 128 registers (A/B: BPC_F2_CTAS)
-__global__ void __launch_bounds__(32, CTAS_PER_SM) k_frame2048(const float* __restrict__ y, Geometry g, Tables tb,
+// 168 registers = 12 one-warp CTAs per SM, no spills.  Measured alternatives: 128 registers (16 warps, 75 spilled
+// doubles per frame) 2.78 vs 2.71 ms; 144 registers (14 warps) 4.74 vs 2.58 ms.
+constexpr int kF2CtasPerSm = 12;
+__global__ void __launch_bounds__(32, kF2CtasPerSm) k_frame2048(const float* __restrict__ y, Geometry g, Tables tb,
                                                                  Workspace ws, int total_frames) {
     __shared__ __align__(16) unsigned char smem_raw[kF2RowBytes];
     const int lane = threadIdx.x;
@@ -136,14 +138,24 @@ __global__ void __launch_bounds__(32, CTAS_PER_SM) k_frame2048(const float* __re
         const int g0 = t * hop - 1024;
         {
             double2 a[32];
+            if (g0 >= 0 && g0 + 2048 <= L) {                   // interior frame (55 of 63): no bounds checks, one base pointer
+                const float2* src = reinterpret_cast<const float2*>(yb + g0) + lane;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int m = lane + 32 * j;
-                const int gi = g0 + 2 * m;                     // even; L is even, so the pair is in or out together
-                float2 v = make_float2(0.f, 0.f);
-                if (gi >= 0 && gi < L) v = __ldg(reinterpret_cast<const float2*>(yb + gi));
-                const double2 w = __ldg(win2 + m);
-                a[j] = make_double2((double)v.x * w.x, (double)v.y * w.y);
+                for (int j = 0; j < 32; ++j) {
+                    const float2 v = __ldg(src + 32 * j);
+                    const double2 w = __ldg(win2 + lane + 32 * j);
+                    a[j] = make_double2((double)v.x * w.x, (double)v.y * w.y);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int m = lane + 32 * j;
+                    const int gi = g0 + 2 * m;                 // even; L is even, so the pair is in or out together
+                    float2 v = make_float2(0.f, 0.f);
+                    if (gi >= 0 && gi < L) v = __ldg(reinterpret_cast<const float2*>(yb + gi));
+                    const double2 w = __ldg(win2 + m);
+                    a[j] = make_double2((double)v.x * w.x, (double)v.y * w.y);
+                }
             }
             team_fft_split<32>(a, twa, 32, xch, lane);
             // real split, every conjugate pair once: with Z = FFT_1024 of the packed frame (already halved),
@@ -178,6 +190,11 @@ __global__ void __launch_bounds__(32, CTAS_PER_SM) k_frame2048(const float* __re
                 }
             }
             if (lane == 0) row[1024] = fabsf((float)(2.0 * (z0re - z0im)));   // X[1024] = Re Z[0] - Im Z[0] (Z halved)
+            // words 1025 .. 1091 follow the row: the mel-D loop below reads up to 51 words past a band's start with
+            // zero weights, and what the exchange left there may be a NaN pattern
+            row[1025 + lane] = 0.f;
+            row[1057 + lane] = 0.f;
+            if (lane < 3) row[1089 + lane] = 0.f;
         }
         __syncwarp();
         if ((t & 1) == 0) {                                    // hop-512 frame: keep the row for rolloff / tuning-36
@@ -264,12 +281,19 @@ __global__ void __launch_bounds__(32, CTAS_PER_SM) k_frame2048(const float* __re
             const int m = lane + 32 * i;
             const int s0 = __ldg(tb.mel_d.start + m), c = __ldg(tb.mel_d.count + m);
             const int cmax = __reduce_max_sync(0xffffffffu, c);
-            const float* wt = tb.mel_d.wt + m;
+            const float* wp = tb.mel_d.wt + m;                   // [tap][mel], zero beyond a row's count and 4 zero taps
+            const float* rp = row + s0;                          // past the widest row (upload_bank)
             float acc = 0.f;
-            for (int j = 0; j < cmax; ++j) {
-                const float w = __ldg(wt + j * kPlaneRows);          // zero beyond this row's count
-                const float mv = row[min(s0 + j, 1024)];
-                acc = fmaf(w, __fmul_rn(mv, mv), acc);
+            for (int j = 0; j < cmax; j += 4) {                  // same taps, same order as one tap per iteration
+                const float w0 = __ldg(wp), w1 = __ldg(wp + kPlaneRows), w2 = __ldg(wp + 2 * kPlaneRows),
+                            w3 = __ldg(wp + 3 * kPlaneRows);
+                const float m0 = rp[0], m1 = rp[1], m2 = rp[2], m3 = rp[3];
+                acc = fmaf(w0, __fmul_rn(m0, m0), acc);
+                acc = fmaf(w1, __fmul_rn(m1, m1), acc);
+                acc = fmaf(w2, __fmul_rn(m2, m2), acc);
+                acc = fmaf(w3, __fmul_rn(m3, m3), acc);
+                wp += 4 * kPlaneRows;
+                rp += 4;
             }
             md[m] = acc;
         }
@@ -412,7 +436,9 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
     const float floorm = __fsub_rn(__fsub_rn(lmax, ref_db), 80.0f);         // ref = max variant
     for (int j = tid; j < T + 2 * 192 + 8; j += NT) V.onset[j] = 0.f;
     __syncthreads();
-    for (int t = warp; t < T - 1; t += NW) {
+    for (int tf0 = 0; tf0 < T - 1; tf0 += NW) {         // uniform trip count: convergent warp reductions
+        const bool tlive = tf0 + warp < T - 1;
+        const int t = tlive ? tf0 + warp : T - 2;
         double f2 = 0.0, on = 0.0;
         for (int m = lane; m < kPlaneRows; m += 32) {
             const float l0 = V.melD[t * kPlaneRows + m], l1 = V.melD[(t + 1) * kPlaneRows + m];
@@ -424,7 +450,7 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
         }
         f2 = warp_sum(f2);
         on = warp_sum(on);
-        if (lane == 0) {
+        if (lane == 0 && tlive) {
             V.flux[t] = sqrtf((float)f2);
             // onset_env = pad(mean over mels, (1 + 2048 // (2 * 256), 0))[:T]; stored at offset 192 (left tempogram pad)
             if (t + 5 < T) V.onset[192 + t + 5] = (float)(on / (double)kPlaneRows);
@@ -466,15 +492,18 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
     // 4j .. 4j + 3.
     const int gidx = tid / 96, j = tid - gidx * 96, l0 = 4 * j;
     float* F = S.frame[gidx];
+    // trip count from blockIdx only; a group past the last frame redoes frame T - 1 and drops the result, so that the
+    // warp reductions below are provably convergent (plain SHFL)
     const int t_step = kSegGroups * (LONG ? (int)gridDim.y : 1);
-    for (int t = gidx + (LONG ? kSegGroups * (int)blockIdx.y : 0); t < T + kSegGroups - 1; t += t_step) {
-        const bool live = t < T;
-        if (live) {
+    for (int t0 = LONG ? kSegGroups * (int)blockIdx.y : 0; t0 < T; t0 += t_step) {
+        const bool live = t0 + gidx < T;
+        const int t = live ? t0 + gidx : T - 1;
+        {
             for (int n = j; n < kTempoLags + 8; n += 96)
                 F[n] = n < kTempoLags ? (float)((double)V.onset[t + n] * __ldg(tb.hann384 + n)) : 0.f;
         }
         group_bar(1 + gidx, 96);
-        if (live) {
+        {
             // structural zeros: onset[0..4] == 0 and the left pad is 0, so F[n] == 0 for n < 197 - t
             int n = (197 - t) > 0 ? ((197 - t) & ~3) : 0;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -490,8 +519,8 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
                 a3 = fmaf(A.x, B0.w, a3); a3 = fmaf(A.y, B1.x, a3); a3 = fmaf(A.z, B1.y, a3); a3 = fmaf(A.w, B1.z, a3);
                 B0 = B1;
             }
-            if (j == 0) V.ac0[t] = a0;
-            if (l0 < kPlaneRows) {
+            if (j == 0 && live) V.ac0[t] = a0;
+            if (l0 < kPlaneRows && live) {
                 V.tg[(l0 + 0) * T + t] = a0; V.tg[(l0 + 1) * T + t] = a1;
                 V.tg[(l0 + 2) * T + t] = a2; V.tg[(l0 + 3) * T + t] = a3;
             }
@@ -499,7 +528,7 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
             double sq = (double)a0 * a0 + (double)a1 * a1 + (double)a2 * a2 + (double)a3 * a3;
             sv = warp_sum(sv);
             sq = warp_sum(sq);
-            if (lane == 0) { atomicAdd(&V.sumv[t], sv); atomicAdd(&V.sumq[t], sq); }
+            if (lane == 0 && live) { atomicAdd(&V.sumv[t], sv); atomicAdd(&V.sumq[t], sq); }
         }
         group_bar(1 + gidx, 96);
     }
@@ -666,13 +695,11 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
 void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
                      float* scalars, cudaStream_t st) {
     static PerDeviceOnce once;
-    static int sms = 148, ctas = 12;
+    static int sms = 148;
     once.run([&] {
         cudaFuncSetAttribute(k_seg2048<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Seg2048Smem));
         cudaFuncSetAttribute(k_seg2048<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Seg2048Smem));
-        cudaFuncSetAttribute(k_frame2048<12>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-        cudaFuncSetAttribute(k_frame2048<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 66);
-        if (const char* e = getenv("BPC_F2_CTAS")) ctas = atoi(e) >= 16 ? 16 : 12;
+        cudaFuncSetAttribute(k_frame2048, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -680,9 +707,8 @@ void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb,
     const int total = n * g.T;
     // persistent: exactly the one-warp CTAs that fit an SM (168 registers), each striding over the frames
     int grid = total;
-    if (grid > sms * ctas) grid = sms * ctas;
-    if (ctas == 16) k_frame2048<16><<<grid, 32, 0, st>>>(y, g, tb, ws, total);
-    else k_frame2048<12><<<grid, 32, 0, st>>>(y, g, tb, ws, total);
+    if (grid > sms * kF2CtasPerSm) grid = sms * kF2CtasPerSm;
+    k_frame2048<<<grid, 32, 0, st>>>(y, g, tb, ws, total);
     note_launch();
 }
 

@@ -62,8 +62,9 @@ __global__ void __launch_bounds__(kS512Threads, 4) k_stft512(const float* __rest
     const double2 wl = make_double2(wp.y, -wp.x);                         // -i * exp(-2 pi i h / 512)
     const double2* win2 = reinterpret_cast<const double2*>(tb.hann512);
     const int per_iter = gridDim.x * (kS512Threads / 16);
-    for (int f0 = blockIdx.x * (kS512Threads / 16) + (team & ~1); f0 < total_frames; f0 += per_iter) {
-        const int f = f0 + (team & 1);
+    // trip count from blockIdx only (every team runs every iteration, `valid` gates the stores): convergent shuffles
+    for (int f0 = blockIdx.x * (kS512Threads / 16); f0 < total_frames; f0 += per_iter) {
+        const int f = f0 + team;
         const bool valid = f < total_frames;
         const int fc = valid ? f : total_frames - 1;
         const int b = fc / T, t = fc - b * T;
@@ -443,14 +444,20 @@ __device__ void role_mfcc(int b, const Geometry g, const Tables& tb, const Works
     for (int i = threadIdx.x; i < 40 * T; i += blockDim.x) OUT[i] = MF[i];
     delta_rows_block(MF, 40, T, OUT + 40 * T, OUT + 80 * T, nullptr);
     __syncthreads();
-    for (int r = warp; r < 120; r += nw) {
+    // (uniform trip count; a warp past the last row redoes row 119 without storing -- it may read that row while its
+    // owner rewrites it, the result is dropped: the warp reductions inside np_row_zterm are then provably convergent,
+    // plain SHFL instead of WARPSYNC.COLLECTIVE sequences)
+    for (int r0 = 0; r0 < 120; r0 += nw) {
+        const bool live = r0 + warp < 120;
+        const int r = live ? r0 + warp : 119;
         const ZTerm z = np_row_zterm(OUT + r * T, T, lane);
         __syncwarp();
-        for (int t = lane; t < T; t += 32) {
-            const float v = z(OUT[r * T + t]);
-            OUT[r * T + t] = v;
-            mn = fminf(mn, v);
-        }
+        if (live)
+            for (int t = lane; t < T; t += 32) {
+                const float v = z(OUT[r * T + t]);
+                OUT[r * T + t] = v;
+                mn = fminf(mn, v);
+            }
     }
     mn = block_min(mn, fscratch);
     __syncthreads();
@@ -521,17 +528,19 @@ __device__ void role_chroma_stft(int b, const Geometry g, const Tables& tb, cons
 
     // column maxima + low-frequency energy ratio (methods.py:84-88: sum(|X|^2[:32]) / (sum(|X|^2) + 1e-8))
     double e_low = 0.0, e_tot = 0.0;
-    for (int t = warp; t < T; t += nw) {
+    for (int t0 = 0; t0 < T; t0 += nw) {              // uniform trip count: convergent warp reductions
+        const bool live = t0 + warp < T;
+        const int t = live ? t0 + warp : T - 1;
         float mx = 0.f;
         for (int k = lane; k < 257; k += 32) {
             const float v = __ldg(mag_b + (size_t)t * kMagStride + k);
             mx = fmaxf(mx, v);
-            const double p = (double)__fmul_rn(v, v);
+            const double p = live ? (double)__fmul_rn(v, v) : 0.0;
             e_tot += p;
             if (k < 32) e_low += p;
         }
         mx = warp_max(mx);
-        if (lane == 0) colmax[t] = mx;
+        if (lane == 0 && live) colmax[t] = mx;
     }
     block_sum2(e_low, e_tot, dscratch);
     if (tid == 0) {
@@ -566,7 +575,9 @@ __device__ void role_chroma_stft(int b, const Geometry g, const Tables& tb, cons
 
     // raw chroma = chromafb[tuning] @ |X| (float32), one warp per frame
     const float* fb = tb.chroma + (size_t)tbin * 12 * 257;
-    for (int t = warp; t < T; t += nw) {
+    for (int t0 = 0; t0 < T; t0 += nw) {              // uniform trip count: convergent warp reductions
+        const bool live = t0 + warp < T;
+        const int t = live ? t0 + warp : T - 1;
         float acc[12];
 #pragma unroll
         for (int c = 0; c < 12; ++c) acc[c] = 0.f;
@@ -583,7 +594,7 @@ __device__ void role_chroma_stft(int b, const Geometry g, const Tables& tb, cons
         }
         // util.normalize(norm=inf): float64 division, float32 store; columns below tiny are left alone
         const double len = (cmax < 1.17549435e-38f) ? 1.0 : (double)cmax;
-        if (lane < 12) {
+        if (lane < 12 && live) {
             float v = 0.f;
 #pragma unroll
             for (int c = 0; c < 12; ++c) if (c == lane) v = acc[c];
@@ -601,14 +612,17 @@ __device__ void role_chroma_stft(int b, const Geometry g, const Tables& tb, cons
     const bool stats = !LONG && ws.stats_acc != nullptr;
     StatAcc ac;
     ac.init();
-    for (int r = warp; r < 12; r += nw) {
+    for (int r0 = 0; r0 < 12; r0 += nw) {
+        const bool live = r0 + warp < 12;
+        const int r = live ? r0 + warp : 11;
         const ZTerm z = np_row_zterm(raw + r * T, T, lane);
-        for (int t = lane; t < T; t += 32) {
-            const float v = z(raw[r * T + t]);
-            o[r * T + t] = v;
-            mn = fminf(mn, v);
-            if (stats) ac.add(v);
-        }
+        if (live)
+            for (int t = lane; t < T; t += 32) {
+                const float v = z(raw[r * T + t]);
+                o[r * T + t] = v;
+                mn = fminf(mn, v);
+                if (stats) ac.add(v);
+            }
     }
     mn = block_min(mn, fscratch);
     if (tid == 0) ws.chroma_min[b * 2 + 0] = mn;
