@@ -46,6 +46,9 @@ _SIGS = {
                                       C.c_void_p]),
     "bpc_precompute_host_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bpc_precompute_host_compact_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
+    "bpc_host_wait": (C.c_int, [C.c_void_p, C.c_int64]),
     "bpc_live_rows": (C.c_int, [C.c_int]),
     "bpc_expand_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int]),
     "bpc_host_alloc": (C.c_void_p, [C.c_void_p, C.c_int64, C.POINTER(C.c_int)]),

@@ -186,6 +186,36 @@ class Engine:
         _check(self._h, rc, "bpc_precompute_host_compact")
         return rows, pad, scalars, status
 
+    def precompute_host_compact_begin(self, wav: np.ndarray, rows, pad, scalars, status) -> int:
+        """Streaming form (include/bpc.h): enqueue the call behind whatever is still in flight and return a ticket;
+        `host_wait(ticket)` returns once the outputs are in `rows` / `pad` / `scalars` / `status`.  All five arrays
+        belong to the library until then (the engine keeps them alive).  Alternate two sets of output buffers --
+        begin(k + 1), then wait(k) -- to keep the GPU and the copy engines busy across calls."""
+        if wav.ndim != 2 or not wav.flags.c_contiguous or wav.dtype not in (np.float32, np.int16):
+            raise ValueError("wav must be a C-contiguous [B, L_in] float32 / int16 array")
+        dt = L.WAV_F32 if wav.dtype == np.float32 else L.WAV_PCM16
+        B, L_in = wav.shape
+        for name, a, shape, dtp in (("rows", rows, (B, L.LIVE_TOTAL, self.T), np.float32),
+                                    ("pad", pad, (B, L.NUM_CHANNELS), np.float32),
+                                    ("scalars", scalars, (B, self.nscal), np.float32), ("status", status, (B,), np.int32)):
+            if tuple(a.shape) != shape or a.dtype != dtp or not a.flags.c_contiguous or not a.flags.writeable:
+                raise ValueError(f"{name} must be a writable C-contiguous {np.dtype(dtp).name} array of shape {shape}")
+        ticket = C.c_int64(0)
+        rc = self._lib.bpc_precompute_host_compact_begin(self._h, wav.ctypes.data, dt, B, L_in, rows.ctypes.data,
+                                                         pad.ctypes.data, scalars.ctypes.data, status.ctypes.data,
+                                                         C.byref(ticket))
+        _check(self._h, rc, "bpc_precompute_host_compact_begin")
+        self._pending = getattr(self, "_pending", {})
+        self._pending[ticket.value] = (wav, rows, pad, scalars, status)
+        return ticket.value
+
+    def host_wait(self, ticket: int = -1) -> None:
+        """Block until every output of the call with this ticket (default: of every call) is in its host buffers."""
+        _check(self._h, self._lib.bpc_host_wait(self._h, int(ticket)), "bpc_host_wait")
+        pend = getattr(self, "_pending", {})
+        for t in [t for t in pend if ticket < 0 or t <= ticket]:
+            del pend[t]
+
     def host_empty(self, shape, dtype=np.float32) -> np.ndarray:
         """Pinned host array on the NUMA node of this engine's GPU (bpc_host_alloc); lives as long as the engine or until
         `host_free(arr)`.  `arr.bpc_numa_node` is not available on ndarrays, so the node is kept in `self.host_numa_node`."""

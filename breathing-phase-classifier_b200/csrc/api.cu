@@ -11,6 +11,7 @@
 #include <cstring>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <functional>
 #include <mutex>
 #include <string>
@@ -61,6 +62,25 @@ struct Slot {                      // one in-flight chunk of the host-buffer pat
     float* d_fill = nullptr;          // [chunk, 9] pad value of every plane (host path: pad rows are not transferred)
     float* h_fill = nullptr;
     float* d_rows = nullptr;          // [chunk, 772, T] the data rows back to back (k_compact_rows): one contiguous D2H
+};
+
+struct HostOut {                   // exactly one of the two host layouts
+    float* feats;                  // full  [B, 9, 128, T]
+    float* rows;                   // compact [B, 772, T] ...
+    float* pad;                    // ... + [B, 9]
+};
+
+struct Fly {                       // one piece of the host path that has been enqueued and not yet retired
+    int slot;
+    int64_t off;                   // first segment of the piece inside its call
+    int n;
+    HostOut out;
+    float* scalars;
+    int32_t* status;
+    bool to_rows, live_only, pin_f, pin_p, pin_s;
+    bool filled;                   // full layout: the pad rows have been written by the host threads
+    bool last;                     // last piece of its call
+    int64_t ticket;
 };
 
 // Rows of each plane that carry data; rows live..127 are one constant per plane (pad_freq, methods.py:39-46):
@@ -294,6 +314,12 @@ struct bpc_handle {
     bool taper_tail = true;        // host path halves the last pieces of a call (env BPC_TAPER=0: equal chunks)
     bool ramp_head = true;         // ... and starts with small pieces so that the first D2H starts early (env BPC_RAMP=0)
     bool slot_ctx_on = false;      // env BPC_SLOT_CTX=1: every slot computes in its own workspace (pieces overlap on the GPU)
+    // The host path is a ring of pieces that outlives a call: bpc_precompute_host*_begin enqueues the pieces of a call
+    // behind whatever is still in flight and returns with up to two pieces unretired; bpc_host_wait retires them.
+    std::deque<Fly> fly;
+    int64_t piece_seq = 0;         // pieces enqueued so far (slot = piece_seq % kSlots)
+    int64_t ticket_next = 1, ticket_done = 0;
+    double t_wait = 0.0, t_fill = 0.0;
     int last_n = 0;
     int64_t launches0 = 0;
     bool timing = false;           // per-kernel CUDA-event timing (bench.py roofline leg)
@@ -938,16 +964,123 @@ int bpc_precompute(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int
 
 namespace {
 
-struct HostOut {                   // exactly one of the two layouts
-    float* feats;                  // full  [B, 9, 128, T]
-    float* rows;                   // compact [B, 772, T] ...
-    float* pad;                    // ... + [B, 9]
-};
-
 // The host-buffer path: a three-stage software pipeline over pieces of host_chunk segments -- H2D of piece i+1 ||
 // kernels of piece i || D2H (+ host fill, full layout only) of piece i-1 -- on three slots with their own streams.
-int host_pipeline(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in, HostOut out, float* scalars,
-                  int32_t* status) {
+// r02: the ring of pieces is a property of the HANDLE, not of a call.  host_begin enqueues the pieces of one call behind
+// whatever is still in flight and returns with the last two pieces unretired; host_wait retires up to a ticket.  A caller
+// that alternates two sets of host buffers (begin k+1, then wait k) keeps the GPU and the copy engines busy across
+// calls: the ramp at the head of a call (nothing to copy until the first piece is computed) and the D2H of the last
+// piece at its tail overlap with the neighbouring calls.  The synchronous entry points are begin + wait.
+cudaError_t host_wait_event(bpc_handle* h, cudaEvent_t ev) {
+    const auto t_a = std::chrono::steady_clock::now();
+    const cudaError_t e = cudaEventSynchronize(ev);
+    h->t_wait += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count();
+    return e;
+}
+
+void host_job(bpc_handle* h, const std::function<void(int, int)>& job) {
+    const auto t_a = std::chrono::steady_clock::now();
+    h->pool->run(job);
+    h->t_fill += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count();
+}
+
+// Full layout: the 380 constant pad rows of every segment of the piece, from its nine pad values (they leave the device
+// before the bulk rows, so this overlaps the piece's D2H and the next piece's kernels).
+int host_fill(bpc_handle* h, Fly& f) {
+    if (f.to_rows || !f.live_only || f.filled) return BPC_OK;
+    Slot& s = h->slot[f.slot];
+    const int T = h->g.T, n = f.n;
+    const size_t seg_feats = (size_t)9 * kPlaneRows * T;
+    float* user = f.out.feats + (size_t)f.off * seg_feats;
+    BPC_CUDA(h, host_wait_event(h, s.fill_ready));
+    host_job(h, [&](int part, int parts) {
+        for (int b = part; b < n; b += parts) {
+            float* dst = user + (size_t)b * seg_feats;
+            for (int c = 0; c < 9; ++c)
+                if (kLiveRows[c] < kPlaneRows)
+                    fill_stream(dst + ((size_t)c * kPlaneRows + kLiveRows[c]) * T,
+                                dst + (size_t)(c + 1) * kPlaneRows * T, s.h_fill[(size_t)b * 9 + c]);
+        }
+#if defined(__SSE2__)
+        _mm_sfence();
+#endif
+    });
+    f.filled = true;
+    return BPC_OK;
+}
+
+// Retire the oldest piece in flight: its bulk D2H has finished; staging -> user copies for pageable buffers.
+int host_retire_front(bpc_handle* h) {
+    Fly& f = h->fly.front();
+    int rc = host_fill(h, f);
+    if (rc) return rc;
+    Slot& s = h->slot[f.slot];
+    const Geometry& g = h->g;
+    const int T = g.T, n = f.n;
+    const int64_t off = f.off;
+    const size_t seg_feats = (size_t)9 * kPlaneRows * T, seg_rows = (size_t)kLiveTotal * T;
+    BPC_CUDA(h, host_wait_event(h, s.done));
+    if (!f.pin_f) {                                                // pageable output: staging -> user buffer
+        if (f.to_rows) {
+            float* user = f.out.rows + (size_t)off * seg_rows;
+            host_job(h, [&](int part, int parts) {
+                for (int b = part; b < n; b += parts)
+                    std::memcpy(user + (size_t)b * seg_rows, s.h_feats + (size_t)b * seg_rows, seg_rows * 4);
+            });
+        } else {
+            float* user = f.out.feats + (size_t)off * seg_feats;
+            const std::vector<RowRun> runs = live_runs();
+            const bool live_only = f.live_only;
+            host_job(h, [&](int part, int parts) {
+                for (int b = part; b < n; b += parts) {
+                    float* dst = user + (size_t)b * seg_feats;
+                    const float* src = s.h_feats + (size_t)b * seg_feats;
+                    if (live_only) {
+                        for (const RowRun& r : runs)
+                            std::memcpy(dst + (size_t)r.start * T, src + (size_t)r.start * T,
+                                        (size_t)(r.end - r.start) * T * 4);
+                    } else {
+                        std::memcpy(dst, src, seg_feats * 4);
+                    }
+                }
+            });
+        }
+    }
+    if (f.to_rows && !f.pin_p) std::memcpy(f.out.pad + (size_t)off * 9, s.h_fill, (size_t)n * 9 * 4);
+    if (!f.pin_s) std::memcpy(f.scalars + (size_t)off * g.nscal, s.h_scalars, (size_t)n * g.nscal * 4);
+    if (f.status) std::memcpy(f.status + off, s.h_status, (size_t)n * 4);
+    if (f.last) h->ticket_done = f.ticket;
+    h->fly.pop_front();
+    return BPC_OK;
+}
+
+// An error in the middle of the pipeline: copies into the caller's buffers may still be in flight -- let them land,
+// then forget every piece (their tickets count as done; the error has been reported).
+int host_abort(bpc_handle* h, int rc) {
+    for (int i = 0; i < kSlots; ++i) {
+        if (h->slot[i].st) cudaStreamSynchronize(h->slot[i].st);
+        if (h->slot[i].st_out) cudaStreamSynchronize(h->slot[i].st_out);
+    }
+    cudaGetLastError();
+    h->fly.clear();
+    h->ticket_done = h->ticket_next - 1;
+    return rc;
+}
+
+int host_wait(bpc_handle* h, int64_t ticket) {
+    if (ticket < 0 || ticket >= h->ticket_next) ticket = h->ticket_next - 1;      // everything enqueued so far
+    BPC_CUDA(h, cudaSetDevice(h->device));
+    while (h->ticket_done < ticket && !h->fly.empty()) {
+        const int rc = host_retire_front(h);
+        if (rc) return host_abort(h, rc);
+    }
+    return BPC_OK;
+}
+
+struct HostTimeline { cudaEvent_t a, c, d; int n; };
+
+int host_begin(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in, HostOut out, float* scalars,
+               int32_t* status, int64_t* ticket_out, std::vector<HostTimeline>* tl, int64_t* pieces_out) {
     BPC_CUDA(h, cudaSetDevice(h->device));
     int rc = ensure_slots(h);
     if (rc) return rc;
@@ -960,21 +1093,17 @@ int host_pipeline(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int6
     const bool pin_in = is_pinned(wav), pin_f = is_pinned(to_rows ? out.rows : out.feats), pin_s = is_pinned(scalars);
     const bool pin_p = to_rows && is_pinned(out.pad);
     const std::vector<RowRun> runs = live_runs();
-    double t_wait = 0.0, t_fill = 0.0;
-    const auto t_call = std::chrono::steady_clock::now();
-    const char* env_trace = std::getenv("BPC_HOST_TRACE");
-    const bool timeline = env_trace && std::atoi(env_trace) >= 2;      // per-piece device timeline (debugging aid)
-    struct Tl { cudaEvent_t a, c, d; int n; };
-    std::vector<Tl> tl;
     // Piece schedule: full pieces, then the last <= host_chunk segments in halves (not below 128 segments, about one CTA
     // wave): what is exposed at the end of a call is the D2H (+ fill) of the LAST piece only, so it should be small.
     struct Piece { int64_t off; int n; };
     std::vector<Piece> sched;
     {
-        // Ramp: the D2H engine idles until the first piece has been computed, so the call starts with pieces of about
-        // one and two CTA waves (148, 296 segments) before it settles at host_chunk.
+        // Ramp: with an empty ring the D2H engine idles until the first piece has been computed, so the call starts with
+        // pieces of about one and two CTA waves (148, 296 segments) before it settles at host_chunk.  Behind a call
+        // that is still in flight there is nothing to ramp.
         int64_t off = 0;
-        int ramp = (h->ramp_head && !h->g.long_mode && B >= 4 * (int64_t)h->host_chunk) ? 148 : h->host_chunk;
+        const bool cold = h->fly.empty();
+        int ramp = (cold && h->ramp_head && !h->g.long_mode && B >= 4 * (int64_t)h->host_chunk) ? 148 : h->host_chunk;
         while (off < B) {
             const int64_t cap = std::min<int64_t>(ramp, h->host_chunk);
             int64_t rem = B - off, n = std::min<int64_t>(cap, rem);
@@ -989,164 +1118,129 @@ int host_pipeline(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int6
             for (int c = 0; c < 9; ++c)
                 if (kLiveRows[c] == kPlaneRows) out.pad[b * 9 + c] = 0.f;
     const int64_t nchunks = (int64_t)sched.size();
+    if (pieces_out) *pieces_out = nchunks;
     const bool live_only = to_rows || h->compact_d2h;        // only the 772 data rows cross PCIe
-    auto wait_on = [&](cudaEvent_t ev) -> cudaError_t {
-        const auto t_a = std::chrono::steady_clock::now();
-        const cudaError_t e = cudaEventSynchronize(ev);
-        t_wait += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count();
-        return e;
-    };
-    auto host_job = [&](const std::function<void(int, int)>& job) {
-        const auto t_a = std::chrono::steady_clock::now();
-        h->pool->run(job);
-        t_fill += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count();
-    };
-    // Iteration i enqueues piece i, writes the pad rows of piece i - 1 (full layout: needs only its nine pad values,
-    // which leave the device before the bulk rows, so this overlaps that piece's D2H and piece i's kernels) and
-    // retires piece i - 2 (bulk D2H finished).  The GPU always has the next piece queued.
+    const int64_t ticket = h->ticket_next++;
+    if (ticket_out) *ticket_out = ticket;
+    if (nchunks == 0) { if (h->fly.empty()) h->ticket_done = ticket; return BPC_OK; }
+    // Piece i is enqueued while the two pieces before it are still in flight (the GPU always has the next piece
+    // queued); then the pad rows of the piece before it are written (full layout) and the piece two back is retired.
     auto body = [&]() -> int {
-        for (int64_t i = 0; i <= nchunks + 1; ++i) {
-            if (i < nchunks) {
-                Slot& s = h->slot[i % kSlots];
-                const int64_t off = sched[i].off;
-                const int n = sched[i].n;
-                const char* src = static_cast<const char*>(wav) + (size_t)off * L_in * esz;
-                const size_t in_bytes = (size_t)n * L_in * esz;
-                if (timeline) {
-                    Tl e{nullptr, nullptr, nullptr, n};
-                    cudaEventCreate(&e.a); cudaEventCreate(&e.c); cudaEventCreate(&e.d);
-                    cudaEventRecord(e.a, s.st);
-                    tl.push_back(e);
-                }
-                if (pin_in) {
-                    BPC_CUDA(h, cudaMemcpyAsync(s.d_wav, src, in_bytes, cudaMemcpyHostToDevice, s.st));
-                } else {
-                    std::memcpy(s.h_wav, src, in_bytes);
-                    BPC_CUDA(h, cudaMemcpyAsync(s.d_wav, s.h_wav, in_bytes, cudaMemcpyHostToDevice, s.st));
-                }
-                // The H2D above overlaps the previous piece's kernels; the kernels themselves are serialised by the
-                // handle's workspace event (run_chunk), because all slots share the one workspace.
-                // debug on: the raw stages of the last chunk are read from the main context afterwards (bpc_debug_copy)
-                ChunkCtx& cx = (h->debug || !h->slot_ctx_on) ? h->main : h->slot_ctx[i % kSlots];
-                int rc2 = run_chunk(h, cx, s.d_wav, wav_dtype, L_in, n, s.d_feats, s.d_scalars, s.d_status, s.st);
+        for (int64_t i = 0; i < nchunks; ++i) {
+            while (h->fly.size() > 2) {                                    // (a begin right after an abort / odd ring states)
+                const int rc2 = host_retire_front(h);
                 if (rc2) return rc2;
-                if (timeline) cudaEventRecord(tl.back().c, s.st);
-                BPC_CUDA(h, cudaEventRecord(s.computed, s.st));
-                BPC_CUDA(h, cudaStreamWaitEvent(s.st_out, s.computed, 0));
-                cudaStream_t so = s.st_out;                                // everything below: the piece's output side
-                float* sdst = pin_s ? scalars + (size_t)off * g.nscal : s.h_scalars;
-                if (to_rows) {
-                    float* pdst = pin_p ? out.pad + (size_t)off * 9 : s.h_fill;
-                    float* rdst = pin_f ? out.rows + (size_t)off * seg_rows : s.h_feats;
-                    if (h->contig_d2h) {
-                        launch_pad_values(s.d_feats, T, n, h->live_dev, s.d_fill, so);
-                        BPC_CUDA(h, cudaMemcpyAsync(pdst, s.d_fill, (size_t)n * 9 * 4, cudaMemcpyDeviceToHost, so));
-                    } else {
-                        // copy-engine only (no kernel has to find a free SM next to the following piece's persistent
-                        // CTAs): the pad value of plane c is the first element of its first pad row, a 4-byte column
-                        // of the [n, 9 * 128 * T] matrix; planes without pad rows report 0 (memset once per call)
-                        for (int c = 0; c < 9; ++c)
-                            if (kLiveRows[c] < kPlaneRows)
-                                BPC_CUDA(h, cudaMemcpy2DAsync(pdst + c, 9 * 4, s.d_feats + ((size_t)c * kPlaneRows + kLiveRows[c]) * T,
-                                                              seg_feats * 4, 4, (size_t)n, cudaMemcpyDeviceToHost, so));
-                    }
-                    if (h->contig_d2h) {
-                        launch_compact_rows(s.d_feats, T, n, kLiveRows, s.d_rows, so);
-                        BPC_CUDA(h, cudaMemcpyAsync(rdst, s.d_rows, (size_t)n * seg_rows * 4, cudaMemcpyDeviceToHost, so));
-                    } else {
-                        size_t row0 = 0;                               // first compact row of the run
-                        for (const RowRun& r : runs) {
-                            BPC_CUDA(h, cudaMemcpy2DAsync(rdst + row0 * T, seg_rows * 4, s.d_feats + (size_t)r.start * T,
-                                                          seg_feats * 4, (size_t)(r.end - r.start) * T * 4, (size_t)n,
-                                                          cudaMemcpyDeviceToHost, so));
-                            row0 += (size_t)(r.end - r.start);
-                        }
-                    }
+            }
+            const int slot_id = (int)(h->piece_seq % kSlots);
+            Slot& s = h->slot[slot_id];
+            const int64_t off = sched[i].off;
+            const int n = sched[i].n;
+            const char* src = static_cast<const char*>(wav) + (size_t)off * L_in * esz;
+            const size_t in_bytes = (size_t)n * L_in * esz;
+            if (tl) {
+                HostTimeline e{nullptr, nullptr, nullptr, n};
+                cudaEventCreate(&e.a); cudaEventCreate(&e.c); cudaEventCreate(&e.d);
+                cudaEventRecord(e.a, s.st);
+                tl->push_back(e);
+            }
+            if (pin_in) {
+                BPC_CUDA(h, cudaMemcpyAsync(s.d_wav, src, in_bytes, cudaMemcpyHostToDevice, s.st));
+            } else {
+                std::memcpy(s.h_wav, src, in_bytes);
+                BPC_CUDA(h, cudaMemcpyAsync(s.d_wav, s.h_wav, in_bytes, cudaMemcpyHostToDevice, s.st));
+            }
+            // The H2D above overlaps the previous piece's kernels; the kernels themselves are serialised by the
+            // handle's workspace event (run_chunk), because all slots share the one workspace.
+            // debug on: the raw stages of the last chunk are read from the main context afterwards (bpc_debug_copy)
+            ChunkCtx& cx = (h->debug || !h->slot_ctx_on) ? h->main : h->slot_ctx[slot_id];
+            int rc2 = run_chunk(h, cx, s.d_wav, wav_dtype, L_in, n, s.d_feats, s.d_scalars, s.d_status, s.st);
+            if (rc2) return rc2;
+            if (tl) cudaEventRecord(tl->back().c, s.st);
+            BPC_CUDA(h, cudaEventRecord(s.computed, s.st));
+            BPC_CUDA(h, cudaStreamWaitEvent(s.st_out, s.computed, 0));
+            cudaStream_t so = s.st_out;                                // everything below: the piece's output side
+            float* sdst = pin_s ? scalars + (size_t)off * g.nscal : s.h_scalars;
+            if (to_rows) {
+                float* pdst = pin_p ? out.pad + (size_t)off * 9 : s.h_fill;
+                float* rdst = pin_f ? out.rows + (size_t)off * seg_rows : s.h_feats;
+                if (h->contig_d2h) {
+                    launch_pad_values(s.d_feats, T, n, h->live_dev, s.d_fill, so);
+                    BPC_CUDA(h, cudaMemcpyAsync(pdst, s.d_fill, (size_t)n * 9 * 4, cudaMemcpyDeviceToHost, so));
                 } else {
-                    float* fdst = pin_f ? out.feats + (size_t)off * seg_feats : s.h_feats;
-                    if (live_only) {
-                        // PCIe carries only the rows that hold data (772 of the 1152 rows of a segment); the constant
-                        // pad rows are re-created on the host from one value per plane.
-                        launch_pad_values(s.d_feats, T, n, h->live_dev, s.d_fill, so);
-                        BPC_CUDA(h, cudaMemcpyAsync(s.h_fill, s.d_fill, (size_t)n * 9 * 4, cudaMemcpyDeviceToHost, so));
-                        BPC_CUDA(h, cudaEventRecord(s.fill_ready, so));
-                        const size_t pitch = seg_feats * 4;
-                        for (const RowRun& r : runs)
-                            BPC_CUDA(h, cudaMemcpy2DAsync(fdst + (size_t)r.start * T, pitch, s.d_feats + (size_t)r.start * T,
-                                                          pitch, (size_t)(r.end - r.start) * T * 4, (size_t)n,
-                                                          cudaMemcpyDeviceToHost, so));
-                    } else {
-                        BPC_CUDA(h, cudaMemcpyAsync(fdst, s.d_feats, (size_t)n * seg_feats * 4, cudaMemcpyDeviceToHost, so));
+                    // copy-engine only (no kernel has to find a free SM next to the following piece's persistent
+                    // CTAs): the pad value of plane c is the first element of its first pad row, a 4-byte column
+                    // of the [n, 9 * 128 * T] matrix; planes without pad rows report 0 (memset once per call)
+                    for (int c = 0; c < 9; ++c)
+                        if (kLiveRows[c] < kPlaneRows)
+                            BPC_CUDA(h, cudaMemcpy2DAsync(pdst + c, 9 * 4, s.d_feats + ((size_t)c * kPlaneRows + kLiveRows[c]) * T,
+                                                          seg_feats * 4, 4, (size_t)n, cudaMemcpyDeviceToHost, so));
+                }
+                if (h->contig_d2h) {
+                    launch_compact_rows(s.d_feats, T, n, kLiveRows, s.d_rows, so);
+                    BPC_CUDA(h, cudaMemcpyAsync(rdst, s.d_rows, (size_t)n * seg_rows * 4, cudaMemcpyDeviceToHost, so));
+                } else {
+                    size_t row0 = 0;                               // first compact row of the run
+                    for (const RowRun& r : runs) {
+                        BPC_CUDA(h, cudaMemcpy2DAsync(rdst + row0 * T, seg_rows * 4, s.d_feats + (size_t)r.start * T,
+                                                      seg_feats * 4, (size_t)(r.end - r.start) * T * 4, (size_t)n,
+                                                      cudaMemcpyDeviceToHost, so));
+                        row0 += (size_t)(r.end - r.start);
                     }
                 }
-                BPC_CUDA(h, cudaMemcpyAsync(sdst, s.d_scalars, (size_t)n * g.nscal * 4, cudaMemcpyDeviceToHost, so));
-                BPC_CUDA(h, cudaMemcpyAsync(s.h_status, s.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, so));
-                BPC_CUDA(h, cudaEventRecord(s.done, so));
-                if (timeline) cudaEventRecord(tl.back().d, so);
-            }
-            if (!to_rows && live_only && i >= 1 && i - 1 < nchunks) {     // pad rows of piece i - 1 (disjoint from the D2H rows)
-                const int64_t j = i - 1;
-                Slot& s = h->slot[j % kSlots];
-                const int n = sched[j].n;
-                float* user = out.feats + (size_t)sched[j].off * seg_feats;
-                BPC_CUDA(h, wait_on(s.fill_ready));
-                host_job([&](int part, int parts) {
-                    for (int b = part; b < n; b += parts) {
-                        float* dst = user + (size_t)b * seg_feats;
-                        for (int c = 0; c < 9; ++c)
-                            if (kLiveRows[c] < kPlaneRows)
-                                fill_stream(dst + ((size_t)c * kPlaneRows + kLiveRows[c]) * T,
-                                            dst + (size_t)(c + 1) * kPlaneRows * T, s.h_fill[(size_t)b * 9 + c]);
-                    }
-#if defined(__SSE2__)
-                    _mm_sfence();
-#endif
-                });
-            }
-            if (i >= 2) {                                                  // retire piece i - 2
-                const int64_t j = i - 2;
-                Slot& s = h->slot[j % kSlots];
-                const int64_t off = sched[j].off;
-                const int n = sched[j].n;
-                BPC_CUDA(h, wait_on(s.done));
-                if (!pin_f) {                                              // pageable output: staging -> user buffer
-                    if (to_rows) {
-                        float* user = out.rows + (size_t)off * seg_rows;
-                        host_job([&](int part, int parts) {
-                            for (int b = part; b < n; b += parts)
-                                std::memcpy(user + (size_t)b * seg_rows, s.h_feats + (size_t)b * seg_rows, seg_rows * 4);
-                        });
-                    } else {
-                        float* user = out.feats + (size_t)off * seg_feats;
-                        host_job([&](int part, int parts) {
-                            for (int b = part; b < n; b += parts) {
-                                float* dst = user + (size_t)b * seg_feats;
-                                const float* src = s.h_feats + (size_t)b * seg_feats;
-                                if (live_only) {
-                                    for (const RowRun& r : runs)
-                                        std::memcpy(dst + (size_t)r.start * T, src + (size_t)r.start * T,
-                                                    (size_t)(r.end - r.start) * T * 4);
-                                } else {
-                                    std::memcpy(dst, src, seg_feats * 4);
-                                }
-                            }
-                        });
-                    }
+            } else {
+                float* fdst = pin_f ? out.feats + (size_t)off * seg_feats : s.h_feats;
+                if (live_only) {
+                    // PCIe carries only the rows that hold data (772 of the 1152 rows of a segment); the constant
+                    // pad rows are re-created on the host from one value per plane.
+                    launch_pad_values(s.d_feats, T, n, h->live_dev, s.d_fill, so);
+                    BPC_CUDA(h, cudaMemcpyAsync(s.h_fill, s.d_fill, (size_t)n * 9 * 4, cudaMemcpyDeviceToHost, so));
+                    BPC_CUDA(h, cudaEventRecord(s.fill_ready, so));
+                    const size_t pitch = seg_feats * 4;
+                    for (const RowRun& r : runs)
+                        BPC_CUDA(h, cudaMemcpy2DAsync(fdst + (size_t)r.start * T, pitch, s.d_feats + (size_t)r.start * T,
+                                                      pitch, (size_t)(r.end - r.start) * T * 4, (size_t)n,
+                                                      cudaMemcpyDeviceToHost, so));
+                } else {
+                    BPC_CUDA(h, cudaMemcpyAsync(fdst, s.d_feats, (size_t)n * seg_feats * 4, cudaMemcpyDeviceToHost, so));
                 }
-                if (to_rows && !pin_p) std::memcpy(out.pad + (size_t)off * 9, s.h_fill, (size_t)n * 9 * 4);
-                if (!pin_s) std::memcpy(scalars + (size_t)off * g.nscal, s.h_scalars, (size_t)n * g.nscal * 4);
-                if (status) std::memcpy(status + off, s.h_status, (size_t)n * 4);
+            }
+            BPC_CUDA(h, cudaMemcpyAsync(sdst, s.d_scalars, (size_t)n * g.nscal * 4, cudaMemcpyDeviceToHost, so));
+            BPC_CUDA(h, cudaMemcpyAsync(s.h_status, s.d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, so));
+            BPC_CUDA(h, cudaEventRecord(s.done, so));
+            if (tl) cudaEventRecord(tl->back().d, so);
+            h->piece_seq++;
+            h->fly.push_back(Fly{slot_id, off, n, out, scalars, status, to_rows, live_only, pin_f, pin_p, pin_s, false,
+                                 i + 1 == nchunks, ticket});
+            if (h->fly.size() >= 2) {                                      // pad rows of the piece before this one
+                rc2 = host_fill(h, h->fly[h->fly.size() - 2]);
+                if (rc2) return rc2;
+            }
+            while (h->fly.size() > 2) {                                    // retire the piece two back
+                rc2 = host_retire_front(h);
+                if (rc2) return rc2;
             }
         }
         return BPC_OK;
     };
     rc = body();
-    if (rc) {
-        // copies into the caller's buffers may still be in flight: let them land before the error is reported
-        for (int i = 0; i < kSlots; ++i) cudaStreamSynchronize(h->slot[i].st);
-        cudaGetLastError();
-        return rc;
-    }
+    if (rc) return host_abort(h, rc);
+    return BPC_OK;
+}
+
+// Synchronous call = begin + wait (+ the optional trace lines).
+int host_pipeline(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in, HostOut out, float* scalars,
+                  int32_t* status) {
+    const auto t_call = std::chrono::steady_clock::now();
+    const char* env_trace = std::getenv("BPC_HOST_TRACE");
+    const bool timeline = env_trace && std::atoi(env_trace) >= 2;      // per-piece device timeline (debugging aid)
+    std::vector<HostTimeline> tl;
+    h->t_wait = h->t_fill = 0.0;
+    int64_t ticket = 0, nchunks = 0;
+    int rc = host_begin(h, wav, wav_dtype, B, L_in, out, scalars, status, &ticket, timeline ? &tl : nullptr, &nchunks);
+    if (rc) return rc;
+    rc = host_wait(h, ticket);
+    if (rc) return rc;
+    const bool to_rows = out.rows != nullptr;
     if (timeline) {
         cudaDeviceSynchronize();
         for (size_t i = 0; i < tl.size(); ++i) {
@@ -1168,8 +1262,8 @@ int host_pipeline(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int6
         std::fprintf(stderr, "[bpc host] B=%lld pieces=%lld layout=%s total %.2f ms, waiting on GPU/PCIe %.2f ms, host copy/fill %.2f ms "
                      "(%d threads, %d cpus in the affinity mask, GPU numa node %d with %d local cpus, placement %s)\n",
                      (long long)B, (long long)nchunks, to_rows ? (h->contig_d2h ? "compact/contiguous" : "compact/2d") : "full",
-                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(), t_wait,
-                     t_fill, h->pool->size(), ncpu, h->numa.node, (int)h->numa.cpus.size(), h->numa_place ? "on" : "off");
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(), h->t_wait,
+                     h->t_fill, h->pool->size(), ncpu, h->numa.node, (int)h->numa.cpus.size(), h->numa_place ? "on" : "off");
     }
     return BPC_OK;
 }
@@ -1197,6 +1291,23 @@ int bpc_precompute_host_compact(bpc_handle* h, const void* wav, int wav_dtype, i
         return BPC_ERR_ARG;
     }
     return host_pipeline(h, wav, wav_dtype, B, L_in, HostOut{nullptr, rows, pad}, scalars, status);
+}
+
+int bpc_precompute_host_compact_begin(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in, float* rows,
+                                      float* pad, float* scalars, int32_t* status, int64_t* ticket) {
+    if (!h) return BPC_ERR_ARG;
+    if (!wav || !rows || !pad || !scalars || !ticket || B < 0 || L_in <= 0 ||
+        (wav_dtype != BPC_WAV_F32 && wav_dtype != BPC_WAV_PCM16)) {
+        h->err = "bpc_precompute_host_compact_begin: bad argument";
+        return BPC_ERR_ARG;
+    }
+    return host_begin(h, wav, wav_dtype, B, L_in, HostOut{nullptr, rows, pad}, scalars, status, ticket, nullptr, nullptr);
+}
+
+int bpc_host_wait(bpc_handle* h, int64_t ticket) {
+    if (!h) return BPC_ERR_ARG;
+    if (!h->slots_ready) return BPC_OK;                     // nothing was ever enqueued
+    return host_wait(h, ticket);
 }
 
 int bpc_live_rows(int channel) { return (channel >= 0 && channel < 9) ? kLiveRows[channel] : BPC_ERR_ARG; }

@@ -945,7 +945,8 @@ __global__ void __launch_bounds__(kLmThreads, 1) k_logmel_fused(const void* __re
         parity ^= 1u;
         // ---- FFT phase
         float pmax = 0.f;
-        for (int t = team; t < T + (T & 1); t += kLmTeams) {              // both teams of a warp iterate together (shuffles)
+        for (int t0 = 0; t0 < T; t0 += kLmTeams) {                        // uniform trip count: every shuffle is convergent
+            const int t = t0 + team;
             const bool valid = t < T;
             const int tt = valid ? t : T - 1;
             double2 a[16];

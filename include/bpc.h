@@ -117,6 +117,19 @@ int  bpc_precompute_host_compact(bpc_handle* h, const void* wav, int wav_dtype, 
                                  float* rows, float* pad, float* scalars, int32_t* status);
 int  bpc_expand_compact(const float* rows, const float* pad, int64_t n, int T, float* feats, int n_threads);
 
+/* Streaming form of bpc_precompute_host_compact, for a caller that works through a dataset batch after batch (the
+ * loop of process_dataset_threaded, core.py:33-43).  The pieces of a call join a ring that belongs to the handle:
+ * _begin enqueues them behind whatever is still in flight, returns with (at most) the last two pieces of this call
+ * unretired and hands back a ticket; bpc_host_wait(ticket) returns once every output of that call is in its host
+ * buffers (ticket < 0: everything enqueued so far).  With two sets of output buffers -- begin(k + 1), then wait(k) --
+ * the GPU and both copy engines stay busy across calls: the head of a call (nothing to copy until its first piece has
+ * been computed) and its tail (the D2H of the last piece) overlap with the neighbouring calls.  Until its ticket has
+ * been waited for, a call's input and output buffers belong to the library.  The synchronous entry points are
+ * exactly begin + wait, and they may be mixed with this pair (a synchronous call retires older tickets first). */
+int  bpc_precompute_host_compact_begin(bpc_handle* h, const void* wav, int wav_dtype, int64_t B, int64_t L_in,
+                                       float* rows, float* pad, float* scalars, int32_t* status, int64_t* ticket);
+int  bpc_host_wait(bpc_handle* h, int64_t ticket);
+
 /* Pinned host memory placed on the NUMA node the handle's GPU hangs off (sysfs numa_node of its PCI address; mbind +
  * first touch from a thread bound to that node's CPUs, then cudaHostRegister).  Buffers passed to bpc_precompute_host*
  * need not come from here, but on multi-socket boxes device<->host copies into remote-node memory run at a fraction

@@ -588,6 +588,47 @@ def test_compact_host_layout_matches_full(torch_cuda, mode, monkeypatch):
     eng.close()
 
 
+def test_streaming_host_calls_match_synchronous(torch_cuda, monkeypatch):
+    """bpc_precompute_host_compact_begin / bpc_host_wait (include/bpc.h): calls enqueued behind one another -- pinned
+    and pageable outputs, different batch sizes, a synchronous call in the middle, waits out of order and a wait for
+    everything -- must leave exactly what the synchronous call leaves."""
+    torch = torch_cuda
+    import bpc_b200
+    from bpc_b200.synth import synth_batch_pcm16
+    monkeypatch.setenv("BPC_HOST_CHUNK", "64")
+    eng = bpc_b200.Engine(device=0, max_batch=512)
+    sets = []
+    for k, n in enumerate((301, 64, 17, 200)):                             # several pieces / one piece / less than a piece
+        pcm = synth_batch_pcm16(9000 + 31 * k, n)
+        ref = eng.precompute_host_compact(pcm)
+        pinned = k % 2 == 0
+        mk = (lambda shape, dt=np.float32: eng.host_empty(shape, dt)) if pinned else (lambda shape, dt=np.float32: np.zeros(shape, dt))
+        h_in = eng.host_empty(pcm.shape, np.int16) if pinned else pcm.copy()
+        h_in[:] = pcm
+        out = (mk((n, 772, 63)), mk((n, 9)), mk((n, 36)), mk((n,), np.int32))
+        out[3][:] = -1
+        sets.append((h_in, out, ref))
+    tickets = [eng.precompute_host_compact_begin(h_in, *out) for h_in, out, _ in sets[:3]]
+    assert tickets == sorted(tickets) and len(set(tickets)) == 3
+    mid = eng.precompute_host_compact(sets[3][0])                          # synchronous call behind three pending ones
+    assert all(np.array_equal(a, b) for a, b in zip(mid, sets[3][2]))
+    eng.host_wait(tickets[2])                                              # retires tickets 0 and 1 on the way
+    eng.host_wait(tickets[0])
+    for h_in, out, ref in sets[:3]:
+        assert all(np.array_equal(a, b) for a, b in zip(out, ref))
+    # a second round on the same buffers, waited for all at once
+    for h_in, out, _ in sets:
+        for a in out:
+            a[...] = 0
+    for h_in, out, _ in sets:
+        eng.precompute_host_compact_begin(h_in, *out)
+    eng.host_wait()
+    for h_in, out, ref in sets:
+        assert all(np.array_equal(a, b) for a, b in zip(out, ref))
+    eng.host_wait()                                                        # nothing pending: returns at once
+    eng.close()
+
+
 def test_resample_on_device_matches_oracle(engine, torch_cuda):
     """process.py:28 `librosa.load(path, sr=16000)` for files of another rate: bpc_resample against oracle/resample.py
     (the shared Kaiser stand-in for libsoxr HQ).  Both accumulate the same float64 products; the device result must be

@@ -13,4 +13,4 @@ wav = (torch.from_numpy(np.tile(base, ((a.batch + 63) // 64, 1))[:a.batch]).cuda
 for _ in range(a.steps):
     f, s, st = eng.precompute(wav)
 torch.cuda.synchronize()
-print("ok", float(f.sum()), eng.launch_count())
+print("ok", eng.launch_count())          # (no torch reduction here: it would show up in the capture with 1.2 GB of reads)

@@ -1,6 +1,7 @@
 #!/bin/bash
 # One multi-GPU gpurun call: box topology, the concurrent D2H ceiling and bench.py at N = 1, 2, 4, 8 (as many as the box has).
-tag=$1
+tag=$1; shift
+NS="${@:-1 2 4 8}"                 # usage: tools/scale_probe.sh <tag> [N ...]   (default: 1 2 4 8)
 mkdir -p gpurun_out
 {
   nvidia-smi topo -m
@@ -9,7 +10,7 @@ mkdir -p gpurun_out
   nproc; free -g | head -2
 } > gpurun_out/topo_$tag.txt 2>&1
 NG=$(nvidia-smi -L | wc -l)
-for N in 1 2 4 8; do
+for N in $NS; do
   [ $N -gt $NG ] && break
   if [ $N -eq 1 ]; then
     D2H_K=4 timeout 300 python tools/d2h_ceiling.py > gpurun_out/d2h_${tag}_n$N.json 2> gpurun_out/d2h_${tag}_n$N.err
