@@ -29,7 +29,12 @@ static __device__ __noinline__ float c64_abs_exact(float re, float im) {
     return (float)sqrt((double)re * (double)re + (double)im * (double)im);
 }
 
-__device__ __forceinline__ float c64_abs_f32(float re, float im) {
+// The float32-pair evaluation without its range check; *x receives max(|re|, |im|).  The result is only valid for
+// 1e-18 < x < 1e18 (squares neither denormal nor infinite; x == 0 yields NaN): the caller tracks the range of x over a
+// whole row and redoes the row with c64_abs_exact in the rare case (an all-zero frame) -- one warp-uniform branch per
+// row instead of a branch per bin, which split the split loops of the STFT kernels into 33 basic blocks
+// (r02: k_frame2048 2.55 -> 2.41 ms, k_stft512 0.365 -> 0.34 ms).
+__device__ __forceinline__ float c64_abs_f32_unchecked(float re, float im, float* xmax_out) {
     const float a = fabsf(re), b = fabsf(im);
     const float x = fmaxf(a, b), y = fminf(a, b);
     const float p = __fmul_rn(x, x), pe = __fmaf_rn(x, x, -p);          // x^2 = p + pe
@@ -40,8 +45,17 @@ __device__ __forceinline__ float c64_abs_f32(float re, float im) {
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(hi));           // ~2 ulp: the residual step absorbs it
     const float r0 = __fmul_rn(hi, rs);
     const float res = __fadd_rn(__fmaf_rn(-r0, r0, hi), lo);            // (hi + lo) - r0^2
-    float out = __fmaf_rn(res, __fmul_rn(0.5f, rs), r0);
-    if (!(x > 1e-18f && x < 1e18f)) out = c64_abs_exact(re, im);       // zero / denormal squares / overflow: exact path
+    *xmax_out = x;
+    return __fmaf_rn(res, __fmul_rn(0.5f, rs), r0);
+}
+__device__ __forceinline__ bool c64_abs_in_range(float x) { return x > 1e-18f && x < 1e18f; }
+
+__device__ __forceinline__ float c64_abs_f32(float re, float im) {
+    float x;
+    float out = c64_abs_f32_unchecked(re, im, &x);
+#ifndef BPC_ABS_NOCHECK_EXPERIMENT
+    if (!c64_abs_in_range(x)) out = c64_abs_exact(re, im);              // zero / denormal squares / overflow: exact path
+#endif
     return out;
 }
 

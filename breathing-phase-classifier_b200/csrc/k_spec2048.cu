@@ -10,6 +10,7 @@
 //  47 % of its shared wavefronts bank conflicts -- profiles/r01_*.)
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 #include "kernels.cuh"
 #include "fft.cuh"
 #include "fft_reg.cuh"
@@ -120,11 +121,20 @@ __device__ __forceinline__ void warp_band_minmax(const float* row, int lo, int l
 constexpr int kF2RowBytes = 32 * 33 * 8;             // exchange buffer (one component at a time), later the |X| row (1028 floats)
 // 168 registers = 12 one-warp CTAs per SM, no spills.  Measured alternatives: 128 registers (16 warps, 75 spilled
 // doubles per frame) 2.78 vs 2.71 ms; 144 registers (14 warps) 4.74 vs 2.58 ms.
-constexpr int kF2CtasPerSm = 12;
-__global__ void __launch_bounds__(32, kF2CtasPerSm) k_frame2048(const float* __restrict__ y, Geometry g, Tables tb,
-                                                                 Workspace ws, int total_frames) {
-    __shared__ __align__(16) unsigned char smem_raw[kF2RowBytes];
-    const int lane = threadIdx.x;
+constexpr int kF2WarpsPerSm = 12;
+// WARPS = 1: one-warp CTAs, 12 per SM.  WARPS = 12: one CTA per SM whose warps take CONSECUTIVE frames of a contiguous
+// frame range: twelve consecutive frames span 2048 + 11 * 256 samples, and the next round's twelve overlap the last one
+// by 7 / 8, so all but 12 * 256 samples of a round are L1 hits instead of L2 round trips (with frame = blockIdx +
+// k * gridDim neighbouring frames ran on different SMs and every frame fetched its 8 KB from L2).  The trip count depends
+// on blockIdx and kernel arguments only and warps past the end of the range redo its last frame without storing, so the
+// collectives stay convergent (no WARPSYNC.COLLECTIVE) in the multi-warp CTA as well.
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, kF2WarpsPerSm / WARPS) k_frame2048(const float* __restrict__ y, Geometry g,
+                                                                                 Tables tb, Workspace ws,
+                                                                                 int total_frames, int frames_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* smem_raw = smem_dyn + (size_t)warp * kF2RowBytes;
     double* xch = reinterpret_cast<double*>(smem_raw);
     float* row = reinterpret_cast<float*>(smem_raw);
     const int T = g.T, L = g.L, hop = g.hop, TE = (T + 1) / 2;
@@ -132,7 +142,11 @@ __global__ void __launch_bounds__(32, kF2CtasPerSm) k_frame2048(const float* __r
     const double2* win2 = reinterpret_cast<const double2*>(tb.hann2048h);   // 0.5 * Hann: the 1/2 of the real split
     const double2* twa = tb.twa1024 + lane;                               // [k1][lane]
     const double2* rs = tb.rs2048 + lane;                                 // split twiddles as (scale, tan / cot)
-    for (int f = blockIdx.x; f < total_frames; f += gridDim.x) {
+    const int f_lo = blockIdx.x * frames_per_cta;
+    const int f_hi = f_lo + frames_per_cta < total_frames ? f_lo + frames_per_cta : total_frames;
+    for (int f0 = f_lo; f0 < f_hi; f0 += WARPS) {
+        const bool live = f0 + warp < f_hi;
+        const int f = live ? f0 + warp : f_hi - 1;
         const int b = f / T, t = f - b * T;
         const float* yb = y + (size_t)b * L;
         const int g0 = t * hop - 1024;
@@ -162,33 +176,58 @@ __global__ void __launch_bounds__(32, kF2CtasPerSm) k_frame2048(const float* __r
             //   s = Z[k] + conj(Z[N-k]),  d = Z[k] - conj(Z[N-k]),  p = w d,  w = -i exp(-2 pi i k / 2048),
             //   X[k] = s + p,  X[N-k] = conj(s - p);   w = c (t + i) for k < 256 and c (1 + i t) for k >= 256.
             const double z0re = a[0].x, z0im = a[0].y;
+            // EXACT = false: float32-pair magnitudes without a per-bin range check, the range of max(|re|, |im|) is
+            // tracked over the row; EXACT = true (the rare redo, e.g. an all-zero frame): the double-precision form.
+            auto split_row = [&](auto exact_tag, float& xlo, float& xhi) {
+                constexpr bool EXACT = decltype(exact_tag)::value;
 #pragma unroll
-            for (int K2 = 0; K2 <= 16; ++K2) {
-                const double2 zk = a[bitrev<32>(K2)];
-                double2 zn;
-                if (K2 < 16) {
-                    const double2 src = a[bitrev<32>(31 - K2)];
-                    zn.x = __shfl_sync(0xffffffffu, src.x, partner);
-                    zn.y = __shfl_sync(0xffffffffu, src.y, partner);
-                    if (lane == 0) zn = a[bitrev<32>((32 - K2) & 31)];
-                } else {
-                    zn = zk;                                   // k = 512 (lane 0) pairs with itself
+                for (int K2 = 0; K2 <= 16; ++K2) {
+                    const double2 zk = a[bitrev<32>(K2)];
+                    double2 zn;
+                    if (K2 < 16) {
+                        const double2 src = a[bitrev<32>(31 - K2)];
+                        zn.x = __shfl_sync(0xffffffffu, src.x, partner);
+                        zn.y = __shfl_sync(0xffffffffu, src.y, partner);
+                        if (lane == 0) zn = a[bitrev<32>((32 - K2) & 31)];
+                    } else {
+                        zn = zk;                                   // k = 512 (lane 0) pairs with itself
+                    }
+                    const double2 ct = __ldg(rs + 32 * K2);
+                    const double sx = zk.x + zn.x, sy = zk.y - zn.y, dx = zk.x - zn.x, dy = zk.y + zn.y;
+                    double qx, qy;
+                    if (K2 < 8) { qx = fma(ct.y, dx, -dy); qy = fma(ct.y, dy, dx); }
+                    else        { qx = fma(-ct.y, dy, dx); qy = fma(ct.y, dx, dy); }
+                    const double x0 = fma(ct.x, qx, sx), y0 = fma(ct.x, qy, sy);
+                    const double x1 = fma(-ct.x, qx, sx), y1 = fma(ct.x, qy, -sy);
+                    const int k = lane + 32 * K2;
+                    float m0, m1, xa = 1.f, xb = 1.f;
+                    if (EXACT) {
+                        m0 = c64_abs_exact((float)x0, (float)y0);
+                        m1 = c64_abs_exact((float)x1, (float)y1);
+                    } else {
+                        m0 = c64_abs_f32_unchecked((float)x0, (float)y0, &xa);
+                        m1 = c64_abs_f32_unchecked((float)x1, (float)y1, &xb);
+                    }
+                    if (K2 < 16) {
+                        row[k] = m0;
+                        xlo = fminf(xlo, xa);
+                        xhi = fmaxf(xhi, xa);
+                        if (K2 > 0 || lane > 0) {
+                            row[1024 - k] = m1;
+                            xlo = fminf(xlo, xb);
+                            xhi = fmaxf(xhi, xb);
+                        }
+                    } else if (lane == 0) {
+                        row[512] = m0;
+                        xlo = fminf(xlo, xa);
+                        xhi = fmaxf(xhi, xa);
+                    }
                 }
-                const double2 ct = __ldg(rs + 32 * K2);
-                const double sx = zk.x + zn.x, sy = zk.y - zn.y, dx = zk.x - zn.x, dy = zk.y + zn.y;
-                double qx, qy;
-                if (K2 < 8) { qx = fma(ct.y, dx, -dy); qy = fma(ct.y, dy, dx); }
-                else        { qx = fma(-ct.y, dy, dx); qy = fma(ct.y, dx, dy); }
-                const double x0 = fma(ct.x, qx, sx), y0 = fma(ct.x, qy, sy);
-                const double x1 = fma(-ct.x, qx, sx), y1 = fma(ct.x, qy, -sy);
-                const int k = lane + 32 * K2;
-                if (K2 < 16) {
-                    row[k] = c64_abs_f32((float)x0, (float)y0);
-                    if (K2 > 0 || lane > 0) row[1024 - k] = c64_abs_f32((float)x1, (float)y1);
-                } else if (lane == 0) {
-                    row[512] = c64_abs_f32((float)x0, (float)y0);
-                }
-            }
+            };
+            float xlo = 1.f, xhi = 1.f;
+            split_row(std::false_type{}, xlo, xhi);
+            if (__any_sync(0xffffffffu, !(c64_abs_in_range(xlo) && c64_abs_in_range(xhi))))
+                split_row(std::true_type{}, xlo, xhi);
             if (lane == 0) row[1024] = fabsf((float)(2.0 * (z0re - z0im)));   // X[1024] = Re Z[0] - Im Z[0] (Z halved)
             // words 1025 .. 1091 follow the row: the mel-D loop below reads up to 51 words past a band's start with
             // zero weights, and what the exchange left there may be a NaN pattern
@@ -197,7 +236,7 @@ __global__ void __launch_bounds__(32, kF2CtasPerSm) k_frame2048(const float* __r
             if (lane < 3) row[1089 + lane] = 0.f;
         }
         __syncwarp();
-        if ((t & 1) == 0) {                                    // hop-512 frame: keep the row for rolloff / tuning-36
+        if ((t & 1) == 0 && live) {                            // hop-512 frame: keep the row for rolloff / tuning-36
             float4* dst = reinterpret_cast<float4*>(ws.mag_even + ((size_t)b * TE + (t >> 1)) * kMag2048Stride);
 #pragma unroll
             for (int q = 0; q < (kMag2048Stride / 4 + 31) / 32; ++q) {
@@ -245,7 +284,7 @@ __global__ void __launch_bounds__(32, kF2CtasPerSm) k_frame2048(const float* __r
         slog = warp_sum(slog);
         spow = warp_sum(spow);
         double* ff = ws.frame_feat + (size_t)f * kFrameFeat;
-        if (lane == 0) {
+        if (lane == 0 && live) {
             const double len = sm < 1.17549435e-38 ? 1.0 : sm;     // util.normalize(norm=1): tiny(float32) guard
             const double c = smf_w / len;
             ff[0] = c;
@@ -265,7 +304,7 @@ __global__ void __launch_bounds__(32, kF2CtasPerSm) k_frame2048(const float* __r
             warp_band_extremes<8, 7, 4>(row, 204, 205, lane, &va[4], &pk[4]);
             warp_band_extremes<16, 13, 8>(row, 409, 410, lane, &va[5], &pk[5]);
             warp_band_extremes<8, 7, 4>(row, 819, 206, lane, &va[6], &pk[6]);
-            if (lane < 7) {
+            if (lane < 7 && live) {
                 double p = pk[0], v = va[0];
 #pragma unroll
                 for (int bnd = 1; bnd < 7; ++bnd) if (lane == bnd) { p = pk[bnd]; v = va[bnd]; }
@@ -295,7 +334,7 @@ __global__ void __launch_bounds__(32, kF2CtasPerSm) k_frame2048(const float* __r
                 wp += 4 * kPlaneRows;
                 rp += 4;
             }
-            md[m] = acc;
+            if (live) md[m] = acc;
         }
         __syncwarp();                                          // the row is the next frame's exchange buffer
     }
@@ -695,20 +734,27 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
 void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
                      float* scalars, cudaStream_t st) {
     static PerDeviceOnce once;
-    static int sms = 148;
+    static int sms = 148, warps = 12;
     once.run([&] {
         cudaFuncSetAttribute(k_seg2048<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Seg2048Smem));
         cudaFuncSetAttribute(k_seg2048<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Seg2048Smem));
-        cudaFuncSetAttribute(k_frame2048, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        cudaFuncSetAttribute(k_frame2048<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * kF2RowBytes);
+        cudaFuncSetAttribute(k_frame2048<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        cudaFuncSetAttribute(k_frame2048<12>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        if (const char* e = getenv("BPC_F2_WARPS")) warps = atoi(e) == 1 ? 1 : 12;     // A/B switch
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     });
     const int total = n * g.T;
-    // persistent: exactly the one-warp CTAs that fit an SM (168 registers), each striding over the frames
-    int grid = total;
-    if (grid > sms * kF2CtasPerSm) grid = sms * kF2CtasPerSm;
-    k_frame2048<<<grid, 32, 0, st>>>(y, g, tb, ws, total);
+    if (total <= 0) return;
+    // persistent: the 12 warps an SM holds at 168 registers, each CTA walking a contiguous range of frames
+    int grid = sms * (kF2WarpsPerSm / warps);
+    int per = (total + grid - 1) / grid;
+    per = (per + warps - 1) / warps * warps;
+    grid = (total + per - 1) / per;
+    if (warps == 1) k_frame2048<1><<<grid, 32, kF2RowBytes, st>>>(y, g, tb, ws, total, per);
+    else k_frame2048<12><<<grid, 32 * 12, 12 * kF2RowBytes, st>>>(y, g, tb, ws, total, per);
     note_launch();
 }
 

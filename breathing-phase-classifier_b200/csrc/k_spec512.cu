@@ -82,13 +82,28 @@ __global__ void __launch_bounds__(kS512Threads, 4) k_stft512(const float* __rest
         }
         team_fft<16>(a, tw, 1, xch, h);
         float* out = mag + (size_t)fc * kMagStride;
+        // every conjugate pair once (bins 0 .. 256, the Nyquist bin as the second output of k = 0); float32-pair
+        // magnitudes without a per-bin range check: the range is tracked over the row and the row redone exactly in the
+        // rare case (an all-zero frame) -- one warp-uniform branch per row (fft.cuh)
+        float xlo = 1.f, xhi = 1.f;
         auto emit = [&](int k, double2 t2) {
-            const float v = c64_abs_f32(0.5f * (float)t2.x, 0.5f * (float)t2.y);
+            float x;
+            const float re = 0.5f * (float)t2.x;
+            float v = c64_abs_f32_unchecked(re, 0.5f * (float)t2.y, &x);
+            if (k == 256) { v = fabsf(re); x = 1.f; }         // X[N] is real: |.| without the hypot (and never out of range)
+            xlo = fminf(xlo, x);
+            xhi = fmaxf(xhi, x);
             if (valid) out[k] = v;
         };
-        const double z0 = a[0].x - a[0].y;                    // lane h == 0: X[256] = Re Z[0] - Im Z[0]
-        team_rsplit<16, 0, 15>(a, wl, h, partner, emit);
-        if (h == 0 && valid) out[256] = fabsf((float)z0);
+        team_rsplit_pairs<16, 0>(a, wl, h, partner, emit);
+        if (__any_sync(0xffffffffu, !(c64_abs_in_range(xlo) && c64_abs_in_range(xhi)))) {
+            auto emit_exact = [&](int k, double2 t2) {
+                const float re = 0.5f * (float)t2.x;
+                const float v = k == 256 ? fabsf(re) : c64_abs_exact(re, 0.5f * (float)t2.y);
+                if (valid) out[k] = v;
+            };
+            team_rsplit_pairs<16, 0>(a, wl, h, partner, emit_exact);
+        }
     }
 }
 
@@ -970,13 +985,29 @@ __global__ void __launch_bounds__(kLmThreads, 1) k_logmel_fused(const void* __re
             team_fft_split<16>(a, twa, 16, xr, h);
             float* row = tile + tt * kLmPStride;
             // every conjugate pair once (fft_reg.cuh::team_rsplit_pairs); bin 256 = X[N] is real: |.| without the hypot
+            float xlo = 1.f, xhi = 1.f, pmax_row = 0.f;
             auto emit = [&](int k, double2 t2) {
                 const float re = out_scale * (float)t2.x, im = out_scale * (float)t2.y;
-                const float v = k == 256 ? fabsf(re) : c64_abs_f32(re, im);
+                float x;
+                float v = c64_abs_f32_unchecked(re, im, &x);             // range checked once per row (fft.cuh)
+                if (k == 256) { v = fabsf(re); x = 1.f; }
+                xlo = fminf(xlo, x);
+                xhi = fmaxf(xhi, x);
                 const float p = __fmul_rn(v, v);
-                if (valid) { row[k] = p; pmax = fmaxf(pmax, p); }
+                if (valid) { row[k] = p; pmax_row = fmaxf(pmax_row, p); }
             };
             team_rsplit_pairs<16, 0>(a, wl, h, partner, emit);
+            if (__any_sync(0xffffffffu, !(c64_abs_in_range(xlo) && c64_abs_in_range(xhi)))) {
+                pmax_row = 0.f;
+                auto emit_exact = [&](int k, double2 t2) {
+                    const float re = out_scale * (float)t2.x, im = out_scale * (float)t2.y;
+                    const float v = k == 256 ? fabsf(re) : c64_abs_exact(re, im);
+                    const float p = __fmul_rn(v, v);
+                    if (valid) { row[k] = p; pmax_row = fmaxf(pmax_row, p); }
+                };
+                team_rsplit_pairs<16, 0>(a, wl, h, partner, emit_exact);
+            }
+            pmax = fmaxf(pmax, pmax_row);
         }
         const float mx = block_max(pmax, fscratch);               // has the barrier that ends the FFT phase
         __syncthreads();
