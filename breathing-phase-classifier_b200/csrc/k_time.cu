@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(kHilbertThreads, 2) k_hilbert(const float* __r
     {
         constexpr int kPer = (kHN + kHilbertThreads - 1) / kHilbertThreads;   // 20
         float e0[kPer], e1[kPer];
+        float xlo = 1.f, xhi = 1.f;                       // range of max(|re|, |im|): checked once per segment (fft.cuh)
 #pragma unroll
         for (int i = 0; i < kPer; ++i) {
             const int m = tid + kHilbertThreads * i;
@@ -461,11 +462,29 @@ __global__ void __launch_bounds__(kHilbertThreads, 2) k_hilbert(const float* __r
                 const float2 o = X[h20_pad(m)];
                 const float2 v = __ldg(reinterpret_cast<const float2*>(yb) + m);
                 const float h0 = o.x * (1.0f / (float)kHN), h1 = -o.y * (1.0f / (float)kHN);
-                e0[i] = c64_abs_f32(v.x, h0);                                  // np.abs(complex64)
-                e1[i] = c64_abs_f32(v.y, h1);
+                float xa, xb;
+                e0[i] = c64_abs_f32_unchecked(v.x, h0, &xa);                   // np.abs(complex64)
+                e1[i] = c64_abs_f32_unchecked(v.y, h1, &xb);
+                xlo = fminf(xlo, fminf(xa, xb));
+                xhi = fmaxf(xhi, fmaxf(xa, xb));
             }
         }
-        __syncthreads();
+        // (the barrier the envelope store below needs anyway) a segment with exact zeros -- digital silence, a zero
+        // padded tail -- takes the checked form for every sample
+        if (__syncthreads_or(!(c64_abs_in_range(xlo) && c64_abs_in_range(xhi)))) {
+#pragma unroll                                             // (e0 / e1 must stay registers: no run-time indexing)
+            for (int i = 0; i < kPer; ++i) {
+                const int m = tid + kHilbertThreads * i;
+                if (m < kHN) {
+                    const float2 o = X[h20_pad(m)];
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(yb) + m);
+                    const float h0 = o.x * (1.0f / (float)kHN), h1 = -o.y * (1.0f / (float)kHN);
+                    e0[i] = c64_abs_f32(v.x, h0);
+                    e1[i] = c64_abs_f32(v.y, h1);
+                }
+            }
+            __syncthreads();
+        }
 #pragma unroll
         for (int i = 0; i < kPer; ++i) {
             const int m = tid + kHilbertThreads * i;
