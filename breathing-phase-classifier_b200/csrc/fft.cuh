@@ -53,9 +53,7 @@ __device__ __forceinline__ bool c64_abs_in_range(float x) { return x > 1e-18f &&
 __device__ __forceinline__ float c64_abs_f32(float re, float im) {
     float x;
     float out = c64_abs_f32_unchecked(re, im, &x);
-#ifndef BPC_ABS_NOCHECK_EXPERIMENT
     if (!c64_abs_in_range(x)) out = c64_abs_exact(re, im);              // zero / denormal squares / overflow: exact path
-#endif
     return out;
 }
 
