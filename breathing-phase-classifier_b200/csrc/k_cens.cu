@@ -12,6 +12,7 @@
 // The decimator stands in for soxr_hq (absent library): the same 127-tap Kaiser half-band the oracle uses.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include "kernels.cuh"
 #include "fft.cuh"
 #include "fft_reg.cuh"
@@ -164,6 +165,49 @@ __global__ void __launch_bounds__(256) k_dec_stage_long(const float* __restrict_
         for (int m = 0; m < 32; ++m) acc = fma(c_hb_odd[m], O(n - 1 - m) + O(n + m), acc);
         out[n] = (float)(acc * inv_s);
     }
+}
+
+// Long mode, r02: the same stage as a tiled kernel -- a CTA produces 1024 consecutive outputs of one segment from a
+// shared-memory copy of the 2 * 1024 + 128 input samples it needs (de-interleaved into even / odd samples, padded like
+// the 1 s kernel's arrays), every thread four outputs from a 67-sample FP64 register window: 17 shared-memory loads per
+// output instead of 65 global ones (k_dec_stage_long: 2.25 ms for the six stages of a step against 0.55 ms for the 1 s
+// decimator; this kernel: see DESIGN section 8).  Same taps, pairing and accumulation order: bit-identical output.
+constexpr int kDecTile = 1024, kDecTileThreads = kDecTile / kOutPerThread;
+__host__ __device__ constexpr int dpad(int i) { return i + (i >> 5); }
+__global__ void __launch_bounds__(kDecTileThreads) k_dec_tile_long(const float* __restrict__ in_base, size_t in_stride,
+                                                                   int in_off, int n_in, float* __restrict__ out_base,
+                                                                   size_t out_stride, int out_off) {
+    __shared__ float sE[dpad(kDecTile) + 1];
+    __shared__ float sO[dpad(kDecTile + 64) + 1];
+    const int tid = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * kDecTile;
+    const float* in = in_base + (size_t)b * in_stride + in_off;
+    float* out = out_base + (size_t)b * out_stride + out_off;
+    const int n_out = n_in >> 1;
+    // pair q = (in[2q], in[2q+1]); the tile needs O[t0 - 32 .. t0 + 1024 + 31] and E[t0 .. t0 + 1023]
+    for (int i = tid; i < kDecTile + 64; i += kDecTileThreads) {
+        const int q = t0 - 32 + i;
+        float2 v = make_float2(0.f, 0.f);
+        if (q >= 0 && 2 * q + 1 < n_in) v = __ldg(reinterpret_cast<const float2*>(in) + q);
+        sO[dpad(i)] = v.y;
+        if (i >= 32 && i < kDecTile + 32) sE[dpad(i - 32)] = v.x;
+    }
+    __syncthreads();
+    const double inv_s = 1.0 / sqrt(0.5);
+    const int n0 = kOutPerThread * tid;
+    double w[kWin];
+#pragma unroll
+    for (int q = 0; q < kWin; ++q) w[q] = (double)sO[dpad(n0 + q)];
+    float v[kOutPerThread];
+#pragma unroll
+    for (int p = 0; p < kOutPerThread; ++p) {
+        double acc = c_hb_centre * (double)sE[dpad(n0 + p)];
+#pragma unroll
+        for (int m = 0; m < 32; ++m) acc = fma(c_hb_odd[m], w[p + 31 - m] + w[p + 32 + m], acc);
+        v[p] = (float)(acc * inv_s);
+    }
+#pragma unroll
+    for (int p = 0; p < kOutPerThread; ++p)
+        if (t0 + n0 + p < n_out) out[t0 + n0 + p] = v[p];
 }
 
 // ---------------------------------------------------------------------------------------------- k_cens (CQT)
@@ -387,22 +431,31 @@ void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, con
     });
     if (g.long_mode) {
         const int L = g.L;
+        static const bool tiled = !(std::getenv("BPC_DEC_TILED") && std::atoi(std::getenv("BPC_DEC_TILED")) == 0);
         for (int o = 1; o <= 6; ++o) {
             const int n_in = L >> (o - 1);
-            const int blocks = std::min(64, (n_in / 2 + 255) / 256);
-            if (o == 1)
-                k_dec_stage_long<<<dim3(blocks, n), 256, 0, st>>>(y, (size_t)L, 0, n_in, ws.dec, (size_t)ws.dec_stride,
-                                                                  goff_len(1, L) + kGPad);
-            else
-                k_dec_stage_long<<<dim3(blocks, n), 256, 0, st>>>(ws.dec, (size_t)ws.dec_stride, goff_len(o - 1, L) + kGPad,
-                                                                  n_in, ws.dec, (size_t)ws.dec_stride, goff_len(o, L) + kGPad);
+            const float* src = o == 1 ? y : ws.dec;
+            const size_t sstride = o == 1 ? (size_t)L : (size_t)ws.dec_stride;
+            const int soff = o == 1 ? 0 : goff_len(o - 1, L) + kGPad;
+            if (tiled) {
+                const int tiles = (n_in / 2 + kDecTile - 1) / kDecTile;
+                k_dec_tile_long<<<dim3(tiles, n), kDecTileThreads, 0, st>>>(src, sstride, soff, n_in, ws.dec,
+                                                                            (size_t)ws.dec_stride, goff_len(o, L) + kGPad);
+            } else {
+                const int blocks = std::min(64, (n_in / 2 + 255) / 256);
+                k_dec_stage_long<<<dim3(blocks, n), 256, 0, st>>>(src, sstride, soff, n_in, ws.dec, (size_t)ws.dec_stride,
+                                                                  goff_len(o, L) + kGPad);
+            }
         }
         note_launch(5);
     } else {
         k_cens_dec<<<n, kDecThreads, sizeof(DecSmem), st>>>(y, g, ws);
     }
     if (g.long_mode) {
-        k_cens<true><<<dim3(n, 16), kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats, 1);
+        // a CTA takes kCensTeams frames per round: no more parts than rounds (16 parts left half of the teams of a
+        // 2 s segment, 126 frames, without a frame: 3.55 ms against 2.35 ms for the same samples at 30 s)
+        const int parts = std::max(1, std::min(16, (g.T + kCensTeams - 1) / kCensTeams));
+        k_cens<true><<<dim3(n, parts), kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats, 1);
         k_cens<true><<<dim3(n, 1), kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats, 2);
         note_launch();
     } else {
