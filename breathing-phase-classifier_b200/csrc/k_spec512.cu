@@ -228,12 +228,23 @@ __device__ void apply_bank(const BankDev& bank, const float* __restrict__ mag_b,
         const float* src1 = mag_b + (size_t)(live1 ? t1 : t0) * kMagStride;
         const float* wt = bank.wt + m;
         float acc0 = 0.f, acc1 = 0.f;
-        for (int j = 0; j < cmax; ++j) {
-            const int k = min(s + j, 256);
-            const float w = __ldg(wt + j * ROWS);
-            const float v0 = __ldg(src0 + k), v1 = __ldg(src1 + k);
-            acc0 = fmaf(w, power ? __fmul_rn(v0, v0) : v0, acc0);
-            acc1 = fmaf(w, power ? __fmul_rn(v1, v1) : v1, acc1);
+        // taps in rounds of four (the transposed table carries four zero taps past the widest row, upload_bank): twelve
+        // independent loads in flight per round instead of three -- the kernel waits on these loads (long scoreboard 3.8
+        // warps per issue); same taps in the same order, a zero weight adds +-0
+        for (int j = 0; j < cmax; j += 4) {
+            float w[4], v0[4], v1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = min(s + j + u, 256);
+                w[u] = __ldg(wt + (j + u) * ROWS);
+                v0[u] = __ldg(src0 + k);
+                v1[u] = __ldg(src1 + k);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc0 = fmaf(w[u], power ? __fmul_rn(v0[u], v0[u]) : v0[u], acc0);
+                acc1 = fmaf(w[u], power ? __fmul_rn(v1[u], v1[u]) : v1[u], acc1);
+            }
         }
         if (live) out[m * T + t0] = acc0;
         if (live1) out[m * T + t1] = acc1;
