@@ -693,7 +693,8 @@ int run_chunk(bpc_handle* h, ChunkCtx& cx, const void* wav, int wav_dtype, int64
         timed(3, [&] { launch_spec2048(y, n, g, h->tb, ws, feats, scalars, st); });
         timed(4, [&] { launch_even2048(n, g, h->tb, ws, scalars, status, st); });
         timed(10, [&] { launch_seg2048(n, g, h->tb, ws, feats, scalars, st); });
-        timed(5, [&] { launch_cens(y, n, g, h->tb, ws, feats, st); });
+        timed(11, [&] { launch_cens(y, n, g, h->tb, ws, feats, st, 1); });
+        timed(5, [&] { launch_cens(y, n, g, h->tb, ws, feats, st, 2); });
         timed(8, [&] { launch_lpc(y, n, g, h->tb, ws, feats, st); });
         timed(6, [&] { launch_time_scalars(y, n, g, h->tb, ws, scalars, status, st); });
         timed(7, [&] { launch_hilbert(y, n, g, h->tb, ws, scalars, st); });
@@ -703,7 +704,8 @@ int run_chunk(bpc_handle* h, ChunkCtx& cx, const void* wav, int wav_dtype, int64
         timed(3, [&] { launch_spec2048(y, n, g, h->tb, ws, feats, scalars, st); });
         timed(4, [&] { launch_even2048(n, g, h->tb, ws, scalars, status, st); });
         timed(10, [&] { launch_seg2048(n, g, h->tb, ws, feats, scalars, st); });
-        timed(5, [&] { launch_cens(y, n, g, h->tb, ws, feats, st); });
+        timed(11, [&] { launch_cens(y, n, g, h->tb, ws, feats, st, 1); });
+        timed(5, [&] { launch_cens(y, n, g, h->tb, ws, feats, st, 2); });
         timed(6, [&] { launch_time_scalars(y, n, g, h->tb, ws, scalars, status, st); });
         timed(7, [&] { launch_hilbert(y, n, g, h->tb, ws, scalars, st); });
         timed(8, [&] { launch_lpc(y, n, g, h->tb, ws, feats, st); });
@@ -1589,9 +1591,9 @@ int bpc_kernel_times(bpc_handle* h, double* ms_out, int64_t* launches_out, int n
 
 const char* bpc_kernel_name(int id) {
     static const char* names[BPC_NUM_KERNEL_IDS] = {"k_ingest", "k_stft512", "k_spec512_consumers",
-                                                    "k_frame2048", "k_even2048", "k_cens_dec+k_cens",
+                                                    "k_frame2048", "k_even2048", "k_cens",
                                                     "k_time_basic+k_autocorr", "k_hilbert", "k_lpc", "k_stats",
-                                                    "k_seg2048"};
+                                                    "k_seg2048", "k_cens_dec"};
     return (id >= 0 && id < BPC_NUM_KERNEL_IDS) ? names[id] : "";
 }
 

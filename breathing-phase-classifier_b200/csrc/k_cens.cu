@@ -421,15 +421,16 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
     }
 }
 
+// stage 1: the half-band decimations, 2: the CQT / CENS kernel, 0: both (the per-kernel timing leg launches them apart)
 void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
-                 cudaStream_t st) {
+                 cudaStream_t st, int stage) {
     static PerDeviceOnce once;
     once.run([&] {
         cudaFuncSetAttribute(k_cens_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
         cudaFuncSetAttribute(k_cens<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CensSmem));
         cudaFuncSetAttribute(k_cens<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CensSmem));
     });
-    if (g.long_mode) {
+    if (stage != 2 && g.long_mode) {
         const int L = g.L;
         static const bool tiled = !(std::getenv("BPC_DEC_TILED") && std::atoi(std::getenv("BPC_DEC_TILED")) == 0);
         for (int o = 1; o <= 6; ++o) {
@@ -447,21 +448,23 @@ void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, con
                                                                   goff_len(o, L) + kGPad);
             }
         }
-        note_launch(5);
-    } else {
+        note_launch(6);
+    } else if (stage != 2) {
         k_cens_dec<<<n, kDecThreads, sizeof(DecSmem), st>>>(y, g, ws);
+        note_launch();
     }
+    if (stage == 1) return;
     if (g.long_mode) {
         // a CTA takes kCensTeams frames per round: no more parts than rounds (16 parts left half of the teams of a
         // 2 s segment, 126 frames, without a frame: 3.55 ms against 2.35 ms for the same samples at 30 s)
         const int parts = std::max(1, std::min(16, (g.T + kCensTeams - 1) / kCensTeams));
         k_cens<true><<<dim3(n, parts), kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats, 1);
         k_cens<true><<<dim3(n, 1), kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats, 2);
-        note_launch();
+        note_launch(2);
     } else {
         k_cens<false><<<n, kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats, 0);
+        note_launch();
     }
-    note_launch(2);
 }
 
 }  // namespace bpc

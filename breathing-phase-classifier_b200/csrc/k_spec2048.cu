@@ -119,8 +119,9 @@ __device__ __forceinline__ void warp_band_minmax(const float* row, int lo, int l
 // lock-step (every frame costs the same, so they do).  r01 v30-v32 moved the hop-512 work in here: the even frames then
 // took longer than the odd ones, the warps drifted apart, and 11 of 12 issue slots went to "no instruction" stalls.
 constexpr int kF2RowBytes = 32 * 33 * 8;             // exchange buffer (one component at a time), later the |X| row (1028 floats)
-// 168 registers = 12 one-warp CTAs per SM, no spills.  Measured alternatives: 128 registers (16 warps, 75 spilled
-// doubles per frame) 2.78 vs 2.71 ms; 144 registers (14 warps) 4.74 vs 2.58 ms.
+// 168 registers = 12 warps per SM, no spills.  Measured alternatives: 128 registers (16 warps, 75 spilled doubles per
+// frame) 2.78 vs 2.71 ms; 144 registers (14 warps) 4.74 vs 2.58 ms; 8 warps per SM at 168 registers (a third of the
+// register file left to the kernels of the side streams) 2.76 vs 2.43 ms for the kernel and 11.42 vs 11.18 ms per step.
 constexpr int kF2WarpsPerSm = 12;
 // WARPS = 1: one-warp CTAs, 12 per SM.  WARPS = 12: one CTA per SM whose warps take CONSECUTIVE frames of a contiguous
 // frame range: twelve consecutive frames span 2048 + 11 * 256 samples, and the next round's twelve overlap the last one
@@ -129,9 +130,8 @@ constexpr int kF2WarpsPerSm = 12;
 // on blockIdx and kernel arguments only and warps past the end of the range redo its last frame without storing, so the
 // collectives stay convergent (no WARPSYNC.COLLECTIVE) in the multi-warp CTA as well.
 template <int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, kF2WarpsPerSm / WARPS) k_frame2048(const float* __restrict__ y, Geometry g,
-                                                                                 Tables tb, Workspace ws,
-                                                                                 int total_frames, int frames_per_cta) {
+__device__ __forceinline__ void frame2048_body(const float* __restrict__ y, const Geometry& g, const Tables& tb,
+                                               const Workspace& ws, int total_frames, int frames_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* smem_raw = smem_dyn + (size_t)warp * kF2RowBytes;
@@ -340,6 +340,12 @@ __global__ void __launch_bounds__(32 * WARPS, kF2WarpsPerSm / WARPS) k_frame2048
     }
 }
 
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, kF2WarpsPerSm / WARPS) k_frame2048(const float* __restrict__ y, Geometry g,
+                                                                                 Tables tb, Workspace ws,
+                                                                                 int total_frames, int frames_per_cta) {
+    frame2048_body<WARPS>(y, g, tb, ws, total_frames, frames_per_cta);
+}
 // ================================================================================================= k_seg2048
 constexpr int kSegGroups = 3;                // tempogram frames in flight per CTA (96 threads x 4 lags each)
 constexpr int kSegThreads = 96 * kSegGroups; // 9 warps (v41: two groups; the kernel runs four CTAs per SM either way)
@@ -749,7 +755,7 @@ void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb,
     const int total = n * g.T;
     if (total <= 0) return;
     // persistent: the 12 warps an SM holds at 168 registers, each CTA walking a contiguous range of frames
-    int grid = sms * (kF2WarpsPerSm / warps);
+    int grid = warps == 1 ? sms * kF2WarpsPerSm : sms;
     int per = (total + grid - 1) / grid;
     per = (per + warps - 1) / warps * warps;
     grid = (total + per - 1) / per;

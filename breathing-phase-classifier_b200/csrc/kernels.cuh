@@ -122,7 +122,7 @@ void launch_hilbert(const float* y, int n, const Geometry& g, const Tables& tb, 
 void launch_lpc(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
                 cudaStream_t st);
 void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
-                 cudaStream_t st);
+                 cudaStream_t st, int stage = 0);
 void launch_stats(int n, const Geometry& g, const float* feats, const float* scalars, double* acc, bool planes,
                   cudaStream_t st);
 void launch_modspec(int n, const Geometry& g, const Tables& tb, const Workspace& ws, const float* mel_db, float* out,

@@ -231,9 +231,10 @@ int  bpc_chunk_size(const bpc_handle* h);
 int64_t bpc_launch_count(const bpc_handle* h);
 
 /* Per-kernel device times (CUDA events around every launch of the full path) for bench.py's roofline leg.
- * ids: 0 ingest, 1 stft512, 2 spec512 consumers, 3 frame2048, 4 even2048, 5 cens_dec+cens, 6 time_basic+autocorr,
- * 7 hilbert, 8 lpc, 9 stats, 10 seg2048.  bpc_kernel_times synchronises, sums the elapsed ms / launch counts since the last call. */
-#define BPC_NUM_KERNEL_IDS 11
+ * ids: 0 ingest, 1 stft512, 2 spec512 consumers (both launches), 3 frame2048, 4 even2048, 5 cens, 6 time_basic+autocorr,
+ * 7 hilbert, 8 lpc, 9 stats, 10 seg2048, 11 cens_dec.  bpc_kernel_times synchronises, sums the elapsed ms / launch counts
+ * since the last call. */
+#define BPC_NUM_KERNEL_IDS 12
 int  bpc_set_kernel_timing(bpc_handle* h, int on);
 int  bpc_kernel_times(bpc_handle* h, double* ms_out, int64_t* launches_out, int n_ids);
 const char* bpc_kernel_name(int id);
