@@ -561,7 +561,10 @@ int build_tables(bpc_handle* h) {
                     }
                 }
                 start.push_back((int16_t)lo);
-                gw[r / 16] = std::max(gw[r / 16], hi - lo + 1);
+                // rounds of the basis product in k_cens (cens_round_row): rows 20-35, 4-19, 0-3 -- the band widths grow
+                // with the row, so the four-row round is the narrow one
+                const int q = r >= 20 ? 0 : (r >= 4 ? 1 : 2);
+                gw[q] = std::max(gw[q], hi - lo + 1);
             }
             re.insert(re.end(), bre.begin(), bre.end());
             im.insert(im.end(), bim.begin(), bim.end());

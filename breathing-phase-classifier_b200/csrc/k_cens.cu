@@ -331,10 +331,13 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
             const float2* bas = S.basis[o & 1];
             const float pow2 = (float)(1 << (o >> 1));
             const double* isl = S.inv_sl + (kCqtBins - kCqtBinsPerOct * (o + 1));
+            // three rounds of 16 / 16 / 4 rows per team.  The band of a row widens with the row index (8 .. 18 bins), a
+            // round costs the width of its widest row for every lane, so the four-row round takes the NARROW rows 0-3:
+            // 18 + 14 + 11 tap steps instead of the 13 + 17 + 18 of rows 0-15 / 16-31 / 32-35 (tuning 0)
 #pragma unroll
             for (int rr = 0; rr < 3; ++rr) {
-                const int r = h + 16 * rr;
-                if (r < kCqtBinsPerOct) {
+                const int r = rr == 0 ? 20 + h : (rr == 1 ? 4 + h : h);
+                if (rr < 2 || h < 4) {
                     float cr = 0.f, ci = 0.f;
                     const float2* wr = bas + r * kBasisPitch;
                     const float2* sp = spec + S.bstart[r];

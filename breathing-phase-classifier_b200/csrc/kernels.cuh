@@ -41,7 +41,7 @@ struct Tables {
     const float* cqt_re;          // [100, 36, W]  band form: entry j of row r weighs bin cqt_start[r] + j (zeros in gaps)
     const float* cqt_im;          // [100, 36, W]
     const double* cqt_sqrt_len;   // [100, 252]
-    int cqt_gw[3];                // band width needed by the rows 0-15 / 16-31 / 32-35 over all tunings (<= kCqtEllWidth)
+    int cqt_gw[3];                // band width needed by the rows 20-35 / 4-19 / 0-3 over all tunings (<= kCqtEllWidth)
     // LPC
     const double* hamming400;     // [400]
     // Hilbert (FFT-8000 = 4^3 * 5^3)
