@@ -123,12 +123,16 @@ constexpr int kF2RowBytes = 32 * 33 * 8;             // exchange buffer (one com
 // frame) 2.78 vs 2.71 ms; 144 registers (14 warps) 4.74 vs 2.58 ms; 8 warps per SM at 168 registers (a third of the
 // register file left to the kernels of the side streams) 2.76 vs 2.43 ms for the kernel and 11.42 vs 11.18 ms per step.
 constexpr int kF2WarpsPerSm = 12;
-// WARPS = 1: one-warp CTAs, 12 per SM.  WARPS = 12: one CTA per SM whose warps take CONSECUTIVE frames of a contiguous
-// frame range: twelve consecutive frames span 2048 + 11 * 256 samples, and the next round's twelve overlap the last one
-// by 7 / 8, so all but 12 * 256 samples of a round are L1 hits instead of L2 round trips (with frame = blockIdx +
-// k * gridDim neighbouring frames ran on different SMs and every frame fetched its 8 KB from L2).  The trip count depends
-// on blockIdx and kernel arguments only and warps past the end of the range redo its last frame without storing, so the
-// collectives stay convergent (no WARPSYNC.COLLECTIVE) in the multi-warp CTA as well.
+// WARPS = 1 (default): one-warp CTAs, 12 per SM, each walking its own contiguous range of frames (consecutive frames of
+// a warp overlap by 7 / 8 of their samples).  WARPS = 12 (BPC_F2_WARPS=12): one CTA per SM whose warps take CONSECUTIVE
+// frames of a contiguous range: twelve consecutive frames span 2048 + 11 * 256 samples, so all but 12 * 256 samples
+// of a round are L1 hits.  Measured 2.375 ms (1) against 2.427 ms (12): the sample loads are not what the warps wait
+// for, and independent warps drift into different phases of the frame, which fills the pipes better than twelve warps
+// that start every round together.  The same reason sank the r02 attempt to stage a round's sample window by bulk TMA
+// (one cp.async.bulk into a double-buffered shared window + mbarrier, every warp reading its frame with LDS): correct,
+// UBLKCP in the SASS, but the CTA-wide barrier per round that frees the window put all warps into the same phase --
+// 2.87 ms.  The trip count depends on blockIdx and kernel arguments only and warps past the end of the range redo its
+// last frame without storing, so the collectives stay convergent (no WARPSYNC.COLLECTIVE) in the multi-warp CTA too.
 template <int WARPS>
 __device__ __forceinline__ void frame2048_body(const float* __restrict__ y, const Geometry& g, const Tables& tb,
                                                const Workspace& ws, int total_frames, int frames_per_cta) {
@@ -740,14 +744,14 @@ __global__ void __launch_bounds__(256) k_even2048(Geometry g, Tables tb, Workspa
 void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
                      float* scalars, cudaStream_t st) {
     static PerDeviceOnce once;
-    static int sms = 148, warps = 12;
+    static int sms = 148, warps = 1;
     once.run([&] {
         cudaFuncSetAttribute(k_seg2048<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Seg2048Smem));
         cudaFuncSetAttribute(k_seg2048<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Seg2048Smem));
         cudaFuncSetAttribute(k_frame2048<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * kF2RowBytes);
         cudaFuncSetAttribute(k_frame2048<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
         cudaFuncSetAttribute(k_frame2048<12>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-        if (const char* e = getenv("BPC_F2_WARPS")) warps = atoi(e) == 1 ? 1 : 12;     // A/B switch
+        if (const char* e = getenv("BPC_F2_WARPS")) warps = atoi(e) == 12 ? 12 : 1;    // A/B switch
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
