@@ -540,6 +540,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "segments_per_step_per_gpu": B, "seq_len": L, "frames": T,
                        "distinct_segments": distinct, "input_dtype_resident": "f32",
+                       "segments_total_timed": int(world * args.steps * B),
                        "l2_policy": f"inputs ({B * L * 4 / 1e6:.0f} MB) and outputs ({B * 9 * 128 * T * 4 / 1e6:.0f} MB) "
                                     "per step exceed the 126 MB L2",
                        "parallelism": f"dp{world} (batch-sharded, one NCCL all-reduce of channel statistics)"},
