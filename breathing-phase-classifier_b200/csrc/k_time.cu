@@ -236,7 +236,7 @@ void launch_time_scalars(const float* y, int n, const Geometry& g, const Tables&
 // points per lane, one exchange) and leaves its spectrum in its own exchange buffer, then all 256 threads fold the eight
 // spectra of the round into thread-private bins of R.  Two rounds cover the 16 blocks; warp 0 runs the inverse.
 // (v1..v7: 17 CTA-wide shared-memory radix-4 FFTs in sequence, 90 % of the shared-memory pipe, half of it bank conflicts.)
-constexpr int kAcWarps = 8, kAcThreads = 32 * kAcWarps;
+constexpr int kAcWarps = 4, kAcThreads = 32 * kAcWarps;   // r02: 4 warps x 3 CTAs per SM (168 registers) instead of 8 x 1 (255)
 constexpr int kAcBins = (1025 + kAcThreads - 1) / kAcThreads;          // bins of R per thread (5)
 
 struct AutocorrSmem {
@@ -245,7 +245,7 @@ struct AutocorrSmem {
     int iscratch[32];
 };
 
-__global__ void __launch_bounds__(kAcThreads, 1) k_autocorr(const float* __restrict__ y, Geometry g, Tables tb,
+__global__ void __launch_bounds__(kAcThreads, 3) k_autocorr(const float* __restrict__ y, Geometry g, Tables tb,
                                                             int* __restrict__ ints, float* scalars) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AutocorrSmem& S = *reinterpret_cast<AutocorrSmem*>(smem_raw);
@@ -280,10 +280,9 @@ __global__ void __launch_bounds__(kAcThreads, 1) k_autocorr(const float* __restr
                 a[j] = make_double2((double)v.x, (double)v.y);
             }
             team_fft<32>(a, twa, 32, xch, lane);
-            const double z0 = a[0].x - a[0].y;                            // lane 0: X[1024]
+            // every conjugate pair once (bins 0 .. 1024; the second output of k = 0 is the real Nyquist bin X[1024])
             auto emit = [&](int k, double2 t2) { xch[k] = make_double2(0.5 * t2.x, 0.5 * t2.y); };
-            team_rsplit<32, 0, 31>(a, wl, lane, partner, emit);
-            if (lane == 0) xch[1024] = make_double2(z0, 0.0);
+            team_rsplit_pairs<32, 0>(a, wl, lane, partner, emit);
         }
         __syncthreads();
 #pragma unroll
