@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BPC_ABI_VERSION 1
+#define BPC_ABI_VERSION 2   /* 2: streaming host calls (begin / wait), 12 kernel timing ids */
 
 /* feats channel order = sorted .npz keys (dataset.py:26) */
 enum bpc_channel {
