@@ -95,7 +95,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.bpc_abi_version() != 2:
+        if handle.bpc_abi_version() != 3:
             raise BpcError("libbpc_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -263,7 +263,7 @@ class Engine:
 
     def kernel_times(self):
         """{kernel name: (total ms, launches)} since the last call (synchronises the device)."""
-        n = 12                                           # BPC_NUM_KERNEL_IDS
+        n = 13                                           # BPC_NUM_KERNEL_IDS
         ms = np.zeros(n, dtype=np.float64)
         cnt = np.zeros(n, dtype=np.int64)
         _check(self._h, self._lib.bpc_kernel_times(self._h, ms.ctypes.data, cnt.ctypes.data, n), "bpc_kernel_times")

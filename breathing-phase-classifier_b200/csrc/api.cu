@@ -607,6 +607,8 @@ int build_workspace(bpc_handle* h, ChunkCtx& ctx, int cap) {
     if ((rc = dalloc(h, C * T * 128, &w.melD))) return rc;
     w.dec_stride = cens_dec_floats_per_segment(g.L);
     if ((rc = dalloc(h, C * (size_t)w.dec_stride, &w.dec))) return rc;
+    w.cens_lo = nullptr;
+    if (!g.long_mode && (rc = dalloc(h, C * 3 * 12 * T, &w.cens_lo))) return rc;
     if ((rc = dalloc(h, C * 2, &w.tuning))) return rc;
     if ((rc = dalloc(h, C * 2, &w.chroma_min))) return rc;
     if ((rc = dalloc(h, C * 2, &w.ints))) return rc;
@@ -708,7 +710,8 @@ int run_chunk(bpc_handle* h, ChunkCtx& cx, const void* wav, int wav_dtype, int64
         timed(4, [&] { launch_even2048(n, g, h->tb, ws, scalars, status, st); });
         timed(10, [&] { launch_seg2048(n, g, h->tb, ws, feats, scalars, st); });
         timed(11, [&] { launch_cens(y, n, g, h->tb, ws, feats, st, 1); });
-        timed(5, [&] { launch_cens(y, n, g, h->tb, ws, feats, st, 2); });
+        timed(12, [&] { launch_cens(y, n, g, h->tb, ws, feats, st, 4); });
+        timed(5, [&] { launch_cens(y, n, g, h->tb, ws, feats, st, 3); });
         timed(6, [&] { launch_time_scalars(y, n, g, h->tb, ws, scalars, status, st); });
         timed(7, [&] { launch_hilbert(y, n, g, h->tb, ws, scalars, st); });
         timed(8, [&] { launch_lpc(y, n, g, h->tb, ws, feats, st); });
@@ -1596,7 +1599,7 @@ const char* bpc_kernel_name(int id) {
     static const char* names[BPC_NUM_KERNEL_IDS] = {"k_ingest", "k_stft512", "k_spec512_consumers",
                                                     "k_frame2048", "k_even2048", "k_cens",
                                                     "k_time_basic+k_autocorr", "k_hilbert", "k_lpc", "k_stats",
-                                                    "k_seg2048", "k_cens_dec"};
+                                                    "k_seg2048", "k_cens_dec", "k_cens_lo"};
     return (id >= 0 && id < BPC_NUM_KERNEL_IDS) ? names[id] : "";
 }
 

@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(kDecTileThreads) k_dec_tile_long(const float* 
 
 // ---------------------------------------------------------------------------------------------- k_cens (CQT)
 constexpr int kCensThreads = 256, kCensTeams = kCensThreads / 16;
+constexpr int kLoFirstOct = 4, kLoOcts = kCqtOctaves - kLoFirstOct;   // octaves of k_cens_lo (1 s mode)
 
 // ~101 KB and <= 128 registers: two 256-thread CTAs per SM, so a 592-segment chunk is exactly two full waves (at three
 // 128-thread CTAs per SM the second wave ran one third full)
@@ -241,7 +242,7 @@ struct CensSmem {
 
 template <bool LONG>
 __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restrict__ y, Geometry g, Tables tb,
-                                                          Workspace ws, float* feats, int phase) {
+                                                          Workspace ws, float* feats, int phase, int n_oct) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CensSmem& S = *reinterpret_cast<CensSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
         const bool valid = t < T;
         float csum = 0.f;                                        // lanes h < 12: chroma c = h
 #pragma unroll 1
-        for (int o = 0; o < kCqtOctaves; ++o) {
+        for (int o = 0; o < n_oct; ++o) {
             const int c0 = (valid ? t : 0) * (128 >> o) - 128;   // first complex sample of the frame
             double2 a[16];
             if (o == 0) {
@@ -362,7 +363,14 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
             }
             __syncwarp();
         }
-        if (h < 12 && valid) p_csum[h * T + t] = csum;
+        if (h < 12 && valid) {
+            if (n_oct < kCqtOctaves) {                           // octaves 4-6 come from k_cens_lo, added in octave order
+                const float* lo = ws.cens_lo + ((size_t)b * kLoOcts * 12 + h) * T + t;
+#pragma unroll
+                for (int q2 = 0; q2 < kLoOcts; ++q2) csum += lo[q2 * 12 * T];
+            }
+            p_csum[h * T + t] = csum;
+        }
     }
     if (LONG && phase == 1) return;
     __syncthreads();
@@ -424,7 +432,167 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
     }
 }
 
-// stage 1: the half-band decimations, 2: the CQT / CENS kernel, 0: both (the per-kernel timing leg launches them apart)
+// ---------------------------------------------------------------------------------------------- k_cens_lo (r02-h)
+// The three lowest octaves (o = 4, 5, 6: 1000 / 500 / 250 samples, hop h = 16 / 8 / 4 against n_fft = 512) without FFTs.
+// Consecutive frames of these octaves overlap in 496 .. 508 of their 512 samples, and the sparsified bases touch only
+// the 85 bins kBinLo .. kBinHi, so each of those bins is carried from frame to frame by the sliding-DFT recurrence of
+// the rectangular window ('ones', which is what librosa's CQT uses):
+//     X_{j+1}[k] = W^{-hk} ( X_j[k] + sum_{n<h} (x[s_j + 512 + n] - x[s_j + n]) W^{nk} ),   W = exp(-2 pi i / 512),
+// started h-aligned from the window [-512, 0) that lies wholly in the zero padding (X = 0); frame t is j = t + 256 / h.
+// Per bin and frame that is 2 h + 4 FP64 instructions with the h twiddles in registers -- 36 / 20 / 12 against the
+// ~6.9 k of an FFT-512 + split per frame shared by 85 bins (81 per bin) -- and no shared-memory exchange at all.  In
+// octave 6 every frame holds the whole 250-sample signal: after the start-up the recurrence is a pure rotation.
+// Rounding: one unit rotation per hop, <= 127 hops: 3e-14 of the largest |X| the bin has seen (numpy check in DESIGN),
+// the same order as the FFT's own error and nine orders below the complex64 rounding that follows.
+// A thread owns one (octave, bin); frames are produced in batches of 16 into a shared spectrum tile, the basis product
+// (one thread per (octave, row, frame pair): every weight is loaded once for two frames), |.| and the chroma fold follow
+// per batch.  The three per-octave chroma sums go to Workspace::cens_lo and k_cens adds them after its own octaves 0-3 in
+// the order the single-kernel version used (bit-identical folding).
+constexpr int kLoWarpsPerOct = 3, kLoThreads = 32 * kLoWarpsPerOct * kLoOcts;      // 288
+constexpr int kLoBatch = 16, kLoSpecPitch = 88;
+constexpr int kLoFrames = 63;                                                       // 1 s mode only: T = 63
+__host__ __device__ constexpr int lo_hop(int q) { return 16 >> q; }                 // q = octave - 4
+__host__ __device__ constexpr int lo_dlen(int q) { return kLoFrames * lo_hop(q) + 256; }
+static_assert(kBinSpan <= kLoSpecPitch && kBinSpan <= 32 * kLoWarpsPerOct, "one thread per touched bin");
+static_assert(kLoOcts * kCqtBinsPerOct * (kLoBatch / 2) == 3 * kLoThreads, "basis product: three items per thread");
+
+struct CensLoSmem {
+    double d0[lo_dlen(0)], d1[lo_dlen(1)], d2[lo_dlen(2)];       // x[i] - x[i - 512] per octave
+    float2 spec[kLoOcts][kLoBatch][kLoSpecPitch];
+    float cqmag[kLoOcts][kLoBatch][kCqtBinsPerOct + 4];
+    float2 basis[2][kCqtBinsPerOct * kBasisPitch];
+    short bstart[kCqtBinsPerOct + 4];
+    double inv_sl[kLoOcts * kCqtBinsPerOct];
+};
+
+// `frames` frames of one bin: store X, then hop.  `mac_hops`: hops whose difference samples can be non-zero.
+template <int H>
+__device__ __forceinline__ void lo_slide(const double* __restrict__ d, const double2 (&tw)[16], double2 rot, double2& X,
+                                         int& j, int hops, bool emit, float2* __restrict__ out, bool store) {
+    constexpr int kPre = 256 / H;
+    // octave 6 (H = 4): the signal ends at sample 250, differences are zero from hop 63 on
+    const int mac_end = H == 4 ? 63 : (1 << 30);
+    for (int i = 0; i < hops; ++i, ++j) {
+        if (emit && store) out[(j - kPre) % kLoBatch * kLoSpecPitch] = make_float2((float)X.x, (float)X.y);
+        double ar0 = X.x, ai0 = X.y, ar1 = 0.0, ai1 = 0.0;
+        if (j < mac_end) {
+            const double2* dp = reinterpret_cast<const double2*>(d + j * H);
+#pragma unroll
+            for (int n = 0; n < H; n += 2) {
+                const double2 dd = dp[n >> 1];
+                ar0 = fma(dd.x, tw[n].x, ar0);         ai0 = fma(dd.x, tw[n].y, ai0);
+                ar1 = fma(dd.y, tw[n + 1].x, ar1);     ai1 = fma(dd.y, tw[n + 1].y, ai1);
+            }
+        }
+        const double ar = ar0 + ar1, ai = ai0 + ai1;
+        X.x = fma(ar, rot.x, -(ai * rot.y));
+        X.y = fma(ar, rot.y, ai * rot.x);
+    }
+}
+
+__global__ void __launch_bounds__(kLoThreads, 2) k_cens_lo(Geometry g, Tables tb, Workspace ws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CensLoSmem& S = *reinterpret_cast<CensLoSmem*>(smem_raw);
+    const int tid = threadIdx.x, b = blockIdx.x, T = g.T;
+    const float* G = ws.dec + (size_t)b * cens_dec_stride(ws);
+    const int tun = ws.tuning[b * 2 + 1];
+    {
+        const float* bre = tb.cqt_re + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
+        const float* bim = tb.cqt_im + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
+        const double sqrt2 = sqrt(2.0);
+        for (int i = tid; i < kCqtBinsPerOct * kCqtEllWidth; i += kLoThreads) {
+            const float re = bre[i], im = bim[i];
+            const int o = (i / kCqtEllWidth) * kBasisPitch + i % kCqtEllWidth;
+            S.basis[0][o] = make_float2(re, im);
+            S.basis[1][o] = make_float2((float)((double)re * sqrt2), (float)((double)im * sqrt2));   // as in k_cens
+        }
+        if (tid < kCqtBinsPerOct) S.bstart[tid] = (short)(tb.cqt_start[tun * kCqtBinsPerOct + tid] - kBinLo);
+        // rows of octave o: inv_sl index kCqtBins - 36 (o + 1) + r; octaves 6, 5, 4 are the first three groups of 36
+        const double* slen = tb.cqt_sqrt_len + (size_t)tun * kCqtBins;
+        for (int i = tid; i < kLoOcts * kCqtBinsPerOct; i += kLoThreads) S.inv_sl[i] = 1.0 / slen[i];
+    }
+#pragma unroll
+    for (int q = 0; q < kLoOcts; ++q) {
+        const int n = 16000 >> (kLoFirstOct + q);
+        const float* x = G + goff(kLoFirstOct + q) + kGPad;
+        double* d = q == 0 ? S.d0 : (q == 1 ? S.d1 : S.d2);
+        for (int i = tid; i < lo_dlen(q); i += kLoThreads) {
+            const double a = i < n ? (double)__ldg(x + i) : 0.0;
+            const double c = (i >= 512 && i - 512 < n) ? (double)__ldg(x + i - 512) : 0.0;
+            d[i] = a - c;
+        }
+    }
+    // this thread's bin: twiddles W^{nk} (n < h) and the hop rotation W^{-hk}
+    const int q = tid / (32 * kLoWarpsPerOct);                  // octave - 4, warp-uniform
+    const int kk = tid - q * (32 * kLoWarpsPerOct);             // bin - kBinLo (lanes past the span idle along)
+    const int k = kBinLo + kk, H = lo_hop(q);
+    auto wpow = [&](int m) {                                    // exp(-2 pi i m / 512), m in [0, 512)
+        m &= 511;
+        const double2 w = __ldg(tb.ptw512 + (m <= 256 ? m : 512 - m));
+        return m <= 256 ? w : make_double2(w.x, -w.y);
+    };
+    double2 tw[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) tw[n] = wpow(n * k);
+    const double2 rc = wpow(H * k);
+    const double2 rot = make_double2(rc.x, -rc.y);
+    double2 X = make_double2(0.0, 0.0);
+    int j = 0;
+    const bool store = kk < kLoSpecPitch;                       // bins past kBinHi only ever meet zero weights
+    float2* out = &S.spec[q][0][store ? kk : 0];
+    const double* dq = q == 0 ? S.d0 : (q == 1 ? S.d1 : S.d2);
+    __syncthreads();
+    // start-up: slide from the all-zero window to frame 0
+    if (q == 0) lo_slide<16>(dq, tw, rot, X, j, 16, false, out, store);
+    else if (q == 1) lo_slide<8>(dq, tw, rot, X, j, 32, false, out, store);
+    else lo_slide<4>(dq, tw, rot, X, j, 64, false, out, store);
+    float* lo = ws.cens_lo + (size_t)b * kLoOcts * 12 * T;
+    for (int t0 = 0; t0 < T; t0 += kLoBatch) {
+        const int nf = min(kLoBatch, T - t0);
+        if (q == 0) lo_slide<16>(dq, tw, rot, X, j, nf, true, out, store);
+        else if (q == 1) lo_slide<8>(dq, tw, rot, X, j, nf, true, out, store);
+        else lo_slide<4>(dq, tw, rot, X, j, nf, true, out, store);
+        __syncthreads();
+        // basis product: item (octave q2, row r, frames 2 fp and 2 fp + 1)
+#pragma unroll 1
+        for (int q2 = 0; q2 < kLoOcts; ++q2) {
+            const int r = tid % kCqtBinsPerOct, fp = tid / kCqtBinsPerOct;
+            const int o = kLoFirstOct + q2;
+            const float2* wr = S.basis[o & 1] + r * kBasisPitch;
+            const float2* sp0 = &S.spec[q2][2 * fp][S.bstart[r]];
+            const float2* sp1 = sp0 + kLoSpecPitch;
+            const int wn = tb.cqt_gw[r >= 20 ? 0 : (r >= 4 ? 1 : 2)];
+            float cr0 = 0.f, ci0 = 0.f, cr1 = 0.f, ci1 = 0.f;
+#pragma unroll 4
+            for (int jj = 0; jj < wn; ++jj) {
+                const float2 w = wr[jj];
+                const float2 a = sp0[jj], c = sp1[jj];
+                cr0 = fmaf(w.x, a.x, cr0); cr0 = fmaf(-w.y, a.y, cr0);
+                ci0 = fmaf(w.x, a.y, ci0); ci0 = fmaf(w.y, a.x, ci0);
+                cr1 = fmaf(w.x, c.x, cr1); cr1 = fmaf(-w.y, c.y, cr1);
+                ci1 = fmaf(w.x, c.y, ci1); ci1 = fmaf(w.y, c.x, ci1);
+            }
+            const float pow2 = (float)(1 << (o >> 1));
+            const double sl = S.inv_sl[(kCqtOctaves - 1 - o) * kCqtBinsPerOct + r];
+            S.cqmag[q2][2 * fp][r] = c64_abs_f32((float)((double)(cr0 * pow2) * sl), (float)((double)(ci0 * pow2) * sl));
+            S.cqmag[q2][2 * fp + 1][r] = c64_abs_f32((float)((double)(cr1 * pow2) * sl), (float)((double)(ci1 * pow2) * sl));
+        }
+        __syncthreads();
+        // cq_to_chroma per octave: chroma c sums bins {3c-1, 3c, 3c+1} (mod 36)
+        for (int i = tid; i < kLoOcts * 12 * kLoBatch; i += kLoThreads) {
+            const int f = i % kLoBatch, c = (i / kLoBatch) % 12, q2 = i / (12 * kLoBatch);
+            if (f < nf) {
+                const float* m = S.cqmag[q2][f];
+                lo[(q2 * 12 + c) * T + t0 + f] = m[(3 * c + 35) % 36] + m[3 * c] + m[3 * c + 1];
+            }
+        }
+        // the next batch's slide writes `spec` (free since the barrier above); its basis product, which writes `cqmag`,
+        // comes after that slide's barrier
+    }
+}
+
+// stage 1: the half-band decimations, 2: the CQT / CENS kernels, 0: both (the per-kernel timing leg launches them
+// apart: 4 = k_cens_lo alone, 3 = k_cens alone)
 void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, const Workspace& ws, float* feats,
                  cudaStream_t st, int stage) {
     static PerDeviceOnce once;
@@ -432,8 +600,10 @@ void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, con
         cudaFuncSetAttribute(k_cens_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
         cudaFuncSetAttribute(k_cens<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CensSmem));
         cudaFuncSetAttribute(k_cens<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CensSmem));
+        cudaFuncSetAttribute(k_cens_lo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CensLoSmem));
     });
-    if (stage != 2 && g.long_mode) {
+    const bool dec = stage == 0 || stage == 1;
+    if (dec && g.long_mode) {
         const int L = g.L;
         static const bool tiled = !(std::getenv("BPC_DEC_TILED") && std::atoi(std::getenv("BPC_DEC_TILED")) == 0);
         for (int o = 1; o <= 6; ++o) {
@@ -452,7 +622,7 @@ void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, con
             }
         }
         note_launch(6);
-    } else if (stage != 2) {
+    } else if (dec) {
         k_cens_dec<<<n, kDecThreads, sizeof(DecSmem), st>>>(y, g, ws);
         note_launch();
     }
@@ -461,11 +631,19 @@ void launch_cens(const float* y, int n, const Geometry& g, const Tables& tb, con
         // a CTA takes kCensTeams frames per round: no more parts than rounds (16 parts left half of the teams of a
         // 2 s segment, 126 frames, without a frame: 3.55 ms against 2.35 ms for the same samples at 30 s)
         const int parts = std::max(1, std::min(16, (g.T + kCensTeams - 1) / kCensTeams));
-        k_cens<true><<<dim3(n, parts), kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats, 1);
-        k_cens<true><<<dim3(n, 1), kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats, 2);
+        k_cens<true><<<dim3(n, parts), kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats, 1, kCqtOctaves);
+        k_cens<true><<<dim3(n, 1), kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats, 2, kCqtOctaves);
         note_launch(2);
     } else {
-        k_cens<false><<<n, kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats, 0);
+        // BPC_CENS_LO=0: all seven octaves by FFT in k_cens (the r02-g form)
+        static const bool lo = !(std::getenv("BPC_CENS_LO") && std::atoi(std::getenv("BPC_CENS_LO")) == 0);
+        const bool use_lo = lo && ws.cens_lo != nullptr && g.T == kLoFrames;
+        if (use_lo && stage != 3) {
+            k_cens_lo<<<n, kLoThreads, sizeof(CensLoSmem), st>>>(g, tb, ws);
+            note_launch();
+        }
+        if (stage == 4) return;
+        k_cens<false><<<n, kCensThreads, sizeof(CensSmem), st>>>(y, g, tb, ws, feats, 0, use_lo ? kLoFirstOct : kCqtOctaves);
         note_launch();
     }
 }

@@ -66,6 +66,7 @@ struct Workspace {            // per chunk of `cap` segments
     float* melD;              // [cap, T, 128] mel-D power columns
     float* dec;               // [cap, dec_stride]  half-band decimated signals of the CQT octaves 1..6 (zero padded)
     int dec_stride;
+    float* cens_lo;           // [cap, 3, 12, T] 1 s mode: chroma sums of the CQT octaves 4-6 (k_cens_lo -> k_cens)
     int* tuning;              // [cap, 2]   tuning bin for 12 / 36 bins per octave
     float* chroma_min;        // [cap, 2]   min of the normalised chroma_stft / chroma_cens rows
     int* ints;                // [cap, 2]   n_peaks, first-min index

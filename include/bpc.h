@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BPC_ABI_VERSION 2   /* 2: streaming host calls (begin / wait), 12 kernel timing ids */
+#define BPC_ABI_VERSION 3   /* 2: streaming host calls (begin / wait); 3: 13 kernel timing ids (k_cens_lo) */
 
 /* feats channel order = sorted .npz keys (dataset.py:26) */
 enum bpc_channel {
@@ -232,9 +232,9 @@ int64_t bpc_launch_count(const bpc_handle* h);
 
 /* Per-kernel device times (CUDA events around every launch of the full path) for bench.py's roofline leg.
  * ids: 0 ingest, 1 stft512, 2 spec512 consumers (both launches), 3 frame2048, 4 even2048, 5 cens, 6 time_basic+autocorr,
- * 7 hilbert, 8 lpc, 9 stats, 10 seg2048, 11 cens_dec.  bpc_kernel_times synchronises, sums the elapsed ms / launch counts
+ * 7 hilbert, 8 lpc, 9 stats, 10 seg2048, 11 cens_dec, 12 cens_lo.  bpc_kernel_times synchronises, sums the elapsed ms / launch counts
  * since the last call. */
-#define BPC_NUM_KERNEL_IDS 12
+#define BPC_NUM_KERNEL_IDS 13
 int  bpc_set_kernel_timing(bpc_handle* h, int on);
 int  bpc_kernel_times(bpc_handle* h, double* ms_out, int64_t* launches_out, int n_ids);
 const char* bpc_kernel_name(int id);

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/bpc.h but not exported"
     assert declared == set(bpc_b200.EXPORTS), declared ^ set(bpc_b200.EXPORTS)
-    assert bpc_b200.lib().bpc_abi_version() == 2
+    assert bpc_b200.lib().bpc_abi_version() == 3
 
 
 def test_default_params_are_the_reference_constants():
