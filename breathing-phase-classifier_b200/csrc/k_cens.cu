@@ -438,59 +438,63 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
 // the 85 bins kBinLo .. kBinHi, so each of those bins is carried from frame to frame by the sliding-DFT recurrence of
 // the rectangular window ('ones', which is what librosa's CQT uses):
 //     X_{j+1}[k] = W^{-hk} ( X_j[k] + sum_{n<h} (x[s_j + 512 + n] - x[s_j + n]) W^{nk} ),   W = exp(-2 pi i / 512),
-// started h-aligned from the window [-512, 0) that lies wholly in the zero padding (X = 0); frame t is j = t + 256 / h.
-// Per bin and frame that is 2 h + 4 FP64 instructions with the h twiddles in registers -- 36 / 20 / 12 against the
-// ~6.9 k of an FFT-512 + split per frame shared by 85 bins (81 per bin) -- and no shared-memory exchange at all.  In
-// octave 6 every frame holds the whole 250-sample signal: after the start-up the recurrence is a pure rotation.
-// Rounding: one unit rotation per hop, <= 127 hops: 3e-14 of the largest |X| the bin has seen (numpy check in DESIGN),
-// the same order as the FFT's own error and nine orders below the complex64 rounding that follows.
-// A thread owns one (octave, bin); frames are produced in batches of 16 into a shared spectrum tile, the basis product
-// (one thread per (octave, row, frame pair): every weight is loaded once for two frames), |.| and the chroma fold follow
-// per batch.  The three per-octave chroma sums go to Workspace::cens_lo and k_cens adds them after its own octaves 0-3 in
-// the order the single-kernel version used (bit-identical folding).
-constexpr int kLoWarpsPerOct = 3, kLoThreads = 32 * kLoWarpsPerOct * kLoOcts;      // 288
-constexpr int kLoBatch = 16, kLoSpecPitch = 88;
+// started from the window [-512, 0) that lies wholly in the zero padding (X = 0) and brought to frame 0 (window
+// [-256, 256)) in 16 hops of 16 samples.  Per bin and frame that is 2 h + 8 FP64 instructions with the twiddles W^{nk}
+// (the same for every octave) in registers -- 40 / 24 / 4 against the ~6.9 k of an FFT-512 + split per frame shared by 85
+// bins (81 per bin) -- and no shared-memory exchange at all.  In octave 6 every frame holds the whole 250-sample
+// signal: after the start-up the recurrence is a pure rotation.
+// Rounding: one unit rotation per hop, <= 79 hops: 3e-14 of the largest |X| the bin has seen, the same order as the
+// FFT's own error and nine orders below the complex64 rounding that follows (A/B against the FFT form: 0 of 1,048,320
+// chroma values differ on 130 segments, tools/cens_ab.py).
+// Threads 0-95 own the bins of octave 4, threads 96-191 those of octaves 5 AND 6 (2844 against 2664 FP64 instructions
+// per bin).  Frames are produced in batches of 16 into a shared spectrum tile; the basis product runs with LANES =
+// FRAMES (row pitch 89 float2: the sixteen frames of a half-warp fall into sixteen bank pairs) and three adjacent basis
+// rows per thread: one conflict-free data load feeds twelve FMAs, the weights are half-warp broadcasts from rows padded
+// with zeros on either side (a zero weight adds +-0: the sums are those of the per-row product).  The three per-octave
+// chroma sums go to Workspace::cens_lo and k_cens adds them after its own octaves 0-3 in the order the single-kernel
+// version used (bit-identical folding).
+constexpr int kLoGroup = 96, kLoThreads = 2 * kLoGroup;                             // 192
+constexpr int kLoBatch = 16, kLoSpecPitch = 89;
 constexpr int kLoFrames = 63;                                                       // 1 s mode only: T = 63
-__host__ __device__ constexpr int lo_hop(int q) { return 16 >> q; }                 // q = octave - 4
-__host__ __device__ constexpr int lo_dlen(int q) { return kLoFrames * lo_hop(q) + 256; }
-static_assert(kBinSpan <= kLoSpecPitch && kBinSpan <= 32 * kLoWarpsPerOct, "one thread per touched bin");
-static_assert(kLoOcts * kCqtBinsPerOct * (kLoBatch / 2) == 3 * kLoThreads, "basis product: three items per thread");
+constexpr int kLoPadL = 8, kLoWPitch = 33;                                          // padded weight rows: jj in [-8, 25)
+constexpr int kLoTriples = kCqtBinsPerOct / 3;
+constexpr int kLoD0 = 256 + kLoFrames * 16, kLoD1 = 256 + kLoFrames * 8, kLoD2 = 256;
+static_assert(kBinSpan <= kLoSpecPitch && kLoSpecPitch <= kLoGroup, "one thread per touched bin");
+static_assert(kLoOcts * kLoTriples * kLoBatch == 3 * kLoThreads, "basis product: three items per thread");
 
 struct CensLoSmem {
-    double d0[lo_dlen(0)], d1[lo_dlen(1)], d2[lo_dlen(2)];       // x[i] - x[i - 512] per octave
+    double d0[kLoD0], d1[kLoD1], d2[kLoD2];                      // x[i] - x[i - 512] per octave (octave 6: x[i], i < 256)
     float2 spec[kLoOcts][kLoBatch][kLoSpecPitch];
-    float cqmag[kLoOcts][kLoBatch][kCqtBinsPerOct + 4];
-    float2 basis[2][kCqtBinsPerOct * kBasisPitch];
-    short bstart[kCqtBinsPerOct + 4];
+    float2 wpad[2][kCqtBinsPerOct * kLoWPitch];                  // [0]: basis, [1]: basis * sqrt(2) (octave 5)
+    float m2[kLoOcts][kLoBatch][kLoTriples];                     // |CQ| of row 3 p + 2 (goes to chroma p + 1)
     double inv_sl[kLoOcts * kCqtBinsPerOct];
+    short tri_s[kLoTriples], tri_d1[kLoTriples], tri_d2[kLoTriples], tri_u[kLoTriples];
+    short cnt[kCqtBinsPerOct];
 };
+static_assert(sizeof(CensLoSmem) <= 75 * 1024 + 640, "three CTAs per SM");
 
-// `frames` frames of one bin: store X, then hop.  `mac_hops`: hops whose difference samples can be non-zero.
-template <int H>
-__device__ __forceinline__ void lo_slide(const double* __restrict__ d, const double2 (&tw)[16], double2 rot, double2& X,
-                                         int& j, int hops, bool emit, float2* __restrict__ out, bool store) {
-    constexpr int kPre = 256 / H;
-    // octave 6 (H = 4): the signal ends at sample 250, differences are zero from hop 63 on
-    const int mac_end = H == 4 ? 63 : (1 << 30);
-    for (int i = 0; i < hops; ++i, ++j) {
-        if (emit && store) out[(j - kPre) % kLoBatch * kLoSpecPitch] = make_float2((float)X.x, (float)X.y);
-        double ar0 = X.x, ai0 = X.y, ar1 = 0.0, ai1 = 0.0;
-        if (j < mac_end) {
-            const double2* dp = reinterpret_cast<const double2*>(d + j * H);
+// `hops` hops of H samples of one bin: (store X as complex64,) then X <- rot (X + sum_n d[n] tw[n]).
+template <int H, bool EMIT>
+__device__ __forceinline__ void lo_hops(const double* __restrict__ d, const double2 (&tw)[16], double2 rot, double2& X,
+                                        int hops, float2* __restrict__ out, bool store) {
+#pragma unroll 2
+    for (int i = 0; i < hops; ++i) {
+        if (EMIT && store) out[i * kLoSpecPitch] = make_float2((float)X.x, (float)X.y);
+        const double2* dp = reinterpret_cast<const double2*>(d + i * H);
+        double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
 #pragma unroll
-            for (int n = 0; n < H; n += 2) {
-                const double2 dd = dp[n >> 1];
-                ar0 = fma(dd.x, tw[n].x, ar0);         ai0 = fma(dd.x, tw[n].y, ai0);
-                ar1 = fma(dd.y, tw[n + 1].x, ar1);     ai1 = fma(dd.y, tw[n + 1].y, ai1);
-            }
+        for (int n = 0; n < H; n += 2) {
+            const double2 dd = dp[n >> 1];
+            ar0 = fma(dd.x, tw[n].x, ar0);         ai0 = fma(dd.x, tw[n].y, ai0);
+            ar1 = fma(dd.y, tw[n + 1].x, ar1);     ai1 = fma(dd.y, tw[n + 1].y, ai1);
         }
-        const double ar = ar0 + ar1, ai = ai0 + ai1;
+        const double ar = X.x + (ar0 + ar1), ai = X.y + (ai0 + ai1);
         X.x = fma(ar, rot.x, -(ai * rot.y));
         X.y = fma(ar, rot.y, ai * rot.x);
     }
 }
 
-__global__ void __launch_bounds__(kLoThreads, 2) k_cens_lo(Geometry g, Tables tb, Workspace ws) {
+__global__ void __launch_bounds__(kLoThreads, 3) k_cens_lo(Geometry g, Tables tb, Workspace ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CensLoSmem& S = *reinterpret_cast<CensLoSmem*>(smem_raw);
     const int tid = threadIdx.x, b = blockIdx.x, T = g.T;
@@ -500,13 +504,19 @@ __global__ void __launch_bounds__(kLoThreads, 2) k_cens_lo(Geometry g, Tables tb
         const float* bre = tb.cqt_re + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
         const float* bim = tb.cqt_im + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
         const double sqrt2 = sqrt(2.0);
-        for (int i = tid; i < kCqtBinsPerOct * kCqtEllWidth; i += kLoThreads) {
-            const float re = bre[i], im = bim[i];
-            const int o = (i / kCqtEllWidth) * kBasisPitch + i % kCqtEllWidth;
-            S.basis[0][o] = make_float2(re, im);
-            S.basis[1][o] = make_float2((float)((double)re * sqrt2), (float)((double)im * sqrt2));   // as in k_cens
+        for (int i = tid; i < kCqtBinsPerOct * kLoWPitch; i += kLoThreads) {
+            const int r = i / kLoWPitch, jj = i - r * kLoWPitch - kLoPadL;
+            float re = 0.f, im = 0.f;
+            if (jj >= 0 && jj < kCqtEllWidth) { re = bre[r * kCqtEllWidth + jj]; im = bim[r * kCqtEllWidth + jj]; }
+            S.wpad[0][i] = make_float2(re, im);
+            S.wpad[1][i] = make_float2((float)((double)re * sqrt2), (float)((double)im * sqrt2));   // as in k_cens
         }
-        if (tid < kCqtBinsPerOct) S.bstart[tid] = (short)(tb.cqt_start[tun * kCqtBinsPerOct + tid] - kBinLo);
+        if (tid < kCqtBinsPerOct) {                              // taps of the row up to its last non-zero weight
+            int c = 1;
+            for (int jj = 1; jj < kCqtEllWidth; ++jj)
+                if (bre[tid * kCqtEllWidth + jj] != 0.f || bim[tid * kCqtEllWidth + jj] != 0.f) c = jj + 1;
+            S.cnt[tid] = (short)c;
+        }
         // rows of octave o: inv_sl index kCqtBins - 36 (o + 1) + r; octaves 6, 5, 4 are the first three groups of 36
         const double* slen = tb.cqt_sqrt_len + (size_t)tun * kCqtBins;
         for (int i = tid; i < kLoOcts * kCqtBinsPerOct; i += kLoThreads) S.inv_sl[i] = 1.0 / slen[i];
@@ -516,17 +526,27 @@ __global__ void __launch_bounds__(kLoThreads, 2) k_cens_lo(Geometry g, Tables tb
         const int n = 16000 >> (kLoFirstOct + q);
         const float* x = G + goff(kLoFirstOct + q) + kGPad;
         double* d = q == 0 ? S.d0 : (q == 1 ? S.d1 : S.d2);
-        for (int i = tid; i < lo_dlen(q); i += kLoThreads) {
+        const int len = q == 0 ? kLoD0 : (q == 1 ? kLoD1 : kLoD2);
+        for (int i = tid; i < len; i += kLoThreads) {
             const double a = i < n ? (double)__ldg(x + i) : 0.0;
             const double c = (i >= 512 && i - 512 < n) ? (double)__ldg(x + i - 512) : 0.0;
             d[i] = a - c;
         }
     }
-    // this thread's bin: twiddles W^{nk} (n < h) and the hop rotation W^{-hk}
-    const int q = tid / (32 * kLoWarpsPerOct);                  // octave - 4, warp-uniform
-    const int kk = tid - q * (32 * kLoWarpsPerOct);             // bin - kBinLo (lanes past the span idle along)
-    const int k = kBinLo + kk, H = lo_hop(q);
-    auto wpow = [&](int m) {                                    // exp(-2 pi i m / 512), m in [0, 512)
+    __syncthreads();
+    if (tid < kLoTriples) {
+        const short* bs = tb.cqt_start + tun * kCqtBinsPerOct + 3 * tid;
+        const int s0 = bs[0], d1 = bs[1] - s0, d2 = bs[2] - s0;      // band starts do not decrease with the row
+        S.tri_s[tid] = (short)(s0 - kBinLo);
+        S.tri_d1[tid] = (short)d1;
+        S.tri_d2[tid] = (short)d2;
+        S.tri_u[tid] = (short)max((int)S.cnt[3 * tid], max(d1 + (int)S.cnt[3 * tid + 1], d2 + (int)S.cnt[3 * tid + 2]));
+    }
+    // this thread's bin: twiddles W^{nk}, n < 16, and the hop rotations W^{-hk}
+    const int grp = tid / kLoGroup;                             // warp-uniform: 0 = octave 4, 1 = octaves 5 and 6
+    const int kk = tid - grp * kLoGroup;                        // bin - kBinLo (lanes past the span idle along)
+    const int k = kBinLo + kk;
+    auto wpow = [&](int m) {                                    // exp(-2 pi i m / 512)
         m &= 511;
         const double2 w = __ldg(tb.ptw512 + (m <= 256 ? m : 512 - m));
         return m <= 256 ? w : make_double2(w.x, -w.y);
@@ -534,59 +554,67 @@ __global__ void __launch_bounds__(kLoThreads, 2) k_cens_lo(Geometry g, Tables tb
     double2 tw[16];
 #pragma unroll
     for (int n = 0; n < 16; ++n) tw[n] = wpow(n * k);
-    const double2 rc = wpow(H * k);
-    const double2 rot = make_double2(rc.x, -rc.y);
-    double2 X = make_double2(0.0, 0.0);
-    int j = 0;
+    auto conj_w = [&](int m) { const double2 w = wpow(m); return make_double2(w.x, -w.y); };
+    const double2 rot16 = conj_w(16 * k), rot8 = conj_w(8 * k), rot4 = conj_w(4 * k);
     const bool store = kk < kLoSpecPitch;                       // bins past kBinHi only ever meet zero weights
-    float2* out = &S.spec[q][0][store ? kk : 0];
-    const double* dq = q == 0 ? S.d0 : (q == 1 ? S.d1 : S.d2);
-    __syncthreads();
-    // start-up: slide from the all-zero window to frame 0
-    if (q == 0) lo_slide<16>(dq, tw, rot, X, j, 16, false, out, store);
-    else if (q == 1) lo_slide<8>(dq, tw, rot, X, j, 32, false, out, store);
-    else lo_slide<4>(dq, tw, rot, X, j, 64, false, out, store);
+    const int ks = store ? kk : 0;
+    double2 Xa = make_double2(0.0, 0.0), Xb = make_double2(0.0, 0.0);
+    // start-up: from the all-zero window to frame 0 in 16 hops of 16 samples (every octave)
+    lo_hops<16, false>(grp == 0 ? S.d0 : S.d1, tw, rot16, Xa, 16, nullptr, false);
+    if (grp == 1) lo_hops<16, false>(S.d2, tw, rot16, Xb, 16, nullptr, false);
     float* lo = ws.cens_lo + (size_t)b * kLoOcts * 12 * T;
+    const int f = tid & 15, p = tid >> 4;                       // basis product: frame of the batch, row triple
+    __syncthreads();                                            // tri_* visible
+    const int ts = S.tri_s[p], td1 = S.tri_d1[p], td2 = S.tri_d2[p], tu = S.tri_u[p];
     for (int t0 = 0; t0 < T; t0 += kLoBatch) {
         const int nf = min(kLoBatch, T - t0);
-        if (q == 0) lo_slide<16>(dq, tw, rot, X, j, nf, true, out, store);
-        else if (q == 1) lo_slide<8>(dq, tw, rot, X, j, nf, true, out, store);
-        else lo_slide<4>(dq, tw, rot, X, j, nf, true, out, store);
+        if (grp == 0) {
+            lo_hops<16, true>(S.d0 + 256 + t0 * 16, tw, rot16, Xa, nf, &S.spec[0][0][ks], store);
+        } else {
+            lo_hops<8, true>(S.d1 + 256 + t0 * 8, tw, rot8, Xa, nf, &S.spec[1][0][ks], store);
+            for (int i = 0; i < nf; ++i) {                      // octave 6: rotation only
+                if (store) S.spec[2][i][ks] = make_float2((float)Xb.x, (float)Xb.y);
+                const double xr = Xb.x, xi = Xb.y;
+                Xb.x = fma(xr, rot4.x, -(xi * rot4.y));
+                Xb.y = fma(xr, rot4.y, xi * rot4.x);
+            }
+        }
         __syncthreads();
-        // basis product: item (octave q2, row r, frames 2 fp and 2 fp + 1)
-#pragma unroll 1
+        float m0[kLoOcts], m1[kLoOcts];
+#pragma unroll
         for (int q2 = 0; q2 < kLoOcts; ++q2) {
-            const int r = tid % kCqtBinsPerOct, fp = tid / kCqtBinsPerOct;
             const int o = kLoFirstOct + q2;
-            const float2* wr = S.basis[o & 1] + r * kBasisPitch;
-            const float2* sp0 = &S.spec[q2][2 * fp][S.bstart[r]];
-            const float2* sp1 = sp0 + kLoSpecPitch;
-            const int wn = tb.cqt_gw[r >= 20 ? 0 : (r >= 4 ? 1 : 2)];
-            float cr0 = 0.f, ci0 = 0.f, cr1 = 0.f, ci1 = 0.f;
+            const float2* w0 = S.wpad[o & 1] + 3 * p * kLoWPitch + kLoPadL;
+            const float2* w1 = w0 + kLoWPitch - td1;
+            const float2* w2 = w0 + 2 * kLoWPitch - td2;
+            const float2* sp = &S.spec[q2][f][ts];
+            float cr0 = 0.f, ci0 = 0.f, cr1 = 0.f, ci1 = 0.f, cr2 = 0.f, ci2 = 0.f;
 #pragma unroll 4
-            for (int jj = 0; jj < wn; ++jj) {
-                const float2 w = wr[jj];
-                const float2 a = sp0[jj], c = sp1[jj];
-                cr0 = fmaf(w.x, a.x, cr0); cr0 = fmaf(-w.y, a.y, cr0);
-                ci0 = fmaf(w.x, a.y, ci0); ci0 = fmaf(w.y, a.x, ci0);
-                cr1 = fmaf(w.x, c.x, cr1); cr1 = fmaf(-w.y, c.y, cr1);
-                ci1 = fmaf(w.x, c.y, ci1); ci1 = fmaf(w.y, c.x, ci1);
+            for (int u = 0; u < tu; ++u) {
+                const float2 d = sp[u];
+                const float2 a = w0[u], c = w1[u], e = w2[u];
+                cr0 = fmaf(a.x, d.x, cr0); cr0 = fmaf(-a.y, d.y, cr0);
+                ci0 = fmaf(a.x, d.y, ci0); ci0 = fmaf(a.y, d.x, ci0);
+                cr1 = fmaf(c.x, d.x, cr1); cr1 = fmaf(-c.y, d.y, cr1);
+                ci1 = fmaf(c.x, d.y, ci1); ci1 = fmaf(c.y, d.x, ci1);
+                cr2 = fmaf(e.x, d.x, cr2); cr2 = fmaf(-e.y, d.y, cr2);
+                ci2 = fmaf(e.x, d.y, ci2); ci2 = fmaf(e.y, d.x, ci2);
             }
+            // complex64 response, V /= sqrt(lengths) (complex128 math, complex64 store), |V|: as in k_cens
             const float pow2 = (float)(1 << (o >> 1));
-            const double sl = S.inv_sl[(kCqtOctaves - 1 - o) * kCqtBinsPerOct + r];
-            S.cqmag[q2][2 * fp][r] = c64_abs_f32((float)((double)(cr0 * pow2) * sl), (float)((double)(ci0 * pow2) * sl));
-            S.cqmag[q2][2 * fp + 1][r] = c64_abs_f32((float)((double)(cr1 * pow2) * sl), (float)((double)(ci1 * pow2) * sl));
+            const double* sl = S.inv_sl + (kCqtOctaves - 1 - o) * kCqtBinsPerOct + 3 * p;
+            m0[q2] = c64_abs_f32((float)((double)(cr0 * pow2) * sl[0]), (float)((double)(ci0 * pow2) * sl[0]));
+            m1[q2] = c64_abs_f32((float)((double)(cr1 * pow2) * sl[1]), (float)((double)(ci1 * pow2) * sl[1]));
+            S.m2[q2][f][p] = c64_abs_f32((float)((double)(cr2 * pow2) * sl[2]), (float)((double)(ci2 * pow2) * sl[2]));
         }
         __syncthreads();
-        // cq_to_chroma per octave: chroma c sums bins {3c-1, 3c, 3c+1} (mod 36)
-        for (int i = tid; i < kLoOcts * 12 * kLoBatch; i += kLoThreads) {
-            const int f = i % kLoBatch, c = (i / kLoBatch) % 12, q2 = i / (12 * kLoBatch);
-            if (f < nf) {
-                const float* m = S.cqmag[q2][f];
-                lo[(q2 * 12 + c) * T + t0 + f] = m[(3 * c + 35) % 36] + m[3 * c] + m[3 * c + 1];
-            }
+        // cq_to_chroma per octave: chroma c = p sums rows {3c-1, 3c, 3c+1} (mod 36), in that order
+        if (f < nf) {
+#pragma unroll
+            for (int q2 = 0; q2 < kLoOcts; ++q2)
+                lo[(q2 * 12 + p) * T + t0 + f] = S.m2[q2][f][(p + kLoTriples - 1) % kLoTriples] + m0[q2] + m1[q2];
         }
-        // the next batch's slide writes `spec` (free since the barrier above); its basis product, which writes `cqmag`,
+        // the next batch's slide writes `spec` (free since the barrier above); its basis product, which writes `m2`,
         // comes after that slide's barrier
     }
 }
