@@ -214,13 +214,86 @@ __global__ void __launch_bounds__(kDecTileThreads) k_dec_tile_long(const float* 
 constexpr int kCensThreads = 256, kCensTeams = kCensThreads / 16;
 constexpr int kLoFirstOct = 4, kLoOcts = kCqtOctaves - kLoFirstOct;   // octaves of k_cens_lo (1 s mode)
 
-// ~101 KB and <= 128 registers: two 256-thread CTAs per SM, so a 592-segment chunk is exactly two full waves (at three
-// 128-thread CTAs per SM the second wave ran one third full)
-// row pitch of the basis bands in shared memory: 21 float2 = 42 words, so the 16 rows a half-warp reads together fall
-// into 16 different bank pairs (at the table's pitch of 20 they fell into 4: a 4-way conflict on every weight load,
-// a third of this kernel's shared-memory wavefronts)
-constexpr int kBasisPitch = kCqtEllWidth + 1;
+// ---- the sparse basis product  C[r, t] = sum_k B[r, k] X_t[k]  with LANES = FRAMES (r02-h)
+// The spectra of sixteen frames sit in shared memory at a row pitch of 89 float2 (178 words: the sixteen frames of a
+// half-warp fall into sixteen different bank pairs), a thread takes one frame and THREE adjacent basis rows: one
+// conflict-free data load feeds twelve FMAs, the weights are half-warp broadcasts.  The band of row r starts at bin
+// cqt_start[r]; the three rows of a triple start within 7 bins of each other (all 100 tunings), so their weights are
+// staged in rows padded with zeros on either side and walked over the union of the three bands -- a zero weight adds
+// +-0, so every sum is bit-identical to the per-row product the r01 kernel ran with lanes = rows (whose data loads
+// were 2.5-way bank conflicts and whose weight loads doubled the wavefronts: 0.19 wavefronts per complex MAC against
+// 0.08 here).
+constexpr int kCqSpecPitch = 89;
+constexpr int kCqPadL = 8, kCqWPitch = 33;                            // padded weight rows: tap index in [-8, 25)
+constexpr int kCqTriples = kCqtBinsPerOct / 3;
+static_assert(kBinSpan + 3 <= kCqSpecPitch, "bands may read up to three bins past kBinHi (zero weights there)");
 
+struct CqTables {
+    float2 wpad[2][kCqtBinsPerOct * kCqWPitch];                  // [0]: basis, [1]: basis * sqrt(2) (odd octaves), (re, im)
+    short tri_s[kCqTriples], tri_d1[kCqTriples], tri_d2[kCqTriples], tri_u[kCqTriples];
+    short cnt[kCqtBinsPerOct];
+};
+
+// Stage the basis of tuning `tun`.  Ends with a CTA barrier.
+__device__ __forceinline__ void cq_stage(CqTables& Q, const Tables& tb, int tun, int tid, int nthreads) {
+    const float* bre = tb.cqt_re + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
+    const float* bim = tb.cqt_im + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
+    const double sqrt2 = sqrt(2.0);
+    for (int i = tid; i < kCqtBinsPerOct * kCqWPitch; i += nthreads) {
+        const int r = i / kCqWPitch, jj = i - r * kCqWPitch - kCqPadL;
+        float re = 0.f, im = 0.f;
+        if (jj >= 0 && jj < kCqtEllWidth) { re = bre[r * kCqtEllWidth + jj]; im = bim[r * kCqtEllWidth + jj]; }
+        Q.wpad[0][i] = make_float2(re, im);
+        // fft_basis *= sqrt(sr / my_sr) rounded to complex64: odd octaves carry a factor sqrt(2); the remaining
+        // power of two is applied to the (linear) response, which is exact
+        Q.wpad[1][i] = make_float2((float)((double)re * sqrt2), (float)((double)im * sqrt2));
+    }
+    if (tid < kCqtBinsPerOct) {                                  // taps of the row up to its last non-zero weight
+        int c = 1;
+        for (int jj = 1; jj < kCqtEllWidth; ++jj)
+            if (bre[tid * kCqtEllWidth + jj] != 0.f || bim[tid * kCqtEllWidth + jj] != 0.f) c = jj + 1;
+        Q.cnt[tid] = (short)c;
+    }
+    __syncthreads();
+    if (tid < kCqTriples) {
+        const int16_t* bs = tb.cqt_start + tun * kCqtBinsPerOct + 3 * tid;
+        const int s0 = bs[0], d1 = bs[1] - s0, d2 = bs[2] - s0;      // band starts do not decrease with the row
+        Q.tri_s[tid] = (short)(s0 - kBinLo);
+        Q.tri_d1[tid] = (short)d1;
+        Q.tri_d2[tid] = (short)d2;
+        Q.tri_u[tid] = (short)max((int)Q.cnt[3 * tid], max(d1 + (int)Q.cnt[3 * tid + 1], d2 + (int)Q.cnt[3 * tid + 2]));
+    }
+    __syncthreads();
+}
+
+// |CQ| of rows 3 p, 3 p + 1, 3 p + 2 of octave o for the frame whose spectrum row is `sp` (= spec row + tri_s[p]).
+// w0 = wpad[o & 1] + 3 p kCqWPitch + kCqPadL; sl = 1 / sqrt(lengths) of row 3 p of this octave.
+__device__ __forceinline__ void cq_triple(const float2* __restrict__ w0, int td1, int td2, int tu,
+                                          const float2* __restrict__ sp, int o, const double* __restrict__ sl,
+                                          float& m0, float& m1, float& m2) {
+    const float2* w1 = w0 + kCqWPitch - td1;
+    const float2* w2 = w0 + 2 * kCqWPitch - td2;
+    float cr0 = 0.f, ci0 = 0.f, cr1 = 0.f, ci1 = 0.f, cr2 = 0.f, ci2 = 0.f;
+#pragma unroll 4
+    for (int u = 0; u < tu; ++u) {
+        const float2 d = sp[u];
+        const float2 a = w0[u], c = w1[u], e = w2[u];
+        cr0 = fmaf(a.x, d.x, cr0); cr0 = fmaf(-a.y, d.y, cr0);
+        ci0 = fmaf(a.x, d.y, ci0); ci0 = fmaf(a.y, d.x, ci0);
+        cr1 = fmaf(c.x, d.x, cr1); cr1 = fmaf(-c.y, d.y, cr1);
+        ci1 = fmaf(c.x, d.y, ci1); ci1 = fmaf(c.y, d.x, ci1);
+        cr2 = fmaf(e.x, d.x, cr2); cr2 = fmaf(-e.y, d.y, cr2);
+        ci2 = fmaf(e.x, d.y, ci2); ci2 = fmaf(e.y, d.x, ci2);
+    }
+    // complex64 response, then V /= sqrt(lengths) (complex128 math, complex64 store), then |V|
+    const float pow2 = (float)(1 << (o >> 1));
+    m0 = c64_abs_f32((float)((double)(cr0 * pow2) * sl[0]), (float)((double)(ci0 * pow2) * sl[0]));
+    m1 = c64_abs_f32((float)((double)(cr1 * pow2) * sl[1]), (float)((double)(ci1 * pow2) * sl[1]));
+    m2 = c64_abs_f32((float)((double)(cr2 * pow2) * sl[2]), (float)((double)(ci2 * pow2) * sl[2]));
+}
+
+// ~108 KB and <= 128 registers: two 256-thread CTAs per SM, so a 592-segment chunk is exactly two full waves (at three
+// 128-thread CTAs per SM the second wave ran one third full)
 struct CensSmem {
     union {
         double2 xch[kCensTeams][16 * 17];              // FFT exchange buffers (CQT phase)
@@ -229,16 +302,16 @@ struct CensSmem {
             float quant[12 * kMaxFrames];
         } post;
     } u;
-    float2 spec[kCensTeams][kBinSpan + 3];
-    float cqmag[kCensTeams][kCqtBinsPerOct + 4];
+    float2 spec[kCensTeams][kCqSpecPitch];             // complex64 STFT bins kBinLo.. of the round's sixteen frames
+    float m2[2][kCensTeams][kCqTriples];               // |CQ| of row 3 p + 2 (goes to chroma p + 1), by octave parity
     float csum[12 * kMaxFrames];                       // folded chroma sums of the CQT phase
-    float2 basis[2][kCqtBinsPerOct * kBasisPitch];     // [0]: basis, [1]: basis * sqrt(2) (odd octaves), (re, im)
-    short bstart[kCqtBinsPerOct + 4];                  // first bin of each row's band - kBinLo
+    CqTables cq;
     double inv_sl[kCqtBins];                           // 1 / sqrt(lengths)
     double swin[43];                                   // hann(43) / sum
     double dscratch[32];
     float fscratch[32];
 };
+static_assert(sizeof(CensSmem) <= 111 * 1024, "two CTAs per SM");
 
 template <bool LONG>
 __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restrict__ y, Geometry g, Tables tb,
@@ -259,18 +332,6 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
     // ---- stage the basis of this segment's tuning and the smoothing window
     const int tun = ws.tuning[b * 2 + 1];
     {
-        const float* bre = tb.cqt_re + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
-        const float* bim = tb.cqt_im + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
-        const double sqrt2 = sqrt(2.0);
-        for (int i = tid; i < kCqtBinsPerOct * kCqtEllWidth; i += kCensThreads) {
-            const float re = bre[i], im = bim[i];
-            const int o = (i / kCqtEllWidth) * kBasisPitch + i % kCqtEllWidth;
-            S.basis[0][o] = make_float2(re, im);
-            // fft_basis *= sqrt(sr / my_sr) rounded to complex64: odd octaves carry a factor sqrt(2); the remaining
-            // power of two is applied to the (linear) response, which is exact
-            S.basis[1][o] = make_float2((float)((double)re * sqrt2), (float)((double)im * sqrt2));
-        }
-        if (tid < kCqtBinsPerOct) S.bstart[tid] = (short)(tb.cqt_start[tun * kCqtBinsPerOct + tid] - kBinLo);
         const double* slen = tb.cqt_sqrt_len + (size_t)tun * kCqtBins;
         for (int i = tid; i < kCqtBins; i += kCensThreads) S.inv_sl[i] = 1.0 / slen[i];
     }
@@ -280,9 +341,11 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
         for (int j = 0; j < 43; ++j) wsum += 0.5 - 0.5 * cos(2.0 * 3.14159265358979323846 * (double)j / 42.0);
         S.swin[tid] = (0.5 - 0.5 * cos(2.0 * 3.14159265358979323846 * (double)tid / 42.0)) / wsum;
     }
-    __syncthreads();
+    cq_stage(S.cq, tb, tun, tid, kCensThreads);                  // ends with a barrier
 
-    // ---- CQT -> chroma fold, one half-warp per frame, 7 octaves each
+    // ---- CQT -> chroma fold.  A round is sixteen frames: per octave every half-warp transforms its frame
+    // (team_fft<16>) and leaves the 85 touched bins in `spec`; then the basis product runs over the round's sixteen
+    // spectra with lanes = frames (thread = frame pf, row triple pp; cq_triple above).
     const int h = lane & 15, team = tid >> 4;
     const int partner = (lane & 16) | ((16 - h) & 15);
     double2* xch = S.u.xch[team];
@@ -292,15 +355,18 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
     const double2 wp = __ldg(tb.ptw512 + h);
     const double2 wl = make_double2(wp.y, -wp.x);                         // -i * exp(-2 pi i h / 512)
     float2* spec = S.spec[team];
-    float* cqmag = S.cqmag[team];
+    const int pf = tid & 15, pp = tid >> 4;                               // product: frame of the round, row triple
+    const bool pact = pp < kCqTriples;                                    // warps 6, 7 only transform
+    const int pq = pact ? pp : 0;
+    const int ts = S.cq.tri_s[pq], td1 = S.cq.tri_d1[pq], td2 = S.cq.tri_d2[pq], tu = S.cq.tri_u[pq];
     // long mode: phase 1 = the CQT frames of this CTA's share (grid (segment, part)), phase 2 = post-processing
-    // (trip count from blockIdx only, `valid` gates the result: the shuffles and warp barriers inside are convergent)
+    // (trip count from blockIdx only: the barriers, shuffles and warp barriers inside are convergent)
     const int t_first = LONG ? (int)blockIdx.y * kCensTeams : 0;
     const int t_step = kCensTeams * (LONG ? (int)gridDim.y : 1);
     for (int t0 = t_first; t0 < T && phase != 2; t0 += t_step) {
-        const int t = t0 + 2 * warp + (lane >> 4);
+        const int t = t0 + team;
         const bool valid = t < T;
-        float csum = 0.f;                                        // lanes h < 12: chroma c = h
+        float csum = 0.f, pm0 = 0.f, pm1 = 0.f;                  // thread (pf, pp): chroma pp of frame t0 + pf
 #pragma unroll 1
         for (int o = 0; o < n_oct; ++o) {
             const int c0 = (valid ? t : 0) * (128 >> o) - 128;   // first complex sample of the frame
@@ -323,53 +389,34 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
                 }
             }
             team_fft<16>(a, tw, 1, xch, h);
+            __syncthreads();                                     // the previous octave's product has read `spec`
             auto emit = [&](int k, double2 t2) {
-                if (k >= kBinLo && k <= kBinHi)
+                if (k >= kBinLo && k < kBinLo + kCqSpecPitch)    // bins past kBinHi only ever meet zero weights
                     spec[k - kBinLo] = make_float2((float)(0.5 * t2.x), (float)(0.5 * t2.y));   // complex64 STFT
             };
             team_rsplit<16, 3, 9>(a, wl, h, partner, emit);
-            __syncwarp();
-            const float2* bas = S.basis[o & 1];
-            const float pow2 = (float)(1 << (o >> 1));
-            const double* isl = S.inv_sl + (kCqtBins - kCqtBinsPerOct * (o + 1));
-            // three rounds of 16 / 16 / 4 rows per team.  The band of a row widens with the row index (8 .. 18 bins), a
-            // round costs the width of its widest row for every lane, so the four-row round takes the NARROW rows 0-3:
-            // 18 + 14 + 11 tap steps instead of the 13 + 17 + 18 of rows 0-15 / 16-31 / 32-35 (tuning 0)
-#pragma unroll
-            for (int rr = 0; rr < 3; ++rr) {
-                const int r = rr == 0 ? 20 + h : (rr == 1 ? 4 + h : h);
-                if (rr < 2 || h < 4) {
-                    float cr = 0.f, ci = 0.f;
-                    const float2* wr = bas + r * kBasisPitch;
-                    const float2* sp = spec + S.bstart[r];
-                    const int wn = tb.cqt_gw[rr];
-#pragma unroll 4
-                    for (int j = 0; j < wn; ++j) {
-                        const float2 w = wr[j];
-                        const float2 d = sp[j];
-                        cr = fmaf(w.x, d.x, cr); cr = fmaf(-w.y, d.y, cr);
-                        ci = fmaf(w.x, d.y, ci); ci = fmaf(w.y, d.x, ci);
-                    }
-                    // complex64 response, then V /= sqrt(lengths) (complex128 math, complex64 store), then |V|
-                    const double sl = isl[r];
-                    cqmag[r] = c64_abs_f32((float)((double)(cr * pow2) * sl), (float)((double)(ci * pow2) * sl));
-                }
+            __syncthreads();
+            if (pact) {
+                // cq_to_chroma: chroma c sums bins {3c-1, 3c, 3c+1} (mod 36) of every octave, octave by octave
+                if (o > 0) csum += S.m2[(o - 1) & 1][pf][(pp + kCqTriples - 1) % kCqTriples] + pm0 + pm1;
+                float m2v;
+                cq_triple(S.cq.wpad[o & 1] + 3 * pp * kCqWPitch + kCqPadL, td1, td2, tu, &S.spec[pf][ts], o,
+                          S.inv_sl + (kCqtBins - kCqtBinsPerOct * (o + 1)) + 3 * pp, pm0, pm1, m2v);
+                S.m2[o & 1][pf][pp] = m2v;
             }
-            __syncwarp();
-            if (h < 12) {
-                // cq_to_chroma: chroma c sums bins {3c-1, 3c, 3c+1} (mod 36) of every octave
-                const int j0 = (3 * h + 35) % 36;
-                csum += cqmag[j0] + cqmag[3 * h] + cqmag[3 * h + 1];
-            }
-            __syncwarp();
         }
-        if (h < 12 && valid) {
-            if (n_oct < kCqtOctaves) {                           // octaves 4-6 come from k_cens_lo, added in octave order
-                const float* lo = ws.cens_lo + ((size_t)b * kLoOcts * 12 + h) * T + t;
+        __syncthreads();
+        if (pact) {
+            csum += S.m2[(n_oct - 1) & 1][pf][(pp + kCqTriples - 1) % kCqTriples] + pm0 + pm1;
+            const int tt = t0 + pf;
+            if (tt < T) {
+                if (n_oct < kCqtOctaves) {                       // octaves 4-6 come from k_cens_lo, added in octave order
+                    const float* lo = ws.cens_lo + ((size_t)b * kLoOcts * 12 + pp) * T + tt;
 #pragma unroll
-                for (int q2 = 0; q2 < kLoOcts; ++q2) csum += lo[q2 * 12 * T];
+                    for (int q2 = 0; q2 < kLoOcts; ++q2) csum += lo[q2 * 12 * T];
+                }
+                p_csum[pp * T + tt] = csum;
             }
-            p_csum[h * T + t] = csum;
         }
     }
     if (LONG && phase == 1) return;
@@ -454,10 +501,9 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
 // chroma sums go to Workspace::cens_lo and k_cens adds them after its own octaves 0-3 in the order the single-kernel
 // version used (bit-identical folding).
 constexpr int kLoGroup = 96, kLoThreads = 2 * kLoGroup;                             // 192
-constexpr int kLoBatch = 16, kLoSpecPitch = 89;
+constexpr int kLoBatch = 16, kLoSpecPitch = kCqSpecPitch;
 constexpr int kLoFrames = 63;                                                       // 1 s mode only: T = 63
-constexpr int kLoPadL = 8, kLoWPitch = 33;                                          // padded weight rows: jj in [-8, 25)
-constexpr int kLoTriples = kCqtBinsPerOct / 3;
+constexpr int kLoTriples = kCqTriples;
 constexpr int kLoD0 = 256 + kLoFrames * 16, kLoD1 = 256 + kLoFrames * 8, kLoD2 = 256;
 static_assert(kBinSpan <= kLoSpecPitch && kLoSpecPitch <= kLoGroup, "one thread per touched bin");
 static_assert(kLoOcts * kLoTriples * kLoBatch == 3 * kLoThreads, "basis product: three items per thread");
@@ -465,11 +511,9 @@ static_assert(kLoOcts * kLoTriples * kLoBatch == 3 * kLoThreads, "basis product:
 struct CensLoSmem {
     double d0[kLoD0], d1[kLoD1], d2[kLoD2];                      // x[i] - x[i - 512] per octave (octave 6: x[i], i < 256)
     float2 spec[kLoOcts][kLoBatch][kLoSpecPitch];
-    float2 wpad[2][kCqtBinsPerOct * kLoWPitch];                  // [0]: basis, [1]: basis * sqrt(2) (octave 5)
+    CqTables cq;
     float m2[kLoOcts][kLoBatch][kLoTriples];                     // |CQ| of row 3 p + 2 (goes to chroma p + 1)
     double inv_sl[kLoOcts * kCqtBinsPerOct];
-    short tri_s[kLoTriples], tri_d1[kLoTriples], tri_d2[kLoTriples], tri_u[kLoTriples];
-    short cnt[kCqtBinsPerOct];
 };
 static_assert(sizeof(CensLoSmem) <= 75 * 1024 + 640, "three CTAs per SM");
 
@@ -501,22 +545,6 @@ __global__ void __launch_bounds__(kLoThreads, 3) k_cens_lo(Geometry g, Tables tb
     const float* G = ws.dec + (size_t)b * cens_dec_stride(ws);
     const int tun = ws.tuning[b * 2 + 1];
     {
-        const float* bre = tb.cqt_re + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
-        const float* bim = tb.cqt_im + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
-        const double sqrt2 = sqrt(2.0);
-        for (int i = tid; i < kCqtBinsPerOct * kLoWPitch; i += kLoThreads) {
-            const int r = i / kLoWPitch, jj = i - r * kLoWPitch - kLoPadL;
-            float re = 0.f, im = 0.f;
-            if (jj >= 0 && jj < kCqtEllWidth) { re = bre[r * kCqtEllWidth + jj]; im = bim[r * kCqtEllWidth + jj]; }
-            S.wpad[0][i] = make_float2(re, im);
-            S.wpad[1][i] = make_float2((float)((double)re * sqrt2), (float)((double)im * sqrt2));   // as in k_cens
-        }
-        if (tid < kCqtBinsPerOct) {                              // taps of the row up to its last non-zero weight
-            int c = 1;
-            for (int jj = 1; jj < kCqtEllWidth; ++jj)
-                if (bre[tid * kCqtEllWidth + jj] != 0.f || bim[tid * kCqtEllWidth + jj] != 0.f) c = jj + 1;
-            S.cnt[tid] = (short)c;
-        }
         // rows of octave o: inv_sl index kCqtBins - 36 (o + 1) + r; octaves 6, 5, 4 are the first three groups of 36
         const double* slen = tb.cqt_sqrt_len + (size_t)tun * kCqtBins;
         for (int i = tid; i < kLoOcts * kCqtBinsPerOct; i += kLoThreads) S.inv_sl[i] = 1.0 / slen[i];
@@ -533,15 +561,7 @@ __global__ void __launch_bounds__(kLoThreads, 3) k_cens_lo(Geometry g, Tables tb
             d[i] = a - c;
         }
     }
-    __syncthreads();
-    if (tid < kLoTriples) {
-        const short* bs = tb.cqt_start + tun * kCqtBinsPerOct + 3 * tid;
-        const int s0 = bs[0], d1 = bs[1] - s0, d2 = bs[2] - s0;      // band starts do not decrease with the row
-        S.tri_s[tid] = (short)(s0 - kBinLo);
-        S.tri_d1[tid] = (short)d1;
-        S.tri_d2[tid] = (short)d2;
-        S.tri_u[tid] = (short)max((int)S.cnt[3 * tid], max(d1 + (int)S.cnt[3 * tid + 1], d2 + (int)S.cnt[3 * tid + 2]));
-    }
+    cq_stage(S.cq, tb, tun, tid, kLoThreads);                   // ends with a barrier (d0 .. d2 visible too)
     // this thread's bin: twiddles W^{nk}, n < 16, and the hop rotations W^{-hk}
     const int grp = tid / kLoGroup;                             // warp-uniform: 0 = octave 4, 1 = octaves 5 and 6
     const int kk = tid - grp * kLoGroup;                        // bin - kBinLo (lanes past the span idle along)
@@ -564,8 +584,7 @@ __global__ void __launch_bounds__(kLoThreads, 3) k_cens_lo(Geometry g, Tables tb
     if (grp == 1) lo_hops<16, false>(S.d2, tw, rot16, Xb, 16, nullptr, false);
     float* lo = ws.cens_lo + (size_t)b * kLoOcts * 12 * T;
     const int f = tid & 15, p = tid >> 4;                       // basis product: frame of the batch, row triple
-    __syncthreads();                                            // tri_* visible
-    const int ts = S.tri_s[p], td1 = S.tri_d1[p], td2 = S.tri_d2[p], tu = S.tri_u[p];
+    const int ts = S.cq.tri_s[p], td1 = S.cq.tri_d1[p], td2 = S.cq.tri_d2[p], tu = S.cq.tri_u[p];
     for (int t0 = 0; t0 < T; t0 += kLoBatch) {
         const int nf = min(kLoBatch, T - t0);
         if (grp == 0) {
@@ -584,28 +603,10 @@ __global__ void __launch_bounds__(kLoThreads, 3) k_cens_lo(Geometry g, Tables tb
 #pragma unroll
         for (int q2 = 0; q2 < kLoOcts; ++q2) {
             const int o = kLoFirstOct + q2;
-            const float2* w0 = S.wpad[o & 1] + 3 * p * kLoWPitch + kLoPadL;
-            const float2* w1 = w0 + kLoWPitch - td1;
-            const float2* w2 = w0 + 2 * kLoWPitch - td2;
-            const float2* sp = &S.spec[q2][f][ts];
-            float cr0 = 0.f, ci0 = 0.f, cr1 = 0.f, ci1 = 0.f, cr2 = 0.f, ci2 = 0.f;
-#pragma unroll 4
-            for (int u = 0; u < tu; ++u) {
-                const float2 d = sp[u];
-                const float2 a = w0[u], c = w1[u], e = w2[u];
-                cr0 = fmaf(a.x, d.x, cr0); cr0 = fmaf(-a.y, d.y, cr0);
-                ci0 = fmaf(a.x, d.y, ci0); ci0 = fmaf(a.y, d.x, ci0);
-                cr1 = fmaf(c.x, d.x, cr1); cr1 = fmaf(-c.y, d.y, cr1);
-                ci1 = fmaf(c.x, d.y, ci1); ci1 = fmaf(c.y, d.x, ci1);
-                cr2 = fmaf(e.x, d.x, cr2); cr2 = fmaf(-e.y, d.y, cr2);
-                ci2 = fmaf(e.x, d.y, ci2); ci2 = fmaf(e.y, d.x, ci2);
-            }
-            // complex64 response, V /= sqrt(lengths) (complex128 math, complex64 store), |V|: as in k_cens
-            const float pow2 = (float)(1 << (o >> 1));
-            const double* sl = S.inv_sl + (kCqtOctaves - 1 - o) * kCqtBinsPerOct + 3 * p;
-            m0[q2] = c64_abs_f32((float)((double)(cr0 * pow2) * sl[0]), (float)((double)(ci0 * pow2) * sl[0]));
-            m1[q2] = c64_abs_f32((float)((double)(cr1 * pow2) * sl[1]), (float)((double)(ci1 * pow2) * sl[1]));
-            S.m2[q2][f][p] = c64_abs_f32((float)((double)(cr2 * pow2) * sl[2]), (float)((double)(ci2 * pow2) * sl[2]));
+            float m2v;
+            cq_triple(S.cq.wpad[o & 1] + 3 * p * kCqWPitch + kCqPadL, td1, td2, tu, &S.spec[q2][f][ts], o,
+                      S.inv_sl + (kCqtOctaves - 1 - o) * kCqtBinsPerOct + 3 * p, m0[q2], m1[q2], m2v);
+            S.m2[q2][f][p] = m2v;
         }
         __syncthreads();
         // cq_to_chroma per octave: chroma c = p sums rows {3c-1, 3c, 3c+1} (mod 36), in that order

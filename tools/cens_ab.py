@@ -1,8 +1,11 @@
-"""A/B of the CQT low-octave path: k_cens_lo (sliding DFT, BPC_CENS_LO=1) against all seven octaves by FFT (=0).
+"""A/B of CQT / chroma_cens variants on the GPU box: every variant runs in its own process and dumps the chroma plane
+and the raw chroma_cens rows of 130 one-second segments (+ 6 five-second segments with --long); the first variant is the
+reference the others are compared with, value by value.
 
-Run on the GPU box:  python tools/cens_ab.py
-Each variant runs in its own process (the switch is read once per process); prints how many chroma_cens values differ
-between the two and by how much.
+usage: python tools/cens_ab.py [--long] VARIANT [VARIANT ...]
+  VARIANT = name[:KEY=VAL[,KEY=VAL ...]]   environment of the child; LIB=<path> loads that library instead of the
+                                           in-tree libbpc_b200.so (e.g. gpurun_variants/lib_prev.so)
+  e.g.  python tools/cens_ab.py fft7:BPC_CENS_LO=0,LIB=gpurun_variants/lib_prev.so new new_nolo:BPC_CENS_LO=0
 """
 import os
 import subprocess
@@ -15,9 +18,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "breathing-phase-classifier_b200"))
 
 
-def child(out):
+def child(out, long_mode):
     import torch
     import bpc_b200
+    from bpc_b200 import _lib
+    if os.environ.get("BPC_AB_LIB"):
+        _lib.LIB_PATH = os.path.join(ROOT, os.environ["BPC_AB_LIB"])
     from oracle import pipeline as P
     gold = np.load(os.path.join(ROOT, "tests", "golden", "golden_segments.npz"))["pcm16"]
     real = np.load(os.path.join(ROOT, "tests", "golden", "real_inputs_pcm16.npz"))["pcm16"]
@@ -30,23 +36,43 @@ def child(out):
     eng = bpc_b200.Engine(device=0, max_batch=len(Y), debug=True)
     feats, scal, status = eng.precompute(torch.from_numpy(Y).cuda())
     torch.cuda.synchronize()
-    np.savez(out, chroma=feats[:, 0].cpu().numpy(), raw=eng.debug("chroma_cens_raw", len(Y)))
+    res = dict(chroma=feats[:, 0].cpu().numpy(), raw=eng.debug("chroma_cens_raw", len(Y)))
+    if long_mode:
+        d = 5
+        YL = np.stack([np.concatenate([ys[(7 * i + j) % 128] for j in range(d)]) for i in range(6)])
+        engl = bpc_b200.Engine(device=0, max_batch=len(YL), params=_lib.default_params(expected_len=16000 * d))
+        fl, sl, stl = engl.precompute(torch.from_numpy(YL).cuda())
+        torch.cuda.synchronize()
+        res["chroma_long"] = fl[:, 0].cpu().numpy()
+    np.savez(out, **res)
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1:
-        child(sys.argv[1])
+    if sys.argv[1] == "--child":
+        child(sys.argv[2], sys.argv[3] == "1")
         sys.exit(0)
+    args = sys.argv[1:]
+    long_mode = "--long" in args
+    variants = [a for a in args if a != "--long"]
     res = {}
-    for v in ("1", "0"):
-        out = f"/tmp/cens_ab_{v}.npz"
-        subprocess.run([sys.executable, __file__, out], check=True, env=dict(os.environ, BPC_CENS_LO=v))
-        res[v] = np.load(out)
-    for k in ("raw", "chroma"):
-        a, b = res["1"][k], res["0"][k]
-        same = (a == b) | (np.isnan(a) & np.isnan(b))
-        d = np.abs(a.astype(np.float64) - b.astype(np.float64))
-        d = np.where(np.isnan(d), 0.0 if True else 0.0, d)
-        per_seg = (~same).reshape(len(a), -1).sum(1)
-        print(f"{k}: {int((~same).sum())} of {a.size} values differ (segments touched: {int((per_seg > 0).sum())} of {len(a)}), "
-              f"max |delta| {d.max():.3e}, nan mismatch {int((np.isnan(a) != np.isnan(b)).sum())}")
+    for v in variants:
+        name, _, envs = v.partition(":")
+        env = dict(os.environ)
+        for kv in filter(None, envs.split(",")):
+            k, _, val = kv.partition("=")
+            env["BPC_AB_LIB" if k == "LIB" else k] = val
+        out = f"/tmp/cens_ab_{name}.npz"
+        subprocess.run([sys.executable, __file__, "--child", out, "1" if long_mode else "0"], check=True, env=env)
+        res[name] = np.load(out)
+    ref = variants[0].partition(":")[0]
+    for v in variants[1:]:
+        name = v.partition(":")[0]
+        for k in res[ref].files:
+            a, b = res[name][k], res[ref][k]
+            same = (a == b) | (np.isnan(a) & np.isnan(b))
+            d = np.abs(a.astype(np.float64) - b.astype(np.float64))
+            d = np.where(np.isnan(d), 0.0, d)
+            per_seg = (~same).reshape(len(a), -1).sum(1)
+            print(f"{name} vs {ref} {k}: {int((~same).sum())} of {a.size} values differ (segments touched: "
+                  f"{int((per_seg > 0).sum())} of {len(a)}), max |delta| {d.max():.3e}, "
+                  f"nan mismatch {int((np.isnan(a) != np.isnan(b)).sum())}")
