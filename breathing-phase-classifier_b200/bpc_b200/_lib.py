@@ -19,6 +19,12 @@ SEG_NONFINITE, SEG_TUNING_EMPTY, SEG_CAND_OVERFLOW, SEG_SILENT = 1, 2, 4, 8
 MIX_NONE, MIX_MIXUP, MIX_CUTMIX = 0, 1, 2
 
 
+class WavInfo(C.Structure):
+    """include/bpc.h::bpc_wav_info"""
+    _fields_ = [("data_offset", C.c_int64), ("frames", C.c_int64), ("sr", C.c_int32), ("channels", C.c_int32),
+                ("fmt", C.c_int32), ("reserved", C.c_int32)]
+
+
 class Params(C.Structure):
     """bpc_params: the module constants of reference process.py:12-23."""
     _fields_ = [("sr", C.c_int32), ("n_fft", C.c_int32), ("hop", C.c_int32), ("n_mels", C.c_int32),
@@ -53,6 +59,9 @@ _SIGS = {
     "bpc_expand_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int]),
     "bpc_host_alloc": (C.c_void_p, [C.c_void_p, C.c_int64, C.POINTER(C.c_int)]),
     "bpc_host_free": (None, [C.c_void_p, C.c_void_p]),
+    "bpc_wav_parse": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "bpc_wav_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                 C.c_void_p]),
     "bpc_resample_len": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "bpc_resample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "bpc_resample_filter": (C.c_int64, [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int),

@@ -126,6 +126,64 @@ class Engine:
         _check(self._h, rc, "bpc_resample")
         return out.cpu().numpy() if is_np else out
 
+    def decode_wavs(self, images, length: int | None = None, sr: int = 16000):
+        """GPU-side `librosa.load(path, sr=sr)` + `pad_or_truncate` (process.py:28-29) for a list of RIFF/WAVE file
+        images (bytes as read from disk): the host walks the chunk headers (`bpc_wav_parse`), the images go to the
+        device as they are, `bpc_wav_decode` scales / down-mixes / pads there, files of another rate are resampled on
+        the device (`bpc_resample`).  Returns (cuda float32 [n, length], errors) with errors[i] = None or a message
+        (the row of a failed file is zero)."""
+        import torch
+        length = int(self.L if length is None else length)
+        n = len(images)
+        infos = (L.WavInfo * max(n, 1))()
+        offs = np.zeros(max(n, 1), dtype=np.int64)
+        errors = [None] * n
+        pos = 0
+        for i, img in enumerate(images):
+            rc = self._lib.bpc_wav_parse(img, len(img), C.byref(infos[i]))
+            if rc != 0:
+                errors[i] = "not a RIFF/WAVE file" if rc == -11 else f"unsupported wav format ({rc})"
+            offs[i] = pos
+            pos += (len(img) + 15) & ~15
+        dev = torch.device("cuda", self.device)
+        y = torch.zeros((n, length), dtype=torch.float32, device=dev)
+        good = [i for i in range(n) if errors[i] is None]
+        if not good:
+            return y, errors
+        blob_h = torch.empty(max(pos, 16), dtype=torch.uint8, pin_memory=True)
+        bh = blob_h.numpy()
+        for i in good:
+            bh[offs[i]:offs[i] + len(images[i])] = np.frombuffer(images[i], dtype=np.uint8)
+        blob = blob_h.to(dev, non_blocking=True)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        same = [i for i in good if infos[i].sr == sr]
+        other = [i for i in good if infos[i].sr != sr]
+
+        def _decode(idx, out, out_len):
+            inf = (L.WavInfo * len(idx))(*[infos[i] for i in idx])
+            of = np.ascontiguousarray(offs[idx])
+            _check(self._h, self._lib.bpc_wav_decode(self._h, blob.data_ptr(), of.ctypes.data, C.byref(inf), len(idx),
+                                                     int(out_len), out.data_ptr(), st), "bpc_wav_decode")
+
+        if same:
+            if len(same) == n:
+                _decode(same, y, length)
+            else:
+                tmp = torch.empty((len(same), length), dtype=torch.float32, device=dev)
+                _decode(same, tmp, length)
+                y[torch.as_tensor(same, device=dev)] = tmp
+        for i in other:                                   # decode at the file's own rate, then convert
+            frames = int(infos[i].frames)
+            if frames == 0:
+                continue
+            raw = torch.empty((1, frames), dtype=torch.float32, device=dev)
+            _decode([i], raw, frames)
+            r = self.resample(raw[0], int(infos[i].sr), sr)
+            m = min(int(r.numel()), length)
+            y[i, :m] = r[:m]
+        torch.cuda.current_stream(dev).synchronize()      # the pinned blob may be released
+        return y, errors
+
     # ---------------------------------------------------------------------------------------------- host arrays
     def precompute_host(self, wav: np.ndarray, feats=None, scalars=None, status=None):
         """wav: numpy [B, L_in] float32 / int16 (pageable or pinned) -> numpy (feats, scalars, status)."""

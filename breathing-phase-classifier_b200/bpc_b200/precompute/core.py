@@ -79,8 +79,18 @@ def process_dataset_threaded(df, audio_dir, target_dir, dataset_name, engine=Non
     starts = list(range(0, len(items), batch))
     shard = ShardWriter(os.path.join(target_dir, dataset_name), len(items), eng.T, eng.nscal) if packed and items else None
 
+    # The reader thread decodes the rare general files (stereo, 8 / 24 / 32-bit, float, other rates) on the GPU through a
+    # handle of its own (calls on one handle are serialised by its owner; handles are independent, include/bpc.h).
+    dec = []
+
+    def _decoder():
+        if not dec:
+            from ..engine import Engine
+            dec.append(Engine(device=eng.device, max_batch=1, params=eng.params))
+        return dec[0]
+
     def _load(lo):
-        return load_wav_batch([p for _, p in items[lo:lo + batch]], eng.L, threads=IO_THREADS)
+        return load_wav_batch([p for _, p in items[lo:lo + batch]], eng.L, threads=IO_THREADS, engine=_decoder)
 
     def _write(pos, ids, feats, scal, status):
         for p, r in zip(pos, write_npz_batch(target_dir, ids, feats, scal, status, threads=IO_THREADS)):
@@ -129,6 +139,8 @@ def process_dataset_threaded(df, audio_dir, target_dir, dataset_name, engine=Non
             pending_write.result()
     if shard is not None:
         shard.close()
+    for d in dec:
+        d.close()
     if own_engine:
         eng.close()
     successful = failed = 0

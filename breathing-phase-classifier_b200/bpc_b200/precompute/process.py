@@ -48,13 +48,15 @@ def load_wav(path: str):
 WAV_ERR_OPEN, WAV_ERR_FORMAT, WAV_ERR_UNSUPPORTED = -10, -11, -12        # include/bpc.h: bpc_wav_code
 
 
-def load_wav_batch(paths, length=EXPECTED_LEN, threads=8):
+def load_wav_batch(paths, length=EXPECTED_LEN, threads=8, engine=None):
     """`librosa.load(p, sr=16000)` + `pad_or_truncate` (process.py:28-29) for many files at once.
 
     The library's C++ reader pool handles what the reference is fed (RIFF PCM16 mono 16 kHz) straight into one
-    [n, length] int16 batch; a file it reports as unsupported (stereo, other sample formats) is decoded by `load_wav`,
-    which switches the whole batch to float32.  Returns (batch, errors) with errors[i] = None or the failure message
-    (the row of a failed file is zero; the caller reports it as `(id, False, err)`)."""
+    [n, length] int16 batch.  Files it reports as unsupported (stereo, other sample formats or rates) are decoded ON THE
+    GPU when the caller passes an engine or a callable that returns one (`Engine.decode_wavs`: the file images go to the device as read, scaling /
+    down-mix / resampling / padding happen there), else by `load_wav` on the host (scipy); either way the batch becomes
+    float32.  Returns (batch, errors) with errors[i] = None or the failure message (the row of a failed file is zero;
+    the caller reports it as `(id, False, err)`)."""
     import ctypes as C
     from .._lib import lib
     n = len(paths)
@@ -67,8 +69,29 @@ def load_wav_batch(paths, length=EXPECTED_LEN, threads=8):
         raise RuntimeError(f"bpc_wav_load_batch failed ({rc})")
     errors = [None] * n
     slow = {}
+    general = [int(i) for i in np.flatnonzero(code == WAV_ERR_UNSUPPORTED)]
+    if general and engine is not None:                  # GPU-side decode of everything the PCM16 reader does not take
+        if callable(engine):                            # created on first use (most datasets never need it)
+            engine = engine()
+        images = []
+        for i in general:
+            with open(paths[i], "rb") as fh:
+                images.append(fh.read())
+        ydev, errs = engine.decode_wavs(images, length=length, sr=SR)
+        yh = ydev.cpu().numpy()
+        for j, i in enumerate(general):
+            if errs[j] is None:
+                slow[i] = yh[j]
+            else:                                       # a format the device decoder does not take either: host reader
+                try:
+                    slow[i] = load_wav(paths[i])
+                except Exception as e:  # noqa: BLE001
+                    errors[i] = str(e)
+        general = []
     for i in np.flatnonzero(code):
         if code[i] == WAV_ERR_UNSUPPORTED:              # stereo, other sample formats, other rates (resampled on the device)
+            if i in slow or errors[i] is not None:
+                continue
             try:
                 slow[i] = load_wav(paths[i])
             except Exception as e:  # noqa: BLE001

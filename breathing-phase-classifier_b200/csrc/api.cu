@@ -308,6 +308,8 @@ struct bpc_handle {
     bool contig_d2h = true;        // compact host layout: k_compact_rows + ONE copy per piece (env BPC_D2H_MODE=2d: row runs)
     struct Resampler { int sr_in, sr_out, p, q, half; const double* tab; };
     std::vector<Resampler> resamplers;   // polyphase tables uploaded so far (bpc_resample)
+    WavItem* wav_items = nullptr;        // device copy of the per-file descriptors of bpc_wav_decode
+    int64_t wav_items_cap = 0;
     bool compact_d2h = true;       // host path transfers live rows only (env BPC_COMPACT_D2H=0: whole planes)
     int host_chunk = 0;            // piece size of the host path (env BPC_HOST_CHUNK, default chunk / 2: the D2H of a piece
                                    // can only start when its kernels are done, so smaller pieces shorten the ramp)
@@ -1565,6 +1567,39 @@ int bpc_resample(bpc_handle* h, const float* in, int64_t n_in, int sr_in, int sr
         r = &h->resamplers.back();
     }
     launch_resample(in, n_in, r->tab, r->p, r->q, r->half, out, n_out, static_cast<cudaStream_t>(stream));
+    BPC_CUDA(h, cudaGetLastError());
+    return BPC_OK;
+}
+
+int bpc_wav_decode(bpc_handle* h, const void* blob, const int64_t* file_offset, const bpc_wav_info* info, int64_t n,
+                   int64_t L, float* y, void* stream) {
+    if (!h) return BPC_ERR_ARG;
+    if (n == 0) return BPC_OK;
+    if (!blob || !file_offset || !info || !y || n < 0 || n > 65535 || L <= 0 || L > 0x7fffffff) {
+        h->err = "bpc_wav_decode: bad argument (at most 65535 files per call)";
+        return BPC_ERR_ARG;
+    }
+    std::vector<WavItem> items((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        const bpc_wav_info& f = info[i];
+        if (f.fmt < BPC_FMT_U8 || f.fmt > BPC_FMT_F64 || f.channels < 1 || f.channels > 7 || f.frames < 0 || f.data_offset < 0) {
+            h->err = "bpc_wav_decode: info[" + std::to_string(i) + "] does not come from a successful bpc_wav_parse";
+            return BPC_ERR_ARG;
+        }
+        items[(size_t)i] = {(long long)(file_offset[i] + f.data_offset), (long long)f.frames, f.channels, f.fmt};
+    }
+    BPC_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (h->wav_items_cap < n) {                                    // grows; freed with the handle
+        WavItem* d = nullptr;
+        BPC_CUDA(h, cudaMalloc((void**)&d, sizeof(WavItem) * (size_t)n));
+        h->dev_allocs.push_back(d);
+        h->wav_items = d;
+        h->wav_items_cap = n;
+    }
+    // pageable source: the runtime stages it before returning, `items` may die with this call
+    BPC_CUDA(h, cudaMemcpyAsync(h->wav_items, items.data(), sizeof(WavItem) * (size_t)n, cudaMemcpyHostToDevice, st));
+    launch_wav_decode(static_cast<const unsigned char*>(blob), h->wav_items, (int)n, (int)L, y, st);
     BPC_CUDA(h, cudaGetLastError());
     return BPC_OK;
 }

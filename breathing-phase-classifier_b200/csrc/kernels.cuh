@@ -147,6 +147,9 @@ void launch_modspec_time_tc(int n, const Geometry& g, const Tables& tb, const Wo
 void launch_resample(const float* x, long long n_in, const double* tab, int p, int q, int half, float* out,
                      long long n_out, cudaStream_t st);
 
+struct WavItem { long long offset, frames; int channels, fmt; };   // payload of one file inside the blob (k_wav.cu)
+void launch_wav_decode(const unsigned char* blob, const WavItem* items, int n, int L, float* y, cudaStream_t st);
+
 void upload_cens_constants(const double* taps127);
 int cens_dec_floats_per_segment(int L);
 int64_t launches_issued();   // process-wide counter bumped by every launcher

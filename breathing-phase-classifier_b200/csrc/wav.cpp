@@ -63,6 +63,43 @@ int load_one(const char* path, int expected_sr, int64_t L, int16_t* out, int32_t
 
 }  // namespace
 
+// Chunk walk over a file image in memory (the GPU-side decode path: the samples themselves are only touched by
+// k_wav_decode).  Same acceptance rules as soundfile / scipy.io.wavfile for uncompressed data.
+extern "C" int bpc_wav_parse(const void* image, int64_t n_bytes, bpc_wav_info* info) {
+    if (!image || !info || n_bytes < 0) return BPC_ERR_ARG;
+    std::memset(info, 0, sizeof(*info));
+    const unsigned char* p = static_cast<const unsigned char*>(image);
+    if (n_bytes < 12 || std::memcmp(p, "RIFF", 4) || std::memcmp(p + 8, "WAVE", 4)) return BPC_WAV_ERR_FORMAT;
+    int64_t pos = 12;
+    bool have_fmt = false;
+    uint16_t tag = 0, channels = 0, bits = 0;
+    while (pos + 8 <= n_bytes) {
+        const uint32_t size = rd32(p + pos + 4);
+        const unsigned char* body = p + pos + 8;
+        if (!std::memcmp(p + pos, "fmt ", 4)) {
+            if (size < 16 || pos + 8 + 16 > n_bytes) return BPC_WAV_ERR_FORMAT;
+            tag = rd16(body); channels = rd16(body + 2); info->sr = (int32_t)rd32(body + 4); bits = rd16(body + 14);
+            if (tag == 0xFFFE && size >= 26 && pos + 8 + 26 <= n_bytes) tag = rd16(body + 24);   // WAVE_FORMAT_EXTENSIBLE
+            have_fmt = true;
+        } else if (!std::memcmp(p + pos, "data", 4)) {
+            if (!have_fmt) return BPC_WAV_ERR_FORMAT;
+            int fmt = 0;
+            if (tag == 1) fmt = bits == 8 ? BPC_FMT_U8 : bits == 16 ? BPC_FMT_PCM16 : bits == 24 ? BPC_FMT_PCM24 : bits == 32 ? BPC_FMT_PCM32 : 0;
+            else if (tag == 3) fmt = bits == 32 ? BPC_FMT_F32 : bits == 64 ? BPC_FMT_F64 : 0;
+            if (!fmt || channels < 1 || channels > 7 || info->sr <= 0) return BPC_WAV_ERR_UNSUPPORTED;
+            const int64_t avail = n_bytes - (pos + 8);
+            const int64_t bytes = (int64_t)size < avail ? (int64_t)size : avail;          // truncated file: what is there
+            info->data_offset = pos + 8;
+            info->channels = channels;
+            info->fmt = fmt;
+            info->frames = bytes / ((int64_t)channels * (bits / 8));
+            return BPC_OK;
+        }
+        pos += 8 + (int64_t)size + (size & 1);
+    }
+    return BPC_WAV_ERR_FORMAT;
+}
+
 extern "C" int bpc_wav_load_batch(const char* const* paths, int64_t n, int expected_sr, int64_t L, int16_t* out,
                                   int32_t* sr, int32_t* frames, int32_t* code, int n_threads) {
     if (!paths || !out || !sr || !frames || !code || n < 0 || L <= 0) return BPC_ERR_ARG;

@@ -210,6 +210,26 @@ enum bpc_wav_code { BPC_WAV_ERR_OPEN = -10, BPC_WAV_ERR_FORMAT = -11, BPC_WAV_ER
 int  bpc_wav_load_batch(const char* const* paths, int64_t n, int expected_sr, int64_t L, int16_t* out,
                         int32_t* sr, int32_t* frames, int32_t* code, int n_threads);
 
+/* ---- GPU-side decode ---------------------------------------------------------------------------------
+ * process.py:28 `librosa.load(wav_path, sr=SR)` = soundfile decode to float32 (int16 / 2^15, 24- and 32-bit / 2^31,
+ * unsigned 8-bit (x - 128) / 2^7, IEEE float as stored) + librosa.to_mono (float32 mean over the channels) and
+ * process.py:29 pad_or_truncate -- for any RIFF/WAVE sample format and channel count, on the device.  The host only
+ * walks the chunk headers (bpc_wav_parse: no sample is touched) and copies the file images to the GPU as they are.
+ * bpc_wav_parse: image of one file -> where its samples lie and how they are stored; returns BPC_OK or a bpc_wav_code
+ *   (BPC_WAV_ERR_UNSUPPORTED: compressed formats, other bit depths, more than 7 channels).
+ * bpc_wav_decode: blob = n file images in DEVICE memory, file i starting at byte file_offset[i] (host array);
+ *   info[i] from bpc_wav_parse (host array).  Writes y[n, L] float32 (device): frames beyond the file are zero, frames
+ *   beyond L are dropped.  Files of another sample rate are decoded at their own rate (resample with bpc_resample). */
+enum bpc_sample_fmt { BPC_FMT_U8 = 1, BPC_FMT_PCM16 = 2, BPC_FMT_PCM24 = 3, BPC_FMT_PCM32 = 4, BPC_FMT_F32 = 5, BPC_FMT_F64 = 6 };
+typedef struct bpc_wav_info {
+    int64_t data_offset;   /* byte offset of the first sample inside the file image */
+    int64_t frames;        /* sample frames present (a truncated data chunk counts what is there) */
+    int32_t sr, channels, fmt, reserved;
+} bpc_wav_info;
+int  bpc_wav_parse(const void* image, int64_t n_bytes, bpc_wav_info* info);
+int  bpc_wav_decode(bpc_handle* h, const void* blob, const int64_t* file_offset, const bpc_wav_info* info, int64_t n,
+                    int64_t L, float* y, void* stream);
+
 /* ---- sample-rate conversion on load ---------------------------------------------------------------
  * process.py:28 `librosa.load(wav_path, sr=SR)` resamples files of any other rate with libsoxr "HQ", an un-vendored
  * dependency that cannot be restated bit for bit.  Stand-in (the same disclosure as the CQT's half-band decimator):

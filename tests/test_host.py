@@ -526,3 +526,30 @@ def test_host_only_entry_points_reject_bad_arguments(tmp_path):
     assert lib.bpc_num_frames(None) == -1 and lib.bpc_num_scalars(None) == -1
     assert lib.bpc_create(None, C.byref(bpc_b200.default_params()), 0, 16) == -1
     assert b"NULL" in lib.bpc_last_error(None)
+
+
+def test_wav_parse_walks_chunks_without_touching_samples():
+    """bpc_wav_parse (host half of the GPU-side decode): formats, WAVE_FORMAT_EXTENSIBLE, a junk chunk of odd size,
+    a truncated data chunk, rejections."""
+    import ctypes as C
+    from bpc_b200 import _lib as L
+    import wavutil as W
+    lib = L.lib()
+    for kind, fmt in (("u8", 1), ("pcm16", 2), ("pcm24", 3), ("pcm32", 4), ("f32", 5), ("f64", 6)):
+        for ch in (1, 2, 3):
+            x = W.samples(kind, 1000 + ch, ch, 7)
+            for ext, junk in ((False, False), (True, True)):
+                img = W.image(kind, x, 22050, extensible=ext, junk=junk)
+                info = L.WavInfo()
+                assert lib.bpc_wav_parse(img, len(img), C.byref(info)) == 0
+                assert (info.sr, info.channels, info.fmt, info.frames) == (22050, ch, fmt, 1000 + ch)
+                assert img[info.data_offset:info.data_offset + 16] == W.payload(kind, x)[:16]
+    x = W.samples("pcm16", 1000, 2, 1)
+    img = W.image("pcm16", x, 16000, cut=402)                       # 100 whole frames + half a frame missing
+    info = L.WavInfo()
+    assert lib.bpc_wav_parse(img, len(img), C.byref(info)) == 0 and info.frames == 899
+    assert lib.bpc_wav_parse(b"RIFX" + img[4:], len(img), C.byref(info)) == -11
+    assert lib.bpc_wav_parse(img[:30], 30, C.byref(info)) == -11
+    bad = bytearray(W.image("pcm16", x, 16000)); bad[20] = 2                     # ADPCM
+    assert lib.bpc_wav_parse(bytes(bad), len(bad), C.byref(info)) == -12
+    assert lib.bpc_wav_parse(None, 0, C.byref(info)) == -1
