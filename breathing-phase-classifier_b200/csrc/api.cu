@@ -586,6 +586,7 @@ int build_tables(bpc_handle* h) {
                 return BPC_ERR_UNSUPPORTED;
             }
         upload_cens_constants(hb.data());
+        upload_lpc_constants(hamming_sym(400).data());
     }
     return BPC_OK;
 }
@@ -610,6 +611,10 @@ int build_workspace(bpc_handle* h, ChunkCtx& ctx, int cap) {
     w.dec_stride = cens_dec_floats_per_segment(g.L);
     if ((rc = dalloc(h, C * (size_t)w.dec_stride, &w.dec))) return rc;
     w.cens_lo = nullptr;
+    w.lpc_coef = nullptr;
+    w.lpc_redo = nullptr;
+    if (!g.long_mode && (rc = dalloc(h, C * 12 * (size_t)g.lpc_frames, &w.lpc_coef))) return rc;
+    if (!g.long_mode && (rc = dalloc(h, 1 + C * (size_t)g.lpc_frames, &w.lpc_redo))) return rc;
     if (!g.long_mode && (rc = dalloc(h, C * 3 * 12 * T, &w.cens_lo))) return rc;
     if ((rc = dalloc(h, C * 2, &w.tuning))) return rc;
     if ((rc = dalloc(h, C * 2, &w.chroma_min))) return rc;

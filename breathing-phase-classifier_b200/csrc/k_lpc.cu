@@ -2,6 +2,8 @@
 // of order 12 as in librosa.lpc (float64), whole-array z-score over ALL frames, first T frames kept, rows padded.
 // One CTA per segment, one warp per frame; forward / backward prediction errors live in shared memory.
 #include <cmath>
+#include <cstdlib>
+#include <type_traits>
 #include "kernels.cuh"
 
 namespace bpc {
@@ -76,6 +78,229 @@ __device__ __forceinline__ void burg_all(double (&F)[kLpcPer], double (&B)[kLpcP
     }
 }
 
+// Burg's method on one frame, one warp: lane j returns a[j] (j <= 12).  All 32 lanes must call it.
+__device__ __forceinline__ double burg_frame(const float* __restrict__ yb, int start, const double* __restrict__ hamming,
+                                             int lane) {
+    double Bv[kLpcPer], Fv[kLpcPer];
+#pragma unroll
+    for (int q = 0; q < kLpcPer; ++q) {
+        const int n = kLpcPer * lane + q, gi = start + n;
+        double x = 0.0;
+        if (n < kLpcFrame) {
+            // y_emph = append(y[0], y[1:] - 0.97 * y[:-1])   (float32)
+            const float e = gi == 0 ? __ldg(yb) : __fsub_rn(__ldg(yb + gi), __fmul_rn(0.97f, __ldg(yb + gi - 1)));
+            x = (double)e * __ldg(hamming + n);
+        }
+        Bv[q] = x;
+    }
+    // fwd[n] pairs with bwd[n]: F[q] = x[n + 1]
+    const double nxt = __shfl_down_sync(0xffffffffu, Bv[0], 1);
+#pragma unroll
+    for (int q = 0; q < kLpcPer - 1; ++q) Fv[q] = Bv[q + 1];
+    Fv[kLpcPer - 1] = lane < 31 ? nxt : 0.0;
+    // bwd = x[:-1]: sample 399 is never a backward error
+    if (lane == (kLpcFrame - 1) / kLpcPer) Bv[(kLpcFrame - 1) % kLpcPer] = 0.0;
+    double den = 0.0;
+#pragma unroll
+    for (int q = 0; q < kLpcPer; ++q) den = fma(Fv[q], Fv[q], fma(Bv[q], Bv[q], den));
+    den = warp_sum(den);
+    double a_lane = lane == 0 ? 1.0 : 0.0;
+    burg_all<0>(Fv, Bv, a_lane, den, lane);
+    return a_lane;
+}
+
+// ---------------------------------------------------------------------------------------------- k_lpc_fast (r02-i)
+// Burg's reflection coefficients from lag products instead of three passes over the error signals per order.
+// With f_i[n] = sum_j a_j x[n-j] and b_i[n-1] = sum_j a_j x[n-1-i+j] (a = the order-i predictor, a_0 = 1) the
+// numerator of librosa's recursion is a quadratic form in a,
+//     sum_{n=i+1}^{N-1} f_i[n] b_i[n-1] = sum_{j,l<=i} a_j a_l Phi[j][i+1-l]  +  (the terms n = i+1 .. M-1, explicit),
+//     Phi[u][v] = sum_{n=M}^{N-1} x[n-u] x[n-v],   Phi[u+1][v+1] = Phi[u][v] + x[M-1-u] x[M-1-v] - x[N-1-u] x[N-1-v],
+// so one pass over the frame (13 lag sums, Phi[0][.]) and O(M^3) scalar work replace 3 M passes: 5.4 k + ~2.5 k FP64
+// operations per frame against 29 k.  The denominator follows librosa's own recursion
+// den <- (1 - k^2) den - b_{i+1}[N-1]^2 - f_{i+1}[i+1]^2 with the two edge errors evaluated from the frame's first and
+// last 13 samples.  Same reflection coefficients in exact arithmetic; in floating point the quadratic form cancels
+// where the direct sums do not, by a factor ~ den_0 / den_i (the prediction gain): measured on 1100 frames (real
+// fixtures, tones, chirps, 30 Hz low-passed noise) against oracle/librosa_shim's lpc the coefficients differ by
+// <= 3e-9 wherever min_i den_i / den_0 > 1e-4, 2e-7 down to 1e-6, 6e-4 at 1e-10.  Frames below
+// kLfGainFloor (6 % of the real fixture frames, none of the synthetic bench frames) are therefore queued and redone by
+// the direct method (burg_frame, one warp per frame: k_lpc_redo), so every output is either the direct recursion or
+// within 3e-9 of it -- two orders below the float32 rounding of the stored coefficients.
+// One THREAD per (segment, frame): the 13 lag sums are 13 independent FMA chains over a register ring of the last 13
+// samples (FP64-pipe bound, 82 % of the instructions of the pass are DFMA), Phi (91 doubles) lives in shared memory
+// column-per-thread, the order recursion is fully unrolled so that a, the head and the tail samples stay in registers.
+constexpr int kLfThreads = 128, kLfM = kLpcOrder, kLfPhi = (kLfM + 1) * (kLfM + 2) / 2;
+constexpr double kLfGainFloor = 1e-4;
+__host__ __device__ constexpr int lf_idx(int u, int v) {        // u <= v
+    return u * (kLfM + 1) - u * (u - 1) / 2 + (v - u);
+}
+static_assert(lf_idx(kLfM, kLfM) == kLfPhi - 1, "upper triangle, row major");
+__constant__ double c_hamming400[kLpcFrame];
+
+void upload_lpc_constants(const double* hamming400) {
+    cudaMemcpyToSymbol(c_hamming400, hamming400, sizeof(double) * kLpcFrame);
+}
+
+struct LfState {
+    double a[kLfM + 1];
+    double head[kLfM + 1];      // x[0 .. 12]
+    double tl[kLfM + 1];        // x[N-1-k], k = 0 .. 12
+    double den, den0;
+    bool redo;
+};
+
+#define LF_PHI(u, v) phi[lf_idx((u) < (v) ? (u) : (v), (u) < (v) ? (v) : (u)) * kLfThreads]
+
+template <int I>
+__device__ __forceinline__ void lf_order(LfState& s, const double* __restrict__ phi) {
+    if constexpr (I < kLfM) {
+        const double eps = 2.2250738585072014e-308;             // util.tiny(float64)
+        // main part: Q = sum_{v=1}^{I+1} a[I+1-v] * (sum_{j<=I} a[j] Phi[j][v])
+        double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+        for (int v = 1; v <= I + 1; ++v) {
+            double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+            for (int j = 0; j <= I; j += 2) {
+                g0 = fma(s.a[j], LF_PHI(j, v), g0);
+                if (j + 1 <= I) g1 = fma(s.a[j + 1], LF_PHI(j + 1, v), g1);
+            }
+            if (v & 1) q0 = fma(s.a[I + 1 - v], g0 + g1, q0);
+            else q1 = fma(s.a[I + 1 - v], g0 + g1, q1);
+        }
+        // head part: the pairs n = I+1 .. M-1, from the first samples directly
+        double hsum = 0.0;
+#pragma unroll
+        for (int n = I + 1; n < kLfM; ++n) {
+            double f = 0.0, b = 0.0;
+#pragma unroll
+            for (int j = 0; j <= I; ++j) {
+                f = fma(s.a[j], s.head[n - j], f);
+                b = fma(s.a[j], s.head[n - 1 - I + j], b);
+            }
+            hsum = fma(f, b, hsum);
+        }
+        const double num = (q0 + q1) + hsum;
+        const double k = div_fast(num * -2.0, s.den + eps);
+        // Levinson: a[j] <- a[j] + k a[I+1-j], j = 1 .. I+1 (a[I+1] = 0 before)
+#pragma unroll
+        for (int j = 1; 2 * j <= I + 1; ++j) {
+            const double t1 = s.a[j], t2 = s.a[I + 1 - j];
+            s.a[j] = fma(k, t2, t1);
+            if (j != I + 1 - j) s.a[I + 1 - j] = fma(k, t1, t2);
+        }
+        s.a[I + 1] = k;                                         // j = I+1 pairs with a[0] = 1
+        // edge errors of the new order: f_{I+1}[I+1] and b_{I+1}[N-1]
+        double fe = 0.0, be = 0.0;
+#pragma unroll
+        for (int j = 0; j <= I + 1; ++j) {
+            fe = fma(s.a[j], s.head[I + 1 - j], fe);
+            be = fma(s.a[j], s.tl[I + 1 - j], be);
+        }
+        s.den = (1.0 - k * k) * s.den - be * be - fe * fe;
+        if (!(s.den > kLfGainFloor * s.den0)) s.redo = true;    // also catches NaN
+        lf_order<I + 1>(s, phi);
+    }
+}
+
+__global__ void __launch_bounds__(kLfThreads, 2) k_lpc_fast(const float* __restrict__ y, Geometry g, Workspace ws,
+                                                            int n_seg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* phi = reinterpret_cast<double*>(smem_raw) + threadIdx.x;        // [kLfPhi][kLfThreads], this thread's column
+    const int F = g.lpc_frames, L = g.L;
+    const long long gid = (long long)blockIdx.x * kLfThreads + threadIdx.x;
+    const bool live = gid < (long long)n_seg * F;
+    const int b = live ? (int)(gid / F) : 0, fr = live ? (int)(gid - (long long)b * F) : 0;
+    const float* yb = y + (size_t)b * L;
+    const int start = fr * kLpcShift;
+    LfState s;
+    double ring[kLfM + 1], acc[kLfM + 1];
+    // samples 0 .. 12: fill the ring; y_emph = append(y[0], y[1:] - 0.97 * y[:-1]) (float32), frame = y_emph * hamming
+    float yprev = start > 0 ? __ldg(yb + start - 1) : 0.f;
+    double e_head = 0.0;
+#pragma unroll
+    for (int n = 0; n <= kLfM; ++n) {
+        const float yc = __ldg(yb + start + n);
+        const float e = (start + n == 0) ? yc : __fsub_rn(yc, __fmul_rn(0.97f, yprev));
+        yprev = yc;
+        const double x = (double)e * c_hamming400[n];
+        ring[n] = x;
+        s.head[n] = x;
+        if (n < kLfM) e_head = fma(x, x, e_head);
+    }
+    // n = 12: the first term of every lag sum
+#pragma unroll
+    for (int v = 0; v <= kLfM; ++v) acc[v] = ring[kLfM] * ring[kLfM - v];
+    // n = 13 .. 399 in blocks of 13 (static ring rotation): 29 blocks + 10 samples
+    auto step = [&](int n, auto slot_c) {
+        constexpr int slot = decltype(slot_c)::value;
+        const float yc = __ldg(yb + start + n);
+        const float e = __fsub_rn(yc, __fmul_rn(0.97f, yprev));
+        yprev = yc;
+        const double x = (double)e * c_hamming400[n];
+        ring[slot] = x;
+#pragma unroll
+        for (int v = 0; v <= kLfM; ++v) acc[v] = fma(x, ring[(slot - v + 13) % 13], acc[v]);
+    };
+#pragma unroll 1
+    for (int blk = 0; blk < 29; ++blk) {
+        const int n0 = 13 + 13 * blk;
+        step(n0 + 0, std::integral_constant<int, 0>{});   step(n0 + 1, std::integral_constant<int, 1>{});
+        step(n0 + 2, std::integral_constant<int, 2>{});   step(n0 + 3, std::integral_constant<int, 3>{});
+        step(n0 + 4, std::integral_constant<int, 4>{});   step(n0 + 5, std::integral_constant<int, 5>{});
+        step(n0 + 6, std::integral_constant<int, 6>{});   step(n0 + 7, std::integral_constant<int, 7>{});
+        step(n0 + 8, std::integral_constant<int, 8>{});   step(n0 + 9, std::integral_constant<int, 9>{});
+        step(n0 + 10, std::integral_constant<int, 10>{}); step(n0 + 11, std::integral_constant<int, 11>{});
+        step(n0 + 12, std::integral_constant<int, 12>{});
+    }
+    step(390, std::integral_constant<int, 0>{}); step(391, std::integral_constant<int, 1>{});
+    step(392, std::integral_constant<int, 2>{}); step(393, std::integral_constant<int, 3>{});
+    step(394, std::integral_constant<int, 4>{}); step(395, std::integral_constant<int, 5>{});
+    step(396, std::integral_constant<int, 6>{}); step(397, std::integral_constant<int, 7>{});
+    step(398, std::integral_constant<int, 8>{}); step(399, std::integral_constant<int, 9>{});
+    // x[N-1-k] sits in ring slot (399 - k) % 13 = (9 - k + 13) % 13
+#pragma unroll
+    for (int k = 0; k <= kLfM; ++k) s.tl[k] = ring[(9 - k + 13) % 13];
+    // Phi: first row from the lag sums, the rest by the edge recurrence
+#pragma unroll
+    for (int v = 0; v <= kLfM; ++v) phi[lf_idx(0, v) * kLfThreads] = acc[v];
+#pragma unroll
+    for (int u = 0; u < kLfM; ++u)
+#pragma unroll
+        for (int v = u; v < kLfM; ++v)
+            phi[lf_idx(u + 1, v + 1) * kLfThreads] =
+                fma(-s.tl[u], s.tl[v], fma(s.head[kLfM - 1 - u], s.head[kLfM - 1 - v], phi[lf_idx(u, v) * kLfThreads]));
+    // den_0 = sum fwd^2 + sum bwd^2 = 2 sum x^2 - x[0]^2 - x[N-1]^2
+    const double c0 = acc[0] + e_head;
+    s.den0 = s.den = 2.0 * c0 - s.head[0] * s.head[0] - s.tl[0] * s.tl[0];
+    s.redo = false;
+#pragma unroll
+    for (int j = 0; j <= kLfM; ++j) s.a[j] = j == 0 ? 1.0 : 0.0;
+    if (s.den0 == 0.0) {
+        // an all-zero frame: every reflection coefficient is -2 * 0 / (0 + tiny) = 0
+    } else {
+        lf_order<0>(s, phi);
+    }
+    if (!live) return;
+    float* coef = ws.lpc_coef + (size_t)b * kLpcOrder * F;
+#pragma unroll
+    for (int j = 1; j <= kLfM; ++j) coef[(j - 1) * F + fr] = (float)s.a[j];
+    if (s.redo) ws.lpc_redo[1 + atomicAdd(ws.lpc_redo, 1)] = (int)gid;
+}
+
+// The frames k_lpc_fast queued, by the direct recursion: one warp per frame.
+__global__ void __launch_bounds__(kLpcThreads, 3) k_lpc_redo(const float* __restrict__ y, Geometry g, Tables tb,
+                                                             Workspace ws) {
+    const int lane = threadIdx.x & 31;
+    const int warps = gridDim.x * (kLpcThreads / 32), w0 = blockIdx.x * (kLpcThreads / 32) + (threadIdx.x >> 5);
+    const int count = ws.lpc_redo[0], F = g.lpc_frames;
+    for (int i = w0; i < count; i += warps) {
+        const int gid = ws.lpc_redo[1 + i];
+        const int b = gid / F, fr = gid - b * F;
+        const double a_lane = burg_frame(y + (size_t)b * g.L, fr * kLpcShift, tb.hamming400, lane);
+        if (lane >= 1 && lane <= kLpcOrder) ws.lpc_coef[((size_t)b * kLpcOrder + (lane - 1)) * F + fr] = (float)a_lane;
+    }
+}
+
 // phase 0: everything (1 s).  Long mode: phase 1 = the Burg frames of this CTA's share (grid (segment, part)) into the
 // scratch region, phase 2 = statistics + plane (grid (segment)).
 template <bool LONG>
@@ -87,7 +312,9 @@ __global__ void __launch_bounds__(kLpcThreads, 3) k_lpc(const float* __restrict_
     const int b = blockIdx.x, L = g.L, T = g.T, F_ = g.lpc_frames;
     const float* yb = y + (size_t)b * L;
     // [12, F] coefficients: shared memory (1 s: F = 98), the segment's global scratch region in long mode
-    float* coef = LONG ? ws.scratch + (size_t)b * ws.scratch_stride : S.coef;
+    // (1 s mode, phase 2: the coefficients k_lpc_fast / k_lpc_redo left in Workspace::lpc_coef)
+    float* coef = LONG ? ws.scratch + (size_t)b * ws.scratch_stride
+                       : (phase == 2 ? ws.lpc_coef + (size_t)b * kLpcOrder * F_ : S.coef);
 
     // The trip count depends on blockIdx only and every warp runs every iteration (warps past the last frame redo it
     // and drop the result): the compiler can then prove that the ~200 shuffles per frame are convergent.  With
@@ -97,32 +324,7 @@ __global__ void __launch_bounds__(kLpcThreads, 3) k_lpc(const float* __restrict_
     for (int fr_base = frb; fr_base < F_ && phase != 2; fr_base += frs) {
         const bool fr_valid = fr_base + warp < F_;
         const int fr = fr_valid ? fr_base + warp : F_ - 1;
-        const int start = fr * kLpcShift;
-        double Bv[kLpcPer], Fv[kLpcPer];
-#pragma unroll
-        for (int q = 0; q < kLpcPer; ++q) {
-            const int n = kLpcPer * lane + q, gi = start + n;
-            double x = 0.0;
-            if (n < kLpcFrame) {
-                // y_emph = append(y[0], y[1:] - 0.97 * y[:-1])   (float32)
-                const float e = gi == 0 ? __ldg(yb) : __fsub_rn(__ldg(yb + gi), __fmul_rn(0.97f, __ldg(yb + gi - 1)));
-                x = (double)e * __ldg(tb.hamming400 + n);
-            }
-            Bv[q] = x;
-        }
-        // fwd[n] pairs with bwd[n]: F[q] = x[n + 1]
-        const double nxt = __shfl_down_sync(0xffffffffu, Bv[0], 1);
-#pragma unroll
-        for (int q = 0; q < kLpcPer - 1; ++q) Fv[q] = Bv[q + 1];
-        Fv[kLpcPer - 1] = lane < 31 ? nxt : 0.0;
-        // bwd = x[:-1]: sample 399 is never a backward error
-        if (lane == (kLpcFrame - 1) / kLpcPer) Bv[(kLpcFrame - 1) % kLpcPer] = 0.0;
-        double den = 0.0;
-#pragma unroll
-        for (int q = 0; q < kLpcPer; ++q) den = fma(Fv[q], Fv[q], fma(Bv[q], Bv[q], den));
-        den = warp_sum(den);
-        double a_lane = lane == 0 ? 1.0 : 0.0;
-        burg_all<0>(Fv, Bv, a_lane, den, lane);
+        const double a_lane = burg_frame(yb, fr * kLpcShift, tb.hamming400, lane);
         if (fr_valid && lane >= 1 && lane <= kLpcOrder) coef[(lane - 1) * F_ + fr] = (float)a_lane;
     }
     if (LONG && phase == 1) return;
@@ -168,13 +370,25 @@ void launch_lpc(const float* y, int n, const Geometry& g, const Tables& tb, cons
     once.run([&] {
         cudaFuncSetAttribute(k_lpc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpcSmem));
         cudaFuncSetAttribute(k_lpc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpcSmem));
+        cudaFuncSetAttribute(k_lpc_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLfPhi * kLfThreads * sizeof(double)));
     });
     if (g.long_mode) {
         k_lpc<true><<<dim3(n, 16), kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats, 1);
         k_lpc<true><<<dim3(n, 1), kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats, 2);
         note_launch();
     } else {
-        k_lpc<false><<<n, kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats, 0);
+        // BPC_LPC_FAST=0: the direct recursion for every frame in one kernel (the r02-g form)
+        static const bool fast = !(std::getenv("BPC_LPC_FAST") && std::atoi(std::getenv("BPC_LPC_FAST")) == 0);
+        if (fast && ws.lpc_coef && g.L >= kLpcFrame + kLpcShift) {
+            cudaMemsetAsync(ws.lpc_redo, 0, sizeof(int), st);
+            const long long frames = (long long)n * g.lpc_frames;
+            k_lpc_fast<<<(unsigned)((frames + kLfThreads - 1) / kLfThreads), kLfThreads, kLfPhi * kLfThreads * sizeof(double), st>>>(y, g, ws, n);
+            k_lpc_redo<<<148 * 3, kLpcThreads, 0, st>>>(y, g, tb, ws);
+            k_lpc<false><<<n, kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats, 2);
+            note_launch(2);
+        } else {
+            k_lpc<false><<<n, kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats, 0);
+        }
     }
     note_launch();
 }

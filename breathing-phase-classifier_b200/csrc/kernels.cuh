@@ -67,6 +67,8 @@ struct Workspace {            // per chunk of `cap` segments
     float* dec;               // [cap, dec_stride]  half-band decimated signals of the CQT octaves 1..6 (zero padded)
     int dec_stride;
     float* cens_lo;           // [cap, 3, 12, T] 1 s mode: chroma sums of the CQT octaves 4-6 (k_cens_lo -> k_cens)
+    float* lpc_coef;          // [cap, 12, F] 1 s mode: LPC coefficients of every frame (k_lpc_fast / k_lpc_redo -> k_lpc)
+    int* lpc_redo;            // [1 + cap F]  count, then the (segment F + frame) ids k_lpc_fast left to the direct method
     int* tuning;              // [cap, 2]   tuning bin for 12 / 36 bins per octave
     float* chroma_min;        // [cap, 2]   min of the normalised chroma_stft / chroma_cens rows
     int* ints;                // [cap, 2]   n_peaks, first-min index
@@ -151,6 +153,7 @@ struct WavItem { long long offset, frames; int channels, fmt; };   // payload of
 void launch_wav_decode(const unsigned char* blob, const WavItem* items, int n, int L, float* y, cudaStream_t st);
 
 void upload_cens_constants(const double* taps127);
+void upload_lpc_constants(const double* hamming400);
 int cens_dec_floats_per_segment(int L);
 int64_t launches_issued();   // process-wide counter bumped by every launcher
 void note_launch(int n = 1);

@@ -1,5 +1,5 @@
-"""A/B of CQT / chroma_cens variants on the GPU box: every variant runs in its own process and dumps the chroma plane
-and the raw chroma_cens rows of 130 one-second segments (+ 6 five-second segments with --long); the first variant is the
+"""A/B of CQT / chroma_cens / LPC variants on the GPU box: every variant runs in its own process and dumps the chroma plane
+the raw chroma_cens rows, the LPC plane and the raw LPC coefficients of 130 one-second segments (+ 6 five-second segments with --long); the first variant is the
 reference the others are compared with, value by value.
 
 usage: python tools/cens_ab.py [--long] VARIANT [VARIANT ...]
@@ -36,7 +36,8 @@ def child(out, long_mode):
     eng = bpc_b200.Engine(device=0, max_batch=len(Y), debug=True)
     feats, scal, status = eng.precompute(torch.from_numpy(Y).cuda())
     torch.cuda.synchronize()
-    res = dict(chroma=feats[:, 0].cpu().numpy(), raw=eng.debug("chroma_cens_raw", len(Y)))
+    res = dict(chroma=feats[:, 0].cpu().numpy(), raw=eng.debug("chroma_cens_raw", len(Y)),
+               lpc=feats[:, 2].cpu().numpy(), lpc_raw=eng.debug("lpc_raw", len(Y)))
     if long_mode:
         d = 5
         YL = np.stack([np.concatenate([ys[(7 * i + j) % 128] for j in range(d)]) for i in range(6)])
