@@ -125,10 +125,10 @@ __device__ __forceinline__ double burg_frame(const float* __restrict__ yb, int s
 // kLfGainFloor (6 % of the real fixture frames, none of the synthetic bench frames) are therefore queued and redone by
 // the direct method (burg_frame, one warp per frame: k_lpc_redo), so every output is either the direct recursion or
 // within 3e-9 of it -- two orders below the float32 rounding of the stored coefficients.
-// One THREAD per (segment, frame): the 13 lag sums are 13 independent FMA chains over a register ring of the last 13
-// samples (FP64-pipe bound, 82 % of the instructions of the pass are DFMA), Phi (91 doubles) lives in shared memory
-// column-per-thread, the order recursion is fully unrolled so that a, the head and the tail samples stay in registers.
-constexpr int kLfThreads = 128, kLfM = kLpcOrder, kLfPhi = (kLfM + 1) * (kLfM + 2) / 2;
+// One THREAD per frame: the 13 lag sums are 13 independent FMA chains over a register ring of the last 13
+// samples (FP64-pipe bound, 82 % of the instructions of the pass are DFMA), the order recursion is fully unrolled so
+// that Phi (91 doubles), a, the head and the tail samples are statically indexed registers.
+constexpr int kLfThreads = 96, kLfM = kLpcOrder, kLfPhi = (kLfM + 1) * (kLfM + 2) / 2;
 constexpr double kLfGainFloor = 1e-4;
 __host__ __device__ constexpr int lf_idx(int u, int v) {        // u <= v
     return u * (kLfM + 1) - u * (u - 1) / 2 + (v - u);
@@ -144,11 +144,17 @@ struct LfState {
     double a[kLfM + 1];
     double head[kLfM + 1];      // x[0 .. 12]
     double tl[kLfM + 1];        // x[N-1-k], k = 0 .. 12
+    double c[kLfM + 1];         // Phi[0][v]: the 13 lag sums
     double den, den0;
     bool redo;
 };
 
-#define LF_PHI(u, v) phi[lf_idx((u) < (v) ? (u) : (v), (u) < (v) ? (v) : (u)) * kLfThreads]
+// Phi[u][v] (symmetric): row 0 in registers, rows 1 .. 12 in shared memory, one column of 78 doubles per thread
+#define LF_LO(u, v) ((u) < (v) ? (u) : (v))
+#define LF_HI(u, v) ((u) < (v) ? (v) : (u))
+// (volatile: without it the compiler forwards the 78 stored values to their uses, i.e. keeps them in registers it
+// does not have -- 880 bytes of local-memory spills per thread)
+#define LF_PHI(u, v) (LF_LO(u, v) == 0 ? s.c[LF_HI(u, v)] : static_cast<const volatile double*>(phi)[(lf_idx(LF_LO(u, v), LF_HI(u, v)) - (kLfM + 1)) * kLfThreads])
 
 template <int I>
 __device__ __forceinline__ void lf_order(LfState& s, const double* __restrict__ phi) {
@@ -202,89 +208,114 @@ __device__ __forceinline__ void lf_order(LfState& s, const double* __restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(kLfThreads, 2) k_lpc_fast(const float* __restrict__ y, Geometry g, Workspace ws,
-                                                            int n_seg) {
+// One CTA per segment, 96 threads = frames 0 .. 95 (three full warps; the two remaining frames of a 1 s segment go to
+// k_lpc_redo).  The segment is staged by bulk-TMA copies (cp.async.bulk + mbarrier, SASS UBLKCP): one copy per row of
+// 160 samples (= the frame shift) at a row pitch of 164 floats, so that the float4 a thread loads for its frame --
+// frame f starts at row f -- falls into a different 16-byte bank group for each of eight consecutive lanes: the
+// strided per-frame reads (stride 640 B: 32 distinct L1 lines per request from global memory, which bound the first
+// version of this kernel by its load pipe) become conflict-free LDS.128.
+constexpr int kLfRow = kLpcShift, kLfPitch = kLfRow + 4, kLfRows = 16000 / kLfRow;
+struct LfSmem {
+    float y[kLfRows * kLfPitch];                                 // later: Phi rows 1 .. 12, [78][96] doubles
+    uint64_t bar;
+};
+static_assert((kLfPhi - kLfM - 1) * kLfThreads * sizeof(double) <= kLfRows * kLfPitch * sizeof(float), "Phi fits the staging buffer");
+
+__global__ void __launch_bounds__(kLfThreads, 3) k_lpc_fast(const float* __restrict__ y, Geometry g, Workspace ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* phi = reinterpret_cast<double*>(smem_raw) + threadIdx.x;        // [kLfPhi][kLfThreads], this thread's column
-    const int F = g.lpc_frames, L = g.L;
-    const long long gid = (long long)blockIdx.x * kLfThreads + threadIdx.x;
-    const bool live = gid < (long long)n_seg * F;
-    const int b = live ? (int)(gid / F) : 0, fr = live ? (int)(gid - (long long)b * F) : 0;
-    const float* yb = y + (size_t)b * L;
-    const int start = fr * kLpcShift;
+    LfSmem& S = *reinterpret_cast<LfSmem*>(smem_raw);
+    const int F = g.lpc_frames, tid = threadIdx.x, b = blockIdx.x;
+    const float* yb = y + (size_t)b * g.L;
+    if (tid == 0) mbar_init(&S.bar, 1);
+    __syncthreads();
+    if (tid < 32) {
+        if (tid == 0) mbar_expect_tx(&S.bar, (uint32_t)(kLfRows * kLfRow * sizeof(float)));
+        __syncwarp();
+        for (int r = tid; r < kLfRows; r += 32)
+            tma_bulk_g2s(S.y + r * kLfPitch, yb + r * kLfRow, (uint32_t)(kLfRow * sizeof(float)), &S.bar);
+    }
+    mbar_wait(&S.bar, 0);
+    const int fr = tid;                                          // F >= 96 in 1 s mode (98)
+    const float* srow = S.y + fr * kLfPitch;                     // sample n of the frame: srow[n + 4 (n / 160)]
     LfState s;
     double ring[kLfM + 1], acc[kLfM + 1];
-    // samples 0 .. 12: fill the ring; y_emph = append(y[0], y[1:] - 0.97 * y[:-1]) (float32), frame = y_emph * hamming
-    float yprev = start > 0 ? __ldg(yb + start - 1) : 0.f;
+    // y_emph = append(y[0], y[1:] - 0.97 * y[:-1]) (float32), frame = y_emph * hamming (float64)
+    float yprev = fr > 0 ? srow[-5] : 0.f;                       // sample 160 fr - 1 = column 159 of the previous row
     double e_head = 0.0;
 #pragma unroll
-    for (int n = 0; n <= kLfM; ++n) {
-        const float yc = __ldg(yb + start + n);
-        const float e = (start + n == 0) ? yc : __fsub_rn(yc, __fmul_rn(0.97f, yprev));
-        yprev = yc;
-        const double x = (double)e * c_hamming400[n];
-        ring[n] = x;
-        s.head[n] = x;
-        if (n < kLfM) e_head = fma(x, x, e_head);
+    for (int n4 = 0; n4 < 12; n4 += 4) {                         // samples 0 .. 11: fill the ring
+        const float4 q = *reinterpret_cast<const float4*>(srow + n4);
+        const float ys[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int n = n4 + w;
+            const float e = (fr == 0 && n == 0) ? ys[w] : __fsub_rn(ys[w], __fmul_rn(0.97f, yprev));
+            yprev = ys[w];
+            const double x = (double)e * c_hamming400[n];
+            ring[n] = x;
+            s.head[n] = x;
+            e_head = fma(x, x, e_head);
+        }
     }
-    // n = 12: the first term of every lag sum
 #pragma unroll
-    for (int v = 0; v <= kLfM; ++v) acc[v] = ring[kLfM] * ring[kLfM - v];
-    // n = 13 .. 399 in blocks of 13 (static ring rotation): 29 blocks + 10 samples
-    auto step = [&](int n, auto slot_c) {
-        constexpr int slot = decltype(slot_c)::value;
-        const float yc = __ldg(yb + start + n);
-        const float e = __fsub_rn(yc, __fmul_rn(0.97f, yprev));
-        yprev = yc;
-        const double x = (double)e * c_hamming400[n];
-        ring[slot] = x;
+    for (int v = 0; v <= kLfM; ++v) acc[v] = 0.0;
+    // samples 12 .. 399: the 13 lag sums over a register ring (slot = n % 13: static inside a block of 52 = lcm(13, 4))
+    auto block = [&](int n0, auto count_c, bool first) {
+        constexpr int kCount = decltype(count_c)::value;         // samples in this block, a multiple of 4
 #pragma unroll
-        for (int v = 0; v <= kLfM; ++v) acc[v] = fma(x, ring[(slot - v + 13) % 13], acc[v]);
+        for (int u4 = 0; u4 < kCount; u4 += 4) {
+            const int n = n0 + u4;
+            const float4 q = *reinterpret_cast<const float4*>(srow + n + 4 * ((n >= kLfRow) + (n >= 2 * kLfRow)));
+            const float ys[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                constexpr int kDummy = 0; (void)kDummy;
+                const int u = u4 + w;
+                const float e = __fsub_rn(ys[w], __fmul_rn(0.97f, yprev));
+                yprev = ys[w];
+                const double x = (double)e * c_hamming400[n + w];
+                const int slot = (12 + u) % 13;
+                ring[slot] = x;
+                if (u == 0 && first) s.head[kLfM] = x;           // x[12]
+#pragma unroll
+                for (int v = 0; v <= kLfM; ++v) acc[v] = fma(x, ring[(slot - v + 13) % 13], acc[v]);
+            }
+        }
     };
 #pragma unroll 1
-    for (int blk = 0; blk < 29; ++blk) {
-        const int n0 = 13 + 13 * blk;
-        step(n0 + 0, std::integral_constant<int, 0>{});   step(n0 + 1, std::integral_constant<int, 1>{});
-        step(n0 + 2, std::integral_constant<int, 2>{});   step(n0 + 3, std::integral_constant<int, 3>{});
-        step(n0 + 4, std::integral_constant<int, 4>{});   step(n0 + 5, std::integral_constant<int, 5>{});
-        step(n0 + 6, std::integral_constant<int, 6>{});   step(n0 + 7, std::integral_constant<int, 7>{});
-        step(n0 + 8, std::integral_constant<int, 8>{});   step(n0 + 9, std::integral_constant<int, 9>{});
-        step(n0 + 10, std::integral_constant<int, 10>{}); step(n0 + 11, std::integral_constant<int, 11>{});
-        step(n0 + 12, std::integral_constant<int, 12>{});
-    }
-    step(390, std::integral_constant<int, 0>{}); step(391, std::integral_constant<int, 1>{});
-    step(392, std::integral_constant<int, 2>{}); step(393, std::integral_constant<int, 3>{});
-    step(394, std::integral_constant<int, 4>{}); step(395, std::integral_constant<int, 5>{});
-    step(396, std::integral_constant<int, 6>{}); step(397, std::integral_constant<int, 7>{});
-    step(398, std::integral_constant<int, 8>{}); step(399, std::integral_constant<int, 9>{});
+    for (int blk = 0; blk < 7; ++blk) block(12 + 52 * blk, std::integral_constant<int, 52>{}, blk == 0);
+    block(376, std::integral_constant<int, 24>{}, false);
     // x[N-1-k] sits in ring slot (399 - k) % 13 = (9 - k + 13) % 13
 #pragma unroll
     for (int k = 0; k <= kLfM; ++k) s.tl[k] = ring[(9 - k + 13) % 13];
-    // Phi: first row from the lag sums, the rest by the edge recurrence
+    // Phi: first row = the lag sums (registers), rows 1 .. 12 by the edge recurrence into the staging buffer, which
+    // every thread of the CTA has finished reading
 #pragma unroll
-    for (int v = 0; v <= kLfM; ++v) phi[lf_idx(0, v) * kLfThreads] = acc[v];
+    for (int v = 0; v <= kLfM; ++v) s.c[v] = acc[v];
+    __syncthreads();
+    double* phi = reinterpret_cast<double*>(S.y) + tid;
 #pragma unroll
     for (int u = 0; u < kLfM; ++u)
 #pragma unroll
-        for (int v = u; v < kLfM; ++v)
-            phi[lf_idx(u + 1, v + 1) * kLfThreads] =
-                fma(-s.tl[u], s.tl[v], fma(s.head[kLfM - 1 - u], s.head[kLfM - 1 - v], phi[lf_idx(u, v) * kLfThreads]));
+        for (int v = u; v < kLfM; ++v) {
+            const double prev = u == 0 ? s.c[v] : phi[(lf_idx(u, v) - (kLfM + 1)) * kLfThreads];
+            phi[(lf_idx(u + 1, v + 1) - (kLfM + 1)) * kLfThreads] =
+                fma(-s.tl[u], s.tl[v], fma(s.head[kLfM - 1 - u], s.head[kLfM - 1 - v], prev));
+        }
     // den_0 = sum fwd^2 + sum bwd^2 = 2 sum x^2 - x[0]^2 - x[N-1]^2
     const double c0 = acc[0] + e_head;
     s.den0 = s.den = 2.0 * c0 - s.head[0] * s.head[0] - s.tl[0] * s.tl[0];
     s.redo = false;
 #pragma unroll
     for (int j = 0; j <= kLfM; ++j) s.a[j] = j == 0 ? 1.0 : 0.0;
-    if (s.den0 == 0.0) {
-        // an all-zero frame: every reflection coefficient is -2 * 0 / (0 + tiny) = 0
-    } else {
-        lf_order<0>(s, phi);
-    }
-    if (!live) return;
+    // (an all-zero frame keeps a = [1, 0, ...]: every reflection coefficient is -2 * 0 / (0 + tiny) = 0)
+    if (s.den0 != 0.0) lf_order<0>(s, phi);
     float* coef = ws.lpc_coef + (size_t)b * kLpcOrder * F;
 #pragma unroll
     for (int j = 1; j <= kLfM; ++j) coef[(j - 1) * F + fr] = (float)s.a[j];
-    if (s.redo) ws.lpc_redo[1 + atomicAdd(ws.lpc_redo, 1)] = (int)gid;
+    if (s.redo) ws.lpc_redo[1 + atomicAdd(ws.lpc_redo, 1)] = b * F + fr;
+    // frames 96 .. F-1: the direct method (no fourth warp for two frames)
+    if (tid < F - kLfThreads) ws.lpc_redo[1 + atomicAdd(ws.lpc_redo, 1)] = b * F + kLfThreads + tid;
 }
 
 // The frames k_lpc_fast queued, by the direct recursion: one warp per frame.
@@ -370,7 +401,7 @@ void launch_lpc(const float* y, int n, const Geometry& g, const Tables& tb, cons
     once.run([&] {
         cudaFuncSetAttribute(k_lpc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpcSmem));
         cudaFuncSetAttribute(k_lpc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpcSmem));
-        cudaFuncSetAttribute(k_lpc_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLfPhi * kLfThreads * sizeof(double)));
+        cudaFuncSetAttribute(k_lpc_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LfSmem));
     });
     if (g.long_mode) {
         k_lpc<true><<<dim3(n, 16), kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats, 1);
@@ -379,10 +410,10 @@ void launch_lpc(const float* y, int n, const Geometry& g, const Tables& tb, cons
     } else {
         // BPC_LPC_FAST=0: the direct recursion for every frame in one kernel (the r02-g form)
         static const bool fast = !(std::getenv("BPC_LPC_FAST") && std::atoi(std::getenv("BPC_LPC_FAST")) == 0);
-        if (fast && ws.lpc_coef && g.L >= kLpcFrame + kLpcShift) {
+        if (fast && ws.lpc_coef && g.L == kLfRows * kLfRow && g.lpc_frames >= kLfThreads &&
+            (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
             cudaMemsetAsync(ws.lpc_redo, 0, sizeof(int), st);
-            const long long frames = (long long)n * g.lpc_frames;
-            k_lpc_fast<<<(unsigned)((frames + kLfThreads - 1) / kLfThreads), kLfThreads, kLfPhi * kLfThreads * sizeof(double), st>>>(y, g, ws, n);
+            k_lpc_fast<<<n, kLfThreads, sizeof(LfSmem), st>>>(y, g, ws);
             k_lpc_redo<<<148 * 3, kLpcThreads, 0, st>>>(y, g, tb, ws);
             k_lpc<false><<<n, kLpcThreads, sizeof(LpcSmem), st>>>(y, g, tb, ws, feats, 2);
             note_launch(2);
