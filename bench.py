@@ -482,7 +482,7 @@ def run_ours(args):
         timing_ids = {"k_stft512": ["k_stft512"], "k_spec512_consumers": ["k_spec512_consumers", "k_spec512_light"],
                       "k_frame2048": ["k_frame2048"], "k_even2048": ["k_even2048"], "k_cens": ["k_cens"], "k_cens_dec": ["k_cens_dec"], "k_cens_lo": ["k_cens_lo"],
                       "k_time_basic+k_autocorr": ["k_time_basic", "k_autocorr"], "k_hilbert": ["k_hilbert"],
-                      "k_lpc": ["k_lpc"], "k_stats": ["k_stats_scalars", "k_stats"], "k_seg2048": ["k_seg2048"],
+                      "k_lpc": ["k_lpc", "k_lpc_fast", "k_lpc_redo"], "k_stats": ["k_stats_scalars", "k_stats"], "k_seg2048": ["k_seg2048"],
                       "k_ingest": ["k_ingest"]}
         segs_per_launch = min(B, eng.chunk)
         traffic = None
