@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbpc_b200.so")
+LIB_PATH = os.environ.get("BPC_LIB") or os.path.join(_HERE, "libbpc_b200.so")
 
 NUM_CHANNELS = 9
 NUM_SCALARS = 36
@@ -60,8 +60,8 @@ _SIGS = {
     "bpc_host_alloc": (C.c_void_p, [C.c_void_p, C.c_int64, C.POINTER(C.c_int)]),
     "bpc_host_free": (None, [C.c_void_p, C.c_void_p]),
     "bpc_wav_parse": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
-    "bpc_wav_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
-                                 C.c_void_p]),
+    "bpc_wav_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                 C.c_void_p, C.c_void_p]),
     "bpc_resample_len": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "bpc_resample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "bpc_resample_filter": (C.c_int64, [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int),

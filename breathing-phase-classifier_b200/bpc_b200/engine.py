@@ -162,7 +162,7 @@ class Engine:
         def _decode(idx, out, out_len):
             inf = (L.WavInfo * len(idx))(*[infos[i] for i in idx])
             of = np.ascontiguousarray(offs[idx])
-            _check(self._h, self._lib.bpc_wav_decode(self._h, blob.data_ptr(), of.ctypes.data, C.byref(inf), len(idx),
+            _check(self._h, self._lib.bpc_wav_decode(self._h, blob.data_ptr(), int(blob.numel()), of.ctypes.data, C.byref(inf), len(idx),
                                                      int(out_len), out.data_ptr(), st), "bpc_wav_decode")
 
         if same:

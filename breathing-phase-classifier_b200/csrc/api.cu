@@ -1576,8 +1576,8 @@ int bpc_resample(bpc_handle* h, const float* in, int64_t n_in, int sr_in, int sr
     return BPC_OK;
 }
 
-int bpc_wav_decode(bpc_handle* h, const void* blob, const int64_t* file_offset, const bpc_wav_info* info, int64_t n,
-                   int64_t L, float* y, void* stream) {
+int bpc_wav_decode(bpc_handle* h, const void* blob, int64_t blob_bytes, const int64_t* file_offset,
+                   const bpc_wav_info* info, int64_t n, int64_t L, float* y, void* stream) {
     if (!h) return BPC_ERR_ARG;
     if (n == 0) return BPC_OK;
     if (!blob || !file_offset || !info || !y || n < 0 || n > 65535 || L <= 0 || L > 0x7fffffff) {
@@ -1591,7 +1591,13 @@ int bpc_wav_decode(bpc_handle* h, const void* blob, const int64_t* file_offset, 
             h->err = "bpc_wav_decode: info[" + std::to_string(i) + "] does not come from a successful bpc_wav_parse";
             return BPC_ERR_ARG;
         }
-        items[(size_t)i] = {(long long)(file_offset[i] + f.data_offset), (long long)f.frames, f.channels, f.fmt};
+        static const int width[7] = {0, 1, 2, 3, 4, 4, 8};
+        const int64_t first = file_offset[i] + f.data_offset, bytes = f.frames * f.channels * width[f.fmt];
+        if (file_offset[i] < 0 || first < 0 || first > blob_bytes || bytes > blob_bytes - first) {
+            h->err = "bpc_wav_decode: the samples of file " + std::to_string(i) + " do not lie inside the blob";
+            return BPC_ERR_ARG;
+        }
+        items[(size_t)i] = {(long long)first, (long long)f.frames, f.channels, f.fmt};
     }
     BPC_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1604,7 +1610,7 @@ int bpc_wav_decode(bpc_handle* h, const void* blob, const int64_t* file_offset, 
     }
     // pageable source: the runtime stages it before returning, `items` may die with this call
     BPC_CUDA(h, cudaMemcpyAsync(h->wav_items, items.data(), sizeof(WavItem) * (size_t)n, cudaMemcpyHostToDevice, st));
-    launch_wav_decode(static_cast<const unsigned char*>(blob), h->wav_items, (int)n, (int)L, y, st);
+    launch_wav_decode(static_cast<const unsigned char*>(blob), (long long)blob_bytes, h->wav_items, (int)n, (int)L, y, st);
     BPC_CUDA(h, cudaGetLastError());
     return BPC_OK;
 }

@@ -23,6 +23,16 @@ struct PerDeviceOnce {
 };
 
 
+// Index assertions of the checked build (`make checked` -> gpurun_variants/lib_checked.so, -DBPC_CHECKED): the GPU pool
+// has no compute-sanitizer, so the kernels added in r02 state their own bounds; a violated one traps the kernel and the
+// next API call reports the launch failure.  Compiled out of the product library.
+#ifdef BPC_CHECKED
+#include <cassert>
+#define BPC_ASSERT(c) assert(c)
+#else
+#define BPC_ASSERT(c) ((void)0)
+#endif
+
 constexpr int kPlaneRows = 128;
 constexpr int kMagStride = 260;          // |STFT512| workspace row stride (257 valid bins, 16-byte aligned rows)
 constexpr int kMag2048Stride = 1028;     // |STFT2048| workspace row stride (1025 valid bins)

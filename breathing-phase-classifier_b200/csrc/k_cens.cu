@@ -273,6 +273,7 @@ __device__ __forceinline__ void cq_triple(const float2* __restrict__ w0, int td1
                                           float& m0, float& m1, float& m2) {
     const float2* w1 = w0 + kCqWPitch - td1;
     const float2* w2 = w0 + 2 * kCqWPitch - td2;
+    BPC_ASSERT(td1 >= 0 && td2 >= td1 && td2 <= kCqPadL && tu >= 1 && tu <= kCqWPitch - kCqPadL);   // taps inside the padded rows
     float cr0 = 0.f, ci0 = 0.f, cr1 = 0.f, ci1 = 0.f, cr2 = 0.f, ci2 = 0.f;
 #pragma unroll 4
     for (int u = 0; u < tu; ++u) {
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
                 // cq_to_chroma: chroma c sums bins {3c-1, 3c, 3c+1} (mod 36) of every octave, octave by octave
                 if (o > 0) csum += S.m2[(o - 1) & 1][pf][(pp + kCqTriples - 1) % kCqTriples] + pm0 + pm1;
                 float m2v;
+                BPC_ASSERT(ts >= 0 && ts + tu <= kCqSpecPitch);
                 cq_triple(S.cq.wpad[o & 1] + 3 * pp * kCqWPitch + kCqPadL, td1, td2, tu, &S.spec[pf][ts], o,
                           S.inv_sl + (kCqtBins - kCqtBinsPerOct * (o + 1)) + 3 * pp, pm0, pm1, m2v);
                 S.m2[o & 1][pf][pp] = m2v;
@@ -525,6 +527,7 @@ __device__ __forceinline__ void lo_hops(const double* __restrict__ d, const doub
     for (int i = 0; i < hops; ++i) {
         if (EMIT && store) out[i * kLoSpecPitch] = make_float2((float)X.x, (float)X.y);
         const double2* dp = reinterpret_cast<const double2*>(d + i * H);
+        BPC_ASSERT((reinterpret_cast<uintptr_t>(dp) & 15) == 0);
         double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
 #pragma unroll
         for (int n = 0; n < H; n += 2) {
@@ -587,6 +590,7 @@ __global__ void __launch_bounds__(kLoThreads, 3) k_cens_lo(Geometry g, Tables tb
     const int ts = S.cq.tri_s[p], td1 = S.cq.tri_d1[p], td2 = S.cq.tri_d2[p], tu = S.cq.tri_u[p];
     for (int t0 = 0; t0 < T; t0 += kLoBatch) {
         const int nf = min(kLoBatch, T - t0);
+        BPC_ASSERT(256 + (t0 + nf) * 16 <= kLoD0 && 256 + (t0 + nf) * 8 <= kLoD1 && t0 + nf <= T);
         if (grp == 0) {
             lo_hops<16, true>(S.d0 + 256 + t0 * 16, tw, rot16, Xa, nf, &S.spec[0][0][ks], store);
         } else {
@@ -604,6 +608,7 @@ __global__ void __launch_bounds__(kLoThreads, 3) k_cens_lo(Geometry g, Tables tb
         for (int q2 = 0; q2 < kLoOcts; ++q2) {
             const int o = kLoFirstOct + q2;
             float m2v;
+            BPC_ASSERT(ts >= 0 && ts + tu <= kLoSpecPitch && f < kLoBatch && p < kLoTriples);
             cq_triple(S.cq.wpad[o & 1] + 3 * p * kCqWPitch + kCqPadL, td1, td2, tu, &S.spec[q2][f][ts], o,
                       S.inv_sl + (kCqtOctaves - 1 - o) * kCqtBinsPerOct + 3 * p, m0[q2], m1[q2], m2v);
             S.m2[q2][f][p] = m2v;

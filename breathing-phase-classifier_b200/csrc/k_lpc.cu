@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(kLfThreads, 3) k_lpc_fast(const float* __restr
 #pragma unroll
         for (int u4 = 0; u4 < kCount; u4 += 4) {
             const int n = n0 + u4;
+            BPC_ASSERT(fr * kLfPitch + n + 4 * ((n >= kLfRow) + (n >= 2 * kLfRow)) + 3 < kLfRows * kLfPitch);
             const float4 q = *reinterpret_cast<const float4*>(srow + n + 4 * ((n >= kLfRow) + (n >= 2 * kLfRow)));
             const float ys[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(kLfThreads, 3) k_lpc_fast(const float* __restr
     float* coef = ws.lpc_coef + (size_t)b * kLpcOrder * F;
 #pragma unroll
     for (int j = 1; j <= kLfM; ++j) coef[(j - 1) * F + fr] = (float)s.a[j];
+    BPC_ASSERT(F - kLfThreads <= kLfThreads && b < ws.cap);
     if (s.redo) ws.lpc_redo[1 + atomicAdd(ws.lpc_redo, 1)] = b * F + fr;
     // frames 96 .. F-1: the direct method (no fourth warp for two frames)
     if (tid < F - kLfThreads) ws.lpc_redo[1 + atomicAdd(ws.lpc_redo, 1)] = b * F + kLfThreads + tid;
@@ -327,6 +329,7 @@ __global__ void __launch_bounds__(kLpcThreads, 3) k_lpc_redo(const float* __rest
     for (int i = w0; i < count; i += warps) {
         const int gid = ws.lpc_redo[1 + i];
         const int b = gid / F, fr = gid - b * F;
+        BPC_ASSERT(count <= ws.cap * F && gid >= 0 && b < ws.cap);
         const double a_lane = burg_frame(y + (size_t)b * g.L, fr * kLpcShift, tb.hamming400, lane);
         if (lane >= 1 && lane <= kLpcOrder) ws.lpc_coef[((size_t)b * kLpcOrder + (lane - 1)) * F + fr] = (float)a_lane;
     }

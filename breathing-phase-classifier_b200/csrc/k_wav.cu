@@ -31,7 +31,7 @@ __device__ __forceinline__ float wav_sample(const unsigned char* __restrict__ p,
     }
 }
 
-__global__ void __launch_bounds__(256) k_wav_decode(const unsigned char* __restrict__ blob,
+__global__ void __launch_bounds__(256) k_wav_decode(const unsigned char* __restrict__ blob, long long blob_bytes,
                                                     const WavItem* __restrict__ items, int L, float* __restrict__ y) {
     const int i = blockIdx.y;
     const WavItem it = items[i];
@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256) k_wav_decode(const unsigned char* __restr
         float v = 0.f;
         if (t < it.frames) {
             const unsigned char* p = blob + it.offset + (size_t)t * it.channels * bytes;
+            BPC_ASSERT(it.offset + ((long long)t + 1) * it.channels * bytes <= blob_bytes);
             float acc = wav_sample(p, it.fmt);
             // librosa.to_mono = np.mean(axis = channels) in float32: sequential sum (fewer than 8 addends), then / count
             for (int c = 1; c < it.channels; ++c) acc = __fadd_rn(acc, wav_sample(p + c * bytes, it.fmt));
@@ -50,9 +51,10 @@ __global__ void __launch_bounds__(256) k_wav_decode(const unsigned char* __restr
     }
 }
 
-void launch_wav_decode(const unsigned char* blob, const WavItem* items, int n, int L, float* y, cudaStream_t st) {
+void launch_wav_decode(const unsigned char* blob, long long blob_bytes, const WavItem* items, int n, int L, float* y,
+                       cudaStream_t st) {
     const int bx = (L + 255) / 256 < 64 ? (L + 255) / 256 : 64;
-    k_wav_decode<<<dim3(bx, n), 256, 0, st>>>(blob, items, L, y);
+    k_wav_decode<<<dim3(bx, n), 256, 0, st>>>(blob, blob_bytes, items, L, y);
     note_launch();
 }
 

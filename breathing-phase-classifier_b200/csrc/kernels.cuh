@@ -150,7 +150,8 @@ void launch_resample(const float* x, long long n_in, const double* tab, int p, i
                      long long n_out, cudaStream_t st);
 
 struct WavItem { long long offset, frames; int channels, fmt; };   // payload of one file inside the blob (k_wav.cu)
-void launch_wav_decode(const unsigned char* blob, const WavItem* items, int n, int L, float* y, cudaStream_t st);
+void launch_wav_decode(const unsigned char* blob, long long blob_bytes, const WavItem* items, int n, int L, float* y,
+                       cudaStream_t st);
 
 void upload_cens_constants(const double* taps127);
 void upload_lpc_constants(const double* hamming400);

@@ -218,7 +218,8 @@ int  bpc_wav_load_batch(const char* const* paths, int64_t n, int expected_sr, in
  * bpc_wav_parse: image of one file -> where its samples lie and how they are stored; returns BPC_OK or a bpc_wav_code
  *   (BPC_WAV_ERR_UNSUPPORTED: compressed formats, other bit depths, more than 7 channels).
  * bpc_wav_decode: blob = n file images in DEVICE memory, file i starting at byte file_offset[i] (host array);
- *   info[i] from bpc_wav_parse (host array).  Writes y[n, L] float32 (device): frames beyond the file are zero, frames
+ *   info[i] from bpc_wav_parse (host array); a payload that does not lie inside blob[0, blob_bytes) is rejected
+ *   (BPC_ERR_ARG) before anything is launched.  Writes y[n, L] float32 (device): frames beyond the file are zero, frames
  *   beyond L are dropped.  Files of another sample rate are decoded at their own rate (resample with bpc_resample). */
 enum bpc_sample_fmt { BPC_FMT_U8 = 1, BPC_FMT_PCM16 = 2, BPC_FMT_PCM24 = 3, BPC_FMT_PCM32 = 4, BPC_FMT_F32 = 5, BPC_FMT_F64 = 6 };
 typedef struct bpc_wav_info {
@@ -227,8 +228,8 @@ typedef struct bpc_wav_info {
     int32_t sr, channels, fmt, reserved;
 } bpc_wav_info;
 int  bpc_wav_parse(const void* image, int64_t n_bytes, bpc_wav_info* info);
-int  bpc_wav_decode(bpc_handle* h, const void* blob, const int64_t* file_offset, const bpc_wav_info* info, int64_t n,
-                    int64_t L, float* y, void* stream);
+int  bpc_wav_decode(bpc_handle* h, const void* blob, int64_t blob_bytes, const int64_t* file_offset,
+                    const bpc_wav_info* info, int64_t n, int64_t L, float* y, void* stream);
 
 /* ---- sample-rate conversion on load ---------------------------------------------------------------
  * process.py:28 `librosa.load(wav_path, sr=SR)` resamples files of any other rate with libsoxr "HQ", an un-vendored
