@@ -553,3 +553,88 @@ def test_wav_parse_walks_chunks_without_touching_samples():
     bad = bytearray(W.image("pcm16", x, 16000)); bad[20] = 2                     # ADPCM
     assert lib.bpc_wav_parse(bytes(bad), len(bad), C.byref(info)) == -12
     assert lib.bpc_wav_parse(None, 0, C.byref(info)) == -1
+
+
+def _burg_lag_products(x, M=12, floor=1e-4):
+    """numpy restatement of csrc/k_lpc.cu::k_lpc_fast: Burg's recursion with the numerator as a quadratic form in the
+    lag-product matrix Phi, librosa's own denominator recursion from the two edge errors.  Returns (a, min den_i / den_0)."""
+    N = len(x)
+    Phi = np.zeros((M + 1, M + 1))
+    for v in range(M + 1):
+        Phi[0, v] = np.dot(x[M:N], x[M - v:N - v])
+    for u in range(M):
+        for v in range(u, M):
+            Phi[u + 1, v + 1] = Phi[u, v] + x[M - 1 - u] * x[M - 1 - v] - x[N - 1 - u] * x[N - 1 - v]
+    Phi = np.triu(Phi) + np.triu(Phi, 1).T
+    a = np.zeros(M + 1); a[0] = 1.0
+    den = den0 = 2 * np.dot(x, x) - x[0] ** 2 - x[N - 1] ** 2
+    gain = 1.0
+    if den0 == 0.0:
+        return a, 1.0
+    for i in range(M):
+        G = Phi[:i + 1, 1:i + 2].T @ a[:i + 1]                       # G[v-1] = sum_j a_j Phi[j][v], v = 1 .. i+1
+        num = float(np.dot(a[i::-1][:i + 1], G))                      # sum_v a_{i+1-v} G[v]
+        for n in range(i + 1, M):                                     # the pairs n = i+1 .. M-1, explicitly
+            j = np.arange(i + 1)
+            num += np.dot(a[:i + 1], x[n - j]) * np.dot(a[:i + 1], x[n - 1 - i + j])
+        k = -2.0 * num / (den + np.finfo(np.float64).tiny)
+        an = a.copy()
+        an[1:i + 2] = a[1:i + 2] + k * a[i::-1][:i + 1]
+        a = an
+        j = np.arange(i + 2)
+        fe, be = np.dot(a[:i + 2], x[i + 1 - j]), np.dot(a[:i + 2], x[N - 1 - (i + 1) + j])
+        den = (1.0 - k * k) * den - be ** 2 - fe ** 2
+        gain = min(gain, den / den0)
+    return a, gain
+
+
+def test_burg_from_lag_products_matches_direct_recursion(golden):
+    """wherever the inverse prediction gain stays above the kernel's floor of 1e-4 the
+    lag-product form of Burg's method agrees with librosa's direct recursion to 1e-8 (measured 3e-9); below it the
+    frame is one the kernel hands to the direct method (a pure tone is such a frame)."""
+    import librosa
+    from oracle import pipeline as P
+    ys = [q.astype(np.float32) / np.float32(32768.0) for q in golden["pcm16"][:4]] + [P.synth_segment(1000 + i) for i in range(3)]
+    worst, kept, dropped = 0.0, 0, 0
+    for y in ys:
+        emph = np.append(y[0], y[1:] - 0.97 * y[:-1])
+        for start in range(0, len(emph) - 400, 160 * 5):
+            fr = np.asarray(emph[start:start + 400] * np.hamming(400), dtype=np.float64)
+            a, gain = _burg_lag_products(fr)
+            if gain > 1e-4:
+                kept += 1
+                worst = max(worst, float(np.abs(a - librosa.lpc(fr, order=12)).max()))
+            else:
+                dropped += 1
+    assert kept > 100 and worst < 1e-8, (kept, dropped, worst)
+    t = np.arange(400) / 16000.0
+    tone = np.round(0.5 * np.sin(2 * np.pi * 440.0 * t) * 32768.0) / 32768.0 * np.hamming(400)
+    assert _burg_lag_products(tone)[1] < 1e-4                         # queued for the direct recursion
+    assert np.array_equal(_burg_lag_products(np.zeros(400))[0], np.eye(13)[0])
+
+
+def test_sliding_dft_of_the_low_cqt_octaves_matches_fft():
+    """DESIGN section 4 (r02-h), csrc/k_cens.cu::k_cens_lo: the rectangular-window STFT-512 of a 1000 / 500 / 250
+    sample signal at hop 16 / 8 / 4, bins 60 .. 148, carried from frame to frame by
+    X_{j+1}[k] = W^{-hk} (X_j[k] + sum_n (x[s_j + 512 + n] - x[s_j + n]) W^{nk}) after a start-up of 16 hops of 16
+    samples from the all-zero window; in the 250-sample octave every frame is a pure rotation of the first."""
+    rng = np.random.default_rng(3)
+    ks = np.arange(60, 149)
+    W = np.exp(-2j * np.pi * np.arange(512) / 512)
+    for n, h in ((1000, 16), (500, 8), (250, 4)):
+        x = rng.standard_normal(n).astype(np.float32).astype(np.float64)
+        xp = np.concatenate([np.zeros(256), x, np.zeros(768)])
+        ref = np.stack([np.fft.rfft(xp[t * h:t * h + 512])[ks] for t in range(63)])
+        xx = np.concatenate([x, np.zeros(2048)])
+        d = np.array([xx[i] - (xx[i - 512] if i >= 512 else 0.0) for i in range(256 + 63 * h)])
+        X = np.zeros(len(ks), complex)
+        for j in range(16):                                           # start-up: 16 hops of 16 samples
+            X = np.conj(W[(16 * ks) % 512]) * (X + sum(d[16 * j + m] * W[(m * ks) % 512] for m in range(16)))
+        out = []
+        for t in range(63):
+            out.append(X)
+            X = np.conj(W[(h * ks) % 512]) * (X + sum(d[256 + t * h + m] * W[(m * ks) % 512] for m in range(h)))
+        err = np.abs(np.array(out) - ref).max() / np.abs(ref).max()
+        assert err < 1e-12, (n, h, err)
+        if n == 250:
+            assert np.all(d[256:] == 0.0)                             # nothing enters or leaves the window any more
