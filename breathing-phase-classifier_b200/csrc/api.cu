@@ -576,6 +576,49 @@ int build_tables(bpc_handle* h) {
         if ((rc = upload(h, re, &tb.cqt_re))) return rc;
         if ((rc = upload(h, im, &tb.cqt_im))) return rc;
         if ((rc = upload(h, sl, &tb.cqt_sqrt_len))) return rc;
+        // the same tables as per-tuning blocks in the layout the CQT kernels keep in shared memory (kernels.cuh::CqBlock)
+        {
+            std::vector<CqBlock> blocks(kNumTunings);
+            std::memset(blocks.data(), 0, blocks.size() * sizeof(CqBlock));
+            const double sqrt2 = std::sqrt(2.0), pi = 3.14159265358979323846;
+            double wsum = 0.0;                                          // hann(43) normalised to unit sum, in index order
+            for (int j = 0; j < 43; ++j) wsum += 0.5 - 0.5 * std::cos(2.0 * pi * (double)j / 42.0);
+            for (int i = 0; i < kNumTunings; ++i) {
+                CqBlock& B = blocks[(size_t)i];
+                const float* bre = re.data() + (size_t)i * kCqtBinsPerOct * kCqtEllWidth;
+                const float* bim = im.data() + (size_t)i * kCqtBinsPerOct * kCqtEllWidth;
+                int cnt[kCqtBinsPerOct];
+                for (int r = 0; r < kCqtBinsPerOct; ++r) {
+                    cnt[r] = 1;                                         // taps up to the row's last non-zero weight
+                    for (int jj = 0; jj < kCqtEllWidth; ++jj) {
+                        const float wr = bre[r * kCqtEllWidth + jj], wi = bim[r * kCqtEllWidth + jj];
+                        const size_t o = (size_t)r * kCqWPitch + kCqPadL + jj;
+                        B.wpad[0][o] = make_float2(wr, wi);
+                        // fft_basis *= sqrt(sr / my_sr) rounded to complex64: odd octaves carry a factor sqrt(2); the
+                        // remaining power of two is applied to the (linear) response, which is exact
+                        B.wpad[1][o] = make_float2((float)((double)wr * sqrt2), (float)((double)wi * sqrt2));
+                        if (jj >= 1 && (wr != 0.f || wi != 0.f)) cnt[r] = jj + 1;
+                    }
+                }
+                for (int p3 = 0; p3 < kCqTriples; ++p3) {
+                    const int16_t* bs = start.data() + (size_t)i * kCqtBinsPerOct + 3 * p3;
+                    const int s0 = bs[0], d1 = bs[1] - s0, d2 = bs[2] - s0;
+                    const int u = std::max(cnt[3 * p3], std::max(d1 + cnt[3 * p3 + 1], d2 + cnt[3 * p3 + 2]));
+                    if (d1 < 0 || d2 < d1 || d2 > kCqPadL || u > kCqWPitch - kCqPadL || s0 - 60 < 0 || s0 - 60 + u > 89) {
+                        h->err = "CQT basis rows do not fit the padded triple layout";
+                        return BPC_ERR_UNSUPPORTED;
+                    }
+                    B.tri_s[p3] = (short)(s0 - 60);
+                    B.tri_d1[p3] = (short)d1;
+                    B.tri_d2[p3] = (short)d2;
+                    B.tri_u[p3] = (short)u;
+                }
+                for (int k = 0; k < kCqtBins; ++k) B.inv_sl[k] = 1.0 / sl[(size_t)i * kCqtBins + k];
+                // scipy.signal.get_window('hann', 43, fftbins=False) / sum
+                for (int j = 0; j < 43; ++j) B.swin[j] = (0.5 - 0.5 * std::cos(2.0 * pi * (double)j / 42.0)) / wsum;
+            }
+            if ((rc = upload(h, blocks, &tb.cq_blocks))) return rc;
+        }
         for (int q = 0; q < 3; ++q) tb.cqt_gw[q] = gw[q];
     }
     {

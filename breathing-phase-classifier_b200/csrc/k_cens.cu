@@ -224,46 +224,17 @@ constexpr int kLoFirstOct = 4, kLoOcts = kCqtOctaves - kLoFirstOct;   // octaves
 // were 2.5-way bank conflicts and whose weight loads doubled the wavefronts: 0.19 wavefronts per complex MAC against
 // 0.08 here).
 constexpr int kCqSpecPitch = 89;
-constexpr int kCqPadL = 8, kCqWPitch = 33;                            // padded weight rows: tap index in [-8, 25)
-constexpr int kCqTriples = kCqtBinsPerOct / 3;
 static_assert(kBinSpan + 3 <= kCqSpecPitch, "bands may read up to three bins past kBinHi (zero weights there)");
+static_assert(kCqBinsPerOct == kCqtBinsPerOct && kCqOctaves == kCqtOctaves, "kernels.cuh mirrors tables.hpp");
 
-struct CqTables {
-    float2 wpad[2][kCqtBinsPerOct * kCqWPitch];                  // [0]: basis, [1]: basis * sqrt(2) (odd octaves), (re, im)
-    short tri_s[kCqTriples], tri_d1[kCqTriples], tri_d2[kCqTriples], tri_u[kCqTriples];
-    short cnt[kCqtBinsPerOct];
-};
-
-// Stage the basis of tuning `tun`.  Ends with a CTA barrier.
-__device__ __forceinline__ void cq_stage(CqTables& Q, const Tables& tb, int tun, int tid, int nthreads) {
-    const float* bre = tb.cqt_re + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
-    const float* bim = tb.cqt_im + (size_t)tun * kCqtBinsPerOct * kCqtEllWidth;
-    const double sqrt2 = sqrt(2.0);
-    for (int i = tid; i < kCqtBinsPerOct * kCqWPitch; i += nthreads) {
-        const int r = i / kCqWPitch, jj = i - r * kCqWPitch - kCqPadL;
-        float re = 0.f, im = 0.f;
-        if (jj >= 0 && jj < kCqtEllWidth) { re = bre[r * kCqtEllWidth + jj]; im = bim[r * kCqtEllWidth + jj]; }
-        Q.wpad[0][i] = make_float2(re, im);
-        // fft_basis *= sqrt(sr / my_sr) rounded to complex64: odd octaves carry a factor sqrt(2); the remaining
-        // power of two is applied to the (linear) response, which is exact
-        Q.wpad[1][i] = make_float2((float)((double)re * sqrt2), (float)((double)im * sqrt2));
+// Stage the first `bytes` of the block of tuning `tun` (bulk-TMA, SASS UBLKCP).  `bar` must have been initialised
+// (mbar_init by one thread + a CTA barrier); every thread waits for the data.
+__device__ __forceinline__ void cq_stage(CqBlock& Q, const Tables& tb, int tun, uint32_t bytes, uint64_t* bar, int tid) {
+    if (tid == 0) {
+        mbar_expect_tx(bar, bytes);
+        tma_bulk_g2s(&Q, tb.cq_blocks + tun, bytes, bar);
     }
-    if (tid < kCqtBinsPerOct) {                                  // taps of the row up to its last non-zero weight
-        int c = 1;
-        for (int jj = 1; jj < kCqtEllWidth; ++jj)
-            if (bre[tid * kCqtEllWidth + jj] != 0.f || bim[tid * kCqtEllWidth + jj] != 0.f) c = jj + 1;
-        Q.cnt[tid] = (short)c;
-    }
-    __syncthreads();
-    if (tid < kCqTriples) {
-        const int16_t* bs = tb.cqt_start + tun * kCqtBinsPerOct + 3 * tid;
-        const int s0 = bs[0], d1 = bs[1] - s0, d2 = bs[2] - s0;      // band starts do not decrease with the row
-        Q.tri_s[tid] = (short)(s0 - kBinLo);
-        Q.tri_d1[tid] = (short)d1;
-        Q.tri_d2[tid] = (short)d2;
-        Q.tri_u[tid] = (short)max((int)Q.cnt[3 * tid], max(d1 + (int)Q.cnt[3 * tid + 1], d2 + (int)Q.cnt[3 * tid + 2]));
-    }
-    __syncthreads();
+    mbar_wait(bar, 0);
 }
 
 // |CQ| of rows 3 p, 3 p + 1, 3 p + 2 of octave o for the frame whose spectrum row is `sp` (= spec row + tri_s[p]).
@@ -306,9 +277,8 @@ struct CensSmem {
     float2 spec[kCensTeams][kCqSpecPitch];             // complex64 STFT bins kBinLo.. of the round's sixteen frames
     float m2[2][kCensTeams][kCqTriples];               // |CQ| of row 3 p + 2 (goes to chroma p + 1), by octave parity
     float csum[12 * kMaxFrames];                       // folded chroma sums of the CQT phase
-    CqTables cq;
-    double inv_sl[kCqtBins];                           // 1 / sqrt(lengths)
-    double swin[43];                                   // hann(43) / sum
+    CqBlock cq;                                        // padded basis rows, row triples, 1 / sqrt(lengths), hann(43) / sum
+    uint64_t bar;
     double dscratch[32];
     float fscratch[32];
 };
@@ -330,19 +300,10 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
     float* p_chroma = LONG ? lbase + 12 * (size_t)T : S.u.post.chroma;
     float* p_quant = LONG ? lbase + 24 * (size_t)T : S.u.post.quant;
 
-    // ---- stage the basis of this segment's tuning and the smoothing window
-    const int tun = ws.tuning[b * 2 + 1];
-    {
-        const double* slen = tb.cqt_sqrt_len + (size_t)tun * kCqtBins;
-        for (int i = tid; i < kCqtBins; i += kCensThreads) S.inv_sl[i] = 1.0 / slen[i];
-    }
-    if (tid < 43) {
-        // scipy.signal.get_window('hann', 43, fftbins=False) normalised to unit sum (accumulated in index order)
-        double wsum = 0.0;
-        for (int j = 0; j < 43; ++j) wsum += 0.5 - 0.5 * cos(2.0 * 3.14159265358979323846 * (double)j / 42.0);
-        S.swin[tid] = (0.5 - 0.5 * cos(2.0 * 3.14159265358979323846 * (double)tid / 42.0)) / wsum;
-    }
-    cq_stage(S.cq, tb, tun, tid, kCensThreads);                  // ends with a barrier
+    // ---- stage the tables of this segment's tuning (padded basis rows, 1 / sqrt(lengths), smoothing window)
+    if (tid == 0) mbar_init(&S.bar, 1);
+    __syncthreads();
+    cq_stage(S.cq, tb, ws.tuning[b * 2 + 1], (uint32_t)sizeof(CqBlock), &S.bar, tid);
 
     // ---- CQT -> chroma fold.  A round is sixteen frames: per octave every half-warp transforms its frame
     // (team_fft<16>) and leaves the 85 touched bins in `spec`; then the basis product runs over the round's sixteen
@@ -403,7 +364,7 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
                 float m2v;
                 BPC_ASSERT(ts >= 0 && ts + tu <= kCqSpecPitch);
                 cq_triple(S.cq.wpad[o & 1] + 3 * pp * kCqWPitch + kCqPadL, td1, td2, tu, &S.spec[pf][ts], o,
-                          S.inv_sl + (kCqtBins - kCqtBinsPerOct * (o + 1)) + 3 * pp, pm0, pm1, m2v);
+                          S.cq.inv_sl + (kCqtBins - kCqtBinsPerOct * (o + 1)) + 3 * pp, pm0, pm1, m2v);
                 S.m2[o & 1][pf][pp] = m2v;
             }
         }
@@ -439,7 +400,7 @@ __global__ void __launch_bounds__(kCensThreads, 2) k_cens(const float* __restric
         const int c = i / T, t = i - c * T;
         double acc = 0.0;
         const int jlo = max(0, t + 21 - (T - 1)), jhi = min(42, t + 21);
-        for (int j = jlo; j <= jhi; ++j) acc += S.swin[j] * (double)p_quant[c * T + t + 21 - j];
+        for (int j = jlo; j <= jhi; ++j) acc += S.cq.swin[j] * (double)p_quant[c * T + t + 21 - j];
         p_chroma[i] = (float)acc;
     }
     __syncthreads();
@@ -513,9 +474,10 @@ static_assert(kLoOcts * kLoTriples * kLoBatch == 3 * kLoThreads, "basis product:
 struct CensLoSmem {
     double d0[kLoD0], d1[kLoD1], d2[kLoD2];                      // x[i] - x[i - 512] per octave (octave 6: x[i], i < 256)
     float2 spec[kLoOcts][kLoBatch][kLoSpecPitch];
-    CqTables cq;
+    alignas(16) unsigned char cq_bytes[kCqBlockLoBytes];         // the head of the tuning's CqBlock: basis rows, triples,
+                                                                 // 1 / sqrt(lengths) of octaves 6, 5, 4
     float m2[kLoOcts][kLoBatch][kLoTriples];                     // |CQ| of row 3 p + 2 (goes to chroma p + 1)
-    double inv_sl[kLoOcts * kCqtBinsPerOct];
+    uint64_t bar;
 };
 static_assert(sizeof(CensLoSmem) <= 75 * 1024 + 640, "three CTAs per SM");
 
@@ -544,13 +506,15 @@ __device__ __forceinline__ void lo_hops(const double* __restrict__ d, const doub
 __global__ void __launch_bounds__(kLoThreads, 3) k_cens_lo(Geometry g, Tables tb, Workspace ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CensLoSmem& S = *reinterpret_cast<CensLoSmem*>(smem_raw);
+    const CqBlock& cq = *reinterpret_cast<const CqBlock*>(S.cq_bytes);
     const int tid = threadIdx.x, b = blockIdx.x, T = g.T;
     const float* G = ws.dec + (size_t)b * cens_dec_stride(ws);
-    const int tun = ws.tuning[b * 2 + 1];
-    {
-        // rows of octave o: inv_sl index kCqtBins - 36 (o + 1) + r; octaves 6, 5, 4 are the first three groups of 36
-        const double* slen = tb.cqt_sqrt_len + (size_t)tun * kCqtBins;
-        for (int i = tid; i < kLoOcts * kCqtBinsPerOct; i += kLoThreads) S.inv_sl[i] = 1.0 / slen[i];
+    // tables of this segment's tuning: the bulk copy runs while the difference signals are built
+    if (tid == 0) {
+        mbar_init(&S.bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&S.bar, (uint32_t)kCqBlockLoBytes);
+        tma_bulk_g2s(S.cq_bytes, tb.cq_blocks + ws.tuning[b * 2 + 1], (uint32_t)kCqBlockLoBytes, &S.bar);
     }
 #pragma unroll
     for (int q = 0; q < kLoOcts; ++q) {
@@ -564,7 +528,8 @@ __global__ void __launch_bounds__(kLoThreads, 3) k_cens_lo(Geometry g, Tables tb
             d[i] = a - c;
         }
     }
-    cq_stage(S.cq, tb, tun, tid, kLoThreads);                   // ends with a barrier (d0 .. d2 visible too)
+    __syncthreads();                                            // d0 .. d2 and the barrier object are visible
+    mbar_wait(&S.bar, 0);                                       // ... and so are the tables
     // this thread's bin: twiddles W^{nk}, n < 16, and the hop rotations W^{-hk}
     const int grp = tid / kLoGroup;                             // warp-uniform: 0 = octave 4, 1 = octaves 5 and 6
     const int kk = tid - grp * kLoGroup;                        // bin - kBinLo (lanes past the span idle along)
@@ -587,7 +552,7 @@ __global__ void __launch_bounds__(kLoThreads, 3) k_cens_lo(Geometry g, Tables tb
     if (grp == 1) lo_hops<16, false>(S.d2, tw, rot16, Xb, 16, nullptr, false);
     float* lo = ws.cens_lo + (size_t)b * kLoOcts * 12 * T;
     const int f = tid & 15, p = tid >> 4;                       // basis product: frame of the batch, row triple
-    const int ts = S.cq.tri_s[p], td1 = S.cq.tri_d1[p], td2 = S.cq.tri_d2[p], tu = S.cq.tri_u[p];
+    const int ts = cq.tri_s[p], td1 = cq.tri_d1[p], td2 = cq.tri_d2[p], tu = cq.tri_u[p];
     for (int t0 = 0; t0 < T; t0 += kLoBatch) {
         const int nf = min(kLoBatch, T - t0);
         BPC_ASSERT(256 + (t0 + nf) * 16 <= kLoD0 && 256 + (t0 + nf) * 8 <= kLoD1 && t0 + nf <= T);
@@ -609,8 +574,8 @@ __global__ void __launch_bounds__(kLoThreads, 3) k_cens_lo(Geometry g, Tables tb
             const int o = kLoFirstOct + q2;
             float m2v;
             BPC_ASSERT(ts >= 0 && ts + tu <= kLoSpecPitch && f < kLoBatch && p < kLoTriples);
-            cq_triple(S.cq.wpad[o & 1] + 3 * p * kCqWPitch + kCqPadL, td1, td2, tu, &S.spec[q2][f][ts], o,
-                      S.inv_sl + (kCqtOctaves - 1 - o) * kCqtBinsPerOct + 3 * p, m0[q2], m1[q2], m2v);
+            cq_triple(cq.wpad[o & 1] + 3 * p * kCqWPitch + kCqPadL, td1, td2, tu, &S.spec[q2][f][ts], o,
+                      cq.inv_sl + (kCqtOctaves - 1 - o) * kCqtBinsPerOct + 3 * p, m0[q2], m1[q2], m2v);
             S.m2[q2][f][p] = m2v;
         }
         __syncthreads();

@@ -1,6 +1,7 @@
 // Device-side table / workspace descriptors and kernel launchers shared between api.cu and the k_*.cu files.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstddef>
 #include <cstdint>
 #include "common.cuh"
 #include "../../include/bpc.h"
@@ -14,6 +15,23 @@ struct BankDev {            // band-form triangular filterbank (see tables.hpp::
     const float* wt;        // [width, rows]  (transposed: lanes that own consecutive rows read consecutive words)
     int rows, width;
 };
+
+// ---- per-tuning constant block of the CQT kernels (k_cens, k_cens_lo), built on the host (api.cu::build_tables) in
+// exactly the layout the kernels keep in shared memory, so that staging it is ONE bulk-TMA copy (r02-j; the kernels
+// used to derive it from the band tables in their prologues: 21 % of k_cens's stall samples).
+constexpr int kCqBinsPerOct = 36, kCqOctaves = 7, kCqBins = kCqBinsPerOct * kCqOctaves;
+constexpr int kCqPadL = 8, kCqWPitch = 33;                 // basis rows padded with zeros: tap index in [-8, 25)
+constexpr int kCqTriples = kCqBinsPerOct / 3;
+struct alignas(16) CqBlock {
+    float2 wpad[2][kCqBinsPerOct * kCqWPitch];             // [0]: basis, [1]: basis * sqrt(2) (odd octaves), (re, im)
+    short tri_s[kCqTriples], tri_d1[kCqTriples], tri_d2[kCqTriples], tri_u[kCqTriples];   // row triples: first bin - 60,
+                                                           // offsets of rows 3p+1 / 3p+2, taps of the union band
+    double inv_sl[kCqBins];                                // 1 / sqrt(lengths), lowest octave first
+    double swin[44];                                       // hann(43) / sum (CENS smoothing), one pad entry
+};
+static_assert(sizeof(CqBlock) % 16 == 0, "bulk copies move multiples of 16 bytes");
+constexpr int kCqBlockLoBytes = (int)(offsetof(CqBlock, inv_sl) + 3 * kCqBinsPerOct * sizeof(double));   // k_cens_lo's share
+static_assert(kCqBlockLoBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
 
 struct Tables {
     // FFT
@@ -41,6 +59,7 @@ struct Tables {
     const float* cqt_re;          // [100, 36, W]  band form: entry j of row r weighs bin cqt_start[r] + j (zeros in gaps)
     const float* cqt_im;          // [100, 36, W]
     const double* cqt_sqrt_len;   // [100, 252]
+    const CqBlock* cq_blocks;     // [100]  the same tables per tuning, staged whole by the CQT kernels
     int cqt_gw[3];                // band width needed by the rows 20-35 / 4-19 / 0-3 over all tunings (<= kCqtEllWidth)
     // LPC
     const double* hamming400;     // [400]
