@@ -282,7 +282,8 @@ def run_ours(args):
     h_pad = eng.host_empty((B, 9), np.float32)
     h_scal = eng.host_empty((B, eng.nscal), np.float32)
     h_stat = eng.host_empty((B,), np.int32)
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 5))                 # the two comparison legs (synchronous call, full layout)
+    stream_n = max(1, min(args.steps, 20))                 # the headline leg runs the K steps of the run (at most 20)
 
     def timed_host(fn):
         fn()                                                              # warm-up (allocates the slots)
@@ -320,13 +321,13 @@ def run_ours(args):
     stream_steps(2)                                                        # warm-up (second buffer set gets touched)
     barrier()
     t0 = time.perf_counter()
-    stream_steps(e2e_steps)
+    stream_steps(stream_n)
     torch.cuda.synchronize()
     tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt_c = float(tt.item())
-    e2e_value = world * e2e_steps * B / dt_c
+    e2e_value = world * stream_n * B / dt_c
     stream_check = bool(np.array_equal(out_sets[0][0][:64], out_sets[1][0][:64]) and np.array_equal(out_sets[0][2], out_sets[1][2]))
     d2h_step = int(B * (772 * T * 4 + 9 * 4 + eng.nscal * 4 + 4))
     # the compact result must be the full-layout result: expand 16 segments on the host and compare with the device path
@@ -351,8 +352,57 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     d2h_ceiling_gbs = world * d2h_step / (float(tt.item()) * 1e-3) / 1e9
-    d2h_gbs = world * e2e_steps * d2h_step / dt_c / 1e9
+    d2h_gbs = world * stream_n * d2h_step / dt_c / 1e9
     del d_dummy
+
+    # ---- BASELINE configs[3]: long-segment sweep (1 s - 30 s), equal total samples per point (B / d segments of d seconds
+    # per GPU).  Every rank runs it on its own shard (no data-path collective: segments are independent at every length);
+    # a point's time is the MAX over ranks of the CUDA-event time, its throughput the whole job's.  The collective that
+    # combines the ranks sits outside the try block, so a failing rank cannot leave the others waiting.
+    sweep_all = None
+    if not args.no_extras:
+        lens = (1, 2, 5, 10, 30)
+        sw = torch.zeros(len(lens) + 1, dtype=torch.float64, device=dev)      # ms per point + a failure flag
+        frames = {}
+        err = None
+        try:
+            for i, d in enumerate(lens):
+                Bd = max(1, B // d)
+                e_d = eng if d == 1 else bpc_b200.Engine(device=local, max_batch=Bd,
+                                                         params=bpc_b200.default_params(expected_len=L * d))
+                wd = wav_f32[:Bd * d].reshape(Bd, d * L).contiguous()
+                fd = torch.empty((Bd, 9, 128, e_d.T), dtype=torch.float32, device=dev)
+                sd = torch.empty((Bd, e_d.nscal), dtype=torch.float32, device=dev)
+                td = torch.empty((Bd,), dtype=torch.int32, device=dev)
+                e_d.precompute(wd, fd, sd, td)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(2):
+                    e_d.precompute(wd, fd, sd, td)
+                b.record()
+                torch.cuda.synchronize()
+                sw[i] = a.elapsed_time(b) / 2
+                frames[d] = e_d.T
+                if d != 1:
+                    e_d.close()
+                del fd, sd, td, wd
+        except Exception as e:
+            err = repr(e)
+            sw[len(lens)] = 1.0
+        if dist is not None:
+            dist.all_reduce(sw, op=dist.ReduceOp.MAX)
+        sw_h = sw.cpu().tolist()
+        if sw_h[len(lens)] > 0:
+            sweep_all = {"error": err or "another rank failed"}
+        else:
+            sweep_all = {"ranks": world}
+            for i, d in enumerate(lens):
+                Bd = max(1, B // d)
+                sweep_all[f"{d}s"] = {"segments": world * Bd, "frames": frames[d], "ms": sw_h[i],
+                                      "segments_per_s": world * Bd / (sw_h[i] * 1e-3),
+                                      "audio_seconds_per_s": world * Bd * d / (sw_h[i] * 1e-3),
+                                      "alg_bytes_per_segment": 4 * L * d + 9 * 128 * frames[d] * 4 + 144}
 
     # ---- side measurements (not the headline): BASELINE configs[1] stage and the HBM-bound batch-assembly kernel
     extras = {}
@@ -409,27 +459,9 @@ def run_ours(args):
         except Exception as e:                           # the side measurement must not take the bench line down
             extras["config5_precompute_plus_forward"] = {"error": repr(e)}
 
-        # BASELINE configs[3]: long-segment sweep, equal total samples per point (B = 4096 / d segments of d seconds)
-        try:
-            sweep = {}
-            for d in (1, 2, 5, 10, 30):
-                Bd = max(1, B // d)
-                e_d = eng if d == 1 else bpc_b200.Engine(device=local, max_batch=Bd,
-                                                         params=bpc_b200.default_params(expected_len=L * d))
-                wd = wav_f32[:Bd * d].reshape(Bd, d * L).contiguous()
-                fd = torch.empty((Bd, 9, 128, e_d.T), dtype=torch.float32, device=dev)
-                sd = torch.empty((Bd, e_d.nscal), dtype=torch.float32, device=dev)
-                td = torch.empty((Bd,), dtype=torch.int32, device=dev)
-                msd = timed(lambda: e_d.precompute(wd, fd, sd, td), 2)
-                sweep[f"{d}s"] = {"segments": Bd, "frames": e_d.T, "ms": msd, "segments_per_s": Bd / (msd * 1e-3),
-                                  "audio_seconds_per_s": Bd * d / (msd * 1e-3),
-                                  "alg_bytes_per_segment": 4 * L * d + 9 * 128 * e_d.T * 4 + 144}
-                if d != 1:
-                    e_d.close()
-                del fd, sd, td
-            extras["config4_long_segment_sweep"] = sweep
-        except Exception as e:
-            extras["config4_long_segment_sweep"] = {"error": repr(e)}
+        # BASELINE configs[3]: the long-segment sweep measured above on every rank
+        if sweep_all is not None:
+            extras["config4_long_segment_sweep"] = sweep_all
 
         # BASELINE configs[0] through OUR entry point: wav files + CSV rows -> process_dataset_threaded -> .npz files
         # (reader pool -> bpc_precompute_host -> writer pool), next to the same rows into one packed shard
@@ -559,7 +591,7 @@ def run_ours(args):
                          "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": int(B * L * 2),
-                    "d2h_bytes_per_step": d2h_step, "steps": e2e_steps,
+                    "d2h_bytes_per_step": d2h_step, "steps": stream_n,
                     "input": "pinned host PCM16 [B,16000] -> bpc_precompute_host_compact -> pinned host float32 rows "
                              "[B,772,63] + pad [B,9] + scalars [B,36] + status [B] (the compact host layout of "
                              "include/bpc.h: every data row of the nine planes + one pad_freq constant per plane; "
@@ -572,9 +604,9 @@ def run_ours(args):
                     "matches_device_path": e2e_check and stream_check,
                     "call": "bpc_precompute_host_compact_begin(step k + 1) then bpc_host_wait(step k): two sets of pinned "
                             "output buffers, every step's copies and the final wait inside the timed region",
-                    "synchronous_call": {"value": e2e_sync, "unit": "segments/s",
+                    "synchronous_call": {"value": e2e_sync, "unit": "segments/s", "steps": e2e_steps,
                                          "call": "bpc_precompute_host_compact, one blocking call per step"},
-                    "full_layout": {"value": e2e_full, "unit": "segments/s",
+                    "full_layout": {"value": e2e_full, "unit": "segments/s", "steps": e2e_steps,
                                     "call": "bpc_precompute_host -> pinned host float32 [B,9,128,63]: the same bytes over "
                                             "PCIe, the 380 constant pad rows per segment written by the library's host threads"}},
             "parity_probe": parity_probe,
