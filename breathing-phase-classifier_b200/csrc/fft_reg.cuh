@@ -214,6 +214,54 @@ BPC_HD double2 rsplit_term(double2 zk, double2 zn, double2 wl) {
     return make_double2(s.x + fma(w.x, d.x, -(w.y * d.y)), s.y + fma(w.x, d.y, w.y * d.x));
 }
 
+// ------------------------------------------------------------------------ r02-k: N = 1024 on TWO warps (team of 64)
+// 64 threads x 16 register-resident points, three register stages 16 x 16 x 4 around two exchanges (k_frame2048_w2:
+// half the registers per thread of team_fft<32>, so 20 instead of 12 warps per SM).  With W = exp(-2 pi i / 1024),
+// n = j + 64 n1 and k = k1 + 16 (k2 + 16 k3):
+//   stage A  thread j           : B[j][k1]     = W^(j k1)        sum_n1 x[j + 64 n1]      W_16^(n1 k1)
+//   stage B  thread (k1, j0)    : C[j0][k2]    = W_64^(j0 k2)    sum_m  B[j0 + 4 m][k1]   W_16^(m k2)
+//   stage C  thread (k1, q)     : Z[k1 + 16 (q + 4 r) + 256 k3]  = sum_j0 C[j0][q + 4 r]  W_4^(j0 k3),   r, k3 < 4
+// so the thread ends with Z[c + 64 u], c = k1 + 16 q, u = r + 4 k3 < 16, in register t64_zidx(u).  Exchange 1 goes
+// through rows [k1][j] of pitch 68 (stage B reads j0 + 4 m of row k1: the sixteen (k1, j0) of a half-warp fall into
+// sixteen different 8-byte banks because 68 = 4 mod 16 and the k1 of a half-warp are distinct mod 4); exchange 2 stays
+// inside the four lanes that share k1 and reuses their row ([j0] at pitch 17).
+// Thread -> (k1, q): lane = 4 g + q; the k1 of a warp are chosen so that the thread holding Z[N - k] (c' = (64 - c) % 64,
+// i.e. k1' = (16 - k1) % 16) is in the SAME warp -- the real-input split then pairs bins with shuffles:
+//   warp 0: k1 = 0 1 2 3 | 8 15 14 13      warp 1: k1 = 4 5 6 7 | 12 11 10 9      (g = 0..3 | 4..7)
+constexpr int kT64Pitch = 68;
+BPC_HD constexpr int t64_zidx(int u) { return 4 * (u & 3) + bitrev<4>(u >> 2); }
+BPC_HD int t64_k1(int tid) {
+    const int w = tid >> 5, g = (tid >> 2) & 7;
+    return g < 4 ? 4 * w + g : ((w == 0 && g == 4) ? 8 : 16 - (4 * w + (g - 4)));
+}
+// lane (of the same warp) that holds row c' = (64 - c) % 64; Z[N - (c + 64 u)] is its register t64_zidx(15 - u), except
+// for c = 0, where it is this thread's own t64_zidx((16 - u) % 16)
+BPC_HD int t64_partner_lane(int tid) {
+    const int l = tid & 31, g = l >> 2, q = l & 3, k1 = t64_k1(tid);
+    if (k1 == 0) return (g << 2) | ((4 - q) & 3);
+    if (k1 == 8) return (g << 2) | (3 - q);
+    return ((g ^ 4) << 2) | (3 - q);
+}
+// stages A and B: radix-16 DFT of the 16 register points, then the inter-stage twiddles tw[k * tws], k = 1 .. 15
+// (A: W^(j k1), table [k1][j], tw = table + j, tws = 64;  B: W_64^(j0 k2), table [k2][j0], tw = table + j0, tws = 4)
+BPC_HD void team64_stage(double2* a, const double2* tw, int tws) {
+    reg_dft<16>(a);
+#pragma unroll
+    for (int k = 1; k < 16; ++k) a[bitrev<16>(k)] = c_mul(a[bitrev<16>(k)], tw[k * tws]);
+}
+// stage C: four radix-4 DFTs over j0 (a[4 r + j0] -> a[4 r + bitrev_4(k3)])
+BPC_HD void team64_stage_c(double2* a) {
+    DitR<4, 0, 1>::run(a);
+    DitR<4, 4, 1>::run(a);
+    DitR<4, 8, 1>::run(a);
+    DitR<4, 12, 1>::run(a);
+}
+// exchange indices (elements of the buffer, 16 * kT64Pitch of them)
+BPC_HD constexpr int t64_x1_store(int k1, int j) { return k1 * kT64Pitch + j; }                 // stage A thread j, all k1
+BPC_HD constexpr int t64_x1_load(int k1, int j0, int m) { return k1 * kT64Pitch + j0 + 4 * m; } // -> a[m]
+BPC_HD constexpr int t64_x2_store(int k1, int j0, int k2) { return k1 * kT64Pitch + 17 * j0 + k2; }
+BPC_HD constexpr int t64_x2_load(int k1, int q, int r, int j0) { return k1 * kT64Pitch + 17 * j0 + q + 4 * r; }   // -> a[4 r + j0]
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------ device wrappers
 // Full transform for a team of R lanes inside one warp (R = 16: two teams per warp, R = 32: the warp).  All 32 lanes of
@@ -295,7 +343,44 @@ __device__ __forceinline__ void team_rsplit_pairs(const double2* a, double2 wl, 
         team_rsplit_pairs<R, K2 + 1>(a, wl, h, partner, emit);
     }
 }
+// The whole transform for a CTA of exactly 64 threads (both warps call it together; it contains CTA barriers).
+// in: a[n1] = x[tid + 64 n1]; out: a[t64_zidx(u)] = Z[c + 64 u], c = k1 + 16 q.  xr: 16 * kT64Pitch doubles, exchanged one
+// component at a time (the other component waits in its registers).  twa = table [k1][j] + tid, twb = table [k2][j0] + q.
+__device__ __forceinline__ void team64_fft(double2* a, const double2* twa, const double2* twb, double* xr, int tid,
+                                           int k1, int q) {
+    team64_stage(a, twa, 64);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) xr[t64_x1_store(k, tid)] = a[bitrev<16>(k)].x;
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) a[m].x = xr[t64_x1_load(k1, q, m)];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) xr[t64_x1_store(k, tid)] = a[bitrev<16>(k)].y;
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) a[m].y = xr[t64_x1_load(k1, q, m)];
+    __syncwarp();                       // row k1 is read by its own four lanes only: they may now rewrite it
+    team64_stage(a, twb, 4);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) xr[t64_x2_store(k1, q, k)] = a[bitrev<16>(k)].x;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j0 = 0; j0 < 4; ++j0) a[4 * r + j0].x = xr[t64_x2_load(k1, q, r, j0)];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) xr[t64_x2_store(k1, q, k)] = a[bitrev<16>(k)].y;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j0 = 0; j0 < 4; ++j0) a[4 * r + j0].y = xr[t64_x2_load(k1, q, r, j0)];
+    team64_stage_c(a);
+}
 #endif
+
 
 
 }  // namespace bpc

@@ -272,7 +272,7 @@ def test_register_fft_index_logic_on_host(tmp_path):
                    check=True, capture_output=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     errs = [float(x.split()[-1]) for x in out.strip().splitlines()]
-    assert len(errs) == 2 and errs[0] < 1e-10 and errs[1] < 1e-9, out
+    assert len(errs) == 3 and errs[0] < 1e-10 and errs[1] < 1e-9 and errs[2] < 1e-9, out
 
 
 def test_radix20_hilbert_fft_on_host(tmp_path):
