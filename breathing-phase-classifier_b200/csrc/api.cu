@@ -423,8 +423,8 @@ int build_tables(bpc_handle* h) {
         std::vector<double> hw = hann_periodic(2048);
         for (double& v : hw) v *= 0.5;
         if ((rc = upload(h, hw, &tb.hann2048h))) return rc;
-        std::vector<double2> t(544);
-        for (int k = 0; k < 544; ++k) {
+        std::vector<double2> t(576);
+        for (int k = 0; k < 576; ++k) {
             const double th = 2.0 * kPi * double(k) / 2048.0;
             const double wr = -std::sin(th), wi = -std::cos(th);          // -i exp(-i th)
             t[k] = k < 256 ? make_double2(wi, wr / wi) : make_double2(wr, wi / wr);
@@ -451,6 +451,21 @@ int build_tables(bpc_handle* h) {
                 t[k1 * 16 + hh] = make_double2(std::cos(ang), std::sin(ang));
             }
         if ((rc = upload(h, t, &tb.twa256))) return rc;
+    }
+    {
+        std::vector<double2> ta(16 * 64), tbb(16 * 4);
+        for (int k1 = 0; k1 < 16; ++k1)
+            for (int j = 0; j < 64; ++j) {
+                const double ang = -2.0 * kPi * double(j * k1) / 1024.0;
+                ta[k1 * 64 + j] = make_double2(std::cos(ang), std::sin(ang));
+            }
+        for (int k2 = 0; k2 < 16; ++k2)
+            for (int j0 = 0; j0 < 4; ++j0) {
+                const double ang = -2.0 * kPi * double((j0 * k2) & 63) / 64.0;
+                tbb[k2 * 4 + j0] = make_double2(std::cos(ang), std::sin(ang));
+            }
+        if ((rc = upload(h, ta, &tb.t64a))) return rc;
+        if ((rc = upload(h, tbb, &tb.t64b))) return rc;
     }
     if ((rc = upload(h, twiddles(512, 257), &tb.ptw512))) return rc;
     if ((rc = upload(h, twiddles(2048, 1025), &tb.ptw2048))) return rc;

@@ -350,6 +350,250 @@ __global__ void __launch_bounds__(32 * WARPS, kF2WarpsPerSm / WARPS) k_frame2048
                                                                                  int total_frames, int frames_per_cta) {
     frame2048_body<WARPS>(y, g, tb, ws, total_frames, frames_per_cta);
 }
+// ============================================================================================ k_frame2048_w2 (r02-k)
+// The same frame pipeline on TWO warps per frame (a 64-thread CTA = one frame at a time): 16 instead of 32
+// register-resident points per thread (team64_fft, fft_reg.cuh: three register stages 16 x 16 x 4, the first exchange
+// across the CTA, the second inside groups of four lanes), 128 instead of 168 registers, 16 instead of 12 warps per SM.
+// Per frame the two warps execute what the one warp executed (the FFT has the same operation count; the second exchange
+// adds 64 shared-memory instructions per thread), every per-frame consumer is split between them:
+//   * real split: thread c = k1 + 16 q holds Z[c + 64 u]; its conjugate partner c' = (64 - c) % 64 is a lane of the
+//     same warp by construction of the thread map (t64_partner_lane), so the pairing is two shuffles as before;
+//   * moments / flatness: bins k = tid + 64 i, combined across the warps through 5 doubles of shared memory;
+//   * spectral contrast: warp 0 takes the 410-bin band (sort network of 13, eight extraction rounds), warp 1 the six
+//     others -- about the same instruction count;
+//   * mel-D: warp 0 rows 0-31 and 96-127, warp 1 rows 32-95 (narrowest + widest bands against the two middle groups).
+// Same formulas per bin as k_frame2048; the FFT factorisation differs, so |X| agrees to the last float32 bit or two
+// (the kernel passes the whole GPU parity suite as the default path).
+// MEASURED AND NOT THE DEFAULT (BPC_F2_W2=1 selects it; profiles/r02_k_frame2048_w2.txt): 2.62 ms against 2.39 ms for
+// the one-warp kernel.  The question it answers is whether k_frame2048 is bound by its three warps per scheduler: it
+// is not -- at 16 warps per SM the issue slots are as busy as at 12 (47.9 % against 48.2 %), while the two-warp form
+// executes 11 % more instructions (per-frame prologue, twiddle and table loads per warp instead of per frame, the second
+// exchange) and pushes the L1 data pipe from 50 % to 69 % of its wavefront peak (window, twiddle and split tables are
+// re-read from L1 for every frame by every thread: ~130 KB through a 128 B / clk pipe per frame, plus 32 KB for the second
+// exchange).  With 96 registers (20 warps per SM, 33 doubles spilled per frame) it runs at 2.84 ms.
+#ifndef BPC_F2W2_CTAS
+#define BPC_F2W2_CTAS 8
+#endif
+constexpr int kF2w2CtasPerSm = BPC_F2W2_CTAS;
+#ifdef BPC_F2W2_REGS
+__global__ void __maxnreg__(BPC_F2W2_REGS) k_frame2048_w2(
+#else
+__global__ void __launch_bounds__(64, kF2w2CtasPerSm) k_frame2048_w2(
+#endif
+    const float* __restrict__ y, Geometry g, Tables tb, Workspace ws, int total_frames, int frames_per_cta) {
+    __shared__ __align__(16) double xr_s[16 * kT64Pitch];      // exchange buffer, then the |X| row (1092 floats)
+    __shared__ double red[2][8];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int k1 = t64_k1(tid), q = tid & 3, c = k1 + 16 * q;
+    const int partner = t64_partner_lane(tid);
+    float* row = reinterpret_cast<float*>(xr_s);
+    const int T = g.T, L = g.L, hop = g.hop, TE = (T + 1) / 2;
+    const double2* win2 = reinterpret_cast<const double2*>(tb.hann2048h) + tid;   // 0.5 * Hann: the 1/2 of the real split
+    const double2* twa = tb.t64a + tid;
+    const double2* twb = tb.t64b + q;
+    const double2* rs = tb.rs2048 + c;                                    // split twiddles as (scale, tan / cot)
+    const int f_lo = blockIdx.x * frames_per_cta;
+    const int f_hi = f_lo + frames_per_cta < total_frames ? f_lo + frames_per_cta : total_frames;
+    for (int f = f_lo; f < f_hi; ++f) {
+        const int b = f / T, t = f - b * T;
+        const float* yb = y + (size_t)b * L;
+        const int g0 = t * hop - 1024;
+        {
+            double2 a[16];
+            if (g0 >= 0 && g0 + 2048 <= L) {                   // interior frame (55 of 63): no bounds checks, one base pointer
+                const float2* src = reinterpret_cast<const float2*>(yb + g0) + tid;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float2 v = __ldg(src + 64 * j);
+                    const double2 wv = __ldg(win2 + 64 * j);
+                    a[j] = make_double2((double)v.x * wv.x, (double)v.y * wv.y);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int gi = g0 + 2 * (tid + 64 * j);    // even; L is even, so the pair is in or out together
+                    float2 v = make_float2(0.f, 0.f);
+                    if (gi >= 0 && gi < L) v = __ldg(reinterpret_cast<const float2*>(yb + gi));
+                    const double2 wv = __ldg(win2 + 64 * j);
+                    a[j] = make_double2((double)v.x * wv.x, (double)v.y * wv.y);
+                }
+            }
+            team64_fft(a, twa, twb, xr_s, tid, k1, q);
+            __syncthreads();                                   // everyone has its exchange-2 values: the buffer becomes the row
+            // real split, every conjugate pair once (see k_frame2048): bin k = c + 64 u, u < 8, pairs with N - k, which
+            // the partner lane holds as its u' = 15 - u (c = 0: this thread's own (16 - u) % 16); k = 512 is c = 0, u = 8
+            const double z0re = a[0].x, z0im = a[0].y;         // c = 0: Z[0]
+            auto split_row = [&](auto exact_tag, float& xlo, float& xhi) {
+                constexpr bool EXACT = decltype(exact_tag)::value;
+#pragma unroll
+                for (int U = 0; U <= 8; ++U) {
+                    const double2 zk = a[t64_zidx(U)];
+                    double2 zn;
+                    if (U < 8) {
+                        const double2 src = a[t64_zidx(15 - U)];
+                        zn.x = __shfl_sync(0xffffffffu, src.x, partner);
+                        zn.y = __shfl_sync(0xffffffffu, src.y, partner);
+                        if (c == 0) zn = a[t64_zidx((16 - U) & 15)];
+                    } else {
+                        zn = zk;                                   // k = 512 pairs with itself
+                    }
+                    const double2 ct = __ldg(rs + 64 * U);
+                    const double sx = zk.x + zn.x, sy = zk.y - zn.y, dx = zk.x - zn.x, dy = zk.y + zn.y;
+                    double qx, qy;
+                    if (U < 4) { qx = fma(ct.y, dx, -dy); qy = fma(ct.y, dy, dx); }       // k < 256
+                    else       { qx = fma(-ct.y, dy, dx); qy = fma(ct.y, dx, dy); }
+                    const double x0 = fma(ct.x, qx, sx), y0 = fma(ct.x, qy, sy);
+                    const double x1 = fma(-ct.x, qx, sx), y1 = fma(ct.x, qy, -sy);
+                    const int k = c + 64 * U;
+                    float m0, m1, xa = 1.f, xb = 1.f;
+                    if (EXACT) {
+                        m0 = c64_abs_exact((float)x0, (float)y0);
+                        m1 = c64_abs_exact((float)x1, (float)y1);
+                    } else {
+                        m0 = c64_abs_f32_unchecked((float)x0, (float)y0, &xa);
+                        m1 = c64_abs_f32_unchecked((float)x1, (float)y1, &xb);
+                    }
+                    if (U < 8) {
+                        row[k] = m0;
+                        xlo = fminf(xlo, xa);
+                        xhi = fmaxf(xhi, xa);
+                        if (U > 0 || c > 0) {
+                            row[1024 - k] = m1;
+                            xlo = fminf(xlo, xb);
+                            xhi = fmaxf(xhi, xb);
+                        }
+                    } else if (c == 0) {
+                        row[512] = m0;
+                        xlo = fminf(xlo, xa);
+                        xhi = fmaxf(xhi, xa);
+                    }
+                }
+            };
+            float xlo = 1.f, xhi = 1.f;
+            split_row(std::false_type{}, xlo, xhi);
+            if (__any_sync(0xffffffffu, !(c64_abs_in_range(xlo) && c64_abs_in_range(xhi))))
+                split_row(std::true_type{}, xlo, xhi);            // each warp redoes its own bins (all-zero frames)
+            if (c == 0) row[1024] = fabsf((float)(2.0 * (z0re - z0im)));   // X[1024] = Re Z[0] - Im Z[0] (Z halved)
+            // words 1025 .. 1091 follow the row: the mel-D loop reads up to 51 words past a band's start with zero
+            // weights, and what the exchange left there may be a NaN pattern
+            row[1025 + tid] = 0.f;
+            if (tid < 3) row[1089 + tid] = 0.f;
+        }
+        __syncthreads();                                       // the row is complete
+        if ((t & 1) == 0) {                                    // hop-512 frame: keep the row for rolloff / tuning-36
+            float4* dst = reinterpret_cast<float4*>(ws.mag_even + ((size_t)b * TE + (t >> 1)) * kMag2048Stride);
+#pragma unroll
+            for (int r = 0; r < (kMag2048Stride / 4 + 63) / 64; ++r) {
+                const int i = tid + 64 * r;
+                if (i < kMag2048Stride / 4) {
+                    float4 v = reinterpret_cast<const float4*>(row)[i];
+                    if (i == kMag2048Stride / 4 - 1) { v.y = 0.f; v.z = 0.f; v.w = 0.f; }
+                    dst[i] = v;
+                }
+            }
+        }
+        // spectral_centroid / bandwidth / flatness (methods.py:59-62): bin k = tid + 64 i, the thread accumulates
+        // sum m, sum i m, sum i^2 m with compile-time weights and the product of its 16 (thread 0: 17) clamped powers
+        {
+            double sm = 0.0, s1 = 0.0, s2 = 0.0, spow = 0.0, prod = 1.0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float m = row[tid + 64 * i];
+                const double dm = (double)m;
+                sm += dm;
+                if (i > 0) { s1 = fma(dm, (double)i, s1); s2 = fma(dm, (double)(i * i), s2); }
+                const double p = (double)fmaxf(1e-10f, __fmul_rn(m, m));
+                spow += p;
+                prod *= p;
+            }
+            {
+                const float m = tid == 0 ? row[1024] : 0.f;     // the Nyquist bin (i = 16) exists for thread 0 only
+                const double dm = (double)m;
+                sm += dm;
+                s1 = fma(dm, 16.0, s1);
+                s2 = fma(dm, 256.0, s2);
+                if (tid == 0) {
+                    const double p = (double)fmaxf(1e-10f, __fmul_rn(m, m));
+                    spow += p;
+                    prod *= p;
+                }
+            }
+            double slog = log(prod);
+            const double dt = (double)tid;
+            const double smk = fma(64.0, s1, dt * sm);                                       // sum m k
+            const double smk2 = fma(4096.0, s2, fma(128.0 * dt, s1, dt * dt * sm));          // sum m k^2
+            const double smf = smk * 7.8125, smf2 = smk2 * (7.8125 * 7.8125);
+            sm = warp_sum(sm);
+            const double smf_w = warp_sum(smf), smf2_w = warp_sum(smf2);
+            slog = warp_sum(slog);
+            spow = warp_sum(spow);
+            if (lane == 0) {
+                red[w][0] = sm; red[w][1] = smf_w; red[w][2] = smf2_w; red[w][3] = slog; red[w][4] = spow;
+            }
+        }
+        double* ff = ws.frame_feat + (size_t)f * kFrameFeat;
+        // spectral_contrast order statistics (methods.py:63); band table: first bin, length, order count
+        //   {0,25,1} {25,26,1} {51,51,1} {102,102,2} {204,205,4} {409,410,8} {819,206,4}
+        if (w == 0) {
+            double va, pk;
+            warp_band_extremes<16, 13, 8>(row, 409, 410, lane, &va, &pk);
+            if (lane == 0) { ff[3 + 5] = pk; ff[10 + 5] = va; }
+        } else {
+            double va[7], pk[7];
+            warp_band_minmax(row, 0, 25, lane, &va[0], &pk[0]);
+            warp_band_minmax(row, 25, 26, lane, &va[1], &pk[1]);
+            warp_band_minmax(row, 51, 51, lane, &va[2], &pk[2]);
+            warp_band_extremes<4, 4, 2>(row, 102, 102, lane, &va[3], &pk[3]);
+            warp_band_extremes<8, 7, 4>(row, 204, 205, lane, &va[4], &pk[4]);
+            warp_band_extremes<8, 7, 4>(row, 819, 206, lane, &va[6], &pk[6]);
+            va[5] = 0.0; pk[5] = 0.0;
+            if (lane < 7 && lane != 5) {
+                double p = pk[0], v = va[0];
+#pragma unroll
+                for (int bnd = 1; bnd < 7; ++bnd) if (lane == bnd) { p = pk[bnd]; v = va[bnd]; }
+                ff[3 + lane] = p;
+                ff[10 + lane] = v;
+            }
+        }
+        // mel-D power column (n_fft 2048, 128 mels, fmax 8000): methods.py:90 and process.py:74.  Row groups of 32:
+        // warp 0 takes groups 0 and 3, warp 1 groups 1 and 2.
+        float* md = ws.melD + (size_t)f * kPlaneRows;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int m = lane + 32 * (i == 0 ? w : 3 - w);
+            const int s0 = __ldg(tb.mel_d.start + m), cnt = __ldg(tb.mel_d.count + m);
+            const int cmax = __reduce_max_sync(0xffffffffu, cnt);
+            const float* wp = tb.mel_d.wt + m;                   // [tap][mel], zero beyond a row's count and 4 zero taps
+            const float* rp = row + s0;                          // past the widest row (upload_bank)
+            float acc = 0.f;
+            for (int j = 0; j < cmax; j += 4) {                  // same taps, same order as one tap per iteration
+                const float w0 = __ldg(wp), w1 = __ldg(wp + kPlaneRows), w2 = __ldg(wp + 2 * kPlaneRows),
+                            w3 = __ldg(wp + 3 * kPlaneRows);
+                const float m0 = rp[0], m1 = rp[1], m2 = rp[2], m3 = rp[3];
+                acc = fmaf(w0, __fmul_rn(m0, m0), acc);
+                acc = fmaf(w1, __fmul_rn(m1, m1), acc);
+                acc = fmaf(w2, __fmul_rn(m2, m2), acc);
+                acc = fmaf(w3, __fmul_rn(m3, m3), acc);
+                wp += 4 * kPlaneRows;
+                rp += 4;
+            }
+            md[m] = acc;
+        }
+        __syncthreads();                                       // red[] is complete; the row is the next frame's exchange buffer
+        if (tid == 0) {
+            const double sm = red[0][0] + red[1][0], smf_w = red[0][1] + red[1][1], smf2_w = red[0][2] + red[1][2];
+            const double slog = red[0][3] + red[1][3], spow = red[0][4] + red[1][4];
+            const double len = sm < 1.17549435e-38 ? 1.0 : sm;     // util.normalize(norm=1): tiny(float32) guard
+            const double cc = smf_w / len;
+            ff[0] = cc;
+            ff[1] = sqrt(fmax(0.0, smf2_w / len - 2.0 * cc * (smf_w / len) + cc * cc * (sm / len)));
+            const float gmean = expf((float)(slog / 1025.0));
+            const float amean = (float)(spow / 1025.0);
+            ff[2] = (double)__fdiv_rn(gmean, amean);
+        }
+    }
+}
+
 // ================================================================================================= k_seg2048
 constexpr int kSegGroups = 3;                // tempogram frames in flight per CTA (96 threads x 4 lags each)
 constexpr int kSegThreads = 96 * kSegGroups; // 9 warps (v41: two groups; the kernel runs four CTAs per SM either way)
@@ -751,6 +995,7 @@ void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb,
         cudaFuncSetAttribute(k_frame2048<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * kF2RowBytes);
         cudaFuncSetAttribute(k_frame2048<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
         cudaFuncSetAttribute(k_frame2048<12>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        cudaFuncSetAttribute(k_frame2048_w2, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
         if (const char* e = getenv("BPC_F2_WARPS")) warps = atoi(e) == 12 ? 12 : 1;    // A/B switch
         int dev = 0;
         cudaGetDevice(&dev);
@@ -758,6 +1003,17 @@ void launch_spec2048(const float* y, int n, const Geometry& g, const Tables& tb,
     });
     const int total = n * g.T;
     if (total <= 0) return;
+    // r02-k: two warps per frame, measured slower (see k_frame2048_w2) and kept behind BPC_F2_W2=1 (read per launch so
+    // that a test can compare the two kernels in one process)
+    const char* w2e = std::getenv("BPC_F2_W2");
+    if (w2e && std::atoi(w2e) == 1) {
+        int grid2 = sms * kF2w2CtasPerSm;
+        const int per2 = (total + grid2 - 1) / grid2;
+        grid2 = (total + per2 - 1) / per2;
+        k_frame2048_w2<<<grid2, 64, 0, st>>>(y, g, tb, ws, total, per2);
+        note_launch();
+        return;
+    }
     // persistent: the 12 warps an SM holds at 168 registers, each CTA walking a contiguous range of frames
     int grid = warps == 1 ? sms * kF2WarpsPerSm : sms;
     int per = (total + grid - 1) / grid;

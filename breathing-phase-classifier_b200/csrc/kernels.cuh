@@ -38,13 +38,15 @@ struct Tables {
     const double* hann512;        // [512]
     const double* hann2048;       // [2048]
     const double* hann2048h;      // [2048] 0.5 * Hann (k_frame2048: the 1/2 of the real-input split folded into the window)
-    const double2* rs2048;        // [544] split twiddle w_k = -i exp(-2 pi i k / 2048) factored for FMA butterflies:
+    const double2* rs2048;        // [576] split twiddle w_k = -i exp(-2 pi i k / 2048) factored for FMA butterflies:
                                   //       (c, t) with w = c (t + i) for k < 256 and w = c (1 + i t) for k >= 256
     const double2* tw256;         // exp(-2 pi i j / 256), j < 256
     const double2* ptw512;        // exp(-2 pi i k / 512),  k <= 256
     const double2* ptw2048;       // exp(-2 pi i k / 2048), k <= 1024
     const double2* twa1024;       // [k1][h] = exp(-2 pi i h k1 / 1024), 32 x 32: inter-stage twiddles of team_fft<32>
     const double2* twa256;        // [k1][h] = exp(-2 pi i h k1 / 256), 16 x 16: the same for team_fft<16> (k_logmel_fused)
+    const double2* t64a;          // [k1][j] = exp(-2 pi i j k1 / 1024), 16 x 64: stage A -> B twiddles of team64_fft (k_frame2048_w2)
+    const double2* t64b;          // [k2][j0] = exp(-2 pi i j0 k2 / 64), 16 x 4: stage B -> C twiddles of team64_fft
     // filterbanks
     BankDev mel_a, mel_b, mel_c, mel_d;
     const float* dct_mel;         // [40, 128]

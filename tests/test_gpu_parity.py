@@ -234,6 +234,35 @@ def test_dataset_statistics(torch_cuda, fused, monkeypatch):
     eng.close()
 
 
+def test_frame2048_two_warp_kernel_matches_default(torch_cuda, monkeypatch):
+    """k_frame2048_w2 (BPC_F2_W2=1, read per launch: the STFT-2048 frame pipeline on two warps per frame with the
+    16 x 16 x 4 team64 FFT) against the default one-warp kernel on the same segments: integer outputs equal, every scalar
+    inside the parity gate, every plane within the plane gate (the kernel feeds centroid / bandwidth / flatness / contrast,
+    the mel-D flux and onset envelope -> tempogram, and through mag_even the rolloff and the 36-bin tuning of chroma_cens)."""
+    torch = torch_cuda
+    import bpc_b200
+    from bpc_b200.synth import synth_batch_pcm16
+    eng = bpc_b200.Engine(device=0, max_batch=32)
+    wav = torch.from_numpy(synth_batch_pcm16(0, 24)).cuda()
+    monkeypatch.delenv("BPC_F2_W2", raising=False)
+    f1, s1, st1 = [x.clone() for x in eng.precompute(wav)]
+    monkeypatch.setenv("BPC_F2_W2", "1")
+    f2, s2, st2 = [x.clone() for x in eng.precompute(wav)]
+    torch.cuda.synchronize()
+    assert torch.equal(st1, st2)
+    a, b = s1.double().cpu().numpy(), s2.double().cpu().numpy()
+    assert np.array_equal(a[:, 22], b[:, 22]) and np.array_equal(a[:, 35], b[:, 35])
+    excess = np.abs(a - b) - (1e-4 * np.abs(a) + 2e-6)
+    assert excess.max() <= 0.0, (np.unravel_index(excess.argmax(), excess.shape), excess.max())
+    d = (f1 - f2).abs().amax(dim=(0, 2, 3)).cpu().numpy()
+    assert d.max() < 2e-4, dict(zip(bpc_b200.CHANNELS, d.tolist()))
+    # planes that do not depend on the STFT-2048 frames are untouched
+    for c, name in enumerate(bpc_b200.CHANNELS):
+        if name not in ("tempogram", "chroma"):
+            assert d[c] == 0.0, (name, d[c])
+    eng.close()
+
+
 def test_padded_scalars_39(torch_cuda):
     torch = torch_cuda
     import bpc_b200
