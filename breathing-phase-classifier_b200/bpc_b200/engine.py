@@ -388,7 +388,7 @@ def table(name: str, tuning_idx: int = 50, params: L.Params | None = None) -> np
     p = params if params is not None else L.default_params()
     T = p.expected_len // p.hop + 1
     shapes = {"mel_a": ((128, 257), np.float32), "mel_b": ((128, 257), np.float32), "mel_c": ((64, 257), np.float32),
-              "mel_d": ((128, 1025), np.float32), "dct_mel": ((40, 128), np.float32), "dct_time": ((T, T), np.float32),
+              "mel_d": ((128, 1025), np.float32), "mel_d_band": ((128, 82), np.float32), "dct_mel": ((40, 128), np.float32), "dct_time": ((T, T), np.float32),
               "hann512": ((512,), np.float64), "hann2048": ((2048,), np.float64), "hann384": ((384,), np.float64),
               "hamming400": ((400,), np.float64), "chroma": ((12, 257), np.float32),
               "hist_edges": ((101,), np.float64), "halfband": ((127,), np.float64),

@@ -379,6 +379,57 @@ int upload_bank(bpc_handle* h, const SparseBank& b, BankDev* out) {
     return BPC_OK;
 }
 
+// Band starts moved down so that the 32 rows a warp reads together start in 32 different shared-memory banks.
+// k_frame2048 walks the band of mel row m = lane + 32 i as row[start[m] + j], j = 0, 1, ...: with the natural starts of
+// the n_fft 2048 bank 2-4 lanes of a group fall into the same bank at every tap (316 instead of 92 wavefronts per frame,
+// all 5.8e7 excess shared wavefronts of the kernel: profiles/r02_j_ncu_summary.txt).  Row m gets start - r and r leading
+// ZERO weights, r in [0, 32) chosen per group of 32 rows by a bipartite matching (rows x banks) that minimises the
+// longest padded band; fma(0, p, +0) = +0 for the finite p the row holds, so every sum is bit-identical.
+SparseBank deconflict_bank(const SparseBank& b, int group) {
+    SparseBank o = b;
+    std::vector<int> shift(b.rows, 0);
+    for (int g0 = 0; g0 < b.rows; g0 += group) {
+        const int n = std::min(group, b.rows - g0);
+        int cmax = 0;
+        for (int i = 0; i < n; ++i) cmax = std::max(cmax, b.count[g0 + i]);
+        for (int cap = cmax; cap <= cmax + 32; ++cap) {
+            std::vector<int> owner(32, -1);                                  // bank -> row of the group
+            auto ok = [&](int i, int bank) {
+                const int r = ((b.start[g0 + i] - bank) % 32 + 32) % 32;
+                return b.start[g0 + i] - r >= 0 && b.count[g0 + i] + r <= cap;
+            };
+            std::function<bool(int, std::vector<char>&)> augment = [&](int i, std::vector<char>& seen) {
+                for (int bank = 0; bank < 32; ++bank) {
+                    if (seen[bank] || !ok(i, bank)) continue;
+                    seen[bank] = 1;
+                    if (owner[bank] < 0 || augment(owner[bank], seen)) { owner[bank] = i; return true; }
+                }
+                return false;
+            };
+            int matched = 0;
+            for (int i = 0; i < n; ++i) {
+                std::vector<char> seen(32, 0);
+                matched += augment(i, seen) ? 1 : 0;
+            }
+            if (matched == n) {
+                for (int bank = 0; bank < 32; ++bank)
+                    if (owner[bank] >= 0) shift[g0 + owner[bank]] = ((b.start[g0 + owner[bank]] - bank) % 32 + 32) % 32;
+                break;
+            }
+        }
+    }
+    o.width = 0;
+    for (int r = 0; r < b.rows; ++r) {
+        o.start[r] = b.start[r] - shift[r];
+        o.count[r] = b.count[r] + shift[r];
+        o.width = std::max(o.width, o.count[r]);
+    }
+    o.w.assign((size_t)o.rows * std::max(1, o.width), 0.f);
+    for (int r = 0; r < b.rows; ++r)
+        for (int j = 0; j < b.count[r]; ++j) o.w[(size_t)r * o.width + shift[r] + j] = b.w[(size_t)r * b.width + j];
+    return o;
+}
+
 std::vector<double2> twiddles(int n, int count) {
     std::vector<double2> t(count);
     for (int j = 0; j < count; ++j) {
@@ -511,7 +562,13 @@ int build_tables(bpc_handle* h) {
     if ((rc = upload_bank(h, mel_bank(p.sr, 512, 128, 0.0, p.fmax), &tb.mel_a))) return rc;
     if ((rc = upload_bank(h, mel_bank(p.sr, 512, 128, 0.0, p.sr / 2.0), &tb.mel_b))) return rc;
     if ((rc = upload_bank(h, mel_bank(p.sr, 512, 64, 0.0, p.sr / 2.0), &tb.mel_c))) return rc;
-    if ((rc = upload_bank(h, mel_bank(p.sr, 2048, 128, 0.0, p.sr / 2.0), &tb.mel_d))) return rc;
+    {
+        // BPC_MELD_SHIFT=0: the natural band starts (A/B of the bank-conflict-free layout)
+        const char* e = std::getenv("BPC_MELD_SHIFT");
+        SparseBank md = mel_bank(p.sr, 2048, 128, 0.0, p.sr / 2.0);
+        if (!(e && std::atoi(e) == 0)) md = deconflict_bank(md, 32);
+        if ((rc = upload_bank(h, md, &tb.mel_d))) return rc;
+    }
     if ((rc = upload(h, dct2_ortho(40, 128), &tb.dct_mel))) return rc;
     {
         const int T = h->g.T;
@@ -1571,6 +1628,17 @@ int64_t bpc_table_copy(const bpc_params* p, const char* name, int tuning_idx, vo
     if (k == "mel_b") return put_f(mel_bank(p->sr, 512, 128, 0.0, p->sr / 2.0).dense);
     if (k == "mel_c") return put_f(mel_bank(p->sr, 512, 64, 0.0, p->sr / 2.0).dense);
     if (k == "mel_d") return put_f(mel_bank(p->sr, 2048, 128, 0.0, p->sr / 2.0).dense);
+    if (k == "mel_d_band") {                                   // the band form k_frame2048 reads: [128, 2 + 80] = start, count, weights
+        const SparseBank md = deconflict_bank(mel_bank(p->sr, 2048, 128, 0.0, p->sr / 2.0), 32);
+        if (md.width > 80) return BPC_ERR_UNSUPPORTED;
+        std::vector<float> v((size_t)md.rows * 82, 0.f);
+        for (int r = 0; r < md.rows; ++r) {
+            v[(size_t)r * 82] = (float)md.start[r];
+            v[(size_t)r * 82 + 1] = (float)md.count[r];
+            for (int j = 0; j < md.width; ++j) v[(size_t)r * 82 + 2 + j] = md.w[(size_t)r * md.width + j];
+        }
+        return put_f(v);
+    }
     if (k == "dct_mel") return put_f(dct2_ortho(40, 128));
     if (k == "dct_time") return put_f(dct2_ortho(T, T));
     if (k == "hann512") return put_d(hann_periodic(512));

@@ -170,6 +170,8 @@ int  bpc_set_debug(bpc_handle* h, int on);
  *   "mel_a" [128,257] "mel_b" [128,257] "mel_c" [64,257] "mel_d" [128,1025] "dct_mel" [40,128] "dct_time" [T,T]
  *   "hann512" [512] f64 "hann2048" [2048] f64 "chroma" [12,257] (tuning_idx) "cqt_basis" [36,257,2] (tuning_idx)
  *   "cqt_sqrt_len" [252] f64 (tuning_idx) "halfband" [ntaps] f64 "hist_edges" [101] f64
+ *   "mel_d_band" [128,82]: the band form of "mel_d" the STFT-2048 kernel walks (start, count, 80 weights per row; starts
+ *   moved down and padded with leading zero weights so that 32 consecutive rows start in 32 different shared-memory banks)
  * Writes float32 unless noted; returns the element count or a negative status. */
 int64_t bpc_table_copy(const bpc_params* p, const char* name, int tuning_idx, void* out, int64_t cap_elems);
 

@@ -67,6 +67,31 @@ def test_mel_tables_bit_exact(name, args):
     assert np.array_equal(bpc_b200.table(name), F.mel(sr=16000, n_fft=n_fft, n_mels=n_mels, fmax=fmax))
 
 
+def test_mel_d_band_is_the_dense_bank_and_bank_conflict_free():
+    """The band form of the n_fft 2048 mel bank that k_frame2048 walks (starts moved down by r < 32 with r leading zero
+    weights): every row reproduces the dense bank exactly, the 32 rows a warp reads together start in 32 different
+    shared-memory banks, the padded bands stay inside the |X| row and its zero tail (1092 words)."""
+    import bpc_b200
+    dense = bpc_b200.table("mel_d")
+    band = bpc_b200.table("mel_d_band")
+    start, count, w = band[:, 0].astype(int), band[:, 1].astype(int), band[:, 2:]
+    assert start.min() >= 0 and count.max() <= 80
+    for r in range(128):
+        row = np.zeros(1025 + 128, np.float32)
+        row[start[r]:start[r] + 80] = w[r]
+        assert np.array_equal(row[:1025], dense[r]) and not row[1025:].any()
+        assert not w[r, count[r]:].any()
+    for g in range(4):
+        sl = slice(32 * g, 32 * g + 32)
+        assert len(set((start[sl] % 32).tolist())) == 32
+        rounds = (count[sl].max() + 3) // 4 * 4                       # the kernel walks a group's bands in rounds of four
+        assert (start[sl] + rounds).max() <= 1092
+    nat = [int(np.flatnonzero(dense[r])[0]) for r in range(128)]
+    cnt = [int(np.flatnonzero(dense[r])[-1]) - nat[r] + 1 for r in range(128)]
+    # the padding costs at most two more rounds of four taps per frame than the natural layout (23)
+    assert sum((count[32 * g:32 * g + 32].max() + 3) // 4 for g in range(4)) <= 2 + sum((max(cnt[32 * g:32 * g + 32]) + 3) // 4 for g in range(4))
+
+
 def test_window_and_misc_tables():
     import scipy.fftpack
     import scipy.signal
