@@ -42,8 +42,17 @@ void upload_cens_constants(const double* taps127) {
 // decimator (thread i reads q = 4 i + c) on 32 distinct banks.
 constexpr int kZPad = 128;
 __device__ __forceinline__ int cens_dec_stride(const Workspace& ws) { return ws.dec_stride; }
+#ifdef BPC_DEC_PAD32
+// r01 layout: one pad word per 32 and scalar loads (thread i reads q = 4 i + c: 1.84 wavefronts per load on average over
+// the 67 offsets of a window -- every one of k_cens_dec's 2.7e7 excess shared wavefronts, profiles/r02_j_*)
 __device__ __forceinline__ int ppos(int q) { return (q + kZPad) + ((q + kZPad) >> 5); }
 __host__ __device__ constexpr int plen(int n) { return (n + 2 * kZPad) + ((n + 2 * kZPad) >> 5) + 1; }
+#else
+// r02-k layout: no pad words; a thread's window of 67 odd samples starts at a multiple of four, so it is read as 17
+// LDS.128 (the 32 lanes of a warp read 512 contiguous bytes: conflict-free) instead of 67 scalar loads
+__device__ __forceinline__ int ppos(int q) { return q + kZPad; }
+__host__ __device__ constexpr int plen(int n) { return (n + 2 * kZPad + 3) & ~3; }
+#endif
 
 // de-interleaved signals of octaves 1..6 (lengths 8000 .. 250 -> halves 4000 .. 125)
 constexpr int kHalf1 = 4000, kHalf2 = 2000, kHalf3 = 1000, kHalf4 = 500, kHalf5 = 250, kHalf6 = 125;
@@ -71,7 +80,10 @@ struct DecSmem {
     float a[2 * plen(8000)];                           // input (even | odd); later octaves 2..6
     float o1[2 * plen(kHalf1)];                        // octave 1
 };
-constexpr int kDecThreads = 192;                    // 2 CTAs x 6 warps: what 156 registers per thread allow (v46; was 128)
+#ifndef BPC_DEC_THREADS
+#define BPC_DEC_THREADS 256
+#endif
+constexpr int kDecThreads = BPC_DEC_THREADS;      // r01 (scalar window loads, 156-168 registers): 2 CTAs x 6 warps was what the registers allowed
 
 // One decimation stage: in (de-interleaved, half-length hin, i.e. 2 hin samples) -> out (de-interleaved, hin samples)
 // and to global memory in natural order.
@@ -81,17 +93,41 @@ __device__ __forceinline__ void decimate_stage(const float* __restrict__ inE, co
                                                float* __restrict__ outG, int tid) {
     const double inv_s = 1.0 / sqrt(0.5);
     for (int n0 = kOutPerThread * tid; n0 < hin; n0 += kOutPerThread * kDecThreads) {
+#ifdef BPC_DEC_PAD32
         double w[kWin];
 #pragma unroll
         for (int q = 0; q < kWin; ++q) w[q] = (double)inO[ppos(n0 - 32 + q)];   // zero pads cover q < 0 and q >= hin
+        float ev[kOutPerThread];
+#pragma unroll
+        for (int p = 0; p < kOutPerThread; ++p) ev[p] = inE[ppos(n0 + p)];
+#else
+        static_assert(kOutPerThread == 4 && kZPad % 4 == 0 && kWin <= 68, "LDS.128 windows");
+        double w[68];
+        const float4* o4 = reinterpret_cast<const float4*>(inO + ppos(n0 - 32));   // zero pads cover q < 0 and q >= hin
+#pragma unroll
+        for (int q4 = 0; q4 < 17; ++q4) {
+            const float4 t4 = o4[q4];
+            w[4 * q4] = (double)t4.x; w[4 * q4 + 1] = (double)t4.y; w[4 * q4 + 2] = (double)t4.z; w[4 * q4 + 3] = (double)t4.w;
+        }
+        const float4 e4 = *reinterpret_cast<const float4*>(inE + ppos(n0));
+        const float ev[kOutPerThread] = {e4.x, e4.y, e4.z, e4.w};
+#endif
         float v[kOutPerThread];
 #pragma unroll
         for (int p = 0; p < kOutPerThread; ++p) {
-            double acc = c_hb_centre * (double)inE[ppos(n0 + p)];
+            double acc = c_hb_centre * (double)ev[p];
 #pragma unroll
             for (int m = 0; m < 32; ++m) acc = fma(c_hb_odd[m], w[p + 31 - m] + w[p + 32 + m], acc);
             v[p] = (float)(acc * inv_s);
         }
+#ifndef BPC_DEC_PAD32
+        if (n0 + 3 < hin) {                                    // all four outputs exist: contiguous vector stores
+            *reinterpret_cast<float2*>(outE + ppos(n0 >> 1)) = make_float2(v[0], v[2]);
+            *reinterpret_cast<float2*>(outO + ppos(n0 >> 1)) = make_float2(v[1], v[3]);
+            *reinterpret_cast<float4*>(outG + n0) = make_float4(v[0], v[1], v[2], v[3]);
+            continue;
+        }
+#endif
         // hin is a multiple of 4 for every stage but the last (250 outputs): guard per pair
 #pragma unroll
         for (int p = 0; p < kOutPerThread; p += 2) {

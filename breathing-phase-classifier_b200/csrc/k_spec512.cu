@@ -259,7 +259,11 @@ __device__ void apply_bank(const BankDev& bank, const float* __restrict__ mag_b,
 __device__ void dct_mel40(const float* __restrict__ Dg, const float* P, int T, float* C) {
     const int kb = threadIdx.x >> 5, tp = threadIdx.x & 31;
     for (int tb0 = 0; tb0 < T; tb0 += 64) {                    // one pass per 64 columns (a single pass when T <= 64)
-        const int t0 = tb0 + 2 * tp, t1 = min(t0 + 1, T - 1);
+        // columns tp and tp + 32 of the pass: the lanes of a warp read consecutive words of a P row (the r01 pairing
+        // 2 tp, 2 tp + 1 was a two-way bank conflict on every load: half of this kernel's excess shared wavefronts)
+        const int t0 = tb0 + tp;
+        const bool has1 = t0 + 32 < T;
+        const int t1 = has1 ? t0 + 32 : T - 1;
         if (kb < 8 && t0 < T) {
             double acc[5][2];
 #pragma unroll
@@ -289,7 +293,7 @@ __device__ void dct_mel40(const float* __restrict__ Dg, const float* P, int T, f
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
                 C[(5 * kb + i) * T + t0] = (float)acc[i][0];
-                if (t0 + 1 < T) C[(5 * kb + i) * T + t0 + 1] = (float)acc[i][1];
+                if (has1) C[(5 * kb + i) * T + t1] = (float)acc[i][1];
             }
         }
     }
@@ -300,7 +304,9 @@ __device__ void dct_mel40(const float* __restrict__ Dg, const float* P, int T, f
 // shared memory.  Same 5 x 2 register tile; float32 partial sums over 16 t combined in float64.
 __device__ __forceinline__ void dct_time40_tile(const float* DTs, const float* C1, int T, float* C2, int ub0) {
     const int kb = threadIdx.x >> 5, up = threadIdx.x & 31;
-    const int u0 = ub0 + 2 * up, u1 = min(u0 + 1, T - 1);
+    const int u0 = ub0 + up;                                   // columns up and up + 32 of the tile (conflict-free rows of DTs)
+    const bool has1 = u0 + 32 < T;
+    const int u1 = has1 ? u0 + 32 : T - 1;
     if (kb < 8 && u0 < T) {
         double acc[5][2];
         float part[5][2];
@@ -327,7 +333,7 @@ __device__ __forceinline__ void dct_time40_tile(const float* DTs, const float* C
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
             C2[(5 * kb + i) * T + u0] = (float)(acc[i][0] + (double)part[i][0]);
-            if (u0 + 1 < T) C2[(5 * kb + i) * T + u0 + 1] = (float)(acc[i][1] + (double)part[i][1]);
+            if (has1) C2[(5 * kb + i) * T + u1] = (float)(acc[i][1] + (double)part[i][1]);
         }
     }
 }
