@@ -257,6 +257,28 @@ __device__ __forceinline__ void stage_segment_tma(float* dst, const float* src, 
     mbar_wait(bar, 0);
 }
 
+// Thread-strided copy loop over n float2 elements of a segment with BATCH loads in flight per thread before the first
+// use: sink(m, v) receives element m (elements >= n_valid read as zero).  The plain `for (m = tid; ...) dst[f(m)] = src[m]`
+// loops of the CTA-per-segment kernels compile to one LDG -> one STS per trip, i.e. one DRAM round trip per element and
+// thread (k_hilbert: 20 serialised round trips, 20 % of its stall samples; k_cens_dec: 19 %, profiles/r02_j_*).
+template <int BATCH, class Sink>
+__device__ __forceinline__ void load_f2_batched(const float2* __restrict__ src, int n, int n_valid, int tid, int nthreads,
+                                                Sink&& sink) {
+    for (int m0 = tid; m0 < n; m0 += BATCH * nthreads) {
+        float2 v[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const int m = m0 + u * nthreads;
+            v[u] = m < n_valid ? __ldg(src + m) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const int m = m0 + u * nthreads;
+            if (m < n) sink(m, v[u]);
+        }
+    }
+}
+
 // float atomic min/max via ordered-int trick (values must not be NaN)
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
     if (v >= 0.f) atomicMax((int*)addr, __float_as_int(v));

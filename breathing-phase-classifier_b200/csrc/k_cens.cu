@@ -154,12 +154,10 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_cens_dec(const float* __rest
     {
         float* E0 = S.a;
         float* O0 = S.a + plen(8000);
-        for (int m = tid; m < 8000; m += kDecThreads) {
-            float2 v = make_float2(0.f, 0.f);
-            if (2 * m < L) v = __ldg(y2 + m);
+        load_f2_batched<8>(y2, 8000, (L + 1) / 2, tid, kDecThreads, [&](int m, float2 v) {
             E0[ppos(m)] = v.x;
             O0[ppos(m)] = v.y;
-        }
+        });
     }
     __syncthreads();
     decimate_stage(S.a, S.a + plen(8000), 8000, S.o1, S.o1 + plen(kHalf1), G + goff(1) + kGPad, tid);
@@ -558,10 +556,20 @@ __global__ void __launch_bounds__(kLoThreads, 3) k_cens_lo(Geometry g, Tables tb
         const float* x = G + goff(kLoFirstOct + q) + kGPad;
         double* d = q == 0 ? S.d0 : (q == 1 ? S.d1 : S.d2);
         const int len = q == 0 ? kLoD0 : (q == 1 ? kLoD1 : kLoD2);
-        for (int i = tid; i < len; i += kLoThreads) {
-            const double a = i < n ? (double)__ldg(x + i) : 0.0;
-            const double c = (i >= 512 && i - 512 < n) ? (double)__ldg(x + i - 512) : 0.0;
-            d[i] = a - c;
+        // (loads of a batch of four trips first: the plain loop waited for one L2 round trip per element)
+        for (int i0 = tid; i0 < len; i0 += 4 * kLoThreads) {
+            float a[4], c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kLoThreads;
+                a[u] = (i < len && i < n) ? __ldg(x + i) : 0.f;
+                c[u] = (i < len && i >= 512 && i - 512 < n) ? __ldg(x + i - 512) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kLoThreads;
+                if (i < len) d[i] = (double)a[u] - (double)c[u];
+            }
         }
     }
     __syncthreads();                                            // d0 .. d2 and the barrier object are visible

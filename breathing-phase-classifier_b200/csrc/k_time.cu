@@ -425,10 +425,8 @@ __global__ void __launch_bounds__(kHilbertThreads, 2) k_hilbert(const float* __r
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x, L = g.L;                                        // L == 16000 (checked on the host)
     const float* yb = y + (size_t)b * L;
-    for (int m = tid; m < kHN; m += kHilbertThreads) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(yb) + m);
-        X[h20_pad(m)] = v;
-    }
+    load_f2_batched<(kHN + kHilbertThreads - 1) / kHilbertThreads>(reinterpret_cast<const float2*>(yb), kHN, kHN, tid,
+                                                                   kHilbertThreads, [&](int m, float2 v) { X[h20_pad(m)] = v; });
     __syncthreads();
     const float2* twa = tb.tw20a;                                             // [20][400]: exp(-2 pi i k pos / 8000)
     const float2* twb = tb.tw20b;                                             // [20][20]:  exp(-2 pi i k pos / 400)
