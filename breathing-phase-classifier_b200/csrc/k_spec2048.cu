@@ -643,16 +643,36 @@ __global__ void __launch_bounds__(kSegThreads) k_seg2048(Geometry g, Tables tb, 
     if (!LONG || phase == 1) {
     {   // stage per-frame features and mel-D
         const float4* src = reinterpret_cast<const float4*>(ws.melD + (size_t)b * T * kPlaneRows);
-        for (int i = tid; i < T * kPlaneRows / 4; i += NT) reinterpret_cast<float4*>(V.melD)[i] = __ldg(src + i);
+        // (four trips' loads in flight before the first store: the plain copy loops were one L2 round trip per trip)
+        const int n4 = T * kPlaneRows / 4;
+        for (int i0 = tid; i0 < n4; i0 += 4 * NT) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldg(src + min(i0 + u * NT, n4 - 1));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u * NT < n4) reinterpret_cast<float4*>(V.melD)[i0 + u * NT] = v[u];
+        }
         const double* ff = ws.frame_feat + (size_t)b * T * kFrameFeat;
-        for (int i = tid; i < T * 17; i += NT) {
-            const int t = i / 17, j = i - t * 17;
-            const double v = ff[t * kFrameFeat + j];
-            if (j == 0) V.cent[t] = v;
-            else if (j == 1) V.bw[t] = v;
-            else if (j == 2) V.flat[t] = v;
-            else if (j < 10) V.peak[(j - 3) * T + t] = v;
-            else V.valley[(j - 10) * T + t] = v;
+        for (int i0 = tid; i0 < T * 17; i0 += 4 * NT) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = min(i0 + u * NT, T * 17 - 1), t = i / 17;
+                v[u] = __ldg(ff + t * kFrameFeat + (i - t * 17));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * NT;
+                if (i < T * 17) {
+                    const int t = i / 17, j = i - t * 17;
+                    if (j == 0) V.cent[t] = v[u];
+                    else if (j == 1) V.bw[t] = v[u];
+                    else if (j == 2) V.flat[t] = v[u];
+                    else if (j < 10) V.peak[(j - 3) * T + t] = v[u];
+                    else V.valley[(j - 10) * T + t] = v[u];
+                }
+            }
         }
     }
     __syncthreads();

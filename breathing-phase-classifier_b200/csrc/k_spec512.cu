@@ -345,7 +345,16 @@ __device__ void dct_time40(const float* DTs, const float* C1, int T, float* C2) 
 
 // copy a constant matrix into shared memory (all threads; caller syncs)
 __device__ __forceinline__ void stage_matrix(float* dst, const float* __restrict__ src, int n) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+    // eight trips' loads in flight before the first store (the plain loop: one L2 round trip per trip, 14 trips)
+    const int nt = blockDim.x;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 8 * nt) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(src + min(i0 + u * nt, n - 1));
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (i0 + u * nt < n) dst[i0 + u * nt] = v[u];
+    }
 }
 
 // whole-array statistics of a shared-memory array
